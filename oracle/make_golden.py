@@ -1,0 +1,189 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (dev container only).
+
+TEST INFRASTRUCTURE ONLY.  Run:  python oracle/make_golden.py
+Imports /root/reference/model_v1 and model_window through oracle/refload.py, loads weights made by
+htrvt_oracle.init_state_dict (numpy RandomState => reproducible on any box) with
+load_state_dict(strict=True), runs the reference's own forward / CTCLoss / decode on seeded
+inputs and stores ONLY the outputs (+ the seeds / shapes needed to regenerate the inputs).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import htrvt_oracle as O  # noqa: E402
+import refload  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def images(seed, B, W):
+    return torch.from_numpy(np.random.RandomState(seed).rand(B, 1, 64, W).astype(np.float32))
+
+
+def labels(seed, B, C, lo, hi):
+    rs = np.random.RandomState(seed)
+    lens = rs.randint(lo, hi + 1, size=B).astype(np.int32)
+    tg = rs.randint(1, C, size=int(lens.sum())).astype(np.int32)
+    return torch.from_numpy(tg), torch.from_numpy(lens)
+
+
+def grad_digest(grads):
+    names = sorted(grads)
+    norms = np.array([float(grads[k].double().norm()) for k in names])
+    heads = np.stack([np.pad(grads[k].reshape(-1)[:8].numpy(), (0, max(0, 8 - grads[k].numel()))) for k in names])
+    return names, norms, heads
+
+
+def model_case(variant, tag, nb_cls, W, B, seed, cfg, train_seed=7, mask_ratio=0.4, span=8):
+    htr, _ = refload.load_variant("model_v1" if variant == "v1" else "model_window")
+    kw = dict(nb_cls=nb_cls, img_size=[64, W], patch_size=(4, 64), embed_dim=cfg["embed_dim"],
+              depth=cfg["depth"], num_heads=cfg["num_heads"], mlp_ratio=4,
+              norm_layer=__import__("functools").partial(torch.nn.LayerNorm, eps=1e-6))
+    if variant == "window":
+        kw["img_size"] = [W, 64]          # window ctor builds its dummy as [1,1,img_size[1],img_size[0]]
+    ref = htr.MaskedAutoencoderViT(**kw)
+    sd = O.init_state_dict(nb_cls, [64, W], seed=seed, embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+                           num_heads=cfg["num_heads"], variant=variant)
+    ref_keys = list(ref.state_dict().keys())
+    assert sorted(ref_keys) == sorted(sd.keys()), (set(ref_keys) ^ set(sd.keys()))
+    for k in ref_keys:
+        assert tuple(ref.state_dict()[k].shape) == tuple(sd[k].shape), k
+    ref.load_state_dict(sd, strict=True)
+    x = images(seed + 1, B, W)
+    out = {"keys": np.array(ref_keys)}
+    ref.eval()
+    with torch.no_grad():
+        out["logits_eval"] = ref(x).numpy()
+    if variant == "v1":
+        # train mode: span mask drawn from the CPU default generator inside the reference
+        ref.train()
+        tg, tl = labels(seed + 2, B, nb_cls, 4, 12)
+        torch.manual_seed(train_seed)
+        preds = ref(x, mask_ratio, span, use_masking=True)
+        lp = preds.float().permute(1, 0, 2).log_softmax(2)
+        crit = torch.nn.CTCLoss(reduction="none", zero_infinity=True)
+        in_len = torch.IntTensor([preds.size(1)] * B)
+        loss = crit(lp, tg, in_len, tl).mean()
+        loss.backward()
+        grads = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+        names, norms, heads = grad_digest(grads)
+        out.update(logits_train=preds.detach().numpy(), loss=np.float64(loss.item()),
+                   grad_names=np.array(names), grad_norms=norms, grad_heads=heads,
+                   bn1_running_mean=ref.state_dict()["patch_embed.bn1.running_mean"].numpy(),
+                   l3_running_var=ref.state_dict()["patch_embed.layer3.1.bn2.running_var"].numpy(),
+                   nbt=np.int64(ref.state_dict()["patch_embed.bn1.num_batches_tracked"].item()))
+        torch.manual_seed(train_seed)
+        out["mask"] = O.draw_span_mask(W // 4, mask_ratio, span).numpy()
+    out["meta"] = np.array([nb_cls, W, B, seed, cfg["embed_dim"], cfg["depth"], cfg["num_heads"], train_seed])
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print("wrote", tag, {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
+def ctc_cases():
+    """torch.nn.CTCLoss (the reference's criterion, model_v1/train.py:95) on CPU."""
+    specs = [  # name, B, T, C, (Lmin, Lmax), special
+        ("basic", 4, 32, 12, (3, 10), None),
+        ("iam_shape", 6, 128, 80, (16, 64), None),
+        ("repeats", 4, 24, 5, (6, 11), "repeats"),
+        ("infeasible", 4, 10, 6, (2, 9), "infeasible"),
+        ("empty_target", 3, 12, 7, (0, 3), "empty"),
+        ("single_state", 2, 1, 4, (1, 1), None),
+        ("long_labels", 3, 256, 90, (150, 200), None),
+        ("ragged_T", 4, 40, 10, (3, 9), "ragged"),
+    ]
+    out = {}
+    for name, B, T, C, (lo, hi), special in specs:
+        rs = np.random.RandomState(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
+        logits = (rs.randn(B, T, C) * 2.0).astype(np.float32)
+        lens = rs.randint(lo, hi + 1, size=B).astype(np.int32)
+        if special == "empty":
+            lens[0] = 0
+        if special == "infeasible":
+            lens[1] = 9          # needs >= 9 frames (+repeats) out of 10: likely infeasible with repeats
+        tg = rs.randint(1, C, size=int(lens.sum())).astype(np.int32)
+        if special in ("repeats", "infeasible"):
+            tg[1::2] = tg[0::2][: len(tg[1::2])]       # force adjacent repeated labels
+        in_len = np.full(B, T, dtype=np.int32)
+        if special == "ragged":
+            in_len = rs.randint(20, T + 1, size=B).astype(np.int32)
+        lg = torch.from_numpy(logits).requires_grad_(True)
+        lp = lg.permute(1, 0, 2).log_softmax(2)
+        nll = torch.nn.CTCLoss(reduction="none", zero_infinity=True)(
+            lp, torch.from_numpy(tg), torch.from_numpy(in_len), torch.from_numpy(lens))
+        nll.sum().backward()
+        out[name + ".logits"] = logits
+        out[name + ".targets"] = tg
+        out[name + ".in_len"] = in_len
+        out[name + ".tgt_len"] = lens
+        out[name + ".nll"] = nll.detach().numpy()
+        out[name + ".grad"] = lg.grad.numpy()
+        print("ctc", name, nll.detach().numpy()[:4])
+    out["names"] = np.array([s[0] for s in specs])
+    np.savez_compressed(os.path.join(OUT, "ctc_cases.npz"), **out)
+
+
+def decode_cases():
+    """CTCLabelConverter.decode (model_v1/utils/utils.py:72-86) on adversarial index streams."""
+    _, utl = refload.load_variant("model_v1")
+    alphabet = "abcdefghijklmnopqrstuvwxyz0123456789 .,'-"
+    conv = utl.CTCLabelConverter(alphabet)
+    rs = np.random.RandomState(5)
+    T = 24
+    rows = [
+        np.zeros(T, dtype=np.int64),                                   # all blank
+        np.full(T, 3, dtype=np.int64),                                 # one long repeat
+        np.tile([1, 0, 1, 1, 0, 0, 2, 2], 3),                          # repeats across blanks
+        np.tile([5, 60, 5, 5, 60, 60, 7, 0], 3),                       # ids >= len(character) dropped, still "previous"
+        rs.randint(0, len(alphabet) + 1, size=T),
+        rs.randint(0, 6, size=T),
+        np.arange(T) % (len(alphabet) + 6),
+        np.array([41] * 3 + [42] * 3 + [43] * 3 + [0] * 3 + [41, 42] * 6),
+    ]
+    idx = np.concatenate(rows).astype(np.int64)
+    lens = np.full(len(rows), T, dtype=np.int32)
+    strs = conv.decode(torch.from_numpy(idx), torch.from_numpy(lens))
+    # ragged lengths too
+    lens2 = np.array([5, 24, 1, 30, 24, 12, 48, 24, 24], dtype=np.int32)
+    assert lens2.sum() == idx.size
+    strs2 = conv.decode(torch.from_numpy(idx), torch.from_numpy(lens2))
+    # READ2016 special case: 87-char alphabet gets '[' -> 88, ']' -> 89 (utils.py:61-62)
+    conv87 = utl.CTCLabelConverter("".join(chr(48 + i) for i in range(87)))
+    enc87 = conv87.encode(["0a", "[x]"])
+    np.savez_compressed(os.path.join(OUT, "decode_cases.npz"), alphabet=np.array(alphabet), index=idx,
+                        lens=lens, strings=np.array(strs), lens2=lens2, strings2=np.array(strs2),
+                        enc87_text=enc87[0].cpu().numpy(), enc87_len=enc87[1].cpu().numpy(),
+                        n_character87=np.int64(len(conv87.character)))
+    print("decode", strs, strs2)
+
+
+def argmax_cases():
+    """torch.max(2) index semantics (model_v1/valid.py:40): ties and NaNs."""
+    a = np.random.RandomState(9).randn(3, 6, 7).astype(np.float32)
+    a[0, 0, 2] = a[0, 0, 5] = 9.0
+    a[0, 1, :] = 1.0
+    a[1, 2, 4] = np.nan
+    a[1, 3, 1] = np.nan
+    a[1, 3, 6] = np.nan
+    a[2, 0, 3] = np.inf
+    a[2, 1, :] = -np.inf
+    _, idx = torch.from_numpy(a).max(2)
+    np.savez_compressed(os.path.join(OUT, "argmax_cases.npz"), logits=a, index=idx.numpy())
+    print("argmax", idx.numpy().tolist())
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    small = dict(embed_dim=64, depth=2, num_heads=2)
+    full = dict(embed_dim=768, depth=4, num_heads=6)
+    model_case("v1", "v1_small", 20, 128, 3, 11, small)
+    model_case("v1", "v1_full", 80, 512, 2, 123, full)
+    model_case("window", "win_small", 20, 128, 3, 21, dict(embed_dim=64, depth=4, num_heads=2))
+    model_case("window", "win_full", 90, 1024, 1, 321, full)
+    ctc_cases()
+    decode_cases()
+    argmax_cases()

@@ -1,0 +1,100 @@
+"""Pin the CPU oracle (oracle/htrvt_oracle.py) to fixtures generated from the unmodified reference
+(oracle/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import htrvt_oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _images(seed, B, W):
+    return torch.from_numpy(np.random.RandomState(seed).rand(B, 1, 64, W).astype(np.float32))
+
+
+def _labels(seed, B, C, lo, hi):
+    rs = np.random.RandomState(seed)
+    lens = rs.randint(lo, hi + 1, size=B).astype(np.int32)
+    tg = rs.randint(1, C, size=int(lens.sum())).astype(np.int32)
+    return torch.from_numpy(tg), torch.from_numpy(lens)
+
+
+@pytest.mark.parametrize("tag,variant", [("v1_small", "v1"), ("v1_full", "v1"),
+                                         ("win_small", "window"), ("win_full", "window")])
+def test_forward_eval_matches_reference(tag, variant):
+    g = np.load(os.path.join(G, tag + ".npz"))
+    nb_cls, W, B, seed, D, depth, heads, _ = [int(v) for v in g["meta"]]
+    sd = O.init_state_dict(nb_cls, [64, W], seed=seed, embed_dim=D, depth=depth, num_heads=heads, variant=variant)
+    assert sorted(sd.keys()) == sorted(g["keys"].tolist())
+    with torch.no_grad():
+        y = O.forward(sd, _images(seed + 1, B, W), training=False, num_heads=heads, variant=variant)
+    np.testing.assert_allclose(y.numpy(), g["logits_eval"], rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize("tag", ["v1_small", "v1_full"])
+def test_train_step_matches_reference(tag):
+    g = np.load(os.path.join(G, tag + ".npz"))
+    nb_cls, W, B, seed, D, depth, heads, train_seed = [int(v) for v in g["meta"]]
+    sd = O.init_state_dict(nb_cls, [64, W], seed=seed, embed_dim=D, depth=depth, num_heads=heads)
+    torch.manual_seed(train_seed)
+    mask = O.draw_span_mask(W // 4, 0.4, 8)
+    np.testing.assert_array_equal(mask.numpy(), g["mask"])
+    tg, tl = _labels(seed + 2, B, nb_cls, 4, 12)
+    loss, grads, logits = O.train_step(sd, _images(seed + 1, B, W), tg, tl, mask, num_heads=heads)
+    np.testing.assert_allclose(logits.numpy(), g["logits_train"], rtol=0, atol=3e-4)
+    assert abs(loss - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    names = sorted(grads)
+    assert names == g["grad_names"].tolist()
+    norms = np.array([float(grads[k].double().norm()) for k in names])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(sd["patch_embed.bn1.running_mean"].numpy(), g["bn1_running_mean"], atol=1e-6)
+    np.testing.assert_allclose(sd["patch_embed.layer3.1.bn2.running_var"].numpy(), g["l3_running_var"], rtol=1e-4)
+    assert int(sd["patch_embed.bn1.num_batches_tracked"]) == int(g["nbt"]) == 1
+
+
+def test_ctc_f64_restatement_matches_torch_ctcloss():
+    g = np.load(os.path.join(G, "ctc_cases.npz"))
+    for name in g["names"].tolist():
+        if name in ("iam_shape", "long_labels"):       # pure-python loops: keep the CPU suite fast
+            sl = slice(0, 1)
+        else:
+            sl = slice(None)
+        logits, tg = g[name + ".logits"], g[name + ".targets"]
+        il, tl = g[name + ".in_len"], g[name + ".tgt_len"]
+        B = logits[sl].shape[0]
+        nll, grad = O.ctc_loss_grad(logits[:B], tg[: int(tl[:B].sum())], il[:B], tl[:B])
+        np.testing.assert_allclose(nll, g[name + ".nll"][:B], rtol=1e-5, atol=1e-5, err_msg=name)
+        np.testing.assert_allclose(grad, g[name + ".grad"][:B], rtol=1e-4, atol=1e-4, err_msg=name)  # torch CPU is fp32
+
+
+def test_decode_restatement_matches_reference_converter():
+    g = np.load(os.path.join(G, "decode_cases.npz"))
+    alphabet = str(g["alphabet"])
+    assert O.decode_strings(g["index"], g["lens"], alphabet) == g["strings"].tolist()
+    assert O.decode_strings(g["index"], g["lens2"], alphabet) == g["strings2"].tolist()
+
+
+def test_argmax_semantics_match_torch_max():
+    g = np.load(os.path.join(G, "argmax_cases.npz"))
+    np.testing.assert_array_equal(O.argmax_first(g["logits"]), g["index"])
+
+
+def test_live_reference_when_present():
+    """If the reference tree is mounted (dev container), compare against it live on a fresh seed."""
+    import refload
+    if not refload.available():
+        pytest.skip("reference tree not mounted")
+    htr, utl = refload.load_variant("model_v1")
+    sd = O.init_state_dict(80, [64, 512], seed=77)
+    ref = htr.create_model(80, [64, 512])
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    x = _images(78, 1, 512)
+    with torch.no_grad():
+        a = ref(x)
+        b = O.forward(sd, x)
+    np.testing.assert_allclose(a.numpy(), b.numpy(), atol=2e-4)
+    assert list(ref.state_dict().keys()) == list(O.reorder_like(sd, ref.state_dict().keys()).keys())
