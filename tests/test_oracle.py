@@ -67,7 +67,7 @@ def test_ctc_f64_restatement_matches_torch_ctcloss():
         B = logits[sl].shape[0]
         nll, grad = O.ctc_loss_grad(logits[:B], tg[: int(tl[:B].sum())], il[:B], tl[:B])
         np.testing.assert_allclose(nll, g[name + ".nll"][:B], rtol=1e-5, atol=1e-5, err_msg=name)
-        np.testing.assert_allclose(grad, g[name + ".grad"][:B], rtol=1e-4, atol=1e-4, err_msg=name)  # torch CPU is fp32
+        np.testing.assert_allclose(grad, g[name + ".grad"][:B], rtol=1e-3, atol=1e-4, err_msg=name)  # torch CPU golden is fp32 (nll~1e3 => ~3e-4 rel)
 
 
 def test_decode_restatement_matches_reference_converter():
