@@ -1,0 +1,62 @@
+"""ctypes loader for the C-ABI CUDA library (include/htrvt.h).
+
+There is NO CPU fallback: if libhtrvt_b200.so is missing or a call returns a negative status the
+caller gets an exception.  Build with `python htr-vt_b200/build.py` (or __graft_entry__.build()).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhtrvt_b200.so")
+_lib = None
+
+ERRORS = {-1: "bad shape", -2: "bad alignment", -3: "wrong architecture (sm_100a only)",
+          -4: "kernel launch failed", -5: "workspace missing or too small", -6: "CUDA driver entry point failed"}
+
+
+class HtrvtError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HtrvtError(
+                "htr-vt_b200: %s not found. The CUDA extension is mandatory (no CPU fallback); build it with "
+                "`python htr-vt_b200/build.py`." % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise HtrvtError("%s failed: %s (status %d)" % (what, ERRORS.get(status, "unknown"), status))
+
+
+_P, _I, _L, _F, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
+
+SIGNATURES = {
+    # name: (restype, argtypes)
+    "htrvt_version": (_I, []),
+    "htrvt_ctc_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "htrvt_ctc_loss_grad": (_I, [_P, _L, _L, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _L, _L, _P, _F, _P, _Z, _P]),
+    "htrvt_greedy_decode": (_I, [_P, _L, _L, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
+    "htrvt_ctc_collapse": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "htrvt_gemm_tn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P, _L, _P, _F, _I, _I, _I, _I, _P]),
+    "htrvt_gemm_nn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _F, _P]),
+    "htrvt_wgrad_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "htrvt_linear_wgrad": (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _Z, _P]),
+    "htrvt_conv_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "htrvt_conv_fwd_stats_rows": (_I, [_I, _I, _I, _I, _I, _I]),
+    "htrvt_conv_dgrad": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P]),
+    "htrvt_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _Z, _P]),
+}
+
+
+def _declare(l: ctypes.CDLL) -> None:
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(l, name)          # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args

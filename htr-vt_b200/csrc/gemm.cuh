@@ -1,0 +1,47 @@
+// Parameters of the sm_100a "tap GEMM" (gemm.cu): one persistent, warp-specialised tcgen05 kernel
+// that serves every dense contraction of the encoder: linear fwd/dgrad/wgrad and the 3x3 / 1x1
+// stem convolutions (implicit GEMM over shifted TMA windows of the NHWC activation) fwd/dgrad/wgrad.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace htrvt {
+
+struct TapTab {
+  int8_t dh[9], dw[9], pw[9], widx[9];
+};
+
+enum : int {
+  EPI_BF16 = 1 << 0,       // store bf16 (else fp32)
+  EPI_BIAS = 1 << 1,       // + bias[n]
+  EPI_GELU = 1 << 2,       // out2 = pre-activation (bf16), out = gelu(pre) (bf16)
+  EPI_RESID = 1 << 3,      // + resid_f32[row, n] (fp32, same addressing as out)
+  EPI_ACCUM = 1 << 4,      // out += (read-modify-write, same dtype as out)
+  EPI_STATS = 1 << 5,      // per-tile column sum / sum of squares -> stats[tile_m][2][N]
+  EPI_QKV = 1 << 6,        // scatter columns to [3][B][H][T][hd]
+  EPI_RELU = 1 << 7,       // max(x, 0)
+};
+
+struct GemmP {
+  int kind;                // 0: rows = output pixels, K = taps x channels; 1: wgrad (K = pixels)
+  int Wo, Ho, NB;          // output pixel grid (kind 0) / dY pixel grid (kind 1)
+  int tiles_per_row;       // kind 0: ceil(Wo / 128)
+  int tiles_m, tiles_n, n_taps, splits;
+  int k_chunks;            // kind 0: 64-channel chunks per tap; kind 1: 64-pixel chunks per row
+  int a_sh;                // input-row multiplier (vertical stride) for the shifted operand
+  int b_tap_stride;        // kind 0: K (K-major B) or N (MN-major B) elements per tap in the weight matrix
+  TapTab tap;
+  int M_valid, N_valid;    // kind 1: rows (Cout) valid; columns valid
+  int flags;
+  // epilogue addressing (elements)
+  long long o_sn, o_sh, o_sw, o_base, o_split, o_tap;
+  void* out;
+  void* out2;
+  const float* bias;
+  const float* resid;
+  float* stats;
+  int qkv_T, qkv_H, qkv_hd;
+  float alpha;             // scale applied to the accumulator
+};
+
+}  // namespace htrvt

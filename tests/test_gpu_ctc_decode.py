@@ -1,0 +1,123 @@
+"""GPU parity: CTC loss/grad and greedy decode kernels (through the C ABI) vs the oracle / goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import htrvt_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _pkg():
+    import htrvt_b200
+    return htrvt_b200
+
+
+def _ctc_ref64(logits, tg, il, tl):
+    """float64 torch CPU CTC (same recursion as the float64 numpy oracle it is pinned to in test_oracle)."""
+    lg = torch.from_numpy(logits).double().requires_grad_(True)
+    lp = lg.permute(1, 0, 2).log_softmax(2)
+    nll = torch.nn.functional.ctc_loss(lp, torch.from_numpy(tg).long(), torch.from_numpy(il).long(),
+                                       torch.from_numpy(tl).long(), blank=0, reduction="none", zero_infinity=True)
+    nll.sum().backward()
+    return nll.detach().numpy(), lg.grad.numpy()
+
+
+def test_ctc_golden_cases_fused_logits():
+    h = _pkg()
+    g = np.load(os.path.join(G, "ctc_cases.npz"))
+    for name in g["names"].tolist():
+        logits, tg, il, tl = g[name + ".logits"], g[name + ".targets"], g[name + ".in_len"], g[name + ".tgt_len"]
+        x = torch.from_numpy(logits).cuda().requires_grad_(True)
+        nll = h.ctc_loss_from_logits(x, torch.from_numpy(tg).cuda(), torch.from_numpy(tl).cuda(),
+                                     input_lengths=torch.from_numpy(il).cuda())
+        nll.sum().backward()
+        ref_nll, ref_grad = _ctc_ref64(logits, tg, il, tl)
+        # tolerance stated by north_star: 1e-4 relative (fp32)
+        np.testing.assert_allclose(nll.detach().cpu().numpy(), ref_nll, rtol=1e-4, atol=1e-4, err_msg=name)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), ref_grad, rtol=1e-4, atol=1e-5, err_msg=name)
+        # and against the reference's own fp32 numbers (golden), whose rounding error is ~3e-4 at nll~1e3
+        np.testing.assert_allclose(nll.detach().cpu().numpy(), g[name + ".nll"], rtol=1e-4, atol=1e-3, err_msg=name)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), g[name + ".grad"], rtol=1e-3, atol=1e-4, err_msg=name)
+
+
+def test_ctc_module_reference_call_signature():
+    """criterion(log_probs[T,B,C], targets, preds_size (CPU!), length) exactly as valid.py:33-38 / train.py:24-28."""
+    h = _pkg()
+    g = np.load(os.path.join(G, "ctc_cases.npz"))
+    name = "iam_shape"
+    logits, tg, tl = g[name + ".logits"], g[name + ".targets"], g[name + ".tgt_len"]
+    B, T, C = logits.shape
+    preds = torch.from_numpy(logits).cuda().requires_grad_(True)
+    lp = preds.float().permute(1, 0, 2).log_softmax(2)
+    crit = h.CTCLoss(reduction="none", zero_infinity=True).to("cuda")
+    preds_size = torch.IntTensor([T] * B)                       # CPU tensor, as in valid.py
+    loss = crit(lp, torch.from_numpy(tg).cuda(), preds_size, torch.from_numpy(tl).cuda()).mean()
+    loss.backward()
+    assert abs(loss.item() - g[name + ".nll"].mean()) <= 1e-4 * abs(g[name + ".nll"].mean())
+    np.testing.assert_allclose(preds.grad.cpu().numpy() * B, g[name + ".grad"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,T,C,lo,hi", [(128, 128, 80, 16, 64), (32, 256, 90, 64, 200), (16, 128, 228, 1, 64)])
+def test_ctc_full_size_properties(B, T, C, lo, hi):
+    """Full BASELINE sizes: compare a subset against the float64 reference, and check size-independent
+    properties on everything (rows of softmax - posterior sum to 0; nll finite and > 0)."""
+    h = _pkg()
+    rs = np.random.RandomState(B + T)
+    logits = rs.randn(B, T, C).astype(np.float32)
+    tl = rs.randint(lo, hi + 1, size=B).astype(np.int32)
+    tg = rs.randint(1, C, size=int(tl.sum())).astype(np.int32)
+    il = np.full(B, T, dtype=np.int32)
+    x = torch.from_numpy(logits).cuda().requires_grad_(True)
+    nll = h.ctc_loss_from_logits(x, torch.from_numpy(tg).cuda(), torch.from_numpy(tl), max_target_len=int(tl.max()))
+    nll.sum().backward()
+    gr = x.grad.cpu().numpy()
+    assert np.isfinite(gr).all() and (nll > 0).all()
+    assert np.abs(gr.sum(axis=2)).max() < 2e-4
+    n = 8
+    ref_nll, ref_grad = _ctc_ref64(logits[:n], tg[: int(tl[:n].sum())], il[:n], tl[:n])
+    np.testing.assert_allclose(nll.detach().cpu().numpy()[:n], ref_nll, rtol=1e-4)
+    np.testing.assert_allclose(gr[:n], ref_grad, rtol=1e-4, atol=1e-5)
+    # worst-case provisioning path (no host knowledge of the label lengths): same numbers
+    x2 = torch.from_numpy(logits).cuda().requires_grad_(True)
+    nll2 = h.ctc_loss_from_logits(x2, torch.from_numpy(tg).cuda(), torch.from_numpy(tl).cuda())
+    nll2.sum().backward()
+    np.testing.assert_allclose(nll2.detach().cpu().numpy(), nll.detach().cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(x2.grad.cpu().numpy(), gr, rtol=1e-5, atol=1e-7)
+
+
+def test_decode_golden_strings():
+    h = _pkg()
+    g = np.load(os.path.join(G, "decode_cases.npz"))
+    conv = h.CTCLabelConverter(str(g["alphabet"]))
+    idx = torch.from_numpy(g["index"]).cuda()
+    assert conv.decode(idx, torch.from_numpy(g["lens"])) == g["strings"].tolist()
+    assert conv.decode(idx, torch.from_numpy(g["lens2"])) == g["strings2"].tolist()
+    c87 = h.CTCLabelConverter("".join(chr(48 + i) for i in range(87)))
+    t, l = c87.encode(["0a", "[x]"])
+    assert t.cpu().tolist() == g["enc87_text"].tolist() and l.cpu().tolist() == g["enc87_len"].tolist()
+    assert len(c87.character) == int(g["n_character87"])
+
+
+def test_argmax_semantics_and_fused_decode():
+    h = _pkg()
+    from importlib import import_module
+    ops = import_module("htr-vt_b200.ops")
+    g = np.load(os.path.join(G, "argmax_cases.npz"))
+    ids, lens, raw = ops.greedy_decode_ids(torch.from_numpy(g["logits"]).cuda(), 1000, want_raw=True)
+    np.testing.assert_array_equal(raw.cpu().numpy(), g["index"])
+    # fused decode == oracle collapse of oracle argmax, full size, bit exact
+    rs = np.random.RandomState(3)
+    B, T, C = 512, 128, 80
+    logits = rs.randn(B, T, C).astype(np.float32)
+    logits[:, :, 0] += 1.5                         # plenty of blanks and repeats
+    logits = np.round(logits * 2) / 2              # many exact ties
+    am = O.argmax_first(logits)
+    want = O.greedy_ids(am.reshape(-1), [T] * B, 60)
+    ids, lens = h.greedy_decode(torch.from_numpy(logits).cuda(), 60)
+    ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
+    got = [ids[b, : lens[b]].tolist() for b in range(B)]
+    assert got == want

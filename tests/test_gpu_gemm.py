@@ -1,0 +1,146 @@
+"""GPU parity: the tcgen05 tap-GEMM (linear fwd/dgrad/wgrad, conv fwd/dgrad/wgrad) through the C ABI
+against fp32 torch references computed from the same bf16 operands."""
+from importlib import import_module
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def ops():
+    import htrvt_b200  # noqa: F401
+    return import_module("htr-vt_b200.ops")
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (16384, 2304, 768), (16384, 768, 3072), (1000, 80, 768),
+                                   (16384, 3072, 768), (384, 192, 192)])
+def test_gemm_tn_bias(M, N, K):
+    o = ops()
+    torch.manual_seed(0)
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda")
+    ref = x.float() @ w.float().t() + b
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    o.gemm_tn(x, w, out, bias=b)
+    assert _rel(out, ref) < 1e-2
+    out32 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    o.gemm_tn(x, w, out32, bias=b)
+    assert _rel(out32, ref) < 1e-4
+
+
+def test_gemm_tn_gelu_resid_qkv():
+    o = ops()
+    torch.manual_seed(1)
+    M, N, K = 1024, 3072, 768
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda") * 0.1
+    pre = x.float() @ w.float().t() + b
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    o.gemm_tn(x, w, out, bias=b, out2=out2)
+    assert _rel(out2, pre) < 1e-2
+    assert _rel(out, F.gelu(pre)) < 1e-2
+    # residual fp32
+    w2 = (torch.randn(768, N, device="cuda") / N ** 0.5).bfloat16()
+    res = torch.randn(M, 768, device="cuda")
+    y = torch.empty(M, 768, device="cuda")
+    a = out
+    o.gemm_tn(a, w2, y, bias=b[:768].contiguous(), resid=res)
+    assert _rel(y, a.float() @ w2.float().t() + b[:768] + res) < 1e-4
+    # qkv scatter: [3][B][H][T][hd]
+    B, T, H, hd = 8, 128, 6, 128
+    wq = (torch.randn(3 * H * hd, K, device="cuda") / K ** 0.5).bfloat16()
+    bq = torch.randn(3 * H * hd, device="cuda") * 0.1
+    qkv = torch.empty(3, B, H, T, hd, device="cuda", dtype=torch.bfloat16)
+    o.gemm_tn(x, wq, qkv, bias=bq, qkv=(B, T, H, hd))
+    ref = (x.float() @ wq.float().t() + bq).reshape(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    assert _rel(qkv, ref) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(16384, 768, 2304), (1024, 768, 80), (16384, 3072, 768), (300, 192, 384)])
+def test_gemm_nn_dgrad(M, N, K):
+    o = ops()
+    torch.manual_seed(2)
+    Kp = (K + 7) // 8 * 8
+    dy = torch.zeros(M, Kp, device="cuda", dtype=torch.bfloat16)
+    dy[:, :K] = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(K, N, device="cuda") / K ** 0.5).bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    o.gemm_nn(dy[:, :K], w, out)
+    ref = dy[:, :K].float() @ w.float()
+    assert _rel(out, ref) < 1e-2
+    out32 = torch.randn(M, N, device="cuda")
+    base = out32.clone()
+    o.gemm_nn(dy[:, :K], w, out32, accumulate=True)
+    assert _rel(out32, ref + base) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(16384, 2304, 768), (16384, 768, 3072), (4096, 80, 768), (1000, 192, 192)])
+def test_linear_wgrad(M, N, K):
+    o = ops()
+    torch.manual_seed(3)
+    Np = (N + 7) // 8 * 8
+    dy = torch.randn(M, Np, device="cuda").bfloat16()
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    g = torch.randn(N, K, device="cuda")
+    base = g.clone()
+    o.linear_wgrad(dy[:, :N], x, g, accumulate=True)
+    ref = dy[:, :N].float().t() @ x.float()
+    assert _rel(g - base, ref) < 2e-4
+    o.linear_wgrad(dy[:, :N], x, g, accumulate=False)
+    assert _rel(g, ref) < 2e-4
+
+
+CONVS = [  # NB, H, W, Cin, Cout, ks, sh, sw
+    (2, 16, 512, 192, 192, 3, 2, 1),
+    (2, 8, 512, 192, 192, 3, 1, 1),
+    (2, 8, 512, 192, 384, 3, 2, 2),
+    (2, 4, 256, 384, 384, 3, 1, 1),
+    (2, 4, 256, 384, 768, 3, 2, 2),
+    (2, 2, 128, 768, 768, 3, 1, 1),
+    (2, 16, 512, 192, 192, 1, 2, 1),
+    (2, 8, 512, 192, 384, 1, 2, 2),
+    (3, 4, 64, 64, 128, 3, 2, 2),        # ragged: Wo=32 < tile
+    (1, 8, 200, 64, 64, 3, 1, 1),        # W not a multiple of the tile
+]
+
+
+def _conv_ref(x_nhwc, w_oihw, ks, sh, sw):
+    return F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w_oihw.float(), None, (sh, sw), ks // 2)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,ks,sh,sw", CONVS)
+def test_conv_fwd_dgrad_wgrad(NB, H, W, Cin, Cout, ks, sh, sw):
+    o = ops()
+    torch.manual_seed(4)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = torch.randn(NB, H, W, Cin, device="cuda").bfloat16()
+    w = (torch.randn(Cout, Cin, ks, ks, device="cuda") / (Cin * ks * ks) ** 0.5).bfloat16()
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, ks * ks, Cin).contiguous()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, (sh, sw), ks // 2)
+    rows = o.conv_stats_rows(NB, H, W, ks, sh, sw)
+    stats = torch.zeros(rows, 2, Cout, device="cuda")
+    y = o.conv_fwd(x, wk, ks, sh, sw, stats=stats)
+    assert y.shape == (NB, yr.shape[2], yr.shape[3], Cout)
+    assert _rel(y.permute(0, 3, 1, 2), yr) < 1e-2
+    yf = y.float()
+    assert _rel(stats[:, 0].sum(0), yf.sum((0, 1, 2))) < 1e-3 or float((stats[:, 0].sum(0) - yf.sum((0, 1, 2))).abs().max()) < 0.5
+    assert _rel(stats[:, 1].sum(0), (yf * yf).sum((0, 1, 2))) < 1e-3
+    dy = torch.randn_like(y)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    dx = o.conv_dgrad(dy, wk, (NB, H, W, Cin), ks, sh, sw)
+    assert _rel(dx.permute(0, 3, 1, 2), xr.grad) < 1e-2
+    gw = torch.zeros(Cout, Cin, ks, ks, device="cuda")
+    o.conv_wgrad(dy, x, ks, sh, sw, gw, accumulate=False)
+    assert _rel(gw, wr.grad) < 1e-3
