@@ -52,6 +52,29 @@ SIGNATURES = {
     "htrvt_conv_fwd_stats_rows": (_I, [_I, _I, _I, _I, _I, _I]),
     "htrvt_conv_dgrad": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P]),
     "htrvt_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _Z, _P]),
+    "htrvt_sample_ln_fwd": (_I, [_P, _P, _I, _P, _P, _I, _I, _F, _P]),
+    "htrvt_sample_ln_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_row_ln_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "htrvt_row_ln_bwd_ctas": (_I, [_I]),
+    "htrvt_row_ln_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
+    "htrvt_tokens_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "htrvt_tokens_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "htrvt_gelu_bwd": (_I, [_P, _P, _P, _L, _P]),
+    "htrvt_colsum_rows": (_I, [_I]),
+    "htrvt_colsum_bf16": (_I, [_P, _L, _I, _I, _P, _I, _P, _P]),
+    "htrvt_cast_bf16": (_I, [_P, _P, _L, _P]),
+    "htrvt_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _P]),
+    "htrvt_conv1_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_bn_finalize": (_I, [_P, _I, ctypes.c_double, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P]),
+    "htrvt_bn_act_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "htrvt_pool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_pool_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_bn_bwd_ctas": (_I, [_L]),
+    "htrvt_bn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P]),
+    "htrvt_conv1_wgrad_ctas": (_I, []),
+    "htrvt_conv1_wgrad": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "htrvt_attention_fwd": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "htrvt_attention_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
 }
 
 

@@ -19,9 +19,13 @@ __device__ __forceinline__ float lse3_log2(float a, float b, float c) {
 }
 
 // alpha recursion.  Lane owns states s = lane*K + j.  A is [T][32*K] (shared or global).
+// Every kRenorm steps the running maximum is subtracted and accumulated in double (`off[t]` = offset of
+// row t), so stored values stay O(10^1): fp32 log-space then resolves ~4e-6 instead of ~6e-5 at |nll|~10^3.
+constexpr int kRenorm = 8;
+
 template <int K>
 __device__ __forceinline__ void ctc_alpha(const float* __restrict__ l2p, int ldp, const int* __restrict__ ext, int S,
-                                          int Tb, float* A) {
+                                          int Tb, float* A, double* off) {
   const int lane = threadIdx.x & 31;
   const int SP = 32 * K;
   float a[K], p[K];
@@ -38,6 +42,8 @@ __device__ __forceinline__ void ctc_alpha(const float* __restrict__ l2p, int ldp
     if (s == 1 && S > 1) a[j] = l2p[lab[j]];
     A[s] = a[j];
   }
+  double c = 0.0;
+  if (lane == 0) off[0] = 0.0;
   if (Tb > 1) {
 #pragma unroll
     for (int j = 0; j < K; ++j) p[j] = l2p[ldp + lab[j]];
@@ -61,6 +67,18 @@ __device__ __forceinline__ void ctc_alpha(const float* __restrict__ l2p, int ldp
       const float v = lse3_log2(a[j], p1, skip[j] ? p2 : kNeg) + p[j];
       n[j] = valid[j] ? fmaxf(v, kNeg) : kNeg;
     }
+    if ((t & (kRenorm - 1)) == 0) {
+      float m = n[0];
+#pragma unroll
+      for (int j = 1; j < K; ++j) m = fmaxf(m, n[j]);
+      m = warp_max(m);
+      if (m > -1.0e29f) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) n[j] = fmaxf(n[j] - m, kNeg);
+        c += static_cast<double>(m);
+      }
+    }
+    if (lane == 0) off[t] = c;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       a[j] = n[j];
@@ -73,7 +91,7 @@ __device__ __forceinline__ void ctc_alpha(const float* __restrict__ l2p, int ldp
 // beta recursion (backwards in time).  Bt is [T][32*K].
 template <int K>
 __device__ __forceinline__ void ctc_beta(const float* __restrict__ l2p, int ldp, const int* __restrict__ ext, int S,
-                                         int Tb, float* Bt) {
+                                         int Tb, float* Bt, double* off) {
   const int lane = threadIdx.x & 31;
   const int SP = 32 * K;
   float b[K], p[K];
@@ -91,6 +109,8 @@ __device__ __forceinline__ void ctc_beta(const float* __restrict__ l2p, int ldp,
     if (s == S - 2 && S > 1) b[j] = row[lab[j]];
     Bt[(Tb - 1) * SP + s] = b[j];
   }
+  double c = 0.0;
+  if (lane == 0) off[Tb - 1] = 0.0;
   if (Tb > 1) {
 #pragma unroll
     for (int j = 0; j < K; ++j) p[j] = l2p[(Tb - 2) * ldp + lab[j]];
@@ -114,6 +134,18 @@ __device__ __forceinline__ void ctc_beta(const float* __restrict__ l2p, int ldp,
       const float v = lse3_log2(b[j], p1, skip[j] ? p2 : kNeg) + p[j];
       n[j] = valid[j] ? fmaxf(v, kNeg) : kNeg;
     }
+    if ((t & (kRenorm - 1)) == 0) {
+      float m = n[0];
+#pragma unroll
+      for (int j = 1; j < K; ++j) m = fmaxf(m, n[j]);
+      m = warp_max(m);
+      if (m > -1.0e29f) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) n[j] = fmaxf(n[j] - m, kNeg);
+        c += static_cast<double>(m);
+      }
+    }
+    if (lane == 0) off[t] = c;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       b[j] = n[j];
@@ -168,7 +200,9 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
   float* post = l2p + T * ldp;                     // [NW][ldp] per-warp posterior row
   int* ext = reinterpret_cast<int*>(post + NW * ldp);   // [32*kmax] extended label sequence
   float* red = reinterpret_cast<float*>(ext + 32 * P.kmax);   // [40] reductions / broadcast
-  float* AB = red + 40;                            // alpha | beta when they fit in shared memory
+  double* offA = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(red + 40) + 7) & ~uintptr_t(7));         // [T] renormalisation offsets of alpha rows
+  double* offB = offA + T;                                    // [T] ... of beta rows
+  float* AB = reinterpret_cast<float*>(offB + T);  // alpha | beta when they fit in shared memory
 
   // ---- per-sequence metadata -------------------------------------------------------------------
   int Tb = P.input_lengths ? P.input_lengths[b] : T;
@@ -230,26 +264,28 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
   const bool run = fits && Tb > 0;
   if (run) {
     if (warp == 0) {
-      CTC_DISPATCH(ctc_alpha, l2p, ldp, ext, S, Tb, A)
+      CTC_DISPATCH(ctc_alpha, l2p, ldp, ext, S, Tb, A, offA)
     } else if (warp == 1) {
-      CTC_DISPATCH(ctc_beta, l2p, ldp, ext, S, Tb, Bt)
+      CTC_DISPATCH(ctc_beta, l2p, ldp, ext, S, Tb, Bt, offB)
     }
   }
   if (!P.scratch_in_smem) __threadfence_block();
   __syncthreads();
 
-  float ll2 = kNeg;                                // log2 likelihood
+  float ll2r = kNeg;                               // log2 likelihood relative to offA[Tb-1]
+  double ll2 = 0.0;
   if (run) {
     const float a1 = A[(Tb - 1) * SP + S - 1];
     const float a2 = S > 1 ? A[(Tb - 1) * SP + S - 2] : kNeg;
     const float m = fmaxf(a1, a2);
-    ll2 = m + lg2f(ex2f(a1 - m) + ex2f(a2 - m));
+    ll2r = m + lg2f(ex2f(a1 - m) + ex2f(a2 - m));
+    ll2 = static_cast<double>(ll2r) + offA[Tb - 1];
   } else if (Tb == 0 && L == 0) {
-    ll2 = 0.f;
+    ll2r = 0.f;
   }
-  const bool feasible = ll2 > -1.0e29f;
+  const bool feasible = ll2r > -1.0e29f;
   if (tid == 0) {
-    float out = feasible ? -ll2 * kLn2 : 0.f;      // zero_infinity=True
+    float out = feasible ? static_cast<float>(-ll2 * 0.6931471805599453) : 0.f;      // zero_infinity=True
     if (L > Tb) out = 0.f;
     else if (K > P.kmax) out = __int_as_float(0x7fc00000);   // provisioning error: be loud
     P.nll[b] = out;
@@ -271,9 +307,10 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
     float blank = 0.f;
     const float* ar = A + t * SP;
     const float* br = Bt + t * SP;
+    const float rowc = static_cast<float>(offA[t] + offB[t] - ll2);
     for (int s = lane; s < S; s += 32) {
       const int c = ext[s];
-      const float v = ex2f(ar[s] + br[s] - lr[c] - ll2);
+      const float v = ex2f((ar[s] + br[s] - lr[c]) + rowc);
       if (s & 1) atomicAdd(&pw[c], v);
       else blank += v;
     }
@@ -291,7 +328,7 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
 
 size_t ctc_smem_bytes(int T, int C, int kmax, bool scratch_in_smem) {
   const int ldp = C | 1;
-  size_t words = static_cast<size_t>(T) * ldp + (kCtcThreads / 32) * ldp + 32 * kmax + 40;
+  size_t words = static_cast<size_t>(T) * ldp + (kCtcThreads / 32) * ldp + 32 * kmax + 40 + 4 * T + 2;
   if (scratch_in_smem) words += static_cast<size_t>(2) * T * 32 * kmax;
   return words * 4;
 }

@@ -1,0 +1,461 @@
+// HBM-bound normalisation / elementwise kernels of the transformer part (sm_100a):
+// whole-sample LayerNorm (input image and logits slab), row LayerNorm fwd/bwd fused with the fp32
+// residual stream, span-mask + positional embedding, GELU backward, bias-gradient column sums,
+// weight casts.  All vectorised 16-byte accesses, one pass over HBM where the math allows.
+//
+// Replaces: LayerNorm.forward (model_v1/model/HTR_VT.py:134-136), nn.LayerNorm(768, eps=1e-6)
+// (:68,75,169), random_masking + pos_embed add (:212-220,229-231), nn.GELU backward (timm Mlp).
+#include "common.cuh"
+
+namespace htrvt {
+
+// ------------------------------------------------------------------------------------------------
+// Whole-sample LayerNorm (no affine): y = (x - mean) * rstd over all N elements of a sample
+// ------------------------------------------------------------------------------------------------
+template <typename OutT>
+__global__ void __launch_bounds__(1024) sample_ln_fwd_kernel(const float* __restrict__ x, OutT* __restrict__ y,
+                                                             float* __restrict__ mean_out,
+                                                             float* __restrict__ rstd_out, int N, float eps) {
+  __shared__ float red[40];
+  const float* xb = x + static_cast<long long>(blockIdx.x) * N;
+  OutT* yb = y + static_cast<long long>(blockIdx.x) * N;
+  float s = 0.f;
+  for (int i = threadIdx.x * 4; i < N; i += 4096) {
+    const float4 v = *reinterpret_cast<const float4*>(xb + i);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = block_sum(s, red) / N;
+  float q = 0.f;
+  for (int i = threadIdx.x * 4; i < N; i += 4096) {
+    const float4 v = *reinterpret_cast<const float4*>(xb + i);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = block_sum(q, red) / N;
+  const float rstd = rsqrtf(var + eps);
+  if (threadIdx.x == 0) {
+    if (mean_out) mean_out[blockIdx.x] = mean;
+    if (rstd_out) rstd_out[blockIdx.x] = rstd;
+  }
+  for (int i = threadIdx.x * 4; i < N; i += 4096) {
+    const float4 v = *reinterpret_cast<const float4*>(xb + i);
+    const float a = (v.x - mean) * rstd, b = (v.y - mean) * rstd, c = (v.z - mean) * rstd, d = (v.w - mean) * rstd;
+    if (sizeof(OutT) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(yb) + i) = make_float4(a, b, c, d);
+    } else {
+      uint2 u;
+      u.x = pack_bf16(a, b); u.y = pack_bf16(c, d);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(yb) + i) = u;
+    }
+  }
+}
+
+// dx = rstd * (dy - mean(dy) - y * mean(dy*y)), y = normalised output.  dx is bf16 [rows, ld_out] with
+// the sample's N = T*C elements laid out as T rows of C (padded row stride for the head GEMM's TMA).
+__global__ void __launch_bounds__(1024) sample_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                             const float* __restrict__ rstd,
+                                                             __nv_bfloat16* __restrict__ dx, int N, int C,
+                                                             int ld_out) {
+  __shared__ float red[40];
+  const long long base = static_cast<long long>(blockIdx.x) * N;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < N; i += 1024) {
+    const float g = dy[base + i];
+    s1 += g;
+    s2 += g * y[base + i];
+  }
+  const float m1 = block_sum(s1, red) / N;
+  const float m2 = block_sum(s2, red) / N;
+  const float r = rstd[blockIdx.x];
+  const int T = N / C;
+  __nv_bfloat16* ob = dx + static_cast<long long>(blockIdx.x) * T * ld_out;
+  for (int i = threadIdx.x; i < T * ld_out; i += 1024) {
+    const int t = i / ld_out, c = i - t * ld_out;
+    float v = 0.f;
+    if (c < C) v = r * (dy[base + t * C + c] - m1 - y[base + t * C + c] * m2);
+    ob[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row LayerNorm with affine (D % 128 == 0, D <= 1024): one warp per row
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256) row_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta,
+                                                         __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                                                         float* __restrict__ rstd_out, int M, float eps) {
+  constexpr int V = D / 128;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* xr = x + static_cast<long long>(row) * D;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(xr + lane * 4 + 128 * i);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  __nv_bfloat16* yr = y + static_cast<long long>(row) * D;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = lane * 4 + 128 * i;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 b = *reinterpret_cast<const float4*>(beta + c);
+    uint2 u;
+    u.x = pack_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+    u.y = pack_bf16((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    *reinterpret_cast<uint2*>(yr + c) = u;
+  }
+}
+
+// gx (+)= rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); per-CTA partial dgamma / dbeta.
+// If accumulate == 0 the result overwrites gx (used for the final norm, whose input grad starts the stream).
+template <int D>
+__global__ void __launch_bounds__(256) row_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                         const float* __restrict__ x, const float* __restrict__ mean,
+                                                         const float* __restrict__ rstd,
+                                                         const float* __restrict__ gamma, float* __restrict__ gx,
+                                                         float* __restrict__ partial, int M, int rows_per_cta,
+                                                         int accumulate) {
+  constexpr int V = D / 128;
+  __shared__ float sg[8][D], sb[8][D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 dg[V], db[V], gm[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[i] = *reinterpret_cast<const float4*>(gamma + lane * 4 + 128 * i);
+  }
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  for (int row = r0 + warp; row < r1; row += 8) {
+    const float mu = mean[row], rs = rstd[row];
+    const float* xr = x + static_cast<long long>(row) * D;
+    const __nv_bfloat16* dr = dy + static_cast<long long>(row) * D;
+    float4 xh[V], gy[V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = lane * 4 + 128 * i;
+      const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+      const uint2 u = *reinterpret_cast<const uint2*>(dr + c);
+      const float2 d01 = unpack_bf16(u.x), d23 = unpack_bf16(u.y);
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      dg[i].x += d01.x * xh[i].x; dg[i].y += d01.y * xh[i].y; dg[i].z += d23.x * xh[i].z; dg[i].w += d23.y * xh[i].w;
+      db[i].x += d01.x; db[i].y += d01.y; db[i].z += d23.x; db[i].w += d23.y;
+      gy[i] = make_float4(d01.x * gm[i].x, d01.y * gm[i].y, d23.x * gm[i].z, d23.y * gm[i].w);
+      s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+      s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
+    }
+    const float m1 = warp_sum(s1) * (1.0f / D), m2 = warp_sum(s2) * (1.0f / D);
+    float* gr = gx + static_cast<long long>(row) * D;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = lane * 4 + 128 * i;
+      float4 o = make_float4(rs * (gy[i].x - m1 - xh[i].x * m2), rs * (gy[i].y - m1 - xh[i].y * m2),
+                             rs * (gy[i].z - m1 - xh[i].z * m2), rs * (gy[i].w - m1 - xh[i].w * m2));
+      if (accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(gr + c);
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      *reinterpret_cast<float4*>(gr + c) = o;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = lane * 4 + 128 * i;
+    *reinterpret_cast<float4*>(&sg[warp][c]) = dg[i];
+    *reinterpret_cast<float4*>(&sb[warp][c]) = db[i];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += sg[w][c]; b += sb[w][c]; }
+    partial[(static_cast<long long>(blockIdx.x) * 2) * D + c] = a;
+    partial[(static_cast<long long>(blockIdx.x) * 2 + 1) * D + c] = b;
+  }
+}
+
+// out[c] (+)= sum_r partial[r*stride + c]  (deterministic second stage of every column reduction)
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int R, long long stride, int Ccols,
+                                       float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Ccols) return;
+  float s = 0.f;
+  for (int r = 0; r < R; ++r) s += partial[r * stride + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tokens: x = (mask ? tok : mask_token) + pos      (fp32 residual stream from the bf16 stem output)
+// ------------------------------------------------------------------------------------------------
+__global__ void tokens_fwd_kernel(const __nv_bfloat16* __restrict__ tok, const float* __restrict__ mask,
+                                  const float* __restrict__ mask_token, const float* __restrict__ pos,
+                                  float* __restrict__ x, int B, int T, int D) {
+  const long long n4 = static_cast<long long>(B) * T * D / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 4;
+    const int d = static_cast<int>(e % D);
+    const int t = static_cast<int>((e / D) % T);
+    const uint2 u = *reinterpret_cast<const uint2*>(tok + e);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    float4 v = make_float4(a.x, a.y, b.x, b.y);
+    if (mask) {
+      const float m = mask[t];
+      const float4 mt = *reinterpret_cast<const float4*>(mask_token + d);
+      v.x = v.x * m + (1.f - m) * mt.x; v.y = v.y * m + (1.f - m) * mt.y;
+      v.z = v.z * m + (1.f - m) * mt.z; v.w = v.w * m + (1.f - m) * mt.w;
+    }
+    if (pos) {
+      const float4 p = *reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * D + d);
+      v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+    }
+    *reinterpret_cast<float4*>(x + e) = v;
+  }
+}
+
+// dtok = gx * mask (bf16); partial[t][d] = sum_b gx[b,t,d] * (1 - mask[t])   (one CTA per token position)
+__global__ void __launch_bounds__(256) tokens_bwd_kernel(const float* __restrict__ gx, const float* __restrict__ mask,
+                                                         __nv_bfloat16* __restrict__ dtok,
+                                                         float* __restrict__ partial, int B, int T, int D) {
+  const int t = blockIdx.x;
+  const float m = mask ? mask[t] : 1.f;
+  for (int d = threadIdx.x; d < D; d += 256) {
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const long long e = (static_cast<long long>(b) * T + t) * D + d;
+      const float g = gx[e];
+      dtok[e] = __float2bfloat16_rn(g * m);
+      acc += g * (1.f - m);
+    }
+    if (partial) partial[static_cast<long long>(t) * D + d] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GELU backward: du = da * (Phi(u) + u phi(u)), erf form (nn.GELU default)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_grad(float u) {
+  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
+  return cdf + u * pdf;
+}
+__global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ u,
+                                __nv_bfloat16* __restrict__ du, long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 a = *reinterpret_cast<const uint4*>(da + i * 8);
+    const uint4 b = *reinterpret_cast<const uint4*>(u + i * 8);
+    uint4 o;
+    float2 x, y;
+    x = unpack_bf16(a.x); y = unpack_bf16(b.x); o.x = pack_bf16(x.x * gelu_grad(y.x), x.y * gelu_grad(y.y));
+    x = unpack_bf16(a.y); y = unpack_bf16(b.y); o.y = pack_bf16(x.x * gelu_grad(y.x), x.y * gelu_grad(y.y));
+    x = unpack_bf16(a.z); y = unpack_bf16(b.z); o.z = pack_bf16(x.x * gelu_grad(y.x), x.y * gelu_grad(y.y));
+    x = unpack_bf16(a.w); y = unpack_bf16(b.w); o.w = pack_bf16(x.x * gelu_grad(y.x), x.y * gelu_grad(y.y));
+    *reinterpret_cast<uint4*>(du + i * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column sums of a bf16 matrix [M, N] (bias gradients): partial[cta][N]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long ld, int M,
+                                                          int N, int rows_per_cta, float* __restrict__ partial) {
+  // thread handles a pair of columns; blockDim.y row lanes are reduced through shared memory
+  __shared__ float2 sm[8][128];
+  const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;       // 128 column pairs x 2 row lanes
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  const int c = (blockIdx.x * 128 + tx) * 2;
+  float2 acc = make_float2(0.f, 0.f);
+  if (c < N) {
+    for (int r = r0 + ty; r < r1; r += 2) {
+      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(a + r * ld + c));
+      acc.x += v.x; acc.y += v.y;
+    }
+  }
+  sm[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    const float2 o = sm[1][tx];
+    partial[static_cast<long long>(blockIdx.y) * N + c] = acc.x + o.x;
+    if (c + 1 < N) partial[static_cast<long long>(blockIdx.y) * N + c + 1] = acc.y + o.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight packing (fp32 master -> bf16 operand copies), refreshed every forward because SAM perturbs
+// the parameters in place twice per iteration
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+// OIHW fp32 [Cout, Cin, taps] -> bf16 [Cout, taps, Cin]
+__global__ void pack_conv_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cout,
+                                        int Cin, int taps) {
+  const long long n = static_cast<long long>(Cout) * Cin * taps;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    const long long r = i / Cin;
+    const int tap = static_cast<int>(r % taps);
+    const int co = static_cast<int>(r / taps);
+    dst[i] = __float2bfloat16_rn(src[(static_cast<long long>(co) * Cin + ci) * taps + tap]);
+  }
+}
+
+}  // namespace htrvt
+
+using namespace htrvt;
+
+static inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  return static_cast<int>(g < 1 ? 1 : (g > 148LL * 16 ? 148LL * 16 : g));
+}
+
+extern "C" int htrvt_sample_ln_fwd(const float* x, void* y, int y_is_bf16, float* mean, float* rstd, int B, int N,
+                                   float eps, cudaStream_t stream) {
+  if (B <= 0 || N <= 0 || (N & 3)) return HTRVT_ERR_SHAPE;
+  if (y_is_bf16)
+    sample_ln_fwd_kernel<__nv_bfloat16><<<B, 1024, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y), mean, rstd, N, eps);
+  else
+    sample_ln_fwd_kernel<float><<<B, 1024, 0, stream>>>(x, static_cast<float*>(y), mean, rstd, N, eps);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_sample_ln_bwd(const float* dy, const float* y, const float* rstd, void* dx_bf16, int B, int N,
+                                   int C, int ld_out, cudaStream_t stream) {
+  if (B <= 0 || N <= 0 || C <= 0 || (N % C) || ld_out < C) return HTRVT_ERR_SHAPE;
+  sample_ln_bwd_kernel<<<B, 1024, 0, stream>>>(dy, y, rstd, static_cast<__nv_bfloat16*>(dx_bf16), N, C, ld_out);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_row_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* mean,
+                                float* rstd, int M, int D, float eps, cudaStream_t stream) {
+  if (M <= 0) return HTRVT_ERR_SHAPE;
+  const int grid = (M + 7) / 8;
+  if (D == 768)
+    row_ln_fwd_kernel<768><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, M, eps);
+  else if (D == 128)
+    row_ln_fwd_kernel<128><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, M, eps);
+  else if (D == 256)
+    row_ln_fwd_kernel<256><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, M, eps);
+  else
+    return HTRVT_ERR_SHAPE;
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_row_ln_bwd_ctas(int M) {
+  int ctas = (M + 63) / 64;
+  return ctas > 592 ? 592 : ctas;
+}
+
+// partial: fp32 [ctas][2][D]; dgamma / dbeta are accumulated (+=)
+extern "C" int htrvt_row_ln_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd,
+                                const float* gamma, float* gx, int accumulate, float* dgamma, float* dbeta,
+                                float* partial, int M, int D, cudaStream_t stream) {
+  if (M <= 0) return HTRVT_ERR_SHAPE;
+  const int ctas = htrvt_row_ln_bwd_ctas(M);
+  const int rows = (M + ctas - 1) / ctas;
+  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_bf16);
+  if (D == 768)
+    row_ln_bwd_kernel<768><<<ctas, 256, 0, stream>>>(dy, x, mean, rstd, gamma, gx, partial, M, rows, accumulate);
+  else if (D == 128)
+    row_ln_bwd_kernel<128><<<ctas, 256, 0, stream>>>(dy, x, mean, rstd, gamma, gx, partial, M, rows, accumulate);
+  else if (D == 256)
+    row_ln_bwd_kernel<256><<<ctas, 256, 0, stream>>>(dy, x, mean, rstd, gamma, gx, partial, M, rows, accumulate);
+  else
+    return HTRVT_ERR_SHAPE;
+  HTRVT_LAUNCH_CHECK();
+  colsum_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial, ctas, 2LL * D, D, dgamma, 1);
+  colsum_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial + D, ctas, 2LL * D, D, dbeta, 1);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_tokens_fwd(const void* tok_bf16, const float* mask, const float* mask_token, const float* pos,
+                                float* x, int B, int T, int D, cudaStream_t stream) {
+  if (B <= 0 || T <= 0 || (D & 3)) return HTRVT_ERR_SHAPE;
+  const long long n4 = static_cast<long long>(B) * T * D / 4;
+  tokens_fwd_kernel<<<grid_for(n4, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(tok_bf16), mask,
+                                                           mask_token, pos, x, B, T, D);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+// partial: fp32 [T][D] scratch; dmask_token (+=) may be null (no masking => no gradient)
+extern "C" int htrvt_tokens_bwd(const float* gx, const float* mask, void* dtok_bf16, float* dmask_token,
+                                float* partial, int B, int T, int D, cudaStream_t stream) {
+  if (B <= 0 || T <= 0 || D <= 0) return HTRVT_ERR_SHAPE;
+  const bool want = mask && dmask_token;
+  tokens_bwd_kernel<<<T, 256, 0, stream>>>(gx, mask, static_cast<__nv_bfloat16*>(dtok_bf16), want ? partial : nullptr,
+                                           B, T, D);
+  HTRVT_LAUNCH_CHECK();
+  if (want) {
+    colsum_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial, T, D, D, dmask_token, 1);
+    HTRVT_LAUNCH_CHECK();
+  }
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_gelu_bwd(const void* da, const void* u, void* du, long long n, cudaStream_t stream) {
+  if (n <= 0 || (n & 7)) return HTRVT_ERR_SHAPE;
+  gelu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(da),
+                                                            static_cast<const __nv_bfloat16*>(u),
+                                                            static_cast<__nv_bfloat16*>(du), n / 8);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_colsum_rows(int M) {
+  int r = (M + 255) / 256;
+  return r > 128 ? 128 : r;
+}
+
+// out[N] (+)= column sums of a bf16 [M, N] (row stride ld); partial: fp32 [htrvt_colsum_rows(M)][N]
+extern "C" int htrvt_colsum_bf16(const void* a, long long ld, int M, int N, float* out, int accumulate,
+                                 float* partial, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || (ld & 1)) return HTRVT_ERR_SHAPE;
+  const int gy = htrvt_colsum_rows(M);
+  const int rows = (M + gy - 1) / gy;
+  dim3 grid((N + 255) / 256, gy);
+  colsum_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a), ld, M, N, rows, partial);
+  HTRVT_LAUNCH_CHECK();
+  colsum_finalize_kernel<<<(N + 127) / 128, 128, 0, stream>>>(partial, gy, N, N, out, accumulate);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_cast_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
+  if (n <= 0) return HTRVT_ERR_SHAPE;
+  cast_bf16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_pack_conv_weight(const float* w_oihw, void* dst, int Cout, int Cin, int taps,
+                                      cudaStream_t stream) {
+  if (Cout <= 0 || Cin <= 0 || taps <= 0) return HTRVT_ERR_SHAPE;
+  pack_conv_weight_kernel<<<grid_for(static_cast<long long>(Cout) * Cin * taps, 256), 256, 0, stream>>>(
+      w_oihw, static_cast<__nv_bfloat16*>(dst), Cout, Cin, taps);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}

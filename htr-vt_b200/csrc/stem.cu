@@ -1,0 +1,600 @@
+// HBM-bound kernels of the conv stem (sm_100a), NHWC bf16 activations:
+//   first conv (1 input channel, K = 9: direct, memory bound) + batch statistics,
+//   BatchNorm finalise (batch or running statistics, running-stat update), BN-apply + ReLU (+ residual),
+//   3x3 / stride (2,1) max-pool fused with BN + ReLU (+ arg-max byte for the backward),
+//   BatchNorm backward (two-stage reduction + apply, ReLU mask fused), max-pool backward,
+//   first-conv weight gradient.
+// Replaces the ATen / cuDNN dispatches behind ResNet18 / BasicBlock (model_v1/model/resnet18.py:10-39,
+// 42-84): BatchNorm2d(eps=1e-5, momentum 0.1), ReLU, MaxPool2d(3, (2,1), 1), residual adds.
+#include "common.cuh"
+
+namespace htrvt {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
+  u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1: x [B,H,W] bf16 (one channel) -> raw [B,H/2,W,C] bf16, stride (2,1), pad 1, + channel statistics
+// grid (W/128 tiles, H/2, B); blockDim = C threads: thread -> channel pair (t % (C/2)), pixel half (t / (C/2))
+// ------------------------------------------------------------------------------------------------
+__global__ void conv1_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                 __nv_bfloat16* __restrict__ raw, float* __restrict__ partial, int H, int W, int C) {
+  __shared__ float in[3][132];
+  extern __shared__ float red[];                     // [2][C] statistics of the second pixel half
+  const int w0 = blockIdx.x * 128, ho = blockIdx.y, n = blockIdx.z, Ho = H / 2;
+  for (int i = threadIdx.x; i < 3 * 130; i += blockDim.x) {
+    const int r = i / 130, c = i - r * 130;
+    const int hh = 2 * ho + r - 1, ww = w0 + c - 1;
+    in[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                   ? __bfloat162float(x[(static_cast<long long>(n) * H + hh) * W + ww]) : 0.f;
+  }
+  const int half_c = C / 2;
+  const int cp = threadIdx.x % half_c, ph = threadIdx.x / half_c;
+  float wa[9], wb[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { wa[k] = w[(2 * cp) * 9 + k]; wb[k] = w[(2 * cp + 1) * 9 + k]; }
+  __syncthreads();
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  __nv_bfloat16* orow = raw + ((static_cast<long long>(n) * Ho + ho) * W + w0) * C + 2 * cp;
+  for (int p = ph * 64; p < ph * 64 + 64; ++p) {
+    if (w0 + p >= W) break;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float v = in[kh][p + kw];
+        a = fmaf(v, wa[kh * 3 + kw], a);
+        b = fmaf(v, wb[kh * 3 + kw], b);
+      }
+    const uint32_t u = pack_bf16(a, b);
+    *reinterpret_cast<uint32_t*>(orow + static_cast<long long>(p) * C) = u;
+    const float2 r = unpack_bf16(u);                 // statistics of what is stored
+    s0 += r.x; s1 += r.y; q0 += r.x * r.x; q1 += r.y * r.y;
+  }
+  if (!partial) return;
+  if (ph == 1) {
+    red[2 * cp] = s0; red[2 * cp + 1] = s1; red[C + 2 * cp] = q0; red[C + 2 * cp + 1] = q1;
+  }
+  __syncthreads();
+  if (ph == 0) {
+    const long long cta = (static_cast<long long>(n) * gridDim.y + ho) * gridDim.x + blockIdx.x;
+    float* dst = partial + cta * 2 * C;
+    dst[2 * cp] = s0 + red[2 * cp];
+    dst[2 * cp + 1] = s1 + red[2 * cp + 1];
+    dst[C + 2 * cp] = q0 + red[C + 2 * cp];
+    dst[C + 2 * cp + 1] = q1 + red[C + 2 * cp + 1];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm finalise: partial [R][2][C] (sum, sum of squares) -> mean, rstd, scale, shift (+ running stats)
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int R, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches_tracked, float momentum, float eps,
+                                   int training, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < R; ++r) {
+      s += partial[(static_cast<long long>(r) * 2) * C + c];
+      q += partial[(static_cast<long long>(r) * 2 + 1) * C + c];
+    }
+    const double m = s / count;
+    double v = q / count - m * m;
+    if (v < 0.0) v = 0.0;
+    mean = static_cast<float>(m);
+    var = static_cast<float>(v);
+    if (running_mean) {
+      const double unbiased = count > 1.0 ? v * count / (count - 1.0) : v;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * rstd;
+  mean_out[c] = mean;
+  rstd_out[c] = rstd;
+  scale_out[c] = sc;
+  shift_out[c] = beta[c] - mean * sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = [relu](raw*scale + shift [+ res | + raw2*scale2 + shift2])       8 channels per thread
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
+                                  const __nv_bfloat16* __restrict__ raw2, const float* __restrict__ scale2,
+                                  const float* __restrict__ shift2, __nv_bfloat16* __restrict__ y, long long n8,
+                                  int C, int relu) {
+  const int G = C / 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % G) * 8;
+    float v[8], s[8], b[8];
+    unpack8(*reinterpret_cast<const uint4*>(raw + i * 8), v);
+    *reinterpret_cast<float4*>(s) = *reinterpret_cast<const float4*>(scale + c);
+    *reinterpret_cast<float4*>(s + 4) = *reinterpret_cast<const float4*>(scale + c + 4);
+    *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(shift + c);
+    *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(shift + c + 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], s[k], b[k]);
+    if (res) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(res + i * 8), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    } else if (raw2) {
+      float r[8];
+      unpack8(*reinterpret_cast<const uint4*>(raw2 + i * 8), r);
+      *reinterpret_cast<float4*>(s) = *reinterpret_cast<const float4*>(scale2 + c);
+      *reinterpret_cast<float4*>(s + 4) = *reinterpret_cast<const float4*>(scale2 + c + 4);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(shift2 + c);
+      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(shift2 + c + 4);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += fmaf(r[k], s[k], b[k]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool 3x3, stride (2,1), pad 1 over a = relu(raw*scale+shift) (scale == null: a = raw as is)
+// out [B,Ho,W,C]; idx (optional) = kh*3+kw of the first maximum (torch's arg-max rule)
+// ------------------------------------------------------------------------------------------------
+__global__ void pool_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ scale,
+                                const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
+                                uint8_t* __restrict__ idx, int B, int H, int W, int C) {
+  const int G = C / 8, Ho = (H - 1) / 2 + 1;
+  const long long n8 = static_cast<long long>(B) * Ho * W * G;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    long long r = i / G;
+    const int wo = static_cast<int>(r % W); r /= W;
+    const int ho = static_cast<int>(r % Ho);
+    const int n = static_cast<int>(r / Ho);
+    float s[8], b[8];
+    if (scale) {
+      *reinterpret_cast<float4*>(s) = *reinterpret_cast<const float4*>(scale + g * 8);
+      *reinterpret_cast<float4*>(s + 4) = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(shift + g * 8);
+      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
+    }
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hh = 2 * ho + kh - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ww = wo + kw - 1;
+        if (ww < 0 || ww >= W) continue;
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(raw + ((static_cast<long long>(n) * H + hh) * W + ww) * C + g * 8), v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (scale) v[k] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(v[k], s[k], b[k]), 0.f)));
+          if (v[k] > best[k]) { best[k] = v[k]; bi[k] = kh * 3 + kw; }
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(best);
+    if (idx) {
+      uint2 u;
+      u.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      u.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = u;
+    }
+  }
+}
+
+// gin[n,h,w,c] = sum over windows (ho,wo) containing (h,w) of gout[ho,wo] * [idx[ho,wo] == position code]
+// optional relu mask: multiply by (relu(raw*scale+shift) > 0); optional fp32 gout (token gradient).
+template <typename GT>
+__global__ void pool_bwd_kernel(const GT* __restrict__ gout, const uint8_t* __restrict__ idx,
+                                const __nv_bfloat16* __restrict__ raw, const float* __restrict__ scale,
+                                const float* __restrict__ shift, __nv_bfloat16* __restrict__ gin, int B, int H,
+                                int W, int C) {
+  const int G = C / 8, Ho = (H - 1) / 2 + 1;
+  const long long n8 = static_cast<long long>(B) * H * W * G;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    long long r = i / G;
+    const int w = static_cast<int>(r % W); r /= W;
+    const int h = static_cast<int>(r % H);
+    const int n = static_cast<int>(r / H);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    // windows: ho with 2ho-1 <= h <= 2ho+1
+    const int ho_lo = h / 2, ho_hi = (h + 1) / 2;       // equal when h is even
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      if (ho >= Ho) continue;
+      const int kh = h - (2 * ho - 1);
+      for (int wo = w - 1; wo <= w + 1; ++wo) {
+        if (wo < 0 || wo >= W) continue;
+        const int kw = w - (wo - 1);
+        const int code = kh * 3 + kw;
+        const long long o = ((static_cast<long long>(n) * Ho + ho) * W + wo) * C + g * 8;
+        const uint2 iv = *reinterpret_cast<const uint2*>(idx + o);
+        float gv[8];
+        if (sizeof(GT) == 4) {
+          *reinterpret_cast<float4*>(gv) = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(gout) + o);
+          *reinterpret_cast<float4*>(gv + 4) = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(gout) + o + 4);
+        } else {
+          unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(gout) + o), gv);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int id = ((k < 4 ? iv.x : iv.y) >> (8 * (k & 3))) & 0xff;
+          if (id == code) acc[k] += gv[k];
+        }
+      }
+    }
+    if (scale) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(raw + i * 8), v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (!(fmaf(v[k], scale[g * 8 + k], shift[g * 8 + k]) > 0.f)) acc[k] = 0.f;
+    }
+    *reinterpret_cast<uint4*>(gin + i * 8) = pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm backward, stage 1: per-CTA partial sums of g' = g * [y > 0] and g' * xhat (one or two BNs)
+// partial [cta][3][C] : sum g', sum g' xhat_a, sum g' xhat_b
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                     const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mean_a,
+                                     const float* __restrict__ rstd_a, const __nv_bfloat16* __restrict__ raw_b,
+                                     const float* __restrict__ mean_b, const float* __restrict__ rstd_b,
+                                     float* __restrict__ partial, long long P, int C, int rows_per_cta) {
+  extern __shared__ float sm[];                         // [R][3][C]
+  const int G = C / 8, R = blockDim.x / G;
+  const int grp = threadIdx.x % G, lane_r = threadIdx.x / G;
+  float s0[8], s1[8], s2[8], ma[8], ra[8], mb[8], rb[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    s0[k] = s1[k] = s2[k] = 0.f;
+    ma[k] = mean_a[grp * 8 + k]; ra[k] = rstd_a[grp * 8 + k];
+    mb[k] = raw_b ? mean_b[grp * 8 + k] : 0.f; rb[k] = raw_b ? rstd_b[grp * 8 + k] : 0.f;
+  }
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
+  if (lane_r < R) {
+    for (long long r = r0 + lane_r; r < r1; r += R) {
+      const long long o = r * C + grp * 8;
+      float gv[8], yv[8], xa[8];
+      unpack8(*reinterpret_cast<const uint4*>(g + o), gv);
+      unpack8(*reinterpret_cast<const uint4*>(raw_a + o), xa);
+      if (y) {
+        unpack8(*reinterpret_cast<const uint4*>(y + o), yv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (!(yv[k] > 0.f)) gv[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s0[k] += gv[k];
+        s1[k] += gv[k] * (xa[k] - ma[k]) * ra[k];
+      }
+      if (raw_b) {
+        float xb[8];
+        unpack8(*reinterpret_cast<const uint4*>(raw_b + o), xb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s2[k] += gv[k] * (xb[k] - mb[k]) * rb[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sm[(lane_r * 3 + 0) * C + grp * 8 + k] = s0[k];
+      sm[(lane_r * 3 + 1) * C + grp * 8 + k] = s1[k];
+      sm[(lane_r * 3 + 2) * C + grp * 8 + k] = s2[k];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int rr = 0; rr < R; ++rr) s += sm[rr * 3 * C + i];
+    partial[static_cast<long long>(blockIdx.x) * 3 * C + i] = s;
+  }
+}
+
+// stage 2: coefficients k1 = sum g'/N, k2 = sum g' xhat / N; dgamma += sum g' xhat, dbeta += sum g'
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int R, double count, int C,
+                                       float* __restrict__ coef_a, float* __restrict__ dgamma_a,
+                                       float* __restrict__ dbeta_a, float* __restrict__ coef_b,
+                                       float* __restrict__ dgamma_b, float* __restrict__ dbeta_b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int r = 0; r < R; ++r) {
+    const float* p = partial + static_cast<long long>(r) * 3 * C;
+    s0 += p[c]; s1 += p[C + c]; s2 += p[2 * C + c];
+  }
+  coef_a[c] = static_cast<float>(s0 / count);
+  coef_a[C + c] = static_cast<float>(s1 / count);
+  if (dgamma_a) { dgamma_a[c] += static_cast<float>(s1); dbeta_a[c] += static_cast<float>(s0); }
+  if (coef_b) {
+    coef_b[c] = static_cast<float>(s0 / count);
+    coef_b[C + c] = static_cast<float>(s2 / count);
+    if (dgamma_b) { dgamma_b[c] += static_cast<float>(s2); dbeta_b[c] += static_cast<float>(s0); }
+  }
+}
+
+// stage 3: d_raw = gamma*rstd * (g' - k1 - xhat*k2) for one or two BNs; optional gz = g' (identity residual)
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                    const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mean_a,
+                                    const float* __restrict__ rstd_a, const float* __restrict__ gamma_a,
+                                    const float* __restrict__ coef_a, __nv_bfloat16* __restrict__ d_a,
+                                    const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ mean_b,
+                                    const float* __restrict__ rstd_b, const float* __restrict__ gamma_b,
+                                    const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ d_b,
+                                    __nv_bfloat16* __restrict__ gz, long long n8, int C) {
+  const int G = C / 8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % G) * 8;
+    float gv[8], xa[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(g + i * 8), gv);
+    unpack8(*reinterpret_cast<const uint4*>(raw_a + i * 8), xa);
+    if (y) {
+      float yv[8];
+      unpack8(*reinterpret_cast<const uint4*>(y + i * 8), yv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (!(yv[k] > 0.f)) gv[k] = 0.f;
+    }
+    if (gz) *reinterpret_cast<uint4*>(gz + i * 8) = pack8(gv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float rs = rstd_a[c + k];
+      const float xh = (xa[k] - mean_a[c + k]) * rs;
+      o[k] = gamma_a[c + k] * rs * (gv[k] - coef_a[c + k] - xh * coef_a[C + c + k]);
+    }
+    *reinterpret_cast<uint4*>(d_a + i * 8) = pack8(o);
+    if (raw_b) {
+      float xb[8];
+      unpack8(*reinterpret_cast<const uint4*>(raw_b + i * 8), xb);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float rs = rstd_b[c + k];
+        const float xh = (xb[k] - mean_b[c + k]) * rs;
+        o[k] = gamma_b[c + k] * rs * (gv[k] - coef_b[c + k] - xh * coef_b[C + c + k]);
+      }
+      *reinterpret_cast<uint4*>(d_b + i * 8) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1 weight gradient: dw[c][kh][kw] = sum dy[n,ho,wo,c] * x[n, 2ho+kh-1, wo+kw-1]; partial [cta][9][C]
+// persistent CTAs over (n, ho, w-tile) work items; thread -> channel pair / pixel half as in conv1_fwd
+// ------------------------------------------------------------------------------------------------
+__global__ void conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                   float* __restrict__ partial, int B, int H, int W, int C) {
+  __shared__ float in[3][132];
+  extern __shared__ float red[];                      // [18][C/2] for the second pixel half
+  const int Ho = H / 2, tiles_w = (W + 127) / 128;
+  const long long items = static_cast<long long>(B) * Ho * tiles_w;
+  const int half_c = C / 2;
+  const int cp = threadIdx.x % half_c, ph = threadIdx.x / half_c;
+  float ga[9], gb[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { ga[k] = 0.f; gb[k] = 0.f; }
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int tw = static_cast<int>(it % tiles_w);
+    const int ho = static_cast<int>((it / tiles_w) % Ho);
+    const int n = static_cast<int>(it / (static_cast<long long>(tiles_w) * Ho));
+    const int w0 = tw * 128;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 130; i += blockDim.x) {
+      const int r = i / 130, c = i - r * 130;
+      const int hh = 2 * ho + r - 1, ww = w0 + c - 1;
+      in[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                     ? __bfloat162float(x[(static_cast<long long>(n) * H + hh) * W + ww]) : 0.f;
+    }
+    __syncthreads();
+    const __nv_bfloat16* drow = dy + ((static_cast<long long>(n) * Ho + ho) * W + w0) * C + 2 * cp;
+    for (int p = ph * 64; p < ph * 64 + 64; ++p) {
+      if (w0 + p >= W) break;
+      const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(drow + static_cast<long long>(p) * C));
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float v = in[kh][p + kw];
+          ga[kh * 3 + kw] = fmaf(d.x, v, ga[kh * 3 + kw]);
+          gb[kh * 3 + kw] = fmaf(d.y, v, gb[kh * 3 + kw]);
+        }
+    }
+  }
+  __syncthreads();
+  if (ph == 1) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { red[(2 * k) * half_c + cp] = ga[k]; red[(2 * k + 1) * half_c + cp] = gb[k]; }
+  }
+  __syncthreads();
+  if (ph == 0) {
+    float* dst = partial + static_cast<long long>(blockIdx.x) * 9 * C;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      dst[(2 * cp) * 9 + k] = ga[k] + red[(2 * k) * half_c + cp];
+      dst[(2 * cp + 1) * 9 + k] = gb[k] + red[(2 * k + 1) * half_c + cp];
+    }
+  }
+}
+
+__global__ void colsum_finalize2_kernel(const float* __restrict__ partial, int R, long long stride, int n,
+                                        float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double s = 0.0;
+  for (int r = 0; r < R; ++r) s += partial[r * stride + c];
+  out[c] = accumulate ? out[c] + static_cast<float>(s) : static_cast<float>(s);
+}
+
+}  // namespace htrvt
+
+using namespace htrvt;
+
+static inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  return static_cast<int>(g < 1 ? 1 : (g > 148LL * 16 ? 148LL * 16 : g));
+}
+
+// partial: fp32 [B * (H/2) * ceil(W/128)][2][C]  (null: no statistics, eval mode)
+extern "C" int htrvt_conv1_fwd(const void* x_bf16, const float* w, void* raw_bf16, float* partial, int B, int H,
+                               int W, int C, cudaStream_t stream) {
+  if (B <= 0 || (H & 1) || W <= 0 || (C & 1) || C > 1024 || C < 2) return HTRVT_ERR_SHAPE;
+  dim3 grid((W + 127) / 128, H / 2, B);
+  conv1_fwd_kernel<<<grid, C, 2 * C * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(x_bf16), w,
+                                                               static_cast<__nv_bfloat16*>(raw_bf16), partial, H, W, C);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_bn_finalize(const float* partial, int R, double count, const float* gamma, const float* beta,
+                                 float* running_mean, float* running_var, long long* num_batches_tracked,
+                                 float momentum, float eps, int training, float* mean, float* rstd, float* scale,
+                                 float* shift, int C, cudaStream_t stream) {
+  if (C <= 0 || (training && (!partial || R <= 0))) return HTRVT_ERR_SHAPE;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, R, count, gamma, beta, running_mean, running_var,
+                                                          num_batches_tracked, momentum, eps, training, mean, rstd,
+                                                          scale, shift, C);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_bn_act_fwd(const void* raw, const float* scale, const float* shift, const void* res,
+                                const void* raw2, const float* scale2, const float* shift2, void* y, long long P,
+                                int C, int relu, cudaStream_t stream) {
+  if (P <= 0 || (C & 7)) return HTRVT_ERR_SHAPE;
+  const long long n8 = P * C / 8;
+  bn_act_fwd_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(raw), scale, shift, static_cast<const __nv_bfloat16*>(res),
+      static_cast<const __nv_bfloat16*>(raw2), scale2, shift2, static_cast<__nv_bfloat16*>(y), n8, C, relu);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_pool_fwd(const void* raw, const float* scale, const float* shift, void* out, void* idx, int B,
+                              int H, int W, int C, cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || (C & 7)) return HTRVT_ERR_SHAPE;
+  const int Ho = (H - 1) / 2 + 1;
+  const long long n8 = static_cast<long long>(B) * Ho * W * C / 8;
+  pool_fwd_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(raw), scale, shift,
+                                                         static_cast<__nv_bfloat16*>(out),
+                                                         static_cast<uint8_t*>(idx), B, H, W, C);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_pool_bwd(const void* gout, int gout_is_f32, const void* idx, const void* raw, const float* scale,
+                              const float* shift, void* gin, int B, int H, int W, int C, cudaStream_t stream) {
+  if (B <= 0 || H <= 0 || W <= 0 || (C & 7) || !idx) return HTRVT_ERR_SHAPE;
+  const long long n8 = static_cast<long long>(B) * H * W * C / 8;
+  if (gout_is_f32)
+    pool_bwd_kernel<float><<<grid_for(n8, 256), 256, 0, stream>>>(
+        static_cast<const float*>(gout), static_cast<const uint8_t*>(idx), static_cast<const __nv_bfloat16*>(raw),
+        scale, shift, static_cast<__nv_bfloat16*>(gin), B, H, W, C);
+  else
+    pool_bwd_kernel<__nv_bfloat16><<<grid_for(n8, 256), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(gout), static_cast<const uint8_t*>(idx),
+        static_cast<const __nv_bfloat16*>(raw), scale, shift, static_cast<__nv_bfloat16*>(gin), B, H, W, C);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_bn_bwd_ctas(long long P) {
+  long long c = (P + 255) / 256;
+  return static_cast<int>(c > 1184 ? 1184 : (c < 1 ? 1 : c));
+}
+
+// BatchNorm backward for the BN (a) that produced `raw_a` (and optionally a second BN (b) fed by the same
+// upstream gradient: the downsample branch).  g: gradient w.r.t. the post-activation output y (ReLU mask
+// y > 0 applied when y != null).  Writes d_a (/d_b) = gradient w.r.t. the raw conv outputs, accumulates
+// dgamma / dbeta, optionally writes gz = masked g (identity-residual gradient).
+// partial: fp32 [htrvt_bn_bwd_ctas(P)][3][C]; coef: fp32 [2][2][C] scratch.
+extern "C" int htrvt_bn_bwd(const void* g, const void* y, const void* raw_a, const float* mean_a,
+                            const float* rstd_a, const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a,
+                            const void* raw_b, const float* mean_b, const float* rstd_b, const float* gamma_b,
+                            float* dgamma_b, float* dbeta_b, void* d_b, void* gz, long long P, int C,
+                            float* partial, float* coef, cudaStream_t stream) {
+  if (P <= 0 || (C & 7) || C > 2048) return HTRVT_ERR_SHAPE;
+  const int G = C / 8;
+  if (G > 256) return HTRVT_ERR_SHAPE;
+  const int R = 256 / G;
+  const int threads = G * R;
+  const int ctas = htrvt_bn_bwd_ctas(P);
+  const int rows = static_cast<int>((P + ctas - 1) / ctas);
+  const size_t smem = static_cast<size_t>(R) * 3 * C * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    configured = true;
+  }
+  if (smem > 96 * 1024) return HTRVT_ERR_SHAPE;
+  bn_bwd_reduce_kernel<<<ctas, threads, smem, stream>>>(
+      static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y),
+      static_cast<const __nv_bfloat16*>(raw_a), mean_a, rstd_a, static_cast<const __nv_bfloat16*>(raw_b), mean_b,
+      rstd_b, partial, P, C, rows);
+  HTRVT_LAUNCH_CHECK();
+  float* coef_a = coef;
+  float* coef_b = raw_b ? coef + 2 * C : nullptr;
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, ctas, static_cast<double>(P), C, coef_a,
+                                                              dgamma_a, dbeta_a, coef_b, dgamma_b, dbeta_b);
+  HTRVT_LAUNCH_CHECK();
+  const long long n8 = P * C / 8;
+  bn_bwd_apply_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y),
+      static_cast<const __nv_bfloat16*>(raw_a), mean_a, rstd_a, gamma_a, coef_a, static_cast<__nv_bfloat16*>(d_a),
+      static_cast<const __nv_bfloat16*>(raw_b), mean_b, rstd_b, gamma_b, coef_b, static_cast<__nv_bfloat16*>(d_b),
+      static_cast<__nv_bfloat16*>(gz), n8, C);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_conv1_wgrad_ctas() { return 148 * 4; }
+
+// grad [C][1][3][3] fp32 (+=); partial: fp32 [htrvt_conv1_wgrad_ctas()][9*C]
+extern "C" int htrvt_conv1_wgrad(const void* dy_bf16, const void* x_bf16, float* grad, int accumulate,
+                                 float* partial, int B, int H, int W, int C, cudaStream_t stream) {
+  if (B <= 0 || (H & 1) || W <= 0 || (C & 1) || C > 1024 || C < 2) return HTRVT_ERR_SHAPE;
+  const int ctas = htrvt_conv1_wgrad_ctas();
+  conv1_wgrad_kernel<<<ctas, C, 18 * (C / 2) * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(dy_bf16), static_cast<const __nv_bfloat16*>(x_bf16), partial, B, H, W, C);
+  HTRVT_LAUNCH_CHECK();
+  colsum_finalize2_kernel<<<(9 * C + 127) / 128, 128, 0, stream>>>(partial, ctas, 9LL * C, 9 * C, grad, accumulate);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}

@@ -1,0 +1,230 @@
+"""Forward / backward schedule of the HTR-VT encoder on the sm_100a kernels.
+
+One explicit kernel sequence (no autograd graph inside): forward() records the activations the
+backward needs in a context, backward() walks the layers in reverse and writes fp32 gradients for
+every trainable parameter.  Data layout in HBM:
+  * stem activations   NHWC bf16 (channels innermost => the implicit-GEMM A operand is a TMA box);
+  * token stream       fp32 [B*T, D] residual, bf16 copies only as GEMM operands;
+  * weights            fp32 masters in the nn.Parameters (reference layouts: OIHW, [out,in]);
+                       bf16 operand copies ([Cout, taps, Cin] / [out, in]) are re-packed every forward,
+                       because SAM perturbs the masters in place twice per iteration.
+Reference semantics: model_v1/model/HTR_VT.py:222-241 and model_v1/model/resnet18.py:73-84.
+"""
+import torch
+
+from . import ops
+
+STEM_LAYERS = (("layer1", (2, 1)), ("layer2", (2, 2)), ("layer3", (2, 2)))
+
+
+class _Ctx(object):
+    pass
+
+
+def _bn_args(sd, prefix):
+    return (sd[prefix + ".weight"], sd[prefix + ".bias"], sd[prefix + ".running_mean"], sd[prefix + ".running_var"],
+            sd[prefix + ".num_batches_tracked"])
+
+
+class Engine(object):
+    """Stateless w.r.t. parameters: every call receives the module's current tensors by name."""
+
+    def __init__(self, embed_dim, depth, num_heads, nb_cls, ln_eps=1e-6, variant="v1"):
+        self.D, self.depth, self.H, self.C = embed_dim, depth, num_heads, nb_cls
+        self.hd = embed_dim // num_heads
+        self.ln_eps = ln_eps
+        self.variant = variant
+        if self.hd != 128:
+            raise ops.HtrvtError("attention kernel is specialised for head_dim 128 (got %d)" % self.hd)
+        if embed_dim % 256 or nb_cls < 2:
+            raise ops.HtrvtError("embed_dim must be a multiple of 256")
+
+    # ------------------------------------------------------------------------------------------
+    def _bn(self, sd, prefix, partial, count, training):
+        g, b, rm, rv, nbt = _bn_args(sd, prefix)
+        return ops.bn_finalize(partial if training else None, count, g, b, rm, rv, nbt, training)
+
+    def _conv(self, x, wp, ks, stride, training):
+        N, H, W, _ = x.shape
+        stats = None
+        if training:
+            rows = ops.conv_stats_rows(N, H, W, ks, stride[0], stride[1])
+            stats = torch.empty((rows, 2, wp.shape[0]), dtype=torch.float32, device=x.device)
+        y = ops.conv_fwd(x, wp, ks, stride[0], stride[1], stats=stats)
+        return y, stats
+
+    def forward(self, sd, image, mask, training, save):
+        """sd: name -> tensor (parameters + BN buffers); image fp32 [B,1,H,W]; mask fp32 [T] or None.
+        Returns (logits fp32 [B,T,C], ctx | None)."""
+        if image.dim() != 4 or image.shape[1] != 1:
+            raise ValueError("expected image [B, 1, H, W]")
+        if not image.is_cuda:
+            raise ops.HtrvtError("htr-vt_b200 runs on CUDA only (no CPU fallback)")
+        B, _, Hi, Wi = image.shape
+        D, C = self.D, self.C
+        ctx = _Ctx() if save else None
+        image = image.contiguous().float()
+
+        # ---- weights: bf16 operand copies -----------------------------------------------------
+        wp = {}
+        for k, v in sd.items():
+            if k.startswith("patch_embed.") and k.endswith("weight") and v.dim() == 4 and v.shape[1] > 1:
+                wp[k] = ops.pack_conv_weight(v)
+            elif v.dim() == 2 and k.endswith(".weight"):
+                wp[k] = ops.cast_bf16(v)
+
+        # ---- stem -----------------------------------------------------------------------------
+        x0, _, _ = ops.sample_ln_fwd(image.view(B, Hi, Wi), torch.bfloat16, 1e-5)
+        c1raw, part = ops.conv1_fwd(x0, sd["patch_embed.conv1.weight"], training)
+        st1 = self._bn(sd, "patch_embed.bn1", part, B * (Hi // 2) * Wi, training)
+        x, idx1 = ops.pool_fwd(c1raw, st1, save)
+        blocks = []
+        for lname, stride in STEM_LAYERS:
+            for bi in range(2):
+                p = "patch_embed.%s.%d" % (lname, bi)
+                s = stride if bi == 0 else (1, 1)
+                r1, pt1 = self._conv(x, wp[p + ".conv1.weight"], 3, s, training)
+                cnt = r1.numel() // r1.shape[-1]
+                sa = self._bn(sd, p + ".bn1", pt1, cnt, training)
+                a1 = ops.bn_act_fwd(r1, sa, True)
+                r2, pt2 = self._conv(a1, wp[p + ".conv2.weight"], 3, (1, 1), training)
+                sb = self._bn(sd, p + ".bn2", pt2, cnt, training)
+                rd = sdn = None
+                if (p + ".downsample.0.weight") in sd:
+                    rd, ptd = self._conv(x, wp[p + ".downsample.0.weight"], 1, s, training)
+                    sdn = self._bn(sd, p + ".downsample.1", ptd, cnt, training)
+                    y = ops.bn_act_fwd(r2, sb, True, raw2=rd, st2=sdn)
+                else:
+                    y = ops.bn_act_fwd(r2, sb, True, res=x)
+                if save:
+                    blocks.append((p, s, x, r1, sa, a1, r2, sb, rd, sdn, y))
+                x = y
+        Bx, Hx, Wx, Cx = x.shape
+        tok, idx2 = ops.pool_fwd(x, None, save)                  # [B, Hx/2, T, D]
+        if tok.shape[1] != 1 or Cx != D:
+            raise ValueError("stem output height must pool to 1 (image height 64)")
+        T = Wx
+        M = B * T
+
+        # ---- tokens ---------------------------------------------------------------------------
+        pos = sd.get("pos_embed")
+        if pos is not None and pos.shape[1] != T:
+            raise ValueError("pos_embed has %d positions, sequence has %d" % (pos.shape[1], T))
+        xs = ops.tokens_fwd(tok, mask, sd["mask_token"], pos, B, T, D)
+        scale = self.hd ** -0.5
+        tblocks = []
+        for i in range(self.depth):
+            p = "blocks.%d" % i
+            h1, m1, r1s = ops.row_ln_fwd(xs, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], self.ln_eps)
+            qkv = torch.empty((3, B, self.H, T, self.hd), dtype=torch.bfloat16, device=xs.device)
+            ops.gemm_tn(h1, wp[p + ".attn.qkv.weight"], qkv, bias=sd[p + ".attn.qkv.bias"], qkv=(B, T, self.H, self.hd))
+            o = torch.empty((M, D), dtype=torch.bfloat16, device=xs.device)
+            lse = torch.empty((B, self.H, T), dtype=torch.float32, device=xs.device)
+            ops.attention_fwd(qkv, o.view(B, T, D), lse, scale)
+            x2 = torch.empty_like(xs)
+            ops.gemm_tn(o, wp[p + ".attn.proj.weight"], x2, bias=sd[p + ".attn.proj.bias"], resid=xs)
+            h2, m2, r2s = ops.row_ln_fwd(x2, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], self.ln_eps)
+            hid = wp[p + ".mlp.fc1.weight"].shape[0]
+            a = torch.empty((M, hid), dtype=torch.bfloat16, device=xs.device)
+            u = torch.empty((M, hid), dtype=torch.bfloat16, device=xs.device)
+            ops.gemm_tn(h2, wp[p + ".mlp.fc1.weight"], a, bias=sd[p + ".mlp.fc1.bias"], out2=u)
+            x3 = torch.empty_like(xs)
+            ops.gemm_tn(a, wp[p + ".mlp.fc2.weight"], x3, bias=sd[p + ".mlp.fc2.bias"], resid=x2)
+            if save:
+                tblocks.append((p, xs, h1, m1, r1s, qkv, o, lse, x2, h2, m2, r2s, a, u))
+            xs = x3
+        hf, mf, rf = ops.row_ln_fwd(xs, sd["norm.weight"], sd["norm.bias"], self.ln_eps)
+        raw_logits = torch.empty((M, C), dtype=torch.float32, device=xs.device)
+        ops.gemm_tn(hf, wp["head.weight"], raw_logits, bias=sd["head.bias"])
+        if self.variant == "v1":
+            logits, _, rl = ops.sample_ln_fwd(raw_logits.view(B, T, C), torch.float32, 1e-5)
+        else:
+            logits, rl = raw_logits.view(B, T, C), None
+        if save:
+            ctx.B, ctx.T, ctx.Hi, ctx.Wi = B, T, Hi, Wi
+            ctx.wp, ctx.x0, ctx.c1raw, ctx.st1, ctx.idx1 = wp, x0, c1raw, st1, idx1
+            ctx.blocks, ctx.l3_shape, ctx.idx2, ctx.mask = blocks, (Bx, Hx, Wx, Cx), idx2, mask
+            ctx.tblocks, ctx.x_final, ctx.hf, ctx.mf, ctx.rf = tblocks, xs, hf, mf, rf
+            ctx.logits, ctx.rl = logits, rl
+        return logits, ctx
+
+    # ------------------------------------------------------------------------------------------
+    def backward(self, sd, ctx, dlogits, grads):
+        """dlogits fp32 [B,T,C]; grads: name -> fp32 tensor (accumulated into, +=)."""
+        B, T, D, C = ctx.B, ctx.T, self.D, self.C
+        M = B * T
+        wp = ctx.wp
+        dev = dlogits.device
+        dlogits = dlogits.contiguous().float()
+        ldc = (C + 7) // 8 * 8
+        if self.variant == "v1":
+            draw = ops.sample_ln_bwd(dlogits, ctx.logits, ctx.rl, C, ldc)          # bf16 [M, ldc]
+        else:
+            draw = torch.zeros((M, ldc), dtype=torch.bfloat16, device=dev)
+            draw[:, :C] = ops.cast_bf16(dlogits.view(M, C))
+        dr = draw[:, :C]
+        ops.linear_wgrad(dr, ctx.hf, grads["head.weight"])
+        ops.colsum_bf16(dr, grads["head.bias"])
+        dhf = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+        ops.gemm_nn(dr, wp["head.weight"], dhf)
+        gx = torch.empty((M, D), dtype=torch.float32, device=dev)
+        ops.row_ln_bwd(dhf, ctx.x_final, ctx.mf, ctx.rf, sd["norm.weight"], gx, False, grads["norm.weight"],
+                       grads["norm.bias"])
+        scale = self.hd ** -0.5
+        for (p, x1, h1, m1, r1s, qkv, o, lse, x2, h2, m2, r2s, a, u) in reversed(ctx.tblocks):
+            gy = ops.cast_bf16(gx)
+            ops.linear_wgrad(gy, a, grads[p + ".mlp.fc2.weight"])
+            ops.colsum_bf16(gy, grads[p + ".mlp.fc2.bias"])
+            da = torch.empty_like(a)
+            ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], da)
+            du = ops.gelu_bwd(da, u)
+            ops.linear_wgrad(du, h2, grads[p + ".mlp.fc1.weight"])
+            ops.colsum_bf16(du, grads[p + ".mlp.fc1.bias"])
+            dh2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+            ops.gemm_nn(du, wp[p + ".mlp.fc1.weight"], dh2)
+            ops.row_ln_bwd(dh2, x2, m2, r2s, sd[p + ".norm2.weight"], gx, True, grads[p + ".norm2.weight"],
+                           grads[p + ".norm2.bias"])
+            gy = ops.cast_bf16(gx)
+            ops.linear_wgrad(gy, o, grads[p + ".attn.proj.weight"])
+            ops.colsum_bf16(gy, grads[p + ".attn.proj.bias"])
+            do = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+            ops.gemm_nn(gy, wp[p + ".attn.proj.weight"], do)
+            dqkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
+            ops.attention_bwd(qkv, o.view(B, T, D), do.view(B, T, D), lse, dqkv.view(B, T, 3, self.H, self.hd), scale)
+            ops.linear_wgrad(dqkv, h1, grads[p + ".attn.qkv.weight"])
+            ops.colsum_bf16(dqkv, grads[p + ".attn.qkv.bias"])
+            dh1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+            ops.gemm_nn(dqkv, wp[p + ".attn.qkv.weight"], dh1)
+            ops.row_ln_bwd(dh1, x1, m1, r1s, sd[p + ".norm1.weight"], gx, True, grads[p + ".norm1.weight"],
+                           grads[p + ".norm1.bias"])
+        dtok = ops.tokens_bwd(gx, ctx.mask, grads["mask_token"].view(-1), B, T, D)
+        g = ops.pool_bwd(dtok.view(B, 1, T, D), ctx.idx2, ctx.l3_shape)
+
+        # ---- stem blocks ------------------------------------------------------------------------
+        for (p, s, xin, r1, sa, a1, r2, sb, rd, sdn, y) in reversed(ctx.blocks):
+            has_ds = rd is not None
+            d2, dd, gz = ops.bn_bwd(
+                g, y, r2, sb, sd[p + ".bn2.weight"], grads[p + ".bn2.weight"], grads[p + ".bn2.bias"],
+                raw_b=rd, st_b=sdn, gamma_b=sd[p + ".downsample.1.weight"] if has_ds else None,
+                dgamma_b=grads[p + ".downsample.1.weight"] if has_ds else None,
+                dbeta_b=grads[p + ".downsample.1.bias"] if has_ds else None, want_gz=not has_ds)
+            ops.conv_wgrad(d2, a1, 3, 1, 1, grads[p + ".conv2.weight"])
+            da1 = ops.conv_dgrad(d2, wp[p + ".conv2.weight"], tuple(a1.shape), 3, 1, 1)
+            d1, _, _ = ops.bn_bwd(da1, a1, r1, sa, sd[p + ".bn1.weight"], grads[p + ".bn1.weight"],
+                                  grads[p + ".bn1.bias"])
+            ops.conv_wgrad(d1, xin, 3, s[0], s[1], grads[p + ".conv1.weight"])
+            if has_ds:
+                gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1])
+                ops.conv_wgrad(dd, xin, 1, s[0], s[1], grads[p + ".downsample.0.weight"])
+                ops.conv_dgrad(dd, wp[p + ".downsample.0.weight"], tuple(xin.shape), 1, s[0], s[1], dx=gin,
+                               accumulate=True)
+            else:
+                gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1], dx=gz,
+                                     accumulate=True)
+            g = gin
+        # ---- stem head: pool -> relu -> bn1 -> conv1 ---------------------------------------------
+        gc = ops.pool_bwd(g, ctx.idx1, tuple(ctx.c1raw.shape), raw=ctx.c1raw, st=ctx.st1)
+        dc1, _, _ = ops.bn_bwd(gc, None, ctx.c1raw, ctx.st1, sd["patch_embed.bn1.weight"],
+                               grads["patch_embed.bn1.weight"], grads["patch_embed.bn1.bias"])
+        ops.conv1_wgrad(dc1, ctx.x0, grads["patch_embed.conv1.weight"])
+        return grads

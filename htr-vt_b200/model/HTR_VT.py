@@ -1,0 +1,169 @@
+"""`HTR_VT.create_model(nb_cls, img_size)` with the reference's module surface
+(model_v1/model/HTR_VT.py:139-254): same constructor arguments, same
+`forward(x, mask_ratio=0.0, max_span_length=1, use_masking=False) -> [B, T, nb_cls]`, same
+state_dict keys / shapes, gradients delivered into ordinary nn.Parameter.grad.
+
+The nn.Modules below are PARAMETER CONTAINERS only (they give the state_dict its reference names and
+default initialisers); all arithmetic runs in the hand-written sm_100a kernels through engine.Engine.
+There is no CPU path: calling forward on CPU tensors raises.
+"""
+import math
+from functools import partial
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..engine import Engine
+
+
+def _sincos_table(embed_dim, grid_size):
+    """Fixed 2-D sin/cos code over the token axis: first half of the channels encodes n % grid_w, second
+    half n // grid_w, each as [sin | cos] of pos * 10000^(-k/(D/4)) (model_v1/model/HTR_VT.py:86-131)."""
+    gh, gw = int(grid_size[0]), int(grid_size[1])
+    n = np.arange(gh * gw)
+    quarter = embed_dim // 4
+    omega = 1.0 / 10000 ** (np.arange(quarter, dtype=np.float64) / quarter)
+    parts = []
+    for pos in ((n % gw).astype(np.float32), (n // gw).astype(np.float32)):
+        ang = pos[:, None].astype(np.float64) * omega[None, :]
+        parts += [np.sin(ang), np.cos(ang)]
+    return torch.from_numpy(np.concatenate(parts, axis=1)).float().unsqueeze(0)
+
+
+class _Residual(nn.Module):
+    """Parameter container for one residual unit of the stem (names: conv1/bn1/conv2/bn2/downsample)."""
+
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout, eps=1e-5)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout, eps=1e-5)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout, eps=1e-5))
+
+
+class _Stem(nn.Module):
+    """Parameter container for the truncated ResNet-18 stem (model_v1/model/resnet18.py:42-71)."""
+
+    def __init__(self, nb_feat):
+        super().__init__()
+        c1, c2, c3 = nb_feat // 4, nb_feat // 2, nb_feat
+        self.conv1 = nn.Conv2d(1, c1, 3, (2, 1), 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(c1, eps=1e-5)
+        self.layer1 = nn.Sequential(_Residual(c1, c1, (2, 1)), _Residual(c1, c1, 1))
+        self.layer2 = nn.Sequential(_Residual(c1, c2, 2), _Residual(c2, c2, 1))
+        self.layer3 = nn.Sequential(_Residual(c2, c3, 2), _Residual(c3, c3, 1))
+
+
+class _Attn(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.qkv = nn.Linear(dim, 3 * dim, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, mlp_ratio, norm_layer):
+        super().__init__()
+        self.norm1 = norm_layer(dim, elementwise_affine=True)
+        self.attn = _Attn(dim)
+        self.norm2 = norm_layer(dim, elementwise_affine=True)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+
+
+class _EncoderFn(torch.autograd.Function):
+    """Whole-encoder autograd node: forward/backward are Engine kernel schedules."""
+
+    @staticmethod
+    def forward(ctx, module, image, mask, names, *params):
+        sd = module._tensor_table()
+        save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        logits, ectx = module.engine.forward(sd, image, mask, module.training, save)
+        ctx.module, ctx.ectx, ctx.names, ctx.sd = module, ectx, names, sd
+        ctx.shapes = [(p.shape, p.requires_grad) for p in params]
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        if ctx.ectx is None:
+            raise RuntimeError("backward through a forward that did not record activations")
+        grads = {}
+        for name, (shape, req) in zip(ctx.names, ctx.shapes):
+            grads[name] = torch.zeros(shape, dtype=torch.float32, device=dlogits.device)
+        ctx.module.engine.backward(ctx.sd, ctx.ectx, dlogits, grads)
+        ctx.ectx = None
+        out = tuple(grads[n] if req else None for n, (_, req) in zip(ctx.names, ctx.shapes))
+        return (None, None, None, None) + out
+
+
+class MaskedAutoencoderViT(nn.Module):
+    """HTR-VT encoder.  Constructor mirrors the reference (model_v1/model/HTR_VT.py:143-151)."""
+
+    def __init__(self, nb_cls=80, img_size=[512, 32], patch_size=[8, 32], embed_dim=1024, depth=24, num_heads=16,
+                 mlp_ratio=4., norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.patch_embed = _Stem(embed_dim)
+        self.grid_size = [img_size[0] // patch_size[0], img_size[1] // patch_size[1]]
+        self.embed_dim = embed_dim
+        self.num_patches = self.grid_size[0] * self.grid_size[1]
+        self.num_heads = num_heads
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.num_patches, embed_dim), requires_grad=False)
+        self.blocks = nn.ModuleList([_Block(embed_dim, mlp_ratio, norm_layer) for _ in range(depth)])
+        self.norm = norm_layer(embed_dim, elementwise_affine=True)
+        self.head = nn.Linear(embed_dim, nb_cls)
+        eps = getattr(self.norm, "eps", 1e-6)
+        self.engine = Engine(embed_dim, depth, num_heads, nb_cls, ln_eps=eps, variant="v1")
+        self._init_parameters()
+
+    def _init_parameters(self):
+        self.pos_embed.data.copy_(_sincos_table(self.embed_dim, self.grid_size))
+        nn.init.normal_(self.mask_token, std=.02)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _tensor_table(self):
+        table = {k: v for k, v in self.named_parameters()}
+        table.update({k: v for k, v in self.named_buffers()})
+        return table
+
+    @staticmethod
+    def span_mask(L, mask_ratio, max_span_length):
+        """Same draws, in the same order, from the CPU default generator as the reference's
+        generate_span_mask (model_v1/model/HTR_VT.py:202-210): int(L*ratio)//span spans, one mask per batch."""
+        mask = torch.ones(L)
+        for _ in range(int(L * mask_ratio) // max_span_length):
+            idx = int(torch.randint(L - max_span_length, (1,)))
+            mask[idx:idx + max_span_length] = 0
+        return mask
+
+    def forward(self, x, mask_ratio=0.0, max_span_length=1, use_masking=False):
+        if not x.is_cuda:
+            raise ops.HtrvtError("htr-vt_b200 MaskedAutoencoderViT.forward needs CUDA tensors (no CPU fallback)")
+        mask = None
+        if use_masking:
+            L = x.shape[-1] // 4
+            mask = self.span_mask(L, mask_ratio, max_span_length).to(x.device, non_blocking=True)
+        names, params = zip(*[(k, v) for k, v in self.named_parameters()])
+        return _EncoderFn.apply(self, x, mask, names, *params)
+
+
+def create_model(nb_cls, img_size, **kwargs):
+    """Reference factory (model_v1/model/HTR_VT.py:244-254): fixed architecture hyper-parameters."""
+    return MaskedAutoencoderViT(nb_cls, img_size=img_size, patch_size=(4, 64), embed_dim=768, depth=4, num_heads=6,
+                                mlp_ratio=4, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)

@@ -129,6 +129,26 @@ def conv_wgrad(dy, x, ks, sh, sw, grad_oihw, accumulate=True):
 
 
 # ------------------------------------------------------------------------------------------------
+# Attention
+# ------------------------------------------------------------------------------------------------
+def attention_fwd(qkv, out, lse, scale):
+    """qkv bf16 [3,B,H,T,hd] -> out bf16 [B,T,H*hd]; lse fp32 [B,H,T]."""
+    _need_cuda(qkv, out)
+    _, B, H, T, hd = qkv.shape
+    check(lib().htrvt_attention_fwd(_p(qkv), B, H, T, hd, scale, _p(out), _p(lse), _stream()), "htrvt_attention_fwd")
+    return out
+
+
+def attention_bwd(qkv, out, dout, lse, dqkv, scale):
+    """-> dqkv bf16 [B,T,3,H,hd] (token-major gradient of the qkv projection output)."""
+    _need_cuda(qkv, out, dout, lse, dqkv)
+    _, B, H, T, hd = qkv.shape
+    check(lib().htrvt_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), B, H, T, hd, scale, _p(dqkv), _stream()),
+          "htrvt_attention_bwd")
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------------------
 # CTC + decode
 # ------------------------------------------------------------------------------------------------
 def ctc_loss_grad(x, targets, input_lengths, target_lengths, *, layout, is_logprob, want_grad=True,
@@ -206,3 +226,180 @@ def ctc_collapse(index_flat, lengths, n_character):
     check(lib().htrvt_ctc_collapse(_p(idx), int(idx.dtype == torch.int64), _p(ln), B, max(Tmax, 1), n_character,
                                    _p(ids), _p(lens), _stream()), "htrvt_ctc_collapse")
     return ids, lens
+
+
+# ------------------------------------------------------------------------------------------------
+# Normalisation / elementwise
+# ------------------------------------------------------------------------------------------------
+def _f32(n, dev):
+    return torch.empty(n, dtype=torch.float32, device=dev)
+
+
+def sample_ln_fwd(x, out_dtype, eps=1e-5):
+    """x fp32 [B, ...] -> y (same shape, out_dtype), mean [B], rstd [B]."""
+    _need_cuda(x)
+    B = x.shape[0]
+    N = x.numel() // B
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    mean, rstd = _f32(B, x.device), _f32(B, x.device)
+    check(lib().htrvt_sample_ln_fwd(_p(x), _p(y), int(out_dtype == torch.bfloat16), _p(mean), _p(rstd), B, N, eps,
+                                    _stream()), "htrvt_sample_ln_fwd")
+    return y, mean, rstd
+
+
+def sample_ln_bwd(dy, y, rstd, C, ld_out):
+    """dy, y fp32 [B, T, C] -> dx bf16 [B*T, ld_out] (columns >= C zero)."""
+    B = dy.shape[0]
+    N = dy.numel() // B
+    dx = torch.empty((B * (N // C), ld_out), dtype=torch.bfloat16, device=dy.device)
+    check(lib().htrvt_sample_ln_bwd(_p(dy), _p(y), _p(rstd), _p(dx), B, N, C, ld_out, _stream()),
+          "htrvt_sample_ln_bwd")
+    return dx
+
+
+def row_ln_fwd(x, gamma, beta, eps):
+    M, D = x.shape
+    y = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
+    mean, rstd = _f32(M, x.device), _f32(M, x.device)
+    check(lib().htrvt_row_ln_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, D, eps, _stream()),
+          "htrvt_row_ln_fwd")
+    return y, mean, rstd
+
+
+def row_ln_bwd(dy, x, mean, rstd, gamma, gx, accumulate, dgamma, dbeta):
+    M, D = x.shape
+    ctas = lib().htrvt_row_ln_bwd_ctas(M)
+    partial = workspace(ctas * 2 * D * 4, x.device)
+    check(lib().htrvt_row_ln_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(gx), int(accumulate), _p(dgamma),
+                                 _p(dbeta), _p(partial), M, D, _stream()), "htrvt_row_ln_bwd")
+    return gx
+
+
+def tokens_fwd(tok, mask, mask_token, pos, B, T, D):
+    x = torch.empty((B * T, D), dtype=torch.float32, device=tok.device)
+    check(lib().htrvt_tokens_fwd(_p(tok), _p(mask), _p(mask_token if mask is not None else None), _p(pos), _p(x), B, T,
+                                 D, _stream()), "htrvt_tokens_fwd")
+    return x
+
+
+def tokens_bwd(gx, mask, dmask_token, B, T, D):
+    dtok = torch.empty((B, T, D), dtype=torch.bfloat16, device=gx.device)
+    partial = workspace(T * D * 4, gx.device)
+    check(lib().htrvt_tokens_bwd(_p(gx), _p(mask), _p(dtok), _p(dmask_token if mask is not None else None),
+                                 _p(partial), B, T, D, _stream()), "htrvt_tokens_bwd")
+    return dtok
+
+
+def gelu_bwd(da, u):
+    du = torch.empty_like(u)
+    check(lib().htrvt_gelu_bwd(_p(da), _p(u), _p(du), u.numel(), _stream()), "htrvt_gelu_bwd")
+    return du
+
+
+def colsum_bf16(a, out, accumulate=True):
+    M, N = a.shape
+    rows = lib().htrvt_colsum_rows(M)
+    partial = workspace(rows * N * 4, a.device)
+    check(lib().htrvt_colsum_bf16(_p(a), a.stride(0), M, N, _p(out), int(accumulate), _p(partial), _stream()),
+          "htrvt_colsum_bf16")
+    return out
+
+
+def cast_bf16(src, dst=None):
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(lib().htrvt_cast_bf16(_p(src), _p(dst), src.numel(), _stream()), "htrvt_cast_bf16")
+    return dst
+
+
+def pack_conv_weight(w, dst=None):
+    """fp32 OIHW -> bf16 [Cout, kh*kw, Cin]."""
+    Cout, Cin, kh, kw = w.shape
+    if dst is None:
+        dst = torch.empty((Cout, kh * kw, Cin), dtype=torch.bfloat16, device=w.device)
+    check(lib().htrvt_pack_conv_weight(_p(w), _p(dst), Cout, Cin, kh * kw, _stream()), "htrvt_pack_conv_weight")
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------
+# Stem
+# ------------------------------------------------------------------------------------------------
+def conv1_fwd(x, w, want_stats):
+    """x bf16 [B,H,W]; w fp32 [C,1,3,3] -> raw bf16 [B,H/2,W,C], partial stats [R,2,C] | None."""
+    B, H, W = x.shape
+    C = w.shape[0]
+    raw = torch.empty((B, H // 2, W, C), dtype=torch.bfloat16, device=x.device)
+    R = B * (H // 2) * ((W + 127) // 128)
+    partial = torch.empty((R, 2, C), dtype=torch.float32, device=x.device) if want_stats else None
+    check(lib().htrvt_conv1_fwd(_p(x), _p(w), _p(raw), _p(partial), B, H, W, C, _stream()), "htrvt_conv1_fwd")
+    return raw, partial
+
+
+def bn_finalize(partial, count, gamma, beta, running_mean, running_var, nbt, training, momentum=0.1, eps=1e-5):
+    """-> (mean, rstd, scale, shift) fp32 [C] each (one [4,C] buffer)."""
+    C = gamma.numel()
+    out = torch.empty((4, C), dtype=torch.float32, device=gamma.device)
+    R = partial.shape[0] if partial is not None else 0
+    check(lib().htrvt_bn_finalize(_p(partial), R, float(count), _p(gamma), _p(beta), _p(running_mean),
+                                  _p(running_var), _p(nbt), momentum, eps, int(training), _p(out[0]), _p(out[1]),
+                                  _p(out[2]), _p(out[3]), C, _stream()), "htrvt_bn_finalize")
+    return out
+
+
+def bn_act_fwd(raw, st, relu, res=None, raw2=None, st2=None):
+    C = raw.shape[-1]
+    P = raw.numel() // C
+    y = torch.empty_like(raw)
+    check(lib().htrvt_bn_act_fwd(_p(raw), _p(st[2]), _p(st[3]), _p(res), _p(raw2),
+                                 _p(st2[2] if st2 is not None else None), _p(st2[3] if st2 is not None else None),
+                                 _p(y), P, C, int(relu), _stream()), "htrvt_bn_act_fwd")
+    return y
+
+
+def pool_fwd(raw, st, want_idx):
+    B, H, W, C = raw.shape
+    Ho = (H - 1) // 2 + 1
+    out = torch.empty((B, Ho, W, C), dtype=torch.bfloat16, device=raw.device)
+    idx = torch.empty((B, Ho, W, C), dtype=torch.uint8, device=raw.device) if want_idx else None
+    check(lib().htrvt_pool_fwd(_p(raw), _p(st[2] if st is not None else None), _p(st[3] if st is not None else None),
+                               _p(out), _p(idx), B, H, W, C, _stream()), "htrvt_pool_fwd")
+    return out, idx
+
+
+def pool_bwd(gout, idx, in_shape, raw=None, st=None):
+    B, H, W, C = in_shape
+    gin = torch.empty(in_shape, dtype=torch.bfloat16, device=gout.device)
+    check(lib().htrvt_pool_bwd(_p(gout), int(gout.dtype == torch.float32), _p(idx), _p(raw),
+                               _p(st[2] if st is not None else None), _p(st[3] if st is not None else None), _p(gin),
+                               B, H, W, C, _stream()), "htrvt_pool_bwd")
+    return gin
+
+
+def bn_bwd(g, y, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=None, gamma_b=None, dgamma_b=None,
+           dbeta_b=None, want_gz=False):
+    """-> (d_a, d_b | None, gz | None), all bf16 with the shape of raw_a."""
+    C = raw_a.shape[-1]
+    P = raw_a.numel() // C
+    dev = raw_a.device
+    d_a = torch.empty_like(raw_a)
+    d_b = torch.empty_like(raw_a) if raw_b is not None else None
+    gz = torch.empty_like(raw_a) if want_gz else None
+    ctas = lib().htrvt_bn_bwd_ctas(P)
+    partial = workspace(ctas * 3 * C * 4 + 4 * C * 4, dev)
+    coef = partial[ctas * 3 * C * 4:]
+    z = None
+    check(lib().htrvt_bn_bwd(_p(g), _p(y), _p(raw_a), _p(st_a[0]), _p(st_a[1]), _p(gamma_a), _p(dgamma_a),
+                             _p(dbeta_a), _p(d_a), _p(raw_b), _p(st_b[0] if st_b is not None else z),
+                             _p(st_b[1] if st_b is not None else z), _p(gamma_b), _p(dgamma_b), _p(dbeta_b), _p(d_b),
+                             _p(gz), P, C, _p(partial), _p(coef), _stream()), "htrvt_bn_bwd")
+    return d_a, d_b, gz
+
+
+def conv1_wgrad(dy, x, grad, accumulate=True):
+    B, H, W = x.shape
+    C = dy.shape[-1]
+    ctas = lib().htrvt_conv1_wgrad_ctas()
+    partial = workspace(ctas * 9 * C * 4, x.device)
+    check(lib().htrvt_conv1_wgrad(_p(dy), _p(x), _p(grad), int(accumulate), _p(partial), B, H, W, C, _stream()),
+          "htrvt_conv1_wgrad")
+    return grad

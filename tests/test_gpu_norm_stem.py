@@ -1,0 +1,200 @@
+"""GPU parity: normalisation / elementwise / stem kernels (through the C ABI) vs fp32 torch references."""
+from importlib import import_module
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def ops():
+    import htrvt_b200  # noqa: F401
+    return import_module("htr-vt_b200.ops")
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+
+
+def test_sample_ln_fwd_bwd():
+    o = ops()
+    torch.manual_seed(0)
+    x = torch.rand(5, 1, 64, 512, device="cuda") * 3 + 1
+    y, mean, rstd = o.sample_ln_fwd(x.view(5, 64, 512), torch.bfloat16)
+    ref = F.layer_norm(x, x.shape[1:], None, None, 1e-5)
+    assert _rel(y.view_as(ref), ref) < 1e-2
+    lg = torch.randn(4, 128, 80, device="cuda", requires_grad=True)
+    yl, _, rl = o.sample_ln_fwd(lg.detach(), torch.float32)
+    refl = F.layer_norm(lg, lg.shape[1:], None, None, 1e-5)
+    assert _rel(yl, refl) < 1e-5
+    dy = torch.randn_like(lg)
+    refl.backward(dy)
+    dx = o.sample_ln_bwd(dy, yl, rl, 80, 88)
+    assert dx.shape == (4 * 128, 88)
+    assert _rel(dx[:, :80].reshape(4, 128, 80), lg.grad) < 1e-2
+    assert float(dx[:, 80:].abs().max()) == 0.0
+
+
+def test_row_ln_fwd_bwd():
+    o = ops()
+    torch.manual_seed(1)
+    M, D = 1000, 768
+    x = (torch.randn(M, D, device="cuda") * 2 + 0.5).requires_grad_(True)
+    g = (torch.rand(D, device="cuda") + 0.5).requires_grad_(True)
+    b = torch.randn(D, device="cuda").requires_grad_(True)
+    y, mean, rstd = o.row_ln_fwd(x.detach(), g.detach(), b.detach(), 1e-6)
+    ref = F.layer_norm(x, (D,), g, b, 1e-6)
+    assert _rel(y, ref) < 1e-2
+    dy = torch.randn(M, D, device="cuda").bfloat16()
+    ref.backward(dy.float())
+    gx = torch.ones(M, D, device="cuda")
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    o.row_ln_bwd(dy, x.detach(), mean, rstd, g.detach(), gx, True, dg, db)
+    assert _rel(gx - 1, x.grad) < 1e-4
+    assert _rel(dg, g.grad) < 1e-4 and _rel(db, b.grad) < 1e-4
+    o.row_ln_bwd(dy, x.detach(), mean, rstd, g.detach(), gx, False, dg, db)
+    assert _rel(gx, x.grad) < 1e-4
+    assert _rel(dg, 2 * g.grad) < 1e-4
+
+
+def test_tokens_gelu_colsum_cast():
+    o = ops()
+    torch.manual_seed(2)
+    B, T, D = 6, 32, 256
+    tok = torch.randn(B, T, D, device="cuda").bfloat16()
+    mask = (torch.rand(T, device="cuda") > 0.4).float()
+    mt = torch.randn(D, device="cuda")
+    pos = torch.randn(T, D, device="cuda")
+    x = o.tokens_fwd(tok, mask, mt, pos, B, T, D)
+    m = mask.view(1, T, 1)
+    ref = tok.float() * m + (1 - m) * mt + pos
+    assert _rel(x.view(B, T, D), ref) < 1e-6
+    x2 = o.tokens_fwd(tok, None, mt, None, B, T, D)
+    assert _rel(x2.view(B, T, D), tok.float()) < 1e-6
+    gx = torch.randn(B * T, D, device="cuda")
+    dmt = torch.zeros(D, device="cuda")
+    dtok = o.tokens_bwd(gx, mask, dmt, B, T, D)
+    assert _rel(dtok, gx.view(B, T, D) * m) < 1e-2
+    assert _rel(dmt, (gx.view(B, T, D) * (1 - m)).sum((0, 1))) < 1e-5
+    u = (torch.randn(512, 1024, device="cuda") * 2).bfloat16()
+    da = torch.randn(512, 1024, device="cuda").bfloat16()
+    uf = u.float().requires_grad_(True)
+    F.gelu(uf).backward(da.float())
+    assert _rel(o.gelu_bwd(da, u), uf.grad) < 1e-2
+    a = torch.randn(3000, 776, device="cuda").bfloat16()
+    out = torch.ones(770, device="cuda")
+    o.colsum_bf16(a[:, :770], out, accumulate=True)
+    assert _rel(out - 1, a[:, :770].float().sum(0)) < 1e-5
+    w = torch.randn(64, 32, 3, 3, device="cuda")
+    assert torch.equal(o.pack_conv_weight(w), w.permute(0, 2, 3, 1).reshape(64, 9, 32).bfloat16())
+    assert torch.equal(o.cast_bf16(w), w.bfloat16())
+
+
+def test_stem_head_conv1_bn_pool():
+    o = ops()
+    torch.manual_seed(3)
+    B, H, W, C = 3, 64, 256, 64
+    x = torch.randn(B, H, W, device="cuda").bfloat16()
+    w = torch.randn(C, 1, 3, 3, device="cuda") * 0.3
+    raw, part = o.conv1_fwd(x, w, True)
+    xr = x.float().view(B, 1, H, W)
+    wr = w.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, (2, 1), 1)
+    assert _rel(raw.permute(0, 3, 1, 2), ref) < 1e-2
+    gamma = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device="cuda") * 0.1).requires_grad_(True)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    st = o.bn_finalize(part, B * (H // 2) * W, gamma.detach(), beta.detach(), rm, rv, nbt, True)
+    rawf = raw.float().permute(0, 3, 1, 2).detach().requires_grad_(True)     # BN on what is stored
+    rm2, rv2 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    bn = F.batch_norm(rawf, rm2, rv2, gamma, beta, True, 0.1, 1e-5)
+    assert int(nbt) == 1
+    assert _rel(rm, rm2) < 1e-4 and _rel(rv, rv2) < 1e-4
+    act = F.relu(bn)
+    pooled_ref = F.max_pool2d(act, 3, (2, 1), 1)
+    pooled, idx = o.pool_fwd(raw, st, True)
+    assert _rel(pooled.permute(0, 3, 1, 2), pooled_ref) < 1e-2
+    # eval-mode statistics path
+    st_eval = o.bn_finalize(None, 1, gamma.detach(), beta.detach(), rm, rv, nbt, False)
+    ev = F.batch_norm(rawf, rm, rv, gamma, beta, False, 0.1, 1e-5)
+    y_eval = o.bn_act_fwd(raw, st_eval, True)
+    assert _rel(y_eval.permute(0, 3, 1, 2), F.relu(ev)) < 1e-2
+    # backward: pool -> relu -> bn -> conv1 weight
+    gout = torch.randn_like(pooled)
+    pooled_ref.backward(gout.float().permute(0, 3, 1, 2))
+    gc = o.pool_bwd(gout, idx, tuple(raw.shape), raw=raw, st=st)
+    dgam, dbet = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dc1, _, _ = o.bn_bwd(gc, None, raw, st, gamma.detach(), dgam, dbet)
+    assert _rel(dgam, gamma.grad) < 2e-2 and _rel(dbet, beta.grad) < 2e-2
+    assert _rel(dc1.permute(0, 3, 1, 2), rawf.grad) < 3e-2
+    ref.backward(dc1.float().permute(0, 3, 1, 2))
+    gw = torch.zeros_like(w)
+    o.conv1_wgrad(dc1, x, gw)
+    assert _rel(gw, wr.grad) < 1e-3
+
+
+@pytest.mark.parametrize("ds", [False, True])
+def test_bn_act_and_bn_bwd_block(ds):
+    o = ops()
+    torch.manual_seed(4)
+    B, H, W, C = 2, 8, 64, 128
+    P = B * H * W
+    r2 = torch.randn(B, H, W, C, device="cuda").bfloat16()
+    rd = torch.randn(B, H, W, C, device="cuda").bfloat16()
+    xin = torch.randn(B, H, W, C, device="cuda").bfloat16()
+    g2 = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
+    b2 = (torch.randn(C, device="cuda") * 0.1).requires_grad_(True)
+    gd = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
+    bd = (torch.randn(C, device="cuda") * 0.1).requires_grad_(True)
+
+    def stats(raw, g, b):
+        f = raw.float().view(P, C)
+        part = torch.stack([f.sum(0), (f * f).sum(0)]).view(1, 2, C).contiguous()
+        return o.bn_finalize(part, P, g.detach(), b.detach(), None, None, None, True)
+
+    s2, sdn = stats(r2, g2, b2), stats(rd, gd, bd)
+    r2f = r2.float().requires_grad_(True)
+    rdf = rd.float().requires_grad_(True)
+    xf = xin.float().requires_grad_(True)
+
+    def bn(v, g, b):
+        return F.batch_norm(v.permute(0, 3, 1, 2), None, None, g, b, True, 0.1, 1e-5).permute(0, 2, 3, 1)
+
+    if ds:
+        ref = F.relu(bn(r2f, g2, b2) + bn(rdf, gd, bd))
+        y = o.bn_act_fwd(r2, s2, True, raw2=rd, st2=sdn)
+    else:
+        ref = F.relu(bn(r2f, g2, b2) + xf)
+        y = o.bn_act_fwd(r2, s2, True, res=xin)
+    assert _rel(y, ref) < 1e-2
+    g = torch.randn_like(y)
+    ref.backward(g.float())
+    dg2, db2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dgd, dbd = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    if ds:
+        d2, dd, gz = o.bn_bwd(g, y, r2, s2, g2.detach(), dg2, db2, raw_b=rd, st_b=sdn, gamma_b=gd.detach(),
+                              dgamma_b=dgd, dbeta_b=dbd)
+        assert _rel(dd, rdf.grad) < 3e-2 and _rel(dgd, gd.grad) < 2e-2 and _rel(dbd, bd.grad) < 2e-2
+    else:
+        d2, dd, gz = o.bn_bwd(g, y, r2, s2, g2.detach(), dg2, db2, want_gz=True)
+        assert _rel(gz, xf.grad) < 2e-2
+    assert _rel(d2, r2f.grad) < 3e-2 and _rel(dg2, g2.grad) < 2e-2 and _rel(db2, b2.grad) < 2e-2
+
+
+def test_final_pool_fwd_bwd():
+    o = ops()
+    torch.manual_seed(5)
+    B, H, W, C = 4, 2, 32, 256
+    x = torch.relu(torch.randn(B, H, W, C, device="cuda")).bfloat16()
+    xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.max_pool2d(xf, 3, (2, 1), 1)
+    out, idx = o.pool_fwd(x, None, True)
+    assert torch.equal(out.permute(0, 3, 1, 2).float(), ref)
+    g = torch.randn(B, 1, W, C, device="cuda")
+    ref.backward(g.permute(0, 3, 1, 2))
+    gin = o.pool_bwd(g.bfloat16(), idx, (B, H, W, C))
+    want = xf.grad.permute(0, 2, 3, 1)
+    # ties among equal maxima (zeros after ReLU) go to the first element in both implementations
+    assert _rel(gin, want) < 2e-2
