@@ -13,8 +13,12 @@
 #define HTRVT_ERR_WORKSPACE (-5)
 #define HTRVT_ERR_DRIVER (-6)
 
+// every kernel launch of the library is followed by HTRVT_LAUNCH_CHECK(): it counts the launch
+// (htrvt_launch_count(), used by bench.py's gpu_launches) and converts launch errors to a status.
+extern "C" unsigned long long htrvt_launch_counter;
 #define HTRVT_LAUNCH_CHECK()                                   \
   do {                                                         \
+    ++htrvt_launch_counter;                                    \
     cudaError_t e__ = cudaGetLastError();                      \
     if (e__ != cudaSuccess) return HTRVT_ERR_LAUNCH;           \
   } while (0)

@@ -350,7 +350,7 @@ extern "C" int htrvt_ctc_loss_grad(const float* x, long long x_stride_b, long lo
                                    float* nll, float* grad, long long g_stride_b, long long g_stride_t,
                                    const float* grad_scale, float grad_scale_const, void* workspace,
                                    size_t workspace_bytes, cudaStream_t stream) {
-  if (B <= 0 || T <= 0 || C <= 1 || !x || !nll || !targets || !target_lengths) return HTRVT_ERR_SHAPE;
+  if (B <= 0 || T <= 0 || C <= 1 || !x || !nll || !target_lengths) return HTRVT_ERR_SHAPE;   // targets may be null when every label is empty
   int lmax = max_target_len < 0 || max_target_len > T ? T : max_target_len;
   CtcParams P;
   P.x = x; P.x_sb = x_stride_b; P.x_st = x_stride_t;

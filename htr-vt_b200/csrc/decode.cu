@@ -132,3 +132,6 @@ extern "C" int htrvt_ctc_collapse(const void* index, int index_is_int64, const i
 }
 
 extern "C" int htrvt_version() { return 100; }   // 0.1.0
+
+unsigned long long htrvt_launch_counter = 0;
+extern "C" unsigned long long htrvt_launch_count() { return htrvt_launch_counter; }

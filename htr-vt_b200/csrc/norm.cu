@@ -386,6 +386,7 @@ extern "C" int htrvt_row_ln_bwd(const void* dy_bf16, const float* x, const float
     return HTRVT_ERR_SHAPE;
   HTRVT_LAUNCH_CHECK();
   colsum_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial, ctas, 2LL * D, D, dgamma, 1);
+  HTRVT_LAUNCH_CHECK();
   colsum_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial + D, ctas, 2LL * D, D, dbeta, 1);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;

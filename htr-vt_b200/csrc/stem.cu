@@ -28,7 +28,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // conv1: x [B,H,W] bf16 (one channel) -> raw [B,H/2,W,C] bf16, stride (2,1), pad 1, + channel statistics
 // grid (W/128 tiles, H/2, B); blockDim = C threads: thread -> channel pair (t % (C/2)), pixel half (t / (C/2))
 // ------------------------------------------------------------------------------------------------
-__global__ void conv1_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+__global__ void conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                  __nv_bfloat16* __restrict__ raw, float* __restrict__ partial, int H, int W, int C) {
   __shared__ float in[3][132];
   extern __shared__ float red[];                     // [2][C] statistics of the second pixel half
@@ -36,8 +36,7 @@ __global__ void conv1_fwd_kernel(const __nv_bfloat16* __restrict__ x, const floa
   for (int i = threadIdx.x; i < 3 * 130; i += blockDim.x) {
     const int r = i / 130, c = i - r * 130;
     const int hh = 2 * ho + r - 1, ww = w0 + c - 1;
-    in[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                   ? __bfloat162float(x[(static_cast<long long>(n) * H + hh) * W + ww]) : 0.f;
+    in[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(static_cast<long long>(n) * H + hh) * W + ww] : 0.f;
   }
   const int half_c = C / 2;
   const int cp = threadIdx.x % half_c, ph = threadIdx.x / half_c;
@@ -400,7 +399,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const _
 // conv1 weight gradient: dw[c][kh][kw] = sum dy[n,ho,wo,c] * x[n, 2ho+kh-1, wo+kw-1]; partial [cta][9][C]
 // persistent CTAs over (n, ho, w-tile) work items; thread -> channel pair / pixel half as in conv1_fwd
 // ------------------------------------------------------------------------------------------------
-__global__ void conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+__global__ void conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
                                    float* __restrict__ partial, int B, int H, int W, int C) {
   __shared__ float in[3][132];
   extern __shared__ float red[];                      // [18][C/2] for the second pixel half
@@ -420,8 +419,7 @@ __global__ void conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const _
     for (int i = threadIdx.x; i < 3 * 130; i += blockDim.x) {
       const int r = i / 130, c = i - r * 130;
       const int hh = 2 * ho + r - 1, ww = w0 + c - 1;
-      in[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                     ? __bfloat162float(x[(static_cast<long long>(n) * H + hh) * W + ww]) : 0.f;
+      in[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(static_cast<long long>(n) * H + hh) * W + ww] : 0.f;
     }
     __syncthreads();
     const __nv_bfloat16* drow = dy + ((static_cast<long long>(n) * Ho + ho) * W + w0) * C + 2 * cp;
@@ -473,11 +471,11 @@ static inline int grid_for(long long n, int block) {
 }
 
 // partial: fp32 [B * (H/2) * ceil(W/128)][2][C]  (null: no statistics, eval mode)
-extern "C" int htrvt_conv1_fwd(const void* x_bf16, const float* w, void* raw_bf16, float* partial, int B, int H,
+extern "C" int htrvt_conv1_fwd(const float* x, const float* w, void* raw_bf16, float* partial, int B, int H,
                                int W, int C, cudaStream_t stream) {
   if (B <= 0 || (H & 1) || W <= 0 || (C & 1) || C > 1024 || C < 2) return HTRVT_ERR_SHAPE;
   dim3 grid((W + 127) / 128, H / 2, B);
-  conv1_fwd_kernel<<<grid, C, 2 * C * sizeof(float), stream>>>(static_cast<const __nv_bfloat16*>(x_bf16), w,
+  conv1_fwd_kernel<<<grid, C, 2 * C * sizeof(float), stream>>>(x, w,
                                                                static_cast<__nv_bfloat16*>(raw_bf16), partial, H, W, C);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
@@ -587,12 +585,12 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* y, const void* raw_a, con
 extern "C" int htrvt_conv1_wgrad_ctas() { return 148 * 4; }
 
 // grad [C][1][3][3] fp32 (+=); partial: fp32 [htrvt_conv1_wgrad_ctas()][9*C]
-extern "C" int htrvt_conv1_wgrad(const void* dy_bf16, const void* x_bf16, float* grad, int accumulate,
+extern "C" int htrvt_conv1_wgrad(const void* dy_bf16, const float* x, float* grad, int accumulate,
                                  float* partial, int B, int H, int W, int C, cudaStream_t stream) {
   if (B <= 0 || (H & 1) || W <= 0 || (C & 1) || C > 1024 || C < 2) return HTRVT_ERR_SHAPE;
   const int ctas = htrvt_conv1_wgrad_ctas();
   conv1_wgrad_kernel<<<ctas, C, 18 * (C / 2) * sizeof(float), stream>>>(
-      static_cast<const __nv_bfloat16*>(dy_bf16), static_cast<const __nv_bfloat16*>(x_bf16), partial, B, H, W, C);
+      static_cast<const __nv_bfloat16*>(dy_bf16), x, partial, B, H, W, C);
   HTRVT_LAUNCH_CHECK();
   colsum_finalize2_kernel<<<(9 * C + 127) / 128, 128, 0, stream>>>(partial, ctas, 9LL * C, 9 * C, grad, accumulate);
   HTRVT_LAUNCH_CHECK();

@@ -74,7 +74,7 @@ class Engine(object):
                 wp[k] = ops.cast_bf16(v)
 
         # ---- stem -----------------------------------------------------------------------------
-        x0, _, _ = ops.sample_ln_fwd(image.view(B, Hi, Wi), torch.bfloat16, 1e-5)
+        x0, _, _ = ops.sample_ln_fwd(image.view(B, Hi, Wi), torch.float32, 1e-5)
         c1raw, part = ops.conv1_fwd(x0, sd["patch_embed.conv1.weight"], training)
         st1 = self._bn(sd, "patch_embed.bn1", part, B * (Hi // 2) * Wi, training)
         x, idx1 = ops.pool_fwd(c1raw, st1, save)
@@ -149,7 +149,7 @@ class Engine(object):
         return logits, ctx
 
     # ------------------------------------------------------------------------------------------
-    def backward(self, sd, ctx, dlogits, grads):
+    def backward(self, sd, ctx, dlogits, grads, on_stage=None):
         """dlogits fp32 [B,T,C]; grads: name -> fp32 tensor (accumulated into, +=)."""
         B, T, D, C = ctx.B, ctx.T, self.D, self.C
         M = B * T
@@ -197,6 +197,8 @@ class Engine(object):
             ops.gemm_nn(dqkv, wp[p + ".attn.qkv.weight"], dh1)
             ops.row_ln_bwd(dh1, x1, m1, r1s, sd[p + ".norm1.weight"], gx, True, grads[p + ".norm1.weight"],
                            grads[p + ".norm1.bias"])
+        if on_stage is not None:
+            on_stage("transformer")          # every blocks.* / norm / head gradient is final
         dtok = ops.tokens_bwd(gx, ctx.mask, grads["mask_token"].view(-1), B, T, D)
         g = ops.pool_bwd(dtok.view(B, 1, T, D), ctx.idx2, ctx.l3_shape)
 

@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..ddp import GradAllReduce, segment_bounds
 from ..engine import Engine
 
 
@@ -86,9 +87,8 @@ class _EncoderFn(torch.autograd.Function):
     """Whole-encoder autograd node: forward/backward are Engine kernel schedules."""
 
     @staticmethod
-    def forward(ctx, module, image, mask, names, *params):
+    def forward(ctx, module, image, mask, names, save, *params):
         sd = module._tensor_table()
-        save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         logits, ectx = module.engine.forward(sd, image, mask, module.training, save)
         ctx.module, ctx.ectx, ctx.names, ctx.sd = module, ectx, names, sd
         ctx.shapes = [(p.shape, p.requires_grad) for p in params]
@@ -98,13 +98,24 @@ class _EncoderFn(torch.autograd.Function):
     def backward(ctx, dlogits):
         if ctx.ectx is None:
             raise RuntimeError("backward through a forward that did not record activations")
-        grads = {}
-        for name, (shape, req) in zip(ctx.names, ctx.shapes):
-            grads[name] = torch.zeros(shape, dtype=torch.float32, device=dlogits.device)
-        ctx.module.engine.backward(ctx.sd, ctx.ectx, dlogits, grads)
+        module = ctx.module
+        numels = [int(torch.Size(shape).numel()) for shape, _ in ctx.shapes]
+        offs, split = segment_bounds(ctx.names, numels)
+        flat = torch.zeros(offs[-1], dtype=torch.float32, device=dlogits.device)
+        grads = {n: flat[offs[i]:offs[i + 1]].view(shape) for i, (n, (shape, _)) in enumerate(zip(ctx.names, ctx.shapes))}
+        sync = module.grad_sync
+
+        def on_stage(stage):
+            if sync is not None and stage == "transformer":
+                sync.reduce_async(flat[split:])          # overlaps the stem backward
+
+        module.engine.backward(ctx.sd, ctx.ectx, dlogits, grads, on_stage)
+        if sync is not None:
+            sync.reduce_async(flat[:split])
+            sync.finish()
         ctx.ectx = None
         out = tuple(grads[n] if req else None for n, (_, req) in zip(ctx.names, ctx.shapes))
-        return (None, None, None, None) + out
+        return (None, None, None, None, None) + out
 
 
 class MaskedAutoencoderViT(nn.Module):
@@ -125,6 +136,7 @@ class MaskedAutoencoderViT(nn.Module):
         self.head = nn.Linear(embed_dim, nb_cls)
         eps = getattr(self.norm, "eps", 1e-6)
         self.engine = Engine(embed_dim, depth, num_heads, nb_cls, ln_eps=eps, variant="v1")
+        self.grad_sync = None           # set by enable_data_parallel(): NCCL all-reduce inside backward
         self._init_parameters()
 
     def _init_parameters(self):
@@ -141,6 +153,20 @@ class MaskedAutoencoderViT(nn.Module):
         table = {k: v for k, v in self.named_parameters()}
         table.update({k: v for k, v in self.named_buffers()})
         return table
+
+    def enable_data_parallel(self, group=None):
+        """Average gradients over the ranks of `group` inside backward (batch sharding, one process per GPU)."""
+        self.grad_sync = GradAllReduce(group)
+        return self
+
+    def __deepcopy__(self, memo):           # EMA deep-copies the model (utils.py:130): keep comm objects shared
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = v if k == "grad_sync" else copy.deepcopy(v, memo)
+        return new
 
     @staticmethod
     def span_mask(L, mask_ratio, max_span_length):
@@ -160,7 +186,8 @@ class MaskedAutoencoderViT(nn.Module):
             L = x.shape[-1] // 4
             mask = self.span_mask(L, mask_ratio, max_span_length).to(x.device, non_blocking=True)
         names, params = zip(*[(k, v) for k, v in self.named_parameters()])
-        return _EncoderFn.apply(self, x, mask, names, *params)
+        save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _EncoderFn.apply(self, x, mask, names, save, *params)
 
 
 def create_model(nb_cls, img_size, **kwargs):

@@ -155,7 +155,7 @@ def ctc_loss_grad(x, targets, input_lengths, target_lengths, *, layout, is_logpr
                   max_target_len=-1, grad_scale=None, grad_scale_const=1.0):
     """x: fp32 logits [B,T,C] (layout 'btc') or log-probs [T,B,C] (layout 'tbc').
     Returns (nll [B] fp32, grad with the shape of x or None)."""
-    _need_cuda(x, targets, target_lengths)
+    _need_cuda(x)                      # lengths / targets may live on the host (valid.py:33 passes a CPU preds_size)
     if x.dtype != torch.float32 or x.stride(-1) != 1:
         raise HtrvtError("ctc_loss_grad expects fp32 input with a contiguous class axis")
     if layout == "btc":
@@ -325,7 +325,7 @@ def pack_conv_weight(w, dst=None):
 # Stem
 # ------------------------------------------------------------------------------------------------
 def conv1_fwd(x, w, want_stats):
-    """x bf16 [B,H,W]; w fp32 [C,1,3,3] -> raw bf16 [B,H/2,W,C], partial stats [R,2,C] | None."""
+    """x fp32 [B,H,W]; w fp32 [C,1,3,3] -> raw bf16 [B,H/2,W,C], partial stats [R,2,C] | None."""
     B, H, W = x.shape
     C = w.shape[0]
     raw = torch.empty((B, H // 2, W, C), dtype=torch.bfloat16, device=x.device)
@@ -403,3 +403,75 @@ def conv1_wgrad(dy, x, grad, accumulate=True):
     check(lib().htrvt_conv1_wgrad(_p(dy), _p(x), _p(grad), int(accumulate), _p(partial), B, H, W, C, _stream()),
           "htrvt_conv1_wgrad")
     return grad
+
+
+def launch_count() -> int:
+    """Kernels launched by the library so far (host-side counter in the C library)."""
+    fn = lib().htrvt_launch_count
+    fn.restype = ctypes.c_ulonglong
+    return int(fn())
+
+
+# ------------------------------------------------------------------------------------------------
+# Optional per-op CUDA-event profile (bench.py's roofline leg, tools/): PROFILE = [] enables it.
+# ------------------------------------------------------------------------------------------------
+PROFILE = None
+
+
+def _flops(name, a, kw):
+    try:
+        if name == "gemm_tn":
+            return 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0]
+        if name == "gemm_nn":
+            return 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[1]
+        if name == "linear_wgrad":
+            return 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[1]
+        if name == "conv_fwd":
+            x, w, ks, sh, sw = a[:5]
+            Ho, Wo = conv_out_hw(x.shape[1], x.shape[2], ks, sh, sw)
+            return 2.0 * x.shape[0] * Ho * Wo * w.shape[0] * ks * ks * x.shape[3]
+        if name == "conv_dgrad":
+            dy, w, xs, ks = a[:4]
+            return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * xs[3]
+        if name == "conv_wgrad":
+            dy, x, ks = a[:3]
+            return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * x.shape[3]
+        if name == "attention_fwd":
+            _, B, H, T, hd = a[0].shape
+            return 4.0 * B * H * T * T * hd
+        if name == "attention_bwd":
+            _, B, H, T, hd = a[0].shape
+            return 10.0 * B * H * T * T * hd
+    except Exception:
+        pass
+    return 0.0
+
+
+def _instrument():
+    import functools
+    g = globals()
+    names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "attention_fwd",
+             "attention_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd",
+             "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_bwd", "colsum_bf16", "cast_bf16",
+             "pack_conv_weight", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",
+             "conv1_wgrad"]
+    for name in names:
+        fn = g[name]
+
+        def make(fn=fn, name=name):
+            @functools.wraps(fn)
+            def wrapper(*a, **kw):
+                if PROFILE is None:
+                    return fn(*a, **kw)
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(*a, **kw)
+                e1.record()
+                PROFILE.append((name, _flops(name, a, kw), e0, e1))
+                return r
+            return wrapper
+        g[name] = make()
+
+
+_instrument()
