@@ -27,7 +27,7 @@ struct GemmCfg {
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kStatsBytes = 8 * 2 * 16 * 4;                  // per-warp column partials
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
-                                    2 * BN * 4 * 4 /* stats: [4 quadrants][2][BN] */;
+                                    2 * BN * 4 * 4 /* stats: [4 quadrants][2][BN] */ + 2 * 1024 * 4 /* per-CTA column sums */;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -89,6 +89,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   float* stat_smem = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);   // [4][2][BN]
+  float* stat_acc = stat_smem + 8 * BN;                                                    // [2][1024]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = P.tiles_m * P.tiles_n * (P.kind == 0 ? 1 : P.n_taps * P.splits);
@@ -188,6 +189,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int r = quad * 32 + lane;          // tile row
     constexpr int kColsPerWarp = BN / 2;
     int as = 0; uint32_t aphase = 0;
+    if (P.flags & EPI_STATS) {
+      for (int c = threadIdx.x - 64; c < 2048; c += 256) stat_acc[c] = 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     for (int id = blockIdx.x; id < total_tiles; id += gridDim.x) {
       const TileCoord tc = decode_tile(P, id);
       const int n0 = tc.n_tile * BN;
@@ -352,14 +357,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float ssum = 0.f, qsum = 0.f;
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) { ssum += stat_smem[(qd * 2) * BN + c]; qsum += stat_smem[(qd * 2 + 1) * BN + c]; }
-            float* dst = P.stats + static_cast<long long>(tc.m_tile) * 2 * P.N_valid;
-            dst[n0 + c] = ssum;
-            dst[P.N_valid + n0 + c] = qsum;
+            stat_acc[n0 + c] += ssum;                      // column n0+c is owned by exactly one thread per tile
+            stat_acc[1024 + n0 + c] += qsum;
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       as ^= 1; if (as == 0) aphase ^= 1;
+    }
+    if (P.flags & EPI_STATS) {                           // one partial row per CTA: stats[cta][2][N]
+      float* dst = P.stats + static_cast<long long>(blockIdx.x) * 2 * P.N_valid;
+      for (int c = threadIdx.x - 64; c < P.N_valid; c += 256) {
+        dst[c] = stat_acc[c];
+        dst[P.N_valid + c] = stat_acc[1024 + c];
+      }
     }
   }
   tc_fence_before();
@@ -635,6 +646,7 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
                               int sh, int sw, void* y, float* stats_partial, int flags, cudaStream_t stream) {
   const int pad = ks / 2;
   if ((Cin % 64) || (Cout & 7) || (W % sw) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
+  if (stats_partial && Cout > 1024) return HTRVT_ERR_SHAPE;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
   const int bn = pick_bn(Cout);
   CUtensorMap ta, tb;
@@ -656,7 +668,8 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
 extern "C" int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw) {
   const int pad = ks / 2;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
-  return ((Wo + kBM - 1) / kBM) * Ho * NB;      // rows of the [tiles_m][2][Cout] partial-statistics buffer
+  (void)NB; (void)Ho; (void)Wo;
+  return num_sms();   // rows of the [ctas][2][Cout] partial-statistics buffer (upper bound)
 }
 
 // dx[NB,H,W,Cin] (= or +=) conv_transpose(dy[NB,Ho,Wo,Cout], w): one GEMM per output parity class.

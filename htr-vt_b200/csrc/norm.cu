@@ -192,10 +192,16 @@ __global__ void __launch_bounds__(256) row_ln_bwd_kernel(const __nv_bfloat16* __
 // out[c] (+)= sum_r partial[r*stride + c]  (deterministic second stage of every column reduction)
 __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int R, long long stride, int Ccols,
                                        float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Ccols) return;
+  __shared__ float sh[8][32];                           // block = 32 columns x 8 row lanes
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lr = threadIdx.x >> 5;
   float s = 0.f;
-  for (int r = 0; r < R; ++r) s += partial[r * stride + c];
+  if (c < Ccols)
+    for (int r = lr; r < R; r += 8) s += partial[r * stride + c];
+  sh[lr][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (lr != 0 || c >= Ccols) return;
+  s = 0.f;
+  for (int k = 0; k < 8; ++k) s += sh[k][threadIdx.x];
   out[c] = accumulate ? out[c] + s : s;
 }
 
@@ -385,9 +391,9 @@ extern "C" int htrvt_row_ln_bwd(const void* dy_bf16, const float* x, const float
   else
     return HTRVT_ERR_SHAPE;
   HTRVT_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial, ctas, 2LL * D, D, dgamma, 1);
+  colsum_finalize_kernel<<<(D + 31) / 32, 256, 0, stream>>>(partial, ctas, 2LL * D, D, dgamma, 1);
   HTRVT_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial + D, ctas, 2LL * D, D, dbeta, 1);
+  colsum_finalize_kernel<<<(D + 31) / 32, 256, 0, stream>>>(partial + D, ctas, 2LL * D, D, dbeta, 1);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
@@ -411,7 +417,7 @@ extern "C" int htrvt_tokens_bwd(const float* gx, const float* mask, void* dtok_b
                                            B, T, D);
   HTRVT_LAUNCH_CHECK();
   if (want) {
-    colsum_finalize_kernel<<<(D + 127) / 128, 128, 0, stream>>>(partial, T, D, D, dmask_token, 1);
+    colsum_finalize_kernel<<<(D + 31) / 32, 256, 0, stream>>>(partial, T, D, D, dmask_token, 1);
     HTRVT_LAUNCH_CHECK();
   }
   return HTRVT_OK;
@@ -440,7 +446,7 @@ extern "C" int htrvt_colsum_bf16(const void* a, long long ld, int M, int N, floa
   dim3 grid((N + 255) / 256, gy);
   colsum_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a), ld, M, N, rows, partial);
   HTRVT_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<(N + 127) / 128, 128, 0, stream>>>(partial, gy, N, N, out, accumulate);
+  colsum_finalize_kernel<<<(N + 31) / 32, 256, 0, stream>>>(partial, gy, N, N, out, accumulate);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }

@@ -29,38 +29,42 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // grid (W/128 tiles, H/2, B); blockDim = C threads: thread -> channel pair (t % (C/2)), pixel half (t / (C/2))
 // ------------------------------------------------------------------------------------------------
 __global__ void conv1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                 __nv_bfloat16* __restrict__ raw, float* __restrict__ partial, int H, int W, int C) {
+                                 __nv_bfloat16* __restrict__ raw, float* __restrict__ partial, int B, int H, int W,
+                                 int C) {
   __shared__ float in[3][132];
   extern __shared__ float red[];                     // [2][C] statistics of the second pixel half
-  const int w0 = blockIdx.x * 128, ho = blockIdx.y, n = blockIdx.z, Ho = H / 2;
-  for (int i = threadIdx.x; i < 3 * 130; i += blockDim.x) {
-    const int r = i / 130, c = i - r * 130;
-    const int hh = 2 * ho + r - 1, ww = w0 + c - 1;
-    in[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(static_cast<long long>(n) * H + hh) * W + ww] : 0.f;
-  }
+  const int w0 = blockIdx.x * 128, ho = blockIdx.y, Ho = H / 2;
   const int half_c = C / 2;
   const int cp = threadIdx.x % half_c, ph = threadIdx.x / half_c;
   float wa[9], wb[9];
 #pragma unroll
   for (int k = 0; k < 9; ++k) { wa[k] = w[(2 * cp) * 9 + k]; wb[k] = w[(2 * cp + 1) * 9 + k]; }
-  __syncthreads();
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  __nv_bfloat16* orow = raw + ((static_cast<long long>(n) * Ho + ho) * W + w0) * C + 2 * cp;
-  for (int p = ph * 64; p < ph * 64 + 64; ++p) {
-    if (w0 + p >= W) break;
-    float a = 0.f, b = 0.f;
+  for (int n = blockIdx.z; n < B; n += gridDim.z) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 130; i += blockDim.x) {
+      const int r = i / 130, c = i - r * 130;
+      const int hh = 2 * ho + r - 1, ww = w0 + c - 1;
+      in[r][c] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(static_cast<long long>(n) * H + hh) * W + ww] : 0.f;
+    }
+    __syncthreads();
+    __nv_bfloat16* orow = raw + ((static_cast<long long>(n) * Ho + ho) * W + w0) * C + 2 * cp;
+    for (int p = ph * 64; p < ph * 64 + 64; ++p) {
+      if (w0 + p >= W) break;
+      float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
+      for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const float v = in[kh][p + kw];
-        a = fmaf(v, wa[kh * 3 + kw], a);
-        b = fmaf(v, wb[kh * 3 + kw], b);
-      }
-    const uint32_t u = pack_bf16(a, b);
-    *reinterpret_cast<uint32_t*>(orow + static_cast<long long>(p) * C) = u;
-    const float2 r = unpack_bf16(u);                 // statistics of what is stored
-    s0 += r.x; s1 += r.y; q0 += r.x * r.x; q1 += r.y * r.y;
+        for (int kw = 0; kw < 3; ++kw) {
+          const float v = in[kh][p + kw];
+          a = fmaf(v, wa[kh * 3 + kw], a);
+          b = fmaf(v, wb[kh * 3 + kw], b);
+        }
+      const uint32_t u = pack_bf16(a, b);
+      *reinterpret_cast<uint32_t*>(orow + static_cast<long long>(p) * C) = u;
+      const float2 r = unpack_bf16(u);                 // statistics of what is stored
+      s0 += r.x; s1 += r.y; q0 += r.x * r.x; q1 += r.y * r.y;
+    }
   }
   if (!partial) return;
   if (ph == 1) {
@@ -68,7 +72,7 @@ __global__ void conv1_fwd_kernel(const float* __restrict__ x, const float* __res
   }
   __syncthreads();
   if (ph == 0) {
-    const long long cta = (static_cast<long long>(n) * gridDim.y + ho) * gridDim.x + blockIdx.x;
+    const long long cta = (static_cast<long long>(blockIdx.z) * gridDim.y + ho) * gridDim.x + blockIdx.x;
     float* dst = partial + cta * 2 * C;
     dst[2 * cp] = s0 + red[2 * cp];
     dst[2 * cp + 1] = s1 + red[2 * cp + 1];
@@ -86,16 +90,25 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int R, dou
                                    long long* __restrict__ num_batches_tracked, float momentum, float eps,
                                    int training, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                    float* __restrict__ scale_out, float* __restrict__ shift_out, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
-  if (c >= C) return;
-  float mean, var;
-  if (training) {
-    double s = 0.0, q = 0.0;
-    for (int r = 0; r < R; ++r) {
+  // block = 32 channels x 8 row lanes
+  __shared__ double sh[2][8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lr = threadIdx.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
+  double s = 0.0, q = 0.0;
+  if (training && c < C) {
+    for (int r = lr; r < R; r += 8) {
       s += partial[(static_cast<long long>(r) * 2) * C + c];
       q += partial[(static_cast<long long>(r) * 2 + 1) * C + c];
     }
+  }
+  sh[0][lr][threadIdx.x & 31] = s;
+  sh[1][lr][threadIdx.x & 31] = q;
+  __syncthreads();
+  if (lr != 0 || c >= C) return;
+  float mean, var;
+  if (training) {
+    s = 0.0; q = 0.0;
+    for (int k = 0; k < 8; ++k) { s += sh[0][k][threadIdx.x]; q += sh[1][k][threadIdx.x]; }
     const double m = s / count;
     double v = q / count - m * m;
     if (v < 0.0) v = 0.0;
@@ -334,13 +347,20 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int R,
                                        float* __restrict__ coef_a, float* __restrict__ dgamma_a,
                                        float* __restrict__ dbeta_a, float* __restrict__ coef_b,
                                        float* __restrict__ dgamma_b, float* __restrict__ dbeta_b) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double sh[3][8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lr = threadIdx.x >> 5;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  for (int r = 0; r < R; ++r) {
-    const float* p = partial + static_cast<long long>(r) * 3 * C;
-    s0 += p[c]; s1 += p[C + c]; s2 += p[2 * C + c];
+  if (c < C) {
+    for (int r = lr; r < R; r += 8) {
+      const float* p = partial + static_cast<long long>(r) * 3 * C;
+      s0 += p[c]; s1 += p[C + c]; s2 += p[2 * C + c];
+    }
   }
+  sh[0][lr][threadIdx.x & 31] = s0; sh[1][lr][threadIdx.x & 31] = s1; sh[2][lr][threadIdx.x & 31] = s2;
+  __syncthreads();
+  if (lr != 0 || c >= C) return;
+  s0 = s1 = s2 = 0.0;
+  for (int k = 0; k < 8; ++k) { s0 += sh[0][k][threadIdx.x]; s1 += sh[1][k][threadIdx.x]; s2 += sh[2][k][threadIdx.x]; }
   coef_a[c] = static_cast<float>(s0 / count);
   coef_a[C + c] = static_cast<float>(s1 / count);
   if (dgamma_a) { dgamma_a[c] += static_cast<float>(s1); dbeta_a[c] += static_cast<float>(s0); }
@@ -454,10 +474,16 @@ __global__ void conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const f
 
 __global__ void colsum_finalize2_kernel(const float* __restrict__ partial, int R, long long stride, int n,
                                         float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+  __shared__ double sh[8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lr = threadIdx.x >> 5;
   double s = 0.0;
-  for (int r = 0; r < R; ++r) s += partial[r * stride + c];
+  if (c < n)
+    for (int r = lr; r < R; r += 8) s += partial[r * stride + c];
+  sh[lr][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (lr != 0 || c >= n) return;
+  s = 0.0;
+  for (int k = 0; k < 8; ++k) s += sh[k][threadIdx.x];
   out[c] = accumulate ? out[c] + static_cast<float>(s) : static_cast<float>(s);
 }
 
@@ -470,13 +496,15 @@ static inline int grid_for(long long n, int block) {
   return static_cast<int>(g < 1 ? 1 : (g > 148LL * 16 ? 148LL * 16 : g));
 }
 
-// partial: fp32 [B * (H/2) * ceil(W/128)][2][C]  (null: no statistics, eval mode)
+extern "C" int htrvt_conv1_fwd_zdim(int B) { return B < 8 ? B : 8; }
+
+// partial: fp32 [htrvt_conv1_fwd_zdim(B) * (H/2) * ceil(W/128)][2][C]  (null: no statistics, eval mode)
 extern "C" int htrvt_conv1_fwd(const float* x, const float* w, void* raw_bf16, float* partial, int B, int H,
                                int W, int C, cudaStream_t stream) {
   if (B <= 0 || (H & 1) || W <= 0 || (C & 1) || C > 1024 || C < 2) return HTRVT_ERR_SHAPE;
-  dim3 grid((W + 127) / 128, H / 2, B);
-  conv1_fwd_kernel<<<grid, C, 2 * C * sizeof(float), stream>>>(x, w,
-                                                               static_cast<__nv_bfloat16*>(raw_bf16), partial, H, W, C);
+  dim3 grid((W + 127) / 128, H / 2, htrvt_conv1_fwd_zdim(B));
+  conv1_fwd_kernel<<<grid, C, 2 * C * sizeof(float), stream>>>(x, w, static_cast<__nv_bfloat16*>(raw_bf16), partial,
+                                                               B, H, W, C);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
@@ -486,7 +514,7 @@ extern "C" int htrvt_bn_finalize(const float* partial, int R, double count, cons
                                  float momentum, float eps, int training, float* mean, float* rstd, float* scale,
                                  float* shift, int C, cudaStream_t stream) {
   if (C <= 0 || (training && (!partial || R <= 0))) return HTRVT_ERR_SHAPE;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, R, count, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(partial, R, count, gamma, beta, running_mean, running_var,
                                                           num_batches_tracked, momentum, eps, training, mean, rstd,
                                                           scale, shift, C);
   HTRVT_LAUNCH_CHECK();
@@ -569,7 +597,7 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* y, const void* raw_a, con
   HTRVT_LAUNCH_CHECK();
   float* coef_a = coef;
   float* coef_b = raw_b ? coef + 2 * C : nullptr;
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, ctas, static_cast<double>(P), C, coef_a,
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(partial, ctas, static_cast<double>(P), C, coef_a,
                                                               dgamma_a, dbeta_a, coef_b, dgamma_b, dbeta_b);
   HTRVT_LAUNCH_CHECK();
   const long long n8 = P * C / 8;
@@ -592,7 +620,7 @@ extern "C" int htrvt_conv1_wgrad(const void* dy_bf16, const float* x, float* gra
   conv1_wgrad_kernel<<<ctas, C, 18 * (C / 2) * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(dy_bf16), x, partial, B, H, W, C);
   HTRVT_LAUNCH_CHECK();
-  colsum_finalize2_kernel<<<(9 * C + 127) / 128, 128, 0, stream>>>(partial, ctas, 9LL * C, 9 * C, grad, accumulate);
+  colsum_finalize2_kernel<<<(9 * C + 31) / 32, 256, 0, stream>>>(partial, ctas, 9LL * C, 9 * C, grad, accumulate);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }

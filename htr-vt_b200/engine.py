@@ -49,7 +49,7 @@ class Engine(object):
         stats = None
         if training:
             rows = ops.conv_stats_rows(N, H, W, ks, stride[0], stride[1])
-            stats = torch.empty((rows, 2, wp.shape[0]), dtype=torch.float32, device=x.device)
+            stats = torch.zeros((rows, 2, wp.shape[0]), dtype=torch.float32, device=x.device)   # one row per CTA
         y = ops.conv_fwd(x, wp, ks, stride[0], stride[1], stats=stats)
         return y, stats
 
