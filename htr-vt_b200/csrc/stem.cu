@@ -342,16 +342,21 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const 
   }
 }
 
-// stage 2: coefficients k1 = sum g'/N, k2 = sum g' xhat / N; dgamma += sum g' xhat, dbeta += sum g'
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int R, double count, int C,
-                                       float* __restrict__ coef_a, float* __restrict__ dgamma_a,
-                                       float* __restrict__ dbeta_a, float* __restrict__ coef_b,
+// stage 2: dgamma += sum g' xhat, dbeta += sum g'; per-channel affine coefficients of stage 3:
+//   d_raw = gamma*rstd*(g' - k1 - xhat*k2) = A*g' + Bc*raw + Cc,  k1 = sum g'/N, k2 = sum g' xhat / N,
+//   A = gamma*rstd, Bc = -A*rstd*k2, Cc = -A*k1 + A*rstd*k2*mean.         coef layout [3][C]
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int R, double count, int C,
+                                       const float* __restrict__ gamma_a, const float* __restrict__ mean_a,
+                                       const float* __restrict__ rstd_a, float* __restrict__ coef_a,
+                                       float* __restrict__ dgamma_a, float* __restrict__ dbeta_a,
+                                       const float* __restrict__ gamma_b, const float* __restrict__ mean_b,
+                                       const float* __restrict__ rstd_b, float* __restrict__ coef_b,
                                        float* __restrict__ dgamma_b, float* __restrict__ dbeta_b) {
-  __shared__ double sh[3][8][32];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lr = threadIdx.x >> 5;
+  __shared__ double sh[3][32][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lr = threadIdx.x >> 5;      // 32 channels x 32 row lanes
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   if (c < C) {
-    for (int r = lr; r < R; r += 8) {
+    for (int r = lr; r < R; r += 32) {
       const float* p = partial + static_cast<long long>(r) * 3 * C;
       s0 += p[c]; s1 += p[C + c]; s2 += p[2 * C + c];
     }
@@ -360,31 +365,40 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int R,
   __syncthreads();
   if (lr != 0 || c >= C) return;
   s0 = s1 = s2 = 0.0;
-  for (int k = 0; k < 8; ++k) { s0 += sh[0][k][threadIdx.x]; s1 += sh[1][k][threadIdx.x]; s2 += sh[2][k][threadIdx.x]; }
-  coef_a[c] = static_cast<float>(s0 / count);
-  coef_a[C + c] = static_cast<float>(s1 / count);
-  if (dgamma_a) { dgamma_a[c] += static_cast<float>(s1); dbeta_a[c] += static_cast<float>(s0); }
+  for (int k = 0; k < 32; ++k) { s0 += sh[0][k][threadIdx.x]; s1 += sh[1][k][threadIdx.x]; s2 += sh[2][k][threadIdx.x]; }
+  {
+    const float k1 = static_cast<float>(s0 / count), k2 = static_cast<float>(s1 / count);
+    const float A = gamma_a[c] * rstd_a[c];
+    coef_a[c] = A;
+    coef_a[C + c] = -A * rstd_a[c] * k2;
+    coef_a[2 * C + c] = -A * k1 + A * rstd_a[c] * k2 * mean_a[c];
+    if (dgamma_a) { dgamma_a[c] += static_cast<float>(s1); dbeta_a[c] += static_cast<float>(s0); }
+  }
   if (coef_b) {
-    coef_b[c] = static_cast<float>(s0 / count);
-    coef_b[C + c] = static_cast<float>(s2 / count);
+    const float k1 = static_cast<float>(s0 / count), k2 = static_cast<float>(s2 / count);
+    const float A = gamma_b[c] * rstd_b[c];
+    coef_b[c] = A;
+    coef_b[C + c] = -A * rstd_b[c] * k2;
+    coef_b[2 * C + c] = -A * k1 + A * rstd_b[c] * k2 * mean_b[c];
     if (dgamma_b) { dgamma_b[c] += static_cast<float>(s2); dbeta_b[c] += static_cast<float>(s0); }
   }
 }
 
-// stage 3: d_raw = gamma*rstd * (g' - k1 - xhat*k2) for one or two BNs; optional gz = g' (identity residual)
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
-                                    const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mean_a,
-                                    const float* __restrict__ rstd_a, const float* __restrict__ gamma_a,
-                                    const float* __restrict__ coef_a, __nv_bfloat16* __restrict__ d_a,
-                                    const __nv_bfloat16* __restrict__ raw_b, const float* __restrict__ mean_b,
-                                    const float* __restrict__ rstd_b, const float* __restrict__ gamma_b,
-                                    const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ d_b,
-                                    __nv_bfloat16* __restrict__ gz, long long n8, int C) {
+// stage 3: d_raw = A*g' + Bc*raw + Cc for one or two BNs; optional gz = g' (identity-residual gradient)
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+  *reinterpret_cast<float4*>(f) = *reinterpret_cast<const float4*>(p);
+  *reinterpret_cast<float4*>(f + 4) = *reinterpret_cast<const float4*>(p + 4);
+}
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ raw_a,
+    const float* __restrict__ coef_a, __nv_bfloat16* __restrict__ d_a, const __nv_bfloat16* __restrict__ raw_b,
+    const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ d_b, __nv_bfloat16* __restrict__ gz, long long n8,
+    int C) {
   const int G = C / 8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % G) * 8;
-    float gv[8], xa[8], o[8];
+    float gv[8], xa[8], o[8], A[8], Bc[8], Cc[8];
     unpack8(*reinterpret_cast<const uint4*>(g + i * 8), gv);
     unpack8(*reinterpret_cast<const uint4*>(raw_a + i * 8), xa);
     if (y) {
@@ -394,22 +408,16 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const _
       for (int k = 0; k < 8; ++k) if (!(yv[k] > 0.f)) gv[k] = 0.f;
     }
     if (gz) *reinterpret_cast<uint4*>(gz + i * 8) = pack8(gv);
+    load8(coef_a + c, A); load8(coef_a + C + c, Bc); load8(coef_a + 2 * C + c, Cc);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float rs = rstd_a[c + k];
-      const float xh = (xa[k] - mean_a[c + k]) * rs;
-      o[k] = gamma_a[c + k] * rs * (gv[k] - coef_a[c + k] - xh * coef_a[C + c + k]);
-    }
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], gv[k], fmaf(Bc[k], xa[k], Cc[k]));
     *reinterpret_cast<uint4*>(d_a + i * 8) = pack8(o);
     if (raw_b) {
       float xb[8];
       unpack8(*reinterpret_cast<const uint4*>(raw_b + i * 8), xb);
+      load8(coef_b + c, A); load8(coef_b + C + c, Bc); load8(coef_b + 2 * C + c, Cc);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float rs = rstd_b[c + k];
-        const float xh = (xb[k] - mean_b[c + k]) * rs;
-        o[k] = gamma_b[c + k] * rs * (gv[k] - coef_b[c + k] - xh * coef_b[C + c + k]);
-      }
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], gv[k], fmaf(Bc[k], xb[k], Cc[k]));
       *reinterpret_cast<uint4*>(d_b + i * 8) = pack8(o);
     }
   }
@@ -443,17 +451,24 @@ __global__ void conv1_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const f
     }
     __syncthreads();
     const __nv_bfloat16* drow = dy + ((static_cast<long long>(n) * Ho + ho) * W + w0) * C + 2 * cp;
-    for (int p = ph * 64; p < ph * 64 + 64; ++p) {
-      if (w0 + p >= W) break;
-      const float2 d = unpack_bf16(*reinterpret_cast<const uint32_t*>(drow + static_cast<long long>(p) * C));
+    for (int p0 = ph * 64; p0 < ph * 64 + 64; p0 += 8) {
+      uint32_t dv[8];
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
+      for (int j = 0; j < 8; ++j)
+        dv[j] = (w0 + p0 + j < W) ? *reinterpret_cast<const uint32_t*>(drow + static_cast<long long>(p0 + j) * C) : 0u;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const float v = in[kh][p + kw];
-          ga[kh * 3 + kw] = fmaf(d.x, v, ga[kh * 3 + kw]);
-          gb[kh * 3 + kw] = fmaf(d.y, v, gb[kh * 3 + kw]);
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float2 d = unpack_bf16(dv[j]);
+        const int p = p0 + j;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float v = in[kh][p + kw];
+            ga[kh * 3 + kw] = fmaf(d.x, v, ga[kh * 3 + kw]);
+            gb[kh * 3 + kw] = fmaf(d.y, v, gb[kh * 3 + kw]);
+          }
+      }
     }
   }
   __syncthreads();
@@ -563,14 +578,14 @@ extern "C" int htrvt_pool_bwd(const void* gout, int gout_is_f32, const void* idx
 
 extern "C" int htrvt_bn_bwd_ctas(long long P) {
   long long c = (P + 255) / 256;
-  return static_cast<int>(c > 1184 ? 1184 : (c < 1 ? 1 : c));
+  return static_cast<int>(c > 888 ? 888 : (c < 1 ? 1 : c));
 }
 
 // BatchNorm backward for the BN (a) that produced `raw_a` (and optionally a second BN (b) fed by the same
 // upstream gradient: the downsample branch).  g: gradient w.r.t. the post-activation output y (ReLU mask
 // y > 0 applied when y != null).  Writes d_a (/d_b) = gradient w.r.t. the raw conv outputs, accumulates
 // dgamma / dbeta, optionally writes gz = masked g (identity-residual gradient).
-// partial: fp32 [htrvt_bn_bwd_ctas(P)][3][C]; coef: fp32 [2][2][C] scratch.
+// partial: fp32 [htrvt_bn_bwd_ctas(P)][3][C]; coef: fp32 [2][3][C] scratch.
 extern "C" int htrvt_bn_bwd(const void* g, const void* y, const void* raw_a, const float* mean_a,
                             const float* rstd_a, const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a,
                             const void* raw_b, const float* mean_b, const float* rstd_b, const float* gamma_b,
@@ -596,15 +611,16 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* y, const void* raw_a, con
       rstd_b, partial, P, C, rows);
   HTRVT_LAUNCH_CHECK();
   float* coef_a = coef;
-  float* coef_b = raw_b ? coef + 2 * C : nullptr;
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(partial, ctas, static_cast<double>(P), C, coef_a,
-                                                              dgamma_a, dbeta_a, coef_b, dgamma_b, dbeta_b);
+  float* coef_b = raw_b ? coef + 3 * C : nullptr;
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, stream>>>(partial, ctas, static_cast<double>(P), C, gamma_a, mean_a,
+                                                             rstd_a, coef_a, dgamma_a, dbeta_a, gamma_b, mean_b, rstd_b,
+                                                             coef_b, dgamma_b, dbeta_b);
   HTRVT_LAUNCH_CHECK();
   const long long n8 = P * C / 8;
   bn_bwd_apply_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y),
-      static_cast<const __nv_bfloat16*>(raw_a), mean_a, rstd_a, gamma_a, coef_a, static_cast<__nv_bfloat16*>(d_a),
-      static_cast<const __nv_bfloat16*>(raw_b), mean_b, rstd_b, gamma_b, coef_b, static_cast<__nv_bfloat16*>(d_b),
+      static_cast<const __nv_bfloat16*>(raw_a), coef_a, static_cast<__nv_bfloat16*>(d_a),
+      static_cast<const __nv_bfloat16*>(raw_b), coef_b, static_cast<__nv_bfloat16*>(d_b),
       static_cast<__nv_bfloat16*>(gz), n8, C);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;

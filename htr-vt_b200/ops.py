@@ -385,7 +385,7 @@ def bn_bwd(g, y, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=None,
     d_b = torch.empty_like(raw_a) if raw_b is not None else None
     gz = torch.empty_like(raw_a) if want_gz else None
     ctas = lib().htrvt_bn_bwd_ctas(P)
-    partial = workspace(ctas * 3 * C * 4 + 4 * C * 4, dev)
+    partial = workspace(ctas * 3 * C * 4 + 6 * C * 4, dev)
     coef = partial[ctas * 3 * C * 4:]
     z = None
     check(lib().htrvt_bn_bwd(_p(g), _p(y), _p(raw_a), _p(st_a[0]), _p(st_a[1]), _p(gamma_a), _p(dgamma_a),
