@@ -1,0 +1,149 @@
+/* htrvt.h - C ABI of libhtrvt_b200.so: the sm_100a kernels behind the HTR-VT hot path.
+ *
+ * The reference (0xk0ry/HTR-VT) is pure Python/PyTorch: its "FFI" for this path is the set of ATen / cuDNN /
+ * cuBLAS dispatches issued by model_v1/model/{HTR_VT,resnet18}.py, torch.nn.CTCLoss and
+ * CTCLabelConverter.decode.  Each entry point below names the reference call site it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator); the library never
+ *     allocates or frees device memory and keeps no state besides per-kernel attributes;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, no host syncs;
+ *   - return value: 0 = ok, -1 bad shape, -2 bad alignment, -3 wrong arch, -4 launch failed,
+ *     -5 workspace missing/too small, -6 driver entry point (cuTensorMapEncodeTiled) unavailable;
+ *   - "bf16" = __nv_bfloat16; activations of the conv stem are NHWC; matrices are row-major with the stated
+ *     leading dimension (elements).  sm_100a only, no CPU fallback.
+ */
+#ifndef HTRVT_H_
+#define HTRVT_H_
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int htrvt_version(void);
+unsigned long long htrvt_launch_count(void); /* kernels launched so far by this library (bench.py gpu_launches) */
+
+/* ---- CTC loss forward-backward -------------------------------------------------------------------------
+ * Replaces nn.CTCLoss(reduction='none', zero_infinity=True) as called at model_v1/train.py:27-29 and
+ * model_v1/valid.py:36-38 (ATen _ctc_loss + _ctc_loss_backward, blank = 0), optionally fused with the
+ * `.log_softmax(2)` of train.py:25 (is_logprob = 0: x are logits and grad is d/d(logits)).
+ * x / grad: fp32, class axis contiguous, element strides for the batch and time axes ([B,T,C] or [T,B,C]).
+ * targets: int32, concatenated (tgt_stride = 0) or padded [B, tgt_stride]; lengths int32 [B].
+ * max_target_len: host-side hint (max label length) or -1 = unknown (worst-case provisioning).
+ * nll[b] = 0 and grad = 0 for infeasible samples; grad may be NULL (loss only).
+ * grad is scaled by grad_scale[b] (device, may be NULL) or grad_scale_const. */
+size_t htrvt_ctc_workspace_bytes(int B, int T, int C, int max_target_len);
+int htrvt_ctc_loss_grad(const float* x, long long x_stride_b, long long x_stride_t, int is_logprob,
+                        const int* targets, int tgt_stride, const int* input_lengths, const int* target_lengths,
+                        int B, int T, int C, int max_target_len, float* nll, float* grad, long long g_stride_b,
+                        long long g_stride_t, const float* grad_scale, float grad_scale_const, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ---- greedy CTC decode ---------------------------------------------------------------------------------
+ * htrvt_greedy_decode replaces `preds.max(2)` + transpose (model_v1/valid.py:40-41) AND the filtering loop of
+ * CTCLabelConverter.decode (model_v1/utils/utils.py:72-86): ids[b, 0:lens[b]] are the kept class ids.
+ * htrvt_ctc_collapse takes the already arg-maxed sample-major index stream decode() receives. */
+int htrvt_greedy_decode(const float* logits, long long stride_b, long long stride_t, int B, int T, int C,
+                        const int* lengths, int n_character, int* ids, int* lens, int* raw_index, void* stream);
+int htrvt_ctc_collapse(const void* index, int index_is_int64, const int* lengths, int B, int Tmax, int n_character,
+                       int* ids, int* lens, void* stream);
+
+/* ---- tcgen05 tap-GEMM: nn.Linear / nn.Conv2d forward, input gradient, weight gradient ------------------
+ * flags (epilogue): 1 bf16 out, 2 +bias, 4 GELU(erf) with pre-activation to out2, 8 +fp32 residual,
+ * 16 accumulate into out, 32 column statistics, 64 QKV head-major scatter, 128 ReLU.
+ * htrvt_gemm_tn : Y = X W^T          nn.Linear fwd: attn.qkv / attn.proj (model_v1/model/HTR_VT.py:29,37),
+ *                                    timm Mlp fc1 (+GELU) / fc2 (:76), head (:238)
+ * htrvt_gemm_nn : dX = dY W          the same layers' input gradient (autograd of F.linear)
+ * htrvt_linear_wgrad : dW (+)= dY^T X  the same layers' weight gradient, fp32, split-K workspace */
+int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long long ldw, int M, int N, int K, int flags,
+                  const float* bias, const float* resid, void* out, long long ldo, void* out2, float alpha,
+                  int qkv_B, int qkv_T, int qkv_H, int qkv_hd, void* stream);
+int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long long ldw, int M, int N, int K, int flags,
+                  void* out, long long ldo, float alpha, void* stream);
+size_t htrvt_wgrad_workspace_bytes(int Cout, int Cin, int n_taps, int M_pixels);
+int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X, long long ldx, int M, int Nout, int Kin,
+                       float* grad, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+/* conv3x3 / 1x1 of BasicBlock and the downsample branch (model_v1/model/resnet18.py:4-7,23-39,56-63):
+ * x NHWC bf16 [NB,H,W,Cin], w bf16 [Cout][ks*ks][Cin], stride (sh,sw), pad ks/2, bias-free.
+ * stats_partial (optional): fp32 [htrvt_conv_fwd_stats_rows()][2][Cout] zero-initialised by the caller;
+ * receives per-CTA column sum / sum of squares of the stored bf16 output (BatchNorm batch statistics). */
+int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks, int sh, int sw,
+                   void* y, float* stats_partial, int flags, void* stream);
+int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw);
+int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* w, int Cout, int ks, int sh,
+                     int sw, void* dx, int accumulate, void* stream);
+int htrvt_conv_wgrad(const void* dy, const void* x, int NB, int H, int W, int Cin, int Cout, int ks, int sh,
+                     int sw, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* ---- attention -------------------------------------------------------------------------------------------
+ * Replaces Attention.forward's `q @ k^T * scale -> softmax -> @ v -> transpose/reshape`
+ * (model_v1/model/HTR_VT.py:32-36) and its backward.  qkv bf16 [3][B][H][T][128] (written by htrvt_gemm_tn with
+ * the QKV flag), out bf16 [B][T][H*128], lse fp32 [B][H][T], dqkv bf16 [B][T][3][H][128].  T <= 128. */
+int htrvt_attention_fwd(const void* qkv, int B, int H, int T, int hd, float scale, void* out, float* lse,
+                        void* stream);
+int htrvt_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int H, int T,
+                        int hd, float scale, void* dqkv, void* stream);
+
+/* ---- LayerNorms, tokens, elementwise ---------------------------------------------------------------------
+ * sample_ln : parameter-free LayerNorm over all non-batch dims, eps 1e-5 (model_v1/model/HTR_VT.py:134-136,
+ *             used at :224 on the image and :239 on the logits slab)
+ * row_ln    : nn.LayerNorm(D, eps=1e-6) with affine (:68,75,169), fp32 residual stream in, bf16 GEMM operand out;
+ *             backward accumulates into the fp32 residual gradient and into dgamma / dbeta
+ * tokens    : `x * mask + (1 - mask) * mask_token` then `+ pos_embed` (:212-220, 229-231)
+ * gelu_bwd  : nn.GELU (erf form) backward for timm Mlp; colsum_bf16: bias gradients; cast / pack: bf16 operand
+ *             copies of the fp32 master weights ([out,in] and OIHW -> [Cout][taps][Cin]). */
+int htrvt_sample_ln_fwd(const float* x, void* y, int y_is_bf16, float* mean, float* rstd, int B, int N, float eps,
+                        void* stream);
+int htrvt_sample_ln_bwd(const float* dy, const float* y, const float* rstd, void* dx_bf16, int B, int N, int C,
+                        int ld_out, void* stream);
+int htrvt_row_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* mean, float* rstd,
+                     int M, int D, float eps, void* stream);
+int htrvt_row_ln_bwd_ctas(int M);
+int htrvt_row_ln_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
+                     float* gx, int accumulate, float* dgamma, float* dbeta, float* partial, int M, int D,
+                     void* stream);
+int htrvt_tokens_fwd(const void* tok_bf16, const float* mask, const float* mask_token, const float* pos, float* x,
+                     int B, int T, int D, void* stream);
+int htrvt_tokens_bwd(const float* gx, const float* mask, void* dtok_bf16, float* dmask_token, float* partial, int B,
+                     int T, int D, void* stream);
+int htrvt_gelu_bwd(const void* da, const void* u, void* du, long long n, void* stream);
+int htrvt_colsum_rows(int M);
+int htrvt_colsum_bf16(const void* a, long long ld, int M, int N, float* out, int accumulate, float* partial,
+                      void* stream);
+int htrvt_cast_bf16(const float* src, void* dst, long long n, void* stream);
+int htrvt_pack_conv_weight(const float* w_oihw, void* dst, int Cout, int Cin, int taps, void* stream);
+
+/* ---- conv stem: first conv, BatchNorm, ReLU, max-pool ------------------------------------------------------
+ * conv1     : nn.Conv2d(1, C, 3, stride (2,1), pad 1) (model_v1/model/resnet18.py:48), direct (K = 9), + statistics
+ * bn_*      : nn.BatchNorm2d(eps=1e-5, momentum 0.1) train (batch stats, running-stat + counter update) / eval,
+ *             ReLU and the residual add of BasicBlock.forward (resnet18.py:23-39), and their backward
+ * pool_*    : nn.MaxPool2d(3, stride (2,1), pad 1) (resnet18.py:51,77,82) fused with BN + ReLU; idx = arg-max byte */
+int htrvt_conv1_fwd_zdim(int B);
+int htrvt_conv1_fwd(const float* x, const float* w, void* raw_bf16, float* partial, int B, int H, int W, int C,
+                    void* stream);
+int htrvt_bn_finalize(const float* partial, int R, double count, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                      float eps, int training, float* mean, float* rstd, float* scale, float* shift, int C,
+                      void* stream);
+int htrvt_bn_act_fwd(const void* raw, const float* scale, const float* shift, const void* res, const void* raw2,
+                     const float* scale2, const float* shift2, void* y, long long P, int C, int relu, void* stream);
+int htrvt_pool_fwd(const void* raw, const float* scale, const float* shift, void* out, void* idx, int B, int H,
+                   int W, int C, void* stream);
+int htrvt_pool_bwd(const void* gout, int gout_is_f32, const void* idx, const void* raw, const float* scale,
+                   const float* shift, void* gin, int B, int H, int W, int C, void* stream);
+int htrvt_bn_bwd_ctas(long long P);
+int htrvt_bn_bwd(const void* g, const void* y, const void* raw_a, const float* mean_a, const float* rstd_a,
+                 const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a, const void* raw_b,
+                 const float* mean_b, const float* rstd_b, const float* gamma_b, float* dgamma_b, float* dbeta_b,
+                 void* d_b, void* gz, long long P, int C, float* partial, float* coef, void* stream);
+int htrvt_conv1_wgrad_ctas(void);
+int htrvt_conv1_wgrad(const void* dy_bf16, const float* x, float* grad, int accumulate, float* partial, int B,
+                      int H, int W, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HTRVT_H_ */
