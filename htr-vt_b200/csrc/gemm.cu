@@ -17,17 +17,20 @@ namespace htrvt {
 constexpr int kGemmThreads = 320;
 constexpr int kBM = 128;
 constexpr int kBK = 64;
+constexpr int kStatCols = 768;             // widest output a statistics epilogue supports (Cout of the stem)
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int kStages = (BN <= 128) ? 6 : 4;
+  static_assert(true, "");
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kStatsBytes = 8 * 2 * 16 * 4;                  // per-warp column partials
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
-                                    2 * BN * 4 * 4 /* stats: [4 quadrants][2][BN] */ + 2 * 1024 * 4 /* per-CTA column sums */;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + 2 * BN * 4 * 4 /* stats: [4 quadrants][2][BN] */ +
+                                    2 * kStatCols * 4 /* per-CTA column sums */ + 8 * 32 * 20 * 4 /* epilogue transpose staging */;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -79,8 +82,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = GemmCfg<BN>;
   constexpr bool A_MN = (KIND == 1);
   constexpr int kStages = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment
+  if (smem_u32(smem) & 1023u) __trap();
   uint8_t* stage_base = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
   uint64_t* full = bars;
@@ -89,7 +92,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   float* stat_smem = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);   // [4][2][BN]
-  float* stat_acc = stat_smem + 8 * BN;                                                    // [2][1024]
+  float* stat_acc = stat_smem + 8 * BN;                                                    // [2][kStatCols]
+  float* stage_f32 = stat_acc + 2 * kStatCols;                                              // [8 warps][32][20]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = P.tiles_m * P.tiles_n * (P.kind == 0 ? 1 : P.n_taps * P.splits);
@@ -183,167 +187,191 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // =========================== epilogue (8 warps) ===========================
+    // Per 16-column chunk: tcgen05.ld (thread = row) -> per-warp smem transpose -> phase 2 where a lane owns
+    // (row = lane/4 + 8i, 4 consecutive columns), so every global access of the warp covers whole 32-byte
+    // sectors of 8 rows (the thread-per-row pattern touched 32 separate cache lines per instruction and paced
+    // the whole kernel).  The next chunk's TMEM load is in flight while the current one is processed.
     const int ew = warp - 2;                 // 0..7
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int half = ew >> 2;                // column half handled by this warp
-    const int r = quad * 32 + lane;          // tile row
     constexpr int kColsPerWarp = BN / 2;
+    constexpr int kStgStride = 20;           // floats per staged row (16 + pad: conflict-free 128-bit stores)
+    float* stg = stage_f32 + ew * (32 * kStgStride);
+    const int r8 = lane >> 2, cs = lane & 3;
     int as = 0; uint32_t aphase = 0;
     if (P.flags & EPI_STATS) {
-      for (int c = threadIdx.x - 64; c < 2048; c += 256) stat_acc[c] = 0.f;
+      for (int c = threadIdx.x - 64; c < 2 * kStatCols; c += 256) stat_acc[c] = 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     for (int id = blockIdx.x; id < total_tiles; id += gridDim.x) {
       const TileCoord tc = decode_tile(P, id);
       const int n0 = tc.n_tile * BN;
-      bool row_ok;
-      long long row_off;
-      int qb = 0, qt = 0;
-      if (KIND == 0) {
-        const int w = tc.w0 + r;
-        row_ok = w < P.Wo;
-        row_off = tc.n * P.o_sn + tc.h * P.o_sh + w * P.o_sw + P.o_base;
-        if (P.flags & EPI_QKV) {
-          const int m = tc.m_tile * kBM + r;
-          qb = m / P.qkv_T; qt = m - qb * P.qkv_T;
+      // the four rows this lane stores in phase 2
+      bool rok[4];
+      long long roff[4];
+      int qb[4], qt[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = quad * 32 + r8 + 8 * i;
+        qb[i] = 0; qt[i] = 0;
+        if (KIND == 0) {
+          const int w = tc.w0 + r;
+          rok[i] = w < P.Wo;
+          roff[i] = tc.n * P.o_sn + tc.h * P.o_sh + w * P.o_sw + P.o_base;
+          if (P.flags & EPI_QKV) {
+            const int m = tc.m_tile * kBM + r;
+            qb[i] = m / P.qkv_T; qt[i] = m - qb[i] * P.qkv_T;
+          }
+        } else {
+          const int co = tc.m_tile * kBM + r;
+          rok[i] = co < P.M_valid;
+          roff[i] = tc.split * P.o_split + co * P.o_sw + tc.tap * P.o_tap + P.o_base;
         }
-      } else {
-        const int co = tc.m_tile * kBM + r;
-        row_ok = co < P.M_valid;
-        row_off = tc.split * P.o_split + co * P.o_sw + tc.tap * P.o_tap + P.o_base;
+      }
+      if ((P.flags & (EPI_RESID | EPI_ACCUM)) && !(P.flags & EPI_QKV) && id + static_cast<int>(gridDim.x) < total_tiles) {
+        // warm L2 with the rows the NEXT tile's epilogue will read (each lane: one 128-byte line per row and step)
+        const TileCoord nt = decode_tile(P, id + gridDim.x);
+        const int esz = (P.flags & EPI_RESID) ? 4 : ((P.flags & EPI_BF16) ? 2 : 4);
+        const char* basep = (P.flags & EPI_RESID) ? reinterpret_cast<const char*>(P.resid)
+                                                   : reinterpret_cast<const char*>(P.out);
+        const int line_elems = 128 / esz;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = quad * 32 + r8 + 8 * i;
+          long long ro; bool ok;
+          if (KIND == 0) { const int w = nt.w0 + r; ok = w < P.Wo; ro = nt.n * P.o_sn + nt.h * P.o_sh + w * P.o_sw + P.o_base; }
+          else { const int co = nt.m_tile * kBM + r; ok = co < P.M_valid; ro = nt.split * P.o_split + co * P.o_sw + nt.tap * P.o_tap + P.o_base; }
+          for (int c = cs * line_elems; c < kColsPerWarp; c += 4 * line_elems) {
+            const int cg = nt.n_tile * BN + half * kColsPerWarp + c;
+            if (ok && cg < P.N_valid)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + (ro + cg) * esz));
+          }
+        }
       }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * kColsPerWarp;
+      if (P.flags & EPI_NOSTORE) {                         // measurement aid: main-loop-only timing
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        as ^= 1; if (as == 0) aphase ^= 1;
+        continue;
+      }
+      uint32_t cur[16], nxt[16];
+      tmem_ld16(taddr, cur);
+      tmem_ld_wait();
 #pragma unroll 1
       for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + c0, raw);
-        tmem_ld_wait();
+        const bool more = c0 + 16 < kColsPerWarp;
+        if (more) tmem_ld16(taddr + c0 + 16, nxt);
         const int col = n0 + half * kColsPerWarp + c0;       // first global column of this chunk
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * P.alpha;
-        if (P.flags & EPI_BIAS) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += (col + i < P.N_valid) ? __ldg(P.bias + col + i) : 0.f;
-        }
-        const bool col_ok = col < P.N_valid;                  // N_valid is a multiple of 8; chunks handled below
-        long long off = row_off + col;
+        const int c4 = col + cs * 4;                          // first of this lane's 4 global columns (phase 2)
+        const bool cok = c4 < P.N_valid;
+        long long coff = c4;                                  // column part of the output offset
+        long long qkv_which = 0; int qkv_hh = 0;
         if (P.flags & EPI_QKV) {
           const int D = P.qkv_H * P.qkv_hd;
-          const int which = col / D, rem = col - which * D;
-          const int hh = rem / P.qkv_hd, d = rem - hh * P.qkv_hd;
-          off = (static_cast<long long>(which) * P.NB + qb) * P.qkv_H + hh;      // NB carries the batch size
-          off = (off * P.qkv_T + qt) * P.qkv_hd + d;
+          const int which = c4 / D, rem = c4 - which * D;
+          qkv_hh = rem / P.qkv_hd;
+          coff = rem - qkv_hh * P.qkv_hd;
+          qkv_which = which;
         }
-        if (P.flags & EPI_RESID) {
-          if (row_ok && col_ok) {
+        long long offs[4];
+        float4 pre[4];                                        // residual / accumulate operands, loaded early
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              if (col + i < P.N_valid) {
-                const float4 rr = *reinterpret_cast<const float4*>(P.resid + off + i);
-                v[i] += rr.x; v[i + 1] += rr.y; v[i + 2] += rr.z; v[i + 3] += rr.w;
-              }
+        for (int i = 0; i < 4; ++i) {
+          offs[i] = roff[i] + coff;
+          if (P.flags & EPI_QKV)
+            offs[i] = (((qkv_which * P.NB + qb[i]) * P.qkv_H + qkv_hh) * P.qkv_T + qt[i]) * P.qkv_hd + coff;
+          pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool ok = rok[i] && cok;
+          if (ok && (P.flags & EPI_RESID)) pre[i] = *reinterpret_cast<const float4*>(P.resid + offs[i]);
+          if (ok && (P.flags & EPI_ACCUM)) {
+            if (P.flags & EPI_BF16) {
+              const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(P.out) + offs[i]);
+              const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+              pre[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
+            } else {
+              pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(P.out) + offs[i]);
             }
           }
         }
-        if (P.flags & EPI_GELU) {
-          if (row_ok && col_ok) {
-            __nv_bfloat16* o2 = static_cast<__nv_bfloat16*>(P.out2) + off;
+        // ---- phase 1: thread = row; scale, stage to smem -------------------------------------------
+        __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 16; i += 8) {
-              if (col + i < P.N_valid) {
-                uint4 u;
-                u.x = pack_bf16(v[i], v[i + 1]); u.y = pack_bf16(v[i + 2], v[i + 3]);
-                u.z = pack_bf16(v[i + 4], v[i + 5]); u.w = pack_bf16(v[i + 6], v[i + 7]);
-                *reinterpret_cast<uint4*>(o2 + i) = u;
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+        for (int i = 0; i < 16; i += 4) {
+          float4 f = make_float4(__uint_as_float(cur[i]) * P.alpha, __uint_as_float(cur[i + 1]) * P.alpha,
+                                 __uint_as_float(cur[i + 2]) * P.alpha, __uint_as_float(cur[i + 3]) * P.alpha);
+          *reinterpret_cast<float4*>(stg + lane * kStgStride + i) = f;
         }
-        if (P.flags & EPI_RELU) {
+        __syncwarp();
+        // ---- phase 2: lane = (row group r8, column segment cs) --------------------------------------
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((P.flags & EPI_BIAS) && cok) bias4 = *reinterpret_cast<const float4*>(P.bias + c4);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (P.flags & EPI_BF16) {
-          __nv_bfloat16* o = static_cast<__nv_bfloat16*>(P.out) + off;
-          if (P.flags & EPI_ACCUM) {
-            if (row_ok && col_ok) {
+        for (int i = 0; i < 4; ++i) {
+          const float4 x = *reinterpret_cast<const float4*>(stg + (r8 + 8 * i) * kStgStride + cs * 4);
+          float v[4] = {x.x + bias4.x, x.y + bias4.y, x.z + bias4.z, x.w + bias4.w};
+          const bool ok = rok[i] && cok;
+          const long long off = offs[i];
+          if (P.flags & EPI_RESID) { v[0] += pre[i].x; v[1] += pre[i].y; v[2] += pre[i].z; v[3] += pre[i].w; }
+          if (P.flags & EPI_GELU) {
+            if (ok) {
+              uint2 u;
+              u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(P.out2) + off) = u;
+            }
 #pragma unroll
-              for (int i = 0; i < 16; i += 8) {
-                if (col + i < P.N_valid) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(o + i);
-                  float2 f;
-                  f = unpack_bf16(u.x); v[i] += f.x; v[i + 1] += f.y;
-                  f = unpack_bf16(u.y); v[i + 2] += f.x; v[i + 3] += f.y;
-                  f = unpack_bf16(u.z); v[i + 4] += f.x; v[i + 5] += f.y;
-                  f = unpack_bf16(u.w); v[i + 6] += f.x; v[i + 7] += f.y;
-                }
+            for (int k = 0; k < 4; ++k) v[k] = gelu_erf(v[k]);
+          }
+          if (P.flags & EPI_RELU) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], 0.f);
+          }
+          if (P.flags & EPI_ACCUM) { v[0] += pre[i].x; v[1] += pre[i].y; v[2] += pre[i].z; v[3] += pre[i].w; }
+          if (P.flags & EPI_BF16) {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(P.out) + off;
+            uint2 u;
+            u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+            if (ok) *reinterpret_cast<uint2*>(o) = u;
+            if (P.flags & EPI_STATS) {
+              // statistics of exactly what is stored (bf16-rounded), zero for rows outside the image
+              const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
+              if (rok[i]) {
+                s4[0] += f0.x; s4[1] += f0.y; s4[2] += f1.x; s4[3] += f1.y;
+                q4[0] += f0.x * f0.x; q4[1] += f0.y * f0.y; q4[2] += f1.x * f1.x; q4[3] += f1.y * f1.y;
               }
             }
-          }
-          if (P.flags & EPI_STATS) {
-            // statistics of exactly what is stored (bf16-rounded), zero for rows outside the image
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = row_ok ? __bfloat162float(__float2bfloat16_rn(v[i])) : 0.f;
-          }
-          if (row_ok && col_ok) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 8) {
-              if (col + i < P.N_valid) {
-                uint4 u;
-                u.x = pack_bf16(v[i], v[i + 1]); u.y = pack_bf16(v[i + 2], v[i + 3]);
-                u.z = pack_bf16(v[i + 4], v[i + 5]); u.w = pack_bf16(v[i + 6], v[i + 7]);
-                *reinterpret_cast<uint4*>(o + i) = u;
-              }
-            }
-          }
-        } else {
-          float* o = static_cast<float*>(P.out) + off;
-          if (row_ok && col_ok) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              if (col + i < P.N_valid) {
-                float4 w4 = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                if (P.flags & EPI_ACCUM) {
-                  const float4 old = *reinterpret_cast<const float4*>(o + i);
-                  w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w;
-                }
-                *reinterpret_cast<float4*>(o + i) = w4;
-              }
-            }
+          } else {
+            float* o = static_cast<float*>(P.out) + off;
+            if (ok) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
         if (P.flags & EPI_STATS) {
-          // column sums over the 32 rows of this warp: recursive-halving butterfly (16+16 shuffles)
-          float s[16], q[16];
+          // lanes with equal cs hold the same 4 columns for different rows: 3 shuffle levels
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { s[i] = v[i]; q[i] = v[i] * v[i]; }
+          for (int o = 4; o <= 16; o <<= 1) {
 #pragma unroll
-          for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
-            const bool hi = (lane & bit) != 0;
-#pragma unroll
-            for (int i = 0; i < w; ++i) {
-              const float ss = hi ? s[i] : s[i + w];
-              const float sq = hi ? q[i] : q[i + w];
-              const float rs = __shfl_xor_sync(0xffffffffu, ss, bit);
-              const float rq = __shfl_xor_sync(0xffffffffu, sq, bit);
-              s[i] = (hi ? s[i + w] : s[i]) + rs;
-              q[i] = (hi ? q[i + w] : q[i]) + rq;
+            for (int k = 0; k < 4; ++k) {
+              s4[k] += __shfl_xor_sync(0xffffffffu, s4[k], o);
+              q4[k] += __shfl_xor_sync(0xffffffffu, q4[k], o);
             }
           }
-          s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
-          q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
-          // lane bits 4..1 select the column: bit 16 -> +8, 8 -> +4, 4 -> +2, 2 -> +1
-          if ((lane & 1) == 0) {
-            const int cl = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            const int cc = half * kColsPerWarp + c0 + cl;
-            stat_smem[(quad * 2 + 0) * BN + cc] = s[0];
-            stat_smem[(quad * 2 + 1) * BN + cc] = q[0];
+          if (lane < 4) {
+            const int cc = half * kColsPerWarp + c0 + lane * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              stat_smem[(quad * 2 + 0) * BN + cc + k] = s4[k];
+              stat_smem[(quad * 2 + 1) * BN + cc + k] = q4[k];
+            }
           }
+        }
+        if (more) {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
         }
       }
       tc_fence_before();
@@ -358,7 +386,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) { ssum += stat_smem[(qd * 2) * BN + c]; qsum += stat_smem[(qd * 2 + 1) * BN + c]; }
             stat_acc[n0 + c] += ssum;                      // column n0+c is owned by exactly one thread per tile
-            stat_acc[1024 + n0 + c] += qsum;
+            stat_acc[kStatCols + n0 + c] += qsum;
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -369,7 +397,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float* dst = P.stats + static_cast<long long>(blockIdx.x) * 2 * P.N_valid;
       for (int c = threadIdx.x - 64; c < P.N_valid; c += 256) {
         dst[c] = stat_acc[c];
-        dst[P.N_valid + c] = stat_acc[1024 + c];
+        dst[P.N_valid + c] = stat_acc[kStatCols + c];
       }
     }
   }
@@ -516,7 +544,7 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
                              int flags, const float* bias, const float* resid, void* out, long long ldo,
                              void* out2, float alpha, int qkv_B, int qkv_T, int qkv_H, int qkv_hd,
                              cudaStream_t stream) {
-  if (M <= 0 || N <= 0 || K <= 0 || (N & 7)) return HTRVT_ERR_SHAPE;
+  if (M <= 0 || N <= 0 || K <= 0 || (N & 7) || (ldo & 3)) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(N);
   CUtensorMap ta, tb;
   {
@@ -542,7 +570,7 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
 // dX[M,N] = dY[M,K] W[K,N]: nn.Linear input gradient (B operand MN-major, no transpose copy).
 extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long long ldw, int M, int N, int K,
                              int flags, void* out, long long ldo, float alpha, cudaStream_t stream) {
-  if (M <= 0 || N <= 0 || K <= 0 || (N & 7)) return HTRVT_ERR_SHAPE;
+  if (M <= 0 || N <= 0 || K <= 0 || (N & 7) || (ldo & 3)) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(N);
   CUtensorMap ta, tb;
   {
@@ -564,20 +592,29 @@ extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long
 }
 
 namespace {
-int choose_splits(int base_tiles, long long q_total) {
-  int s = (2 * num_sms()) / (base_tiles > 0 ? base_tiles : 1);
-  if (s < 1) s = 1;
-  if (s > 64) s = 64;
-  if (s > q_total) s = static_cast<int>(q_total);
-  return s;
+// Split-K factor for the weight-gradient GEMMs: minimise (waves x per-split tile time) + partial-sum traffic.
+// base_tiles output tiles, q_total K chunks per tile, out_elems fp32 outputs.
+int choose_splits(int base_tiles, long long q_total, long long out_elems = 0) {
+  const int sms = num_sms();
+  double best = 1e300;
+  int best_s = 1;
+  const double tile_us = static_cast<double>(q_total) * 0.23;          // ~0.23 us per 128xBNx64 k-chunk at full rate
+  for (int s = 1; s <= 32 && s <= q_total; ++s) {
+    const long long tiles = static_cast<long long>(base_tiles) * s;
+    const double waves = static_cast<double>((tiles + sms - 1) / sms);
+    double t = waves * tile_us / s;
+    if (s > 1) t += 2.0 * s * out_elems * 4.0 / 5.0e6;                 // write + read of the partials at ~5 TB/s (us)
+    if (t < best * 0.98) { best = t; best_s = s; }
+  }
+  return best_s;
 }
 }  // namespace
 
 extern "C" size_t htrvt_wgrad_workspace_bytes(int Cout, int Cin, int n_taps, int M_pixels) {
   const int bn = pick_bn(Cin);
   const int base = n_taps * ((Cout + kBM - 1) / kBM) * ((Cin + bn - 1) / bn);
-  const int s = choose_splits(base, (M_pixels + 63) / 64);
-  return static_cast<size_t>(s) * Cout * n_taps * Cin * sizeof(float);
+  (void)base; (void)M_pixels;
+  return static_cast<size_t>(32) * Cout * n_taps * Cin * sizeof(float);   // upper bound (splits <= 32)
 }
 
 // Split-K partial sums [splits][Cout][taps][Cin] -> grad (+= or =); to_oihw permutes to [Cout][Cin][taps].
@@ -623,7 +660,7 @@ extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X,
   P.kind = 1; P.Wo = M; P.Ho = 1; P.NB = 1; P.tiles_per_row = 1;
   P.tiles_m = (Nout + kBM - 1) / kBM; P.tiles_n = (Kin + bn - 1) / bn; P.n_taps = 1;
   P.k_chunks = (M + 63) / 64; P.a_sh = 1;
-  P.splits = choose_splits(P.tiles_m * P.tiles_n, P.k_chunks);
+  P.splits = choose_splits(P.tiles_m * P.tiles_n, P.k_chunks, static_cast<long long>(Nout) * Kin);
   P.M_valid = Nout; P.N_valid = Kin; P.flags = 0; P.alpha = 1.f;
   const size_t need = static_cast<size_t>(P.splits) * Nout * Kin * sizeof(float);
   if (!workspace || workspace_bytes < need) return HTRVT_ERR_WORKSPACE;
@@ -646,7 +683,7 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
                               int sh, int sw, void* y, float* stats_partial, int flags, cudaStream_t stream) {
   const int pad = ks / 2;
   if ((Cin % 64) || (Cout & 7) || (W % sw) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
-  if (stats_partial && Cout > 1024) return HTRVT_ERR_SHAPE;
+  if (stats_partial && Cout > kStatCols) return HTRVT_ERR_SHAPE;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
   const int bn = pick_bn(Cout);
   CUtensorMap ta, tb;
@@ -732,7 +769,7 @@ extern "C" int htrvt_conv_wgrad(const void* dy, const void* x, int NB, int H, in
   fill_taps_conv(P.tap, ks, pad, sw, &P.n_taps);
   P.k_chunks = (Wo + 63) / 64; P.a_sh = sh;
   const long long Q = static_cast<long long>(NB) * Ho * P.k_chunks;
-  P.splits = choose_splits(P.tiles_m * P.tiles_n * P.n_taps, Q);
+  P.splits = choose_splits(P.tiles_m * P.tiles_n * P.n_taps, Q, static_cast<long long>(Cout) * P.n_taps * Cin);
   P.M_valid = Cout; P.N_valid = Cin; P.flags = 0; P.alpha = 1.f;
   const long long per = static_cast<long long>(Cout) * P.n_taps * Cin;
   if (!workspace || workspace_bytes < static_cast<size_t>(P.splits) * per * sizeof(float)) return HTRVT_ERR_WORKSPACE;

@@ -20,6 +20,7 @@ enum : int {
   EPI_STATS = 1 << 5,      // per-tile column sum / sum of squares -> stats[tile_m][2][N]
   EPI_QKV = 1 << 6,        // scatter columns to [3][B][H][T][hd]
   EPI_RELU = 1 << 7,       // max(x, 0)
+  EPI_NOSTORE = 1 << 8,    // measurement aid: skip the epilogue body (main-loop-only timing)
 };
 
 struct GemmP {

@@ -85,7 +85,7 @@ def conv_out_hw(H, W, ks, sh, sw):
     return (H + 2 * pad - ks) // sh + 1, (W + 2 * pad - ks) // sw + 1
 
 
-def conv_fwd(x, w, ks, sh, sw, y=None, stats=None, relu=False):
+def conv_fwd(x, w, ks, sh, sw, y=None, stats=None, relu=False, nostore=False):
     """x [N,H,W,Cin] bf16 NHWC, w [Cout, ks*ks, Cin] bf16 -> y [N,Ho,Wo,Cout] bf16 (raw conv output).
     stats: optional fp32 [rows, 2, Cout] per-tile column sum / sum-of-squares partials."""
     _need_cuda(x, w)
@@ -95,7 +95,7 @@ def conv_fwd(x, w, ks, sh, sw, y=None, stats=None, relu=False):
     if y is None:
         y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
     check(lib().htrvt_conv_fwd(_p(x), N, H, W, Cin, _p(w), Cout, ks, sh, sw, _p(y), _p(stats),
-                               EPI_RELU if relu else 0, _stream()), "htrvt_conv_fwd")
+                               (EPI_RELU if relu else 0) | (256 if nostore else 0), _stream()), "htrvt_conv_fwd")
     return y
 
 
@@ -120,8 +120,7 @@ def conv_wgrad(dy, x, ks, sh, sw, grad_oihw, accumulate=True):
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     Ho, Wo = conv_out_hw(H, W, ks, sh, sw)
-    nbytes = lib().htrvt_wgrad_workspace_bytes(Cout, Cin, ks * ks, Wo)  # chunks are per row; bound below
-    nbytes = max(nbytes, 64 * Cout * ks * ks * Cin * 4)
+    nbytes = lib().htrvt_wgrad_workspace_bytes(Cout, Cin, ks * ks, Wo)
     ws = workspace(nbytes, dy.device)
     check(lib().htrvt_conv_wgrad(_p(dy), _p(x), N, H, W, Cin, Cout, ks, sh, sw, _p(grad_oihw), int(accumulate),
                                  _p(ws), ws.numel(), _stream()), "htrvt_conv_wgrad")
