@@ -44,7 +44,7 @@ SIGNATURES = {
     "htrvt_ctc_loss_grad": (_I, [_P, _L, _L, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _L, _L, _P, _F, _P, _Z, _P]),
     "htrvt_greedy_decode": (_I, [_P, _L, _L, _I, _I, _I, _P, _I, _P, _P, _P, _P]),
     "htrvt_ctc_collapse": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P]),
-    "htrvt_gemm_tn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _P, _L, _P, _F, _I, _I, _I, _I, _P]),
+    "htrvt_gemm_tn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _L, _F, _P]),
     "htrvt_gemm_nn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _F, _P]),
     "htrvt_wgrad_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "htrvt_linear_wgrad": (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _Z, _P]),
@@ -54,7 +54,8 @@ SIGNATURES = {
     "htrvt_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _Z, _P]),
     "htrvt_sample_ln_fwd": (_I, [_P, _P, _I, _P, _P, _I, _I, _F, _P]),
     "htrvt_sample_ln_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "htrvt_row_ln_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "htrvt_row_ln_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "htrvt_gelu_fwd": (_I, [_P, _P, _L, _P]),
     "htrvt_row_ln_bwd_ctas": (_I, [_I]),
     "htrvt_row_ln_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
     "htrvt_tokens_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),

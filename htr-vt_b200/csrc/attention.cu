@@ -59,7 +59,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x, b = bh / P.H, h = bh - b * P.H;
-  const int BH = P.B * P.H;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -77,9 +76,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 4) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_load, 6 * kImg);
-      load_image(sQ, &tmQKV, bar_load, 0, 0, bh);
-      load_image(sK, &tmQKV, bar_load, 0, 0, BH + bh);
-      load_image(sV, &tmQKV, bar_load, 0, 0, 2 * BH + bh);
+      const int D = P.H * kHd;
+      load_image(sQ, &tmQKV, bar_load, h * kHd, 0, b);
+      load_image(sK, &tmQKV, bar_load, D + h * kHd, 0, b);
+      load_image(sV, &tmQKV, bar_load, 2 * D + h * kHd, 0, b);
       mbar_wait(bar_load, 0);
       tc_fence_after();
       const uint32_t q = smem_u32(sQ), k = smem_u32(sK);
@@ -181,7 +181,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x, b = bh / P.H, h = bh - b * P.H;
-  const int BH = P.B * P.H;
 
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -202,9 +201,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 4) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_load, 8 * kImg);
-      load_image(sQ, &tmQKV, bar_load, 0, 0, bh);
-      load_image(sK, &tmQKV, bar_load, 0, 0, BH + bh);
-      load_image(sV, &tmQKV, bar_load, 0, 0, 2 * BH + bh);
+      const int Dm = P.H * kHd;
+      load_image(sQ, &tmQKV, bar_load, h * kHd, 0, b);
+      load_image(sK, &tmQKV, bar_load, Dm + h * kHd, 0, b);
+      load_image(sV, &tmQKV, bar_load, 2 * Dm + h * kHd, 0, b);
       load_image(sDO, &tmDO, bar_load, h * kHd, 0, b);
       mbar_wait(bar_load, 0);
       tc_fence_after();
@@ -347,12 +347,13 @@ int map3(CUtensorMap* m, const void* ptr, long long cols, long long rows, long l
 }
 }  // namespace
 
-// qkv: bf16 [3][B][H][T][128]; out: bf16 [B][T][H*128]; lse: fp32 [B][H][T] (may be null)
+// qkv: bf16 token-major [B][T][3*H*128] (the QKV projection output as is); out: bf16 [B][T][H*128];
+// lse: fp32 [B][H][T] (may be null)
 extern "C" int htrvt_attention_fwd(const void* qkv, int B, int H, int T, int hd, float scale, void* out, float* lse,
                                    cudaStream_t stream) {
   if (hd != kHd || T < 1 || T > kTq || B < 1 || H < 1) return HTRVT_ERR_SHAPE;
   CUtensorMap tm;
-  int r = map3(&tm, qkv, kHd, T, 3LL * B * H, kHd, static_cast<long long>(T) * kHd);
+  int r = map3(&tm, qkv, 3LL * H * kHd, T, B, 3LL * H * kHd, static_cast<long long>(T) * 3 * H * kHd);
   if (r) return r;
   AttnP P = {};
   P.B = B; P.H = H; P.T = T; P.scale = scale; P.out = static_cast<__nv_bfloat16*>(out); P.lse = lse;
@@ -373,7 +374,7 @@ extern "C" int htrvt_attention_bwd(const void* qkv, const void* out, const void*
                                    int T, int hd, float scale, void* dqkv, cudaStream_t stream) {
   if (hd != kHd || T < 1 || T > kTq || B < 1 || H < 1 || !lse) return HTRVT_ERR_SHAPE;
   CUtensorMap tm, tdo;
-  int r = map3(&tm, qkv, kHd, T, 3LL * B * H, kHd, static_cast<long long>(T) * kHd);
+  int r = map3(&tm, qkv, 3LL * H * kHd, T, B, 3LL * H * kHd, static_cast<long long>(T) * 3 * H * kHd);
   if (r) return r;
   r = map3(&tdo, dout, static_cast<long long>(H) * kHd, T, B, static_cast<long long>(H) * kHd,
            static_cast<long long>(T) * H * kHd);

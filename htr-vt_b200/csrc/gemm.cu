@@ -17,19 +17,16 @@ namespace htrvt {
 constexpr int kGemmThreads = 320;
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kStatCols = 768;             // widest output a statistics epilogue supports (Cout of the stem)
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 128) ? 6 : 4;
-  static_assert(true, "");
+  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kStatsBytes = 8 * 2 * 16 * 4;                  // per-warp column partials
-  static constexpr int kSmemBytes = kStages * kStageBytes + 256 /*barriers*/ + 2 * BN * 4 * 4 /* stats: [4 quadrants][2][BN] */ +
-                                    2 * kStatCols * 4 /* per-CTA column sums */ + 8 * 32 * 20 * 4 /* epilogue transpose staging */;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * 8192 /* output staging: 2 x [128][64 B] */ + 256 /*barriers*/;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -78,22 +75,20 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmP& P, int id) {
 template <int BN, int KIND, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ GemmP P) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmP P) {
   using Cfg = GemmCfg<BN>;
   constexpr bool A_MN = (KIND == 1);
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment
   if (smem_u32(smem) & 1023u) __trap();
   uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* stage_out = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 2 * 8192);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* tfull = bars + 2 * kStages;
   uint64_t* tempty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  float* stat_smem = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);   // [4][2][BN]
-  float* stat_acc = stat_smem + 8 * BN;                                                    // [2][kStatCols]
-  float* stage_f32 = stat_acc + 2 * kStatCols;                                              // [8 warps][32][20]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = P.tiles_m * P.tiles_n * (P.kind == 0 ? 1 : P.n_taps * P.splits);
@@ -101,6 +96,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     fence_barrier_init();
@@ -187,219 +183,132 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // =========================== epilogue (8 warps) ===========================
-    // Per 16-column chunk: tcgen05.ld (thread = row) -> per-warp smem transpose -> phase 2 where a lane owns
-    // (row = lane/4 + 8i, 4 consecutive columns), so every global access of the warp covers whole 32-byte
-    // sectors of 8 rows (the thread-per-row pattern touched 32 separate cache lines per instruction and paced
-    // the whole kernel).  The next chunk's TMEM load is in flight while the current one is processed.
+    // Deliberately light: only 8 warps run it, so anything beyond scale / bias / ReLU lives in separate
+    // full-occupancy kernels (GELU, residual add) or in the memory system (accumulate = TMA reduce-add).
+    // Per 64-byte-wide box (32 bf16 or 16 fp32 columns x 128 rows): tcgen05.ld -> registers -> swizzled smem
+    // staging -> one elected thread issues the TMA store; BatchNorm column sums are read back from the
+    // staged tile by the warp that owns the rows and accumulated in registers across tiles.
     const int ew = warp - 2;                 // 0..7
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int half = ew >> 2;                // column half handled by this warp
+    const int r = quad * 32 + lane;          // tile row owned in the register phase
     constexpr int kColsPerWarp = BN / 2;
-    constexpr int kStgStride = 20;           // floats per staged row (16 + pad: conflict-free 128-bit stores)
-    float* stg = stage_f32 + ew * (32 * kStgStride);
-    const int r8 = lane >> 2, cs = lane & 3;
+    const bool out_bf16 = (P.flags & EPI_BF16) != 0;
+    const int box_cols = out_bf16 ? 32 : 16;
+    uint8_t* stg = stage_out + half * 8192;                 // [128 rows][64 B], SWIZZLE_64B
+    const uint32_t stg_row = smem_u32(stg) + r * 64;
+    const int sw_r = (r >> 1) & 3;
+    const bool issuer = (quad == 0) && (lane == 0);
+    const uint32_t bar_id = 2 + half;
+    float ssum[4] = {0.f, 0.f, 0.f, 0.f}, qsum[4] = {0.f, 0.f, 0.f, 0.f};
+    int stats_ntile = -1;
+    auto flush_stats = [&](int n_tile) {
+      if (n_tile < 0) return;
+      float* dst = P.stats + static_cast<long long>(blockIdx.x * 4 + quad) * 2 * P.N_valid;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int col = n_tile * BN + half * kColsPerWarp + b * 32 + lane;
+        if (b * 32 < kColsPerWarp && col < P.N_valid) {
+          dst[col] += ssum[b];
+          dst[P.N_valid + col] += qsum[b];
+        }
+        ssum[b] = 0.f; qsum[b] = 0.f;
+      }
+    };
     int as = 0; uint32_t aphase = 0;
-    if (P.flags & EPI_STATS) {
-      for (int c = threadIdx.x - 64; c < 2 * kStatCols; c += 256) stat_acc[c] = 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
     for (int id = blockIdx.x; id < total_tiles; id += gridDim.x) {
       const TileCoord tc = decode_tile(P, id);
       const int n0 = tc.n_tile * BN;
-      // the four rows this lane stores in phase 2
-      bool rok[4];
-      long long roff[4];
-      int qb[4], qt[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = quad * 32 + r8 + 8 * i;
-        qb[i] = 0; qt[i] = 0;
-        if (KIND == 0) {
-          const int w = tc.w0 + r;
-          rok[i] = w < P.Wo;
-          roff[i] = tc.n * P.o_sn + tc.h * P.o_sh + w * P.o_sw + P.o_base;
-          if (P.flags & EPI_QKV) {
-            const int m = tc.m_tile * kBM + r;
-            qb[i] = m / P.qkv_T; qt[i] = m - qb[i] * P.qkv_T;
-          }
-        } else {
-          const int co = tc.m_tile * kBM + r;
-          rok[i] = co < P.M_valid;
-          roff[i] = tc.split * P.o_split + co * P.o_sw + tc.tap * P.o_tap + P.o_base;
-        }
-      }
-      if ((P.flags & (EPI_RESID | EPI_ACCUM)) && !(P.flags & EPI_QKV) && id + static_cast<int>(gridDim.x) < total_tiles) {
-        // warm L2 with the rows the NEXT tile's epilogue will read (each lane: one 128-byte line per row and step)
-        const TileCoord nt = decode_tile(P, id + gridDim.x);
-        const int esz = (P.flags & EPI_RESID) ? 4 : ((P.flags & EPI_BF16) ? 2 : 4);
-        const char* basep = (P.flags & EPI_RESID) ? reinterpret_cast<const char*>(P.resid)
-                                                   : reinterpret_cast<const char*>(P.out);
-        const int line_elems = 128 / esz;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = quad * 32 + r8 + 8 * i;
-          long long ro; bool ok;
-          if (KIND == 0) { const int w = nt.w0 + r; ok = w < P.Wo; ro = nt.n * P.o_sn + nt.h * P.o_sh + w * P.o_sw + P.o_base; }
-          else { const int co = nt.m_tile * kBM + r; ok = co < P.M_valid; ro = nt.split * P.o_split + co * P.o_sw + nt.tap * P.o_tap + P.o_base; }
-          for (int c = cs * line_elems; c < kColsPerWarp; c += 4 * line_elems) {
-            const int cg = nt.n_tile * BN + half * kColsPerWarp + c;
-            if (ok && cg < P.N_valid)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(basep + (ro + cg) * esz));
-          }
-        }
-      }
+      if ((P.flags & EPI_STATS) && tc.n_tile != stats_ntile) { flush_stats(stats_ntile); stats_ntile = tc.n_tile; }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * kColsPerWarp;
-      if (P.flags & EPI_NOSTORE) {                         // measurement aid: main-loop-only timing
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
-        as ^= 1; if (as == 0) aphase ^= 1;
-        continue;
-      }
-      uint32_t cur[16], nxt[16];
-      tmem_ld16(taddr, cur);
-      tmem_ld_wait();
+      const int nboxes = kColsPerWarp / box_cols;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kColsPerWarp; c0 += 16) {
-        const bool more = c0 + 16 < kColsPerWarp;
-        if (more) tmem_ld16(taddr + c0 + 16, nxt);
-        const int col = n0 + half * kColsPerWarp + c0;       // first global column of this chunk
-        const int c4 = col + cs * 4;                          // first of this lane's 4 global columns (phase 2)
-        const bool cok = c4 < P.N_valid;
-        long long coff = c4;                                  // column part of the output offset
-        long long qkv_which = 0; int qkv_hh = 0;
-        if (P.flags & EPI_QKV) {
-          const int D = P.qkv_H * P.qkv_hd;
-          const int which = c4 / D, rem = c4 - which * D;
-          qkv_hh = rem / P.qkv_hd;
-          coff = rem - qkv_hh * P.qkv_hd;
-          qkv_which = which;
+      for (int b = 0; b < nboxes; ++b) {
+        const int c_local = half * kColsPerWarp + b * box_cols;
+        const int col = n0 + c_local;                        // first global column of this box
+        uint32_t raw[32];
+        tmem_ld16(taddr + b * box_cols, *reinterpret_cast<uint32_t(*)[16]>(&raw[0]));
+        if (out_bf16) tmem_ld16(taddr + b * box_cols + 16, *reinterpret_cast<uint32_t(*)[16]>(&raw[16]));
+        tmem_ld_wait();
+        if (b == nboxes - 1) {                               // accumulator fully read: hand TMEM back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[as]);
         }
-        long long offs[4];
-        float4 pre[4];                                        // residual / accumulate operands, loaded early
+        if (P.flags & EPI_NOSTORE) continue;                 // measurement aid: main loop only
+        uint32_t packed[16];
+        if (out_bf16) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          offs[i] = roff[i] + coff;
-          if (P.flags & EPI_QKV)
-            offs[i] = (((qkv_which * P.NB + qb[i]) * P.qkv_H + qkv_hh) * P.qkv_T + qt[i]) * P.qkv_hd + coff;
-          pre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const bool ok = rok[i] && cok;
-          if (ok && (P.flags & EPI_RESID)) pre[i] = *reinterpret_cast<const float4*>(P.resid + offs[i]);
-          if (ok && (P.flags & EPI_ACCUM)) {
-            if (P.flags & EPI_BF16) {
-              const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(P.out) + offs[i]);
-              const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
-              pre[i] = make_float4(f0.x, f0.y, f1.x, f1.y);
-            } else {
-              pre[i] = *reinterpret_cast<const float4*>(static_cast<const float*>(P.out) + offs[i]);
+          for (int i = 0; i < 32; i += 2) {
+            float a = __uint_as_float(raw[i]) * P.alpha, c = __uint_as_float(raw[i + 1]) * P.alpha;
+            if (P.flags & EPI_BIAS) {
+              a += (col + i < P.N_valid) ? __ldg(P.bias + col + i) : 0.f;
+              c += (col + i + 1 < P.N_valid) ? __ldg(P.bias + col + i + 1) : 0.f;
             }
+            if (P.flags & EPI_RELU) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+            packed[i >> 1] = pack_bf16(a, c);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = __uint_as_float(raw[i]) * P.alpha;
+            if (P.flags & EPI_BIAS) a += (col + i < P.N_valid) ? __ldg(P.bias + col + i) : 0.f;
+            if (P.flags & EPI_RELU) a = fmaxf(a, 0.f);
+            packed[i] = __float_as_uint(a);
           }
         }
-        // ---- phase 1: thread = row; scale, stage to smem -------------------------------------------
-        __syncwarp();
+        // the previous box's TMA store must have finished READING the staging buffer
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          float4 f = make_float4(__uint_as_float(cur[i]) * P.alpha, __uint_as_float(cur[i + 1]) * P.alpha,
-                                 __uint_as_float(cur[i + 2]) * P.alpha, __uint_as_float(cur[i + 3]) * P.alpha);
-          *reinterpret_cast<float4*>(stg + lane * kStgStride + i) = f;
+        for (int c16 = 0; c16 < 4; ++c16) {
+          const uint32_t addr = stg_row + ((c16 ^ sw_r) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * c16]),
+                       "r"(packed[4 * c16 + 1]), "r"(packed[4 * c16 + 2]), "r"(packed[4 * c16 + 3])
+                       : "memory");
         }
-        __syncwarp();
-        // ---- phase 2: lane = (row group r8, column segment cs) --------------------------------------
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((P.flags & EPI_BIAS) && cok) bias4 = *reinterpret_cast<const float4*>(P.bias + c4);
-        float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 x = *reinterpret_cast<const float4*>(stg + (r8 + 8 * i) * kStgStride + cs * 4);
-          float v[4] = {x.x + bias4.x, x.y + bias4.y, x.z + bias4.z, x.w + bias4.w};
-          const bool ok = rok[i] && cok;
-          const long long off = offs[i];
-          if (P.flags & EPI_RESID) { v[0] += pre[i].x; v[1] += pre[i].y; v[2] += pre[i].z; v[3] += pre[i].w; }
-          if (P.flags & EPI_GELU) {
-            if (ok) {
-              uint2 u;
-              u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
-              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(P.out2) + off) = u;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = gelu_erf(v[k]);
-          }
-          if (P.flags & EPI_RELU) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = fmaxf(v[k], 0.f);
-          }
-          if (P.flags & EPI_ACCUM) { v[0] += pre[i].x; v[1] += pre[i].y; v[2] += pre[i].z; v[3] += pre[i].w; }
-          if (P.flags & EPI_BF16) {
-            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(P.out) + off;
-            uint2 u;
-            u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
-            if (ok) *reinterpret_cast<uint2*>(o) = u;
-            if (P.flags & EPI_STATS) {
-              // statistics of exactly what is stored (bf16-rounded), zero for rows outside the image
-              const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y);
-              if (rok[i]) {
-                s4[0] += f0.x; s4[1] += f0.y; s4[2] += f1.x; s4[3] += f1.y;
-                q4[0] += f0.x * f0.x; q4[1] += f0.y * f0.y; q4[2] += f1.x * f1.x; q4[3] += f1.y * f1.y;
-              }
-            }
-          } else {
-            float* o = static_cast<float*>(P.out) + off;
-            if (ok) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          }
+        fence_proxy_async();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (issuer && col < P.N_valid) {
+          int c1, c2, c3, c4;
+          if (KIND == 0) { c1 = tc.w0; c2 = tc.h; c3 = tc.n; c4 = 0; }
+          else { c1 = tc.m_tile * kBM; c2 = tc.tap; c3 = tc.split; c4 = 0; }
+          if (P.flags & EPI_ACCUM)
+            asm volatile(
+                "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(stg)), "r"(col), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                : "memory");
+          else
+            asm volatile(
+                "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(stg)), "r"(col), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (P.flags & EPI_STATS) {
-          // lanes with equal cs hold the same 4 columns for different rows: 3 shuffle levels
-#pragma unroll
-          for (int o = 4; o <= 16; o <<= 1) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              s4[k] += __shfl_xor_sync(0xffffffffu, s4[k], o);
-              q4[k] += __shfl_xor_sync(0xffffffffu, q4[k], o);
-            }
+          // column `lane` of this warp's own 32 staged rows (bf16 box = 32 columns); rows outside the image are
+          // exact zeros (their A rows were TMA zero-filled and convolutions carry no bias)
+          float s = 0.f, q = 0.f;
+          const uint32_t base = smem_u32(stg) + (quad * 32) * 64 + (lane & 7) * 2;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = quad * 32 + rr;
+            uint16_t hv;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(base + rr * 64 + (((lane >> 3) ^ ((row >> 1) & 3)) << 4)));
+            const float f = __uint_as_float(static_cast<uint32_t>(hv) << 16);
+            s += f;
+            q = fmaf(f, f, q);
           }
-          if (lane < 4) {
-            const int cc = half * kColsPerWarp + c0 + lane * 4;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              stat_smem[(quad * 2 + 0) * BN + cc + k] = s4[k];
-              stat_smem[(quad * 2 + 1) * BN + cc + k] = q4[k];
-            }
-          }
+          ssum[b] += s;
+          qsum[b] += q;
         }
-        if (more) {
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-      if (P.flags & EPI_STATS) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int t = threadIdx.x - 64;                       // 0..255
-        for (int c = t; c < BN; c += 256) {
-          if (n0 + c < P.N_valid) {
-            float ssum = 0.f, qsum = 0.f;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) { ssum += stat_smem[(qd * 2) * BN + c]; qsum += stat_smem[(qd * 2 + 1) * BN + c]; }
-            stat_acc[n0 + c] += ssum;                      // column n0+c is owned by exactly one thread per tile
-            stat_acc[kStatCols + n0 + c] += qsum;
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       as ^= 1; if (as == 0) aphase ^= 1;
     }
-    if (P.flags & EPI_STATS) {                           // one partial row per CTA: stats[cta][2][N]
-      float* dst = P.stats + static_cast<long long>(blockIdx.x) * 2 * P.N_valid;
-      for (int c = threadIdx.x - 64; c < P.N_valid; c += 256) {
-        dst[c] = stat_acc[c];
-        dst[P.N_valid + c] = stat_acc[kStatCols + c];
-      }
-    }
+    if (P.flags & EPI_STATS) flush_stats(stats_ntile);
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -435,10 +344,10 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 5-D bf16 tensor map, innermost dimension contiguous, SWIZZLE_128B, zero OOB fill.
-// dims / box: innermost first.  strides: element strides of dims 1..4.
+// 5-D tensor map, innermost dimension contiguous, zero OOB fill.  dims / box: innermost first; strides: element
+// strides of dims 1..4.  Operand maps: bf16 + SWIZZLE_128B; output maps: bf16 or fp32 + SWIZZLE_64B.
 int make_map5(CUtensorMap* m, const void* ptr, const long long dims[5], const long long strides_elems[4],
-              const int box[5]) {
+              const int box[5], int elem_bytes = 2, bool output = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return HTRVT_ERR_DRIVER;
   if (reinterpret_cast<uintptr_t>(ptr) & 15) return HTRVT_ERR_ALIGN;
@@ -450,12 +359,13 @@ int make_map5(CUtensorMap* m, const void* ptr, const long long dims[5], const lo
     es[i] = 1;
   }
   for (int i = 0; i < 4; ++i) {
-    gs[i] = static_cast<cuuint64_t>(strides_elems[i]) * 2;
+    gs[i] = static_cast<cuuint64_t>(strides_elems[i]) * elem_bytes;
     if (gs[i] & 15) return HTRVT_ERR_ALIGN;
   }
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                   const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   output ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? HTRVT_OK : HTRVT_ERR_DRIVER;
 }
 
@@ -477,6 +387,16 @@ int make_map_act(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, in
   return make_map5(m, ptr, dims, st, box);
 }
 
+// Output map of a kind-0 GEMM: (cols, w, h, n, 1) with element strides (s_w, s_h, s_n); box = 64 bytes x 128 rows
+int make_map_out(CUtensorMap* m, void* ptr, int elem_bytes, long long cols, long long W, long long H, long long N,
+                 long long s_w, long long s_h, long long s_n) {
+  const long long dims[5] = {cols, W, H, N, 1};
+  const long long big = s_n * (N > 0 ? N : 1);
+  const long long st[4] = {s_w, H > 1 ? s_h : s_w * W, N > 1 ? s_n : (H > 1 ? s_h * H : s_w * W), big > 0 ? big : s_w * W};
+  const int box[5] = {64 / elem_bytes, kBM, 1, 1, 1};
+  return make_map5(m, ptr, dims, st, box, elem_bytes, true);
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {
@@ -489,7 +409,8 @@ int num_sms() {
 }
 
 template <int BN, int KIND, bool B_MN>
-int launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmP& P, int total_tiles, cudaStream_t stream) {
+int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
+               cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   auto kern = tapgemm_kernel<BN, KIND, B_MN>;
@@ -499,17 +420,18 @@ int launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmP& P, int t
     configured = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, P);
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, c, P);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
 
 template <int KIND, bool B_MN>
-int launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmP& P, int total, cudaStream_t s) {
+int launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total,
+              cudaStream_t s) {
   switch (bn) {
-    case 128: return launch_one<128, KIND, B_MN>(a, b, P, total, s);
-    case 192: return launch_one<192, KIND, B_MN>(a, b, P, total, s);
-    case 256: return launch_one<256, KIND, B_MN>(a, b, P, total, s);
+    case 128: return launch_one<128, KIND, B_MN>(a, b, c, P, total, s);
+    case 192: return launch_one<192, KIND, B_MN>(a, b, c, P, total, s);
+    case 256: return launch_one<256, KIND, B_MN>(a, b, c, P, total, s);
   }
   return HTRVT_ERR_SHAPE;
 }
@@ -537,16 +459,33 @@ void fill_taps_conv(TapTab& t, int ks, int pad, int sw, int* n_taps) {
   *n_taps = n;
 }
 
+// Split-K factor for the weight-gradient GEMMs: minimise (waves x per-split tile time) + partial-sum traffic.
+int choose_splits(int base_tiles, long long q_total, long long out_elems) {
+  const int sms = num_sms();
+  double best = 1e300;
+  int best_s = 1;
+  const double tile_us = static_cast<double>(q_total) * 0.23;          // ~0.23 us per 128 x BN x 64 k-chunk
+  for (int s = 1; s <= 32 && s <= q_total; ++s) {
+    const long long tiles = static_cast<long long>(base_tiles) * s;
+    const double waves = static_cast<double>((tiles + sms - 1) / sms);
+    double t = waves * tile_us / s;
+    if (s > 1) t += 2.0 * s * out_elems * 4.0 / 5.0e6;                 // write + read of the partials (us @ 5 TB/s)
+    if (t < best * 0.98) { best = t; best_s = s; }
+  }
+  return best_s;
+}
+
 }  // namespace
 
 // Y[M,N] = epilogue(alpha * X[M,K] W[N,K]^T): nn.Linear forward (both operands K-major).
+// flags: EPI_BF16 (else fp32 out), EPI_BIAS, EPI_RELU, EPI_ACCUM (out += via TMA reduce-add)
 extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long long ldw, int M, int N, int K,
-                             int flags, const float* bias, const float* resid, void* out, long long ldo,
-                             void* out2, float alpha, int qkv_B, int qkv_T, int qkv_H, int qkv_hd,
+                             int flags, const float* bias, void* out, long long ldo, float alpha,
                              cudaStream_t stream) {
-  if (M <= 0 || N <= 0 || K <= 0 || (N & 7) || (ldo & 3)) return HTRVT_ERR_SHAPE;
+  if (M <= 0 || N <= 0 || K <= 0 || (N & 3)) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(N);
-  CUtensorMap ta, tb;
+  const int esz = (flags & EPI_BF16) ? 2 : 4;
+  CUtensorMap ta, tb, tc;
   {
     const long long dims[5] = {K, 1, M, 1, 1};
     const long long st[4] = {ldx, ldx, ldx * M, ldx * M};
@@ -555,24 +494,25 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
     if (r) return r;
     r = make_map_matrix(&tb, W, N, K, ldw, kBK, bn);
     if (r) return r;
+    r = make_map_out(&tc, out, esz, N, M, 1, 1, ldo, ldo * M, ldo * M);
+    if (r) return r;
   }
   GemmP P = {};
-  P.kind = 0; P.Wo = M; P.Ho = 1; P.NB = (flags & EPI_QKV) ? qkv_B : 1;
+  P.kind = 0; P.Wo = M; P.Ho = 1; P.NB = 1;
   P.tiles_per_row = (M + kBM - 1) / kBM; P.tiles_m = P.tiles_per_row; P.tiles_n = (N + bn - 1) / bn;
   P.n_taps = 1; P.splits = 1; P.k_chunks = (K + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = 0;
-  P.M_valid = M; P.N_valid = N; P.flags = flags;
-  P.o_sn = 0; P.o_sh = 0; P.o_sw = ldo; P.o_base = 0;
-  P.out = out; P.out2 = out2; P.bias = bias; P.resid = resid; P.alpha = alpha;
-  P.qkv_T = qkv_T; P.qkv_H = qkv_H; P.qkv_hd = qkv_hd;
-  return launch_bn<0, false>(bn, ta, tb, P, P.tiles_m * P.tiles_n, stream);
+  P.M_valid = M; P.N_valid = N; P.flags = flags & (EPI_BF16 | EPI_BIAS | EPI_RELU | EPI_ACCUM | EPI_NOSTORE);
+  P.bias = bias; P.alpha = alpha;
+  return launch_bn<0, false>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
 
 // dX[M,N] = dY[M,K] W[K,N]: nn.Linear input gradient (B operand MN-major, no transpose copy).
 extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long long ldw, int M, int N, int K,
                              int flags, void* out, long long ldo, float alpha, cudaStream_t stream) {
-  if (M <= 0 || N <= 0 || K <= 0 || (N & 7) || (ldo & 3)) return HTRVT_ERR_SHAPE;
+  if (M <= 0 || N <= 0 || K <= 0 || (N & 7)) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(N);
-  CUtensorMap ta, tb;
+  const int esz = (flags & EPI_BF16) ? 2 : 4;
+  CUtensorMap ta, tb, tc;
   {
     const long long dims[5] = {K, 1, M, 1, 1};
     const long long st[4] = {lddy, lddy, lddy * M, lddy * M};
@@ -581,39 +521,20 @@ extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long
     if (r) return r;
     r = make_map_matrix(&tb, W, K, N, ldw, 64, 64);
     if (r) return r;
+    r = make_map_out(&tc, out, esz, N, M, 1, 1, ldo, ldo * M, ldo * M);
+    if (r) return r;
   }
   GemmP P = {};
   P.kind = 0; P.Wo = M; P.Ho = 1; P.NB = 1;
   P.tiles_per_row = (M + kBM - 1) / kBM; P.tiles_m = P.tiles_per_row; P.tiles_n = (N + bn - 1) / bn;
   P.n_taps = 1; P.splits = 1; P.k_chunks = (K + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = 0;
-  P.M_valid = M; P.N_valid = N; P.flags = flags;
-  P.o_sw = ldo; P.out = out; P.alpha = alpha;
-  return launch_bn<0, true>(bn, ta, tb, P, P.tiles_m * P.tiles_n, stream);
+  P.M_valid = M; P.N_valid = N; P.flags = flags & (EPI_BF16 | EPI_ACCUM | EPI_NOSTORE);
+  P.alpha = alpha;
+  return launch_bn<0, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
-
-namespace {
-// Split-K factor for the weight-gradient GEMMs: minimise (waves x per-split tile time) + partial-sum traffic.
-// base_tiles output tiles, q_total K chunks per tile, out_elems fp32 outputs.
-int choose_splits(int base_tiles, long long q_total, long long out_elems = 0) {
-  const int sms = num_sms();
-  double best = 1e300;
-  int best_s = 1;
-  const double tile_us = static_cast<double>(q_total) * 0.23;          // ~0.23 us per 128xBNx64 k-chunk at full rate
-  for (int s = 1; s <= 32 && s <= q_total; ++s) {
-    const long long tiles = static_cast<long long>(base_tiles) * s;
-    const double waves = static_cast<double>((tiles + sms - 1) / sms);
-    double t = waves * tile_us / s;
-    if (s > 1) t += 2.0 * s * out_elems * 4.0 / 5.0e6;                 // write + read of the partials at ~5 TB/s (us)
-    if (t < best * 0.98) { best = t; best_s = s; }
-  }
-  return best_s;
-}
-}  // namespace
 
 extern "C" size_t htrvt_wgrad_workspace_bytes(int Cout, int Cin, int n_taps, int M_pixels) {
-  const int bn = pick_bn(Cin);
-  const int base = n_taps * ((Cout + kBM - 1) / kBM) * ((Cin + bn - 1) / bn);
-  (void)base; (void)M_pixels;
+  (void)M_pixels;
   return static_cast<size_t>(32) * Cout * n_taps * Cin * sizeof(float);   // upper bound (splits <= 32)
 }
 
@@ -637,13 +558,24 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
   }
 }
 
+namespace {
+// output map of a kind-1 (wgrad) GEMM: fp32 partials [splits][Cout][taps][Cin] as (Cin, Cout, taps, splits, 1)
+int make_map_wgrad_out(CUtensorMap* m, void* ws, int Cout, int taps, int Cin, int splits) {
+  const long long dims[5] = {Cin, Cout, taps, splits, 1};
+  const long long per = static_cast<long long>(Cout) * taps * Cin;
+  const long long st[4] = {static_cast<long long>(taps) * Cin, Cin, per, per * splits};
+  const int box[5] = {16, kBM, 1, 1, 1};
+  return make_map5(m, ws, dims, st, box, 4, true);
+}
+}  // namespace
+
 // dW[Nout, Kin] (+)= dY[M, Nout]^T X[M, Kin]  (both operands MN-major; split-K over M, fp32 partials)
 extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X, long long ldx, int M, int Nout,
                                   int Kin, float* grad, int accumulate, void* workspace, size_t workspace_bytes,
                                   cudaStream_t stream) {
   if (M <= 0 || Nout <= 0 || Kin <= 0 || (Kin & 7) || (Nout & 7)) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(Kin);
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   int r;
   {
     const long long dimsA[5] = {Nout, 1, M, 1, 1};
@@ -664,9 +596,9 @@ extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X,
   P.M_valid = Nout; P.N_valid = Kin; P.flags = 0; P.alpha = 1.f;
   const size_t need = static_cast<size_t>(P.splits) * Nout * Kin * sizeof(float);
   if (!workspace || workspace_bytes < need) return HTRVT_ERR_WORKSPACE;
-  P.o_split = static_cast<long long>(Nout) * Kin; P.o_sw = Kin; P.o_tap = 0; P.o_base = 0;
-  P.out = workspace;
-  r = launch_bn<1, true>(bn, ta, tb, P, P.tiles_m * P.tiles_n * P.splits, stream);
+  r = make_map_wgrad_out(&tc, workspace, Nout, 1, Kin, P.splits);
+  if (r) return r;
+  r = launch_bn<1, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.splits, stream);
   if (r) return r;
   const long long total = static_cast<long long>(Nout) * Kin;
   const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
@@ -679,34 +611,34 @@ extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X,
 // ---------------------------------------------------------------------------------------------
 // Stem convolutions (NHWC bf16 activations, weights [Cout][ks*ks][Cin] bf16, bias-free), Cin % 64 == 0
 // ---------------------------------------------------------------------------------------------
+extern "C" int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw) {
+  (void)NB; (void)H; (void)W; (void)ks; (void)sh; (void)sw;
+  return 4 * num_sms();     // rows of the [ctas * 4 quadrants][2][Cout] partial-statistics buffer (zero-initialised)
+}
+
 extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks,
                               int sh, int sw, void* y, float* stats_partial, int flags, cudaStream_t stream) {
   const int pad = ks / 2;
   if ((Cin % 64) || (Cout & 7) || (W % sw) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
-  if (stats_partial && Cout > kStatCols) return HTRVT_ERR_SHAPE;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
   const int bn = pick_bn(Cout);
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   int r = make_map_act(&ta, x, NB, H, W, Cin, sw, kBK, kBM);
   if (r) return r;
   r = make_map_matrix(&tb, w, Cout, static_cast<long long>(ks) * ks * Cin, static_cast<long long>(ks) * ks * Cin, kBK, bn);
+  if (r) return r;
+  r = make_map_out(&tc, y, 2, Cout, Wo, Ho, NB, Cout, static_cast<long long>(Wo) * Cout,
+                   static_cast<long long>(Ho) * Wo * Cout);
   if (r) return r;
   GemmP P = {};
   P.kind = 0; P.Wo = Wo; P.Ho = Ho; P.NB = NB;
   P.tiles_per_row = (Wo + kBM - 1) / kBM; P.tiles_m = P.tiles_per_row * Ho * NB; P.tiles_n = (Cout + bn - 1) / bn;
   fill_taps_conv(P.tap, ks, pad, sw, &P.n_taps);
   P.splits = 1; P.k_chunks = Cin / kBK; P.a_sh = sh; P.b_tap_stride = Cin;
-  P.M_valid = 0; P.N_valid = Cout; P.flags = EPI_BF16 | flags | (stats_partial ? EPI_STATS : 0);
-  P.o_sn = static_cast<long long>(Ho) * Wo * Cout; P.o_sh = static_cast<long long>(Wo) * Cout; P.o_sw = Cout;
-  P.out = y; P.stats = stats_partial; P.alpha = 1.f;
-  return launch_bn<0, false>(bn, ta, tb, P, P.tiles_m * P.tiles_n, stream);
-}
-
-extern "C" int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw) {
-  const int pad = ks / 2;
-  const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
-  (void)NB; (void)Ho; (void)Wo;
-  return num_sms();   // rows of the [ctas][2][Cout] partial-statistics buffer (upper bound)
+  P.M_valid = 0; P.N_valid = Cout;
+  P.flags = EPI_BF16 | (flags & (EPI_RELU | EPI_NOSTORE)) | (stats_partial ? EPI_STATS : 0);
+  P.stats = stats_partial; P.alpha = 1.f;
+  return launch_bn<0, false>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
 
 // dx[NB,H,W,Cin] (= or +=) conv_transpose(dy[NB,Ho,Wo,Cout], w): one GEMM per output parity class.
@@ -741,10 +673,13 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
       P.tiles_per_row = (Wq + kBM - 1) / kBM; P.tiles_m = P.tiles_per_row * Hq * NB; P.tiles_n = (Cin + bn - 1) / bn;
       P.n_taps = n; P.splits = 1; P.k_chunks = (Cout + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = Cin;
       P.N_valid = Cin; P.flags = EPI_BF16 | (accumulate ? EPI_ACCUM : 0);
-      P.o_sn = static_cast<long long>(H) * W * Cin; P.o_sh = static_cast<long long>(sh) * W * Cin;
-      P.o_sw = static_cast<long long>(sw) * Cin; P.o_base = (static_cast<long long>(ph) * W + pw) * Cin;
-      P.out = dx; P.alpha = 1.f;
-      r = launch_bn<0, true>(bn, ta, tb, P, P.tiles_m * P.tiles_n, stream);
+      P.alpha = 1.f;
+      CUtensorMap tc;                                     // parity class (ph, pw) of dx as a strided tensor
+      r = make_map_out(&tc, static_cast<__nv_bfloat16*>(dx) + (static_cast<long long>(ph) * W + pw) * Cin, 2, Cin, Wq,
+                       Hq, NB, static_cast<long long>(sw) * Cin, static_cast<long long>(sh) * W * Cin,
+                       static_cast<long long>(H) * W * Cin);
+      if (r) return r;
+      r = launch_bn<0, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
       if (r) return r;
     }
   return HTRVT_OK;
@@ -758,7 +693,7 @@ extern "C" int htrvt_conv_wgrad(const void* dy, const void* x, int NB, int H, in
   if ((Cout % 8) || (Cin % 8) || (W % sw) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
   const int bn = pick_bn(Cin);
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tc;
   int r = make_map_act(&ta, dy, NB, Ho, Wo, Cout, 1, 64, 64);
   if (r) return r;
   r = make_map_act(&tb, x, NB, H, W, Cin, sw, 64, 64);
@@ -769,13 +704,13 @@ extern "C" int htrvt_conv_wgrad(const void* dy, const void* x, int NB, int H, in
   fill_taps_conv(P.tap, ks, pad, sw, &P.n_taps);
   P.k_chunks = (Wo + 63) / 64; P.a_sh = sh;
   const long long Q = static_cast<long long>(NB) * Ho * P.k_chunks;
-  P.splits = choose_splits(P.tiles_m * P.tiles_n * P.n_taps, Q, static_cast<long long>(Cout) * P.n_taps * Cin);
-  P.M_valid = Cout; P.N_valid = Cin; P.flags = 0; P.alpha = 1.f;
   const long long per = static_cast<long long>(Cout) * P.n_taps * Cin;
+  P.splits = choose_splits(P.tiles_m * P.tiles_n * P.n_taps, Q, per);
+  P.M_valid = Cout; P.N_valid = Cin; P.flags = 0; P.alpha = 1.f;
   if (!workspace || workspace_bytes < static_cast<size_t>(P.splits) * per * sizeof(float)) return HTRVT_ERR_WORKSPACE;
-  P.o_split = per; P.o_sw = static_cast<long long>(P.n_taps) * Cin; P.o_tap = Cin; P.o_base = 0;
-  P.out = workspace;
-  r = launch_bn<1, true>(bn, ta, tb, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream);
+  r = make_map_wgrad_out(&tc, workspace, Cout, P.n_taps, Cin, P.splits);
+  if (r) return r;
+  r = launch_bn<1, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream);
   if (r) return r;
   const int blocks = static_cast<int>((per + 255) / 256 < 2048 ? (per + 255) / 256 : 2048);
   wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), P.splits, Cout, P.n_taps, Cin,

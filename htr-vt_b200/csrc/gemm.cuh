@@ -14,11 +14,8 @@ struct TapTab {
 enum : int {
   EPI_BF16 = 1 << 0,       // store bf16 (else fp32)
   EPI_BIAS = 1 << 1,       // + bias[n]
-  EPI_GELU = 1 << 2,       // out2 = pre-activation (bf16), out = gelu(pre) (bf16)
-  EPI_RESID = 1 << 3,      // + resid_f32[row, n] (fp32, same addressing as out)
-  EPI_ACCUM = 1 << 4,      // out += (read-modify-write, same dtype as out)
-  EPI_STATS = 1 << 5,      // per-tile column sum / sum of squares -> stats[tile_m][2][N]
-  EPI_QKV = 1 << 6,        // scatter columns to [3][B][H][T][hd]
+  EPI_ACCUM = 1 << 4,      // out += (TMA reduce-add store)
+  EPI_STATS = 1 << 5,      // column sum / sum of squares of the stored tile -> stats[cta*4+quadrant][2][N] (+=)
   EPI_RELU = 1 << 7,       // max(x, 0)
   EPI_NOSTORE = 1 << 8,    // measurement aid: skip the epilogue body (main-loop-only timing)
 };
@@ -34,14 +31,8 @@ struct GemmP {
   TapTab tap;
   int M_valid, N_valid;    // kind 1: rows (Cout) valid; columns valid
   int flags;
-  // epilogue addressing (elements)
-  long long o_sn, o_sh, o_sw, o_base, o_split, o_tap;
-  void* out;
-  void* out2;
   const float* bias;
-  const float* resid;
   float* stats;
-  int qkv_T, qkv_H, qkv_hd;
   float alpha;             // scale applied to the accumulator
 };
 

@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(1024) sample_ln_bwd_kernel(const float* __rest
 // Row LayerNorm with affine (D % 128 == 0, D <= 1024): one warp per row
 // ------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(256) row_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) row_ln_fwd_kernel(const float* __restrict__ x,
+                                                         const __nv_bfloat16* __restrict__ addend,
+                                                         float* __restrict__ x_out, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta,
                                                          __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                                                          float* __restrict__ rstd_out, int M, float eps) {
@@ -95,6 +97,12 @@ __global__ void __launch_bounds__(256) row_ln_fwd_kernel(const float* __restrict
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     v[i] = *reinterpret_cast<const float4*>(xr + lane * 4 + 128 * i);
+    if (addend) {       // residual stream update fused here: x_out = x + addend (the preceding GEMM's bf16 output)
+      const uint2 u = *reinterpret_cast<const uint2*>(addend + static_cast<long long>(row) * D + lane * 4 + 128 * i);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+      v[i].x += a.x; v[i].y += a.y; v[i].z += b.x; v[i].w += b.y;
+      *reinterpret_cast<float4*>(x_out + static_cast<long long>(row) * D + lane * 4 + 128 * i) = v[i];
+    }
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mean = warp_sum(s) * (1.0f / D);
@@ -260,6 +268,24 @@ __device__ __forceinline__ float gelu_grad(float u) {
   const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
   return cdf + u * pdf;
 }
+// a = gelu(u), exact erf form (nn.GELU default used by timm Mlp); separate full-occupancy kernel because the
+// GEMM epilogue is run by 8 warps only
+__global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ a, long long n8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 b = *reinterpret_cast<const uint4*>(u + i * 8);
+    uint4 o;
+    float2 y;
+#define HTRVT_G(v) (0.5f * (v) * (1.0f + erff((v) * 0.70710678118654752f)))
+    y = unpack_bf16(b.x); o.x = pack_bf16(HTRVT_G(y.x), HTRVT_G(y.y));
+    y = unpack_bf16(b.y); o.y = pack_bf16(HTRVT_G(y.x), HTRVT_G(y.y));
+    y = unpack_bf16(b.z); o.z = pack_bf16(HTRVT_G(y.x), HTRVT_G(y.y));
+    y = unpack_bf16(b.w); o.w = pack_bf16(HTRVT_G(y.x), HTRVT_G(y.y));
+#undef HTRVT_G
+    *reinterpret_cast<uint4*>(a + i * 8) = o;
+  }
+}
+
 __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ u,
                                 __nv_bfloat16* __restrict__ du, long long n8) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
@@ -353,16 +379,20 @@ extern "C" int htrvt_sample_ln_bwd(const float* dy, const float* y, const float*
   return HTRVT_OK;
 }
 
-extern "C" int htrvt_row_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* mean,
-                                float* rstd, int M, int D, float eps, cudaStream_t stream) {
-  if (M <= 0) return HTRVT_ERR_SHAPE;
+// y = LN(x [+ addend]); when addend (bf16 [M,D]) is given, x_out (fp32) receives x + addend (may alias x)
+extern "C" int htrvt_row_ln_fwd(const float* x, const void* addend_bf16, float* x_out, const float* gamma,
+                                const float* beta, void* y_bf16, float* mean, float* rstd, int M, int D, float eps,
+                                cudaStream_t stream) {
+  if (M <= 0 || (addend_bf16 && !x_out)) return HTRVT_ERR_SHAPE;
   const int grid = (M + 7) / 8;
+  const __nv_bfloat16* ad = static_cast<const __nv_bfloat16*>(addend_bf16);
+  __nv_bfloat16* yo = static_cast<__nv_bfloat16*>(y_bf16);
   if (D == 768)
-    row_ln_fwd_kernel<768><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, M, eps);
+    row_ln_fwd_kernel<768><<<grid, 256, 0, stream>>>(x, ad, x_out, gamma, beta, yo, mean, rstd, M, eps);
   else if (D == 128)
-    row_ln_fwd_kernel<128><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, M, eps);
+    row_ln_fwd_kernel<128><<<grid, 256, 0, stream>>>(x, ad, x_out, gamma, beta, yo, mean, rstd, M, eps);
   else if (D == 256)
-    row_ln_fwd_kernel<256><<<grid, 256, 0, stream>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(y_bf16), mean, rstd, M, eps);
+    row_ln_fwd_kernel<256><<<grid, 256, 0, stream>>>(x, ad, x_out, gamma, beta, yo, mean, rstd, M, eps);
   else
     return HTRVT_ERR_SHAPE;
   HTRVT_LAUNCH_CHECK();
@@ -420,6 +450,14 @@ extern "C" int htrvt_tokens_bwd(const float* gx, const float* mask, void* dtok_b
     colsum_finalize_kernel<<<(D + 31) / 32, 256, 0, stream>>>(partial, T, D, D, dmask_token, 1);
     HTRVT_LAUNCH_CHECK();
   }
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_gelu_fwd(const void* u, void* a, long long n, cudaStream_t stream) {
+  if (n <= 0 || (n & 7)) return HTRVT_ERR_SHAPE;
+  gelu_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(u),
+                                                            static_cast<__nv_bfloat16*>(a), n / 8);
+  HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
 

@@ -113,27 +113,29 @@ class Engine(object):
         xs = ops.tokens_fwd(tok, mask, sd["mask_token"], pos, B, T, D)
         scale = self.hd ** -0.5
         tblocks = []
+        pend = None                       # bf16 GEMM output still to be added to the residual stream
         for i in range(self.depth):
             p = "blocks.%d" % i
-            h1, m1, r1s = ops.row_ln_fwd(xs, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], self.ln_eps)
-            qkv = torch.empty((3, B, self.H, T, self.hd), dtype=torch.bfloat16, device=xs.device)
-            ops.gemm_tn(h1, wp[p + ".attn.qkv.weight"], qkv, bias=sd[p + ".attn.qkv.bias"], qkv=(B, T, self.H, self.hd))
+            # x1 = xs + pend (previous block's fc2 output), h1 = LN1(x1): the residual add is fused into the LN
+            h1, m1, r1s, x1 = ops.row_ln_fwd(xs, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], self.ln_eps, pend)
+            qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=xs.device)
+            ops.gemm_tn(h1, wp[p + ".attn.qkv.weight"], qkv, bias=sd[p + ".attn.qkv.bias"])
             o = torch.empty((M, D), dtype=torch.bfloat16, device=xs.device)
             lse = torch.empty((B, self.H, T), dtype=torch.float32, device=xs.device)
-            ops.attention_fwd(qkv, o.view(B, T, D), lse, scale)
-            x2 = torch.empty_like(xs)
-            ops.gemm_tn(o, wp[p + ".attn.proj.weight"], x2, bias=sd[p + ".attn.proj.bias"], resid=xs)
-            h2, m2, r2s = ops.row_ln_fwd(x2, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], self.ln_eps)
+            ops.attention_fwd(qkv.view(B, T, 3, self.H, self.hd), o.view(B, T, D), lse, scale)
+            y1 = torch.empty((M, D), dtype=torch.bfloat16, device=xs.device)
+            ops.gemm_tn(o, wp[p + ".attn.proj.weight"], y1, bias=sd[p + ".attn.proj.bias"])
+            h2, m2, r2s, x2 = ops.row_ln_fwd(x1, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], self.ln_eps, y1)
             hid = wp[p + ".mlp.fc1.weight"].shape[0]
-            a = torch.empty((M, hid), dtype=torch.bfloat16, device=xs.device)
             u = torch.empty((M, hid), dtype=torch.bfloat16, device=xs.device)
-            ops.gemm_tn(h2, wp[p + ".mlp.fc1.weight"], a, bias=sd[p + ".mlp.fc1.bias"], out2=u)
-            x3 = torch.empty_like(xs)
-            ops.gemm_tn(a, wp[p + ".mlp.fc2.weight"], x3, bias=sd[p + ".mlp.fc2.bias"], resid=x2)
+            ops.gemm_tn(h2, wp[p + ".mlp.fc1.weight"], u, bias=sd[p + ".mlp.fc1.bias"])
+            a = ops.gelu_fwd(u)
+            y2 = torch.empty((M, D), dtype=torch.bfloat16, device=xs.device)
+            ops.gemm_tn(a, wp[p + ".mlp.fc2.weight"], y2, bias=sd[p + ".mlp.fc2.bias"])
             if save:
-                tblocks.append((p, xs, h1, m1, r1s, qkv, o, lse, x2, h2, m2, r2s, a, u))
-            xs = x3
-        hf, mf, rf = ops.row_ln_fwd(xs, sd["norm.weight"], sd["norm.bias"], self.ln_eps)
+                tblocks.append((p, x1, h1, m1, r1s, qkv, o, lse, x2, h2, m2, r2s, a, u))
+            xs, pend = x2, y2
+        hf, mf, rf, xs = ops.row_ln_fwd(xs, sd["norm.weight"], sd["norm.bias"], self.ln_eps, pend)
         raw_logits = torch.empty((M, C), dtype=torch.float32, device=xs.device)
         ops.gemm_tn(hf, wp["head.weight"], raw_logits, bias=sd["head.bias"])
         if self.variant == "v1":
@@ -190,7 +192,8 @@ class Engine(object):
             do = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
             ops.gemm_nn(gy, wp[p + ".attn.proj.weight"], do)
             dqkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
-            ops.attention_bwd(qkv, o.view(B, T, D), do.view(B, T, D), lse, dqkv.view(B, T, 3, self.H, self.hd), scale)
+            ops.attention_bwd(qkv.view(B, T, 3, self.H, self.hd), o.view(B, T, D), do.view(B, T, D), lse,
+                              dqkv.view(B, T, 3, self.H, self.hd), scale)
             ops.linear_wgrad(dqkv, h1, grads[p + ".attn.qkv.weight"])
             ops.colsum_bf16(dqkv, grads[p + ".attn.qkv.bias"])
             dh1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)

@@ -8,7 +8,7 @@ import torch
 
 from ._lib import HtrvtError, check, lib
 
-EPI_BF16, EPI_BIAS, EPI_GELU, EPI_RESID, EPI_ACCUM, EPI_STATS, EPI_QKV, EPI_RELU = (1 << i for i in range(8))
+EPI_BF16, EPI_BIAS, _EPI_2, _EPI_3, EPI_ACCUM, EPI_STATS, _EPI_6, EPI_RELU = (1 << i for i in range(8))
 
 
 def _p(t):
@@ -41,19 +41,15 @@ def workspace(nbytes: int, device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # GEMMs
 # ------------------------------------------------------------------------------------------------
-def gemm_tn(x, w, out, *, bias=None, resid=None, out2=None, flags=0, alpha=1.0, qkv=None):
-    """out[M,N] = epilogue(alpha * x[M,K] @ w[N,K]^T).  x, w bf16 row-major."""
+def gemm_tn(x, w, out, *, bias=None, relu=False, accumulate=False, flags=0, alpha=1.0):
+    """out[M,N] (+)= epilogue(alpha * x[M,K] @ w[N,K]^T).  x, w bf16 row-major; out bf16 or fp32 [M, N] view."""
     _need_cuda(x, w, out)
     M, K = x.shape
     N = w.shape[0]
     f = flags | (EPI_BF16 if out.dtype == torch.bfloat16 else 0) | (EPI_BIAS if bias is not None else 0) \
-        | (EPI_RESID if resid is not None else 0) | (EPI_GELU if out2 is not None else 0)
-    qb, qt, qh, qd = qkv if qkv is not None else (0, 0, 0, 0)
-    if qkv is not None:
-        f |= EPI_QKV
-    ldo = out.stride(0) if (qkv is None and out.dim() == 2) else 0
-    check(lib().htrvt_gemm_tn(_p(x), x.stride(0), _p(w), w.stride(0), M, N, K, f, _p(bias), _p(resid), _p(out), ldo,
-                              _p(out2), alpha, qb, qt, qh, qd, _stream()), "htrvt_gemm_tn")
+        | (EPI_RELU if relu else 0) | (EPI_ACCUM if accumulate else 0)
+    check(lib().htrvt_gemm_tn(_p(x), x.stride(0), _p(w), w.stride(0), M, N, K, f, _p(bias), _p(out), out.stride(0),
+                              alpha, _stream()), "htrvt_gemm_tn")
     return out
 
 
@@ -131,9 +127,9 @@ def conv_wgrad(dy, x, ks, sh, sw, grad_oihw, accumulate=True):
 # Attention
 # ------------------------------------------------------------------------------------------------
 def attention_fwd(qkv, out, lse, scale):
-    """qkv bf16 [3,B,H,T,hd] -> out bf16 [B,T,H*hd]; lse fp32 [B,H,T]."""
+    """qkv bf16 [B,T,3,H,hd] (token-major projection output) -> out bf16 [B,T,H*hd]; lse fp32 [B,H,T]."""
     _need_cuda(qkv, out)
-    _, B, H, T, hd = qkv.shape
+    B, T, _, H, hd = qkv.shape
     check(lib().htrvt_attention_fwd(_p(qkv), B, H, T, hd, scale, _p(out), _p(lse), _stream()), "htrvt_attention_fwd")
     return out
 
@@ -141,7 +137,7 @@ def attention_fwd(qkv, out, lse, scale):
 def attention_bwd(qkv, out, dout, lse, dqkv, scale):
     """-> dqkv bf16 [B,T,3,H,hd] (token-major gradient of the qkv projection output)."""
     _need_cuda(qkv, out, dout, lse, dqkv)
-    _, B, H, T, hd = qkv.shape
+    B, T, _, H, hd = qkv.shape
     check(lib().htrvt_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), B, H, T, hd, scale, _p(dqkv), _stream()),
           "htrvt_attention_bwd")
     return dqkv
@@ -256,13 +252,16 @@ def sample_ln_bwd(dy, y, rstd, C, ld_out):
     return dx
 
 
-def row_ln_fwd(x, gamma, beta, eps):
+def row_ln_fwd(x, gamma, beta, eps, addend=None):
+    """y = LN(x [+ addend]) as bf16.  With `addend` (bf16 [M,D], the preceding GEMM's output) the residual update
+    x_new = x + addend is fused here and returned (fp32).  -> (y, mean, rstd, x_new | x)"""
     M, D = x.shape
     y = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
     mean, rstd = _f32(M, x.device), _f32(M, x.device)
-    check(lib().htrvt_row_ln_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, D, eps, _stream()),
-          "htrvt_row_ln_fwd")
-    return y, mean, rstd
+    x_new = torch.empty_like(x) if addend is not None else None
+    check(lib().htrvt_row_ln_fwd(_p(x), _p(addend), _p(x_new), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, D,
+                                 eps, _stream()), "htrvt_row_ln_fwd")
+    return y, mean, rstd, (x_new if addend is not None else x)
 
 
 def row_ln_bwd(dy, x, mean, rstd, gamma, gx, accumulate, dgamma, dbeta):
@@ -287,6 +286,12 @@ def tokens_bwd(gx, mask, dmask_token, B, T, D):
     check(lib().htrvt_tokens_bwd(_p(gx), _p(mask), _p(dtok), _p(dmask_token if mask is not None else None),
                                  _p(partial), B, T, D, _stream()), "htrvt_tokens_bwd")
     return dtok
+
+
+def gelu_fwd(u):
+    a = torch.empty_like(u)
+    check(lib().htrvt_gelu_fwd(_p(u), _p(a), u.numel(), _stream()), "htrvt_gelu_fwd")
+    return a
 
 
 def gelu_bwd(da, u):
@@ -436,10 +441,10 @@ def _flops(name, a, kw):
             dy, x, ks = a[:3]
             return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * x.shape[3]
         if name == "attention_fwd":
-            _, B, H, T, hd = a[0].shape
+            B, T, _, H, hd = a[0].shape
             return 4.0 * B * H * T * T * hd
         if name == "attention_bwd":
-            _, B, H, T, hd = a[0].shape
+            B, T, _, H, hd = a[0].shape
             return 10.0 * B * H * T * T * hd
     except Exception:
         pass
@@ -451,7 +456,7 @@ def _instrument():
     g = globals()
     names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "attention_fwd",
              "attention_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd",
-             "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_bwd", "colsum_bf16", "cast_bf16",
+             "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16",
              "pack_conv_weight", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",
              "conv1_wgrad"]
     for name in names:

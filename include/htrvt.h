@@ -51,15 +51,14 @@ int htrvt_ctc_collapse(const void* index, int index_is_int64, const int* lengths
                        int* ids, int* lens, void* stream);
 
 /* ---- tcgen05 tap-GEMM: nn.Linear / nn.Conv2d forward, input gradient, weight gradient ------------------
- * flags (epilogue): 1 bf16 out, 2 +bias, 4 GELU(erf) with pre-activation to out2, 8 +fp32 residual,
- * 16 accumulate into out, 32 column statistics, 64 QKV head-major scatter, 128 ReLU.
+ * flags (epilogue, run by 8 warps and kept light): 1 bf16 out (else fp32), 2 +bias, 16 accumulate into out
+ * (TMA reduce-add store), 32 column statistics (conv fwd), 128 ReLU.  Outputs leave through TMA stores.
  * htrvt_gemm_tn : Y = X W^T          nn.Linear fwd: attn.qkv / attn.proj (model_v1/model/HTR_VT.py:29,37),
  *                                    timm Mlp fc1 (+GELU) / fc2 (:76), head (:238)
  * htrvt_gemm_nn : dX = dY W          the same layers' input gradient (autograd of F.linear)
  * htrvt_linear_wgrad : dW (+)= dY^T X  the same layers' weight gradient, fp32, split-K workspace */
 int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long long ldw, int M, int N, int K, int flags,
-                  const float* bias, const float* resid, void* out, long long ldo, void* out2, float alpha,
-                  int qkv_B, int qkv_T, int qkv_H, int qkv_hd, void* stream);
+                  const float* bias, void* out, long long ldo, float alpha, void* stream);
 int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long long ldw, int M, int N, int K, int flags,
                   void* out, long long ldo, float alpha, void* stream);
 size_t htrvt_wgrad_workspace_bytes(int Cout, int Cin, int n_taps, int M_pixels);
@@ -68,7 +67,7 @@ int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X, long long 
 /* conv3x3 / 1x1 of BasicBlock and the downsample branch (model_v1/model/resnet18.py:4-7,23-39,56-63):
  * x NHWC bf16 [NB,H,W,Cin], w bf16 [Cout][ks*ks][Cin], stride (sh,sw), pad ks/2, bias-free.
  * stats_partial (optional): fp32 [htrvt_conv_fwd_stats_rows()][2][Cout] zero-initialised by the caller;
- * receives per-CTA column sum / sum of squares of the stored bf16 output (BatchNorm batch statistics). */
+ * receives per-warp-quadrant column sum / sum of squares of the stored bf16 output (BatchNorm batch statistics). */
 int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks, int sh, int sw,
                    void* y, float* stats_partial, int flags, void* stream);
 int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw);
@@ -80,8 +79,9 @@ int htrvt_conv_wgrad(const void* dy, const void* x, int NB, int H, int W, int Ci
 
 /* ---- attention -------------------------------------------------------------------------------------------
  * Replaces Attention.forward's `q @ k^T * scale -> softmax -> @ v -> transpose/reshape`
- * (model_v1/model/HTR_VT.py:32-36) and its backward.  qkv bf16 [3][B][H][T][128] (written by htrvt_gemm_tn with
- * the QKV flag), out bf16 [B][T][H*128], lse fp32 [B][H][T], dqkv bf16 [B][T][3][H][128].  T <= 128. */
+ * (model_v1/model/HTR_VT.py:32-36) and its backward.  qkv bf16 token-major [B][T][3][H][128] (the QKV projection
+ * output as htrvt_gemm_tn writes it: no reshape/permute copy), out bf16 [B][T][H*128], lse fp32 [B][H][T],
+ * dqkv bf16 [B][T][3][H][128].  T <= 128. */
 int htrvt_attention_fwd(const void* qkv, int B, int H, int T, int hd, float scale, void* out, float* lse,
                         void* stream);
 int htrvt_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int H, int T,
@@ -91,16 +91,17 @@ int htrvt_attention_bwd(const void* qkv, const void* out, const void* dout, cons
  * sample_ln : parameter-free LayerNorm over all non-batch dims, eps 1e-5 (model_v1/model/HTR_VT.py:134-136,
  *             used at :224 on the image and :239 on the logits slab)
  * row_ln    : nn.LayerNorm(D, eps=1e-6) with affine (:68,75,169), fp32 residual stream in, bf16 GEMM operand out;
+ *             the residual update `x + attn(...)` / `x + mlp(...)` (Block.forward :80-83) is fused in as `addend`;
  *             backward accumulates into the fp32 residual gradient and into dgamma / dbeta
  * tokens    : `x * mask + (1 - mask) * mask_token` then `+ pos_embed` (:212-220, 229-231)
- * gelu_bwd  : nn.GELU (erf form) backward for timm Mlp; colsum_bf16: bias gradients; cast / pack: bf16 operand
+ * gelu_fwd/bwd : nn.GELU (erf form) of timm Mlp; colsum_bf16: bias gradients; cast / pack: bf16 operand
  *             copies of the fp32 master weights ([out,in] and OIHW -> [Cout][taps][Cin]). */
 int htrvt_sample_ln_fwd(const float* x, void* y, int y_is_bf16, float* mean, float* rstd, int B, int N, float eps,
                         void* stream);
 int htrvt_sample_ln_bwd(const float* dy, const float* y, const float* rstd, void* dx_bf16, int B, int N, int C,
                         int ld_out, void* stream);
-int htrvt_row_ln_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* mean, float* rstd,
-                     int M, int D, float eps, void* stream);
+int htrvt_row_ln_fwd(const float* x, const void* addend_bf16, float* x_out, const float* gamma, const float* beta,
+                     void* y_bf16, float* mean, float* rstd, int M, int D, float eps, void* stream);
 int htrvt_row_ln_bwd_ctas(int M);
 int htrvt_row_ln_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
                      float* gx, int accumulate, float* dgamma, float* dbeta, float* partial, int M, int D,
@@ -109,6 +110,7 @@ int htrvt_tokens_fwd(const void* tok_bf16, const float* mask, const float* mask_
                      int B, int T, int D, void* stream);
 int htrvt_tokens_bwd(const float* gx, const float* mask, void* dtok_bf16, float* dmask_token, float* partial, int B,
                      int T, int D, void* stream);
+int htrvt_gelu_fwd(const void* u, void* a, long long n, void* stream);
 int htrvt_gelu_bwd(const void* da, const void* u, void* du, long long n, void* stream);
 int htrvt_colsum_rows(int M);
 int htrvt_colsum_bf16(const void* a, long long ld, int M, int N, float* out, int accumulate, float* partial,

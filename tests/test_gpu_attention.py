@@ -22,11 +22,12 @@ def test_attention_fwd_bwd(B, H, T):
     o = ops()
     hd = 128
     torch.manual_seed(0)
-    qkv = (torch.randn(3, B, H, T, hd, device="cuda") * 0.7).bfloat16()
+    qkv_tm = (torch.randn(B, T, 3, H, hd, device="cuda") * 0.7).bfloat16()     # token-major, as the QKV GEMM writes it
+    qkv = qkv_tm.permute(2, 0, 3, 1, 4)
     scale = hd ** -0.5
     out = torch.empty(B, T, H * hd, device="cuda", dtype=torch.bfloat16)
     lse = torch.empty(B, H, T, device="cuda")
-    o.attention_fwd(qkv, out, lse, scale)
+    o.attention_fwd(qkv_tm, out, lse, scale)
     q, k, v = [t.float().requires_grad_(True) for t in qkv]
     s = (q @ k.transpose(-2, -1)) * scale
     p = s.softmax(-1)
@@ -36,7 +37,7 @@ def test_attention_fwd_bwd(B, H, T):
     dout = torch.randn(B, T, H * hd, device="cuda").bfloat16()
     ref.backward(dout.float())
     dqkv = torch.empty(B, T, 3, H, hd, device="cuda", dtype=torch.bfloat16)
-    o.attention_bwd(qkv, out, dout, lse, dqkv, scale)
+    o.attention_bwd(qkv_tm, out, dout, lse, dqkv, scale)
     for i, t in enumerate((q, k, v)):
         want = t.grad.permute(0, 2, 1, 3)          # [B,T,H,hd]
         assert _rel(dqkv[:, :, i], want) < 2e-2, i

@@ -35,7 +35,7 @@ def test_gemm_tn_bias(M, N, K):
     assert _rel(out32, ref) < 1e-4
 
 
-def test_gemm_tn_gelu_resid_qkv():
+def test_gemm_tn_relu_accumulate():
     o = ops()
     torch.manual_seed(1)
     M, N, K = 1024, 3072, 768
@@ -44,25 +44,20 @@ def test_gemm_tn_gelu_resid_qkv():
     b = torch.randn(N, device="cuda") * 0.1
     pre = x.float() @ w.float().t() + b
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    o.gemm_tn(x, w, out, bias=b, out2=out2)
-    assert _rel(out2, pre) < 1e-2
-    assert _rel(out, F.gelu(pre)) < 1e-2
-    # residual fp32
-    w2 = (torch.randn(768, N, device="cuda") / N ** 0.5).bfloat16()
-    res = torch.randn(M, 768, device="cuda")
-    y = torch.empty(M, 768, device="cuda")
-    a = out
-    o.gemm_tn(a, w2, y, bias=b[:768].contiguous(), resid=res)
-    assert _rel(y, a.float() @ w2.float().t() + b[:768] + res) < 1e-4
-    # qkv scatter: [3][B][H][T][hd]
-    B, T, H, hd = 8, 128, 6, 128
-    wq = (torch.randn(3 * H * hd, K, device="cuda") / K ** 0.5).bfloat16()
-    bq = torch.randn(3 * H * hd, device="cuda") * 0.1
-    qkv = torch.empty(3, B, H, T, hd, device="cuda", dtype=torch.bfloat16)
-    o.gemm_tn(x, wq, qkv, bias=bq, qkv=(B, T, H, hd))
-    ref = (x.float() @ wq.float().t() + bq).reshape(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
-    assert _rel(qkv, ref) < 1e-2
+    o.gemm_tn(x, w, out, bias=b, relu=True)
+    assert _rel(out, torch.relu(pre)) < 1e-2
+    acc = torch.randn(M, N, device="cuda")
+    base = acc.clone()
+    o.gemm_tn(x, w, acc, bias=b, accumulate=True)           # TMA reduce-add into fp32
+    assert _rel(acc, base + pre) < 1e-4
+    accb = torch.randn(M, N, device="cuda").bfloat16()
+    baseb = accb.clone()
+    o.gemm_tn(x, w, accb, accumulate=True)                  # TMA reduce-add into bf16
+    assert _rel(accb, baseb.float() + (pre - b)) < 1.5e-2
+    # strided (column-sliced) output view
+    big = torch.zeros(M, N + 64, device="cuda", dtype=torch.bfloat16)
+    o.gemm_tn(x, w, big[:, :N], bias=b)
+    assert _rel(big[:, :N], pre) < 1e-2 and float(big[:, N:].abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("M,N,K", [(16384, 768, 2304), (1024, 768, 80), (16384, 3072, 768), (300, 192, 384)])
@@ -131,7 +126,8 @@ def test_conv_fwd_dgrad_wgrad(NB, H, W, Cin, Cout, ks, sh, sw):
     yr = F.conv2d(xr, wr, None, (sh, sw), ks // 2)
     rows = o.conv_stats_rows(NB, H, W, ks, sh, sw)
     stats = torch.zeros(rows, 2, Cout, device="cuda")
-    y = o.conv_fwd(x, wk, ks, sh, sw, stats=stats)
+    y = torch.full((NB, yr.shape[2], yr.shape[3], Cout), 7.0, device="cuda", dtype=torch.bfloat16)
+    y = o.conv_fwd(x, wk, ks, sh, sw, y=y, stats=stats)
     assert y.shape == (NB, yr.shape[2], yr.shape[3], Cout)
     assert _rel(y.permute(0, 3, 1, 2), yr) < 1e-2
     yf = y.float()

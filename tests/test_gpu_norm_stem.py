@@ -43,7 +43,11 @@ def test_row_ln_fwd_bwd():
     x = (torch.randn(M, D, device="cuda") * 2 + 0.5).requires_grad_(True)
     g = (torch.rand(D, device="cuda") + 0.5).requires_grad_(True)
     b = torch.randn(D, device="cuda").requires_grad_(True)
-    y, mean, rstd = o.row_ln_fwd(x.detach(), g.detach(), b.detach(), 1e-6)
+    y, mean, rstd, _ = o.row_ln_fwd(x.detach(), g.detach(), b.detach(), 1e-6)
+    ad = torch.randn(M, D, device="cuda").bfloat16()
+    y2, _, _, xn = o.row_ln_fwd(x.detach(), g.detach(), b.detach(), 1e-6, ad)
+    assert _rel(xn, x.detach() + ad.float()) < 1e-6
+    assert _rel(y2, F.layer_norm(x.detach() + ad.float(), (D,), g.detach(), b.detach(), 1e-6)) < 1e-2
     ref = F.layer_norm(x, (D,), g, b, 1e-6)
     assert _rel(y, ref) < 1e-2
     dy = torch.randn(M, D, device="cuda").bfloat16()
@@ -82,6 +86,7 @@ def test_tokens_gelu_colsum_cast():
     uf = u.float().requires_grad_(True)
     F.gelu(uf).backward(da.float())
     assert _rel(o.gelu_bwd(da, u), uf.grad) < 1e-2
+    assert _rel(o.gelu_fwd(u), F.gelu(u.float())) < 1e-2
     a = torch.randn(3000, 776, device="cuda").bfloat16()
     out = torch.ones(770, device="cuda")
     o.colsum_bf16(a[:, :770], out, accumulate=True)

@@ -26,7 +26,8 @@ a_out, u_out = torch.empty(M, 3072, device=dev, dtype=torch.bfloat16), torch.emp
 qkv = torch.empty(3, 128, 6, 128, 128, device=dev, dtype=torch.bfloat16)
 xl1 = torch.randn(128, 8, 512, 192, device=dev).bfloat16()
 wl1 = torch.randn(192, 9, 192, device=dev).bfloat16()
-stats = torch.zeros(148, 2, 192, device=dev)
+stats = torch.zeros(4 * 148, 2, 192, device=dev)
+stats3 = torch.zeros(4 * 148, 2, 768, device=dev)
 yl1 = torch.empty(128, 8, 512, 192, device=dev, dtype=torch.bfloat16)
 gl1 = torch.zeros(192, 192, 3, 3, device=dev)
 xl3 = torch.randn(128, 2, 128, 768, device=dev).bfloat16()
@@ -36,23 +37,21 @@ gl3 = torch.zeros(768, 768, 3, 3, device=dev)
 g_fc1 = torch.zeros(3072, 768, device=dev)
 
 cases = {
-    "proj_resid": (lambda: o.gemm_tn(x768, w_proj, y32, bias=b768, resid=res), 2.0 * M * 768 * 768),
-    "fc1_gelu": (lambda: o.gemm_tn(x768, w_fc1, a_out, bias=b3072, out2=u_out), 2.0 * M * 3072 * 768),
-    "fc2_resid": (lambda: o.gemm_tn(x3072, w_fc2, y32, bias=b768, resid=res), 2.0 * M * 3072 * 768),
-    "qkv": (lambda: o.gemm_tn(x768, w_qkv, qkv, bias=b2304, qkv=(128, 128, 6, 128)), 2.0 * M * 2304 * 768),
+    "proj": (lambda: o.gemm_tn(x768, w_proj, a_out.view(-1)[: M * 768].view(M, 768), bias=b768), 2.0 * M * 768 * 768),
+    "fc1": (lambda: o.gemm_tn(x768, w_fc1, a_out, bias=b3072), 2.0 * M * 3072 * 768),
+    "fc2": (lambda: o.gemm_tn(x3072, w_fc2, u_out.view(-1)[: M * 768].view(M, 768), bias=b768), 2.0 * M * 3072 * 768),
+    "qkv": (lambda: o.gemm_tn(x768, w_qkv, a_out.view(-1)[: M * 2304].view(M, 2304), bias=b2304), 2.0 * M * 2304 * 768),
     "fc1_dgrad": (lambda: o.gemm_nn(x3072, w_fc1, yl1.view(-1)[: M * 768].view(M, 768)), 2.0 * M * 3072 * 768),
     "fc1_wgrad": (lambda: o.linear_wgrad(x3072, x768, g_fc1), 2.0 * M * 3072 * 768),
     "l1_fwd_stats": (lambda: o.conv_fwd(xl1, wl1, 3, 1, 1, y=yl1, stats=stats), 2.0 * 128 * 8 * 512 * 192 * 1728),
+    "l1_fwd_nostats": (lambda: o.conv_fwd(xl1, wl1, 3, 1, 1, y=yl1), 2.0 * 128 * 8 * 512 * 192 * 1728),
+    "l1_fwd_nostore": (lambda: o.conv_fwd(xl1, wl1, 3, 1, 1, y=yl1, nostore=True), 2.0 * 128 * 8 * 512 * 192 * 1728),
     "l1_dgrad": (lambda: o.conv_dgrad(yl1, wl1, (128, 8, 512, 192), 3, 1, 1, dx=xl1), 2.0 * 128 * 8 * 512 * 192 * 1728),
+    "l1_dgrad_acc": (lambda: o.conv_dgrad(yl1, wl1, (128, 8, 512, 192), 3, 1, 1, dx=xl1, accumulate=True), 2.0 * 128 * 8 * 512 * 192 * 1728),
     "l1_wgrad": (lambda: o.conv_wgrad(yl1, xl1, 3, 1, 1, gl1), 2.0 * 128 * 8 * 512 * 192 * 1728),
-    "l3_fwd_stats": (lambda: o.conv_fwd(xl3, wl3, 3, 1, 1, y=yl3), 2.0 * 128 * 2 * 128 * 768 * 6912),
+    "l3_fwd_stats": (lambda: o.conv_fwd(xl3, wl3, 3, 1, 1, y=yl3, stats=stats3), 2.0 * 128 * 2 * 128 * 768 * 6912),
     "l3_wgrad": (lambda: o.conv_wgrad(yl3, xl3, 3, 1, 1, gl3), 2.0 * 128 * 2 * 128 * 768 * 6912),
 }
-cases["proj_nostore"] = (lambda: o.gemm_tn(x768, w_proj, y32, bias=b768, resid=res, flags=256), 2.0 * M * 768 * 768)
-cases["fc1_nostore"] = (lambda: o.gemm_tn(x768, w_fc1, a_out, bias=b3072, out2=u_out, flags=256), 2.0 * M * 3072 * 768)
-cases["qkv_plain"] = (lambda: o.gemm_tn(x768, w_qkv, a_out.view(-1)[: M * 2304].view(M, 2304), bias=b2304), 2.0 * M * 2304 * 768)
-cases["l1_fwd_nostats"] = (lambda: o.conv_fwd(xl1, wl1, 3, 1, 1, y=yl1), 2.0 * 128 * 8 * 512 * 192 * 1728)
-cases["l1_fwd_nostore"] = (lambda: o.conv_fwd(xl1, wl1, 3, 1, 1, y=yl1, nostore=True), 2.0 * 128 * 8 * 512 * 192 * 1728)
 sel = sys.argv[1].split(",") if len(sys.argv) > 1 else list(cases)
 for name in sel:
     fn, fl = cases[name]
