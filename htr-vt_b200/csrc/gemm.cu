@@ -238,6 +238,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) mbar_arrive(&tempty[as]);
         }
         if (P.flags & EPI_NOSTORE) continue;                 // measurement aid: main loop only
+        if ((P.flags & EPI_STATS) && KIND == 0 && tc.w0 + r >= P.Wo) {
+          // rows past the end of the image row can pick up shifted-window data: keep them out of the statistics
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = 0u;
+        }
         uint32_t packed[16];
         if (out_bf16) {
 #pragma unroll
