@@ -64,10 +64,11 @@ SIGNATURES = {
     "htrvt_colsum_rows": (_I, [_I]),
     "htrvt_colsum_bf16": (_I, [_P, _L, _I, _I, _P, _I, _P, _P]),
     "htrvt_cast_bf16": (_I, [_P, _P, _L, _P]),
+    "htrvt_pack_weights": (_I, [_I, _P, _P, _P, _P, _P, _P]),
     "htrvt_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "htrvt_conv1_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_bn_finalize": (_I, [_P, _I, ctypes.c_double, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P]),
-    "htrvt_bn_act_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "htrvt_bn_act_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "htrvt_pool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_pool_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_bn_bwd_ctas": (_I, [_L]),

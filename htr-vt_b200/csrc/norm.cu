@@ -351,6 +351,36 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ src, __nv_bflo
   }
 }
 
+// All bf16 operand copies of one forward in ONE launch: entry i is a plain cast (taps == 0) or an
+// OIHW -> [Cout][taps][Cin] repack.  blockIdx.y = tensor, grid-stride over its elements.
+constexpr int kMaxPack = 64;
+struct PackTable {
+  const float* src[kMaxPack];
+  __nv_bfloat16* dst[kMaxPack];
+  long long numel[kMaxPack];
+  int cin[kMaxPack];
+  int taps[kMaxPack];
+};
+__global__ void pack_weights_kernel(const __grid_constant__ PackTable T) {
+  const int t = blockIdx.y;
+  const float* __restrict__ src = T.src[t];
+  __nv_bfloat16* __restrict__ dst = T.dst[t];
+  const long long n = T.numel[t];
+  const int Cin = T.cin[t], taps = T.taps[t];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long j = i;
+    if (taps > 0) {
+      const int ci = static_cast<int>(i % Cin);
+      const long long r = i / Cin;
+      const int tap = static_cast<int>(r % taps);
+      const long long co = r / taps;
+      j = (co * Cin + ci) * taps + tap;
+    }
+    dst[i] = __float2bfloat16_rn(src[j]);
+  }
+}
+
 }  // namespace htrvt
 
 using namespace htrvt;
@@ -502,5 +532,26 @@ extern "C" int htrvt_pack_conv_weight(const float* w_oihw, void* dst, int Cout, 
   pack_conv_weight_kernel<<<grid_for(static_cast<long long>(Cout) * Cin * taps, 256), 256, 0, stream>>>(
       w_oihw, static_cast<__nv_bfloat16*>(dst), Cout, Cin, taps);
   HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+// n <= 64 tensors per call: src fp32, dst bf16, numel elements; taps[i] == 0 -> cast, else OIHW -> [Cout][taps][Cin]
+extern "C" int htrvt_pack_weights(int n, const void* const* src, void* const* dst, const long long* numel,
+                                  const int* cin, const int* taps, cudaStream_t stream) {
+  if (n <= 0) return HTRVT_OK;
+  for (int base = 0; base < n; base += kMaxPack) {
+    PackTable T = {};
+    const int cnt = n - base < kMaxPack ? n - base : kMaxPack;
+    for (int i = 0; i < cnt; ++i) {
+      T.src[i] = static_cast<const float*>(src[base + i]);
+      T.dst[i] = static_cast<__nv_bfloat16*>(dst[base + i]);
+      T.numel[i] = numel[base + i];
+      T.cin[i] = cin[base + i] > 0 ? cin[base + i] : 1;
+      T.taps[i] = taps[base + i];
+    }
+    dim3 grid(96, cnt);
+    pack_weights_kernel<<<grid, 256, 0, stream>>>(T);
+    HTRVT_LAUNCH_CHECK();
+  }
   return HTRVT_OK;
 }

@@ -137,8 +137,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int R, dou
 __global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ scale,
                                   const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                                   const __nv_bfloat16* __restrict__ raw2, const float* __restrict__ scale2,
-                                  const float* __restrict__ shift2, __nv_bfloat16* __restrict__ y, long long n8,
-                                  int C, int relu) {
+                                  const float* __restrict__ shift2, __nv_bfloat16* __restrict__ y,
+                                  uint8_t* __restrict__ mask, long long n8, int C, int relu) {
   const int G = C / 8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -167,8 +167,13 @@ __global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const f
       for (int k = 0; k < 8; ++k) v[k] += fmaf(r[k], s[k], b[k]);
     }
     if (relu) {
+      unsigned m = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      for (int k = 0; k < 8; ++k) {
+        m |= (v[k] > 0.f ? 1u : 0u) << k;
+        v[k] = fmaxf(v[k], 0.f);
+      }
+      if (mask) mask[i] = static_cast<uint8_t>(m);       // ReLU mask bits for the backward (1 byte per 8 channels)
     }
     *reinterpret_cast<uint4*>(y + i * 8) = pack8(v);
   }
@@ -287,7 +292,7 @@ __global__ void pool_bwd_kernel(const GT* __restrict__ gout, const uint8_t* __re
 // BatchNorm backward, stage 1: per-CTA partial sums of g' = g * [y > 0] and g' * xhat (one or two BNs)
 // partial [cta][3][C] : sum g', sum g' xhat_a, sum g' xhat_b
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ mask,
                                      const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mean_a,
                                      const float* __restrict__ rstd_a, const __nv_bfloat16* __restrict__ raw_b,
                                      const float* __restrict__ mean_b, const float* __restrict__ rstd_b,
@@ -307,13 +312,13 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const 
   if (lane_r < R) {
     for (long long r = r0 + lane_r; r < r1; r += R) {
       const long long o = r * C + grp * 8;
-      float gv[8], yv[8], xa[8];
+      float gv[8], xa[8];
       unpack8(*reinterpret_cast<const uint4*>(g + o), gv);
       unpack8(*reinterpret_cast<const uint4*>(raw_a + o), xa);
-      if (y) {
-        unpack8(*reinterpret_cast<const uint4*>(y + o), yv);
+      if (mask) {
+        const unsigned m = mask[r * G + grp];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) if (!(yv[k] > 0.f)) gv[k] = 0.f;
+        for (int k = 0; k < 8; ++k) if (!((m >> k) & 1u)) gv[k] = 0.f;
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -390,7 +395,7 @@ __device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
   *reinterpret_cast<float4*>(f + 4) = *reinterpret_cast<const float4*>(p + 4);
 }
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
-    const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ raw_a,
+    const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ mask, const __nv_bfloat16* __restrict__ raw_a,
     const float* __restrict__ coef_a, __nv_bfloat16* __restrict__ d_a, const __nv_bfloat16* __restrict__ raw_b,
     const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ d_b, __nv_bfloat16* __restrict__ gz, long long n8,
     int C) {
@@ -401,11 +406,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     float gv[8], xa[8], o[8], A[8], Bc[8], Cc[8];
     unpack8(*reinterpret_cast<const uint4*>(g + i * 8), gv);
     unpack8(*reinterpret_cast<const uint4*>(raw_a + i * 8), xa);
-    if (y) {
-      float yv[8];
-      unpack8(*reinterpret_cast<const uint4*>(y + i * 8), yv);
+    if (mask) {
+      const unsigned m = mask[i];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) if (!(yv[k] > 0.f)) gv[k] = 0.f;
+      for (int k = 0; k < 8; ++k) if (!((m >> k) & 1u)) gv[k] = 0.f;
     }
     if (gz) *reinterpret_cast<uint4*>(gz + i * 8) = pack8(gv);
     load8(coef_a + c, A); load8(coef_a + C + c, Bc); load8(coef_a + 2 * C + c, Cc);
@@ -537,13 +541,14 @@ extern "C" int htrvt_bn_finalize(const float* partial, int R, double count, cons
 }
 
 extern "C" int htrvt_bn_act_fwd(const void* raw, const float* scale, const float* shift, const void* res,
-                                const void* raw2, const float* scale2, const float* shift2, void* y, long long P,
-                                int C, int relu, cudaStream_t stream) {
+                                const void* raw2, const float* scale2, const float* shift2, void* y, void* mask,
+                                long long P, int C, int relu, cudaStream_t stream) {
   if (P <= 0 || (C & 7)) return HTRVT_ERR_SHAPE;
   const long long n8 = P * C / 8;
   bn_act_fwd_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(raw), scale, shift, static_cast<const __nv_bfloat16*>(res),
-      static_cast<const __nv_bfloat16*>(raw2), scale2, shift2, static_cast<__nv_bfloat16*>(y), n8, C, relu);
+      static_cast<const __nv_bfloat16*>(raw2), scale2, shift2, static_cast<__nv_bfloat16*>(y),
+      static_cast<uint8_t*>(mask), n8, C, relu);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
@@ -582,11 +587,11 @@ extern "C" int htrvt_bn_bwd_ctas(long long P) {
 }
 
 // BatchNorm backward for the BN (a) that produced `raw_a` (and optionally a second BN (b) fed by the same
-// upstream gradient: the downsample branch).  g: gradient w.r.t. the post-activation output y (ReLU mask
-// y > 0 applied when y != null).  Writes d_a (/d_b) = gradient w.r.t. the raw conv outputs, accumulates
+// upstream gradient: the downsample branch).  g: gradient w.r.t. the post-activation output; `mask` (optional) holds
+// the ReLU mask bits written by htrvt_bn_act_fwd (1 byte per 8 channels).  Writes d_a (/d_b) = gradient w.r.t. the raw conv outputs, accumulates
 // dgamma / dbeta, optionally writes gz = masked g (identity-residual gradient).
 // partial: fp32 [htrvt_bn_bwd_ctas(P)][3][C]; coef: fp32 [2][3][C] scratch.
-extern "C" int htrvt_bn_bwd(const void* g, const void* y, const void* raw_a, const float* mean_a,
+extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, const float* mean_a,
                             const float* rstd_a, const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a,
                             const void* raw_b, const float* mean_b, const float* rstd_b, const float* gamma_b,
                             float* dgamma_b, float* dbeta_b, void* d_b, void* gz, long long P, int C,
@@ -606,7 +611,7 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* y, const void* raw_a, con
   }
   if (smem > 96 * 1024) return HTRVT_ERR_SHAPE;
   bn_bwd_reduce_kernel<<<ctas, threads, smem, stream>>>(
-      static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y),
+      static_cast<const __nv_bfloat16*>(g), static_cast<const uint8_t*>(mask),
       static_cast<const __nv_bfloat16*>(raw_a), mean_a, rstd_a, static_cast<const __nv_bfloat16*>(raw_b), mean_b,
       rstd_b, partial, P, C, rows);
   HTRVT_LAUNCH_CHECK();
@@ -618,7 +623,7 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* y, const void* raw_a, con
   HTRVT_LAUNCH_CHECK();
   const long long n8 = P * C / 8;
   bn_bwd_apply_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y),
+      static_cast<const __nv_bfloat16*>(g), static_cast<const uint8_t*>(mask),
       static_cast<const __nv_bfloat16*>(raw_a), coef_a, static_cast<__nv_bfloat16*>(d_a),
       static_cast<const __nv_bfloat16*>(raw_b), coef_b, static_cast<__nv_bfloat16*>(d_b),
       static_cast<__nv_bfloat16*>(gz), n8, C);

@@ -66,12 +66,15 @@ class Engine(object):
         image = image.contiguous().float()
 
         # ---- weights: bf16 operand copies -----------------------------------------------------
-        wp = {}
+        names, items = [], []
         for k, v in sd.items():
             if k.startswith("patch_embed.") and k.endswith("weight") and v.dim() == 4 and v.shape[1] > 1:
-                wp[k] = ops.pack_conv_weight(v)
+                names.append(k)
+                items.append((v, "conv"))
             elif v.dim() == 2 and k.endswith(".weight"):
-                wp[k] = ops.cast_bf16(v)
+                names.append(k)
+                items.append((v, "cast"))
+        wp = dict(zip(names, ops.pack_weights(items)))          # one launch for all 36 weight tensors
 
         # ---- stem -----------------------------------------------------------------------------
         x0, _, _ = ops.sample_ln_fwd(image.view(B, Hi, Wi), torch.float32, 1e-5)
@@ -86,18 +89,21 @@ class Engine(object):
                 r1, pt1 = self._conv(x, wp[p + ".conv1.weight"], 3, s, training)
                 cnt = r1.numel() // r1.shape[-1]
                 sa = self._bn(sd, p + ".bn1", pt1, cnt, training)
-                a1 = ops.bn_act_fwd(r1, sa, True)
+                a1, k1 = ops.bn_act_fwd(r1, sa, True, want_mask=save) if save else (ops.bn_act_fwd(r1, sa, True), None)
                 r2, pt2 = self._conv(a1, wp[p + ".conv2.weight"], 3, (1, 1), training)
                 sb = self._bn(sd, p + ".bn2", pt2, cnt, training)
                 rd = sdn = None
                 if (p + ".downsample.0.weight") in sd:
                     rd, ptd = self._conv(x, wp[p + ".downsample.0.weight"], 1, s, training)
                     sdn = self._bn(sd, p + ".downsample.1", ptd, cnt, training)
-                    y = ops.bn_act_fwd(r2, sb, True, raw2=rd, st2=sdn)
+                    y = ops.bn_act_fwd(r2, sb, True, raw2=rd, st2=sdn, want_mask=save)
                 else:
-                    y = ops.bn_act_fwd(r2, sb, True, res=x)
+                    y = ops.bn_act_fwd(r2, sb, True, res=x, want_mask=save)
+                k2 = None
                 if save:
-                    blocks.append((p, s, x, r1, sa, a1, r2, sb, rd, sdn, y))
+                    y, k2 = y
+                if save:
+                    blocks.append((p, s, x, r1, sa, a1, k1, r2, sb, rd, sdn, k2))
                 x = y
         Bx, Hx, Wx, Cx = x.shape
         tok, idx2 = ops.pool_fwd(x, None, save)                  # [B, Hx/2, T, D]
@@ -206,16 +212,16 @@ class Engine(object):
         g = ops.pool_bwd(dtok.view(B, 1, T, D), ctx.idx2, ctx.l3_shape)
 
         # ---- stem blocks ------------------------------------------------------------------------
-        for (p, s, xin, r1, sa, a1, r2, sb, rd, sdn, y) in reversed(ctx.blocks):
+        for (p, s, xin, r1, sa, a1, k1, r2, sb, rd, sdn, k2) in reversed(ctx.blocks):
             has_ds = rd is not None
             d2, dd, gz = ops.bn_bwd(
-                g, y, r2, sb, sd[p + ".bn2.weight"], grads[p + ".bn2.weight"], grads[p + ".bn2.bias"],
+                g, k2, r2, sb, sd[p + ".bn2.weight"], grads[p + ".bn2.weight"], grads[p + ".bn2.bias"],
                 raw_b=rd, st_b=sdn, gamma_b=sd[p + ".downsample.1.weight"] if has_ds else None,
                 dgamma_b=grads[p + ".downsample.1.weight"] if has_ds else None,
                 dbeta_b=grads[p + ".downsample.1.bias"] if has_ds else None, want_gz=not has_ds)
             ops.conv_wgrad(d2, a1, 3, 1, 1, grads[p + ".conv2.weight"])
             da1 = ops.conv_dgrad(d2, wp[p + ".conv2.weight"], tuple(a1.shape), 3, 1, 1)
-            d1, _, _ = ops.bn_bwd(da1, a1, r1, sa, sd[p + ".bn1.weight"], grads[p + ".bn1.weight"],
+            d1, _, _ = ops.bn_bwd(da1, k1, r1, sa, sd[p + ".bn1.weight"], grads[p + ".bn1.weight"],
                                   grads[p + ".bn1.bias"])
             ops.conv_wgrad(d1, xin, 3, s[0], s[1], grads[p + ".conv1.weight"])
             if has_ds:

@@ -325,6 +325,30 @@ def pack_conv_weight(w, dst=None):
     return dst
 
 
+def pack_weights(items):
+    """items: list of (src fp32 tensor, kind) with kind 'cast' ([out,in]) or 'conv' (OIHW -> [Cout, taps, Cin]).
+    One launch for all of them.  Returns the list of bf16 tensors."""
+    n = len(items)
+    outs = []
+    src = (ctypes.c_void_p * n)()
+    dst = (ctypes.c_void_p * n)()
+    numel = (ctypes.c_longlong * n)()
+    cin = (ctypes.c_int * n)()
+    taps = (ctypes.c_int * n)()
+    for i, (t, kind) in enumerate(items):
+        if kind == "conv":
+            Cout, Ci, kh, kw = t.shape
+            o = torch.empty((Cout, kh * kw, Ci), dtype=torch.bfloat16, device=t.device)
+            cin[i], taps[i] = Ci, kh * kw
+        else:
+            o = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+            cin[i], taps[i] = 1, 0
+        outs.append(o)
+        src[i], dst[i], numel[i] = t.data_ptr(), o.data_ptr(), t.numel()
+    check(lib().htrvt_pack_weights(n, src, dst, numel, cin, taps, _stream()), "htrvt_pack_weights")
+    return outs
+
+
 # ------------------------------------------------------------------------------------------------
 # Stem
 # ------------------------------------------------------------------------------------------------
@@ -350,14 +374,16 @@ def bn_finalize(partial, count, gamma, beta, running_mean, running_var, nbt, tra
     return out
 
 
-def bn_act_fwd(raw, st, relu, res=None, raw2=None, st2=None):
+def bn_act_fwd(raw, st, relu, res=None, raw2=None, st2=None, want_mask=False):
+    """-> y, or (y, mask) with want_mask: mask uint8 [P, C/8] = ReLU mask bits consumed by bn_bwd."""
     C = raw.shape[-1]
     P = raw.numel() // C
     y = torch.empty_like(raw)
+    mask = torch.empty((P, C // 8), dtype=torch.uint8, device=raw.device) if want_mask else None
     check(lib().htrvt_bn_act_fwd(_p(raw), _p(st[2]), _p(st[3]), _p(res), _p(raw2),
                                  _p(st2[2] if st2 is not None else None), _p(st2[3] if st2 is not None else None),
-                                 _p(y), P, C, int(relu), _stream()), "htrvt_bn_act_fwd")
-    return y
+                                 _p(y), _p(mask), P, C, int(relu), _stream()), "htrvt_bn_act_fwd")
+    return (y, mask) if want_mask else y
 
 
 def pool_fwd(raw, st, want_idx):
@@ -379,7 +405,7 @@ def pool_bwd(gout, idx, in_shape, raw=None, st=None):
     return gin
 
 
-def bn_bwd(g, y, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=None, gamma_b=None, dgamma_b=None,
+def bn_bwd(g, mask, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=None, gamma_b=None, dgamma_b=None,
            dbeta_b=None, want_gz=False):
     """-> (d_a, d_b | None, gz | None), all bf16 with the shape of raw_a."""
     C = raw_a.shape[-1]
@@ -392,7 +418,7 @@ def bn_bwd(g, y, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=None,
     partial = workspace(ctas * 3 * C * 4 + 6 * C * 4, dev)
     coef = partial[ctas * 3 * C * 4:]
     z = None
-    check(lib().htrvt_bn_bwd(_p(g), _p(y), _p(raw_a), _p(st_a[0]), _p(st_a[1]), _p(gamma_a), _p(dgamma_a),
+    check(lib().htrvt_bn_bwd(_p(g), _p(mask), _p(raw_a), _p(st_a[0]), _p(st_a[1]), _p(gamma_a), _p(dgamma_a),
                              _p(dbeta_a), _p(d_a), _p(raw_b), _p(st_b[0] if st_b is not None else z),
                              _p(st_b[1] if st_b is not None else z), _p(gamma_b), _p(dgamma_b), _p(dbeta_b), _p(d_b),
                              _p(gz), P, C, _p(partial), _p(coef), _stream()), "htrvt_bn_bwd")
@@ -457,7 +483,7 @@ def _instrument():
     names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "attention_fwd",
              "attention_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd",
              "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16",
-             "pack_conv_weight", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",
+             "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",
              "conv1_wgrad"]
     for name in names:
         fn = g[name]

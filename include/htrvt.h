@@ -116,6 +116,8 @@ int htrvt_colsum_rows(int M);
 int htrvt_colsum_bf16(const void* a, long long ld, int M, int N, float* out, int accumulate, float* partial,
                       void* stream);
 int htrvt_cast_bf16(const float* src, void* dst, long long n, void* stream);
+int htrvt_pack_weights(int n, const void* const* src, void* const* dst, const long long* numel, const int* cin,
+                       const int* taps, void* stream);
 int htrvt_pack_conv_weight(const float* w_oihw, void* dst, int Cout, int Cin, int taps, void* stream);
 
 /* ---- conv stem: first conv, BatchNorm, ReLU, max-pool ------------------------------------------------------
@@ -131,13 +133,14 @@ int htrvt_bn_finalize(const float* partial, int R, double count, const float* ga
                       float eps, int training, float* mean, float* rstd, float* scale, float* shift, int C,
                       void* stream);
 int htrvt_bn_act_fwd(const void* raw, const float* scale, const float* shift, const void* res, const void* raw2,
-                     const float* scale2, const float* shift2, void* y, long long P, int C, int relu, void* stream);
+                     const float* scale2, const float* shift2, void* y, void* relu_mask_bits, long long P, int C, int relu,
+                     void* stream);
 int htrvt_pool_fwd(const void* raw, const float* scale, const float* shift, void* out, void* idx, int B, int H,
                    int W, int C, void* stream);
 int htrvt_pool_bwd(const void* gout, int gout_is_f32, const void* idx, const void* raw, const float* scale,
                    const float* shift, void* gin, int B, int H, int W, int C, void* stream);
 int htrvt_bn_bwd_ctas(long long P);
-int htrvt_bn_bwd(const void* g, const void* y, const void* raw_a, const float* mean_a, const float* rstd_a,
+int htrvt_bn_bwd(const void* g, const void* relu_mask_bits, const void* raw_a, const float* mean_a, const float* rstd_a,
                  const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a, const void* raw_b,
                  const float* mean_b, const float* rstd_b, const float* gamma_b, float* dgamma_b, float* dbeta_b,
                  void* d_b, void* gz, long long P, int C, float* partial, float* coef, void* stream);

@@ -170,21 +170,21 @@ def test_bn_act_and_bn_bwd_block(ds):
 
     if ds:
         ref = F.relu(bn(r2f, g2, b2) + bn(rdf, gd, bd))
-        y = o.bn_act_fwd(r2, s2, True, raw2=rd, st2=sdn)
+        y, km = o.bn_act_fwd(r2, s2, True, raw2=rd, st2=sdn, want_mask=True)
     else:
         ref = F.relu(bn(r2f, g2, b2) + xf)
-        y = o.bn_act_fwd(r2, s2, True, res=xin)
+        y, km = o.bn_act_fwd(r2, s2, True, res=xin, want_mask=True)
     assert _rel(y, ref) < 1e-2
     g = torch.randn_like(y)
     ref.backward(g.float())
     dg2, db2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     dgd, dbd = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     if ds:
-        d2, dd, gz = o.bn_bwd(g, y, r2, s2, g2.detach(), dg2, db2, raw_b=rd, st_b=sdn, gamma_b=gd.detach(),
+        d2, dd, gz = o.bn_bwd(g, km, r2, s2, g2.detach(), dg2, db2, raw_b=rd, st_b=sdn, gamma_b=gd.detach(),
                               dgamma_b=dgd, dbeta_b=dbd)
         assert _rel(dd, rdf.grad) < 3e-2 and _rel(dgd, gd.grad) < 2e-2 and _rel(dbd, bd.grad) < 2e-2
     else:
-        d2, dd, gz = o.bn_bwd(g, y, r2, s2, g2.detach(), dg2, db2, want_gz=True)
+        d2, dd, gz = o.bn_bwd(g, km, r2, s2, g2.detach(), dg2, db2, want_gz=True)
         assert _rel(gz, xf.grad) < 2e-2
     assert _rel(d2, r2f.grad) < 3e-2 and _rel(dg2, g2.grad) < 2e-2 and _rel(db2, b2.grad) < 2e-2
 
