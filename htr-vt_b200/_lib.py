@@ -75,6 +75,11 @@ SIGNATURES = {
     "htrvt_bn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P]),
     "htrvt_conv1_wgrad_ctas": (_I, []),
     "htrvt_conv1_wgrad": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P]),
+    "htrvt_stem_head_moment_ctas": (_I, []),
+    "htrvt_stem_head_bwd_ctas": (_I, []),
+    "htrvt_stem_head_moments": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_stem_head_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_stem_head_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_attention_fwd": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P]),
     "htrvt_attention_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
 }

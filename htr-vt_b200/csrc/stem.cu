@@ -17,6 +17,13 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
   t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
 }
+// 16-byte read of data that is touched once: keep it out of L1
+__device__ __forceinline__ uint4 ld_stream(const __nv_bfloat16* p) {
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  return u;
+}
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 u;
   u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
@@ -84,22 +91,33 @@ __global__ void conv1_fwd_kernel(const float* __restrict__ x, const float* __res
 // ------------------------------------------------------------------------------------------------
 // BatchNorm finalise: partial [R][2][C] (sum, sum of squares) -> mean, rstd, scale, shift (+ running stats)
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int R, double count,
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int R, double count,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches_tracked, float momentum, float eps,
                                    int training, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                    float* __restrict__ scale_out, float* __restrict__ shift_out, int C) {
-  // block = 32 channels x 8 row lanes
-  __shared__ double sh[2][8][32];
+  // block = 32 channels x 32 row lanes; four independent accumulators per lane keep the partial-row loads in flight
+  __shared__ double sh[2][32][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), lr = threadIdx.x >> 5;
   if (blockIdx.x == 0 && threadIdx.x == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
   double s = 0.0, q = 0.0;
   if (training && c < C) {
-    for (int r = lr; r < R; r += 8) {
-      s += partial[(static_cast<long long>(r) * 2) * C + c];
-      q += partial[(static_cast<long long>(r) * 2 + 1) * C + c];
+    float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+    int r = lr;
+    for (; r + 96 < R; r += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s4[u] += partial[(static_cast<long long>(r + 32 * u) * 2) * C + c];
+        q4[u] += partial[(static_cast<long long>(r + 32 * u) * 2 + 1) * C + c];
+      }
     }
+    for (; r < R; r += 32) {
+      s4[0] += partial[(static_cast<long long>(r) * 2) * C + c];
+      q4[0] += partial[(static_cast<long long>(r) * 2 + 1) * C + c];
+    }
+    s = (static_cast<double>(s4[0]) + s4[1]) + (static_cast<double>(s4[2]) + s4[3]);
+    q = (static_cast<double>(q4[0]) + q4[1]) + (static_cast<double>(q4[2]) + q4[3]);
   }
   sh[0][lr][threadIdx.x & 31] = s;
   sh[1][lr][threadIdx.x & 31] = q;
@@ -108,7 +126,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int R, dou
   float mean, var;
   if (training) {
     s = 0.0; q = 0.0;
-    for (int k = 0; k < 8; ++k) { s += sh[0][k][threadIdx.x]; q += sh[1][k][threadIdx.x]; }
+    for (int k = 0; k < 32; ++k) { s += sh[0][k][threadIdx.x]; q += sh[1][k][threadIdx.x]; }
     const double m = s / count;
     double v = q / count - m * m;
     if (v < 0.0) v = 0.0;
@@ -310,26 +328,36 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const 
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
   if (lane_r < R) {
-    for (long long r = r0 + lane_r; r < r1; r += R) {
-      const long long o = r * C + grp * 8;
-      float gv[8], xa[8];
-      unpack8(*reinterpret_cast<const uint4*>(g + o), gv);
-      unpack8(*reinterpret_cast<const uint4*>(raw_a + o), xa);
-      if (mask) {
-        const unsigned m = mask[r * G + grp];
+    for (long long r = r0 + lane_r; r < r1; r += 4 * R) {
+      uint4 gq[4], xq[4], bq[4];
+      unsigned mk[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) if (!((m >> k) & 1u)) gv[k] = 0.f;
+      for (int u = 0; u < 4; ++u) {                       // issue every load of four rows before using any
+        const long long rr = r + static_cast<long long>(u) * R;
+        const bool ok = rr < r1;
+        const long long o = rr * C + grp * 8;
+        gq[u] = ok ? ld_stream(g + o) : make_uint4(0u, 0u, 0u, 0u);
+        xq[u] = ok ? ld_stream(raw_a + o) : make_uint4(0u, 0u, 0u, 0u);
+        bq[u] = (ok && raw_b) ? ld_stream(raw_b + o) : make_uint4(0u, 0u, 0u, 0u);
+        mk[u] = (ok && mask) ? mask[rr * G + grp] : 0xffu;
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        s0[k] += gv[k];
-        s1[k] += gv[k] * (xa[k] - ma[k]) * ra[k];
-      }
-      if (raw_b) {
-        float xb[8];
-        unpack8(*reinterpret_cast<const uint4*>(raw_b + o), xb);
+      for (int u = 0; u < 4; ++u) {
+        float gv[8], xa[8];
+        unpack8(gq[u], gv);
+        unpack8(xq[u], xa);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s2[k] += gv[k] * (xb[k] - mb[k]) * rb[k];
+        for (int k = 0; k < 8; ++k) {
+          if (!((mk[u] >> k) & 1u)) gv[k] = 0.f;
+          s0[k] += gv[k];
+          s1[k] = fmaf(gv[k] * ra[k], xa[k] - ma[k], s1[k]);
+        }
+        if (raw_b) {
+          float xb[8];
+          unpack8(bq[u], xb);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s2[k] = fmaf(gv[k] * rb[k], xb[k] - mb[k], s2[k]);
+        }
       }
     }
 #pragma unroll
@@ -361,10 +389,22 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), lr = threadIdx.x >> 5;      // 32 channels x 32 row lanes
   double s0 = 0.0, s1 = 0.0, s2 = 0.0;
   if (c < C) {
-    for (int r = lr; r < R; r += 32) {
-      const float* p = partial + static_cast<long long>(r) * 3 * C;
-      s0 += p[c]; s1 += p[C + c]; s2 += p[2 * C + c];
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+    int r = lr;
+    for (; r + 96 < R; r += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* p = partial + static_cast<long long>(r + 32 * u) * 3 * C;
+        a0[u] += p[c]; a1[u] += p[C + c]; a2[u] += p[2 * C + c];
+      }
     }
+    for (; r < R; r += 32) {
+      const float* p = partial + static_cast<long long>(r) * 3 * C;
+      a0[0] += p[c]; a1[0] += p[C + c]; a2[0] += p[2 * C + c];
+    }
+    s0 = (static_cast<double>(a0[0]) + a0[1]) + (static_cast<double>(a0[2]) + a0[3]);
+    s1 = (static_cast<double>(a1[0]) + a1[1]) + (static_cast<double>(a1[2]) + a1[3]);
+    s2 = (static_cast<double>(a2[0]) + a2[1]) + (static_cast<double>(a2[2]) + a2[3]);
   }
   sh[0][lr][threadIdx.x & 31] = s0; sh[1][lr][threadIdx.x & 31] = s1; sh[2][lr][threadIdx.x & 31] = s2;
   __syncthreads();
@@ -400,29 +440,42 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ d_b, __nv_bfloat16* __restrict__ gz, long long n8,
     int C) {
   const int G = C / 8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % G) * 8;
-    float gv[8], xa[8], o[8], A[8], Bc[8], Cc[8];
-    unpack8(*reinterpret_cast<const uint4*>(g + i * 8), gv);
-    unpack8(*reinterpret_cast<const uint4*>(raw_a + i * 8), xa);
-    if (mask) {
-      const unsigned m = mask[i];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < n8; i0 += 2 * stride) {
+    uint4 gq[2], xq[2], bq[2];
+    unsigned mk[2];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) if (!((m >> k) & 1u)) gv[k] = 0.f;
+    for (int u = 0; u < 2; ++u) {                         // both groups' loads are issued before any use
+      const long long i = i0 + u * stride;
+      const bool ok = i < n8;
+      gq[u] = ok ? ld_stream(g + i * 8) : make_uint4(0u, 0u, 0u, 0u);
+      xq[u] = ok ? ld_stream(raw_a + i * 8) : make_uint4(0u, 0u, 0u, 0u);
+      bq[u] = (ok && raw_b) ? ld_stream(raw_b + i * 8) : make_uint4(0u, 0u, 0u, 0u);
+      mk[u] = (ok && mask) ? mask[i] : 0xffu;
     }
-    if (gz) *reinterpret_cast<uint4*>(gz + i * 8) = pack8(gv);
-    load8(coef_a + c, A); load8(coef_a + C + c, Bc); load8(coef_a + 2 * C + c, Cc);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], gv[k], fmaf(Bc[k], xa[k], Cc[k]));
-    *reinterpret_cast<uint4*>(d_a + i * 8) = pack8(o);
-    if (raw_b) {
-      float xb[8];
-      unpack8(*reinterpret_cast<const uint4*>(raw_b + i * 8), xb);
-      load8(coef_b + c, A); load8(coef_b + C + c, Bc); load8(coef_b + 2 * C + c, Cc);
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= n8) break;
+      const int c = static_cast<int>(i % G) * 8;
+      float gv[8], xa[8], o[8], A[8], Bc[8], Cc[8];
+      unpack8(gq[u], gv);
+      unpack8(xq[u], xa);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], gv[k], fmaf(Bc[k], xb[k], Cc[k]));
-      *reinterpret_cast<uint4*>(d_b + i * 8) = pack8(o);
+      for (int k = 0; k < 8; ++k) if (!((mk[u] >> k) & 1u)) gv[k] = 0.f;
+      if (gz) *reinterpret_cast<uint4*>(gz + i * 8) = pack8(gv);
+      load8(coef_a + c, A); load8(coef_a + C + c, Bc); load8(coef_a + 2 * C + c, Cc);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], gv[k], fmaf(Bc[k], xa[k], Cc[k]));
+      *reinterpret_cast<uint4*>(d_a + i * 8) = pack8(o);
+      if (raw_b) {
+        float xb[8];
+        unpack8(bq[u], xb);
+        load8(coef_b + c, A); load8(coef_b + C + c, Bc); load8(coef_b + 2 * C + c, Cc);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], gv[k], fmaf(Bc[k], xb[k], Cc[k]));
+        *reinterpret_cast<uint4*>(d_b + i * 8) = pack8(o);
+      }
     }
   }
 }
@@ -533,7 +586,7 @@ extern "C" int htrvt_bn_finalize(const float* partial, int R, double count, cons
                                  float momentum, float eps, int training, float* mean, float* rstd, float* scale,
                                  float* shift, int C, cudaStream_t stream) {
   if (C <= 0 || (training && (!partial || R <= 0))) return HTRVT_ERR_SHAPE;
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, stream>>>(partial, R, count, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, stream>>>(partial, R, count, gamma, beta, running_mean, running_var,
                                                           num_batches_tracked, momentum, eps, training, mean, rstd,
                                                           scale, shift, C);
   HTRVT_LAUNCH_CHECK();
@@ -582,8 +635,8 @@ extern "C" int htrvt_pool_bwd(const void* gout, int gout_is_f32, const void* idx
 }
 
 extern "C" int htrvt_bn_bwd_ctas(long long P) {
-  long long c = (P + 255) / 256;
-  return static_cast<int>(c > 888 ? 888 : (c < 1 ? 1 : c));
+  long long c = (P + 63) / 64;
+  return static_cast<int>(c > 592 ? 592 : (c < 1 ? 1 : c));
 }
 
 // BatchNorm backward for the BN (a) that produced `raw_a` (and optionally a second BN (b) fed by the same

@@ -44,12 +44,17 @@ class Engine(object):
         g, b, rm, rv, nbt = _bn_args(sd, prefix)
         return ops.bn_finalize(partial if training else None, count, g, b, rm, rv, nbt, training)
 
-    def _conv(self, x, wp, ks, stride, training):
+    def _conv(self, x, wp, ks, stride, training, pool=None):
         N, H, W, _ = x.shape
         stats = None
         if training:
             rows = ops.conv_stats_rows(N, H, W, ks, stride[0], stride[1])
-            stats = torch.zeros((rows, 2, wp.shape[0]), dtype=torch.float32, device=x.device)   # one row per CTA
+            n = rows * 2 * wp.shape[0]                                         # one [2, Cout] row per CTA quadrant
+            if pool is not None and pool[1] + n <= pool[0].numel():
+                stats = pool[0][pool[1]:pool[1] + n].view(rows, 2, wp.shape[0])
+                pool[1] += n
+            else:
+                stats = torch.zeros((rows, 2, wp.shape[0]), dtype=torch.float32, device=x.device)
         y = ops.conv_fwd(x, wp, ks, stride[0], stride[1], stats=stats)
         return y, stats
 
@@ -78,23 +83,32 @@ class Engine(object):
 
         # ---- stem -----------------------------------------------------------------------------
         x0, _, _ = ops.sample_ln_fwd(image.view(B, Hi, Wi), torch.float32, 1e-5)
-        c1raw, part = ops.conv1_fwd(x0, sd["patch_embed.conv1.weight"], training)
+        # stem head (conv1 -> bn1 -> relu -> maxpool) fused: the K = 9 conv output is never materialised
+        w1 = sd["patch_embed.conv1.weight"]
+        moments = part = None
+        if training:
+            moments, part = ops.stem_head_moments(x0, w1)
         st1 = self._bn(sd, "patch_embed.bn1", part, B * (Hi // 2) * Wi, training)
-        x, idx1 = ops.pool_fwd(c1raw, st1, save)
+        x, code1 = ops.stem_head_fwd(x0, w1, st1, save)
         blocks = []
+        zpool = None
+        if training:            # one memset for the statistics partials of all 15 stem convolutions
+            rows = ops.conv_stats_rows(B, Hi, Wi, 3, 1, 1)
+            total = sum(rows * 2 * v.shape[0] for k, v in wp.items() if k.startswith("patch_embed."))
+            zpool = [torch.zeros(total, dtype=torch.float32, device=image.device), 0]
         for lname, stride in STEM_LAYERS:
             for bi in range(2):
                 p = "patch_embed.%s.%d" % (lname, bi)
                 s = stride if bi == 0 else (1, 1)
-                r1, pt1 = self._conv(x, wp[p + ".conv1.weight"], 3, s, training)
+                r1, pt1 = self._conv(x, wp[p + ".conv1.weight"], 3, s, training, zpool)
                 cnt = r1.numel() // r1.shape[-1]
                 sa = self._bn(sd, p + ".bn1", pt1, cnt, training)
                 a1, k1 = ops.bn_act_fwd(r1, sa, True, want_mask=save) if save else (ops.bn_act_fwd(r1, sa, True), None)
-                r2, pt2 = self._conv(a1, wp[p + ".conv2.weight"], 3, (1, 1), training)
+                r2, pt2 = self._conv(a1, wp[p + ".conv2.weight"], 3, (1, 1), training, zpool)
                 sb = self._bn(sd, p + ".bn2", pt2, cnt, training)
                 rd = sdn = None
                 if (p + ".downsample.0.weight") in sd:
-                    rd, ptd = self._conv(x, wp[p + ".downsample.0.weight"], 1, s, training)
+                    rd, ptd = self._conv(x, wp[p + ".downsample.0.weight"], 1, s, training, zpool)
                     sdn = self._bn(sd, p + ".downsample.1", ptd, cnt, training)
                     y = ops.bn_act_fwd(r2, sb, True, raw2=rd, st2=sdn, want_mask=save)
                 else:
@@ -150,7 +164,7 @@ class Engine(object):
             logits, rl = raw_logits.view(B, T, C), None
         if save:
             ctx.B, ctx.T, ctx.Hi, ctx.Wi = B, T, Hi, Wi
-            ctx.wp, ctx.x0, ctx.c1raw, ctx.st1, ctx.idx1 = wp, x0, c1raw, st1, idx1
+            ctx.wp, ctx.x0, ctx.moments, ctx.st1, ctx.code1 = wp, x0, moments, st1, code1
             ctx.blocks, ctx.l3_shape, ctx.idx2, ctx.mask = blocks, (Bx, Hx, Wx, Cx), idx2, mask
             ctx.tblocks, ctx.x_final, ctx.hf, ctx.mf, ctx.rf = tblocks, xs, hf, mf, rf
             ctx.logits, ctx.rl = logits, rl
@@ -234,8 +248,9 @@ class Engine(object):
                                      accumulate=True)
             g = gin
         # ---- stem head: pool -> relu -> bn1 -> conv1 ---------------------------------------------
-        gc = ops.pool_bwd(g, ctx.idx1, tuple(ctx.c1raw.shape), raw=ctx.c1raw, st=ctx.st1)
-        dc1, _, _ = ops.bn_bwd(gc, None, ctx.c1raw, ctx.st1, sd["patch_embed.bn1.weight"],
-                               grads["patch_embed.bn1.weight"], grads["patch_embed.bn1.bias"])
-        ops.conv1_wgrad(dc1, ctx.x0, grads["patch_embed.conv1.weight"])
+        if ctx.moments is None:
+            raise ops.HtrvtError("backward needs a train-mode forward (batch statistics)")
+        ops.stem_head_bwd(g, ctx.code1, ctx.x0, sd["patch_embed.conv1.weight"], ctx.moments,
+                          sd["patch_embed.bn1.weight"], ctx.st1, grads["patch_embed.bn1.weight"],
+                          grads["patch_embed.bn1.bias"], grads["patch_embed.conv1.weight"])
         return grads

@@ -425,6 +425,46 @@ def bn_bwd(g, mask, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=No
     return d_a, d_b, gz
 
 
+def stem_head_moments(x, w):
+    """x fp32 [B,H,W], w fp32 [C,1,3,3] -> (moments fp32 [54], stats fp32 [1,2,C]): 3x3-patch moments of the image and
+    the exact per-channel sum / sum of squares of the (never materialised) conv1 output."""
+    _need_cuda(x, w)
+    B, H, W = x.shape
+    C = w.shape[0]
+    moments = torch.empty(54, dtype=torch.float32, device=x.device)
+    stats = torch.empty((1, 2, C), dtype=torch.float32, device=x.device)
+    partial = workspace(lib().htrvt_stem_head_moment_ctas() * 54 * 4, x.device)
+    check(lib().htrvt_stem_head_moments(_p(x), _p(w), _p(partial), _p(moments), _p(stats), B, H, W, C, _stream()),
+          "htrvt_stem_head_moments")
+    return moments, stats
+
+
+def stem_head_fwd(x, w, st, want_code):
+    """conv1 -> BN(scale/shift of st) -> ReLU -> MaxPool(3,(2,1),1).  -> (out bf16 [B,Ho,W,C], code uint8 | None)."""
+    _need_cuda(x, w)
+    B, H, W = x.shape
+    C = w.shape[0]
+    Ho = (H // 2 - 1) // 2 + 1
+    out = torch.empty((B, Ho, W, C), dtype=torch.bfloat16, device=x.device)
+    code = torch.empty((B, Ho, W, C // 2), dtype=torch.uint8, device=x.device) if want_code else None
+    check(lib().htrvt_stem_head_fwd(_p(x), _p(w), _p(st[2]), _p(st[3]), _p(out), _p(code), B, H, W, C, _stream()),
+          "htrvt_stem_head_fwd")
+    return out, code
+
+
+def stem_head_bwd(g, code, x, w, moments, gamma, st, dgamma, dbeta, dw):
+    """One pass over the pooled gradient g bf16 [B,Ho,W,C]: dgamma, dbeta, dw (fp32, +=)."""
+    _need_cuda(g, code, x)
+    B, H, W = x.shape
+    C = w.shape[0]
+    if not g.is_contiguous():
+        g = g.contiguous()
+    partial = workspace(lib().htrvt_stem_head_bwd_ctas() * 11 * C * 4, x.device)
+    check(lib().htrvt_stem_head_bwd(_p(g), _p(code), _p(x), _p(w), _p(moments), _p(gamma), _p(st[0]), _p(st[1]),
+                                    _p(dgamma), _p(dbeta), _p(dw), _p(partial), B, H, W, C, _stream()),
+          "htrvt_stem_head_bwd")
+
+
 def conv1_wgrad(dy, x, grad, accumulate=True):
     B, H, W = x.shape
     C = dy.shape[-1]
@@ -484,7 +524,7 @@ def _instrument():
              "attention_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd",
              "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16",
              "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",
-             "conv1_wgrad"]
+             "conv1_wgrad", "stem_head_moments", "stem_head_fwd", "stem_head_bwd"]
     for name in names:
         fn = g[name]
 

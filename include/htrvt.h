@@ -144,6 +144,23 @@ int htrvt_bn_bwd(const void* g, const void* relu_mask_bits, const void* raw_a, c
                  const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a, const void* raw_b,
                  const float* mean_b, const float* rstd_b, const float* gamma_b, float* dgamma_b, float* dbeta_b,
                  void* d_b, void* gz, long long P, int C, float* partial, float* coef, void* stream);
+/* ---- fused stem head: conv1 -> BatchNorm -> ReLU -> MaxPool without materialising the conv output -----------
+ * Replaces model_v1/model/resnet18.py:74-77 (conv1, bn1, relu, maxpool) and their backward.  The conv has one
+ * input channel and K = 9, so its output is recomputed from the fp32 image wherever it is needed:
+ * htrvt_stem_head_moments: 3x3-patch moments of x (moments[54]: 9 sums + 45 upper-triangular products) and the
+ *   exact per-channel (sum, sum of squares) of the conv output, stats[2][C] -> htrvt_bn_finalize (R = 1);
+ * htrvt_stem_head_fwd: pooled activation bf16 [B,Ho,W,C] + 4-bit arg-max codes [B,Ho,W,C/2] (NULL in eval mode;
+ *   code = kh*3+kw of torch's arg-max, 15 = ReLU inactive);
+ * htrvt_stem_head_bwd: one pass over the pooled gradient g -> dgamma, dbeta (bn1) and dW (conv1, [C][9]), all +=. */
+int htrvt_stem_head_moment_ctas(void);
+int htrvt_stem_head_bwd_ctas(void);
+int htrvt_stem_head_moments(const float* x, const float* w, float* partial, float* moments, float* stats, int B,
+                            int H, int W, int C, void* stream);
+int htrvt_stem_head_fwd(const float* x, const float* w, const float* scale, const float* shift, void* out, void* code,
+                        int B, int H, int W, int C, void* stream);
+int htrvt_stem_head_bwd(const void* g, const void* code, const float* x, const float* w, const float* moments,
+                        const float* gamma, const float* mean, const float* rstd, float* dgamma, float* dbeta,
+                        float* dw, float* partial, int B, int H, int W, int C, void* stream);
 int htrvt_conv1_wgrad_ctas(void);
 int htrvt_conv1_wgrad(const void* dy_bf16, const float* x, float* grad, int accumulate, float* partial, int B,
                       int H, int W, int C, void* stream);

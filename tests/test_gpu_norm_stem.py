@@ -204,3 +204,47 @@ def test_final_pool_fwd_bwd():
     want = xf.grad.permute(0, 2, 3, 1)
     # ties among equal maxima (zeros after ReLU) go to the first element in both implementations
     assert _rel(gin, want) < 2e-2
+
+
+@pytest.mark.parametrize("B,H,W,C", [(3, 64, 128, 64), (2, 64, 512, 192), (2, 12, 72, 64)])
+def test_stem_head_fused(B, H, W, C):
+    """conv1 -> bn1(train) -> relu -> maxpool fused (conv output never materialised) vs the fp32 torch graph
+    (model_v1/model/resnet18.py:74-77): pooled activation, batch statistics, and dW / dgamma / dbeta."""
+    o = ops()
+    torch.manual_seed(7)
+    x = torch.randn(B, 1, H, W, device="cuda")
+    w = (torch.randn(C, 1, 3, 3, device="cuda") * 0.4).requires_grad_(True)
+    gamma = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
+    beta = (torch.randn(C, device="cuda") * 0.3).requires_grad_(True)
+    raw = F.conv2d(x, w, None, (2, 1), 1)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    z = F.batch_norm(raw, rm, rv, gamma, beta, True, 0.1, 1e-5)
+    ref = F.max_pool2d(F.relu(z), 3, (2, 1), 1)                       # [B, C, Ho, W]
+    gout = torch.randn_like(ref).bfloat16().float()
+    ref.backward(gout)
+
+    x3 = x.view(B, H, W).contiguous()
+    moments, stats = o.stem_head_moments(x3, w.detach())
+    cnt = B * (H // 2) * W
+    np_sum = raw.detach().sum((0, 2, 3))
+    np_sq = (raw.detach() ** 2).sum((0, 2, 3))
+    assert _rel(stats[0, 0], np_sum) < 1e-3 * max(1.0, float(np_sq.max().sqrt() / (np_sum.abs().max() + 1e-6)))
+    assert _rel(stats[0, 1], np_sq) < 1e-4
+    rm2, rv2 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    st = o.bn_finalize(stats, cnt, gamma.detach(), beta.detach(), rm2, rv2, nbt, True)
+    assert _rel(rm2, rm) < 1e-4 and _rel(rv2, rv) < 1e-4
+    out, code = o.stem_head_fwd(x3, w.detach(), st, True)
+    assert out.shape == (B, ref.shape[2], W, C)
+    assert _rel(out.permute(0, 3, 1, 2), ref.detach()) < 1e-2          # bf16 storage of an fp32 computation
+    out2, none = o.stem_head_fwd(x3, w.detach(), st, False)
+    assert none is None and torch.equal(out, out2)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dw = torch.zeros(C, 1, 3, 3, device="cuda")
+    g_nhwc = gout.permute(0, 2, 3, 1).contiguous().bfloat16()
+    o.stem_head_bwd(g_nhwc, code, x3, w.detach(), moments, gamma.detach(), st, dg, db, dw)
+    assert _rel(db, beta.grad) < 2e-3
+    assert _rel(dg, gamma.grad) < 2e-3
+    assert _rel(dw, w.grad) < 2e-3
+    o.stem_head_bwd(g_nhwc, code, x3, w.detach(), moments, gamma.detach(), st, dg, db, dw)      # += semantics
+    assert _rel(dw, 2 * w.grad) < 2e-3
