@@ -51,7 +51,8 @@ SIGNATURES = {
     "htrvt_conv_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P]),
     "htrvt_conv_fwd_stats_rows": (_I, [_I, _I, _I, _I, _I, _I]),
     "htrvt_conv_dgrad": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P]),
-    "htrvt_conv_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _Z, _P]),
+    "htrvt_transpose_px": (_I, [_P, _P, _L, _I, _I, _P]),
+    "htrvt_conv_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _Z, _P]),
     "htrvt_sample_ln_fwd": (_I, [_P, _P, _I, _P, _P, _I, _I, _F, _P]),
     "htrvt_sample_ln_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_row_ln_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),

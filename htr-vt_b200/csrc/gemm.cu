@@ -2,6 +2,8 @@
 //   warp 0   : TMA producer (one elected lane) - 5-D tiled tensor maps, SWIZZLE_128B, OOB zero fill
 //              implements conv padding, ragged tiles and K tails
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16, bf16 -> fp32 in TMEM)
+// KIND: 0 = rows are output pixels (linear / conv fwd, dgrad); 1 = weight gradient, both operands pixel-major
+// (MN-major); 2 = weight gradient with a K-major dY^T operand (tcgen05 runs ~1.4x slower with an MN-major A).
 //   warps 2-9: epilogue (tcgen05.ld 32x32b, two warps per TMEM lane quadrant), double-buffered
 //              accumulator so the epilogue of tile i overlaps the main loop of tile i+1
 // Operands can be K-major or MN-major (smem descriptor + instruction-descriptor major bits), which is
@@ -136,9 +138,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int q = tc.q_begin + k;
             const int row = q / P.k_chunks, w0c = (q - row * P.k_chunks) * kBK;
             const int n = row / P.Ho, ho = row - n * P.Ho;
+            if (KIND == 1) {
 #pragma unroll
-            for (int i = 0; i < kBM / 64; ++i)
-              tma_load_5d(sa + i * 8192, &tmA, &full[stage], m0 + 64 * i, 0, w0c, ho, n);
+              for (int i = 0; i < kBM / 64; ++i)
+                tma_load_5d(sa + i * 8192, &tmA, &full[stage], m0 + 64 * i, 0, w0c, ho, n);
+            } else {            // KIND 2: dY^T [n][ho][C][Wo] - pixels contiguous, a plain K-major tile
+              tma_load_5d(sa, &tmA, &full[stage], w0c, m0, ho, n, 0);
+            }
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
               tma_load_5d(sb + i * 8192, &tmB, &full[stage], n0 + 64 * i, P.tap.pw[tc.tap],
@@ -326,6 +332,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Host side: tensor maps + C-ABI entry points
 // =================================================================================================
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <mutex>
 
 using namespace htrvt;
@@ -464,9 +471,17 @@ void fill_taps_conv(TapTab& t, int ks, int pad, int sw, int* n_taps) {
   *n_taps = n;
 }
 
+// developer knobs for tools/profile_gemm.py (unset in production): HTRVT_DBG_SPLITS=n forces the split-K factor,
+// HTRVT_DBG_WGRAD_NOSTORE=1 skips the weight-gradient epilogue stores (main loop timing)
+int dbg_env(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+
 // Split-K factor for the weight-gradient GEMMs: minimise (waves x per-split tile time) + partial-sum traffic.
 int choose_splits(int base_tiles, long long q_total, long long out_elems) {
   const int sms = num_sms();
+  if (const int forced = dbg_env("HTRVT_DBG_SPLITS")) return forced < q_total ? forced : static_cast<int>(q_total);
   double best = 1e300;
   int best_s = 1;
   const double tile_us = static_cast<double>(q_total) * 0.23;          // ~0.23 us per 128 x BN x 64 k-chunk
@@ -691,15 +706,27 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
 }
 
 // dw (+)= sum_pixels dy^T x_shifted; grad is fp32 OIHW (the nn.Conv2d parameter layout).
-extern "C" int htrvt_conv_wgrad(const void* dy, const void* x, int NB, int H, int W, int Cin, int Cout, int ks,
-                                int sh, int sw, float* grad_oihw, int accumulate, void* workspace,
+// dy_t (optional): the same gradient stored [NB][Ho][Cout][Wo] (htrvt_transpose_px) - selects the K-major-A kernel.
+extern "C" int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin,
+                                int Cout, int ks, int sh, int sw, float* grad_oihw, int accumulate, void* workspace,
                                 size_t workspace_bytes, cudaStream_t stream) {
   const int pad = ks / 2;
   if ((Cout % 8) || (Cin % 8) || (W % sw) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
   const int bn = pick_bn(Cin);
   CUtensorMap ta, tb, tc;
-  int r = make_map_act(&ta, dy, NB, Ho, Wo, Cout, 1, 64, 64);
+  const bool a_kmajor = dy_t != nullptr && (Wo % 8) == 0;
+  int r;
+  if (a_kmajor) {
+    const long long dims[5] = {Wo, Cout, Ho, NB, 1};
+    const long long st[4] = {Wo, static_cast<long long>(Cout) * Wo, static_cast<long long>(Ho) * Cout * Wo,
+                             static_cast<long long>(NB) * Ho * Cout * Wo};
+    const int box[5] = {64, kBM, 1, 1, 1};
+    r = make_map5(&ta, dy_t, dims, st, box);
+  } else {
+    if (!dy) return HTRVT_ERR_SHAPE;
+    r = make_map_act(&ta, dy, NB, Ho, Wo, Cout, 1, 64, 64);
+  }
   if (r) return r;
   r = make_map_act(&tb, x, NB, H, W, Cin, sw, 64, 64);
   if (r) return r;
@@ -711,11 +738,12 @@ extern "C" int htrvt_conv_wgrad(const void* dy, const void* x, int NB, int H, in
   const long long Q = static_cast<long long>(NB) * Ho * P.k_chunks;
   const long long per = static_cast<long long>(Cout) * P.n_taps * Cin;
   P.splits = choose_splits(P.tiles_m * P.tiles_n * P.n_taps, Q, per);
-  P.M_valid = Cout; P.N_valid = Cin; P.flags = 0; P.alpha = 1.f;
+  P.M_valid = Cout; P.N_valid = Cin; P.flags = dbg_env("HTRVT_DBG_WGRAD_NOSTORE") ? EPI_NOSTORE : 0; P.alpha = 1.f;
   if (!workspace || workspace_bytes < static_cast<size_t>(P.splits) * per * sizeof(float)) return HTRVT_ERR_WORKSPACE;
   r = make_map_wgrad_out(&tc, workspace, Cout, P.n_taps, Cin, P.splits);
   if (r) return r;
-  r = launch_bn<1, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream);
+  r = a_kmajor ? launch_bn<2, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream)
+               : launch_bn<1, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream);
   if (r) return r;
   const int blocks = static_cast<int>((per + 255) / 256 < 2048 ? (per + 255) / 256 : 2048);
   wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), P.splits, Cout, P.n_taps, Cin,

@@ -381,9 +381,53 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackTable T) {
   }
 }
 
+// in [R][P][C] bf16 (pixels x channels, channels contiguous) -> out [R][C][P] (pixels contiguous): the K-major
+// dY^T operand of the weight-gradient GEMM.  64 x 64 tiles through padded smem; grid (ceil(P/64), ceil(C/64), R).
+__global__ void __launch_bounds__(256) transpose_px_kernel(const __nv_bfloat16* __restrict__ in,
+                                                           __nv_bfloat16* __restrict__ out, int P, int C) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];
+  const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const long long row = blockIdx.z;
+  const __nv_bfloat16* src = in + row * P * C;
+  __nv_bfloat16* dst = out + row * C * P;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int id = threadIdx.x + 256 * k;
+    const int px = id >> 3, cg = id & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (p0 + px < P && c0 + cg * 8 < C)
+      v = *reinterpret_cast<const uint4*>(src + static_cast<long long>(p0 + px) * C + c0 + cg * 8);
+    *reinterpret_cast<uint4*>(&tile[px][cg * 8]) = v;
+  }
+  __syncthreads();
+  const int ch = threadIdx.x & 63;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int pg = (threadIdx.x >> 6) + 4 * k;
+    if (c0 + ch >= C || p0 + pg * 8 >= P) continue;
+    uint16_t e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = *reinterpret_cast<const uint16_t*>(&tile[pg * 8 + j][ch]);
+    uint4 v;
+    v.x = e[0] | (static_cast<uint32_t>(e[1]) << 16); v.y = e[2] | (static_cast<uint32_t>(e[3]) << 16);
+    v.z = e[4] | (static_cast<uint32_t>(e[5]) << 16); v.w = e[6] | (static_cast<uint32_t>(e[7]) << 16);
+    *reinterpret_cast<uint4*>(dst + static_cast<long long>(c0 + ch) * P + p0 + pg * 8) = v;
+  }
+}
+
 }  // namespace htrvt
 
 using namespace htrvt;
+
+// in bf16 [R][P][C] -> out bf16 [R][C][P]; P % 8 == 0 and C % 8 == 0
+extern "C" int htrvt_transpose_px(const void* in, void* out, long long R, int P, int C, cudaStream_t stream) {
+  if (R <= 0 || R > 65535 || P <= 0 || C <= 0 || (P & 7) || (C & 7)) return HTRVT_ERR_SHAPE;
+  dim3 grid((P + 63) / 64, (C + 63) / 64, static_cast<unsigned>(R));
+  transpose_px_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in),
+                                                static_cast<__nv_bfloat16*>(out), P, C);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
 
 static inline int grid_for(long long n, int block) {
   long long g = (n + block - 1) / block;

@@ -73,9 +73,12 @@ int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, 
 int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw);
 int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* w, int Cout, int ks, int sh,
                      int sw, void* dx, int accumulate, void* stream);
-int htrvt_conv_wgrad(const void* dy, const void* x, int NB, int H, int W, int Cin, int Cout, int ks, int sh,
-                     int sw, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
+int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin, int Cout, int ks,
+                     int sh, int sw, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
                      void* stream);
+/* bf16 [R][P][C] -> [R][C][P]: pixel-contiguous copy of a stem gradient (dy_t above; tcgen05 runs an MN-major A
+ * operand ~1.4x slower than a K-major one, so the weight-gradient GEMM is fed dY^T) */
+int htrvt_transpose_px(const void* in, void* out, long long R, int P, int C, void* stream);
 
 /* ---- attention -------------------------------------------------------------------------------------------
  * Replaces Attention.forward's `q @ k^T * scale -> softmax -> @ v -> transpose/reshape`

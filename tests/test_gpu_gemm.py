@@ -138,5 +138,10 @@ def test_conv_fwd_dgrad_wgrad(NB, H, W, Cin, Cout, ks, sh, sw):
     dx = o.conv_dgrad(dy, wk, (NB, H, W, Cin), ks, sh, sw)
     assert _rel(dx.permute(0, 3, 1, 2), xr.grad) < 1e-2
     gw = torch.zeros(Cout, Cin, ks, ks, device="cuda")
-    o.conv_wgrad(dy, x, ks, sh, sw, gw, accumulate=False)
+    o.conv_wgrad(dy, x, ks, sh, sw, gw, accumulate=False, transpose=True)      # K-major dY^T operand (transpose_px)
     assert _rel(gw, wr.grad) < 1e-3
+    dyt = o.transpose_px(dy)
+    assert torch.equal(dyt, dy.permute(0, 1, 3, 2).contiguous())
+    gw2 = torch.zeros(Cout, Cin, ks, ks, device="cuda")
+    o.conv_wgrad(dy, x, ks, sh, sw, gw2, accumulate=False, transpose=False)    # both operands pixel-major
+    assert _rel(gw2, wr.grad) < 1e-3

@@ -35,8 +35,19 @@ wl3 = torch.randn(768, 9, 768, device=dev).bfloat16()
 yl3 = torch.empty(128, 2, 128, 768, device=dev, dtype=torch.bfloat16)
 gl3 = torch.zeros(768, 768, 3, 3, device=dev)
 g_fc1 = torch.zeros(3072, 768, device=dev)
+xl2 = torch.randn(128, 4, 256, 384, device=dev).bfloat16()
+yl2 = torch.randn(128, 4, 256, 384, device=dev).bfloat16()
+gl2 = torch.zeros(384, 384, 3, 3, device=dev)
 
+# operand major-ness experiment: the same 3072 x 768 x 16384 contraction with (A,B) = (K,K), (K,MN), (MN,MN)
+aK = torch.randn(3072, 16384, device=dev).bfloat16()
+bK = torch.randn(768, 16384, device=dev).bfloat16()
+bMN = torch.randn(16384, 768, device=dev).bfloat16()
+oKK = torch.empty(3072, 768, device=dev)
 cases = {
+    "mm_KK": (lambda: o.gemm_tn(aK, bK, oKK), 2.0 * 3072 * 768 * 16384),
+    "mm_KMN": (lambda: o.gemm_nn(aK, bMN, oKK), 2.0 * 3072 * 768 * 16384),
+    "mm_MNMN": (lambda: o.linear_wgrad(x3072, x768, g_fc1), 2.0 * 3072 * 768 * 16384),
     "proj": (lambda: o.gemm_tn(x768, w_proj, a_out.view(-1)[: M * 768].view(M, 768), bias=b768), 2.0 * M * 768 * 768),
     "fc1": (lambda: o.gemm_tn(x768, w_fc1, a_out, bias=b3072), 2.0 * M * 3072 * 768),
     "fc2": (lambda: o.gemm_tn(x3072, w_fc2, u_out.view(-1)[: M * 768].view(M, 768), bias=b768), 2.0 * M * 3072 * 768),
@@ -50,16 +61,18 @@ cases = {
     "l1_dgrad_acc": (lambda: o.conv_dgrad(yl1, wl1, (128, 8, 512, 192), 3, 1, 1, dx=xl1, accumulate=True), 2.0 * 128 * 8 * 512 * 192 * 1728),
     "l1_wgrad": (lambda: o.conv_wgrad(yl1, xl1, 3, 1, 1, gl1), 2.0 * 128 * 8 * 512 * 192 * 1728),
     "l3_fwd_stats": (lambda: o.conv_fwd(xl3, wl3, 3, 1, 1, y=yl3, stats=stats3), 2.0 * 128 * 2 * 128 * 768 * 6912),
+    "l2_wgrad": (lambda: o.conv_wgrad(yl2, xl2, 3, 1, 1, gl2), 2.0 * 128 * 4 * 256 * 384 * 3456),
     "l3_wgrad": (lambda: o.conv_wgrad(yl3, xl3, 3, 1, 1, gl3), 2.0 * 128 * 2 * 128 * 768 * 6912),
 }
 sel = sys.argv[1].split(",") if len(sys.argv) > 1 else list(cases)
+n_iter = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 for name in sel:
     fn, fl = cases[name]
-    for _ in range(2):
+    for _ in range(2 if n_iter > 1 else 1):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 10
+    n = n_iter
     e0.record()
     for _ in range(n):
         fn()
