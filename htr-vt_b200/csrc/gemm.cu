@@ -25,10 +25,10 @@ struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+  static constexpr int kStages = (BN <= 128) ? 6 : 4;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kStatsBytes = 8 * 2 * 16 * 4;                  // per-warp column partials
-  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * 8192 /* output staging: 2 x [128][64 B] */ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 8 * 2 * 2048;   // per epilogue warp: two [32 rows][64 B] output boxes
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 };
 
@@ -85,7 +85,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (smem_u32(smem) & 1023u) __trap();
   uint8_t* stage_base = smem;
   uint8_t* stage_out = smem + kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + 2 * 8192);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + Cfg::kStagingBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* tfull = bars + 2 * kStages;
@@ -191,9 +191,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =========================== epilogue (8 warps) ===========================
     // Deliberately light: only 8 warps run it, so anything beyond scale / bias / ReLU lives in separate
     // full-occupancy kernels (GELU, residual add) or in the memory system (accumulate = TMA reduce-add).
-    // Per 64-byte-wide box (32 bf16 or 16 fp32 columns x 128 rows): tcgen05.ld -> registers -> swizzled smem
-    // staging -> one elected thread issues the TMA store; BatchNorm column sums are read back from the
-    // staged tile by the warp that owns the rows and accumulated in registers across tiles.
+    // Every warp is autonomous: per 64-byte-wide box (32 bf16 or 16 fp32 columns) of ITS 32 rows it does
+    // tcgen05.ld -> registers -> swizzled smem staging (two buffers per warp) -> lane 0 issues the TMA store.
+    // TMA stores queue behind the producer's bulk loads inside the TMA unit (~1 us under load), so a warp never
+    // waits for the store it just issued, only for the one issued two boxes ago (wait_group.read 1).
+    // BatchNorm column sums are read back from the staged box and accumulated in registers across tiles.
     const int ew = warp - 2;                 // 0..7
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
     const int half = ew >> 2;                // column half handled by this warp
@@ -201,11 +203,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int kColsPerWarp = BN / 2;
     const bool out_bf16 = (P.flags & EPI_BF16) != 0;
     const int box_cols = out_bf16 ? 32 : 16;
-    uint8_t* stg = stage_out + half * 8192;                 // [128 rows][64 B], SWIZZLE_64B
-    const uint32_t stg_row = smem_u32(stg) + r * 64;
-    const int sw_r = (r >> 1) & 3;
-    const bool issuer = (quad == 0) && (lane == 0);
-    const uint32_t bar_id = 2 + half;
+    uint8_t* stg = stage_out + ew * 4096;                   // 2 x [32 rows][64 B], SWIZZLE_64B
+    const int sw_r = (lane >> 1) & 3;
+    int sbuf = 0;
     float ssum[4] = {0.f, 0.f, 0.f, 0.f}, qsum[4] = {0.f, 0.f, 0.f, 0.f};
     int stats_ntile = -1;
     auto flush_stats = [&](int n_tile) {
@@ -251,75 +251,89 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         uint32_t packed[16];
         if (out_bf16) {
+          float bv[32];
+          if (P.flags & EPI_BIAS) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {                // N_valid % 4 == 0: whole vectors are in or out
+              const float4 t = (col + i < P.N_valid) ? __ldg(reinterpret_cast<const float4*>(P.bias + col + i))
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+              bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float a = __uint_as_float(raw[i]) * P.alpha, c = __uint_as_float(raw[i + 1]) * P.alpha;
-            if (P.flags & EPI_BIAS) {
-              a += (col + i < P.N_valid) ? __ldg(P.bias + col + i) : 0.f;
-              c += (col + i + 1 < P.N_valid) ? __ldg(P.bias + col + i + 1) : 0.f;
-            }
+            if (P.flags & EPI_BIAS) { a += bv[i]; c += bv[i + 1]; }
             if (P.flags & EPI_RELU) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
             packed[i >> 1] = pack_bf16(a, c);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = __uint_as_float(raw[i]) * P.alpha;
-            if (P.flags & EPI_BIAS) a += (col + i < P.N_valid) ? __ldg(P.bias + col + i) : 0.f;
-            if (P.flags & EPI_RELU) a = fmaxf(a, 0.f);
-            packed[i] = __float_as_uint(a);
+          for (int i = 0; i < 16; i += 4) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((P.flags & EPI_BIAS) && col + i < P.N_valid) t = __ldg(reinterpret_cast<const float4*>(P.bias + col + i));
+            float v[4] = {fmaf(__uint_as_float(raw[i]), P.alpha, t.x), fmaf(__uint_as_float(raw[i + 1]), P.alpha, t.y),
+                          fmaf(__uint_as_float(raw[i + 2]), P.alpha, t.z), fmaf(__uint_as_float(raw[i + 3]), P.alpha, t.w)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (P.flags & EPI_RELU) v[k] = fmaxf(v[k], 0.f);
+              packed[i + k] = __float_as_uint(v[k]);
+            }
           }
         }
-        // the previous box's TMA store must have finished READING the staging buffer
-        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        // the store issued from this buffer two boxes ago must have finished READING it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        const uint32_t sbase = smem_u32(stg) + sbuf * 2048;
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
-          const uint32_t addr = stg_row + ((c16 ^ sw_r) << 4);
+          const uint32_t addr = sbase + lane * 64 + ((c16 ^ sw_r) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * c16]),
                        "r"(packed[4 * c16 + 1]), "r"(packed[4 * c16 + 2]), "r"(packed[4 * c16 + 3])
                        : "memory");
         }
         fence_proxy_async();
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        if (issuer && col < P.N_valid) {
-          int c1, c2, c3, c4;
-          if (KIND == 0) { c1 = tc.w0; c2 = tc.h; c3 = tc.n; c4 = 0; }
-          else { c1 = tc.m_tile * kBM; c2 = tc.tap; c3 = tc.split; c4 = 0; }
-          if (P.flags & EPI_ACCUM)
-            asm volatile(
-                "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(stg)), "r"(col), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-                : "memory");
-          else
-            asm volatile(
-                "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
-                ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(smem_u32(stg)), "r"(col), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-                : "memory");
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (col < P.N_valid) {
+            int c1, c2, c3, c4;
+            if (KIND == 0) { c1 = tc.w0 + quad * 32; c2 = tc.h; c3 = tc.n; c4 = 0; }
+            else { c1 = tc.m_tile * kBM + quad * 32; c2 = tc.tap; c3 = tc.split; c4 = 0; }
+            if (P.flags & EPI_ACCUM)
+              asm volatile(
+                  "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                  ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(sbase), "r"(col), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                  : "memory");
+            else
+              asm volatile(
+                  "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                  ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(sbase), "r"(col), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                  : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (possibly empty) keeps the buffer <-> group pairing
         }
         if (P.flags & EPI_STATS) {
-          // column `lane` of this warp's own 32 staged rows (bf16 box = 32 columns); rows outside the image are
+          // column `lane` of this warp's 32 staged rows (bf16 box = 32 columns); rows outside the image are
           // exact zeros (their A rows were TMA zero-filled and convolutions carry no bias)
-          float s = 0.f, q = 0.f;
-          const uint32_t base = smem_u32(stg) + (quad * 32) * 64 + (lane & 7) * 2;
+          float sacc = 0.f, qacc = 0.f;
+          const uint32_t base = sbase + (lane & 7) * 2;
 #pragma unroll 8
           for (int rr = 0; rr < 32; ++rr) {
-            const int row = quad * 32 + rr;
             uint16_t hv;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(base + rr * 64 + (((lane >> 3) ^ ((row >> 1) & 3)) << 4)));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(base + rr * 64 + (((lane >> 3) ^ ((rr >> 1) & 3)) << 4)));
             const float f = __uint_as_float(static_cast<uint32_t>(hv) << 16);
-            s += f;
-            q = fmaf(f, f, q);
+            sacc += f;
+            qacc = fmaf(f, f, qacc);
           }
-          ssum[b] += s;
-          qsum[b] += q;
+          ssum[b] += sacc;
+          qsum[b] += qacc;
         }
+        sbuf ^= 1;
       }
       as ^= 1; if (as == 0) aphase ^= 1;
     }
     if (P.flags & EPI_STATS) flush_stats(stats_ntile);
-    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -399,13 +413,13 @@ int make_map_act(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, in
   return make_map5(m, ptr, dims, st, box);
 }
 
-// Output map of a kind-0 GEMM: (cols, w, h, n, 1) with element strides (s_w, s_h, s_n); box = 64 bytes x 128 rows
+// Output map of a kind-0 GEMM: (cols, w, h, n, 1) with element strides (s_w, s_h, s_n); box = 64 bytes x 32 rows
 int make_map_out(CUtensorMap* m, void* ptr, int elem_bytes, long long cols, long long W, long long H, long long N,
                  long long s_w, long long s_h, long long s_n) {
   const long long dims[5] = {cols, W, H, N, 1};
   const long long big = s_n * (N > 0 ? N : 1);
   const long long st[4] = {s_w, H > 1 ? s_h : s_w * W, N > 1 ? s_n : (H > 1 ? s_h * H : s_w * W), big > 0 ? big : s_w * W};
-  const int box[5] = {64 / elem_bytes, kBM, 1, 1, 1};
+  const int box[5] = {64 / elem_bytes, 32, 1, 1, 1};          // one epilogue warp's rows
   return make_map5(m, ptr, dims, st, box, elem_bytes, true);
 }
 
@@ -584,7 +598,7 @@ int make_map_wgrad_out(CUtensorMap* m, void* ws, int Cout, int taps, int Cin, in
   const long long dims[5] = {Cin, Cout, taps, splits, 1};
   const long long per = static_cast<long long>(Cout) * taps * Cin;
   const long long st[4] = {static_cast<long long>(taps) * Cin, Cin, per, per * splits};
-  const int box[5] = {16, kBM, 1, 1, 1};
+  const int box[5] = {16, 32, 1, 1, 1};
   return make_map5(m, ws, dims, st, box, 4, true);
 }
 }  // namespace
