@@ -149,6 +149,30 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const void* desc, uint64_
       : "memory");
 }
 
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, and each destination
+// CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_5d_mc(void* dst, const void* desc, uint64_t* bar, int c0, int c1, int c2,
+                                               int c3, int c4, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4), "h"(mask)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// thread-block clusters
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {       // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------------------------
@@ -181,6 +205,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// ... and on the same-offset mbarrier of every CTA in `mask` (smem slots shared through TMA multicast)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
 }
 // TMEM -> registers: each thread reads its own lane (row), 16 consecutive 32-bit columns.
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {

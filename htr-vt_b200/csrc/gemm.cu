@@ -74,7 +74,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmP& P, int id) {
   return c;
 }
 
-template <int BN, int KIND, bool B_MN>
+template <int BN, int KIND, bool B_MN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmP P) {
@@ -94,18 +94,25 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = P.tiles_m * P.tiles_n * (P.kind == 0 ? 1 : P.n_taps * P.splits);
+  // CL == 2: a cluster of two CTAs works on tiles (2p, 2p+1) = neighbouring m-tiles of the same B tile (the host
+  // guarantees tiles_m is even); each CTA loads half of B and multicasts it into both CTAs' smem, which cuts the
+  // L2 -> SM fill traffic per flop by ~1/3 (these GEMMs are fill bound at 128 x BN x 64 stages).
+  const int crank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int first_tile = (CL == 2) ? (static_cast<int>(blockIdx.x >> 1) * 2 + crank) : static_cast<int>(blockIdx.x);
+  const int tile_step = (CL == 2) ? static_cast<int>(gridDim.x & ~1u) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();           // the peer's barriers must be initialised before anything lands on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -113,7 +120,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =========================== TMA producer ===========================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int id = blockIdx.x; id < total_tiles; id += gridDim.x) {
+      for (int id = first_tile; id < total_tiles; id += tile_step) {
         const TileCoord tc = decode_tile(P, id);
         const int n0 = tc.n_tile * BN, m0 = tc.m_tile * kBM;
         const int kiters = (KIND == 0) ? P.n_taps * P.k_chunks : (tc.q_end - tc.q_begin);
@@ -127,12 +134,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_5d(sa, &tmA, &full[stage], cc * kBK, P.tap.pw[tap], tc.w0 + P.tap.dw[tap],
                         tc.h * P.a_sh + P.tap.dh[tap], tc.n);
             if (!B_MN) {
-              tma_load_5d(sb, &tmB, &full[stage], P.tap.widx[tap] * P.b_tap_stride + cc * kBK, n0, 0, 0, 0);
+              if (CL == 2)          // my half of the B rows, into both CTAs
+                tma_load_5d_mc(sb + crank * (BN / 2) * 128, &tmB, &full[stage],
+                               P.tap.widx[tap] * P.b_tap_stride + cc * kBK, n0 + crank * (BN / 2), 0, 0, 0, 3);
+              else
+                tma_load_5d(sb, &tmB, &full[stage], P.tap.widx[tap] * P.b_tap_stride + cc * kBK, n0, 0, 0, 0);
             } else {
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i)
-                tma_load_5d(sb + i * 8192, &tmB, &full[stage], P.tap.widx[tap] * P.b_tap_stride + n0 + 64 * i,
-                            cc * kBK, 0, 0, 0);
+              for (int i = 0; i < BN / 64; ++i) {
+                if (CL == 2)        // my 32 of the 64 K rows of every 64-column atom, into both CTAs
+                  tma_load_5d_mc(sb + i * 8192 + crank * 4096, &tmB, &full[stage],
+                                 P.tap.widx[tap] * P.b_tap_stride + n0 + 64 * i, cc * kBK + 32 * crank, 0, 0, 0, 3);
+                else
+                  tma_load_5d(sb + i * 8192, &tmB, &full[stage], P.tap.widx[tap] * P.b_tap_stride + n0 + 64 * i,
+                              cc * kBK, 0, 0, 0);
+              }
             }
           } else {
             const int q = tc.q_begin + k;
@@ -146,9 +162,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_5d(sa, &tmA, &full[stage], w0c, m0, ho, n, 0);
             }
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_5d(sb + i * 8192, &tmB, &full[stage], n0 + 64 * i, P.tap.pw[tc.tap],
-                          w0c + P.tap.dw[tc.tap], ho * P.a_sh + P.tap.dh[tc.tap], n);
+            for (int i = 0; i < BN / 64; ++i) {
+              if (CL == 2)
+                tma_load_5d_mc(sb + i * 8192 + crank * 4096, &tmB, &full[stage], n0 + 64 * i, P.tap.pw[tc.tap],
+                               w0c + P.tap.dw[tc.tap] + 32 * crank, ho * P.a_sh + P.tap.dh[tc.tap], n, 3);
+              else
+                tma_load_5d(sb + i * 8192, &tmB, &full[stage], n0 + 64 * i, P.tap.pw[tc.tap],
+                            w0c + P.tap.dw[tc.tap], ho * P.a_sh + P.tap.dh[tc.tap], n);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -160,7 +181,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int id = blockIdx.x; id < total_tiles; id += gridDim.x) {
+      for (int id = first_tile; id < total_tiles; id += tile_step) {
         const TileCoord tc = decode_tile(P, id);
         const int kiters = (KIND == 0) ? P.n_taps * P.k_chunks : (tc.q_end - tc.q_begin);
         mbar_wait(&tempty[as], aphase ^ 1);
@@ -179,7 +200,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                      : umma_desc_sw128(sb + kk * 32, 16, 1024);
             umma_bf16(d_tmem, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if (CL == 2) umma_commit_mc(&empty[stage], 3); else umma_commit(&empty[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[as]);
@@ -222,7 +243,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
     int as = 0; uint32_t aphase = 0;
-    for (int id = blockIdx.x; id < total_tiles; id += gridDim.x) {
+    for (int id = first_tile; id < total_tiles; id += tile_step) {
       const TileCoord tc = decode_tile(P, id);
       const int n0 = tc.n_tile * BN;
       if ((P.flags & EPI_STATS) && tc.n_tile != stats_ntile) { flush_stats(stats_ntile); stats_ntile = tc.n_tile; }
@@ -337,6 +358,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();           // no CTA may exit while its peer can still write its smem / barriers
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
@@ -434,32 +456,70 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int KIND, bool B_MN>
+template <int BN, int KIND, bool B_MN, int CL>
 int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
                cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
-  auto kern = tapgemm_kernel<BN, KIND, B_MN>;
+  auto kern = tapgemm_kernel<BN, KIND, B_MN, CL>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return HTRVT_ERR_LAUNCH;
     configured = true;
   }
-  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, c, P);
+  int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  if (CL == 1) {
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, c, P);
+  } else {
+    grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, a, b, c, P) != cudaSuccess) return HTRVT_ERR_LAUNCH;
+  }
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
 
 template <int KIND, bool B_MN>
-int launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total,
-              cudaStream_t s) {
+int launch_bn(int bn, int cl, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P,
+              int total, cudaStream_t s) {
+  if (cl == 2) {
+    switch (bn) {
+      case 128: return launch_one<128, KIND, B_MN, 2>(a, b, c, P, total, s);
+      case 192: return launch_one<192, KIND, B_MN, 2>(a, b, c, P, total, s);
+      case 256: return launch_one<256, KIND, B_MN, 2>(a, b, c, P, total, s);
+    }
+    return HTRVT_ERR_SHAPE;
+  }
   switch (bn) {
-    case 128: return launch_one<128, KIND, B_MN>(a, b, c, P, total, s);
-    case 192: return launch_one<192, KIND, B_MN>(a, b, c, P, total, s);
-    case 256: return launch_one<256, KIND, B_MN>(a, b, c, P, total, s);
+    case 128: return launch_one<128, KIND, B_MN, 1>(a, b, c, P, total, s);
+    case 192: return launch_one<192, KIND, B_MN, 1>(a, b, c, P, total, s);
+    case 256: return launch_one<256, KIND, B_MN, 1>(a, b, c, P, total, s);
   }
   return HTRVT_ERR_SHAPE;
+}
+
+int dbg_env(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+
+// 2-CTA clusters with a multicast B operand need tile pairs (2p, 2p+1) that share their B tile: tiles_m even.
+// Measured on B200 (tools/profile_gemm.py): multicast does NOT speed these GEMMs up - they are bound by the
+// per-SM L2 -> SM ingress (~68 B/clk: tensor-pipe utilisation tracks 68 / ((128 + BN) * 128 / (2 BN)) for every tile
+// shape), and a multicast box still enters both SMs in full.  Kept (opt-in, HTRVT_CLUSTER=1) as the stepping stone
+// to cta_group::2 pairs, where each SM only receives HALF of B.
+int pick_cluster(int tiles_m, int total_tiles) {
+  static const int on = dbg_env("HTRVT_CLUSTER");
+  return (on && (tiles_m % 2) == 0 && total_tiles >= 4) ? 2 : 1;
 }
 
 int pick_bn(int N) {
@@ -487,11 +547,6 @@ void fill_taps_conv(TapTab& t, int ks, int pad, int sw, int* n_taps) {
 
 // developer knobs for tools/profile_gemm.py (unset in production): HTRVT_DBG_SPLITS=n forces the split-K factor,
 // HTRVT_DBG_WGRAD_NOSTORE=1 skips the weight-gradient epilogue stores (main loop timing)
-int dbg_env(const char* name) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : 0;
-}
-
 // Split-K factor for the weight-gradient GEMMs: minimise (waves x per-split tile time) + partial-sum traffic.
 int choose_splits(int base_tiles, long long q_total, long long out_elems) {
   const int sms = num_sms();
@@ -519,6 +574,8 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
   if (M <= 0 || N <= 0 || K <= 0 || (N & 3)) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(N);
   const int esz = (flags & EPI_BF16) ? 2 : 4;
+  const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + bn - 1) / bn;
+  const int cl = pick_cluster(tiles_m, tiles_m * tiles_n);
   CUtensorMap ta, tb, tc;
   {
     const long long dims[5] = {K, 1, M, 1, 1};
@@ -526,18 +583,18 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
     const int box[5] = {kBK, 1, kBM, 1, 1};
     int r = make_map5(&ta, X, dims, st, box);
     if (r) return r;
-    r = make_map_matrix(&tb, W, N, K, ldw, kBK, bn);
+    r = make_map_matrix(&tb, W, N, K, ldw, kBK, bn / cl);
     if (r) return r;
     r = make_map_out(&tc, out, esz, N, M, 1, 1, ldo, ldo * M, ldo * M);
     if (r) return r;
   }
   GemmP P = {};
   P.kind = 0; P.Wo = M; P.Ho = 1; P.NB = 1;
-  P.tiles_per_row = (M + kBM - 1) / kBM; P.tiles_m = P.tiles_per_row; P.tiles_n = (N + bn - 1) / bn;
+  P.tiles_per_row = tiles_m; P.tiles_m = tiles_m; P.tiles_n = tiles_n;
   P.n_taps = 1; P.splits = 1; P.k_chunks = (K + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = 0;
   P.M_valid = M; P.N_valid = N; P.flags = flags & (EPI_BF16 | EPI_BIAS | EPI_RELU | EPI_ACCUM | EPI_NOSTORE);
   P.bias = bias; P.alpha = alpha;
-  return launch_bn<0, false>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+  return launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
 
 // dX[M,N] = dY[M,K] W[K,N]: nn.Linear input gradient (B operand MN-major, no transpose copy).
@@ -546,6 +603,8 @@ extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long
   if (M <= 0 || N <= 0 || K <= 0 || (N & 7)) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(N);
   const int esz = (flags & EPI_BF16) ? 2 : 4;
+  const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + bn - 1) / bn;
+  const int cl = pick_cluster(tiles_m, tiles_m * tiles_n);
   CUtensorMap ta, tb, tc;
   {
     const long long dims[5] = {K, 1, M, 1, 1};
@@ -553,18 +612,18 @@ extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long
     const int box[5] = {kBK, 1, kBM, 1, 1};
     int r = make_map5(&ta, dY, dims, st, box);
     if (r) return r;
-    r = make_map_matrix(&tb, W, K, N, ldw, 64, 64);
+    r = make_map_matrix(&tb, W, K, N, ldw, 64, 64 / cl);
     if (r) return r;
     r = make_map_out(&tc, out, esz, N, M, 1, 1, ldo, ldo * M, ldo * M);
     if (r) return r;
   }
   GemmP P = {};
   P.kind = 0; P.Wo = M; P.Ho = 1; P.NB = 1;
-  P.tiles_per_row = (M + kBM - 1) / kBM; P.tiles_m = P.tiles_per_row; P.tiles_n = (N + bn - 1) / bn;
+  P.tiles_per_row = tiles_m; P.tiles_m = tiles_m; P.tiles_n = tiles_n;
   P.n_taps = 1; P.splits = 1; P.k_chunks = (K + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = 0;
   P.M_valid = M; P.N_valid = N; P.flags = flags & (EPI_BF16 | EPI_ACCUM | EPI_NOSTORE);
   P.alpha = alpha;
-  return launch_bn<0, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+  return launch_bn<0, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
 
 extern "C" size_t htrvt_wgrad_workspace_bytes(int Cout, int Cin, int n_taps, int M_pixels) {
@@ -609,6 +668,7 @@ extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X,
                                   cudaStream_t stream) {
   if (M <= 0 || Nout <= 0 || Kin <= 0 || (Kin & 7) || (Nout & 7)) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(Kin);
+  const int cl = pick_cluster((Nout + kBM - 1) / kBM, 4);
   CUtensorMap ta, tb, tc;
   int r;
   {
@@ -619,7 +679,8 @@ extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X,
     if (r) return r;
     const long long dimsB[5] = {Kin, 1, M, 1, 1};
     const long long stB[4] = {ldx, ldx, ldx * M, ldx * M};
-    r = make_map5(&tb, X, dimsB, stB, box);
+    const int boxB[5] = {64, 1, 64 / cl, 1, 1};
+    r = make_map5(&tb, X, dimsB, stB, boxB);
     if (r) return r;
   }
   GemmP P = {};
@@ -632,7 +693,7 @@ extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X,
   if (!workspace || workspace_bytes < need) return HTRVT_ERR_WORKSPACE;
   r = make_map_wgrad_out(&tc, workspace, Nout, 1, Kin, P.splits);
   if (r) return r;
-  r = launch_bn<1, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.splits, stream);
+  r = launch_bn<1, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.splits, stream);
   if (r) return r;
   const long long total = static_cast<long long>(Nout) * Kin;
   const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
@@ -656,10 +717,13 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
   if ((Cin % 64) || (Cout & 7) || (W % sw) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
   const int bn = pick_bn(Cout);
+  const int tiles_m_all = ((Wo + kBM - 1) / kBM) * Ho * NB;
+  const int cl = pick_cluster(tiles_m_all, tiles_m_all * ((Cout + bn - 1) / bn));
   CUtensorMap ta, tb, tc;
   int r = make_map_act(&ta, x, NB, H, W, Cin, sw, kBK, kBM);
   if (r) return r;
-  r = make_map_matrix(&tb, w, Cout, static_cast<long long>(ks) * ks * Cin, static_cast<long long>(ks) * ks * Cin, kBK, bn);
+  r = make_map_matrix(&tb, w, Cout, static_cast<long long>(ks) * ks * Cin, static_cast<long long>(ks) * ks * Cin, kBK,
+                      bn / cl);
   if (r) return r;
   r = make_map_out(&tc, y, 2, Cout, Wo, Ho, NB, Cout, static_cast<long long>(Wo) * Cout,
                    static_cast<long long>(Ho) * Wo * Cout);
@@ -672,7 +736,7 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
   P.M_valid = 0; P.N_valid = Cout;
   P.flags = EPI_BF16 | (flags & (EPI_RELU | EPI_NOSTORE)) | (stats_partial ? EPI_STATS : 0);
   P.stats = stats_partial; P.alpha = 1.f;
-  return launch_bn<0, false>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+  return launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
 
 // dx[NB,H,W,Cin] (= or +=) conv_transpose(dy[NB,Ho,Wo,Cout], w): one GEMM per output parity class.
@@ -684,8 +748,6 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
   const int bn = pick_bn(Cin);
   CUtensorMap ta, tb;
   int r = make_map_act(&ta, dy, NB, Ho, Wo, Cout, 1, kBK, kBM);
-  if (r) return r;
-  r = make_map_matrix(&tb, w, Cout, static_cast<long long>(ks) * ks * Cin, static_cast<long long>(ks) * ks * Cin, 64, 64);
   if (r) return r;
   for (int ph = 0; ph < sh; ++ph)
     for (int pw = 0; pw < sw; ++pw) {
@@ -708,12 +770,16 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
       P.n_taps = n; P.splits = 1; P.k_chunks = (Cout + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = Cin;
       P.N_valid = Cin; P.flags = EPI_BF16 | (accumulate ? EPI_ACCUM : 0);
       P.alpha = 1.f;
+      const int cl = pick_cluster(P.tiles_m, P.tiles_m * P.tiles_n);
+      r = make_map_matrix(&tb, w, Cout, static_cast<long long>(ks) * ks * Cin, static_cast<long long>(ks) * ks * Cin, 64,
+                          64 / cl);
+      if (r) return r;
       CUtensorMap tc;                                     // parity class (ph, pw) of dx as a strided tensor
       r = make_map_out(&tc, static_cast<__nv_bfloat16*>(dx) + (static_cast<long long>(ph) * W + pw) * Cin, 2, Cin, Wq,
                        Hq, NB, static_cast<long long>(sw) * Cin, static_cast<long long>(sh) * W * Cin,
                        static_cast<long long>(H) * W * Cin);
       if (r) return r;
-      r = launch_bn<0, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+      r = launch_bn<0, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
       if (r) return r;
     }
   return HTRVT_OK;
@@ -742,7 +808,8 @@ extern "C" int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x,
     r = make_map_act(&ta, dy, NB, Ho, Wo, Cout, 1, 64, 64);
   }
   if (r) return r;
-  r = make_map_act(&tb, x, NB, H, W, Cin, sw, 64, 64);
+  const int cl = pick_cluster((Cout + kBM - 1) / kBM, 4);
+  r = make_map_act(&tb, x, NB, H, W, Cin, sw, 64, 64 / cl);
   if (r) return r;
   GemmP P = {};
   P.kind = 1; P.Wo = Wo; P.Ho = Ho; P.NB = NB; P.tiles_per_row = 1;
@@ -756,8 +823,8 @@ extern "C" int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x,
   if (!workspace || workspace_bytes < static_cast<size_t>(P.splits) * per * sizeof(float)) return HTRVT_ERR_WORKSPACE;
   r = make_map_wgrad_out(&tc, workspace, Cout, P.n_taps, Cin, P.splits);
   if (r) return r;
-  r = a_kmajor ? launch_bn<2, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream)
-               : launch_bn<1, true>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream);
+  r = a_kmajor ? launch_bn<2, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream)
+               : launch_bn<1, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream);
   if (r) return r;
   const int blocks = static_cast<int>((per + 255) / 256 < 2048 ? (per + 255) / 256 : 2048);
   wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), P.splits, Cout, P.n_taps, Cin,
