@@ -82,6 +82,10 @@ SIGNATURES = {
     "htrvt_stem_head_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_stem_head_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_attention_fwd": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "htrvt_attention2_fwd": (_I, [_P, _I, _I, _I, _I, _F, _P, _I, _I, _I, _F, ctypes.c_ulonglong, _P, _P, _P]),
+    "htrvt_attention2_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "htrvt_attention2_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _I, _F, ctypes.c_ulonglong, _P, _P, _P,
+                                  _Z, _P]),
     "htrvt_attention_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
 }
 

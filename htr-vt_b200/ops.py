@@ -154,6 +154,29 @@ def attention_bwd(qkv, out, dout, lse, dqkv, scale):
     return dqkv
 
 
+def attention2_fwd(qkv, out, lse, scale, table=None, prel=0, window=0, shift=0, drop_p=0.0, seed=0):
+    """Windowed-variant attention (T <= 256): relative-position bias table fp32 [2*prel-1, H] (None: no bias),
+    window 0 (global) or 16 (16-token windows over the sequence rolled by -shift), attention dropout drop_p."""
+    _need_cuda(qkv, out)
+    B, T, _, H, hd = qkv.shape
+    check(lib().htrvt_attention2_fwd(_p(qkv), B, H, T, hd, scale, _p(table), prel, window, shift, drop_p, seed, _p(out),
+                                     _p(lse), _stream()), "htrvt_attention2_fwd")
+    return out
+
+
+def attention2_bwd(qkv, out, dout, lse, dqkv, scale, table=None, prel=0, window=0, shift=0, dtable=None, drop_p=0.0,
+                   seed=0):
+    """-> dqkv bf16 [B,T,3,H,hd]; dtable fp32 [2*prel-1, H] accumulated (+=) when given."""
+    _need_cuda(qkv, out, dout, lse, dqkv)
+    B, T, _, H, hd = qkv.shape
+    nbytes = lib().htrvt_attention2_bwd_workspace_bytes(B, H, T, window)
+    ws = workspace(nbytes, qkv.device) if nbytes else None
+    check(lib().htrvt_attention2_bwd(_p(qkv), _p(out), _p(dout), _p(lse), B, H, T, hd, scale, _p(table), prel, window,
+                                     shift, drop_p, seed, _p(dqkv), _p(dtable), _p(ws), ws.numel() if ws is not None else 0,
+                                     _stream()), "htrvt_attention2_bwd")
+    return dqkv
+
+
 # ------------------------------------------------------------------------------------------------
 # CTC + decode
 # ------------------------------------------------------------------------------------------------
@@ -517,6 +540,12 @@ def _flops(name, a, kw):
         if name == "conv_wgrad":
             dy, x, ks = a[:3]
             return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * x.shape[3]
+        if name == "attention2_fwd":
+            B, T, _, H, hd = a[0].shape
+            return 4.0 * B * H * T * T * hd
+        if name == "attention2_bwd":
+            B, T, _, H, hd = a[0].shape
+            return 10.0 * B * H * T * T * hd
         if name == "attention_fwd":
             B, T, _, H, hd = a[0].shape
             return 4.0 * B * H * T * T * hd
@@ -532,7 +561,7 @@ def _instrument():
     import functools
     g = globals()
     names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "attention_fwd",
-             "attention_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd",
+             "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd",
              "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16",
              "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",
              "conv1_wgrad", "stem_head_moments", "stem_head_fwd", "stem_head_bwd"]

@@ -90,6 +90,20 @@ int htrvt_attention_fwd(const void* qkv, int B, int H, int T, int hd, float scal
 int htrvt_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int H, int T,
                         int hd, float scale, void* dqkv, void* stream);
 
+/* ---- attention of the windowed variant (model_window/model/HTR_VT.py:33-62 Attention.forward with
+ * relative_position_bias_table, :114-154 Block._attend: roll by -shift, 16-token windows, roll back), T <= 256.
+ * table: fp32 [2*Prel-1][H] or NULL; window: 0 (global) or 16; shift: multiple of 8 (needs T % 128 == 0 when > 0);
+ * drop_p / seed: attention dropout as a counter-based hash of (seed, b, h, query token, key token) - the backward
+ * regenerates the mask.  dtable (+=) is accumulated with fp32 atomics.  workspace: partial dQ for global T > 128. */
+int htrvt_attention2_fwd(const void* qkv, int B, int H, int T, int hd, float scale, const float* table, int Prel,
+                         int window, int shift, float drop_p, unsigned long long seed, void* out, float* lse,
+                         void* stream);
+size_t htrvt_attention2_bwd_workspace_bytes(int B, int H, int T, int window);
+int htrvt_attention2_bwd(const void* qkv, const void* out, const void* dout, const float* lse, int B, int H, int T,
+                         int hd, float scale, const float* table, int Prel, int window, int shift, float drop_p,
+                         unsigned long long seed, void* dqkv, float* dtable, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* ---- LayerNorms, tokens, elementwise ---------------------------------------------------------------------
  * sample_ln : parameter-free LayerNorm over all non-batch dims, eps 1e-5 (model_v1/model/HTR_VT.py:134-136,
  *             used at :224 on the image and :239 on the logits slab)
