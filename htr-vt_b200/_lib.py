@@ -65,6 +65,7 @@ SIGNATURES = {
     "htrvt_colsum_rows": (_I, [_I]),
     "htrvt_colsum_bf16": (_I, [_P, _L, _I, _I, _P, _I, _P, _P]),
     "htrvt_cast_bf16": (_I, [_P, _P, _L, _P]),
+    "htrvt_dropout_bf16": (_I, [_P, _L, _L, _F, ctypes.c_ulonglong, ctypes.c_uint, _P, _P]),
     "htrvt_pack_weights": (_I, [_I, _P, _P, _P, _P, _P, _P]),
     "htrvt_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "htrvt_conv1_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -381,6 +381,37 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackTable T) {
   }
 }
 
+// In-place inverted dropout (+ per-sample DropPath scale) on a bf16 tensor: x[i] *= keep(seed, site, i) / (1 - p)
+// * dp[sample(i)].  The mask is a counter-based hash, so applying the same call to the gradient in the backward
+// regenerates it (nothing is stored).  Replaces nn.Dropout / timm DropPath of the windowed variant
+// (model_window/model/HTR_VT.py:21-23,59-60,100-110; timm Mlp drop1/drop2) in train mode.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+__global__ void dropout_bf16_kernel(__nv_bfloat16* __restrict__ x, long long n8, long long per_sample8, float p,
+                                    float inv_keep, unsigned long long seed, unsigned site,
+                                    const float* __restrict__ dp) {
+  const uint32_t key = mix32(static_cast<uint32_t>(seed) ^ (site * 0x9e3779b9u)) ^ static_cast<uint32_t>(seed >> 32);
+  const uint32_t thr = static_cast<uint32_t>(p * 16777216.0f);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float sc = dp ? dp[i / per_sample8] : 1.0f;
+    uint4 u = *reinterpret_cast<const uint4*>(x + i * 8);
+    uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t r = mix32(key + static_cast<uint32_t>(i) * 4u + k) ^ static_cast<uint32_t>(i >> 30);
+      // the two 16-bit halves of one hash decide the two bf16 of this word (keep test at 2^-16 resolution)
+      const float2 v = unpack_bf16(w[k]);
+      const float k0 = ((r & 0xffffu) << 8) < thr ? 0.f : inv_keep * sc;
+      const float k1 = ((r >> 16) << 8) < thr ? 0.f : inv_keep * sc;
+      w[k] = pack_bf16(v.x * k0, v.y * k1);
+    }
+    *reinterpret_cast<uint4*>(x + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // in [R][P][C] bf16 (pixels x channels, channels contiguous) -> out [R][C][P] (pixels contiguous): the K-major
 // dY^T operand of the weight-gradient GEMM.  64 x 64 tiles through padded smem; grid (ceil(P/64), ceil(C/64), R).
 __global__ void __launch_bounds__(256) transpose_px_kernel(const __nv_bfloat16* __restrict__ in,
@@ -597,5 +628,18 @@ extern "C" int htrvt_pack_weights(int n, const void* const* src, void* const* ds
     pack_weights_kernel<<<grid, 256, 0, stream>>>(T);
     HTRVT_LAUNCH_CHECK();
   }
+  return HTRVT_OK;
+}
+
+
+// x bf16 [n] in place; per_sample = elements per batch sample (DropPath scale dp[b], nullable); n, per_sample % 8 == 0
+extern "C" int htrvt_dropout_bf16(void* x, long long n, long long per_sample, float p, unsigned long long seed,
+                                  unsigned site, const float* dp, cudaStream_t stream) {
+  if (n <= 0 || (n & 7) || per_sample <= 0 || (per_sample & 7) || p < 0.f || p >= 1.f) return HTRVT_ERR_SHAPE;
+  const long long n8 = n / 8;
+  const int blocks = static_cast<int>((n8 + 255) / 256 < 148 * 16 ? (n8 + 255) / 256 : 148 * 16);
+  dropout_bf16_kernel<<<blocks, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(x), n8, per_sample / 8, p,
+                                                  1.0f / (1.0f - p), seed, site, dp);
+  HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }

@@ -29,11 +29,13 @@ def _bn_args(sd, prefix):
 class Engine(object):
     """Stateless w.r.t. parameters: every call receives the module's current tensors by name."""
 
-    def __init__(self, embed_dim, depth, num_heads, nb_cls, ln_eps=1e-6, variant="v1"):
+    def __init__(self, embed_dim, depth, num_heads, nb_cls, ln_eps=1e-6, variant="v1", windows=None):
         self.D, self.depth, self.H, self.C = embed_dim, depth, num_heads, nb_cls
         self.hd = embed_dim // num_heads
         self.ln_eps = ln_eps
         self.variant = variant
+        # window variant: (window_size, shift) per block (model_window/model/HTR_VT.py:274-275)
+        self.windows = list(windows) if windows is not None else [(0, 0)] * depth
         if self.hd != 128:
             raise ops.HtrvtError("attention kernel is specialised for head_dim 128 (got %d)" % self.hd)
         if embed_dim % 256 or nb_cls < 2:
@@ -58,8 +60,9 @@ class Engine(object):
         y = ops.conv_fwd(x, wp, ks, stride[0], stride[1], stats=stats)
         return y, stats
 
-    def forward(self, sd, image, mask, training, save):
+    def forward(self, sd, image, mask, training, save, rng=None):
         """sd: name -> tensor (parameters + BN buffers); image fp32 [B,1,H,W]; mask fp32 [T] or None.
+        rng (window variant, train mode): dict(seed, drop, attn_drop, drop_path=[(dp1, dp2) per block]) or None.
         Returns (logits fp32 [B,T,C], ctx | None)."""
         if image.dim() != 4 or image.shape[1] != 1:
             raise ValueError("expected image [B, 1, H, W]")
@@ -79,7 +82,9 @@ class Engine(object):
             elif v.dim() == 2 and k.endswith(".weight"):
                 names.append(k)
                 items.append((v, "cast"))
-        wp = dict(zip(names, ops.pack_weights(items)))          # one launch for all 36 weight tensors
+        C8 = (C + 7) // 8 * 8            # the head GEMM runs on a class axis padded to a multiple of 8 (zero rows)
+        wp = dict(zip(names, ops.pack_weights(items, pad_rows={"head.weight": C8} if C8 != C else None,
+                                              names=names)))    # one launch for all 36 weight tensors
 
         # ---- stem -----------------------------------------------------------------------------
         x0, _, _ = ops.sample_ln_fwd(image.view(B, Hi, Wi), torch.float32, 1e-5)
@@ -134,30 +139,49 @@ class Engine(object):
         scale = self.hd ** -0.5
         tblocks = []
         pend = None                       # bf16 GEMM output still to be added to the residual stream
+        drop = rng["drop"] if rng else 0.0
+        attn_drop = rng["attn_drop"] if rng else 0.0
+        seed = rng["seed"] if rng else 0
         for i in range(self.depth):
             p = "blocks.%d" % i
+            dp1, dp2 = rng["drop_path"][i] if rng else (None, None)
             # x1 = xs + pend (previous block's fc2 output), h1 = LN1(x1): the residual add is fused into the LN
             h1, m1, r1s, x1 = ops.row_ln_fwd(xs, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], self.ln_eps, pend)
             qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=xs.device)
             ops.gemm_tn(h1, wp[p + ".attn.qkv.weight"], qkv, bias=sd[p + ".attn.qkv.bias"])
             o = torch.empty((M, D), dtype=torch.bfloat16, device=xs.device)
             lse = torch.empty((B, self.H, T), dtype=torch.float32, device=xs.device)
-            ops.attention_fwd(qkv.view(B, T, 3, self.H, self.hd), o.view(B, T, D), lse, scale)
+            if self.variant == "v1":
+                ops.attention_fwd(qkv.view(B, T, 3, self.H, self.hd), o.view(B, T, D), lse, scale)
+            else:
+                tbl = sd[p + ".attn.relative_position_bias_table"]
+                ws, sh = self.windows[i]
+                ops.attention2_fwd(qkv.view(B, T, 3, self.H, self.hd), o.view(B, T, D), lse, scale, tbl,
+                                   (tbl.shape[0] + 1) // 2, ws, sh, attn_drop, seed + 16 * i)
             y1 = torch.empty((M, D), dtype=torch.bfloat16, device=xs.device)
             ops.gemm_tn(o, wp[p + ".attn.proj.weight"], y1, bias=sd[p + ".attn.proj.bias"])
+            if rng:
+                ops.dropout_(y1, T * D, drop, seed, 8 * i + 1, dp1)
             h2, m2, r2s, x2 = ops.row_ln_fwd(x1, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], self.ln_eps, y1)
             hid = wp[p + ".mlp.fc1.weight"].shape[0]
             u = torch.empty((M, hid), dtype=torch.bfloat16, device=xs.device)
             ops.gemm_tn(h2, wp[p + ".mlp.fc1.weight"], u, bias=sd[p + ".mlp.fc1.bias"])
             a = ops.gelu_fwd(u)
+            if rng:
+                ops.dropout_(a, T * hid, drop, seed, 8 * i + 2)
             y2 = torch.empty((M, D), dtype=torch.bfloat16, device=xs.device)
             ops.gemm_tn(a, wp[p + ".mlp.fc2.weight"], y2, bias=sd[p + ".mlp.fc2.bias"])
+            if rng:
+                ops.dropout_(y2, T * D, drop, seed, 8 * i + 3, dp2)
             if save:
-                tblocks.append((p, x1, h1, m1, r1s, qkv, o, lse, x2, h2, m2, r2s, a, u))
+                tblocks.append((i, p, x1, h1, m1, r1s, qkv, o, lse, x2, h2, m2, r2s, a, u))
             xs, pend = x2, y2
         hf, mf, rf, xs = ops.row_ln_fwd(xs, sd["norm.weight"], sd["norm.bias"], self.ln_eps, pend)
-        raw_logits = torch.empty((M, C), dtype=torch.float32, device=xs.device)
-        ops.gemm_tn(hf, wp["head.weight"], raw_logits, bias=sd["head.bias"])
+        raw_logits = torch.empty((M, C8), dtype=torch.float32, device=xs.device)
+        hb = sd["head.bias"] if C8 == C else torch.nn.functional.pad(sd["head.bias"].detach(), (0, C8 - C))
+        ops.gemm_tn(hf, wp["head.weight"], raw_logits, bias=hb)
+        if C8 != C:
+            raw_logits = raw_logits[:, :C].contiguous()
         if self.variant == "v1":
             logits, _, rl = ops.sample_ln_fwd(raw_logits.view(B, T, C), torch.float32, 1e-5)
         else:
@@ -167,7 +191,7 @@ class Engine(object):
             ctx.wp, ctx.x0, ctx.moments, ctx.st1, ctx.code1 = wp, x0, moments, st1, code1
             ctx.blocks, ctx.l3_shape, ctx.idx2, ctx.mask = blocks, (Bx, Hx, Wx, Cx), idx2, mask
             ctx.tblocks, ctx.x_final, ctx.hf, ctx.mf, ctx.rf = tblocks, xs, hf, mf, rf
-            ctx.logits, ctx.rl = logits, rl
+            ctx.logits, ctx.rl, ctx.rng = logits, rl, rng
         return logits, ctx
 
     # ------------------------------------------------------------------------------------------
@@ -180,25 +204,42 @@ class Engine(object):
         dlogits = dlogits.contiguous().float()
         ldc = (C + 7) // 8 * 8
         if self.variant == "v1":
-            draw = ops.sample_ln_bwd(dlogits, ctx.logits, ctx.rl, C, ldc)          # bf16 [M, ldc]
+            draw = ops.sample_ln_bwd(dlogits, ctx.logits, ctx.rl, C, ldc)          # bf16 [M, ldc], pad columns zero
         else:
             draw = torch.zeros((M, ldc), dtype=torch.bfloat16, device=dev)
             draw[:, :C] = ops.cast_bf16(dlogits.view(M, C))
-        dr = draw[:, :C]
-        ops.linear_wgrad(dr, ctx.hf, grads["head.weight"])
-        ops.colsum_bf16(dr, grads["head.bias"])
+        if ldc == C:
+            ops.linear_wgrad(draw, ctx.hf, grads["head.weight"])
+            ops.colsum_bf16(draw, grads["head.bias"])
+        else:                            # class axis padded to a multiple of 8: gradients of the zero rows are dropped
+            gw = torch.zeros((ldc, D), dtype=torch.float32, device=dev)
+            gb = torch.zeros(ldc, dtype=torch.float32, device=dev)
+            ops.linear_wgrad(draw, ctx.hf, gw)
+            ops.colsum_bf16(draw, gb)
+            grads["head.weight"] += gw[:C]
+            grads["head.bias"] += gb[:C]
         dhf = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
-        ops.gemm_nn(dr, wp["head.weight"], dhf)
+        ops.gemm_nn(draw, wp["head.weight"], dhf)
         gx = torch.empty((M, D), dtype=torch.float32, device=dev)
         ops.row_ln_bwd(dhf, ctx.x_final, ctx.mf, ctx.rf, sd["norm.weight"], gx, False, grads["norm.weight"],
                        grads["norm.bias"])
         scale = self.hd ** -0.5
-        for (p, x1, h1, m1, r1s, qkv, o, lse, x2, h2, m2, r2s, a, u) in reversed(ctx.tblocks):
+        rng = ctx.rng
+        drop = rng["drop"] if rng else 0.0
+        attn_drop = rng["attn_drop"] if rng else 0.0
+        seed = rng["seed"] if rng else 0
+        for (i, p, x1, h1, m1, r1s, qkv, o, lse, x2, h2, m2, r2s, a, u) in reversed(ctx.tblocks):
+            dp1, dp2 = rng["drop_path"][i] if rng else (None, None)
+            hid = a.shape[1]
             gy = ops.cast_bf16(gx)
+            if rng:                      # same counter-based masks as the forward
+                ops.dropout_(gy, T * D, drop, seed, 8 * i + 3, dp2)
             ops.linear_wgrad(gy, a, grads[p + ".mlp.fc2.weight"])
             ops.colsum_bf16(gy, grads[p + ".mlp.fc2.bias"])
             da = torch.empty_like(a)
             ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], da)
+            if rng:
+                ops.dropout_(da, T * hid, drop, seed, 8 * i + 2)
             du = ops.gelu_bwd(da, u)
             ops.linear_wgrad(du, h2, grads[p + ".mlp.fc1.weight"])
             ops.colsum_bf16(du, grads[p + ".mlp.fc1.bias"])
@@ -207,13 +248,23 @@ class Engine(object):
             ops.row_ln_bwd(dh2, x2, m2, r2s, sd[p + ".norm2.weight"], gx, True, grads[p + ".norm2.weight"],
                            grads[p + ".norm2.bias"])
             gy = ops.cast_bf16(gx)
+            if rng:
+                ops.dropout_(gy, T * D, drop, seed, 8 * i + 1, dp1)
             ops.linear_wgrad(gy, o, grads[p + ".attn.proj.weight"])
             ops.colsum_bf16(gy, grads[p + ".attn.proj.bias"])
             do = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
             ops.gemm_nn(gy, wp[p + ".attn.proj.weight"], do)
             dqkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
-            ops.attention_bwd(qkv.view(B, T, 3, self.H, self.hd), o.view(B, T, D), do.view(B, T, D), lse,
-                              dqkv.view(B, T, 3, self.H, self.hd), scale)
+            if self.variant == "v1":
+                ops.attention_bwd(qkv.view(B, T, 3, self.H, self.hd), o.view(B, T, D), do.view(B, T, D), lse,
+                                  dqkv.view(B, T, 3, self.H, self.hd), scale)
+            else:
+                tname = p + ".attn.relative_position_bias_table"
+                tbl = sd[tname]
+                ws, sh = self.windows[i]
+                ops.attention2_bwd(qkv.view(B, T, 3, self.H, self.hd), o.view(B, T, D), do.view(B, T, D), lse,
+                                   dqkv.view(B, T, 3, self.H, self.hd), scale, tbl, (tbl.shape[0] + 1) // 2, ws, sh,
+                                   grads.get(tname), attn_drop, seed + 16 * i)
             ops.linear_wgrad(dqkv, h1, grads[p + ".attn.qkv.weight"])
             ops.colsum_bf16(dqkv, grads[p + ".attn.qkv.bias"])
             dh1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)

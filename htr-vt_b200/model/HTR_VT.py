@@ -89,7 +89,8 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, image, mask, names, save, *params):
         sd = module._tensor_table()
-        logits, ectx = module.engine.forward(sd, image, mask, module.training, save)
+        rng = module._train_rng(image.shape[0], image.device) if module.training else None
+        logits, ectx = module.engine.forward(sd, image, mask, module.training, save, rng)
         ctx.module, ctx.ectx, ctx.names, ctx.sd = module, ectx, names, sd
         ctx.shapes = [(p.shape, p.requires_grad) for p in params]
         return logits
@@ -149,6 +150,10 @@ class MaskedAutoencoderViT(nn.Module):
                     nn.init.zeros_(m.bias)
 
     # -- plumbing -------------------------------------------------------------------------------
+    def _train_rng(self, batch, device):
+        """Stochastic-regularisation state of one train-mode forward (None: model_v1 has no dropout / DropPath)."""
+        return None
+
     def _tensor_table(self):
         table = {k: v for k, v in self.named_parameters()}
         table.update({k: v for k, v in self.named_buffers()})

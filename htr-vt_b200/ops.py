@@ -334,6 +334,15 @@ def gelu_bwd(da, u):
     return du
 
 
+def dropout_(x, per_sample, p, seed, site, dp=None):
+    """In-place inverted dropout of probability p (+ per-sample DropPath scale dp [B] fp32) on a bf16 tensor."""
+    if p <= 0.0 and dp is None:
+        return x
+    check(lib().htrvt_dropout_bf16(_p(x), x.numel(), per_sample, float(p), int(seed), int(site), _p(dp), _stream()),
+          "htrvt_dropout_bf16")
+    return x
+
+
 def colsum_bf16(a, out, accumulate=True):
     M, N = a.shape
     rows = lib().htrvt_colsum_rows(M)
@@ -359,9 +368,10 @@ def pack_conv_weight(w, dst=None):
     return dst
 
 
-def pack_weights(items):
+def pack_weights(items, pad_rows=None, names=None):
     """items: list of (src fp32 tensor, kind) with kind 'cast' ([out,in]) or 'conv' (OIHW -> [Cout, taps, Cin]).
-    One launch for all of them.  Returns the list of bf16 tensors."""
+    One launch for all of them.  pad_rows: {name: rows} allocates that 'cast' output with extra zero rows.
+    Returns the list of bf16 tensors."""
     n = len(items)
     outs = []
     src = (ctypes.c_void_p * n)()
@@ -375,7 +385,11 @@ def pack_weights(items):
             o = torch.empty((Cout, kh * kw, Ci), dtype=torch.bfloat16, device=t.device)
             cin[i], taps[i] = Ci, kh * kw
         else:
-            o = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+            rows = pad_rows.get(names[i]) if (pad_rows and names) else None
+            if rows is not None and rows != t.shape[0]:
+                o = torch.zeros((rows, t.shape[1]), dtype=torch.bfloat16, device=t.device)
+            else:
+                o = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
             cin[i], taps[i] = 1, 0
         outs.append(o)
         src[i], dst[i], numel[i] = t.data_ptr(), o.data_ptr(), t.numel()
@@ -562,7 +576,7 @@ def _instrument():
     g = globals()
     names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "attention_fwd",
              "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd",
-             "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16",
+             "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16", "dropout_",
              "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",
              "conv1_wgrad", "stem_head_moments", "stem_head_fwd", "stem_head_bwd"]
     for name in names:

@@ -133,6 +133,11 @@ int htrvt_colsum_rows(int M);
 int htrvt_colsum_bf16(const void* a, long long ld, int M, int N, float* out, int accumulate, float* partial,
                       void* stream);
 int htrvt_cast_bf16(const float* src, void* dst, long long n, void* stream);
+/* in-place inverted dropout (+ per-sample DropPath scale dp[b], nullable) on bf16 x[n]; counter-based mask keyed by
+ * (seed, site, element index): the same call on the gradient regenerates the mask.  Replaces nn.Dropout / timm
+ * DropPath of model_window (model_window/model/HTR_VT.py:21-23, 100-110, 263-273) in train mode. */
+int htrvt_dropout_bf16(void* x, long long n, long long per_sample, float p, unsigned long long seed, unsigned site,
+                       const float* dp, void* stream);
 int htrvt_pack_weights(int n, const void* const* src, void* const* dst, const long long* numel, const int* cin,
                        const int* taps, void* stream);
 int htrvt_pack_conv_weight(const float* w_oihw, void* dst, int Cout, int Cin, int taps, void* stream);

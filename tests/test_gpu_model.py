@@ -139,3 +139,105 @@ def test_end_to_end_decode_strings():
     # bit-exact against the oracle decode of the SAME logits (kernel-level exactness)
     want = O.decode_strings(O.argmax_first(preds.cpu().numpy()).reshape(-1), [preds.size(1)] * 2, alphabet)
     assert got == want
+
+
+# ------------------------------------------------------------------------------------------------
+# windowed variant (model_window): relative-position bias, 16-token shifted windows, T up to 256
+# ------------------------------------------------------------------------------------------------
+def _build_window(nb_cls, W, D, depth, heads, seed):
+    import htrvt_b200  # noqa: F401
+    from functools import partial
+    Wm = import_module("htr-vt_b200.model_window.HTR_VT")
+    m = Wm.MaskedAutoencoderViT(nb_cls, img_size=[64, W], patch_size=(4, 64), embed_dim=D, depth=depth,
+                                num_heads=heads, mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    sd = O.init_state_dict(nb_cls, [64, W], seed=seed, embed_dim=D, depth=depth, num_heads=heads, variant="window")
+    m.load_state_dict(sd, strict=True)
+    return m.cuda(), sd
+
+
+def test_window_eval_logits_match_reference_golden():
+    g = np.load(os.path.join(G, "win_full.npz"), allow_pickle=True)
+    nb_cls, W, B, seed, D, depth, heads, _ = [int(v) for v in g["meta"]]
+    m, sd = _build_window(nb_cls, W, D, depth, heads, seed)
+    assert [str(k) for k in g["keys"]] == list(m.state_dict().keys())          # reference key order
+    m.eval()
+    x = _images(seed + 1, B, W)
+    with torch.no_grad():
+        got = m(x.cuda()).float().cpu().numpy()
+        want = O.forward(sd, x, training=False, num_heads=heads, variant="window").numpy()
+    np.testing.assert_allclose(want, g["logits_eval"], atol=3e-4)              # oracle == reference (pinned)
+    assert got.shape == g["logits_eval"].shape == (B, W // 4, nb_cls)
+    assert _relerr(got, g["logits_eval"]) < 2e-2, _relerr(got, g["logits_eval"])
+
+
+@pytest.mark.parametrize("cfg", [dict(nb_cls=20, W=512, D=256, depth=4, heads=2, B=3, seed=9),
+                                 dict(nb_cls=90, W=1024, D=768, depth=4, heads=6, B=2, seed=321)])
+def test_window_train_step_matches_oracle(cfg):
+    """Train-mode forward/backward with the stochastic regularisers switched off (the reference draws them from the
+    device generator: only eval / p = 0 can be compared value by value)."""
+    import htrvt_b200 as h
+    m, sd = _build_window(cfg["nb_cls"], cfg["W"], cfg["D"], cfg["depth"], cfg["heads"], cfg["seed"])
+    m.train().set_stochastic(0.0, 0.0, 0.0)
+    B, W = cfg["B"], cfg["W"]
+    x = _images(cfg["seed"] + 1, B, W)
+    tg, tl = _labels(cfg["seed"] + 2, B, cfg["nb_cls"], 4, 40)
+    torch.manual_seed(7)
+    preds = m(x.cuda(), 0.4, 8, use_masking=True)
+    loss = h.ctc_loss_from_logits(preds.float(), tg.cuda(), tl).mean()
+    loss.backward()
+    torch.manual_seed(7)
+    mask = O.draw_span_mask(W // 4, 0.4, 8)
+    sd_ref = {k: v.clone() for k, v in sd.items()}
+    ref_loss, ref_grads, ref_logits = O.train_step(sd_ref, x, tg, tl, mask, variant="window", num_heads=cfg["heads"])
+    sd_gpu = {k: v.clone().cuda() for k, v in sd.items()}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ac = O.forward(sd_gpu, x.cuda(), mask=mask.cuda(), training=True, num_heads=cfg["heads"],
+                       variant="window").float().cpu()
+    lib_err = _relerr(ac.numpy(), ref_logits.numpy())
+    err = _relerr(preds.detach().cpu().numpy(), ref_logits.numpy())
+    assert err < max(2e-2, 1.25 * lib_err) and err < 6e-2, (err, lib_err)
+    assert abs(loss.item() - ref_loss) < 2e-2 * abs(ref_loss)
+    bad = []
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        a = p.grad.detach().float().cpu().double().reshape(-1)
+        b = ref_grads[name].double().reshape(-1)
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+        ratio = float(a.norm() / (b.norm() + 1e-30))
+        if not (cos > 0.85 and 0.85 < ratio < 1.15):
+            bad.append((name, round(cos, 4), round(ratio, 4)))
+    assert not bad, bad
+
+
+def test_window_train_mode_is_stochastic_and_seeded():
+    import htrvt_b200 as h
+    m, sd = _build_window(90, 512, 768, 4, 6, 11)
+    m.train()
+    x = _images(12, 4, 512).cuda()
+    tg, tl = _labels(13, 4, 90, 4, 30)
+
+    def run(seed):
+        torch.manual_seed(seed)
+        for p in m.parameters():
+            p.grad = None
+        preds = m(x, 0.4, 8, use_masking=True)
+        loss = h.ctc_loss_from_logits(preds.float(), tg.cuda(), tl).mean()
+        loss.backward()
+        return preds.detach().clone(), m.head.weight.grad.detach().clone()
+
+    a, ga = run(3)
+    b, gb = run(3)
+    c, _ = run(4)
+    assert torch.equal(a, b) and torch.equal(ga, gb)            # same seed: same masks in forward and backward
+    assert not torch.equal(a, c)
+    assert torch.isfinite(a).all() and torch.isfinite(ga).all()
+    m.eval()
+    with torch.no_grad():
+        e1, e2 = m(x), m(x)
+    assert torch.equal(e1, e2)
+    # inverted dropout keeps the expectation: with the regularisers off the SAME train-mode graph (same span mask,
+    # batch statistics) gives logits the dropout run scatters around
+    m.train().set_stochastic(0.0, 0.0, 0.0)
+    d, _ = run(3)
+    assert float((a.float() - d.float()).abs().mean()) < 0.6 * float(d.float().abs().mean())
+    assert float((a.float() - d.float()).abs().mean()) > 1e-3
