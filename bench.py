@@ -129,6 +129,100 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def extra_metrics(torch, dev, h, ops, H, model, peaks):
+    """The other BASELINE.json metrics / configs, measured on the same box right after the headline run (1 GPU):
+    CTC loss+grad us/batch with its HBM roofline fraction, inference (eval forward + greedy decode) img/s at the
+    per-GPU share of config 4 (512 lines), and the windowed wide-line variant's training step (config 5)."""
+    from importlib import import_module
+    out = {}
+    hbm = float(peaks.get("hbm_gbs", 6500.0))
+
+    def timed_ms(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    # ---- CTC loss + gradient, B=128, T=128, C=80, fused log-softmax (one launch); 16 rotating buffers (168 MB of
+    # logits + gradients > 126 MB L2) so no iteration finds its data in L2
+    B, T, C = 128, 128, NB_CLS
+    g = torch.Generator(device="cpu").manual_seed(0)
+    bufs = [torch.randn(B, T, C, generator=g).to(dev) for _ in range(16)]
+    _, tg, tl = synth_batch(B, 0)
+    tg, tl_d = tg.to(dev), tl.to(dev)
+    mtl = int(tl.max())
+    state = {"i": 0}
+
+    def ctc_once():
+        x = bufs[state["i"] % len(bufs)]
+        state["i"] += 1
+        ops.ctc_loss_grad(x, tg, None, tl_d, layout="btc", is_logprob=False, want_grad=True, max_target_len=mtl,
+                          grad_scale_const=1.0 / B)
+
+    ms = timed_ms(ctc_once, 64)
+    bytes_ctc = 2.0 * B * T * C * 4 + float(tg.numel()) * 4 + 12.0 * B
+    out["ctc_loss_grad"] = {"us_per_batch": ms * 1e3, "batch": B, "T": T, "C": C, "algorithmic_bytes": bytes_ctc,
+                            "achieved_gbs": bytes_ctc / (ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm,
+                            "frac_of_hbm_roofline": bytes_ctc / (ms * 1e-3) / 1e9 / hbm,
+                            "note": "T sequential alpha/beta steps bound this kernel by latency, not bytes"}
+    del bufs
+
+    # ---- inference: eval forward + greedy decode (argmax + collapse on device, one D2H copy), 512 lines per GPU
+    Bi = 512
+    conv = h.CTCLabelConverter("".join(chr(33 + i) for i in range(NB_CLS - 1)))
+    img = synth_batch(Bi, 1)[0].to(dev)
+    model.eval()
+
+    def infer_once():
+        with torch.no_grad():
+            preds = model(img)
+            return conv.decode_logits(preds.float())
+
+    ms = timed_ms(infer_once, 5, warm=2)
+    out["inference"] = {"img_per_s": Bi / (ms * 1e-3), "ms_per_batch": ms, "batch_per_gpu": Bi,
+                        "what": "eval-mode forward + greedy CTC decode to Python strings (BASELINE config 4 share)"}
+    model.train()
+    del img
+
+    # ---- windowed variant (model_window), 64x1024 lines, T = 256, 90 classes, labels up to 200: training step with
+    # the reference's train-mode regularisers on (dropout 0.1 / attention dropout 0.05 / DropPath <= 0.1)
+    try:
+        Wm = import_module("htr-vt_b200.model_window.HTR_VT")
+        import numpy as np
+        Bw, Ww, Cw = 128, 1024, 90
+        torch.manual_seed(123)
+        wm = Wm.create_model(Cw, [IMG_H, Ww]).to(dev).train()
+        rs = np.random.RandomState(5)
+        imgw = torch.from_numpy(rs.rand(Bw, 1, IMG_H, Ww).astype("float32")).to(dev)
+        lens = rs.randint(64, 201, size=Bw).astype("int32")
+        tgw = torch.from_numpy(rs.randint(1, Cw, size=int(lens.sum())).astype("int32")).to(dev)
+        tlw = torch.from_numpy(lens)
+        wparams = [p for p in wm.parameters() if p.requires_grad]
+
+        def win_step():
+            for p in wparams:
+                p.grad = None
+            preds = wm(imgw, MASK_RATIO, MAX_SPAN, use_masking=True)
+            loss = h.ctc_loss_from_logits(preds.float(), tgw, tlw).mean()
+            loss.backward()
+
+        ms = timed_ms(win_step, 3, warm=2)
+        out["window_train_step"] = {"img_per_s": Bw / (ms * 1e-3), "ms_per_step": ms, "batch_per_gpu": Bw,
+                                    "img": [1, IMG_H, Ww], "nb_cls": Cw, "T": Ww // 4,
+                                    "what": "model_window fwd+bwd+CTC (BASELINE config 5)"}
+        del wm, imgw
+    except Exception as e:                                   # never lose the headline line to an extra
+        out["window_train_step"] = {"error": repr(e)[:200]}
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -268,6 +362,8 @@ def run_ours(args):
                      "peak_source": peak_src},
         "breakdown_ms": {k: round(v[0], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])},
     }
+    if world == 1 and not args.no_extras:
+        line["extra"] = extra_metrics(torch, dev, h, ops, H, model, peaks)
     if world == 1 and not args.no_cpu_baseline:
         rate, per, threads = cpu_reference_rate(2, 1, B=8)
         line["cpu_baseline"] = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
@@ -285,6 +381,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="images per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the CTC / inference / window-variant side metrics")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

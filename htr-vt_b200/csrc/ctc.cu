@@ -11,7 +11,7 @@
 namespace htrvt {
 
 constexpr float kNeg = -1.0e30f;       // finite stand-in for log(0): keeps ex2(a-a) well defined
-constexpr int kCtcThreads = 256;
+constexpr int kCtcThreads = 512;
 
 __device__ __forceinline__ float lse3_log2(float a, float b, float c) {
   const float m = fmaxf(a, fmaxf(b, c));
