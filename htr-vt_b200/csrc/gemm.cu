@@ -20,16 +20,20 @@ constexpr int kGemmThreads = 320;
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 
-template <int BN>
+// CL = 1: one CTA per 128 x BN tile.  CL = 2: a CTA PAIR (cta_group::2) per 256 x BN tile - each CTA stages its own
+// 128 A rows and only HALF of B, so the bytes entering each SM per flop drop by ~1/3 (these GEMMs are bound by the
+// ~68 B/clk L2 -> SM ingress: tensor-pipe utilisation tracks 68 / ((128 + BN) * 128 / (2 BN)) for every shape).
+template <int BN, int CL>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kBBytes = (BN / CL) * kBK * 2;                 // B bytes staged by THIS CTA
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN <= 128) ? 6 : 4;
+  static constexpr int kStages = (CL == 2) ? 6 : ((BN <= 128) ? 6 : 4);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kStagingBytes = 8 * 2 * 2048;   // per epilogue warp: two [32 rows][64 B] output boxes
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(kStageBytes % 1024 == 0, "SWIZZLE_128B stage alignment");
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -78,7 +82,7 @@ template <int BN, int KIND, bool B_MN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmP P) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   constexpr bool A_MN = (KIND == 1);
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment
@@ -94,9 +98,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = P.tiles_m * P.tiles_n * (P.kind == 0 ? 1 : P.n_taps * P.splits);
-  // CL == 2: a cluster of two CTAs works on tiles (2p, 2p+1) = neighbouring m-tiles of the same B tile (the host
-  // guarantees tiles_m is even); each CTA loads half of B and multicasts it into both CTAs' smem, which cuts the
-  // L2 -> SM fill traffic per flop by ~1/3 (these GEMMs are fill bound at 128 x BN x 64 stages).
+  // CL == 2: the CTA pair works on tiles (2p, 2p+1) = neighbouring m-tiles of the same n-tile (the host guarantees
+  // tiles_m is even).  Each CTA runs its own producer and epilogue; only the leader (rank 0) issues the MMAs.
   const int crank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const int first_tile = (CL == 2) ? (static_cast<int>(blockIdx.x >> 1) * 2 + crank) : static_cast<int>(blockIdx.x);
   const int tile_step = (CL == 2) ? static_cast<int>(gridDim.x & ~1u) : static_cast<int>(gridDim.x);
@@ -105,11 +108,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8 * CL); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) { if (CL == 2) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols); }
   tc_fence_before();
   __syncthreads();
   if (CL == 2) cluster_sync_all();           // the peer's barriers must be initialised before anything lands on them
@@ -128,27 +131,24 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          // CL == 2: every load of the pair reports to the LEADER's full barrier, which expects both CTAs' bytes
+          if (CL == 1) mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          else if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+          auto load = [&](uint8_t* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+            if (CL == 2) tma_load_5d_pair(dst, map, &full[stage], c0, c1, c2, c3, c4);
+            else tma_load_5d(dst, map, &full[stage], c0, c1, c2, c3, c4);
+          };
+          constexpr int BNL = BN / CL;                    // B columns staged by this CTA
+          const int nb0 = n0 + crank * BNL;
           if (KIND == 0) {
             const int tap = k / P.k_chunks, cc = k - tap * P.k_chunks;
-            tma_load_5d(sa, &tmA, &full[stage], cc * kBK, P.tap.pw[tap], tc.w0 + P.tap.dw[tap],
-                        tc.h * P.a_sh + P.tap.dh[tap], tc.n);
+            load(sa, &tmA, cc * kBK, P.tap.pw[tap], tc.w0 + P.tap.dw[tap], tc.h * P.a_sh + P.tap.dh[tap], tc.n);
             if (!B_MN) {
-              if (CL == 2)          // my half of the B rows, into both CTAs
-                tma_load_5d_mc(sb + crank * (BN / 2) * 128, &tmB, &full[stage],
-                               P.tap.widx[tap] * P.b_tap_stride + cc * kBK, n0 + crank * (BN / 2), 0, 0, 0, 3);
-              else
-                tma_load_5d(sb, &tmB, &full[stage], P.tap.widx[tap] * P.b_tap_stride + cc * kBK, n0, 0, 0, 0);
+              load(sb, &tmB, P.tap.widx[tap] * P.b_tap_stride + cc * kBK, nb0, 0, 0, 0);
             } else {
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i) {
-                if (CL == 2)        // my 32 of the 64 K rows of every 64-column atom, into both CTAs
-                  tma_load_5d_mc(sb + i * 8192 + crank * 4096, &tmB, &full[stage],
-                                 P.tap.widx[tap] * P.b_tap_stride + n0 + 64 * i, cc * kBK + 32 * crank, 0, 0, 0, 3);
-                else
-                  tma_load_5d(sb + i * 8192, &tmB, &full[stage], P.tap.widx[tap] * P.b_tap_stride + n0 + 64 * i,
-                              cc * kBK, 0, 0, 0);
-              }
+              for (int i = 0; i < BNL / 64; ++i)
+                load(sb + i * 8192, &tmB, P.tap.widx[tap] * P.b_tap_stride + nb0 + 64 * i, cc * kBK, 0, 0, 0);
             }
           } else {
             const int q = tc.q_begin + k;
@@ -156,20 +156,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int n = row / P.Ho, ho = row - n * P.Ho;
             if (KIND == 1) {
 #pragma unroll
-              for (int i = 0; i < kBM / 64; ++i)
-                tma_load_5d(sa + i * 8192, &tmA, &full[stage], m0 + 64 * i, 0, w0c, ho, n);
+              for (int i = 0; i < kBM / 64; ++i) load(sa + i * 8192, &tmA, m0 + 64 * i, 0, w0c, ho, n);
             } else {            // KIND 2: dY^T [n][ho][C][Wo] - pixels contiguous, a plain K-major tile
-              tma_load_5d(sa, &tmA, &full[stage], w0c, m0, ho, n, 0);
+              load(sa, &tmA, w0c, m0, ho, n, 0);
             }
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) {
-              if (CL == 2)
-                tma_load_5d_mc(sb + i * 8192 + crank * 4096, &tmB, &full[stage], n0 + 64 * i, P.tap.pw[tc.tap],
-                               w0c + P.tap.dw[tc.tap] + 32 * crank, ho * P.a_sh + P.tap.dh[tc.tap], n, 3);
-              else
-                tma_load_5d(sb + i * 8192, &tmB, &full[stage], n0 + 64 * i, P.tap.pw[tc.tap],
-                            w0c + P.tap.dw[tc.tap], ho * P.a_sh + P.tap.dh[tc.tap], n);
-            }
+            for (int i = 0; i < BNL / 64; ++i)
+              load(sb + i * 8192, &tmB, nb0 + 64 * i, P.tap.pw[tc.tap], w0c + P.tap.dw[tc.tap],
+                   ho * P.a_sh + P.tap.dh[tc.tap], n);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -177,8 +171,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM * CL, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int id = first_tile; id < total_tiles; id += tile_step) {
@@ -198,12 +192,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                      : umma_desc_sw128(sa + kk * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc_sw128(sb + kk * 2048, 8192, 1024)
                                      : umma_desc_sw128(sb + kk * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+            if (CL == 2) umma_bf16_pair(d_tmem, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
           }
-          if (CL == 2) umma_commit_mc(&empty[stage], 3); else umma_commit(&empty[stage]);
+          if (CL == 2) umma_commit_pair(&empty[stage], 3); else umma_commit(&empty[stage]);   // frees the slot in both CTAs
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[as]);
+        if (CL == 2) umma_commit_pair(&tfull[as], 3); else umma_commit(&tfull[as]);           // wakes both epilogues
         if (kiters == 0) { /* unreachable: host never creates empty tiles */ }
         as ^= 1; if (as == 0) aphase ^= 1;
       }
@@ -262,7 +257,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (b == nboxes - 1) {                               // accumulator fully read: hand TMEM back early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[as]);
+          if (lane == 0) { if (CL == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]); }
         }
         if (P.flags & EPI_NOSTORE) continue;                 // measurement aid: main loop only
         if ((P.flags & EPI_STATS) && KIND == 0 && tc.w0 + r >= P.Wo) {
@@ -319,7 +314,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (col < P.N_valid) {
             int c1, c2, c3, c4;
             if (KIND == 0) { c1 = tc.w0 + quad * 32; c2 = tc.h; c3 = tc.n; c4 = 0; }
-            else { c1 = tc.m_tile * kBM + quad * 32; c2 = tc.tap; c3 = tc.split; c4 = 0; }
+            else { c1 = tc.m_tile * kBM + quad * 32; c2 = tc.tap; c3 = (P.flags & EPI_ACCUM) ? 0 : tc.split; c4 = 0; }
             if (P.flags & EPI_ACCUM)
               asm volatile(
                   "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
@@ -358,8 +353,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();           // no CTA may exit while its peer can still write its smem / barriers
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (CL == 2) cluster_sync_all();           // no CTA may exit while its peer can still reach its smem / TMEM / barriers
+  if (warp == 1) { if (CL == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols); }
 }
 
 }  // namespace htrvt
@@ -459,7 +454,7 @@ int num_sms() {
 template <int BN, int KIND, bool B_MN, int CL>
 int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
                cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   static bool configured = false;
   auto kern = tapgemm_kernel<BN, KIND, B_MN, CL>;
   if (!configured) {
@@ -512,14 +507,13 @@ int dbg_env(const char* name) {
   return v ? atoi(v) : 0;
 }
 
-// 2-CTA clusters with a multicast B operand need tile pairs (2p, 2p+1) that share their B tile: tiles_m even.
-// Measured on B200 (tools/profile_gemm.py): multicast does NOT speed these GEMMs up - they are bound by the
-// per-SM L2 -> SM ingress (~68 B/clk: tensor-pipe utilisation tracks 68 / ((128 + BN) * 128 / (2 BN)) for every tile
-// shape), and a multicast box still enters both SMs in full.  Kept (opt-in, HTRVT_CLUSTER=1) as the stepping stone
-// to cta_group::2 pairs, where each SM only receives HALF of B.
-int pick_cluster(int tiles_m, int total_tiles) {
-  static const int on = dbg_env("HTRVT_CLUSTER");
-  return (on && (tiles_m % 2) == 0 && total_tiles >= 4) ? 2 : 1;
+// CTA pairs (cta_group::2) need tile pairs (2p, 2p+1) on the same n-tile: tiles_m even; an MN-major B operand is
+// split by 64-column swizzle atoms, so each CTA's half (BN / 2) must be a multiple of 64.
+int pick_cluster(int tiles_m, int total_tiles, int bn, bool b_mn) {
+  static const int off = dbg_env("HTRVT_NOPAIR");
+  if (off || (tiles_m % 2) != 0 || total_tiles < 4) return 1;
+  if (b_mn && ((bn / 2) % 64) != 0) return 1;
+  return 2;
 }
 
 int pick_bn(int N) {
@@ -575,7 +569,7 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
   const int bn = pick_bn(N);
   const int esz = (flags & EPI_BF16) ? 2 : 4;
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + bn - 1) / bn;
-  const int cl = pick_cluster(tiles_m, tiles_m * tiles_n);
+  const int cl = pick_cluster(tiles_m, tiles_m * tiles_n, bn, false);
   CUtensorMap ta, tb, tc;
   {
     const long long dims[5] = {K, 1, M, 1, 1};
@@ -604,7 +598,7 @@ extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long
   const int bn = pick_bn(N);
   const int esz = (flags & EPI_BF16) ? 2 : 4;
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + bn - 1) / bn;
-  const int cl = pick_cluster(tiles_m, tiles_m * tiles_n);
+  const int cl = pick_cluster(tiles_m, tiles_m * tiles_n, bn, true);
   CUtensorMap ta, tb, tc;
   {
     const long long dims[5] = {K, 1, M, 1, 1};
@@ -612,7 +606,7 @@ extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long
     const int box[5] = {kBK, 1, kBM, 1, 1};
     int r = make_map5(&ta, dY, dims, st, box);
     if (r) return r;
-    r = make_map_matrix(&tb, W, K, N, ldw, 64, 64 / cl);
+    r = make_map_matrix(&tb, W, K, N, ldw, 64, 64);
     if (r) return r;
     r = make_map_out(&tc, out, esz, N, M, 1, 1, ldo, ldo * M, ldo * M);
     if (r) return r;
@@ -668,7 +662,7 @@ extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X,
                                   cudaStream_t stream) {
   if (M <= 0 || Nout <= 0 || Kin <= 0 || (Kin & 7) || (Nout & 7)) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(Kin);
-  const int cl = pick_cluster((Nout + kBM - 1) / kBM, 4);
+  const int cl = pick_cluster((Nout + kBM - 1) / kBM, 4, bn, true);
   CUtensorMap ta, tb, tc;
   int r;
   {
@@ -679,7 +673,7 @@ extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X,
     if (r) return r;
     const long long dimsB[5] = {Kin, 1, M, 1, 1};
     const long long stB[4] = {ldx, ldx, ldx * M, ldx * M};
-    const int boxB[5] = {64, 1, 64 / cl, 1, 1};
+    const int boxB[5] = {64, 1, 64, 1, 1};
     r = make_map5(&tb, X, dimsB, stB, boxB);
     if (r) return r;
   }
@@ -688,19 +682,15 @@ extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X,
   P.tiles_m = (Nout + kBM - 1) / kBM; P.tiles_n = (Kin + bn - 1) / bn; P.n_taps = 1;
   P.k_chunks = (M + 63) / 64; P.a_sh = 1;
   P.splits = choose_splits(P.tiles_m * P.tiles_n, P.k_chunks, static_cast<long long>(Nout) * Kin);
-  P.M_valid = Nout; P.N_valid = Kin; P.flags = 0; P.alpha = 1.f;
-  const size_t need = static_cast<size_t>(P.splits) * Nout * Kin * sizeof(float);
-  if (!workspace || workspace_bytes < need) return HTRVT_ERR_WORKSPACE;
-  r = make_map_wgrad_out(&tc, workspace, Nout, 1, Kin, P.splits);
+  // every split-K slice reduce-adds (TMA cp.reduce.async.bulk, fp32) straight into the gradient: no partial-sum
+  // buffers, no reduce kernel; the summation order across slices is not fixed (like cuBLAS / cuDNN split-K)
+  P.M_valid = Nout; P.N_valid = Kin; P.flags = EPI_ACCUM; P.alpha = 1.f;
+  (void)workspace; (void)workspace_bytes;
+  if (!accumulate && cudaMemsetAsync(grad, 0, static_cast<size_t>(Nout) * Kin * sizeof(float), stream) != cudaSuccess)
+    return HTRVT_ERR_LAUNCH;
+  r = make_map_wgrad_out(&tc, grad, Nout, 1, Kin, 1);
   if (r) return r;
-  r = launch_bn<1, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.splits, stream);
-  if (r) return r;
-  const long long total = static_cast<long long>(Nout) * Kin;
-  const int blocks = static_cast<int>((total + 255) / 256 < 2048 ? (total + 255) / 256 : 2048);
-  wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), P.splits, Nout, 1, Kin, grad,
-                                                  accumulate, 0);
-  HTRVT_LAUNCH_CHECK();
-  return HTRVT_OK;
+  return launch_bn<1, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.splits, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -718,7 +708,7 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
   const int bn = pick_bn(Cout);
   const int tiles_m_all = ((Wo + kBM - 1) / kBM) * Ho * NB;
-  const int cl = pick_cluster(tiles_m_all, tiles_m_all * ((Cout + bn - 1) / bn));
+  const int cl = pick_cluster(tiles_m_all, tiles_m_all * ((Cout + bn - 1) / bn), bn, false);
   CUtensorMap ta, tb, tc;
   int r = make_map_act(&ta, x, NB, H, W, Cin, sw, kBK, kBM);
   if (r) return r;
@@ -770,9 +760,9 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
       P.n_taps = n; P.splits = 1; P.k_chunks = (Cout + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = Cin;
       P.N_valid = Cin; P.flags = EPI_BF16 | (accumulate ? EPI_ACCUM : 0);
       P.alpha = 1.f;
-      const int cl = pick_cluster(P.tiles_m, P.tiles_m * P.tiles_n);
+      const int cl = pick_cluster(P.tiles_m, P.tiles_m * P.tiles_n, bn, true);
       r = make_map_matrix(&tb, w, Cout, static_cast<long long>(ks) * ks * Cin, static_cast<long long>(ks) * ks * Cin, 64,
-                          64 / cl);
+                          64);
       if (r) return r;
       CUtensorMap tc;                                     // parity class (ph, pw) of dx as a strided tensor
       r = make_map_out(&tc, static_cast<__nv_bfloat16*>(dx) + (static_cast<long long>(ph) * W + pw) * Cin, 2, Cin, Wq,
@@ -785,11 +775,15 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
   return HTRVT_OK;
 }
 
-// dw (+)= sum_pixels dy^T x_shifted; grad is fp32 OIHW (the nn.Conv2d parameter layout).
+// dw (+)= sum_pixels dy^T x_shifted.  Two output modes:
+//   grad_oihw    : fp32 OIHW (the nn.Conv2d parameter layout) through split-K partials in `workspace` and a
+//                  deterministic reduce / permute kernel;
+//   grad_tapmajor: fp32 [Cout][taps][Cin], every split-K slice reduce-adds (TMA) into it - no partials, no reduce
+//                  kernel; htrvt_unpack_conv_grads permutes all tap-major gradients of a step into OIHW at once.
 // dy_t (optional): the same gradient stored [NB][Ho][Cout][Wo] (htrvt_transpose_px) - selects the K-major-A kernel.
-extern "C" int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin,
-                                int Cout, int ks, int sh, int sw, float* grad_oihw, int accumulate, void* workspace,
-                                size_t workspace_bytes, cudaStream_t stream) {
+static int conv_wgrad_impl(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin, int Cout,
+                           int ks, int sh, int sw, float* grad_oihw, int accumulate, float* grad_tapmajor,
+                           void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int pad = ks / 2;
   if ((Cout % 8) || (Cin % 8) || (W % sw) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
@@ -808,8 +802,8 @@ extern "C" int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x,
     r = make_map_act(&ta, dy, NB, Ho, Wo, Cout, 1, 64, 64);
   }
   if (r) return r;
-  const int cl = pick_cluster((Cout + kBM - 1) / kBM, 4);
-  r = make_map_act(&tb, x, NB, H, W, Cin, sw, 64, 64 / cl);
+  const int cl = pick_cluster((Cout + kBM - 1) / kBM, 4, bn, true);
+  r = make_map_act(&tb, x, NB, H, W, Cin, sw, 64, 64);
   if (r) return r;
   GemmP P = {};
   P.kind = 1; P.Wo = Wo; P.Ho = Ho; P.NB = NB; P.tiles_per_row = 1;
@@ -818,17 +812,84 @@ extern "C" int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x,
   P.k_chunks = (Wo + 63) / 64; P.a_sh = sh;
   const long long Q = static_cast<long long>(NB) * Ho * P.k_chunks;
   const long long per = static_cast<long long>(Cout) * P.n_taps * Cin;
-  P.splits = choose_splits(P.tiles_m * P.tiles_n * P.n_taps, Q, per);
-  P.M_valid = Cout; P.N_valid = Cin; P.flags = dbg_env("HTRVT_DBG_WGRAD_NOSTORE") ? EPI_NOSTORE : 0; P.alpha = 1.f;
-  if (!workspace || workspace_bytes < static_cast<size_t>(P.splits) * per * sizeof(float)) return HTRVT_ERR_WORKSPACE;
-  r = make_map_wgrad_out(&tc, workspace, Cout, P.n_taps, Cin, P.splits);
+  P.splits = choose_splits(P.tiles_m * P.tiles_n * P.n_taps, Q, grad_tapmajor ? per / 2 : per);
+  P.M_valid = Cout; P.N_valid = Cin; P.alpha = 1.f;
+  P.flags = (grad_tapmajor ? EPI_ACCUM : 0) | (dbg_env("HTRVT_DBG_WGRAD_NOSTORE") ? EPI_NOSTORE : 0);
+  if (grad_tapmajor) {
+    r = make_map_wgrad_out(&tc, grad_tapmajor, Cout, P.n_taps, Cin, 1);
+  } else {
+    if (!workspace || workspace_bytes < static_cast<size_t>(P.splits) * per * sizeof(float)) return HTRVT_ERR_WORKSPACE;
+    r = make_map_wgrad_out(&tc, workspace, Cout, P.n_taps, Cin, P.splits);
+  }
   if (r) return r;
   r = a_kmajor ? launch_bn<2, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream)
                : launch_bn<1, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.n_taps * P.splits, stream);
-  if (r) return r;
+  if (r || grad_tapmajor) return r;
   const int blocks = static_cast<int>((per + 255) / 256 < 2048 ? (per + 255) / 256 : 2048);
   wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), P.splits, Cout, P.n_taps, Cin,
                                                   grad_oihw, accumulate, 1);
   HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin,
+                                int Cout, int ks, int sh, int sw, float* grad_oihw, int accumulate, void* workspace,
+                                size_t workspace_bytes, cudaStream_t stream) {
+  if (!grad_oihw) return HTRVT_ERR_SHAPE;
+  return conv_wgrad_impl(dy, dy_t, x, NB, H, W, Cin, Cout, ks, sh, sw, grad_oihw, accumulate, nullptr, workspace,
+                         workspace_bytes, stream);
+}
+
+extern "C" int htrvt_conv_wgrad_acc(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin,
+                                    int Cout, int ks, int sh, int sw, float* grad_tapmajor, cudaStream_t stream) {
+  if (!grad_tapmajor) return HTRVT_ERR_SHAPE;
+  return conv_wgrad_impl(dy, dy_t, x, NB, H, W, Cin, Cout, ks, sh, sw, nullptr, 1, grad_tapmajor, nullptr, 0, stream);
+}
+
+// dst_oihw[i] += permute(src_tapmajor[i]) for n <= 64 conv weights per launch: [Cout][taps][Cin] -> [Cout][Cin][taps]
+namespace htrvt {
+constexpr int kMaxUnpack = 64;
+struct UnpackTable {
+  const float* src[kMaxUnpack];
+  float* dst[kMaxUnpack];
+  long long numel[kMaxUnpack];
+  int cin[kMaxUnpack];
+  int taps[kMaxUnpack];
+};
+__global__ void unpack_conv_grads_kernel(const __grid_constant__ UnpackTable T) {
+  const int t = blockIdx.y;
+  const float* __restrict__ src = T.src[t];
+  float* __restrict__ dst = T.dst[t];
+  const long long n = T.numel[t];
+  const int Cin = T.cin[t], taps = T.taps[t];
+  // thread i owns OIHW element i (coalesced read-modify-write of the gradient; the tap-major source is L2 resident)
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int tap = static_cast<int>(i % taps);
+    const long long r = i / taps;
+    const int ci = static_cast<int>(r % Cin);
+    const long long co = r / Cin;
+    dst[i] += src[(co * taps + tap) * Cin + ci];
+  }
+}
+}  // namespace htrvt
+
+extern "C" int htrvt_unpack_conv_grads(int n, const void* const* src, void* const* dst, const long long* numel,
+                                       const int* cin, const int* taps, cudaStream_t stream) {
+  for (int base = 0; base < n; base += kMaxUnpack) {
+    UnpackTable T = {};
+    const int cnt = n - base < kMaxUnpack ? n - base : kMaxUnpack;
+    for (int i = 0; i < cnt; ++i) {
+      T.src[i] = static_cast<const float*>(src[base + i]);
+      T.dst[i] = static_cast<float*>(dst[base + i]);
+      T.numel[i] = numel[base + i];
+      T.cin[i] = cin[base + i];
+      T.taps[i] = taps[base + i];
+      if (T.cin[i] <= 0 || T.taps[i] <= 0) return HTRVT_ERR_SHAPE;
+    }
+    dim3 grid(148, cnt);
+    unpack_conv_grads_kernel<<<grid, 256, 0, stream>>>(T);
+    HTRVT_LAUNCH_CHECK();
+  }
   return HTRVT_OK;
 }

@@ -35,10 +35,12 @@ class GradAllReduce(object):
 
 
 def segment_bounds(names, numels, first_transformer_prefix="blocks."):
-    """Offsets of the [stem | transformer] split of the flat gradient buffer."""
+    """Offsets of the [stem | transformer] split of the flat gradient buffer.  Every tensor starts on a 256-byte
+    boundary (64 floats): weight-gradient GEMMs reduce-add into these views through TMA tensor maps, which need
+    16-byte aligned bases.  Tensor i occupies [offs[i], offs[i] + numels[i]); the padding stays zero."""
     offs = [0]
     for n in numels:
-        offs.append(offs[-1] + n)
+        offs.append(offs[-1] + (n + 63) // 64 * 64)
     split = len(names)
     for i, n in enumerate(names):
         if n.startswith(first_transformer_prefix):

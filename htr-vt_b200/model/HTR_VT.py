@@ -103,7 +103,8 @@ class _EncoderFn(torch.autograd.Function):
         numels = [int(torch.Size(shape).numel()) for shape, _ in ctx.shapes]
         offs, split = segment_bounds(ctx.names, numels)
         flat = torch.zeros(offs[-1], dtype=torch.float32, device=dlogits.device)
-        grads = {n: flat[offs[i]:offs[i + 1]].view(shape) for i, (n, (shape, _)) in enumerate(zip(ctx.names, ctx.shapes))}
+        grads = {n: flat[offs[i]:offs[i] + numels[i]].view(shape)
+                 for i, (n, (shape, _)) in enumerate(zip(ctx.names, ctx.shapes))}
         sync = module.grad_sync
 
         def on_stage(stage):

@@ -76,6 +76,32 @@ def linear_wgrad(dy, x, grad, *, accumulate=True):
     return grad
 
 
+def conv_wgrad_acc(dy, x, ks, sh, sw, grad_tapmajor):
+    """grad_tapmajor fp32 [Cout, ks*ks, Cin] += dy^T x_shifted (split-K slices reduce-add in place, no reduce kernel)."""
+    _need_cuda(dy, x, grad_tapmajor)
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    check(lib().htrvt_conv_wgrad_acc(_p(dy), _p(None), _p(x), N, H, W, Cin, Cout, ks, sh, sw, _p(grad_tapmajor),
+                                     _stream()), "htrvt_conv_wgrad_acc")
+    return grad_tapmajor
+
+
+def unpack_conv_grads(pairs):
+    """pairs: list of (src fp32 [Cout, taps, Cin], dst fp32 OIHW): dst += permute(src), one launch for all."""
+    n = len(pairs)
+    if n == 0:
+        return
+    src = (ctypes.c_void_p * n)()
+    dst = (ctypes.c_void_p * n)()
+    numel = (ctypes.c_longlong * n)()
+    cin = (ctypes.c_int * n)()
+    taps = (ctypes.c_int * n)()
+    for i, (a, b) in enumerate(pairs):
+        src[i], dst[i], numel[i] = a.data_ptr(), b.data_ptr(), b.numel()
+        cin[i], taps[i] = a.shape[2], a.shape[1]
+    check(lib().htrvt_unpack_conv_grads(n, src, dst, numel, cin, taps, _stream()), "htrvt_unpack_conv_grads")
+
+
 def conv_out_hw(H, W, ks, sh, sw):
     pad = ks // 2
     return (H + 2 * pad - ks) // sh + 1, (W + 2 * pad - ks) // sw + 1
@@ -551,6 +577,9 @@ def _flops(name, a, kw):
         if name == "conv_dgrad":
             dy, w, xs, ks = a[:4]
             return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * xs[3]
+        if name == "conv_wgrad_acc":
+            dy, x, ks = a[:3]
+            return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * x.shape[3]
         if name == "conv_wgrad":
             dy, x, ks = a[:3]
             return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * x.shape[3]
@@ -574,7 +603,7 @@ def _flops(name, a, kw):
 def _instrument():
     import functools
     g = globals()
-    names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "attention_fwd",
+    names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc", "unpack_conv_grads", "attention_fwd",
              "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd",
              "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16", "dropout_",
              "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",

@@ -76,6 +76,12 @@ int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* 
 int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin, int Cout, int ks,
                      int sh, int sw, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
                      void* stream);
+/* split-K slices reduce-add (TMA) straight into grad_tapmajor fp32 [Cout][ks*ks][Cin] (+=): no partial sums, no
+ * reduce kernel; htrvt_unpack_conv_grads then adds all tap-major gradients of a step into the OIHW parameters' .grad */
+int htrvt_conv_wgrad_acc(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin, int Cout,
+                         int ks, int sh, int sw, float* grad_tapmajor, void* stream);
+int htrvt_unpack_conv_grads(int n, const void* const* src_tapmajor, void* const* dst_oihw, const long long* numel,
+                            const int* cin, const int* taps, void* stream);
 /* bf16 [R][P][C] -> [R][C][P]: pixel-contiguous copy of a stem gradient (dy_t above; tcgen05 runs an MN-major A
  * operand ~1.4x slower than a K-major one, so the weight-gradient GEMM is fed dY^T) */
 int htrvt_transpose_px(const void* in, void* out, long long R, int P, int C, void* stream);

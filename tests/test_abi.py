@@ -89,4 +89,5 @@ def test_dp_helpers():
     assert ddp.shard_batch(10, 3, 4) == (9, 10) and ddp.shard_batch(2, 3, 4) == (2, 2)
     names = ["mask_token", "pos_embed", "patch_embed.conv1.weight", "blocks.0.norm1.weight", "head.bias"]
     offs, split = ddp.segment_bounds(names, [768, 10, 1728, 768, 80])
-    assert offs == [0, 768, 778, 2506, 3274, 3354] and split == 2506
+    # every tensor starts on a 64-float (256 B) boundary: TMA reduce-add targets need 16-byte aligned bases
+    assert offs == [0, 768, 832, 2560, 3328, 3392] and split == 2560

@@ -142,6 +142,13 @@ def test_conv_fwd_dgrad_wgrad(NB, H, W, Cin, Cout, ks, sh, sw):
     assert _rel(gw, wr.grad) < 1e-3
     dyt = o.transpose_px(dy)
     assert torch.equal(dyt, dy.permute(0, 1, 3, 2).contiguous())
+    # tap-major in-place accumulation (split-K slices reduce-add through TMA) + the multi-tensor unpack
+    gt = torch.zeros(Cout, ks * ks, Cin, device="cuda")
+    o.conv_wgrad_acc(dy, x, ks, sh, sw, gt)
+    o.conv_wgrad_acc(dy, x, ks, sh, sw, gt)                                    # += semantics
+    gw3 = torch.ones(Cout, Cin, ks, ks, device="cuda")
+    o.unpack_conv_grads([(gt, gw3)])
+    assert _rel(gw3 - 1, 2 * wr.grad) < 1e-3
     gw2 = torch.zeros(Cout, Cin, ks, ks, device="cuda")
     o.conv_wgrad(dy, x, ks, sh, sw, gw2, accumulate=False, transpose=False)    # both operands pixel-major
     assert _rel(gw2, wr.grad) < 1e-3

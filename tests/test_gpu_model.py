@@ -228,7 +228,9 @@ def test_window_train_mode_is_stochastic_and_seeded():
     a, ga = run(3)
     b, gb = run(3)
     c, _ = run(4)
-    assert torch.equal(a, b) and torch.equal(ga, gb)            # same seed: same masks in forward and backward
+    assert torch.equal(a, b)                                    # same seed: same masks in the forward ...
+    # ... and in the backward (split-K slices reduce-add in a free order: equal up to fp32 summation order)
+    assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max())
     assert not torch.equal(a, c)
     assert torch.isfinite(a).all() and torch.isfinite(ga).all()
     m.eval()
