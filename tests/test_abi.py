@@ -90,4 +90,4 @@ def test_dp_helpers():
     names = ["mask_token", "pos_embed", "patch_embed.conv1.weight", "blocks.0.norm1.weight", "head.bias"]
     offs, split = ddp.segment_bounds(names, [768, 10, 1728, 768, 80])
     # every tensor starts on a 64-float (256 B) boundary: TMA reduce-add targets need 16-byte aligned bases
-    assert offs == [0, 768, 832, 2560, 3328, 3392] and split == 2560
+    assert offs == [0, 768, 832, 2560, 3328, 3456] and split == 2560
