@@ -31,8 +31,11 @@ def step():
 for _ in range(2):
     step()
 torch.cuda.synchronize()
+conv = h.CTCLabelConverter("".join(chr(33 + i) for i in range(bench.NB_CLS - 1)))
+logits = torch.randn(512, 128, bench.NB_CLS, device=dev)
 torch.cuda.profiler.start()
 step()
+conv.decode_logits(logits)            # greedy argmax + collapse kernel (inference path), 512 lines
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print("profiled one step, B =", B)
