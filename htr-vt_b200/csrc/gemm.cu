@@ -698,7 +698,8 @@ extern "C" int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X,
 // ---------------------------------------------------------------------------------------------
 extern "C" int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw) {
   (void)NB; (void)H; (void)W; (void)ks; (void)sh; (void)sw;
-  return 4 * num_sms();     // rows of the [ctas * 4 quadrants][2][Cout] partial-statistics buffer (zero-initialised)
+  return 4 * num_sms();     // rows of the [ctas * 4 quadrants][2][Cout] partial-statistics buffer (zero-initialised):
+                            // per-CTA rows + a fixed-order finalise keep the train-mode FORWARD bit-reproducible
 }
 
 extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks,

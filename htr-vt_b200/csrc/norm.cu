@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(256) row_ln_bwd_kernel(const __nv_bfloat16* __
                                                          const float* __restrict__ x, const float* __restrict__ mean,
                                                          const float* __restrict__ rstd,
                                                          const float* __restrict__ gamma, float* __restrict__ gx,
-                                                         float* __restrict__ partial, int M, int rows_per_cta,
-                                                         int accumulate) {
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
+                                                         int rows_per_cta, int accumulate) {
   constexpr int V = D / 128;
   __shared__ float sg[8][D], sb[8][D];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -192,8 +192,10 @@ __global__ void __launch_bounds__(256) row_ln_bwd_kernel(const __nv_bfloat16* __
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { a += sg[w][c]; b += sb[w][c]; }
-    partial[(static_cast<long long>(blockIdx.x) * 2) * D + c] = a;
-    partial[(static_cast<long long>(blockIdx.x) * 2 + 1) * D + c] = b;
+    // one fp32 atomic per CTA and column straight into the gradients (no partial buffer, no finalise launch; the
+    // order of the additions per column is not fixed)
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
   }
 }
 
@@ -306,7 +308,7 @@ __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv
 // Column sums of a bf16 matrix [M, N] (bias gradients): partial[cta][N]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ a, long long ld, int M,
-                                                          int N, int rows_per_cta, float* __restrict__ partial) {
+                                                          int N, int rows_per_cta, float* __restrict__ out) {
   // thread handles a pair of columns; blockDim.y row lanes are reduced through shared memory
   __shared__ float2 sm[8][128];
   const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;       // 128 column pairs x 2 row lanes
@@ -323,8 +325,8 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   __syncthreads();
   if (ty == 0 && c < N) {
     const float2 o = sm[1][tx];
-    partial[static_cast<long long>(blockIdx.y) * N + c] = acc.x + o.x;
-    if (c + 1 < N) partial[static_cast<long long>(blockIdx.y) * N + c + 1] = acc.y + o.y;
+    atomicAdd(out + c, acc.x + o.x);                    // out += (one atomic per CTA and column, no finalise launch)
+    if (c + 1 < N) atomicAdd(out + c + 1, acc.y + o.y);
   }
 }
 
@@ -518,18 +520,15 @@ extern "C" int htrvt_row_ln_bwd(const void* dy_bf16, const float* x, const float
   const int rows = (M + ctas - 1) / ctas;
   const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_bf16);
   if (D == 768)
-    row_ln_bwd_kernel<768><<<ctas, 256, 0, stream>>>(dy, x, mean, rstd, gamma, gx, partial, M, rows, accumulate);
+    row_ln_bwd_kernel<768><<<ctas, 256, 0, stream>>>(dy, x, mean, rstd, gamma, gx, dgamma, dbeta, M, rows, accumulate);
   else if (D == 128)
-    row_ln_bwd_kernel<128><<<ctas, 256, 0, stream>>>(dy, x, mean, rstd, gamma, gx, partial, M, rows, accumulate);
+    row_ln_bwd_kernel<128><<<ctas, 256, 0, stream>>>(dy, x, mean, rstd, gamma, gx, dgamma, dbeta, M, rows, accumulate);
   else if (D == 256)
-    row_ln_bwd_kernel<256><<<ctas, 256, 0, stream>>>(dy, x, mean, rstd, gamma, gx, partial, M, rows, accumulate);
+    row_ln_bwd_kernel<256><<<ctas, 256, 0, stream>>>(dy, x, mean, rstd, gamma, gx, dgamma, dbeta, M, rows, accumulate);
   else
     return HTRVT_ERR_SHAPE;
   HTRVT_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<(D + 31) / 32, 256, 0, stream>>>(partial, ctas, 2LL * D, D, dgamma, 1);
-  HTRVT_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<(D + 31) / 32, 256, 0, stream>>>(partial + D, ctas, 2LL * D, D, dbeta, 1);
-  HTRVT_LAUNCH_CHECK();
+  (void)partial;                 // dgamma / dbeta are accumulated (+=) with per-CTA atomics
   return HTRVT_OK;
 }
 
@@ -587,9 +586,10 @@ extern "C" int htrvt_colsum_bf16(const void* a, long long ld, int M, int N, floa
   const int gy = htrvt_colsum_rows(M);
   const int rows = (M + gy - 1) / gy;
   dim3 grid((N + 255) / 256, gy);
-  colsum_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a), ld, M, N, rows, partial);
-  HTRVT_LAUNCH_CHECK();
-  colsum_finalize_kernel<<<(N + 31) / 32, 256, 0, stream>>>(partial, gy, N, N, out, accumulate);
+  (void)partial;
+  if (!accumulate && cudaMemsetAsync(out, 0, static_cast<size_t>(N) * sizeof(float), stream) != cudaSuccess)
+    return HTRVT_ERR_LAUNCH;
+  colsum_bf16_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a), ld, M, N, rows, out);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }

@@ -371,7 +371,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const 
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) {
     float s = 0.f;
     for (int rr = 0; rr < R; ++rr) s += sm[rr * 3 * C + i];
-    partial[static_cast<long long>(blockIdx.x) * 3 * C + i] = s;
+    atomicAdd(partial + i, s);            // one zeroed [3][C] row: a few hundred fp32 atomics per column
   }
 }
 
@@ -663,6 +663,8 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, 
     configured = true;
   }
   if (smem > 96 * 1024) return HTRVT_ERR_SHAPE;
+  if (cudaMemsetAsync(partial, 0, static_cast<size_t>(3) * C * sizeof(float), stream) != cudaSuccess)
+    return HTRVT_ERR_LAUNCH;
   bn_bwd_reduce_kernel<<<ctas, threads, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(g), static_cast<const uint8_t*>(mask),
       static_cast<const __nv_bfloat16*>(raw_a), mean_a, rstd_a, static_cast<const __nv_bfloat16*>(raw_b), mean_b,
@@ -670,7 +672,7 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, 
   HTRVT_LAUNCH_CHECK();
   float* coef_a = coef;
   float* coef_b = raw_b ? coef + 3 * C : nullptr;
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, stream>>>(partial, ctas, static_cast<double>(P), C, gamma_a, mean_a,
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, stream>>>(partial, 1, static_cast<double>(P), C, gamma_a, mean_a,
                                                              rstd_a, coef_a, dgamma_a, dbeta_a, gamma_b, mean_b, rstd_b,
                                                              coef_b, dgamma_b, dbeta_b);
   HTRVT_LAUNCH_CHECK();
