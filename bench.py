@@ -190,6 +190,54 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
     model.train()
     del img
 
+    # ---- the reference's full training iteration (model_v1/train.py:113-126): SAM(AdamW) = two forward/backward
+    # passes around first_step / second_step + the EMA update, with the multi-tensor optimizer kernels
+    try:
+        SAMm = import_module("htr-vt_b200.utils.sam")
+        Um = import_module("htr-vt_b200.utils.utils")
+        Bs = 128
+        imgs, tgs, tls = [t.to(dev) for t in synth_batch(Bs, 2)]
+        opt = SAMm.SAM(model.parameters(), torch.optim.AdamW, lr=1e-4, betas=(0.9, 0.99), weight_decay=0.5)
+        ema = Um.ModelEma(model, 0.9999)
+        crit = h.CTCLoss(reduction="none", zero_infinity=True)
+        ps = torch.full((Bs,), IMG_W // 4, dtype=torch.int32, device=dev)
+
+        def fb():
+            preds = model(imgs, MASK_RATIO, MAX_SPAN, use_masking=True).float()
+            loss = crit(preds.permute(1, 0, 2).log_softmax(2), tgs, ps, tls).mean()
+            loss.backward()
+
+        def sam_iter():
+            opt.zero_grad()
+            fb()
+            opt.first_step(zero_grad=True)
+            fb()
+            opt.second_step(zero_grad=True)
+            model.zero_grad()
+            ema.update(model, num_updates=10)
+
+        def opt_only():
+            for p in model.parameters():
+                if p.requires_grad and p.grad is None:
+                    p.grad = torch.zeros_like(p)
+            opt.first_step(zero_grad=False)
+            opt.second_step(zero_grad=False)
+            ema.update(model, num_updates=10)
+
+        ms = timed_ms(sam_iter, 5, warm=2)
+        ms_opt = timed_ms(opt_only, 5, warm=1)
+        nparam = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        opt_bytes = nparam * (4 + 16 + 36 + 12)            # norm + climb + restore/AdamW + EMA, fp32 streams
+        out["sam_iteration"] = {"img_per_s": Bs / (ms * 1e-3), "ms_per_iteration": ms, "batch_per_gpu": Bs,
+                                "optimizer_ms": ms_opt, "optimizer_algorithmic_bytes": opt_bytes,
+                                "optimizer_gbs": opt_bytes / (ms_opt * 1e-3) / 1e9,
+                                "what": "2x(fwd+bwd+CTC) + SAM first/second step (fused AdamW) + EMA, train.py:113-126"}
+        del opt, ema
+        for p in model.parameters():
+            p.grad = None
+    except Exception as e:
+        out["sam_iteration"] = {"error": repr(e)[:200]}
+
     # ---- windowed variant (model_window), 64x1024 lines, T = 256, 90 classes, labels up to 200: training step with
     # the reference's train-mode regularisers on (dropout 0.1 / attention dropout 0.05 / DropPath <= 0.1)
     try:

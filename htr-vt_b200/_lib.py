@@ -84,6 +84,10 @@ SIGNATURES = {
     "htrvt_stem_head_moments": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_stem_head_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_stem_head_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_mt_sqnorm": (_I, [_I, _P, _P, _P, _I, _P, _P]),
+    "htrvt_mt_sam_first": (_I, [_I, _P, _P, _P, _P, _P, _F, _I, _P]),
+    "htrvt_mt_adamw": (_I, [_I, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _I, _P]),
+    "htrvt_mt_ema": (_I, [_I, _P, _P, _P, _F, _P]),
     "htrvt_attention_fwd": (_I, [_P, _I, _I, _I, _I, _F, _P, _P, _P]),
     "htrvt_attention2_fwd": (_I, [_P, _I, _I, _I, _I, _F, _P, _I, _I, _I, _F, ctypes.c_ulonglong, _P, _P, _P]),
     "htrvt_attention2_bwd_workspace_bytes": (_Z, [_I, _I, _I, _I]),

@@ -1,0 +1,146 @@
+"""`SAM(params, base_optimizer, rho, adaptive, **kwargs)` with the reference's interface (model_v1/utils/sam.py) on
+multi-tensor sm_100a kernels (csrc/optim.cu).
+
+The reference walks the parameter list in Python: a `norm` launch per tensor + `stack` + `norm` for the gradient
+norm, a `clone` and an `add_` per tensor in `first_step`, a pointer swap per tensor and the base optimizer's own
+per-tensor (or foreach) update in `second_step` - ~10^3 launches per iteration for the 102 parameters of HTR-VT.
+Here each pass (gradient norm, climb, restore + AdamW) is one launch per <= 48 tensors and the norm never visits the
+host.  Same call sequence as model_v1/train.py:117-126: `first_step(zero_grad=True)`, forward/backward,
+`second_step(zero_grad=True)`; `param_groups` (lr set by utils.update_lr_cos), `state_dict()` and `zero_grad()` behave
+as in the reference.  Only AdamW (the optimizer the reference trains with, train.py:93) has a fused path; any other
+base optimizer falls back to calling its own `.step()` after the fused restore.
+"""
+import ctypes
+
+import torch
+
+from .._lib import check, lib
+
+
+def _ptrs(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _numels(tensors):
+    arr = (ctypes.c_longlong * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.numel()
+    return arr
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dense_f32(t):
+    return t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+
+
+class SAM(torch.optim.Optimizer):
+    def __init__(self, params, base_optimizer, rho=0.05, adaptive=False, **kwargs):
+        assert rho >= 0.0, f"Invalid rho, should be non-negative: {rho}"
+        defaults = dict(rho=rho, adaptive=adaptive, **kwargs)
+        super(SAM, self).__init__(params, defaults)
+        self.base_optimizer = base_optimizer(self.param_groups, **kwargs)
+        self.param_groups = self.base_optimizer.param_groups
+        self.defaults.update(self.base_optimizer.defaults)
+        self._fused_adamw = isinstance(self.base_optimizer, torch.optim.AdamW)
+        self._norm2 = None
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _live(self, group):
+        ps = [p for p in group["params"] if p.grad is not None]
+        for p in ps:
+            if not (_dense_f32(p.data) and _dense_f32(p.grad)):
+                raise RuntimeError("htr-vt_b200 SAM needs contiguous fp32 CUDA parameters and gradients")
+        return ps
+
+    def _grad_norm_device(self):
+        """sum |g|^2 (adaptive: |abs(w) g|^2) over every parameter, left on the device as a float64 scalar."""
+        dev = self.param_groups[0]["params"][0].device
+        if self._norm2 is None or self._norm2.device != dev:
+            self._norm2 = torch.zeros((), dtype=torch.float64, device=dev)
+        self._norm2.zero_()
+        for group in self.param_groups:
+            ps = self._live(group)
+            if not ps:
+                continue
+            check(lib().htrvt_mt_sqnorm(len(ps), _ptrs([p.grad for p in ps]), _ptrs([p.data for p in ps]), _numels(ps),
+                                        int(bool(group["adaptive"])), ctypes.c_void_p(self._norm2.data_ptr()),
+                                        _stream()), "htrvt_mt_sqnorm")
+        return self._norm2
+
+    def _grad_norm(self):                     # reference name (sam.py:49): returns the norm as a tensor
+        return self._grad_norm_device().sqrt().float()
+
+    # -- the reference's two steps --------------------------------------------------------------------
+    @torch.no_grad()
+    def first_step(self, zero_grad=False):
+        norm2 = self._grad_norm_device()
+        for group in self.param_groups:
+            ps = self._live(group)
+            if not ps:
+                continue
+            olds = []
+            for p in ps:
+                st = self.state[p]
+                if "old_p" not in st or st["old_p"].shape != p.shape:
+                    st["old_p"] = torch.empty_like(p.data)
+                olds.append(st["old_p"])
+            check(lib().htrvt_mt_sam_first(len(ps), _ptrs([p.data for p in ps]), _ptrs([p.grad for p in ps]),
+                                           _ptrs(olds), _numels(ps), ctypes.c_void_p(norm2.data_ptr()),
+                                           float(group["rho"]), int(bool(group["adaptive"])), _stream()),
+                  "htrvt_mt_sam_first")
+        if zero_grad:
+            self.zero_grad()
+
+    @torch.no_grad()
+    def second_step(self, zero_grad=False):
+        for group in self.param_groups:
+            ps = self._live(group)
+            if not ps:
+                continue
+            olds = [self.state[p]["old_p"] for p in ps]
+            if not self._fused_adamw or group.get("amsgrad", False) or group.get("maximize", False):
+                for p, o in zip(ps, olds):                    # get back to "w" from "w + e(w)"
+                    p.data.copy_(o)
+                continue
+            bst = self.base_optimizer.state
+            ms, vs = [], []
+            for p in ps:
+                st = bst[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p.data)
+                    st["exp_avg_sq"] = torch.zeros_like(p.data)
+                st["step"] += 1
+                ms.append(st["exp_avg"])
+                vs.append(st["exp_avg_sq"])
+            steps = {int(bst[p]["step"]) for p in ps}
+            if len(steps) != 1:
+                raise RuntimeError("htr-vt_b200 SAM: parameters of one group must share their step count")
+            b1, b2 = group["betas"]
+            lr = group["lr"]
+            check(lib().htrvt_mt_adamw(len(ps), _ptrs([p.data for p in ps]), _ptrs([p.grad for p in ps]), _ptrs(ms),
+                                       _ptrs(vs), _ptrs(olds), _numels(ps), float(lr), float(b1), float(b2),
+                                       float(group["eps"]), float(group["weight_decay"]), steps.pop(), _stream()),
+                  "htrvt_mt_adamw")
+        if not self._fused_adamw:
+            self.base_optimizer.step()                        # do the actual "sharpness-aware" update
+        if zero_grad:
+            self.zero_grad()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        assert closure is not None, "Sharpness Aware Minimization requires closure, but it was not provided"
+        closure = torch.enable_grad()(closure)
+        self.first_step(zero_grad=True)
+        closure()
+        self.second_step()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self.base_optimizer.param_groups = self.param_groups

@@ -193,6 +193,20 @@ int htrvt_conv1_wgrad_ctas(void);
 int htrvt_conv1_wgrad(const void* dy_bf16, const float* x, float* grad, int accumulate, float* partial, int B,
                       int H, int W, int C, void* stream);
 
+/* ---- multi-tensor optimizer passes around the hot path -------------------------------
+ * Replace the per-parameter loops of SAM (model_v1/utils/sam.py:15-59), torch.optim.AdamW as configured at
+ * model_v1/train.py:93 and ModelEma.update (model_v1/utils/utils.py:158-173).  Arrays of n DEVICE pointers to fp32
+ * tensors live on the HOST (they travel as kernel parameters, <= 48 tensors per launch); numel[i] elements each.
+ * norm2: device double, zeroed by the caller, receives sum |g|^2 (adaptive: |abs(p) g|^2). */
+int htrvt_mt_sqnorm(int n, void* const* g, void* const* p, const long long* numel, int adaptive, double* norm2,
+                    void* stream);
+int htrvt_mt_sam_first(int n, void* const* p, void* const* g, void* const* old_p, const long long* numel,
+                       const double* norm2, float rho, int adaptive, void* stream);
+int htrvt_mt_adamw(int n, void* const* p, void* const* g, void* const* exp_avg, void* const* exp_avg_sq,
+                   void* const* old_p, const long long* numel, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, void* stream);
+int htrvt_mt_ema(int n, void* const* ema, void* const* src, const long long* numel, float decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
