@@ -731,8 +731,10 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
 }
 
 // dx[NB,H,W,Cin] (= or +=) conv_transpose(dy[NB,Ho,Wo,Cout], w): one GEMM per output parity class.
-extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* w, int Cout, int ks,
-                                int sh, int sw, void* dx, int accumulate, cudaStream_t stream) {
+// w_t (optional): the weights as bf16 [Cin][ks*ks][Cout] (htrvt_pack_weights transposed mode): B becomes a K-major
+// operand, which lets BN = 192 tiles run as cta_group::2 pairs (an MN-major B cannot be split at 96 columns).
+extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* w, const void* w_t, int Cout,
+                                int ks, int sh, int sw, void* dx, int accumulate, cudaStream_t stream) {
   const int pad = ks / 2;
   if ((Cout % 8) || (Cin % 64) || (W % sw) || (H % sh) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
@@ -758,19 +760,25 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
       if (n == 0) continue;                               // class receives no gradient (1x1 strided): caller zero-fills
       P.kind = 0; P.Wo = Wq; P.Ho = Hq; P.NB = NB;
       P.tiles_per_row = (Wq + kBM - 1) / kBM; P.tiles_m = P.tiles_per_row * Hq * NB; P.tiles_n = (Cin + bn - 1) / bn;
-      P.n_taps = n; P.splits = 1; P.k_chunks = (Cout + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = Cin;
+      const bool kmajor = w_t != nullptr && (Cout % 64) == 0;
+      P.n_taps = n; P.splits = 1; P.k_chunks = (Cout + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = kmajor ? Cout : Cin;
       P.N_valid = Cin; P.flags = EPI_BF16 | (accumulate ? EPI_ACCUM : 0);
       P.alpha = 1.f;
-      const int cl = pick_cluster(P.tiles_m, P.tiles_m * P.tiles_n, bn, true);
-      r = make_map_matrix(&tb, w, Cout, static_cast<long long>(ks) * ks * Cin, static_cast<long long>(ks) * ks * Cin, 64,
-                          64);
+      const int cl = pick_cluster(P.tiles_m, P.tiles_m * P.tiles_n, bn, !kmajor);
+      if (kmajor)
+        r = make_map_matrix(&tb, w_t, Cin, static_cast<long long>(ks) * ks * Cout, static_cast<long long>(ks) * ks * Cout,
+                            kBK, bn / cl);
+      else
+        r = make_map_matrix(&tb, w, Cout, static_cast<long long>(ks) * ks * Cin, static_cast<long long>(ks) * ks * Cin,
+                            64, 64);
       if (r) return r;
       CUtensorMap tc;                                     // parity class (ph, pw) of dx as a strided tensor
       r = make_map_out(&tc, static_cast<__nv_bfloat16*>(dx) + (static_cast<long long>(ph) * W + pw) * Cin, 2, Cin, Wq,
                        Hq, NB, static_cast<long long>(sw) * Cin, static_cast<long long>(sh) * W * Cin,
                        static_cast<long long>(H) * W * Cin);
       if (r) return r;
-      r = launch_bn<0, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+      r = kmajor ? launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream)
+                 : launch_bn<0, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
       if (r) return r;
     }
   return HTRVT_OK;
@@ -857,20 +865,24 @@ struct UnpackTable {
   int cin[kMaxUnpack];
   int taps[kMaxUnpack];
 };
-__global__ void unpack_conv_grads_kernel(const __grid_constant__ UnpackTable T) {
+__global__ void __launch_bounds__(256) unpack_conv_grads_kernel(const __grid_constant__ UnpackTable T) {
+  extern __shared__ float up_stage[];                   // one output channel's [taps][Cin] block
   const int t = blockIdx.y;
   const float* __restrict__ src = T.src[t];
   float* __restrict__ dst = T.dst[t];
   const long long n = T.numel[t];
   const int Cin = T.cin[t], taps = T.taps[t];
-  // thread i owns OIHW element i (coalesced read-modify-write of the gradient; the tap-major source is L2 resident)
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int tap = static_cast<int>(i % taps);
-    const long long r = i / taps;
-    const int ci = static_cast<int>(r % Cin);
-    const long long co = r / Cin;
-    dst[i] += src[(co * taps + tap) * Cin + ci];
+  const int per = Cin * taps;
+  const int Cout = static_cast<int>(n / per);
+  // per output channel a [taps][Cin] -> [Cin][taps] transpose through smem: contiguous read, contiguous RMW
+  for (int co = blockIdx.x; co < Cout; co += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < per; i += blockDim.x) up_stage[i] = src[static_cast<long long>(co) * per + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < per; i += blockDim.x) {
+      const int ci = i / taps, tap = i - ci * taps;
+      dst[static_cast<long long>(co) * per + i] += up_stage[tap * Cin + ci];
+    }
   }
 }
 }  // namespace htrvt
@@ -888,8 +900,12 @@ extern "C" int htrvt_unpack_conv_grads(int n, const void* const* src, void* cons
       T.taps[i] = taps[base + i];
       if (T.cin[i] <= 0 || T.taps[i] <= 0) return HTRVT_ERR_SHAPE;
     }
+    int smem = 0;
+    for (int i = 0; i < cnt; ++i)
+      if (T.cin[i] * T.taps[i] * 4 > smem) smem = T.cin[i] * T.taps[i] * 4;
+    if (smem > 48 * 1024) return HTRVT_ERR_SHAPE;
     dim3 grid(148, cnt);
-    unpack_conv_grads_kernel<<<grid, 256, 0, stream>>>(T);
+    unpack_conv_grads_kernel<<<grid, 256, smem, stream>>>(T);
     HTRVT_LAUNCH_CHECK();
   }
   return HTRVT_OK;

@@ -363,23 +363,55 @@ struct PackTable {
   int cin[kMaxPack];
   int taps[kMaxPack];
 };
-__global__ void pack_weights_kernel(const __grid_constant__ PackTable T) {
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackTable T) {
+  extern __shared__ float pk_stage[];                   // one output channel's [Cin][taps] block (conv repack)
   const int t = blockIdx.y;
   const float* __restrict__ src = T.src[t];
   __nv_bfloat16* __restrict__ dst = T.dst[t];
   const long long n = T.numel[t];
   const int Cin = T.cin[t], taps = T.taps[t];
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    long long j = i;
-    if (taps > 0) {
-      const int ci = static_cast<int>(i % Cin);
-      const long long r = i / Cin;
-      const int tap = static_cast<int>(r % taps);
-      const long long co = r / taps;
-      j = (co * Cin + ci) * taps + tap;
+  if (taps < 0) {
+    // transposed cast [R][K] fp32 -> [K][R] bf16 (R = Cin field): OIHW [Cout][Cin*taps] -> [Cin][taps][Cout], the
+    // K-major B operand of the input-gradient GEMM.  32 x 32 tiles through smem: both sides contiguous.
+    float (*tile)[33] = reinterpret_cast<float (*)[33]>(pk_stage);
+    const int R = Cin, K = static_cast<int>(n / R);
+    const int tk = (K + 31) / 32, tr = (R + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
+    for (int tile_id = blockIdx.x; tile_id < tk * tr; tile_id += gridDim.x) {
+      const int r0 = (tile_id / tk) * 32, k0 = (tile_id % tk) * 32;
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + ty + 8 * j, k = k0 + tx;
+        tile[ty + 8 * j][tx] = (r < R && k < K) ? src[static_cast<long long>(r) * K + k] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + ty + 8 * j, r = r0 + tx;
+        if (r < R && k < K) dst[static_cast<long long>(k) * R + r] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
+      }
     }
-    dst[i] = __float2bfloat16_rn(src[j]);
+    return;
+  }
+  if (taps <= 1) {                                      // plain cast ([out,in] linears, 1x1 convs)
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+      dst[i] = __float2bfloat16_rn(src[i]);
+    return;
+  }
+  // OIHW -> [Cout][taps][Cin]: per output channel a [Cin][taps] -> [taps][Cin] transpose through smem, so both the
+  // fp32 read and the bf16 write are contiguous
+  const int per = Cin * taps;
+  const int Cout = static_cast<int>(n / per);
+  for (int co = blockIdx.x; co < Cout; co += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < per; i += blockDim.x) pk_stage[i] = src[static_cast<long long>(co) * per + i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < per; i += blockDim.x) {
+      const int tap = i / Cin, ci = i - tap * Cin;
+      dst[static_cast<long long>(co) * per + i] = __float2bfloat16_rn(pk_stage[ci * taps + tap]);
+    }
   }
 }
 
@@ -610,7 +642,8 @@ extern "C" int htrvt_pack_conv_weight(const float* w_oihw, void* dst, int Cout, 
   return HTRVT_OK;
 }
 
-// n <= 64 tensors per call: src fp32, dst bf16, numel elements; taps[i] == 0 -> cast, else OIHW -> [Cout][taps][Cin]
+// n tensors per call: src fp32, dst bf16, numel elements; taps[i] == 0 -> cast, > 0 -> OIHW -> [Cout][taps][Cin],
+// < 0 -> transposed cast [cin[i]][numel/cin[i]] -> [numel/cin[i]][cin[i]] (cin[i] = rows of the source matrix)
 extern "C" int htrvt_pack_weights(int n, const void* const* src, void* const* dst, const long long* numel,
                                   const int* cin, const int* taps, cudaStream_t stream) {
   if (n <= 0) return HTRVT_OK;
@@ -624,8 +657,14 @@ extern "C" int htrvt_pack_weights(int n, const void* const* src, void* const* ds
       T.cin[i] = cin[base + i] > 0 ? cin[base + i] : 1;
       T.taps[i] = taps[base + i];
     }
+    int smem = 0;
+    for (int i = 0; i < cnt; ++i)
+      if (T.taps[i] > 1 && T.cin[i] * T.taps[i] * 4 > smem) smem = T.cin[i] * T.taps[i] * 4;
+    for (int i = 0; i < cnt; ++i)
+      if (T.taps[i] < 0 && smem < 32 * 33 * 4) smem = 32 * 33 * 4;
+    if (smem > 48 * 1024) return HTRVT_ERR_SHAPE;
     dim3 grid(96, cnt);
-    pack_weights_kernel<<<grid, 256, 0, stream>>>(T);
+    pack_weights_kernel<<<grid, 256, smem, stream>>>(T);
     HTRVT_LAUNCH_CHECK();
   }
   return HTRVT_OK;

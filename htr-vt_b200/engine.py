@@ -79,6 +79,9 @@ class Engine(object):
             if k.startswith("patch_embed.") and k.endswith("weight") and v.dim() == 4 and v.shape[1] > 1:
                 names.append(k)
                 items.append((v, "conv"))
+                if save:                          # [Cin, taps, Cout] copy: K-major B operand of the input-gradient GEMM
+                    names.append("T:" + k)
+                    items.append((v, "convT"))
             elif v.dim() == 2 and k.endswith(".weight"):
                 names.append(k)
                 items.append((v, "cast"))
@@ -293,18 +296,19 @@ class Engine(object):
                 dgamma_b=grads[p + ".downsample.1.weight"] if has_ds else None,
                 dbeta_b=grads[p + ".downsample.1.bias"] if has_ds else None, want_gz=not has_ds)
             ops.conv_wgrad_acc(d2, a1, 3, 1, 1, gt[p + ".conv2.weight"])
-            da1 = ops.conv_dgrad(d2, wp[p + ".conv2.weight"], tuple(a1.shape), 3, 1, 1)
+            da1 = ops.conv_dgrad(d2, wp[p + ".conv2.weight"], tuple(a1.shape), 3, 1, 1, w_t=wp.get("T:" + p + ".conv2.weight"))
             d1, _, _ = ops.bn_bwd(da1, k1, r1, sa, sd[p + ".bn1.weight"], grads[p + ".bn1.weight"],
                                   grads[p + ".bn1.bias"])
             ops.conv_wgrad_acc(d1, xin, 3, s[0], s[1], gt[p + ".conv1.weight"])
             if has_ds:
-                gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1])
+                gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1],
+                                     w_t=wp.get("T:" + p + ".conv1.weight"))
                 ops.conv_wgrad_acc(dd, xin, 1, s[0], s[1], gt[p + ".downsample.0.weight"])
                 ops.conv_dgrad(dd, wp[p + ".downsample.0.weight"], tuple(xin.shape), 1, s[0], s[1], dx=gin,
-                               accumulate=True)
+                               accumulate=True, w_t=wp.get("T:" + p + ".downsample.0.weight"))
             else:
                 gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1], dx=gz,
-                                     accumulate=True)
+                                     accumulate=True, w_t=wp.get("T:" + p + ".conv1.weight"))
             g = gin
         ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames])
         # ---- stem head: pool -> relu -> bn1 -> conv1 ---------------------------------------------

@@ -125,14 +125,16 @@ def conv_stats_rows(N, H, W, ks, sh, sw):
     return lib().htrvt_conv_fwd_stats_rows(N, H, W, ks, sh, sw)
 
 
-def conv_dgrad(dy, w, x_shape, ks, sh, sw, dx=None, accumulate=False):
+def conv_dgrad(dy, w, x_shape, ks, sh, sw, dx=None, accumulate=False, w_t=None):
+    """w bf16 [Cout, taps, Cin]; w_t (optional) bf16 [Cin, taps, Cout]: K-major B operand (CTA-pair kernel)."""
     _need_cuda(dy, w)
     N, H, W, Cin = x_shape
     Cout = w.shape[0]
     if dx is None:
         dx = torch.zeros(x_shape, dtype=torch.bfloat16, device=dy.device) if (ks == 1 and (sh > 1 or sw > 1)) \
             else torch.empty(x_shape, dtype=torch.bfloat16, device=dy.device)
-    check(lib().htrvt_conv_dgrad(_p(dy), N, H, W, Cin, _p(w), Cout, ks, sh, sw, _p(dx), int(accumulate), _stream()),
+    check(lib().htrvt_conv_dgrad(_p(dy), N, H, W, Cin, _p(w), _p(w_t), Cout, ks, sh, sw, _p(dx), int(accumulate),
+                                 _stream()),
           "htrvt_conv_dgrad")
     return dx
 
@@ -410,6 +412,10 @@ def pack_weights(items, pad_rows=None, names=None):
             Cout, Ci, kh, kw = t.shape
             o = torch.empty((Cout, kh * kw, Ci), dtype=torch.bfloat16, device=t.device)
             cin[i], taps[i] = Ci, kh * kw
+        elif kind == "convT":                 # OIHW -> [Cin, taps, Cout] = plain transpose of [Cout, Cin*taps]
+            Cout, Ci, kh, kw = t.shape
+            o = torch.empty((Ci, kh * kw, Cout), dtype=torch.bfloat16, device=t.device)
+            cin[i], taps[i] = Cout, -1
         else:
             rows = pad_rows.get(names[i]) if (pad_rows and names) else None
             if rows is not None and rows != t.shape[0]:

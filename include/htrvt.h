@@ -71,8 +71,8 @@ int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X, long long 
 int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks, int sh, int sw,
                    void* y, float* stats_partial, int flags, void* stream);
 int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw);
-int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* w, int Cout, int ks, int sh,
-                     int sw, void* dx, int accumulate, void* stream);
+int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* w, const void* w_t, int Cout, int ks,
+                     int sh, int sw, void* dx, int accumulate, void* stream);
 int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin, int Cout, int ks,
                      int sh, int sw, float* grad_oihw, int accumulate, void* workspace, size_t workspace_bytes,
                      void* stream);

@@ -137,6 +137,13 @@ def test_conv_fwd_dgrad_wgrad(NB, H, W, Cin, Cout, ks, sh, sw):
     yr.backward(dy.float().permute(0, 3, 1, 2))
     dx = o.conv_dgrad(dy, wk, (NB, H, W, Cin), ks, sh, sw)
     assert _rel(dx.permute(0, 3, 1, 2), xr.grad) < 1e-2
+    # K-major B operand from the transposed pack [Cin, taps, Cout] (CTA-pair kernel where the tile grid allows)
+    packed = o.pack_weights([(w.float().contiguous(), "conv"), (w.float().contiguous(), "convT")])
+    assert torch.equal(packed[0], wk)
+    wt = w.permute(1, 2, 3, 0).reshape(Cin, ks * ks, Cout).contiguous()
+    assert torch.equal(packed[1], wt)
+    dx2 = o.conv_dgrad(dy, wk, (NB, H, W, Cin), ks, sh, sw, w_t=wt)
+    assert _rel(dx2.permute(0, 3, 1, 2), xr.grad) < 1e-2
     gw = torch.zeros(Cout, Cin, ks, ks, device="cuda")
     o.conv_wgrad(dy, x, ks, sh, sw, gw, accumulate=False, transpose=True)      # K-major dY^T operand (transpose_px)
     assert _rel(gw, wr.grad) < 1e-3

@@ -39,6 +39,14 @@ xl2 = torch.randn(128, 4, 256, 384, device=dev).bfloat16()
 yl2 = torch.randn(128, 4, 256, 384, device=dev).bfloat16()
 gl2 = torch.zeros(384, 384, 3, 3, device=dev)
 
+wl1T = wl1.permute(2, 1, 0).contiguous()
+wl2 = torch.randn(384, 9, 384, device=dev).bfloat16()
+wl2T = wl2.permute(2, 1, 0).contiguous()
+yl2b = torch.empty(128, 4, 256, 384, device=dev, dtype=torch.bfloat16)
+gt1 = torch.zeros(192, 9, 192, device=dev)
+gt2 = torch.zeros(384, 9, 384, device=dev)
+gt3 = torch.zeros(768, 9, 768, device=dev)
+
 # operand major-ness experiment: the same 3072 x 768 x 16384 contraction with (A,B) = (K,K), (K,MN), (MN,MN)
 aK = torch.randn(3072, 16384, device=dev).bfloat16()
 bK = torch.randn(768, 16384, device=dev).bfloat16()
@@ -59,6 +67,13 @@ cases = {
     "l1_fwd_nostore": (lambda: o.conv_fwd(xl1, wl1, 3, 1, 1, y=yl1, nostore=True), 2.0 * 128 * 8 * 512 * 192 * 1728),
     "l1_dgrad": (lambda: o.conv_dgrad(yl1, wl1, (128, 8, 512, 192), 3, 1, 1, dx=xl1), 2.0 * 128 * 8 * 512 * 192 * 1728),
     "l1_dgrad_acc": (lambda: o.conv_dgrad(yl1, wl1, (128, 8, 512, 192), 3, 1, 1, dx=xl1, accumulate=True), 2.0 * 128 * 8 * 512 * 192 * 1728),
+    "l1_dgrad_T": (lambda: o.conv_dgrad(yl1, wl1, (128, 8, 512, 192), 3, 1, 1, dx=xl1, w_t=wl1T), 2.0 * 128 * 8 * 512 * 192 * 1728),
+    "l2_dgrad": (lambda: o.conv_dgrad(yl2, wl2, (128, 4, 256, 384), 3, 1, 1, dx=xl2), 2.0 * 128 * 4 * 256 * 384 * 3456),
+    "l2_dgrad_T": (lambda: o.conv_dgrad(yl2, wl2, (128, 4, 256, 384), 3, 1, 1, dx=xl2, w_t=wl2T), 2.0 * 128 * 4 * 256 * 384 * 3456),
+    "l2_fwd": (lambda: o.conv_fwd(xl2, wl2, 3, 1, 1, y=yl2b), 2.0 * 128 * 4 * 256 * 384 * 3456),
+    "l1_wgrad_acc": (lambda: o.conv_wgrad_acc(yl1, xl1, 3, 1, 1, gt1), 2.0 * 128 * 8 * 512 * 192 * 1728),
+    "l2_wgrad_acc": (lambda: o.conv_wgrad_acc(yl2, xl2, 3, 1, 1, gt2), 2.0 * 128 * 4 * 256 * 384 * 3456),
+    "l3_wgrad_acc": (lambda: o.conv_wgrad_acc(yl3, xl3, 3, 1, 1, gt3), 2.0 * 128 * 2 * 128 * 768 * 6912),
     "l1_wgrad": (lambda: o.conv_wgrad(yl1, xl1, 3, 1, 1, gl1), 2.0 * 128 * 8 * 512 * 192 * 1728),
     "l3_fwd_stats": (lambda: o.conv_fwd(xl3, wl3, 3, 1, 1, y=yl3, stats=stats3), 2.0 * 128 * 2 * 128 * 768 * 6912),
     "l2_wgrad": (lambda: o.conv_wgrad(yl2, xl2, 3, 1, 1, gl2), 2.0 * 128 * 4 * 256 * 384 * 3456),
