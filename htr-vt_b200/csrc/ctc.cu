@@ -7,6 +7,7 @@
 //   preds.float().permute(1,0,2).log_softmax(2) -> nn.CTCLoss(reduction='none', zero_infinity=True)
 // (ATen _ctc_loss / _ctc_loss_backward; blank = 0).  Semantics: SURVEY.md 8a / 9.14-9.16.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace htrvt {
 
@@ -158,6 +159,165 @@ __device__ __forceinline__ void ctc_beta(const float* __restrict__ l2p, int ldp,
   }
 }
 
+
+// =================================================================================================
+// Fast path: the same recursion in the LINEAR domain on the FP64 pipe.
+//   value  = double, kept in registers; a step is 2 DADD + 1 DMUL per state behind two 64-bit shuffles -
+//            no MUFU on the dependency chain (the log-space step above costs 3 SFU ops per state);
+//   range  = every 4 rows the row maximum is moved to 2^-16 by an exact power of two folded into the next row's
+//            probabilities (off the chain); the integer shifts accumulate in off[t], so alpha_t = a * 2^off[t];
+//   probs  = softmax values as "packed doubles": bits 61..30 of the IEEE double (10 exponent bits + 22 mantissa
+//            bits), one 32-bit word per (t, c): unpack = two shifts; 0 = exact zero;
+//   stored = alpha / beta rows in the same packed format (22-bit mantissa, |rel err| < 2.4e-7).
+// Linear fp64 can flush states that sit > ~2^-1000 below their row maximum; log space cannot.  Such a loss is
+// only relevant when the other recursion is correspondingly huge there, and then it shows: every row of
+// posteriors must sum to 1 (sum_s alpha_t(s) beta_t(s) / p_t(l_s) = Z for all t; flushing only ever removes mass)
+// and the beta-side likelihood must equal the alpha-side one.  A sequence failing either check (> 2e-5) is
+// recomputed by the log-space path above, so the result never depends on the fast path's range.
+// =================================================================================================
+constexpr int kFastRenorm = 4;
+constexpr int kFastTargetExp = 1023 - 16;
+
+__device__ __forceinline__ double unpack_pd(uint32_t w) { return __hiloint2double(static_cast<int>(w >> 2), static_cast<int>(w << 30)); }
+__device__ __forceinline__ uint32_t pack_pd(double v) {
+  const uint32_t hi = static_cast<uint32_t>(__double2hiint(v)), lo = static_cast<uint32_t>(__double2loint(v));
+  return __funnelshift_l(lo, hi, 2);        // bits 61..30 (values are in [0, 2): sign and exponent MSB are 0)
+}
+__device__ __forceinline__ double shfl_up_d(double v, int d) {
+  return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), d), __shfl_up_sync(0xffffffffu, __double2loint(v), d));
+}
+__device__ __forceinline__ double shfl_down_d(double v, int d) {
+  return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(v), d), __shfl_down_sync(0xffffffffu, __double2loint(v), d));
+}
+// exact 2^-sh as a double (|sh| < 1000)
+__device__ __forceinline__ double pow2_neg(int sh) { return __hiloint2double((1023 - sh) << 20, 0); }
+
+// shift (in binades) that moves the row maximum to 2^-16; 0 for an all-zero row
+template <int K>
+__device__ __forceinline__ int fast_row_shift(const double (&n)[K]) {
+  uint32_t m = static_cast<uint32_t>(__double2hiint(n[0]));
+#pragma unroll
+  for (int j = 1; j < K; ++j) m = max(m, static_cast<uint32_t>(__double2hiint(n[j])));
+  m = __reduce_max_sync(0xffffffffu, m);
+  return m == 0u ? 0 : static_cast<int>(m >> 20) - kFastTargetExp;
+}
+
+// explicit shared-state-space accesses (32-bit addresses): keeps the address arithmetic of the serial loops to
+// one add per access instead of the generic-pointer window conversions the compiler re-materialises under predicates
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void reds_add_u32(uint32_t a, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+// One recursion for both directions.  REV = false: alpha (time ascending, states s = lane*K + j).
+// REV = true: beta = the alpha recursion of the REVERSED label sequence run backwards in time; the lane's states
+// are r = S-1-s (S is odd, so r and s have the same parity) and rows are stored at their natural index s.
+// K is even: state parity == parity of j, so blank states (even) never carry the skip term - they cost one DADD +
+// one DMUL, label states DADD + DFMA (skip mask 0.0 / 1.0) + DMUL, and only ONE neighbour value crosses lanes.
+// pk_s: shared address of the packed probabilities [T][ldp] with column C == 0 (what out-of-range states read);
+// AB: row storage [T][SP] (shared address when SM, else a global pointer).
+template <int K, bool REV, bool SM>
+__device__ __forceinline__ void ctc_rec_fast(uint32_t pk_s, int ldp, int C, const int* __restrict__ ext, int S, int Tb,
+                                             uint32_t ab_s, uint32_t* ab_g, int SP, uint32_t off_s) {
+  static_assert((K & 1) == 0, "even K");
+  const int lane = threadIdx.x & 31;
+  double a[K], msk[K / 2];
+  uint32_t q[K], lo4[K];
+  bool valid[K];
+  const int row_step = REV ? -ldp * 4 : ldp * 4;
+  uint32_t prow = pk_s + (REV ? (Tb - 1) * ldp * 4 : 0);            // probabilities of the current row
+  const int t0 = REV ? Tb - 1 : 0;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int r = lane * K + j;
+    const int s = REV ? S - 1 - r : r;
+    valid[j] = r < S;
+    const int lab = valid[j] ? ext[s] : C;
+    lo4[j] = static_cast<uint32_t>(lab) * 4u;
+    if (j & 1) {
+      const int s2 = REV ? s + 2 : s - 2;                            // the state two steps "behind" in this direction
+      msk[j >> 1] = (valid[j] && r >= 3 && ext[s] != ext[s2]) ? 1.0 : 0.0;
+    }
+    a[j] = 0.0;
+    if (r == 0 || (r == 1 && S > 1)) a[j] = unpack_pd(lds32(prow + lo4[j]));
+  }
+  // store address of state j of row t: base + t*SP*4 + (REV ? S-1-r : r)*4
+  const int st_lane = (REV ? (S - 1 - lane * K) : lane * K) * 4;
+  const int st_row = (REV ? -SP : SP) * 4;
+  long long st = static_cast<long long>(t0) * SP * 4 + st_lane;       // byte offset of (row, state j = 0)
+  auto store_row = [&](const double (&v)[K]) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (valid[j]) {
+        const int o = REV ? -4 * j : 4 * j;
+        if (SM) sts32(ab_s + static_cast<uint32_t>(st) + o, pack_pd(v[j]));
+        else ab_g[(st + o) >> 2] = pack_pd(v[j]);
+      }
+    }
+  };
+  store_row(a);
+  int c = 0;
+  if (lane == 0) sts32(off_s + t0 * 4, 0u);
+  int sh = fast_row_shift<K>(a);
+  prow += row_step;
+  if (Tb > 1) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) q[j] = lds32(prow + lo4[j]);
+  }
+  for (int i = 1; i < Tb; ++i) {
+    const int t = REV ? Tb - 1 - i : i;
+    double pd[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) pd[j] = unpack_pd(q[j]);
+    if (sh != 0) {                                   // warp-uniform; exact power of two, off the dependency chain
+      const double sc = pow2_neg(sh);
+#pragma unroll
+      for (int j = 0; j < K; ++j) pd[j] *= sc;
+      c += sh;
+    }
+    if (lane == 0) sts32(off_s + t * 4, static_cast<uint32_t>(c));
+    double up1 = shfl_up_d(a[K - 1], 1);             // previous lane's last state
+    if (lane == 0) up1 = 0.0;
+    prow += row_step;
+    if (i + 1 < Tb) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) q[j] = lds32(prow + lo4[j]);
+    }
+    double n[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const double p1 = (j >= 1) ? a[j >= 1 ? j - 1 : 0] : up1;
+      if (j & 1) {
+        const double p2 = (j >= 2) ? a[j >= 2 ? j - 2 : 0] : up1;    // j == 1: two behind = previous lane's last state
+        n[j] = fma(msk[j >> 1], p2, a[j] + p1) * pd[j];
+      } else {
+        n[j] = (a[j] + p1) * pd[j];
+      }
+    }
+    st += st_row;
+    store_row(n);
+#pragma unroll
+    for (int j = 0; j < K; ++j) a[j] = n[j];
+    sh = ((i & (kFastRenorm - 1)) == 0) ? fast_row_shift<K>(n) : 0;
+  }
+}
+
+// packed word -> (mantissa float in [1, 2), exponent relative to 2^0); w != 0
+__device__ __forceinline__ float pk_mant(uint32_t w) { return __uint_as_float(0x3F800000u | ((w & 0x3FFFFFu) << 1)); }
+__device__ __forceinline__ int pk_exp(uint32_t w) { return static_cast<int>(w >> 22) - 1023; }
+// packed probability -> fp32 (flushes below 2^-126: only used for the softmax term of the gradient)
+__device__ __forceinline__ float pk_to_float(uint32_t w) {
+  const int e = static_cast<int>(w >> 22) - 896;          // fp32 biased exponent
+  return e > 0 ? __uint_as_float((static_cast<uint32_t>(e) << 23) | ((w & 0x3FFFFFu) << 1)) : 0.f;
+}
+
 struct CtcParams {
   const float* x;            // logits (or log-probs when is_logprob) [.., C] with strides below
   long long x_sb, x_st;      // element strides of the batch and time axes (class axis contiguous)
@@ -171,7 +331,7 @@ struct CtcParams {
   const float* grad_scale;   // [B] per-sample upstream gradient, or null
   float grad_scale_const;    // used when grad_scale == null
   float* scratch;            // global alpha/beta scratch when they do not fit in shared memory
-  int B, T, C, kmax, is_logprob, scratch_in_smem;
+  int B, T, C, kmax, is_logprob, scratch_in_smem, force_slow, dbg;
 };
 
 #define CTC_DISPATCH(FN, ...)                 \
@@ -191,21 +351,37 @@ struct CtcParams {
 
 __host__ __device__ inline int ctc_round_k(int k) { return k <= 9 ? k : (k <= 13 ? 13 : 17); }
 
+__device__ unsigned long long g_ctc_fallbacks = 0ull;
+__device__ long long g_ctc_stamps[16];                      // HTRVT_CTC_DEBUG=1: clock64 at the phase boundaries of CTA 0
+#define CTC_STAMP(i) do { if (P.dbg && b == 0 && (tid & 31) == 0) g_ctc_stamps[i] = clock64(); } while (0)      // sequences recomputed by the log-space path
+
+#define CTC_DISPATCH_FAST(REV, SM, ...)                                  \
+  switch (Kf) {                                                            \
+    case 2: ctc_rec_fast<2, REV, SM>(__VA_ARGS__); break;                  \
+    case 4: ctc_rec_fast<4, REV, SM>(__VA_ARGS__); break;                  \
+    case 6: ctc_rec_fast<6, REV, SM>(__VA_ARGS__); break;                  \
+    case 8: ctc_rec_fast<8, REV, SM>(__VA_ARGS__); break;                  \
+    case 10: ctc_rec_fast<10, REV, SM>(__VA_ARGS__); break;                \
+    case 12: ctc_rec_fast<12, REV, SM>(__VA_ARGS__); break;                \
+    default: ctc_rec_fast<14, REV, SM>(__VA_ARGS__); break;                \
+  }
+
 __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const CtcParams P) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kCtcThreads / 32;
   const int T = P.T, C = P.C;
-  const int ldp = C | 1;
+  const int ldp = (C + 1) | 1;                      // odd row stride with at least one pad column (column C)
 
-  float* l2p = smem;                               // [T][ldp] log2-domain log-probabilities
+  float* l2p = smem;                               // [T][ldp] log2-domain log-probabilities (fast path: packed doubles)
   float* post = l2p + T * ldp;                     // [NW][ldp] per-warp posterior row
   int* ext = reinterpret_cast<int*>(post + NW * ldp);   // [32*kmax] extended label sequence
   float* red = reinterpret_cast<float*>(ext + 32 * P.kmax);   // [40] reductions / broadcast
   double* offA = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(red + 40) + 7) & ~uintptr_t(7));         // [T] renormalisation offsets of alpha rows
   double* offB = offA + T;                                    // [T] ... of beta rows
   float* AB = reinterpret_cast<float*>(offB + T);  // alpha | beta when they fit in shared memory
+  volatile int& s_bad = *reinterpret_cast<volatile int*>(red + 36);   // fast path: "recompute in log space" flag
 
   // ---- per-sequence metadata -------------------------------------------------------------------
   int Tb = P.input_lengths ? P.input_lengths[b] : T;
@@ -228,10 +404,204 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
 
   const float* xb = P.x + static_cast<long long>(b) * P.x_sb;
   float* gb = P.grad ? P.grad + static_cast<long long>(b) * P.g_sb : nullptr;
+  const float gs = P.grad_scale ? P.grad_scale[b] : P.grad_scale_const;
 
+  if (tid == 0) s_bad = 0;
+  if (tid == 0) CTC_STAMP(0);
   if (fits) {
     for (int s = tid; s < SP; s += kCtcThreads) ext[s] = (s < S && (s & 1)) ? P.targets[toff + (s >> 1)] : 0;
   }
+  const bool run = fits && Tb > 0;
+
+  // =============================== fast path (linear domain, FP64 pipe) ===========================
+  const int Kf = ((S + 31) / 32 + 1) & ~1;             // even number of states per lane
+  if (run && Kf <= 14 && !P.force_slow) {
+    const uint32_t pk_s = smem_u32(l2p);
+    const uint32_t ab_s = smem_u32(AB);
+    uint32_t* Au = reinterpret_cast<uint32_t*>(A);
+    uint32_t* Bu = reinterpret_cast<uint32_t*>(Bt);
+    int* ioffA = reinterpret_cast<int*>(offA);
+    int* ioffB = reinterpret_cast<int*>(offB);
+    // ---- phase 0a: raw rows -> smem, every load of the CTA in flight at once --------------------
+    if (((C & 3) == 0) && ((P.x_st & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb) & 15) == 0)) {
+      const int C4 = C >> 2, n4 = Tb * C4;
+#pragma unroll 4
+      for (int i = tid; i < n4; i += kCtcThreads) {
+        const int t = i / C4, c = (i - t * C4) * 4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(xb + static_cast<long long>(t) * P.x_st + c));
+        const uint32_t a4 = pk_s + (t * ldp + c) * 4;
+        sts32(a4, __float_as_uint(v.x)); sts32(a4 + 4, __float_as_uint(v.y));
+        sts32(a4 + 8, __float_as_uint(v.z)); sts32(a4 + 12, __float_as_uint(v.w));
+      }
+    } else {
+      const int n = Tb * C;
+#pragma unroll 8
+      for (int i = tid; i < n; i += kCtcThreads) {
+        const int t = i / C, c = i - t * C;
+        sts32(pk_s + (t * ldp + c) * 4, __float_as_uint(__ldg(xb + static_cast<long long>(t) * P.x_st + c)));
+      }
+    }
+    __syncthreads();
+    if (tid == 0) CTC_STAMP(1);
+    // ---- phase 0b: 4 threads per row: softmax -> packed double ---------------------------------------
+    {
+      const int part = tid & 3;
+      bool oor = false;
+      for (int t0 = 0; t0 < Tb; t0 += kCtcThreads / 4) {       // uniform trip count: the shuffles need whole warps
+        const bool act = t0 + (tid >> 2) < Tb;
+        const int t = act ? t0 + (tid >> 2) : Tb - 1;
+        const uint32_t rowa = pk_s + t * ldp * 4;
+        float lse2 = 0.f;
+        if (!P.is_logprob) {
+          float mx = -INFINITY;
+#pragma unroll 5
+          for (int c = part; c < C; c += 4) mx = fmaxf(mx, __uint_as_float(lds32(rowa + c * 4)));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          float sum = 0.f;
+          const float mxl = mx * kLog2e;
+#pragma unroll 5
+          for (int c = part; c < C; c += 4) sum += ex2f(fmaf(__uint_as_float(lds32(rowa + c * 4)), kLog2e, -mxl));
+          sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+          sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+          lse2 = mx * kLog2e + lg2f(sum);
+        }
+        if (!act) continue;                                    // (a padding thread may have read a row mid-rewrite)
+#pragma unroll 5
+        for (int c = part; c < C; c += 4) {
+          const float l2 = __uint_as_float(lds32(rowa + c * 4)) * kLog2e - lse2;   // log2 p  (<= 0 up to rounding)
+          uint32_t w = 0u;
+          if (l2 > -1000.f) {
+            const float fl = floorf(l2);
+            const float m = fmaxf(ex2f(l2 - fl), 1.0f);      // [1, 2]
+            const int X = 1023 + static_cast<int>(fl);
+            w = (static_cast<uint32_t>(X) << 22) + ((__float_as_uint(m) - 0x3F800000u + 1u) >> 1);   // a carry bumps X
+            if (X > 1023) oor = true;                        // p > 1: only a malformed "log-prob" input gets here
+          } else if (l2 > -INFINITY || l2 != l2) {
+            oor = true;                                      // finite but below the packed range, or NaN
+          }
+          sts32(rowa + c * 4, w);
+        }
+        if (part == 0) sts32(rowa + C * 4, 0u);              // the zero column out-of-range states read
+      }
+      if (oor) s_bad = 1;
+    }
+    __syncthreads();
+    if (tid == 0) CTC_STAMP(2);
+    if (!s_bad) {
+      // ---- phase 1: alpha on warp 0, beta on warp 1, concurrently --------------------------------
+      if (warp == 0) {
+        if (P.scratch_in_smem) { CTC_DISPATCH_FAST(false, true, pk_s, ldp, C, ext, S, Tb, ab_s, Au, SP, smem_u32(ioffA)) }
+        else { CTC_DISPATCH_FAST(false, false, pk_s, ldp, C, ext, S, Tb, 0u, Au, SP, smem_u32(ioffA)) }
+        CTC_STAMP(3);
+      } else if (warp == 1) {
+        if (P.scratch_in_smem) { CTC_DISPATCH_FAST(true, true, pk_s, ldp, C, ext, S, Tb, ab_s + T * SP * 4, Bu, SP, smem_u32(ioffB)) }
+        else { CTC_DISPATCH_FAST(true, false, pk_s, ldp, C, ext, S, Tb, 0u, Bu, SP, smem_u32(ioffB)) }
+        CTC_STAMP(4);
+      }
+      if (!P.scratch_in_smem) __threadfence_block();
+      __syncthreads();
+      // ---- likelihood from both ends --------------------------------------------------------------
+      const double za = unpack_pd(Au[(Tb - 1) * SP + S - 1]) + (S > 1 ? unpack_pd(Au[(Tb - 1) * SP + S - 2]) : 0.0);
+      const double zb = unpack_pd(Bu[0]) + (S > 1 ? unpack_pd(Bu[1]) : 0.0);
+      const bool feasible = za > 0.0;
+      bool bad = (za > 0.0) != (zb > 0.0);
+      double ll2 = 0.0;
+      if (feasible && !bad) {
+        // log2 of a packed value: exponent + lg2 of the 22-bit mantissa (abs err ~2e-7 of a bit)
+        const uint32_t wa2 = pack_pd(za), wb2 = pack_pd(zb);
+        ll2 = static_cast<double>(pk_exp(wa2) + ioffA[Tb - 1]) + static_cast<double>(lg2f(pk_mant(wa2)));
+        const double ll2b = static_cast<double>(pk_exp(wb2) + ioffB[0]) + static_cast<double>(lg2f(pk_mant(wb2)));
+        bad = fabs(ll2 - ll2b) > 3.0e-5;
+      }
+      if (!bad && gb) {
+        // ---- phase 2: posterior collect (fixed point, integer smem atomics) + gradient rows -------
+        const uint32_t wz = feasible ? pack_pd(za) : 0u;
+        const float rz = feasible ? __fdividef(1.0f, pk_mant(wz)) : 0.f;
+        const int ez = feasible ? pk_exp(wz) + ioffA[Tb - 1] : 0;
+        const uint32_t pw_s = smem_u32(post + warp * ldp);
+        constexpr int kSU = 5;                                // states per lane handled with labels in registers
+        int labr[kSU];
+#pragma unroll
+        for (int i = 0; i < kSU; ++i) labr[i] = (lane + 32 * i < S) ? ext[lane + 32 * i] : 0;
+        for (int c = lane; c < C; c += 32) sts32(pw_s + c * 4, 0u);
+        __syncwarp();
+        for (int t = warp; t < T; t += NW) {
+          float* gr = gb + static_cast<long long>(t) * P.g_st;
+          if (t >= Tb || !feasible) {
+            for (int c = lane; c < C; c += 32) gr[c] = 0.f;
+            continue;
+          }
+          if (warp == 5 && t == 5) CTC_STAMP(7);
+          const uint32_t pr_s = pk_s + t * ldp * 4;
+          const uint32_t* ar = Au + t * SP;
+          const uint32_t* br = Bu + t * SP;
+          const int rowk = ioffA[t] + ioffB[t] - ez;
+          uint32_t blank = 0u, tot = 0u;
+          auto load_state = [&](int s, int c, uint32_t& wa, uint32_t& wb, uint32_t& wp) {
+            wa = P.scratch_in_smem ? lds32(ab_s + (t * SP + s) * 4) : ar[s];
+            wb = P.scratch_in_smem ? lds32(ab_s + ((T + t) * SP + s) * 4) : br[s];
+            wp = lds32(pr_s + c * 4);                          // != 0 wherever alpha is
+          };
+          auto add_state = [&](int s, int c, bool ok, uint32_t wa, uint32_t wb, uint32_t wp) {
+            const int k = pk_exp(wa) + pk_exp(wb) - pk_exp(wp) + rowk;
+            ok = ok && wa != 0u && wb != 0u && k >= -60;
+            if (ok && k > 4) s_bad = 1;                        // cannot happen with consistent rows
+            const int kc = min(max(k, -60), 4);
+            const float q = pk_mant(wa) * pk_mant(wb) * __fdividef(rz, pk_mant(wp));
+            // gamma * 2^30, k <= ~1: the scale 2^(k+30) is an exact fp32 power of two
+            const uint32_t u = ok ? __float2uint_rn(q * __uint_as_float(static_cast<uint32_t>(kc + 30 + 127) << 23)) : 0u;
+            tot += u;
+            if (s & 1) { if (u) reds_add_u32(pw_s + c * 4, u); }
+            else blank += u;
+          };
+          {
+            uint32_t wa[kSU], wb[kSU], wp[kSU];
+#pragma unroll
+            for (int i = 0; i < kSU; ++i) {                    // all loads first: the states are independent
+              const int s = min(lane + 32 * i, S - 1);
+              load_state(s, labr[i], wa[i], wb[i], wp[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < kSU; ++i) add_state(lane + 32 * i, labr[i], lane + 32 * i < S, wa[i], wb[i], wp[i]);
+          }
+          for (int s = lane + 32 * kSU; s < S; s += 32) {
+            uint32_t wa, wb, wp;
+            const int c = ext[s];
+            load_state(s, c, wa, wb, wp);
+            add_state(s, c, true, wa, wb, wp);
+          }
+          if (warp == 5 && t == 5) CTC_STAMP(8);
+          blank = __reduce_add_sync(0xffffffffu, blank);
+          tot = __reduce_add_sync(0xffffffffu, tot);
+          if (warp == 5 && t == 5) CTC_STAMP(9);
+          const int dev1 = static_cast<int>(tot) - (1 << 30);
+          if (dev1 > 21475 || dev1 < -21475) s_bad = 1;    // the row's posteriors do not sum to 1 (2e-5): mass was flushed
+          __syncwarp();
+          for (int c = lane; c < C; c += 32) {
+            const uint32_t pc = (c == 0) ? blank : lds32(pw_s + c * 4);
+            sts32(pw_s + c * 4, 0u);                         // ready for this warp's next row
+            gr[c] = (pk_to_float(lds32(pr_s + c * 4)) - static_cast<float>(pc) * 9.313225746154785e-10f) * gs;
+          }
+          __syncwarp();
+          if (warp == 5 && t == 5) CTC_STAMP(10);
+          if (warp == 5 && t == 21) CTC_STAMP(11);
+        }
+      }
+      if (warp == 5) CTC_STAMP(5);
+      if (bad) s_bad = 1;
+      __syncthreads();
+      if (tid == 0) CTC_STAMP(6);
+      if (!s_bad) {
+        if (tid == 0) P.nll[b] = feasible ? static_cast<float>(-ll2 * 0.6931471805599453) : 0.f;   // zero_infinity=True
+        return;
+      }
+    }
+    if (tid == 0) atomicAdd(&g_ctc_fallbacks, 1ull);
+    __syncthreads();
+  }
+
+  // =============================== log-space path ==================================================
   // ---- phase 0: stage log-softmax rows (log2 domain) ------------------------------------------
   for (int t = warp; t < Tb; t += NW) {
     const float* xr = xb + static_cast<long long>(t) * P.x_st;
@@ -264,7 +634,6 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
   __syncthreads();
 
   // ---- phase 1: alpha on warp 0, beta on warp 1, concurrently ---------------------------------
-  const bool run = fits && Tb > 0;
   if (run) {
     if (warp == 0) {
       CTC_DISPATCH(ctc_alpha, l2p, ldp, ext, S, Tb, A, offA)
@@ -296,7 +665,6 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
   if (!gb) return;
 
   // ---- phase 2: posterior collect + gradient rows ----------------------------------------------
-  const float gs = P.grad_scale ? P.grad_scale[b] : P.grad_scale_const;
   float* pw = post + warp * ldp;
   for (int t = warp; t < T; t += NW) {
     float* gr = gb + static_cast<long long>(t) * P.g_st;
@@ -330,7 +698,7 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
 // nll only (validation: model_v1/valid.py:36-38 needs no gradient) reuses the same kernel with grad == null.
 
 size_t ctc_smem_bytes(int T, int C, int kmax, bool scratch_in_smem) {
-  const int ldp = C | 1;
+  const int ldp = (C + 1) | 1;
   size_t words = static_cast<size_t>(T) * ldp + (kCtcThreads / 32) * ldp + 32 * kmax + 40 + 4 * T + 2;
   if (scratch_in_smem) words += static_cast<size_t>(2) * T * 32 * kmax;
   return words * 4;
@@ -345,6 +713,16 @@ extern "C" size_t htrvt_ctc_workspace_bytes(int B, int T, int C, int max_target_
   const int kmax = ctc_round_k((2 * lmax + 1 + 31) / 32);
   if (ctc_smem_bytes(T, C, kmax, true) <= 227 * 1024) return 0;
   return static_cast<size_t>(B) * 2 * T * 32 * kmax * sizeof(float);
+}
+
+// number of sequences the fast (linear fp64) path handed to the log-space path since the library was loaded
+extern "C" int htrvt_ctc_debug_stamps(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, g_ctc_stamps, sizeof(long long) * 16) == cudaSuccess ? HTRVT_OK : HTRVT_ERR_LAUNCH;
+}
+extern "C" long long htrvt_ctc_fallback_count(void) {
+  unsigned long long v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_ctc_fallbacks, sizeof(v)) != cudaSuccess) return -1;
+  return static_cast<long long>(v);
 }
 
 extern "C" int htrvt_ctc_loss_grad(const float* x, long long x_stride_b, long long x_stride_t, int is_logprob,
@@ -363,6 +741,10 @@ extern "C" int htrvt_ctc_loss_grad(const float* x, long long x_stride_b, long lo
   P.nll = nll; P.grad_scale = grad_scale; P.grad_scale_const = grad_scale_const;
   P.B = B; P.T = T; P.C = C; P.is_logprob = is_logprob;
   P.kmax = ctc_round_k((2 * lmax + 1 + 31) / 32);
+  static const int force_slow = (getenv("HTRVT_CTC_SLOW") && atoi(getenv("HTRVT_CTC_SLOW")) != 0) ? 1 : 0;
+  P.force_slow = force_slow;
+  static const int dbg = getenv("HTRVT_CTC_DEBUG") ? 1 : 0;
+  P.dbg = dbg;   // developer knob: run the log-space path only
   P.scratch_in_smem = ctc_smem_bytes(T, C, P.kmax, true) <= 227 * 1024 ? 1 : 0;
   P.scratch = static_cast<float*>(workspace);
   const size_t smem = ctc_smem_bytes(T, C, P.kmax, P.scratch_in_smem);

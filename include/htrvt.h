@@ -40,6 +40,10 @@ int htrvt_ctc_loss_grad(const float* x, long long x_stride_b, long long x_stride
                         int B, int T, int C, int max_target_len, float* nll, float* grad, long long g_stride_b,
                         long long g_stride_t, const float* grad_scale, float grad_scale_const, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* The recursion runs in the linear domain on the FP64 pipe; a sequence whose posterior rows fail the
+ * sum-to-one / two-sided-likelihood checks (a state flushed below the fp64 range that log space would have kept)
+ * is recomputed in log space inside the same launch.  This counts those sequences (synchronous read). */
+long long htrvt_ctc_fallback_count(void);
 
 /* ---- greedy CTC decode ---------------------------------------------------------------------------------
  * htrvt_greedy_decode replaces `preds.max(2)` + transpose (model_v1/valid.py:40-41) AND the filtering loop of

@@ -89,6 +89,62 @@ def test_ctc_full_size_properties(B, T, C, lo, hi):
     np.testing.assert_allclose(x2.grad.cpu().numpy(), gr, rtol=1e-5, atol=1e-7)
 
 
+def _fallbacks():
+    from importlib import import_module
+    return import_module("htr-vt_b200._lib").lib().htrvt_ctc_fallback_count()
+
+
+def test_ctc_fast_path_is_taken_and_fallback_is_exact():
+    """The linear-domain fp64 recursion serves ordinary inputs; confidently-wrong logits (within-row spreads far
+    beyond the fp64 range, which log space keeps) must be detected and recomputed in log space - same numbers."""
+    h = _pkg()
+    rs = np.random.RandomState(7)
+    B, T, C = 16, 128, 80
+    tl = rs.randint(20, 60, size=B).astype(np.int32)
+    tg = rs.randint(1, C, size=int(tl.sum())).astype(np.int32)
+    il = np.full(B, T, dtype=np.int32)
+    # (a) ordinary and moderately peaked logits: no fallback
+    for scale in (1.0, 8.0):
+        logits = (rs.randn(B, T, C) * scale).astype(np.float32)
+        n0 = _fallbacks()
+        x = torch.from_numpy(logits).cuda().requires_grad_(True)
+        nll = h.ctc_loss_from_logits(x, torch.from_numpy(tg).cuda(), torch.from_numpy(tl))
+        nll.sum().backward()
+        torch.cuda.synchronize()
+        assert _fallbacks() == n0, scale
+        ref_nll, ref_grad = _ctc_ref64(logits, tg, il, tl)
+        np.testing.assert_allclose(nll.detach().cpu().numpy(), ref_nll, rtol=1e-4)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), ref_grad, rtol=1e-4, atol=1e-5)
+    # (b) a "trained, confident" network: the labels' own alignment gets +25 logits (fast path, huge dynamic range
+    # between on-path and off-path states, none of it relevant), then the same network on WRONG labels
+    logits = rs.randn(B, T, C).astype(np.float32)
+    pos = 0
+    for b in range(B):
+        lab = tg[pos:pos + tl[b]]
+        pos += tl[b]
+        frames = np.sort(rs.choice(T, size=tl[b], replace=False))
+        logits[b, :, 0] += 25.0
+        for f, c in zip(frames, lab):
+            logits[b, f, 0] -= 25.0
+            logits[b, f, c] += 25.0
+    wrong = ((tg + rs.randint(1, C - 1, size=tg.shape)) % (C - 1) + 1).astype(np.int32)
+    # (labels, logit scale, fallback expected?, grad atol).  x4 = +-100 logits on wrong labels: |log p| ~ 1e4, where
+    # the log-space path itself (fp32, like ATen's) resolves ~3e-4; the fast path must hand such rows over.
+    for labels, scale, expect_fallback, atol in ((tg, 1.0, False, 1e-5), (wrong, 1.0, None, 1e-5),
+                                                 (wrong, 2.0, None, 2e-5), (wrong, 4.0, True, 5e-4)):
+        lg = (logits * scale).astype(np.float32)
+        n0 = _fallbacks()
+        x = torch.from_numpy(lg).cuda().requires_grad_(True)
+        nll = h.ctc_loss_from_logits(x, torch.from_numpy(labels).cuda(), torch.from_numpy(tl))
+        nll.sum().backward()
+        torch.cuda.synchronize()
+        if expect_fallback is not None:
+            assert (_fallbacks() > n0) == expect_fallback, scale
+        ref_nll, ref_grad = _ctc_ref64(lg, labels, il, tl)
+        np.testing.assert_allclose(nll.detach().cpu().numpy(), ref_nll, rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(x.grad.cpu().numpy(), ref_grad, rtol=1e-4, atol=atol)
+
+
 def test_decode_golden_strings():
     h = _pkg()
     g = np.load(os.path.join(G, "decode_cases.npz"))
