@@ -282,6 +282,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= 2ull << 61;                       // SWIZZLE_128B
   return d;
 }
+// MN-major tile under SWIZZLE_64B: 32 MN elements = 64 B contiguous per K index, 8 K-rows per 512-B atom:
+//      SBO = 512 B (next 8 K indices), LBO = byte distance between 32-wide MN atoms.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 4ull << 61;                       // SWIZZLE_64B
+  return d;
+}
 // Instruction descriptor: bf16 x bf16 -> fp32, M x N tile, operand major-ness (0 = K, 1 = MN).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) |

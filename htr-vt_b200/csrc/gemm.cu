@@ -3,7 +3,10 @@
 //              implements conv padding, ragged tiles and K tails
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16, bf16 -> fp32 in TMEM)
 // KIND: 0 = rows are output pixels (linear / conv fwd, dgrad); 1 = weight gradient, both operands pixel-major
-// (MN-major); 2 = weight gradient with a K-major dY^T operand (tcgen05 runs ~1.4x slower with an MN-major A).
+// (MN-major); 2 = weight gradient with a K-major dY^T operand (tcgen05 runs ~1.4x slower with an MN-major A);
+// 3 = weight gradient transposed: rows = (tap, 64-channel atom of x) - every 64-row half of a tile carries its own
+// tap shift, so no rows are wasted when Cout is not a multiple of 128 - columns = Cout; when a CTA of a pair stages
+// 96 columns the B operand uses SWIZZLE_64B (32-column atoms).
 //   warps 2-9: epilogue (tcgen05.ld 32x32b, two warps per TMEM lane quadrant), double-buffered
 //              accumulator so the epilogue of tile i overlaps the main loop of tile i+1
 // Operands can be K-major or MN-major (smem descriptor + instruction-descriptor major bits), which is
@@ -83,7 +86,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmP P) {
   using Cfg = GemmCfg<BN, CL>;
-  constexpr bool A_MN = (KIND == 1);
+  constexpr bool A_MN = (KIND == 1 || KIND == 3);
+  constexpr bool B_SW64 = B_MN && ((BN / CL) % 64) != 0;     // a 96-column half: 32-column atoms, SWIZZLE_64B
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment
   if (smem_u32(smem) & 1023u) __trap();
@@ -127,6 +131,30 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const TileCoord tc = decode_tile(P, id);
         const int n0 = tc.n_tile * BN, m0 = tc.m_tile * kBM;
         const int kiters = (KIND == 0) ? P.n_taps * P.k_chunks : (tc.q_end - tc.q_begin);
+        // running coordinates of the K loop (this one thread feeds the tensor pipe: no divisions per iteration)
+        int tap = 0, cc = 0;                                  // KIND 0: tap and 64-channel chunk
+        int wq = 0, ho = 0, n = 0;                            // KIND != 0: 64-pixel chunk of image row (n, ho)
+        if (KIND != 0) {
+          const int row = tc.q_begin / P.k_chunks;
+          wq = tc.q_begin - row * P.k_chunks;
+          n = row / P.Ho;
+          ho = row - n * P.Ho;
+        }
+        // KIND 3: the tap window of each 64-channel half of the A tile is fixed per tile
+        int a_c0[kBM / 64], a_pw[kBM / 64], a_dw[kBM / 64], a_dh[kBM / 64];
+        bool a_ok[kBM / 64];
+        if (KIND == 3) {
+#pragma unroll
+          for (int i = 0; i < kBM / 64; ++i) {
+            const int atom = tc.m_tile * (kBM / 64) + i;
+            const int t = atom / P.a_atoms_per_tap;
+            a_ok[i] = t < P.a_taps;
+            a_c0[i] = (atom - t * P.a_atoms_per_tap) * 64;
+            a_pw[i] = a_ok[i] ? P.tap.pw[t] : 0;
+            a_dw[i] = a_ok[i] ? P.tap.dw[t] : 0;
+            a_dh[i] = a_ok[i] ? P.tap.dh[t] : 0;
+          }
+        }
         for (int k = 0; k < kiters; ++k) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
@@ -141,7 +169,6 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           constexpr int BNL = BN / CL;                    // B columns staged by this CTA
           const int nb0 = n0 + crank * BNL;
           if (KIND == 0) {
-            const int tap = k / P.k_chunks, cc = k - tap * P.k_chunks;
             load(sa, &tmA, cc * kBK, P.tap.pw[tap], tc.w0 + P.tap.dw[tap], tc.h * P.a_sh + P.tap.dh[tap], tc.n);
             if (!B_MN) {
               load(sb, &tmB, P.tap.widx[tap] * P.b_tap_stride + cc * kBK, nb0, 0, 0, 0);
@@ -150,20 +177,35 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < BNL / 64; ++i)
                 load(sb + i * 8192, &tmB, P.tap.widx[tap] * P.b_tap_stride + nb0 + 64 * i, cc * kBK, 0, 0, 0);
             }
+            if (++cc == P.k_chunks) { cc = 0; ++tap; }
           } else {
-            const int q = tc.q_begin + k;
-            const int row = q / P.k_chunks, w0c = (q - row * P.k_chunks) * kBK;
-            const int n = row / P.Ho, ho = row - n * P.Ho;
-            if (KIND == 1) {
+            const int w0c = wq * kBK;
+            if (KIND == 3) {
+              // A: two 64-channel atoms of the shifted activation, each with its own tap; B: dY, unshifted
 #pragma unroll
-              for (int i = 0; i < kBM / 64; ++i) load(sa + i * 8192, &tmA, m0 + 64 * i, 0, w0c, ho, n);
-            } else {            // KIND 2: dY^T [n][ho][C][Wo] - pixels contiguous, a plain K-major tile
-              load(sa, &tmA, w0c, m0, ho, n, 0);
+              for (int i = 0; i < kBM / 64; ++i)
+                load(sa + i * 8192, &tmA, a_c0[i], a_pw[i], w0c + a_dw[i], ho * P.a_sh + a_dh[i],
+                     a_ok[i] ? n : P.NB);                     // past the last tap: an all-OOB box = zeros
+              if (B_SW64) {
+#pragma unroll
+                for (int i = 0; i < BNL / 32; ++i) load(sb + i * 4096, &tmB, nb0 + 32 * i, 0, w0c, ho, n);
+              } else {
+#pragma unroll
+                for (int i = 0; i < BNL / 64; ++i) load(sb + i * 8192, &tmB, nb0 + 64 * i, 0, w0c, ho, n);
+              }
+            } else {
+              if (KIND == 1) {
+#pragma unroll
+                for (int i = 0; i < kBM / 64; ++i) load(sa + i * 8192, &tmA, m0 + 64 * i, 0, w0c, ho, n);
+              } else {            // KIND 2: dY^T [n][ho][C][Wo] - pixels contiguous, a plain K-major tile
+                load(sa, &tmA, w0c, m0, ho, n, 0);
+              }
+#pragma unroll
+              for (int i = 0; i < BNL / 64; ++i)
+                load(sb + i * 8192, &tmB, nb0 + 64 * i, P.tap.pw[tc.tap], w0c + P.tap.dw[tc.tap],
+                     ho * P.a_sh + P.tap.dh[tc.tap], n);
             }
-#pragma unroll
-            for (int i = 0; i < BNL / 64; ++i)
-              load(sb + i * 8192, &tmB, nb0 + 64 * i, P.tap.pw[tc.tap], w0c + P.tap.dw[tc.tap],
-                   ho * P.a_sh + P.tap.dh[tc.tap], n);
+            if (++wq == P.k_chunks) { wq = 0; if (++ho == P.Ho) { ho = 0; ++n; } }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -190,8 +232,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kk = 0; kk < kBK / 16; ++kk) {
             const uint64_t da = A_MN ? umma_desc_sw128(sa + kk * 2048, 8192, 1024)
                                      : umma_desc_sw128(sa + kk * 32, 16, 1024);
-            const uint64_t db = B_MN ? umma_desc_sw128(sb + kk * 2048, 8192, 1024)
-                                     : umma_desc_sw128(sb + kk * 32, 16, 1024);
+            const uint64_t db = B_SW64 ? umma_desc_sw64(sb + kk * 1024, 4096, 512)
+                                : B_MN ? umma_desc_sw128(sb + kk * 2048, 8192, 1024)
+                                       : umma_desc_sw128(sb + kk * 32, 16, 1024);
             if (CL == 2) umma_bf16_pair(d_tmem, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
             else umma_bf16(d_tmem, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
           }
@@ -422,12 +465,13 @@ int make_map_matrix(CUtensorMap* m, const void* ptr, long long rows, long long c
 }
 
 // NHWC activation [N, H, W, C] viewed as (C, sw, W/sw, H, N): horizontal stride folded into a parity dim
-int make_map_act(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int sw, int box_c, int box_w) {
+int make_map_act(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int sw, int box_c, int box_w,
+                 bool swizzle64 = false) {
   const long long dims[5] = {C, sw, W / sw, H, N};
   const long long st[4] = {C, static_cast<long long>(C) * sw, static_cast<long long>(C) * W,
                            static_cast<long long>(C) * W * H};
   const int box[5] = {box_c, 1, box_w, 1, 1};
-  return make_map5(m, ptr, dims, st, box);
+  return make_map5(m, ptr, dims, st, box, 2, swizzle64);      // (the "output" flavour of make_map5 = SWIZZLE_64B)
 }
 
 // Output map of a kind-0 GEMM: (cols, w, h, n, 1) with element strides (s_w, s_h, s_n); box = 64 bytes x 32 rows
@@ -855,7 +899,54 @@ extern "C" int htrvt_conv_wgrad_acc(const void* dy, const void* dy_t, const void
   return conv_wgrad_impl(dy, dy_t, x, NB, H, W, Cin, Cout, ks, sh, sw, nullptr, 1, grad_tapmajor, nullptr, 0, stream);
 }
 
-// dst_oihw[i] += permute(src_tapmajor[i]) for n <= 64 conv weights per launch: [Cout][taps][Cin] -> [Cout][Cin][taps]
+// Transposed weight gradient: grad_tco[taps][Cin][Cout] (fp32) += x_shifted^T dy.  The GEMM's M axis is the flattened
+// (tap, input channel) index in 64-channel atoms - each half tile loads its own tap window - and N = Cout, so Cout =
+// 192 / 384 waste no MMA rows and every shape runs as cta_group::2 pairs (a 96-column half of dY is staged as three
+// 32-column SWIZZLE_64B atoms).  Split-K slices reduce-add in place.
+extern "C" int htrvt_conv_wgrad_acc_t(const void* dy, const void* x, int NB, int H, int W, int Cin, int Cout, int ks,
+                                      int sh, int sw, float* grad_tco, cudaStream_t stream) {
+  const int pad = ks / 2;
+  if (!dy || !x || !grad_tco || (Cout % 8) || (Cin % 64) || (W % sw) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
+  const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
+  const int bn = pick_bn(Cout);
+  GemmP P = {};
+  fill_taps_conv(P.tap, ks, pad, sw, &P.a_taps);
+  P.a_atoms_per_tap = Cin / 64;
+  const int atoms = P.a_taps * P.a_atoms_per_tap;
+  int tiles_m = (atoms + 1) / 2;
+  // pairs whose halves are 96 columns (three SWIZZLE_64B atoms) are correct but measured ~5 % SLOWER than the single-CTA
+  // SWIZZLE_128B kernel on the 192/384-channel layers: opt-in (HTRVT_SW64=1), halves of 64 / 128 columns pair up
+  static const int nopair = dbg_env("HTRVT_NOPAIR"), sw64_ok = dbg_env("HTRVT_SW64");
+  const int cl = (!nopair && atoms >= 3 && (((bn / 2) % 64) == 0 || (sw64_ok && ((bn / 2) % 32) == 0))) ? 2 : 1;
+  if (cl == 2) tiles_m = (tiles_m + 1) & ~1;
+  const bool sw64 = cl == 2 && ((bn / 2) % 64) != 0;
+  CUtensorMap ta, tb, tc;
+  int r = make_map_act(&ta, x, NB, H, W, Cin, sw, 64, 64);
+  if (r) return r;
+  r = make_map_act(&tb, dy, NB, Ho, Wo, Cout, 1, sw64 ? 32 : 64, 64, sw64);
+  if (r) return r;
+  {
+    const long long rows = static_cast<long long>(P.a_taps) * Cin;
+    const long long dims[5] = {Cout, rows, 1, 1, 1};
+    const long long big = rows * Cout;
+    const long long st[4] = {Cout, big, big, big};
+    const int box[5] = {16, 32, 1, 1, 1};
+    r = make_map5(&tc, grad_tco, dims, st, box, 4, true);
+    if (r) return r;
+  }
+  P.kind = 3; P.Wo = Wo; P.Ho = Ho; P.NB = NB; P.tiles_per_row = 1;
+  P.tiles_m = tiles_m; P.tiles_n = (Cout + bn - 1) / bn; P.n_taps = 1;
+  P.k_chunks = (Wo + 63) / 64; P.a_sh = sh;
+  const long long Q = static_cast<long long>(NB) * Ho * P.k_chunks;
+  const long long per = static_cast<long long>(Cout) * P.a_taps * Cin;
+  P.splits = choose_splits(P.tiles_m * P.tiles_n, Q, per / 2);
+  P.M_valid = P.a_taps * Cin; P.N_valid = Cout; P.alpha = 1.f;
+  P.flags = EPI_ACCUM | (dbg_env("HTRVT_DBG_WGRAD_NOSTORE") ? EPI_NOSTORE : 0);
+  return launch_bn<3, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.splits, stream);
+}
+
+// dst_oihw[i] += permute(src[i]) for n <= 64 conv weights per launch: taps[i] > 0: src [Cout][taps][Cin];
+// taps[i] < 0: src [|taps|][Cin][Cout] (the transposed weight-gradient GEMM)
 namespace htrvt {
 constexpr int kMaxUnpack = 64;
 struct UnpackTable {
@@ -872,6 +963,27 @@ __global__ void __launch_bounds__(256) unpack_conv_grads_kernel(const __grid_con
   float* __restrict__ dst = T.dst[t];
   const long long n = T.numel[t];
   const int Cin = T.cin[t], taps = T.taps[t];
+  if (taps < 0) {
+    // src [tp][Cin][Cout] (htrvt_conv_wgrad_acc_t) -> dst [Cout][Cin][tp]: tiles of 8 co x 64 ci x tp taps through
+    // smem - 32-byte read segments along co, contiguous RMW of 64 * tp floats per output channel
+    const int tp = -taps, per = Cin * tp;
+    const int Cout = static_cast<int>(n / per);
+    const int tiles_ci = Cin / 64, tiles = (Cout / 8) * tiles_ci, cnt = tp * 64 * 8;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int co0 = (tile / tiles_ci) * 8, ci0 = (tile % tiles_ci) * 64;
+      __syncthreads();
+      for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int co = i & 7, ci = (i >> 3) & 63, tap = i >> 9;
+        up_stage[(tap * 64 + ci) * 9 + co] = src[(static_cast<long long>(tap) * Cin + ci0 + ci) * Cout + co0 + co];
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int tap = i % tp, r = i / tp, ci = r & 63, co = r >> 6;
+        dst[static_cast<long long>(co0 + co) * per + (ci0 + ci) * tp + tap] += up_stage[(tap * 64 + ci) * 9 + co];
+      }
+    }
+    return;
+  }
   const int per = Cin * taps;
   const int Cout = static_cast<int>(n / per);
   // per output channel a [taps][Cin] -> [Cin][taps] transpose through smem: contiguous read, contiguous RMW
@@ -898,11 +1010,13 @@ extern "C" int htrvt_unpack_conv_grads(int n, const void* const* src, void* cons
       T.numel[i] = numel[base + i];
       T.cin[i] = cin[base + i];
       T.taps[i] = taps[base + i];
-      if (T.cin[i] <= 0 || T.taps[i] <= 0) return HTRVT_ERR_SHAPE;
+      if (T.cin[i] <= 0 || T.taps[i] == 0 || (T.taps[i] < 0 && (T.cin[i] % 64))) return HTRVT_ERR_SHAPE;
     }
     int smem = 0;
-    for (int i = 0; i < cnt; ++i)
-      if (T.cin[i] * T.taps[i] * 4 > smem) smem = T.cin[i] * T.taps[i] * 4;
+    for (int i = 0; i < cnt; ++i) {
+      const int need = T.taps[i] > 0 ? T.cin[i] * T.taps[i] * 4 : -T.taps[i] * 64 * 9 * 4;
+      if (need > smem) smem = need;
+    }
     if (smem > 48 * 1024) return HTRVT_ERR_SHAPE;
     dim3 grid(148, cnt);
     unpack_conv_grads_kernel<<<grid, 256, smem, stream>>>(T);

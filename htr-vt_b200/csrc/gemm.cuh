@@ -21,7 +21,7 @@ enum : int {
 };
 
 struct GemmP {
-  int kind;                // 0: rows = output pixels, K = taps x channels; 1: wgrad (K = pixels)
+  int kind;                // 0: rows = output pixels, K = taps x channels; 1 / 2 / 3: wgrad (K = pixels)
   int Wo, Ho, NB;          // output pixel grid (kind 0) / dY pixel grid (kind 1)
   int tiles_per_row;       // kind 0: ceil(Wo / 128)
   int tiles_m, tiles_n, n_taps, splits;
@@ -30,6 +30,7 @@ struct GemmP {
   int b_tap_stride;        // kind 0: K (K-major B) or N (MN-major B) elements per tap in the weight matrix
   TapTab tap;
   int M_valid, N_valid;    // kind 1: rows (Cout) valid; columns valid
+  int a_taps, a_atoms_per_tap;   // KIND 3: the M axis is (tap, 64-channel atom of x): real tap count, Cin / 64
   int flags;
   const float* bias;
   float* stats;

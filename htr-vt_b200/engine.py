@@ -280,14 +280,20 @@ class Engine(object):
         g = ops.pool_bwd(dtok.view(B, 1, T, D), ctx.idx2, ctx.l3_shape)
 
         # ---- stem blocks ------------------------------------------------------------------------
-        # conv weight gradients accumulate tap-major ([Cout, taps, Cin]: the GEMM's natural output, split-K slices
-        # reduce-add in place) in one zeroed buffer and are permuted into the OIHW .grad tensors by ONE launch
+        # conv weight gradients accumulate in the GEMM's natural output layout (split-K slices reduce-add in place) in
+        # one zeroed buffer and are permuted into the OIHW .grad tensors by ONE launch.  Cout a multiple of 128:
+        # [Cout, taps, Cin] (rows = Cout); otherwise (192-channel layers) the transposed GEMM, [taps, Cin, Cout],
+        # whose rows = (tap, 64-channel atom) waste no MMA rows
         cnames = [k for k in wp if k.startswith("patch_embed.")]
         gt_flat = torch.zeros(sum(wp[k].numel() for k in cnames), dtype=torch.float32, device=dev)
         gt, off = {}, 0
         for k in cnames:
-            gt[k] = gt_flat[off:off + wp[k].numel()].view(wp[k].shape)
+            co, tp, ci = wp[k].shape
+            gt[k] = gt_flat[off:off + wp[k].numel()].view((tp, ci, co) if (co % 128) else (co, tp, ci))
             off += wp[k].numel()
+
+        def wgrad(dy, x, ks, sh, sw, name):
+            (ops.conv_wgrad_acc_t if (wp[name].shape[0] % 128) else ops.conv_wgrad_acc)(dy, x, ks, sh, sw, gt[name])
         for (p, s, xin, r1, sa, a1, k1, r2, sb, rd, sdn, k2) in reversed(ctx.blocks):
             has_ds = rd is not None
             d2, dd, gz = ops.bn_bwd(
@@ -295,22 +301,23 @@ class Engine(object):
                 raw_b=rd, st_b=sdn, gamma_b=sd[p + ".downsample.1.weight"] if has_ds else None,
                 dgamma_b=grads[p + ".downsample.1.weight"] if has_ds else None,
                 dbeta_b=grads[p + ".downsample.1.bias"] if has_ds else None, want_gz=not has_ds)
-            ops.conv_wgrad_acc(d2, a1, 3, 1, 1, gt[p + ".conv2.weight"])
+            wgrad(d2, a1, 3, 1, 1, p + ".conv2.weight")
             da1 = ops.conv_dgrad(d2, wp[p + ".conv2.weight"], tuple(a1.shape), 3, 1, 1, w_t=wp.get("T:" + p + ".conv2.weight"))
             d1, _, _ = ops.bn_bwd(da1, k1, r1, sa, sd[p + ".bn1.weight"], grads[p + ".bn1.weight"],
                                   grads[p + ".bn1.bias"])
-            ops.conv_wgrad_acc(d1, xin, 3, s[0], s[1], gt[p + ".conv1.weight"])
+            wgrad(d1, xin, 3, s[0], s[1], p + ".conv1.weight")
             if has_ds:
                 gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1],
                                      w_t=wp.get("T:" + p + ".conv1.weight"))
-                ops.conv_wgrad_acc(dd, xin, 1, s[0], s[1], gt[p + ".downsample.0.weight"])
+                wgrad(dd, xin, 1, s[0], s[1], p + ".downsample.0.weight")
                 ops.conv_dgrad(dd, wp[p + ".downsample.0.weight"], tuple(xin.shape), 1, s[0], s[1], dx=gin,
                                accumulate=True, w_t=wp.get("T:" + p + ".downsample.0.weight"))
             else:
                 gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1], dx=gz,
                                      accumulate=True, w_t=wp.get("T:" + p + ".conv1.weight"))
             g = gin
-        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames])
+        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames if wp[k].shape[0] % 128], transposed=True)
+        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames if not (wp[k].shape[0] % 128)])
         # ---- stem head: pool -> relu -> bn1 -> conv1 ---------------------------------------------
         if ctx.moments is None:
             raise ops.HtrvtError("backward needs a train-mode forward (batch statistics)")

@@ -86,8 +86,19 @@ def conv_wgrad_acc(dy, x, ks, sh, sw, grad_tapmajor):
     return grad_tapmajor
 
 
-def unpack_conv_grads(pairs):
-    """pairs: list of (src fp32 [Cout, taps, Cin], dst fp32 OIHW): dst += permute(src), one launch for all."""
+def conv_wgrad_acc_t(dy, x, ks, sh, sw, grad_tco):
+    """grad_tco fp32 [ks*ks, Cin, Cout] += x_shifted^T dy (transposed weight-gradient GEMM, CTA pairs for every shape)."""
+    _need_cuda(dy, x, grad_tco)
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    check(lib().htrvt_conv_wgrad_acc_t(_p(dy), _p(x), N, H, W, Cin, Cout, ks, sh, sw, _p(grad_tco), _stream()),
+          "htrvt_conv_wgrad_acc_t")
+    return grad_tco
+
+
+def unpack_conv_grads(pairs, transposed=False):
+    """pairs: list of (src, dst fp32 OIHW): dst += permute(src), one launch for all.
+    src fp32 [Cout, taps, Cin] (conv_wgrad_acc) or, transposed=True, [taps, Cin, Cout] (conv_wgrad_acc_t)."""
     n = len(pairs)
     if n == 0:
         return
@@ -98,7 +109,10 @@ def unpack_conv_grads(pairs):
     taps = (ctypes.c_int * n)()
     for i, (a, b) in enumerate(pairs):
         src[i], dst[i], numel[i] = a.data_ptr(), b.data_ptr(), b.numel()
-        cin[i], taps[i] = a.shape[2], a.shape[1]
+        if transposed:
+            cin[i], taps[i] = a.shape[1], -a.shape[0]
+        else:
+            cin[i], taps[i] = a.shape[2], a.shape[1]
     check(lib().htrvt_unpack_conv_grads(n, src, dst, numel, cin, taps, _stream()), "htrvt_unpack_conv_grads")
 
 
@@ -583,7 +597,7 @@ def _flops(name, a, kw):
         if name == "conv_dgrad":
             dy, w, xs, ks = a[:4]
             return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * xs[3]
-        if name == "conv_wgrad_acc":
+        if name in ("conv_wgrad_acc", "conv_wgrad_acc_t"):
             dy, x, ks = a[:3]
             return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * x.shape[3]
         if name == "conv_wgrad":
@@ -609,7 +623,7 @@ def _flops(name, a, kw):
 def _instrument():
     import functools
     g = globals()
-    names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc", "unpack_conv_grads", "attention_fwd",
+    names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc", "conv_wgrad_acc_t", "unpack_conv_grads", "attention_fwd",
              "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd",
              "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16", "dropout_",
              "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",

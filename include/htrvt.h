@@ -84,6 +84,11 @@ int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x, int NB, in
  * reduce kernel; htrvt_unpack_conv_grads then adds all tap-major gradients of a step into the OIHW parameters' .grad */
 int htrvt_conv_wgrad_acc(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin, int Cout,
                          int ks, int sh, int sw, float* grad_tapmajor, void* stream);
+/* the same contraction transposed: grad_tco fp32 [ks*ks][Cin][Cout] (+=); rows of the GEMM = (tap, input channel),
+ * columns = Cout: no padded MMA rows for Cout = 192 / 384 and CTA pairs for every shape (Cin % 64 == 0).
+ * htrvt_unpack_conv_grads takes this layout with taps[i] = -(ks*ks). */
+int htrvt_conv_wgrad_acc_t(const void* dy, const void* x, int NB, int H, int W, int Cin, int Cout, int ks, int sh,
+                           int sw, float* grad_tco, void* stream);
 int htrvt_unpack_conv_grads(int n, const void* const* src_tapmajor, void* const* dst_oihw, const long long* numel,
                             const int* cin, const int* taps, void* stream);
 /* bf16 [R][P][C] -> [R][C][P]: pixel-contiguous copy of a stem gradient (dy_t above; tcgen05 runs an MN-major A

@@ -144,6 +144,14 @@ def test_conv_fwd_dgrad_wgrad(NB, H, W, Cin, Cout, ks, sh, sw):
     assert torch.equal(packed[1], wt)
     dx2 = o.conv_dgrad(dy, wk, (NB, H, W, Cin), ks, sh, sw, w_t=wt)
     assert _rel(dx2.permute(0, 3, 1, 2), xr.grad) < 1e-2
+    # transposed weight-gradient GEMM ([taps, Cin, Cout] output, (tap, channel-atom) rows, CTA pairs / SWIZZLE_64B
+    # dY halves) + the one-launch unpack into OIHW (accumulating)
+    gt = torch.zeros(ks * ks, Cin, Cout, device="cuda")
+    o.conv_wgrad_acc_t(dy, x, ks, sh, sw, gt)
+    assert _rel(gt.permute(2, 1, 0).reshape(Cout, Cin, ks, ks), wr.grad) < 1e-3
+    gw2 = torch.ones(Cout, Cin, ks, ks, device="cuda")
+    o.unpack_conv_grads([(gt, gw2)], transposed=True)
+    assert _rel(gw2 - 1.0, wr.grad) < 1e-3
     gw = torch.zeros(Cout, Cin, ks, ks, device="cuda")
     o.conv_wgrad(dy, x, ks, sh, sw, gw, accumulate=False, transpose=True)      # K-major dY^T operand (transpose_px)
     assert _rel(gw, wr.grad) < 1e-3
