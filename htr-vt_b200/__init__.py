@@ -12,5 +12,7 @@ root) or with importlib.import_module("htr-vt_b200").
 from . import _lib  # noqa: F401
 from .ctc import CTCLoss, ctc_loss_from_logits, greedy_decode  # noqa: F401
 from .converter import CTCLabelConverter  # noqa: F401
+from .metrics import ErrorRateMeter, cer_from_ids, edit_distances, format_string_for_wer  # noqa: F401
 
-__all__ = ["CTCLoss", "ctc_loss_from_logits", "greedy_decode", "CTCLabelConverter"]
+__all__ = ["CTCLoss", "ctc_loss_from_logits", "greedy_decode", "CTCLabelConverter", "ErrorRateMeter", "cer_from_ids",
+           "edit_distances", "format_string_for_wer"]

@@ -60,8 +60,10 @@ class Engine(object):
         y = ops.conv_fwd(x, wp, ks, stride[0], stride[1], stats=stats)
         return y, stats
 
-    def forward(self, sd, image, mask, training, save, rng=None):
-        """sd: name -> tensor (parameters + BN buffers); image fp32 [B,1,H,W]; mask fp32 [T] or None.
+    def forward(self, sd, image, mask, training, save, rng=None, widths=None):
+        """sd: name -> tensor (parameters + BN buffers); image fp32 [B,1,H,W] in [0,1], or the loader's uint8 line
+        images [B,1,H,W] (value / 255, columns >= widths[b] read as padding 1.0: dataset.py:13-45,129-130) which one
+        kernel converts, pads and normalises; mask fp32 [T] or None.
         rng (window variant, train mode): dict(seed, drop, attn_drop, drop_path=[(dp1, dp2) per block]) or None.
         Returns (logits fp32 [B,T,C], ctx | None)."""
         if image.dim() != 4 or image.shape[1] != 1:
@@ -71,7 +73,9 @@ class Engine(object):
         B, _, Hi, Wi = image.shape
         D, C = self.D, self.C
         ctx = _Ctx() if save else None
-        image = image.contiguous().float()
+        u8 = image.dtype == torch.uint8
+        if not u8:
+            image = image.contiguous().float()
 
         # ---- weights: bf16 operand copies -----------------------------------------------------
         names, items = [], []
@@ -90,7 +94,10 @@ class Engine(object):
                                               names=names)))    # one launch for all 36 weight tensors
 
         # ---- stem -----------------------------------------------------------------------------
-        x0, _, _ = ops.sample_ln_fwd(image.view(B, Hi, Wi), torch.float32, 1e-5)
+        if u8:
+            x0, _, _ = ops.line_prep_u8(image[:, 0], widths, 1e-5)
+        else:
+            x0, _, _ = ops.sample_ln_fwd(image.view(B, Hi, Wi), torch.float32, 1e-5)
         # stem head (conv1 -> bn1 -> relu -> maxpool) fused: the K = 9 conv output is never materialised
         w1 = sd["patch_embed.conv1.weight"]
         moments = part = None

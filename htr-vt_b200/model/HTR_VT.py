@@ -87,10 +87,10 @@ class _EncoderFn(torch.autograd.Function):
     """Whole-encoder autograd node: forward/backward are Engine kernel schedules."""
 
     @staticmethod
-    def forward(ctx, module, image, mask, names, save, *params):
+    def forward(ctx, module, image, mask, names, save, widths, *params):
         sd = module._tensor_table()
         rng = module._train_rng(image.shape[0], image.device) if module.training else None
-        logits, ectx = module.engine.forward(sd, image, mask, module.training, save, rng)
+        logits, ectx = module.engine.forward(sd, image, mask, module.training, save, rng, widths)
         ctx.module, ctx.ectx, ctx.names, ctx.sd = module, ectx, names, sd
         ctx.shapes = [(p.shape, p.requires_grad) for p in params]
         return logits
@@ -117,7 +117,7 @@ class _EncoderFn(torch.autograd.Function):
             sync.finish()
         ctx.ectx = None
         out = tuple(grads[n] if req else None for n, (_, req) in zip(ctx.names, ctx.shapes))
-        return (None, None, None, None, None) + out
+        return (None, None, None, None, None, None) + out
 
 
 class MaskedAutoencoderViT(nn.Module):
@@ -184,7 +184,10 @@ class MaskedAutoencoderViT(nn.Module):
             mask[idx:idx + max_span_length] = 0
         return mask
 
-    def forward(self, x, mask_ratio=0.0, max_span_length=1, use_masking=False):
+    def forward(self, x, mask_ratio=0.0, max_span_length=1, use_masking=False, widths=None):
+        """Reference signature (model_v1/model/HTR_VT.py:222).  x: fp32 [B,1,H,W] in [0,1] as the reference's loader
+        produces it - or the SAME images still as uint8 (value = round(255 x), padding 255): one kernel then does
+        /255, pad-to-W with 1.0 for columns >= widths[b] (optional) and the input LayerNorm."""
         if not x.is_cuda:
             raise ops.HtrvtError("htr-vt_b200 MaskedAutoencoderViT.forward needs CUDA tensors (no CPU fallback)")
         mask = None
@@ -193,7 +196,7 @@ class MaskedAutoencoderViT(nn.Module):
             mask = self.span_mask(L, mask_ratio, max_span_length).to(x.device, non_blocking=True)
         names, params = zip(*[(k, v) for k, v in self.named_parameters()])
         save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        return _EncoderFn.apply(self, x, mask, names, save, *params)
+        return _EncoderFn.apply(self, x, mask, names, save, widths, *params)
 
 
 def create_model(nb_cls, img_size, **kwargs):

@@ -107,12 +107,12 @@ class MaskedAutoencoderViT(_BaseViT):
             dps.append(tuple(pair))
         return {"seed": seed, "drop": self.drop, "attn_drop": self.attn_drop, "drop_path": dps}
 
-    def forward(self, x, mask_ratio=0.0, max_span_length=1, use_masking=False):
+    def forward(self, x, mask_ratio=0.0, max_span_length=1, use_masking=False, widths=None):
         T = x.shape[-1] // 4
         if T > self.num_patches:                    # model_window/model/HTR_VT.py:35-38
             raise ValueError("Sequence length N=%d exceeds configured num_patches=%d for relative bias."
                              % (T, self.num_patches))
-        return super().forward(x, mask_ratio, max_span_length, use_masking)
+        return super().forward(x, mask_ratio, max_span_length, use_masking, widths)
 
 
 def create_model(nb_cls, img_size, **kwargs):

@@ -318,6 +318,42 @@ def sample_ln_fwd(x, out_dtype, eps=1e-5):
     return y, mean, rstd
 
 
+def line_prep_u8(img, widths=None, eps=1e-5):
+    """img uint8 [B, H, W] (rows may be strided) -> (y fp32 [B, H, W], mean [B], rstd [B]):
+    u8 / 255, columns >= widths[b] read as 1.0, whole-sample LayerNorm - one kernel."""
+    _need_cuda(img)
+    if img.dtype != torch.uint8 or img.dim() != 3 or img.stride(2) != 1:
+        raise HtrvtError("line_prep_u8 expects uint8 [B, H, W] with contiguous rows")
+    B, H, W = img.shape
+    y = torch.empty((B, H, W), dtype=torch.float32, device=img.device)
+    mean, rstd = _f32(B, img.device), _f32(B, img.device)
+    wd = None if widths is None else widths.to(device=img.device, dtype=torch.int32).contiguous()
+    check(lib().htrvt_line_prep_u8(_p(img), img.stride(0), img.stride(1), _p(wd), B, H, W, _p(y), _p(mean), _p(rstd),
+                                   eps, _stream()), "htrvt_line_prep_u8")
+    return y, mean, rstd
+
+
+def edit_distance(a, a_len, b, b_len, a_off=None, b_off=None, max_b_len=None):
+    """Levenshtein distance of n id-sequence pairs on device -> int32 [n].
+    a / b: int32, either padded [n, stride] (x_off None) or concatenated 1-D with x_off int32 [n] start offsets."""
+    _need_cuda(a, b)
+    dev = a.device
+    a = a.to(torch.int32).contiguous()
+    b = b.to(device=dev, dtype=torch.int32).contiguous()
+    a_len = a_len.to(device=dev, dtype=torch.int32).contiguous()
+    b_len_d = b_len.to(device=dev, dtype=torch.int32).contiguous()
+    n = a_len.numel()
+    if max_b_len is None:
+        max_b_len = b.shape[1] if (b_off is None and b.dim() == 2) else int(b_len.max()) if n else 0
+    a_off = None if a_off is None else a_off.to(device=dev, dtype=torch.int32).contiguous()
+    b_off = None if b_off is None else b_off.to(device=dev, dtype=torch.int32).contiguous()
+    out = torch.empty(n, dtype=torch.int32, device=dev)
+    check(lib().htrvt_edit_distance(_p(a), _p(a_off), a.stride(0) if a.dim() == 2 else 0, _p(a_len), _p(b), _p(b_off),
+                                    b.stride(0) if b.dim() == 2 else 0, _p(b_len_d), n, int(max_b_len), _p(out),
+                                    _stream()), "htrvt_edit_distance")
+    return out
+
+
 def sample_ln_bwd(dy, y, rstd, C, ld_out):
     """dy, y fp32 [B, T, C] -> dx bf16 [B*T, ld_out] (columns >= C zero)."""
     B = dy.shape[0]
@@ -624,7 +660,7 @@ def _instrument():
     import functools
     g = globals()
     names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc", "conv_wgrad_acc_t", "unpack_conv_grads", "attention_fwd",
-             "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd",
+             "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd", "line_prep_u8", "edit_distance",
              "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16", "dropout_",
              "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",
              "conv1_wgrad", "stem_head_moments", "stem_head_fwd", "stem_head_bwd"]

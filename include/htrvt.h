@@ -216,6 +216,18 @@ int htrvt_mt_adamw(int n, void* const* p, void* const* g, void* const* exp_avg, 
                    float weight_decay, int step, void* stream);
 int htrvt_mt_ema(int n, void* const* ema, void* const* src, const long long* numel, float decay, void* stream);
 
+/* ---- callers either side of the encoder ----------------------------------------------
+ * htrvt_line_prep_u8: the loader's `u8 / 255`, right padding with 1.0 (model_v1/data/dataset.py:13-45, 104-135) and the
+ * model's whole-sample LayerNorm (model_v1/model/HTR_VT.py:134-136, 224) in one kernel on the uint8 line image.
+ * img: uint8 [B, H, ld] (ld >= W, both multiples of 4; sample_stride in bytes); widths: int32 [B] valid columns or NULL;
+ * y: fp32 [B, H, W]; mean / rstd: fp32 [B] or NULL.
+ * htrvt_edit_distance: Levenshtein distance of n (prediction, ground-truth) int32 id sequences (editdistance.eval in
+ * model_v1/valid.py:49-75); sequence p starts at x_off[p] if x_off else p * x_stride; max_b_len <= 4095. */
+int htrvt_line_prep_u8(const void* img, long long sample_stride, int ld, const int* widths, int B, int H, int W,
+                       float* y, float* mean, float* rstd, float eps, void* stream);
+int htrvt_edit_distance(const int* a, const int* a_off, int a_stride, const int* a_len, const int* b, const int* b_off,
+                        int b_stride, const int* b_len, int n, int max_b_len, int* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,8 @@ from __future__ import annotations
 import math
 from collections import OrderedDict
 
+import re
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -373,6 +375,68 @@ def argmax_first(logits: np.ndarray) -> np.ndarray:
     nan = np.isnan(a)
     idx = np.where(nan.any(axis=-1), nan.argmax(axis=-1), np.where(nan, -np.inf, a).argmax(axis=-1))
     return idx.astype(np.int64)
+
+
+# ----------------------------------------------------------------------------------------------
+# Input pipeline (device half) and error rates: SURVEY.md 8(f) rows 2 and 3
+# ----------------------------------------------------------------------------------------------
+def line_prep_u8(img_u8: np.ndarray, widths=None, eps: float = 1e-5) -> np.ndarray:
+    """What reaches the first convolution for a uint8 line batch [B,H,W]: `/ 255.` (dataset.py:44), right padding
+    with 1.0 from column widths[b] on (dataset.py:129-130), then the whole-sample LayerNorm of
+    model_v1/model/HTR_VT.py:134-136,224 (biased variance, eps 1e-5, no affine)."""
+    x = torch.from_numpy(np.ascontiguousarray(img_u8)).float() / 255.
+    if widths is not None:
+        for b, w in enumerate(widths):
+            x[b, :, int(w):] = 1.0
+    return F.layer_norm(x, x.shape[1:], eps=eps).numpy()
+
+
+def levenshtein(a, b) -> int:
+    """Unit-cost edit distance of two sequences = `editdistance.eval` (model_v1/valid.py:50,63); the recurrence is
+    the one the reference restates at model_v1/test.py:114-133."""
+    a, b = list(a), list(b)
+    if a == b:
+        return 0
+    if not a:
+        return len(b)
+    if not b:
+        return len(a)
+    prev = list(range(len(b) + 1))
+    for i in range(1, len(a) + 1):
+        cur = [i]
+        for j in range(1, len(b) + 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (0 if a[i - 1] == b[j - 1] else 1)))
+        prev = cur
+    return prev[-1]
+
+
+# (in the reference's non-raw literal `\\(` is an escaped parenthesis: the backslash itself is NOT in the class)
+_WER_PUNCT = re.compile(r"""([\[\]{}/()"'&+*=<>?.;:,!\-\u2014_\u20ac#%\u00b0])""")
+
+
+def format_string_for_wer(s: str) -> str:
+    """model_v1/utils/utils.py:176-179: isolate punctuation with spaces, collapse runs of blanks / newlines, strip."""
+    s = _WER_PUNCT.sub(r" \1 ", s)
+    return re.sub(r"([ \n])+", " ", s).strip()
+
+
+def error_rates(preds_str, labels):
+    """The accumulation of model_v1/valid.py:49-75 for one list of (prediction, label) strings."""
+    r = dict(norm_ED=0.0, tot_ED=0, length_of_gt=0, norm_ED_wer=0.0, tot_ED_wer=0, length_of_gt_wer=0)
+    for pred, gt in zip(preds_str, labels):
+        d = levenshtein(pred, gt)
+        r["norm_ED"] += 1 if len(gt) == 0 else d / float(len(gt))
+        r["tot_ED"] += d
+        r["length_of_gt"] += len(gt)
+        pw = format_string_for_wer(pred).split(" ")
+        gw = format_string_for_wer(gt).split(" ")
+        d = levenshtein(pw, gw)
+        r["norm_ED_wer"] += 1 if len(gw) == 0 else d / float(len(gw))
+        r["tot_ED_wer"] += d
+        r["length_of_gt_wer"] += len(gw)
+    r["CER"] = r["tot_ED"] / float(r["length_of_gt"]) if r["length_of_gt"] else 0.0
+    r["WER"] = r["tot_ED_wer"] / float(r["length_of_gt_wer"]) if r["length_of_gt_wer"] else 0.0
+    return r
 
 
 # ----------------------------------------------------------------------------------------------

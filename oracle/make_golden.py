@@ -175,6 +175,41 @@ def argmax_cases():
     print("argmax", idx.numpy().tolist())
 
 
+def metrics_cases():
+    """format_string_for_wer comes from the reference itself (model_v1/utils/utils.py:176-179, imported unmodified);
+    `editdistance` (environment.yaml:35) is not installed here, so the distances are the oracle's restatement of the
+    recurrence the reference spells out at model_v1/test.py:114-133 plus classic known answers."""
+    import json
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import htrvt_oracle as O
+    _, utl = refload.load_variant("model_v1")
+    texts = ["Hello, world!  it's\u2014a [test]\n ok", "a-b_c \u20ac5 #1 100% 3\u00b0 x\\y \"q\" {z}/(w)&+*=<>?;:", "", "   ",
+             "no punctuation here", "tab\there", "He said: (well...) nothing-much_at all!", "MOVE to stop Mr. Gaitskell from"]
+    fmt = [utl.format_string_for_wer(t) for t in texts]
+    kat = [["kitten", "sitting", 3], ["flaw", "lawn", 2], ["", "abc", 3], ["abc", "", 3], ["same", "same", 0],
+           ["intention", "execution", 5], ["sunday", "saturday", 3], ["a", "b", 1]]
+    preds = ["MOVE to stop Mr. Gaitskell from", "nominating any more Labour life Peers", "", "x", "is to be made at a meeting"]
+    labels = ["A MOVE to stop Mr. Gaitskell from", "nominating any more Labour life Peers", "abc", "", "is to be made at a meeting of Labour"]
+    rates = O.error_rates(preds, labels)
+    with open(os.path.join(OUT, "metrics_cases.json"), "w") as fh:
+        json.dump(dict(texts=texts, formatted=fmt, kat=kat, preds=preds, labels=labels, rates=rates), fh, indent=1)
+    print("metrics", rates)
+
+
+def line_prep_cases():
+    """u8 line batch -> what the reference's loader + first LayerNorm produce (dataset.py:44,129-130; HTR_VT.py:224),
+    computed with torch exactly as the reference does (float() / 255., pad 1.0, F.layer_norm)."""
+    rs = np.random.RandomState(5)
+    img = rs.randint(0, 256, size=(3, 64, 128)).astype(np.uint8)
+    widths = np.array([128, 77, 4], dtype=np.int32)
+    x = torch.from_numpy(img).float() / 255.
+    for b, w in enumerate(widths):
+        x[b, :, int(w):] = 1.0
+    y = torch.nn.functional.layer_norm(x, x.shape[1:], eps=1e-5)
+    np.savez_compressed(os.path.join(OUT, "line_prep_cases.npz"), img=img, widths=widths, y=y.numpy())
+    print("line_prep", float(y.abs().max()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -187,3 +222,5 @@ if __name__ == "__main__":
     ctc_cases()
     decode_cases()
     argmax_cases()
+    metrics_cases()
+    line_prep_cases()

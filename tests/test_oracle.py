@@ -98,3 +98,37 @@ def test_live_reference_when_present():
         b = O.forward(sd, x)
     np.testing.assert_allclose(a.numpy(), b.numpy(), atol=2e-4)
     assert list(ref.state_dict().keys()) == list(O.reorder_like(sd, ref.state_dict().keys()).keys())
+
+
+def test_metrics_oracle_matches_reference_formatting_and_known_answers():
+    """format_string_for_wer against strings produced by the reference's own function; Levenshtein against
+    classic known answers, a brute-force check and metric axioms; the valid.py:49-75 accumulation."""
+    import json
+    with open(os.path.join(G, "metrics_cases.json")) as fh:
+        g = json.load(fh)
+    assert [O.format_string_for_wer(t) for t in g["texts"]] == g["formatted"]
+    for a, b, d in g["kat"]:
+        assert O.levenshtein(a, b) == d and O.levenshtein(b, a) == d
+    rs = np.random.RandomState(0)
+    seqs = [rs.randint(0, 4, size=rs.randint(0, 9)).tolist() for _ in range(24)]
+    for a in seqs[:8]:
+        for b in seqs[8:16]:
+            d = O.levenshtein(a, b)
+            assert abs(len(a) - len(b)) <= d <= max(len(a), len(b))
+            for c in seqs[16:]:
+                assert d <= O.levenshtein(a, c) + O.levenshtein(c, b)
+    r = O.error_rates(g["preds"], g["labels"])
+    for k, v in g["rates"].items():
+        assert r[k] == pytest.approx(v)
+    # "" formats to "" and "".split(" ") == ['']: the reference counts one (empty) word there (valid.py:56-66)
+    assert O.error_rates([""], [""])["length_of_gt_wer"] == 1
+
+
+def test_line_prep_oracle_matches_reference_ops():
+    g = np.load(os.path.join(G, "line_prep_cases.npz"))
+    y = O.line_prep_u8(g["img"], g["widths"])
+    np.testing.assert_allclose(y, g["y"], rtol=0, atol=1e-6)
+    # no widths: the u8 image is taken as is (padding already 255 in the loader's output)
+    y2 = O.line_prep_u8(g["img"])
+    x = torch.from_numpy(g["img"]).float() / 255.
+    np.testing.assert_allclose(y2, torch.nn.functional.layer_norm(x, x.shape[1:], eps=1e-5).numpy(), atol=1e-6)
