@@ -170,8 +170,21 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
     out["ctc_loss_grad"] = {"us_per_batch": ms * 1e3, "batch": B, "T": T, "C": C, "algorithmic_bytes": bytes_ctc,
                             "achieved_gbs": bytes_ctc / (ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm,
                             "frac_of_hbm_roofline": bytes_ctc / (ms * 1e-3) / 1e9 / hbm,
-                            "note": "T sequential alpha/beta steps bound this kernel by latency, not bytes"}
+                            "note": "T sequential alpha/beta steps bound this kernel by latency, not bytes; the "
+                                    "recursion runs in the linear domain on the FP64 pipe (fallbacks to log space: %d)"
+                                    % ops.lib().htrvt_ctc_fallback_count()}
     del bufs
+    # the same kernel when the batch fills the chip (one CTA per sequence, 148 SMs): throughput, not latency
+    Bl = 4096
+    xl = torch.randn(Bl, T, C, device=dev)
+    _, tgl, tll = synth_batch(Bl, 3)
+    tgl, tll_d, mtl_l = tgl.to(dev), tll.to(dev), int(tll.max())
+    ms = timed_ms(lambda: ops.ctc_loss_grad(xl, tgl, None, tll_d, layout="btc", is_logprob=False, want_grad=True,
+                                            max_target_len=mtl_l, grad_scale_const=1.0 / Bl), 10)
+    bl = 2.0 * Bl * T * C * 4 + float(tgl.numel()) * 4 + 12.0 * Bl
+    out["ctc_loss_grad"]["batch_4096"] = {"us_per_batch": ms * 1e3, "achieved_gbs": bl / (ms * 1e-3) / 1e9,
+                                          "frac_of_hbm_roofline": bl / (ms * 1e-3) / 1e9 / hbm}
+    del xl
 
     # ---- inference: eval forward + greedy decode (argmax + collapse on device, one D2H copy), 512 lines per GPU
     Bi = 512
@@ -187,8 +200,47 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
     ms = timed_ms(infer_once, 5, warm=2)
     out["inference"] = {"img_per_s": Bi / (ms * 1e-3), "ms_per_batch": ms, "batch_per_gpu": Bi,
                         "what": "eval-mode forward + greedy CTC decode to Python strings (BASELINE config 4 share)"}
+    # validation metrics on device: Levenshtein of the decoded ids against the label ids
+    try:
+        with torch.no_grad():
+            preds = model(img).float()
+        ids, lens = h.greedy_decode(preds, NB_CLS)
+        _, tgv, tlv = synth_batch(Bi, 4)
+        tgv = tgv.to(dev)
+        ms_ed = timed_ms(lambda: h.cer_from_ids(ids, lens, tgv, tlv), 20)
+        out["cer_device"] = {"us_per_batch": ms_ed * 1e3, "pairs": Bi,
+                             "what": "edit distances of 512 decoded id rows vs label ids, one launch (valid.py:49-55)"}
+    except Exception as e:
+        out["cer_device"] = {"error": repr(e)[:200]}
     model.train()
     del img
+
+    # ---- training step fed with the loader's uint8 lines: 4x fewer PCIe bytes, conversion +
+    # padding + input LayerNorm in one kernel; same timed region as the headline e2e (H2D + step + loss.item())
+    try:
+        import numpy as np
+        Bu = 128
+        u8_h = torch.from_numpy(np.random.RandomState(6).randint(0, 256, size=(Bu, 1, IMG_H, IMG_W)).astype("uint8")).pin_memory()
+        _, tgu, tlu = synth_batch(Bu, 6)
+        tgu, tlu = tgu.pin_memory(), tlu.pin_memory()
+        uparams = [p for p in model.parameters() if p.requires_grad]
+
+        def step_u8():
+            for p in uparams:
+                p.grad = None
+            preds = model(u8_h.to(dev, non_blocking=True), MASK_RATIO, MAX_SPAN, use_masking=True)
+            loss = h.ctc_loss_from_logits(preds.float(), tgu.to(dev, non_blocking=True), tlu).mean()
+            loss.backward()
+            return loss.item()
+
+        ms = timed_ms(step_u8, 5, warm=2)
+        out["e2e_uint8_input"] = {"img_per_s": Bu / (ms * 1e-3), "ms_per_step": ms,
+                                  "h2d_bytes_per_step": u8_h.numel() + tgu.numel() * 4,
+                                  "what": "train step from pinned uint8 line images through model.forward(uint8)"}
+        for p in uparams:
+            p.grad = None
+    except Exception as e:
+        out["e2e_uint8_input"] = {"error": repr(e)[:200]}
 
     # ---- the reference's full training iteration (model_v1/train.py:113-126): SAM(AdamW) = two forward/backward
     # passes around first_step / second_step + the EMA update, with the multi-tensor optimizer kernels
@@ -369,7 +421,8 @@ def run_ours(args):
         d[0] += a.elapsed_time(b)
         d[1] += fl
         d[2] += 1
-    gemm_names = ("gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc")
+    gemm_names = ("gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc",
+                  "conv_wgrad_acc_t")
     g_ms = sum(by[n][0] for n in gemm_names if n in by)
     g_fl = sum(by[n][1] for n in gemm_names if n in by)
     g_n = sum(by[n][2] for n in gemm_names if n in by)

@@ -35,6 +35,24 @@ __device__ __forceinline__ void mt_locate(const MtTable& T, int& t, long long& l
   hi = lo + kMtChunk < T.numel[l] ? lo + kMtChunk : T.numel[l];
 }
 
+// Streaming helper: fn4(i, n) is called for 4-element groups while every stream is 16-byte aligned (n = 4: the caller
+// uses float4 accesses), and for single elements otherwise / in the tail (n = 1).  Unrolled x4: each thread keeps four
+// independent 16-byte loads per stream in flight (these kernels are pure HBM streaming).
+template <typename F4, typename F1>
+__device__ __forceinline__ void mt_stream(long long lo, long long hi, bool aligned, F4 f4, F1 f1) {
+  long long i = lo;
+  if (aligned) {
+    const long long n4 = (hi - lo) >> 2;
+#pragma unroll 4
+    for (long long k = threadIdx.x; k < n4; k += 256) f4(lo + 4 * k);
+    i = lo + 4 * n4;
+  }
+  for (i += threadIdx.x; i < hi; i += 256) f1(i);
+}
+__device__ __forceinline__ bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
 // out (double, +=) = sum over tensors of |g|^2  (adaptive: |abs(p) g|^2)      a = g, b = p
 __global__ void __launch_bounds__(256) mt_sqnorm_kernel(const __grid_constant__ MtTable T, int adaptive,
                                                         double* __restrict__ out) {
@@ -44,11 +62,17 @@ __global__ void __launch_bounds__(256) mt_sqnorm_kernel(const __grid_constant__ 
   const float* g = static_cast<const float*>(T.a[t]);
   const float* p = static_cast<const float*>(T.b[t]);
   float s = 0.f;
-  for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-    float v = g[i];
-    if (adaptive) v *= fabsf(p[i]);
-    s = fmaf(v, v, s);
-  }
+  mt_stream(lo, hi, al16(g) && (!adaptive || al16(p)),
+            [&](long long i) {
+              float4 v = ld4(g + i);
+              if (adaptive) { const float4 w = ld4(p + i); v.x *= fabsf(w.x); v.y *= fabsf(w.y); v.z *= fabsf(w.z); v.w *= fabsf(w.w); }
+              s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
+            },
+            [&](long long i) {
+              float v = g[i];
+              if (adaptive) v *= fabsf(p[i]);
+              s = fmaf(v, v, s);
+            });
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(out, static_cast<double>(s));
 }
@@ -62,11 +86,18 @@ __global__ void __launch_bounds__(256) mt_sam_first_kernel(const __grid_constant
   const float* g = static_cast<const float*>(T.b[t]);
   float* old = static_cast<float*>(T.c[t]);
   const float scale = static_cast<float>(static_cast<double>(rho) / (sqrt(*norm2) + 1e-12));
-  for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-    const float w = p[i];
-    old[i] = w;
-    p[i] = w + (adaptive ? w * w : 1.0f) * g[i] * scale;
-  }
+  auto one = [&](float w, float gi) { return w + (adaptive ? w * w : 1.0f) * gi * scale; };
+  mt_stream(lo, hi, al16(p) && al16(g) && al16(old),
+            [&](long long i) {
+              const float4 w = ld4(p + i), gi = ld4(g + i);
+              st4(old + i, w);
+              st4(p + i, make_float4(one(w.x, gi.x), one(w.y, gi.y), one(w.z, gi.z), one(w.w, gi.w)));
+            },
+            [&](long long i) {
+              const float w = p[i];
+              old[i] = w;
+              p[i] = one(w, g[i]);
+            });
 }
 
 // SAM second step + AdamW: w = old (if given) ; torch.optim.AdamW single-tensor update     a = p, b = g, c = m, d = v, e = old
@@ -80,16 +111,26 @@ __global__ void __launch_bounds__(256) mt_adamw_kernel(const __grid_constant__ M
   float* v = static_cast<float*>(T.d[t]);
   const float* old = static_cast<const float*>(T.e[t]);
   const float step_size = lr / bc1;
-  for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-    float w = old ? old[i] : p[i];
-    const float gi = g[i];
+  auto one = [&](float w, float gi, float& mi, float& vi) {
     w *= 1.0f - lr * wd;                                  // decoupled weight decay
-    const float mi = m[i] + (gi - m[i]) * (1.0f - beta1); // exp_avg.lerp_(g, 1 - beta1)
-    const float vi = v[i] * beta2 + gi * gi * (1.0f - beta2);
-    m[i] = mi;
-    v[i] = vi;
-    p[i] = w - step_size * (mi / (sqrtf(vi) * rsqrt_bc2 + eps));
-  }
+    mi = mi + (gi - mi) * (1.0f - beta1);                 // exp_avg.lerp_(g, 1 - beta1)
+    vi = vi * beta2 + gi * gi * (1.0f - beta2);
+    return w - step_size * (mi / (sqrtf(vi) * rsqrt_bc2 + eps));
+  };
+  const float* wsrc = old ? old : p;
+  mt_stream(lo, hi, al16(p) && al16(g) && al16(m) && al16(v) && al16(wsrc),
+            [&](long long i) {
+              const float4 w = ld4(wsrc + i), gi = ld4(g + i);
+              float4 mi = ld4(m + i), vi = ld4(v + i);
+              const float4 o = make_float4(one(w.x, gi.x, mi.x, vi.x), one(w.y, gi.y, mi.y, vi.y),
+                                           one(w.z, gi.z, mi.z, vi.z), one(w.w, gi.w, mi.w, vi.w));
+              st4(m + i, mi); st4(v + i, vi); st4(p + i, o);
+            },
+            [&](long long i) {
+              float mi = m[i], vi = v[i];
+              const float o = one(wsrc[i], g[i], mi, vi);
+              m[i] = mi; v[i] = vi; p[i] = o;
+            });
 }
 
 // EMA: ema = ema * decay + (1 - decay) * src          a = ema, b = src
@@ -98,7 +139,14 @@ __global__ void __launch_bounds__(256) mt_ema_kernel(const __grid_constant__ MtT
   mt_locate(T, t, lo, hi);
   float* e = static_cast<float*>(T.a[t]);
   const float* s = static_cast<const float*>(T.b[t]);
-  for (long long i = lo + threadIdx.x; i < hi; i += 256) e[i] = e[i] * decay + (1.0f - decay) * s[i];
+  const float om = 1.0f - decay;
+  mt_stream(lo, hi, al16(e) && al16(s),
+            [&](long long i) {
+              const float4 a = ld4(e + i), b = ld4(s + i);
+              st4(e + i, make_float4(a.x * decay + om * b.x, a.y * decay + om * b.y, a.z * decay + om * b.z,
+                                     a.w * decay + om * b.w));
+            },
+            [&](long long i) { e[i] = e[i] * decay + om * s[i]; });
 }
 
 }  // namespace htrvt
