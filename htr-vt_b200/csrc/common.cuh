@@ -282,6 +282,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= 2ull << 61;                       // SWIZZLE_128B
   return d;
 }
+// A K-major SWIZZLE_128B operand may start at ANY 128-byte row of a tile that TMA staged at a 1024-byte boundary
+// (a shifted window of a larger tile): just move the start address.  tcgen05 applies the 128B XOR to the absolute
+// shared-memory address bits, exactly as TMA did when writing, so the descriptor's base-offset field stays 0
+// (setting it to (addr >> 7) & 7 double-shifts the pattern: measured, gemm.cu window reuse).
 // MN-major tile under SWIZZLE_64B: 32 MN elements = 64 B contiguous per K index, 8 K-rows per 512-B atom:
 //      SBO = 512 B (next 8 K indices), LBO = byte distance between 32-wide MN atoms.
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

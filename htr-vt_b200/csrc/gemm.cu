@@ -26,12 +26,18 @@ constexpr int kBK = 64;
 // CL = 1: one CTA per 128 x BN tile.  CL = 2: a CTA PAIR (cta_group::2) per 256 x BN tile - each CTA stages its own
 // 128 A rows and only HALF of B, so the bytes entering each SM per flop drop by ~1/3 (these GEMMs are bound by the
 // ~68 B/clk L2 -> SM ingress: tensor-pipe utilisation tracks 68 / ((128 + BN) * 128 / (2 BN)) for every shape).
-template <int BN, int CL>
+// RE (KIND 0, 3x3 stride-1 convs): one stage = ONE 136-pixel window of the activation (the three horizontal taps of a
+// kernel row read it at row offsets 0 / 1 / 2 through the descriptor's base offset) + the three taps' weight tiles,
+// i.e. K = 192 per stage and 1/3 of the A bytes: these GEMMs run at the ~40 B/clk/SM the L2 -> SM path delivers, so
+// bytes per flop, not tensor-pipe issue, set their speed.
+constexpr int kWinRows = 136;
+template <int BN, int CL, bool RE = false>
 struct GemmCfg {
-  static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = (BN / CL) * kBK * 2;                 // B bytes staged by THIS CTA
+  static constexpr int kABytes = RE ? kWinRows * kBK * 2 : kBM * kBK * 2;
+  static constexpr int kBTile = (BN / CL) * kBK * 2;                  // one tap's B bytes staged by THIS CTA
+  static constexpr int kBBytes = RE ? 3 * kBTile : kBTile;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (CL == 2) ? 6 : ((BN <= 128) ? 6 : 4);
+  static constexpr int kStages = RE ? (BN >= 256 ? 2 : 3) : (CL == 2) ? 6 : ((BN <= 128) ? 6 : 4);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kStagingBytes = 8 * 2 * 2048;   // per epilogue warp: two [32 rows][64 B] output boxes
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
@@ -81,11 +87,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmP& P, int id) {
   return c;
 }
 
-template <int BN, int KIND, bool B_MN, int CL>
+template <int BN, int KIND, bool B_MN, int CL, bool RE = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmP P) {
-  using Cfg = GemmCfg<BN, CL>;
+  using Cfg = GemmCfg<BN, CL, RE>;
+  static_assert(!RE || (KIND == 0 && !B_MN && CL == 2), "window reuse: kind 0, K-major weights, CTA pairs");
   constexpr bool A_MN = (KIND == 1 || KIND == 3);
   constexpr bool B_SW64 = B_MN && ((BN / CL) % 64) != 0;     // a 96-column half: 32-column atoms, SWIZZLE_64B
   constexpr int kStages = Cfg::kStages;
@@ -130,7 +137,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int id = first_tile; id < total_tiles; id += tile_step) {
         const TileCoord tc = decode_tile(P, id);
         const int n0 = tc.n_tile * BN, m0 = tc.m_tile * kBM;
-        const int kiters = (KIND == 0) ? P.n_taps * P.k_chunks : (tc.q_end - tc.q_begin);
+        const int kiters = RE ? (P.n_taps / 3) * P.k_chunks
+                              : (KIND == 0) ? P.n_taps * P.k_chunks : (tc.q_end - tc.q_begin);
         // running coordinates of the K loop (this one thread feeds the tensor pipe: no divisions per iteration)
         int tap = 0, cc = 0;                                  // KIND 0: tap and 64-channel chunk
         int wq = 0, ho = 0, n = 0;                            // KIND != 0: 64-pixel chunk of image row (n, ho)
@@ -168,7 +176,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           };
           constexpr int BNL = BN / CL;                    // B columns staged by this CTA
           const int nb0 = n0 + crank * BNL;
-          if (KIND == 0) {
+          if (RE) {
+            // `tap` counts kernel ROWS here: taps 3*tap .. 3*tap+2 share dh; the window starts one pixel to the left
+            load(sa, &tmA, cc * kBK, 0, tc.w0 - 1, tc.h * P.a_sh + P.tap.dh[3 * tap], tc.n);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              load(sb + j * Cfg::kBTile, &tmB, P.tap.widx[3 * tap + j] * P.b_tap_stride + cc * kBK, nb0, 0, 0, 0);
+            if (++cc == P.k_chunks) { cc = 0; ++tap; }
+          } else if (KIND == 0) {
             load(sa, &tmA, cc * kBK, P.tap.pw[tap], tc.w0 + P.tap.dw[tap], tc.h * P.a_sh + P.tap.dh[tap], tc.n);
             if (!B_MN) {
               load(sb, &tmB, P.tap.widx[tap] * P.b_tap_stride + cc * kBK, nb0, 0, 0, 0);
@@ -219,15 +234,32 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int as = 0; uint32_t aphase = 0;
       for (int id = first_tile; id < total_tiles; id += tile_step) {
         const TileCoord tc = decode_tile(P, id);
-        const int kiters = (KIND == 0) ? P.n_taps * P.k_chunks : (tc.q_end - tc.q_begin);
+        const int kiters = RE ? (P.n_taps / 3) * P.k_chunks
+                              : (KIND == 0) ? P.n_taps * P.k_chunks : (tc.q_end - tc.q_begin);
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+        int re_row = 0, re_cc = 0;                             // RE: kernel row / channel chunk of this stage
         for (int k = 0; k < kiters; ++k) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
+          if (RE) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const uint32_t arow = sa + static_cast<uint32_t>(P.tap.dw[3 * re_row + j] + 1) * 128u;   // window row 0..2
+#pragma unroll
+              for (int kk = 0; kk < kBK / 16; ++kk) {
+                // start address = window row: the swizzle phase follows the ABSOLUTE smem address bits (TMA wrote the
+                // tile at a 1024-byte boundary), so no descriptor base offset is needed - verified tap by tap
+                const uint64_t da = umma_desc_sw128(arow + kk * 32, 16, 1024);
+                const uint64_t db = umma_desc_sw128(sb + j * Cfg::kBTile + kk * 32, 16, 1024);
+                umma_bf16_pair(d_tmem, da, db, idesc, (k | j | kk) != 0 ? 1u : 0u);
+              }
+            }
+            if (++re_cc == P.k_chunks) { re_cc = 0; ++re_row; }
+          } else
 #pragma unroll
           for (int kk = 0; kk < kBK / 16; ++kk) {
             const uint64_t da = A_MN ? umma_desc_sw128(sa + kk * 2048, 8192, 1024)
@@ -495,12 +527,12 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int KIND, bool B_MN, int CL>
+template <int BN, int KIND, bool B_MN, int CL, bool RE = false>
 int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
                cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CL>;
+  using Cfg = GemmCfg<BN, CL, RE>;
   static bool configured = false;
-  auto kern = tapgemm_kernel<BN, KIND, B_MN, CL>;
+  auto kern = tapgemm_kernel<BN, KIND, B_MN, CL, RE>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
       return HTRVT_ERR_LAUNCH;
@@ -549,6 +581,18 @@ int launch_bn(int bn, int cl, const CUtensorMap& a, const CUtensorMap& b, const 
 int dbg_env(const char* name) {
   const char* v = getenv(name);
   return v ? atoi(v) : 0;
+}
+
+// 3x3 stride-1 convolution (forward, or input gradient with K-major transposed weights) as CTA pairs with the
+// horizontal taps sharing one staged activation window (GemmCfg RE).  HTRVT_NOREUSE=1 disables it.
+bool use_window_reuse(int ks, int sw, int cl, int bn, int n_taps) {
+  static const int off = dbg_env("HTRVT_NOREUSE");
+  return !off && ks == 3 && sw == 1 && cl == 2 && n_taps == 9 && (bn == 192 || bn == 256);
+}
+int launch_reuse(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total,
+                 cudaStream_t s) {
+  if (bn == 192) return launch_one<192, 0, false, 2, true>(a, b, c, P, total, s);
+  return launch_one<256, 0, false, 2, true>(a, b, c, P, total, s);
 }
 
 // CTA pairs (cta_group::2) need tile pairs (2p, 2p+1) on the same n-tile: tiles_m even; an MN-major B operand is
@@ -754,8 +798,9 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
   const int bn = pick_bn(Cout);
   const int tiles_m_all = ((Wo + kBM - 1) / kBM) * Ho * NB;
   const int cl = pick_cluster(tiles_m_all, tiles_m_all * ((Cout + bn - 1) / bn), bn, false);
+  const bool reuse = use_window_reuse(ks, sw, cl, bn, ks * ks);
   CUtensorMap ta, tb, tc;
-  int r = make_map_act(&ta, x, NB, H, W, Cin, sw, kBK, kBM);
+  int r = make_map_act(&ta, x, NB, H, W, Cin, sw, kBK, reuse ? kWinRows : kBM);
   if (r) return r;
   r = make_map_matrix(&tb, w, Cout, static_cast<long long>(ks) * ks * Cin, static_cast<long long>(ks) * ks * Cin, kBK,
                       bn / cl);
@@ -771,6 +816,7 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
   P.M_valid = 0; P.N_valid = Cout;
   P.flags = EPI_BF16 | (flags & (EPI_RELU | EPI_NOSTORE)) | (stats_partial ? EPI_STATS : 0);
   P.stats = stats_partial; P.alpha = 1.f;
+  if (reuse) return launch_reuse(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
   return launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
 
@@ -809,6 +855,11 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
       P.N_valid = Cin; P.flags = EPI_BF16 | (accumulate ? EPI_ACCUM : 0);
       P.alpha = 1.f;
       const int cl = pick_cluster(P.tiles_m, P.tiles_m * P.tiles_n, bn, !kmajor);
+      const bool reuse = kmajor && sh == 1 && use_window_reuse(ks, sw, cl, bn, n);
+      if (reuse) {
+        r = make_map_act(&ta, dy, NB, Ho, Wo, Cout, 1, kBK, kWinRows);
+        if (r) return r;
+      }
       if (kmajor)
         r = make_map_matrix(&tb, w_t, Cin, static_cast<long long>(ks) * ks * Cout, static_cast<long long>(ks) * ks * Cout,
                             kBK, bn / cl);
@@ -821,8 +872,9 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
                        Hq, NB, static_cast<long long>(sw) * Cin, static_cast<long long>(sh) * W * Cin,
                        static_cast<long long>(H) * W * Cin);
       if (r) return r;
-      r = kmajor ? launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream)
-                 : launch_bn<0, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+      r = reuse ? launch_reuse(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream)
+          : kmajor ? launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream)
+                   : launch_bn<0, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
       if (r) return r;
     }
   return HTRVT_OK;

@@ -16,3 +16,7 @@ ncu --profile-from-start off --metrics $M --clock-control none --csv --page raw 
 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:tapgemm -s 20 -c 3 \
     -f -o $OUT/${TAG}_gemm_full python tools/profile_step.py > $OUT/${TAG}_ncu3.log 2>&1
 ls -la $OUT | tail -8
+# the CTC loss+grad kernel alone (BASELINE metric 2): full set, one launch at batch 128
+ncu --set full --clock-control none --import-source on -k regex:ctc_loss_grad -s 3 -c 1 \
+    -f -o $OUT/${TAG}_ctc_full python tools/ctc_bench.py > $OUT/${TAG}_ncu4.log 2>&1
+ls -la $OUT | tail -4
