@@ -91,3 +91,32 @@ def test_dp_helpers():
     offs, split = ddp.segment_bounds(names, [768, 10, 1728, 768, 80])
     # every tensor starts on a 64-float (256 B) boundary: TMA reduce-add targets need 16-byte aligned bases
     assert offs == [0, 768, 832, 2560, 3328, 3456] and split == 2560
+
+
+def test_reference_checkpoint_round_trip(tmp_path):
+    """The reference's checkpoint layout (train.py:153-172) and its loading recipe (test.py:29-40: 'state_dict_ema',
+    `module.` prefixes, strict=True) work on the drop-in module; CPU only (no kernels involved)."""
+    import copy
+    from importlib import import_module
+    import torch
+    H = import_module("htr-vt_b200.model.HTR_VT")
+    C = import_module("htr-vt_b200.utils.checkpoint")
+    torch.manual_seed(0)
+    m = H.create_model(20, [64, 128])
+    ema = copy.deepcopy(m)
+    with torch.no_grad():
+        for p in ema.parameters():
+            p.add_(1.0)
+    path = str(tmp_path / "best_CER.pth")
+    wrapped = {"module." + k: v for k, v in ema.state_dict().items()}          # as saved from a DataParallel wrapper
+    torch.save({"model": m.state_dict(), "state_dict_ema": wrapped, "nb_iter": 7, "best_cer": 0.05}, path)
+    m2 = H.create_model(20, [64, 128])
+    ckpt = C.load_reference_checkpoint(m2, path)
+    assert ckpt["nb_iter"] == 7
+    for (k, a), (_, b) in zip(m2.state_dict().items(), ema.state_dict().items()):
+        assert torch.equal(a, b), k
+    C.load_reference_checkpoint(m2, path, prefer_ema=False)
+    for (k, a), (_, b) in zip(m2.state_dict().items(), m.state_dict().items()):
+        assert torch.equal(a, b), k
+    out = C.save_reference_checkpoint(str(tmp_path / "x.pth"), m, model_ema=ema, nb_iter=3)
+    assert list(out["state_dict_ema"].keys()) == list(m.state_dict().keys()) and out["nb_iter"] == 3
