@@ -436,6 +436,11 @@ def run_ours(args):
     for cand in (os.path.join(ROOT, "MEASURED_PEAKS.json"),):
         if os.path.exists(cand):
             peaks = json.load(open(cand))
+    traffic = None          # DRAM bytes of the tap-GEMM launches of one step, from the committed ncu counters (profiles/)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["tapgemm_dram_bytes_per_step"]
+    except Exception:
+        pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained)"
     ach_tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
@@ -457,7 +462,9 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": ach_tf / peak_tf if peak_tf else None, "traffic": None,
+                     "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                     "traffic_note": "ncu dram bytes (read + write) summed over the family's launches of one step; "
+                                     "algorithmic = flops, the operands are re-read from L2",
                      "kernel": "tapgemm_kernel (all conv / linear fwd, dgrad, wgrad launches of one step)",
                      "launches": g_n, "ms_in_step": g_ms, "share_of_step": g_ms / all_ms if all_ms else None,
                      "peak_source": peak_src},
