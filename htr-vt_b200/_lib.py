@@ -58,6 +58,7 @@ SIGNATURES = {
     "htrvt_conv_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _Z, _P]),
     "htrvt_conv_wgrad_acc": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "htrvt_conv_wgrad_acc_t": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "htrvt_conv_wgrad_acc_w": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "htrvt_unpack_conv_grads": (_I, [_I, _P, _P, _P, _P, _P, _P]),
     "htrvt_sample_ln_fwd": (_I, [_P, _P, _I, _P, _P, _I, _I, _F, _P]),
     "htrvt_sample_ln_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -6,7 +6,11 @@
 // (MN-major); 2 = weight gradient with a K-major dY^T operand (tcgen05 runs ~1.4x slower with an MN-major A);
 // 3 = weight gradient transposed: rows = (tap, 64-channel atom of x) - every 64-row half of a tile carries its own
 // tap shift, so no rows are wasted when Cout is not a multiple of 128 - columns = Cout; when a CTA of a pair stages
-// 96 columns the B operand uses SWIZZLE_64B (32-column atoms).
+// 96 columns the B operand uses SWIZZLE_64B (32-column atoms);
+// 4 = transposed weight gradient of 3x3 stride-(.,1) convs with TWO live accumulators (256 rows = four (kernel row,
+// channel atom, kw) atoms) that share the dY tile and read x through two staged 72-pixel windows: the three
+// horizontal taps are the same window at row offsets 0 / 1 / 2 (the two 64-row halves of an MN-major A operand are
+// just two start addresses, LBO apart - they may overlap).
 //   warps 2-9: epilogue (tcgen05.ld 32x32b, two warps per TMEM lane quadrant), double-buffered
 //              accumulator so the epilogue of tile i overlaps the main loop of tile i+1
 // Operands can be K-major or MN-major (smem descriptor + instruction-descriptor major bits), which is
@@ -31,13 +35,15 @@ constexpr int kBK = 64;
 // i.e. K = 192 per stage and 1/3 of the A bytes: these GEMMs run at the ~40 B/clk/SM the L2 -> SM path delivers, so
 // bytes per flop, not tensor-pipe issue, set their speed.
 constexpr int kWinRows = 136;
-template <int BN, int CL, bool RE = false>
+constexpr int kWin4Rows = 72;                  // KIND 4: 64 pixels + 2 of halo, padded to whole 1024-byte swizzle atoms
+constexpr int kWin4Bytes = kWin4Rows * 128;
+template <int BN, int CL, bool RE = false, bool W4 = false>
 struct GemmCfg {
-  static constexpr int kABytes = RE ? kWinRows * kBK * 2 : kBM * kBK * 2;
+  static constexpr int kABytes = W4 ? 2 * kWin4Bytes : RE ? kWinRows * kBK * 2 : kBM * kBK * 2;
   static constexpr int kBTile = (BN / CL) * kBK * 2;                  // one tap's B bytes staged by THIS CTA
   static constexpr int kBBytes = RE ? 3 * kBTile : kBTile;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = RE ? (BN >= 256 ? 2 : 3) : (CL == 2) ? 6 : ((BN <= 128) ? 6 : 4);
+  static constexpr int kStages = W4 ? (BN >= 256 ? 3 : 4) : RE ? (BN >= 256 ? 2 : 3) : (CL == 2) ? 6 : ((BN <= 128) ? 6 : 4);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   static constexpr int kStagingBytes = 8 * 2 * 2048;   // per epilogue warp: two [32 rows][64 B] output boxes
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
@@ -91,9 +97,11 @@ template <int BN, int KIND, bool B_MN, int CL, bool RE = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmP P) {
-  using Cfg = GemmCfg<BN, CL, RE>;
+  constexpr bool W4 = (KIND == 4);
+  using Cfg = GemmCfg<BN, CL, RE, W4>;
   static_assert(!RE || (KIND == 0 && !B_MN && CL == 2), "window reuse: kind 0, K-major weights, CTA pairs");
-  constexpr bool A_MN = (KIND == 1 || KIND == 3);
+  static_assert(!W4 || (B_MN && CL == 1 && !RE), "two-accumulator weight gradient: single CTA, MN-major operands");
+  constexpr bool A_MN = (KIND == 1 || KIND == 3 || KIND == 4);
   constexpr bool B_SW64 = B_MN && ((BN / CL) % 64) != 0;     // a 96-column half: 32-column atoms, SWIZZLE_64B
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B tiles need 1024-byte alignment
@@ -163,6 +171,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             a_dh[i] = a_ok[i] ? P.tap.dh[t] : 0;
           }
         }
+        // KIND 4: the unit's four atoms live in two windows = the (kernel row, channel atom) of its first and last atom
+        int w4_c[2] = {0, 0}, w4_dh[2] = {0, 0};
+        if (W4) {
+          const int ca3 = 3 * P.a_atoms_per_tap, n_atoms = 3 * ca3;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int a = min(4 * tc.m_tile + 3 * i, n_atoms - 1);
+            const int kh = a / ca3;
+            w4_c[i] = ((a - kh * ca3) / 3) * 64;
+            w4_dh[i] = kh - 1;
+          }
+        }
         for (int k = 0; k < kiters; ++k) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
@@ -195,7 +215,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++cc == P.k_chunks) { cc = 0; ++tap; }
           } else {
             const int w0c = wq * kBK;
-            if (KIND == 3) {
+            if (W4) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+                load(sa + i * kWin4Bytes, &tmA, w4_c[i], 0, w0c - 1, ho * P.a_sh + w4_dh[i], n);
+#pragma unroll
+              for (int i = 0; i < BNL / 64; ++i) load(sb + i * 8192, &tmB, nb0 + 64 * i, 0, w0c, ho, n);
+            } else if (KIND == 3) {
               // A: two 64-channel atoms of the shifted activation, each with its own tap; B: dY, unshifted
 #pragma unroll
               for (int i = 0; i < kBM / 64; ++i)
@@ -237,8 +263,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kiters = RE ? (P.n_taps / 3) * P.k_chunks
                               : (KIND == 0) ? P.n_taps * P.k_chunks : (tc.q_end - tc.q_begin);
         mbar_wait(&tempty[as], aphase ^ 1);
+        if (W4) mbar_wait(&tempty[1], aphase ^ 1);             // a unit owns BOTH accumulators
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+        // KIND 4: byte offset of each of the unit's four atoms inside the stage's A region (window, row = kw)
+        uint32_t w4_off[4] = {0u, 0u, 0u, 0u};
+        if (W4) {
+          const int ca3 = 3 * P.a_atoms_per_tap, n_atoms = 3 * ca3;
+          const int a0 = min(4 * tc.m_tile, n_atoms - 1), g0 = a0 / 3;       // g = (kernel row, channel atom) index
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int a = min(4 * tc.m_tile + j, n_atoms - 1), g = a / 3;
+            w4_off[j] = static_cast<uint32_t>((g != g0 ? kWin4Bytes : 0) + (a - 3 * g) * 128);
+          }
+        }
         int re_row = 0, re_cc = 0;                             // RE: kernel row / channel chunk of this stage
         for (int k = 0; k < kiters; ++k) {
           mbar_wait(&full[stage], phase);
@@ -259,6 +297,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             if (++re_cc == P.k_chunks) { re_cc = 0; ++re_row; }
+          } else if (W4) {
+#pragma unroll
+            for (int acc = 0; acc < 2; ++acc) {
+              const uint32_t a_lo = sa + w4_off[2 * acc];
+              const uint32_t lbo = w4_off[2 * acc + 1] - w4_off[2 * acc];      // second 64-row half of the A tile
+#pragma unroll
+              for (int kk = 0; kk < kBK / 16; ++kk) {
+                const uint64_t da = umma_desc_sw128(a_lo + kk * 2048, lbo, 1024);
+                const uint64_t db = umma_desc_sw128(sb + kk * 2048, 8192, 1024);
+                umma_bf16(tmem_base + acc * BN, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+              }
+            }
           } else
 #pragma unroll
           for (int kk = 0; kk < kBK / 16; ++kk) {
@@ -274,7 +324,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (CL == 2) umma_commit_pair(&tfull[as], 3); else umma_commit(&tfull[as]);           // wakes both epilogues
-        if (kiters == 0) { /* unreachable: host never creates empty tiles */ }
+        if (W4) { umma_commit(&tfull[1]); aphase ^= 1; continue; }                            // as stays 0
         as ^= 1; if (as == 0) aphase ^= 1;
       }
     }
@@ -317,6 +367,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const TileCoord tc = decode_tile(P, id);
       const int n0 = tc.n_tile * BN;
       if ((P.flags & EPI_STATS) && tc.n_tile != stats_ntile) { flush_stats(stats_ntile); stats_ntile = tc.n_tile; }
+#pragma unroll 1
+      for (int sub = 0; sub < (W4 ? 2 : 1); ++sub) {          // KIND 4: a unit = two accumulators = two 128-row tiles
+      const int m_tile = W4 ? 2 * tc.m_tile + sub : tc.m_tile;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * kColsPerWarp;
@@ -389,7 +442,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (col < P.N_valid) {
             int c1, c2, c3, c4;
             if (KIND == 0) { c1 = tc.w0 + quad * 32; c2 = tc.h; c3 = tc.n; c4 = 0; }
-            else { c1 = tc.m_tile * kBM + quad * 32; c2 = tc.tap; c3 = (P.flags & EPI_ACCUM) ? 0 : tc.split; c4 = 0; }
+            else { c1 = m_tile * kBM + quad * 32; c2 = tc.tap; c3 = (P.flags & EPI_ACCUM) ? 0 : tc.split; c4 = 0; }
             if (P.flags & EPI_ACCUM)
               asm volatile(
                   "cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
@@ -422,6 +475,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         sbuf ^= 1;
       }
       as ^= 1; if (as == 0) aphase ^= 1;
+      }
     }
     if (P.flags & EPI_STATS) flush_stats(stats_ntile);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -530,7 +584,7 @@ int num_sms() {
 template <int BN, int KIND, bool B_MN, int CL, bool RE = false>
 int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
                cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CL, RE>;
+  using Cfg = GemmCfg<BN, CL, RE, KIND == 4>;
   static bool configured = false;
   auto kern = tapgemm_kernel<BN, KIND, B_MN, CL, RE>;
   if (!configured) {
@@ -587,7 +641,7 @@ int dbg_env(const char* name) {
 // horizontal taps sharing one staged activation window (GemmCfg RE).  HTRVT_NOREUSE=1 disables it.
 bool use_window_reuse(int ks, int sw, int cl, int bn, int n_taps) {
   static const int off = dbg_env("HTRVT_NOREUSE");
-  return !off && ks == 3 && sw == 1 && cl == 2 && n_taps == 9 && (bn == 192 || bn == 256);
+  return !off && ks == 3 && sw == 1 && cl == 2 && n_taps >= 3 && (n_taps % 3) == 0 && (bn == 192 || bn == 256);
 }
 int launch_reuse(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total,
                  cudaStream_t s) {
@@ -855,7 +909,8 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
       P.N_valid = Cin; P.flags = EPI_BF16 | (accumulate ? EPI_ACCUM : 0);
       P.alpha = 1.f;
       const int cl = pick_cluster(P.tiles_m, P.tiles_m * P.tiles_n, bn, !kmajor);
-      const bool reuse = kmajor && sh == 1 && use_window_reuse(ks, sw, cl, bn, n);
+      // (a vertical stride only thins the kernel rows of a parity class: 3 or 6 taps, still whole rows of 3)
+      const bool reuse = kmajor && use_window_reuse(ks, sw, cl, bn, n);
       if (reuse) {
         r = make_map_act(&ta, dy, NB, Ho, Wo, Cout, 1, kBK, kWinRows);
         if (r) return r;
@@ -997,6 +1052,51 @@ extern "C" int htrvt_conv_wgrad_acc_t(const void* dy, const void* x, int NB, int
   return launch_bn<3, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n * P.splits, stream);
 }
 
+// Weight gradient of a 3x3 convolution with horizontal stride 1, two live accumulators and shared x windows (KIND 4).
+// grad_atoms: fp32 [3 kh][Cin / 64][3 kw][64][Cout] (+=) - the GEMM's row order; htrvt_unpack_conv_grads takes it with
+// taps[i] = -1009.  Bytes staged per flop are ~half of htrvt_conv_wgrad_acc_t's (dY tile shared by 256 rows, the three
+// horizontal taps read from one window).
+extern "C" int htrvt_conv_wgrad_acc_w(const void* dy, const void* x, int NB, int H, int W, int Cin, int Cout, int sh,
+                                      float* grad_atoms, cudaStream_t stream) {
+  const int ks = 3, pad = 1, sw = 1;
+  if (!dy || !x || !grad_atoms || (Cout % 8) || (Cin % 64)) return HTRVT_ERR_SHAPE;
+  const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
+  const int bn = pick_bn(Cout);
+  GemmP P = {};
+  P.a_taps = 9;
+  P.a_atoms_per_tap = Cin / 64;
+  const int n_atoms = 9 * P.a_atoms_per_tap;
+  CUtensorMap ta, tb, tc;
+  int r = make_map_act(&ta, x, NB, H, W, Cin, 1, 64, kWin4Rows);
+  if (r) return r;
+  r = make_map_act(&tb, dy, NB, Ho, Wo, Cout, 1, 64, 64);
+  if (r) return r;
+  {
+    const long long rows = static_cast<long long>(n_atoms) * 64;
+    const long long dims[5] = {Cout, rows, 1, 1, 1};
+    const long long big = rows * Cout;
+    const long long st[4] = {Cout, big, big, big};
+    const int box[5] = {16, 32, 1, 1, 1};
+    r = make_map5(&tc, grad_atoms, dims, st, box, 4, true);
+    if (r) return r;
+  }
+  P.kind = 4; P.Wo = Wo; P.Ho = Ho; P.NB = NB; P.tiles_per_row = 1;
+  P.tiles_m = (n_atoms + 3) / 4; P.tiles_n = (Cout + bn - 1) / bn; P.n_taps = 1;
+  P.k_chunks = (Wo + 63) / 64; P.a_sh = sh;
+  const long long Q = static_cast<long long>(NB) * Ho * P.k_chunks;
+  const long long per = static_cast<long long>(Cout) * 9 * Cin;
+  P.splits = choose_splits(P.tiles_m * P.tiles_n, 2 * Q, per / 2);          // a unit's k-chunk is two tiles' worth of MMA
+  P.M_valid = n_atoms * 64; P.N_valid = Cout; P.alpha = 1.f;
+  P.flags = EPI_ACCUM | (dbg_env("HTRVT_DBG_WGRAD_NOSTORE") ? EPI_NOSTORE : 0);
+  const int total = P.tiles_m * P.tiles_n * P.splits;
+  switch (bn) {
+    case 128: return launch_one<128, 4, true, 1>(ta, tb, tc, P, total, stream);
+    case 192: return launch_one<192, 4, true, 1>(ta, tb, tc, P, total, stream);
+    case 256: return launch_one<256, 4, true, 1>(ta, tb, tc, P, total, stream);
+  }
+  return HTRVT_ERR_SHAPE;
+}
+
 // dst_oihw[i] += permute(src[i]) for n <= 64 conv weights per launch: taps[i] > 0: src [Cout][taps][Cin];
 // taps[i] < 0: src [|taps|][Cin][Cout] (the transposed weight-gradient GEMM)
 namespace htrvt {
@@ -1018,7 +1118,8 @@ __global__ void __launch_bounds__(256) unpack_conv_grads_kernel(const __grid_con
   if (taps < 0) {
     // src [tp][Cin][Cout] (htrvt_conv_wgrad_acc_t) -> dst [Cout][Cin][tp]: tiles of 8 co x 64 ci x tp taps through
     // smem - 32-byte read segments along co, contiguous RMW of 64 * tp floats per output channel
-    const int tp = -taps, per = Cin * tp;
+    const bool atoms = taps <= -1000;                 // [kh][Cin/64][kw][64][Cout] (htrvt_conv_wgrad_acc_w)
+    const int tp = atoms ? -taps - 1000 : -taps, per = Cin * tp;
     const int Cout = static_cast<int>(n / per);
     const int tiles_ci = Cin / 64, tiles = (Cout / 8) * tiles_ci, cnt = tp * 64 * 8;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -1026,7 +1127,9 @@ __global__ void __launch_bounds__(256) unpack_conv_grads_kernel(const __grid_con
       __syncthreads();
       for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
         const int co = i & 7, ci = (i >> 3) & 63, tap = i >> 9;
-        up_stage[(tap * 64 + ci) * 9 + co] = src[(static_cast<long long>(tap) * Cin + ci0 + ci) * Cout + co0 + co];
+        const long long row = atoms ? ((static_cast<long long>(tap / 3) * (Cin / 64) + ci0 / 64) * 3 + tap % 3) * 64 + ci
+                                    : static_cast<long long>(tap) * Cin + ci0 + ci;
+        up_stage[(tap * 64 + ci) * 9 + co] = src[row * Cout + co0 + co];
       }
       __syncthreads();
       for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
@@ -1066,7 +1169,7 @@ extern "C" int htrvt_unpack_conv_grads(int n, const void* const* src, void* cons
     }
     int smem = 0;
     for (int i = 0; i < cnt; ++i) {
-      const int need = T.taps[i] > 0 ? T.cin[i] * T.taps[i] * 4 : -T.taps[i] * 64 * 9 * 4;
+      const int need = T.taps[i] > 0 ? T.cin[i] * T.taps[i] * 4 : (T.taps[i] <= -1000 ? 9 : -T.taps[i]) * 64 * 9 * 4;
       if (need > smem) smem = need;
     }
     if (smem > 48 * 1024) return HTRVT_ERR_SHAPE;

@@ -288,19 +288,36 @@ class Engine(object):
 
         # ---- stem blocks ------------------------------------------------------------------------
         # conv weight gradients accumulate in the GEMM's natural output layout (split-K slices reduce-add in place) in
-        # one zeroed buffer and are permuted into the OIHW .grad tensors by ONE launch.  Cout a multiple of 128:
-        # [Cout, taps, Cin] (rows = Cout); otherwise (192-channel layers) the transposed GEMM, [taps, Cin, Cout],
-        # whose rows = (tap, 64-channel atom) waste no MMA rows
+        # one zeroed buffer and are permuted into the OIHW .grad tensors by one launch per layout:
+        #   "atoms": 3x3 convs with horizontal stride 1 - the two-accumulator, window-sharing GEMM,
+        #            rows = (kernel row, 64-channel atom, kw): [3, Cin/64, 3, 64, Cout];
+        #   "tco"  : other convs whose Cout is not a multiple of 128 - transposed GEMM, [taps, Cin, Cout];
+        #   "ctc"  : the rest (stride-2 3x3, 1x1 downsamples of the 384 / 768-channel layers) - [Cout, taps, Cin]
         cnames = [k for k in wp if k.startswith("patch_embed.")]
+        hstride = {}
+        for (p, s, *_rest) in ctx.blocks:
+            hstride[p + ".conv1.weight"] = s[1]
+            hstride[p + ".conv2.weight"] = 1
         gt_flat = torch.zeros(sum(wp[k].numel() for k in cnames), dtype=torch.float32, device=dev)
-        gt, off = {}, 0
+        gt, layout, off = {}, {}, 0
         for k in cnames:
             co, tp, ci = wp[k].shape
-            gt[k] = gt_flat[off:off + wp[k].numel()].view((tp, ci, co) if (co % 128) else (co, tp, ci))
+            if tp == 9 and hstride.get(k, 0) == 1:
+                layout[k], shape = "atoms", (3, ci // 64, 3, 64, co)
+            elif co % 128:
+                layout[k], shape = "tco", (tp, ci, co)
+            else:
+                layout[k], shape = "ctc", (co, tp, ci)
+            gt[k] = gt_flat[off:off + wp[k].numel()].view(shape)
             off += wp[k].numel()
 
         def wgrad(dy, x, ks, sh, sw, name):
-            (ops.conv_wgrad_acc_t if (wp[name].shape[0] % 128) else ops.conv_wgrad_acc)(dy, x, ks, sh, sw, gt[name])
+            if layout[name] == "atoms":
+                ops.conv_wgrad_acc_w(dy, x, sh, gt[name])
+            elif layout[name] == "tco":
+                ops.conv_wgrad_acc_t(dy, x, ks, sh, sw, gt[name])
+            else:
+                ops.conv_wgrad_acc(dy, x, ks, sh, sw, gt[name])
         for (p, s, xin, r1, sa, a1, k1, r2, sb, rd, sdn, k2) in reversed(ctx.blocks):
             has_ds = rd is not None
             d2, dd, gz = ops.bn_bwd(
@@ -323,8 +340,9 @@ class Engine(object):
                 gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1], dx=gz,
                                      accumulate=True, w_t=wp.get("T:" + p + ".conv1.weight"))
             g = gin
-        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames if wp[k].shape[0] % 128], transposed=True)
-        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames if not (wp[k].shape[0] % 128)])
+        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames if layout[k] == "atoms"], layout="atoms")
+        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames if layout[k] == "tco"], transposed=True)
+        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames if layout[k] == "ctc"])
         # ---- stem head: pool -> relu -> bn1 -> conv1 ---------------------------------------------
         if ctx.moments is None:
             raise ops.HtrvtError("backward needs a train-mode forward (batch statistics)")

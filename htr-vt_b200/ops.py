@@ -96,7 +96,18 @@ def conv_wgrad_acc_t(dy, x, ks, sh, sw, grad_tco):
     return grad_tco
 
 
-def unpack_conv_grads(pairs, transposed=False):
+def conv_wgrad_acc_w(dy, x, sh, grad_atoms):
+    """3x3 conv, horizontal stride 1: grad_atoms fp32 [3, Cin/64, 3, 64, Cout] += (two-accumulator, window-sharing
+    weight-gradient GEMM).  unpack_conv_grads(..., layout="atoms") permutes it into OIHW."""
+    _need_cuda(dy, x, grad_atoms)
+    N, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    check(lib().htrvt_conv_wgrad_acc_w(_p(dy), _p(x), N, H, W, Cin, Cout, sh, _p(grad_atoms), _stream()),
+          "htrvt_conv_wgrad_acc_w")
+    return grad_atoms
+
+
+def unpack_conv_grads(pairs, transposed=False, layout=None):
     """pairs: list of (src, dst fp32 OIHW): dst += permute(src), one launch for all.
     src fp32 [Cout, taps, Cin] (conv_wgrad_acc) or, transposed=True, [taps, Cin, Cout] (conv_wgrad_acc_t)."""
     n = len(pairs)
@@ -109,7 +120,9 @@ def unpack_conv_grads(pairs, transposed=False):
     taps = (ctypes.c_int * n)()
     for i, (a, b) in enumerate(pairs):
         src[i], dst[i], numel[i] = a.data_ptr(), b.data_ptr(), b.numel()
-        if transposed:
+        if layout == "atoms":                       # [3, Cin/64, 3, 64, Cout]
+            cin[i], taps[i] = a.shape[1] * 64, -1009
+        elif transposed:
             cin[i], taps[i] = a.shape[1], -a.shape[0]
         else:
             cin[i], taps[i] = a.shape[2], a.shape[1]
@@ -633,6 +646,9 @@ def _flops(name, a, kw):
         if name == "conv_dgrad":
             dy, w, xs, ks = a[:4]
             return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * xs[3]
+        if name == "conv_wgrad_acc_w":
+            dy, x = a[:2]
+            return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * 9 * x.shape[3]
         if name in ("conv_wgrad_acc", "conv_wgrad_acc_t"):
             dy, x, ks = a[:3]
             return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * x.shape[3]
@@ -659,7 +675,7 @@ def _flops(name, a, kw):
 def _instrument():
     import functools
     g = globals()
-    names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc", "conv_wgrad_acc_t", "unpack_conv_grads", "attention_fwd",
+    names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc", "conv_wgrad_acc_t", "conv_wgrad_acc_w", "unpack_conv_grads", "attention_fwd",
              "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "sample_ln_fwd", "sample_ln_bwd", "line_prep_u8", "edit_distance",
              "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16", "dropout_",
              "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",

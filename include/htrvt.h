@@ -89,6 +89,11 @@ int htrvt_conv_wgrad_acc(const void* dy, const void* dy_t, const void* x, int NB
  * htrvt_unpack_conv_grads takes this layout with taps[i] = -(ks*ks). */
 int htrvt_conv_wgrad_acc_t(const void* dy, const void* x, int NB, int H, int W, int Cin, int Cout, int ks, int sh,
                            int sw, float* grad_tco, void* stream);
+/* 3x3, horizontal stride 1: two live accumulators share the dY tile and read x through two staged windows (the
+ * three horizontal taps = one window at row offsets 0 / 1 / 2).  grad_atoms fp32 [3][Cin/64][3][64][Cout] (+=);
+ * htrvt_unpack_conv_grads takes this layout with taps[i] = -1009. */
+int htrvt_conv_wgrad_acc_w(const void* dy, const void* x, int NB, int H, int W, int Cin, int Cout, int sh,
+                           float* grad_atoms, void* stream);
 int htrvt_unpack_conv_grads(int n, const void* const* src_tapmajor, void* const* dst_oihw, const long long* numel,
                             const int* cin, const int* taps, void* stream);
 /* bf16 [R][P][C] -> [R][C][P]: pixel-contiguous copy of a stem gradient (dy_t above; tcgen05 runs an MN-major A

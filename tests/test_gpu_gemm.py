@@ -152,6 +152,15 @@ def test_conv_fwd_dgrad_wgrad(NB, H, W, Cin, Cout, ks, sh, sw):
     gw2 = torch.ones(Cout, Cin, ks, ks, device="cuda")
     o.unpack_conv_grads([(gt, gw2)], transposed=True)
     assert _rel(gw2 - 1.0, wr.grad) < 1e-3
+    if ks == 3 and sw == 1:
+        # two-accumulator window-sharing weight gradient ([3, Cin/64, 3, 64, Cout] rows) + its unpack mode
+        ga = torch.zeros(3, Cin // 64, 3, 64, Cout, device="cuda")
+        o.conv_wgrad_acc_w(dy, x, sh, ga)
+        want = wr.grad.permute(2, 1, 3, 0).reshape(3, Cin // 64, 64, 3, Cout).permute(0, 1, 3, 2, 4)   # kh, c, kw, 64, co
+        assert _rel(ga, want) < 1e-3
+        gw3 = torch.ones(Cout, Cin, ks, ks, device="cuda")
+        o.unpack_conv_grads([(ga, gw3)], layout="atoms")
+        assert _rel(gw3 - 1.0, wr.grad) < 1e-3
     gw = torch.zeros(Cout, Cin, ks, ks, device="cuda")
     o.conv_wgrad(dy, x, ks, sh, sw, gw, accumulate=False, transpose=True)      # K-major dY^T operand (transpose_px)
     assert _rel(gw, wr.grad) < 1e-3

@@ -77,6 +77,9 @@ cases = {
     "l1_wgrad_t": (lambda: o.conv_wgrad_acc_t(yl1, xl1, 3, 1, 1, gt1.view(9, 192, 192)), 2.0 * 128 * 8 * 512 * 192 * 1728),
     "l2_wgrad_t": (lambda: o.conv_wgrad_acc_t(yl2, xl2, 3, 1, 1, gt2.view(9, 384, 384)), 2.0 * 128 * 4 * 256 * 384 * 3456),
     "l3_wgrad_t": (lambda: o.conv_wgrad_acc_t(yl3, xl3, 3, 1, 1, gt3.view(9, 768, 768)), 2.0 * 128 * 2 * 128 * 768 * 6912),
+    "l1_wgrad_w": (lambda: o.conv_wgrad_acc_w(yl1, xl1, 1, gt1.view(3, 3, 3, 64, 192)), 2.0 * 128 * 8 * 512 * 192 * 1728),
+    "l2_wgrad_w": (lambda: o.conv_wgrad_acc_w(yl2, xl2, 1, gt2.view(3, 6, 3, 64, 384)), 2.0 * 128 * 4 * 256 * 384 * 3456),
+    "l3_wgrad_w": (lambda: o.conv_wgrad_acc_w(yl3, xl3, 1, gt3.view(3, 12, 3, 64, 768)), 2.0 * 128 * 2 * 128 * 768 * 6912),
     "l1_wgrad": (lambda: o.conv_wgrad(yl1, xl1, 3, 1, 1, gl1), 2.0 * 128 * 8 * 512 * 192 * 1728),
     "l3_fwd_stats": (lambda: o.conv_fwd(xl3, wl3, 3, 1, 1, y=yl3, stats=stats3), 2.0 * 128 * 2 * 128 * 768 * 6912),
     "l2_wgrad": (lambda: o.conv_wgrad(yl2, xl2, 3, 1, 1, gl2), 2.0 * 128 * 4 * 256 * 384 * 3456),
