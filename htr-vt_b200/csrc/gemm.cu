@@ -1173,7 +1173,7 @@ extern "C" int htrvt_unpack_conv_grads(int n, const void* const* src, void* cons
       if (need > smem) smem = need;
     }
     if (smem > 48 * 1024) return HTRVT_ERR_SHAPE;
-    dim3 grid(148, cnt);
+    dim3 grid(4 * 148, cnt);                          // several 256-thread blocks per SM: the pass is pure HBM streaming
     unpack_conv_grads_kernel<<<grid, 256, smem, stream>>>(T);
     HTRVT_LAUNCH_CHECK();
   }

@@ -663,7 +663,7 @@ extern "C" int htrvt_pack_weights(int n, const void* const* src, void* const* ds
     for (int i = 0; i < cnt; ++i)
       if (T.taps[i] < 0 && smem < 32 * 33 * 4) smem = 32 * 33 * 4;
     if (smem > 48 * 1024) return HTRVT_ERR_SHAPE;
-    dim3 grid(96, cnt);
+    dim3 grid(4 * 148, cnt);
     pack_weights_kernel<<<grid, 256, smem, stream>>>(T);
     HTRVT_LAUNCH_CHECK();
   }

@@ -103,6 +103,7 @@ __global__ void conv1_moments_finalize_kernel(const float* __restrict__ partial,
 // forward: x fp32 [B,H,W] -> out bf16 [B,Ho,W,C] (Ho = (H/2 - 1)/2 + 1), code nibbles [B,Ho,W,C/2]
 // grid (ceil(W/64), ceil(Ho/2), B); blockDim = C: thread -> channel pair (tid % (C/2)), column half (tid / (C/2))
 // ------------------------------------------------------------------------------------------------
+template <bool CODE>      // CODE = false (inference): no arg-max bookkeeping, the pooled value alone
 __global__ void __launch_bounds__(256) stem_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ scale,
                                                              const float* __restrict__ shift,
@@ -166,10 +167,15 @@ __global__ void __launch_bounds__(256) stem_head_fwd_kernel(const float* __restr
       for (int q = 0; q < 2; ++q) {
         float va = ya[2 * q], vb = yb[2 * q];
         int ka = 0, kb = 0;
-        if (ya[2 * q + 1] > va) { va = ya[2 * q + 1]; ka = 1; }
-        if (ya[2 * q + 2] > va) { va = ya[2 * q + 2]; ka = 2; }
-        if (yb[2 * q + 1] > vb) { vb = yb[2 * q + 1]; kb = 1; }
-        if (yb[2 * q + 2] > vb) { vb = yb[2 * q + 2]; kb = 2; }
+        if (CODE) {
+          if (ya[2 * q + 1] > va) { va = ya[2 * q + 1]; ka = 1; }
+          if (ya[2 * q + 2] > va) { va = ya[2 * q + 2]; ka = 2; }
+          if (yb[2 * q + 1] > vb) { vb = yb[2 * q + 1]; kb = 1; }
+          if (yb[2 * q + 2] > vb) { vb = yb[2 * q + 2]; kb = 2; }
+        } else {
+          va = fmaxf(va, fmaxf(ya[2 * q + 1], ya[2 * q + 2]));
+          vb = fmaxf(vb, fmaxf(yb[2 * q + 1], yb[2 * q + 2]));
+        }
         cva[q][s] = va; cka[q][s] = ka; cvb[q][s] = vb; ckb[q][s] = kb;
       }
       const int wo = w0 + cb + j - 2;
@@ -181,15 +187,20 @@ __global__ void __launch_bounds__(256) stem_head_fwd_kernel(const float* __restr
           // first maximum in (kh, kw) row-major order = torch's max_pool2d arg-max rule
           float ba = cva[q][(s + 1) % 3], bb = cvb[q][(s + 1) % 3];
           int kha = cka[q][(s + 1) % 3], khb = ckb[q][(s + 1) % 3], kwa = 0, kwb = 0;
+          if (CODE) {
 #pragma unroll
-          for (int kw = 1; kw < 3; ++kw) {
-            const int sl = (s + 1 + kw) % 3;
-            if (cva[q][sl] > ba || (cva[q][sl] == ba && cka[q][sl] < kha)) { ba = cva[q][sl]; kha = cka[q][sl]; kwa = kw; }
-            if (cvb[q][sl] > bb || (cvb[q][sl] == bb && ckb[q][sl] < khb)) { bb = cvb[q][sl]; khb = ckb[q][sl]; kwb = kw; }
+            for (int kw = 1; kw < 3; ++kw) {
+              const int sl = (s + 1 + kw) % 3;
+              if (cva[q][sl] > ba || (cva[q][sl] == ba && cka[q][sl] < kha)) { ba = cva[q][sl]; kha = cka[q][sl]; kwa = kw; }
+              if (cvb[q][sl] > bb || (cvb[q][sl] == bb && ckb[q][sl] < khb)) { bb = cvb[q][sl]; khb = ckb[q][sl]; kwb = kw; }
+            }
+          } else {
+            ba = fmaxf(ba, fmaxf(cva[q][(s + 2) % 3], cva[q][s % 3]));
+            bb = fmaxf(bb, fmaxf(cvb[q][(s + 2) % 3], cvb[q][s % 3]));
           }
           const long long o = ((static_cast<long long>(n) * Ho + ho) * W + wo);
           *reinterpret_cast<uint32_t*>(out + o * C + 2 * cp) = pack_bf16(ba, bb);
-          if (code) {
+          if (CODE && code) {
             const unsigned na = ba > 0.f ? static_cast<unsigned>(kha * 3 + kwa) : 15u;
             const unsigned nb = bb > 0.f ? static_cast<unsigned>(khb * 3 + kwb) : 15u;
             code[o * half_c + cp] = static_cast<uint8_t>(na | (nb << 4));
@@ -414,7 +425,7 @@ extern "C" int htrvt_stem_head_fwd(const float* x, const float* w, const float* 
   if (!head_shape_ok(B, H, W, C)) return HTRVT_ERR_SHAPE;
   const int Ho = (H / 2 - 1) / 2 + 1;
   dim3 grid((W + 63) / 64, (Ho + 1) / 2, B);
-  stem_head_fwd_kernel<<<grid, C, 0, stream>>>(x, w, scale, shift, static_cast<__nv_bfloat16*>(out),
+  (code ? stem_head_fwd_kernel<true> : stem_head_fwd_kernel<false>)<<<grid, C, 0, stream>>>(x, w, scale, shift, static_cast<__nv_bfloat16*>(out),
                                                static_cast<uint8_t*>(code), B, H, W, C);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;

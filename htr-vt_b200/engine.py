@@ -90,8 +90,18 @@ class Engine(object):
                 names.append(k)
                 items.append((v, "cast"))
         C8 = (C + 7) // 8 * 8            # the head GEMM runs on a class axis padded to a multiple of 8 (zero rows)
-        wp = dict(zip(names, ops.pack_weights(items, pad_rows={"head.weight": C8} if C8 != C else None,
-                                              names=names)))    # one launch for all 36 weight tensors
+        # eval mode: the packed copies are reused while no parameter changed (autograd version counters + the epoch
+        # our own raw-pointer optimizer kernels bump); train mode repacks every forward (SAM rewrites the weights)
+        key = None
+        if not training and not save:
+            key = (ops.WEIGHT_EPOCH, tuple((v.data_ptr(), v._version) for v, _ in items))
+        cached = getattr(self, "_wp_cache", None)
+        if key is not None and cached is not None and cached[0] == key:
+            wp = cached[1]
+        else:
+            wp = dict(zip(names, ops.pack_weights(items, pad_rows={"head.weight": C8} if C8 != C else None,
+                                                  names=names)))    # one launch for all 36 weight tensors
+            self._wp_cache = (key, wp) if key is not None else None
 
         # ---- stem -----------------------------------------------------------------------------
         if u8:

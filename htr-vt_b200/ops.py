@@ -629,6 +629,14 @@ def launch_count() -> int:
 # Optional per-op CUDA-event profile (bench.py's roofline leg, tools/): PROFILE = [] enables it.
 # ------------------------------------------------------------------------------------------------
 PROFILE = None
+# bumped by every kernel that rewrites parameters through raw pointers (SAM / AdamW / EMA): autograd's version counters
+# do not see those writes, and the engine keys its eval-mode cache of packed bf16 weights on (versions, this epoch)
+WEIGHT_EPOCH = 0
+
+
+def weights_changed():
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
 
 
 def _flops(name, a, kw):

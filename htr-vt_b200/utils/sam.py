@@ -14,6 +14,7 @@ import ctypes
 
 import torch
 
+from .. import ops as _ops
 from .._lib import check, lib
 
 
@@ -94,6 +95,7 @@ class SAM(torch.optim.Optimizer):
                                            _ptrs(olds), _numels(ps), ctypes.c_void_p(norm2.data_ptr()),
                                            float(group["rho"]), int(bool(group["adaptive"])), _stream()),
                   "htrvt_mt_sam_first")
+        _ops.weights_changed()
         if zero_grad:
             self.zero_grad()
 
@@ -128,6 +130,7 @@ class SAM(torch.optim.Optimizer):
                                        _ptrs(vs), _ptrs(olds), _numels(ps), float(lr), float(b1), float(b2),
                                        float(group["eps"]), float(group["weight_decay"]), steps.pop(), _stream()),
                   "htrvt_mt_adamw")
+        _ops.weights_changed()
         if not self._fused_adamw:
             self.base_optimizer.step()                        # do the actual "sharpness-aware" update
         if zero_grad:

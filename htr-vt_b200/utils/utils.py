@@ -7,6 +7,7 @@ from copy import deepcopy
 
 import torch
 
+from .. import ops as _ops
 from .._lib import check, lib
 from .sam import _numels, _ptrs, _stream
 
@@ -65,3 +66,4 @@ class ModelEma:
             if fused_e:
                 check(lib().htrvt_mt_ema(len(fused_e), _ptrs(fused_e), _ptrs(fused_m), _numels(fused_e),
                                          float(_cdecay), _stream()), "htrvt_mt_ema")
+                _ops.weights_changed()

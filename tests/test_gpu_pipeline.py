@@ -124,3 +124,29 @@ def test_cer_from_device_ids_full_batch():
         pos += tl[b]
     assert d.cpu().tolist() == want
     assert int(n) == int(tl.sum())
+
+
+def test_eval_weight_cache_follows_parameter_updates():
+    """Eval mode reuses the packed bf16 weights; an in-place parameter update (optimizer / load_state_dict bump the
+    autograd version, our raw-pointer SAM / EMA kernels bump ops.WEIGHT_EPOCH) must be seen by the next forward."""
+    from functools import partial
+    from importlib import import_module
+    H = import_module("htr-vt_b200.model.HTR_VT")
+    U = import_module("htr-vt_b200.utils.utils")
+    m = H.MaskedAutoencoderViT(24, img_size=[64, 128], patch_size=(4, 64), embed_dim=256, depth=1, num_heads=2,
+                               mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    m.load_state_dict(O.init_state_dict(24, [64, 128], seed=3, embed_dim=256, depth=1, num_heads=2), strict=True)
+    m = m.cuda().eval()
+    x = torch.from_numpy(np.random.RandomState(2).rand(2, 1, 64, 128).astype(np.float32)).cuda()
+    with torch.no_grad():
+        a = m(x).clone()
+        assert torch.equal(m(x), a)                        # cached weights: bit-identical
+        m.head.weight.mul_(2.0)                            # version bump
+        b = m(x).clone()
+        assert float((b - a).abs().max()) > 1e-3
+        ema = U.ModelEma(m, 0.5)                           # deep copy, eval mode
+        e0 = ema.ema(x).clone()
+        m.head.weight.mul_(0.0)
+        ema.update(m)                                      # raw-pointer kernel: epoch bump
+        e1 = ema.ema(x)
+        assert float((e1 - e0).abs().max()) > 1e-3
