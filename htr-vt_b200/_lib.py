@@ -51,7 +51,7 @@ SIGNATURES = {
     "htrvt_gemm_nn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _F, _P]),
     "htrvt_wgrad_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "htrvt_linear_wgrad": (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _Z, _P]),
-    "htrvt_conv_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "htrvt_conv_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "htrvt_conv_fwd_stats_rows": (_I, [_I, _I, _I, _I, _I, _I]),
     "htrvt_conv_dgrad": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "htrvt_transpose_px": (_I, [_P, _P, _L, _I, _I, _P]),
@@ -73,7 +73,7 @@ SIGNATURES = {
     "htrvt_colsum_bf16": (_I, [_P, _L, _I, _I, _P, _I, _P, _P]),
     "htrvt_cast_bf16": (_I, [_P, _P, _L, _P]),
     "htrvt_dropout_bf16": (_I, [_P, _L, _L, _F, ctypes.c_ulonglong, ctypes.c_uint, _P, _P]),
-    "htrvt_pack_weights": (_I, [_I, _P, _P, _P, _P, _P, _P]),
+    "htrvt_pack_weights": (_I, [_I, _P, _P, _P, _P, _P, _P, _P]),
     "htrvt_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "htrvt_conv1_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_bn_finalize": (_I, [_P, _I, ctypes.c_double, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P]),

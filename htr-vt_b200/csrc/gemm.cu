@@ -844,8 +844,10 @@ extern "C" int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, i
                             // per-CTA rows + a fixed-order finalise keep the train-mode FORWARD bit-reproducible
 }
 
+// bias (nullable, fp32 [Cout]): added in the epilogue before the optional ReLU (eval mode: the folded BatchNorm shift)
 extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks,
-                              int sh, int sw, void* y, float* stats_partial, int flags, cudaStream_t stream) {
+                              int sh, int sw, void* y, float* stats_partial, int flags, const float* bias,
+                              cudaStream_t stream) {
   const int pad = ks / 2;
   if ((Cin % 64) || (Cout & 7) || (W % sw) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
@@ -868,8 +870,9 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
   fill_taps_conv(P.tap, ks, pad, sw, &P.n_taps);
   P.splits = 1; P.k_chunks = Cin / kBK; P.a_sh = sh; P.b_tap_stride = Cin;
   P.M_valid = 0; P.N_valid = Cout;
-  P.flags = EPI_BF16 | (flags & (EPI_RELU | EPI_NOSTORE)) | (stats_partial ? EPI_STATS : 0);
-  P.stats = stats_partial; P.alpha = 1.f;
+  if (bias && ((Cout & 3) || stats_partial)) return HTRVT_ERR_SHAPE;
+  P.flags = EPI_BF16 | (flags & (EPI_RELU | EPI_NOSTORE)) | (stats_partial ? EPI_STATS : 0) | (bias ? EPI_BIAS : 0);
+  P.stats = stats_partial; P.bias = bias; P.alpha = 1.f;
   if (reuse) return launch_reuse(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
   return launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }

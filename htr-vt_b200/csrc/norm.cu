@@ -362,6 +362,7 @@ struct PackTable {
   long long numel[kMaxPack];
   int cin[kMaxPack];
   int taps[kMaxPack];
+  const float* scale[kMaxPack];          // conv repack only: per-output-channel factor (BatchNorm folding), or null
 };
 __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackTable T) {
   extern __shared__ float pk_stage[];                   // one output channel's [Cin][taps] block (conv repack)
@@ -404,13 +405,15 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
   // fp32 read and the bf16 write are contiguous
   const int per = Cin * taps;
   const int Cout = static_cast<int>(n / per);
+  const float* __restrict__ sc = T.scale[t];
   for (int co = blockIdx.x; co < Cout; co += gridDim.x) {
+    const float f = sc ? sc[co] : 1.0f;
     __syncthreads();
     for (int i = threadIdx.x; i < per; i += blockDim.x) pk_stage[i] = src[static_cast<long long>(co) * per + i];
     __syncthreads();
     for (int i = threadIdx.x; i < per; i += blockDim.x) {
       const int tap = i / Cin, ci = i - tap * Cin;
-      dst[static_cast<long long>(co) * per + i] = __float2bfloat16_rn(pk_stage[ci * taps + tap]);
+      dst[static_cast<long long>(co) * per + i] = __float2bfloat16_rn(pk_stage[ci * taps + tap] * f);
     }
   }
 }
@@ -642,10 +645,12 @@ extern "C" int htrvt_pack_conv_weight(const float* w_oihw, void* dst, int Cout, 
   return HTRVT_OK;
 }
 
-// n tensors per call: src fp32, dst bf16, numel elements; taps[i] == 0 -> cast, > 0 -> OIHW -> [Cout][taps][Cin],
+// n tensors per call: src fp32, dst bf16, numel elements; scale (nullable array of nullable fp32 [Cout] pointers):
+// per-output-channel factor folded into a conv repack (eval-mode BatchNorm folding);
+// taps[i] == 0 -> cast, > 0 -> OIHW -> [Cout][taps][Cin],
 // < 0 -> transposed cast [cin[i]][numel/cin[i]] -> [numel/cin[i]][cin[i]] (cin[i] = rows of the source matrix)
 extern "C" int htrvt_pack_weights(int n, const void* const* src, void* const* dst, const long long* numel,
-                                  const int* cin, const int* taps, cudaStream_t stream) {
+                                  const int* cin, const int* taps, const void* const* scale, cudaStream_t stream) {
   if (n <= 0) return HTRVT_OK;
   for (int base = 0; base < n; base += kMaxPack) {
     PackTable T = {};
@@ -656,6 +661,8 @@ extern "C" int htrvt_pack_weights(int n, const void* const* src, void* const* ds
       T.numel[i] = numel[base + i];
       T.cin[i] = cin[base + i] > 0 ? cin[base + i] : 1;
       T.taps[i] = taps[base + i];
+      T.scale[i] = scale ? static_cast<const float*>(scale[base + i]) : nullptr;
+      if (T.scale[i] && T.taps[i] <= 1) return HTRVT_ERR_SHAPE;      // folding is wired for the k x k conv repack only
     }
     int smem = 0;
     for (int i = 0; i < cnt; ++i)

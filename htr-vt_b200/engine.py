@@ -92,16 +92,27 @@ class Engine(object):
         C8 = (C + 7) // 8 * 8            # the head GEMM runs on a class axis padded to a multiple of 8 (zero rows)
         # eval mode: the packed copies are reused while no parameter changed (autograd version counters + the epoch
         # our own raw-pointer optimizer kernels bump); train mode repacks every forward (SAM rewrites the weights)
-        key = None
-        if not training and not save:
-            key = (ops.WEIGHT_EPOCH, tuple((v.data_ptr(), v._version) for v, _ in items))
+        # Eval mode also FOLDS each block's bn1 into conv1 (running statistics: w' = w * scale[co] in the repack, shift + ReLU
+        # in the conv epilogue), so that BatchNorm pass disappears, and keeps every BN's affine coefficients in the cache.
+        fold = not training and not save
+        key = bnst = None
+        if fold:
+            stem = [v for k, v in sd.items() if k.startswith("patch_embed.")]
+            key = (ops.WEIGHT_EPOCH, tuple((v.data_ptr(), v._version) for v, _ in items),
+                   tuple((v.data_ptr(), v._version) for v in stem))
         cached = getattr(self, "_wp_cache", None)
         if key is not None and cached is not None and cached[0] == key:
-            wp = cached[1]
+            wp, bnst = cached[1], cached[2]
         else:
+            if fold:
+                bnst = {k[:-len(".running_mean")]: self._bn(sd, k[:-len(".running_mean")], None, 1, False)
+                        for k in sd if k.startswith("patch_embed.") and k.endswith(".running_mean")}
+                items = [(v, kind, bnst[n[:-len(".conv1.weight")] + ".bn1"][2])
+                         if (kind == "conv" and n.endswith(".conv1.weight") and n.count(".") == 4) else (v, kind)
+                         for n, (v, kind) in zip(names, items)]
             wp = dict(zip(names, ops.pack_weights(items, pad_rows={"head.weight": C8} if C8 != C else None,
                                                   names=names)))    # one launch for all 36 weight tensors
-            self._wp_cache = (key, wp) if key is not None else None
+            self._wp_cache = (key, wp, bnst) if key is not None else None
 
         # ---- stem -----------------------------------------------------------------------------
         if u8:
@@ -113,7 +124,7 @@ class Engine(object):
         moments = part = None
         if training:
             moments, part = ops.stem_head_moments(x0, w1)
-        st1 = self._bn(sd, "patch_embed.bn1", part, B * (Hi // 2) * Wi, training)
+        st1 = bnst["patch_embed.bn1"] if fold else self._bn(sd, "patch_embed.bn1", part, B * (Hi // 2) * Wi, training)
         x, code1 = ops.stem_head_fwd(x0, w1, st1, save)
         blocks = []
         zpool = None
@@ -125,16 +136,23 @@ class Engine(object):
             for bi in range(2):
                 p = "patch_embed.%s.%d" % (lname, bi)
                 s = stride if bi == 0 else (1, 1)
-                r1, pt1 = self._conv(x, wp[p + ".conv1.weight"], 3, s, training, zpool)
-                cnt = r1.numel() // r1.shape[-1]
-                sa = self._bn(sd, p + ".bn1", pt1, cnt, training)
-                a1, k1 = ops.bn_act_fwd(r1, sa, True, want_mask=save) if save else (ops.bn_act_fwd(r1, sa, True), None)
-                r2, pt2 = self._conv(a1, wp[p + ".conv2.weight"], 3, (1, 1), training, zpool)
-                sb = self._bn(sd, p + ".bn2", pt2, cnt, training)
+                if fold:        # conv1 with bn1 folded in: one kernel writes relu(bn1(conv1(x)))
+                    r1 = k1 = None
+                    sa = bnst[p + ".bn1"]
+                    a1 = ops.conv_fwd(x, wp[p + ".conv1.weight"], 3, s[0], s[1], relu=True, bias=sa[3])
+                    r2, pt2 = self._conv(a1, wp[p + ".conv2.weight"], 3, (1, 1), False, None)
+                    sb = bnst[p + ".bn2"]
+                else:
+                    r1, pt1 = self._conv(x, wp[p + ".conv1.weight"], 3, s, training, zpool)
+                    cnt = r1.numel() // r1.shape[-1]
+                    sa = self._bn(sd, p + ".bn1", pt1, cnt, training)
+                    a1, k1 = ops.bn_act_fwd(r1, sa, True, want_mask=save) if save else (ops.bn_act_fwd(r1, sa, True), None)
+                    r2, pt2 = self._conv(a1, wp[p + ".conv2.weight"], 3, (1, 1), training, zpool)
+                    sb = self._bn(sd, p + ".bn2", pt2, cnt, training)
                 rd = sdn = None
                 if (p + ".downsample.0.weight") in sd:
                     rd, ptd = self._conv(x, wp[p + ".downsample.0.weight"], 1, s, training, zpool)
-                    sdn = self._bn(sd, p + ".downsample.1", ptd, cnt, training)
+                    sdn = bnst[p + ".downsample.1"] if fold else self._bn(sd, p + ".downsample.1", ptd, cnt, training)
                     y = ops.bn_act_fwd(r2, sb, True, raw2=rd, st2=sdn, want_mask=save)
                 else:
                     y = ops.bn_act_fwd(r2, sb, True, res=x, want_mask=save)

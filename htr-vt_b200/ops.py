@@ -134,7 +134,7 @@ def conv_out_hw(H, W, ks, sh, sw):
     return (H + 2 * pad - ks) // sh + 1, (W + 2 * pad - ks) // sw + 1
 
 
-def conv_fwd(x, w, ks, sh, sw, y=None, stats=None, relu=False, nostore=False):
+def conv_fwd(x, w, ks, sh, sw, y=None, stats=None, relu=False, nostore=False, bias=None):
     """x [N,H,W,Cin] bf16 NHWC, w [Cout, ks*ks, Cin] bf16 -> y [N,Ho,Wo,Cout] bf16 (raw conv output).
     stats: optional fp32 [rows, 2, Cout] per-tile column sum / sum-of-squares partials."""
     _need_cuda(x, w)
@@ -144,7 +144,8 @@ def conv_fwd(x, w, ks, sh, sw, y=None, stats=None, relu=False, nostore=False):
     if y is None:
         y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
     check(lib().htrvt_conv_fwd(_p(x), N, H, W, Cin, _p(w), Cout, ks, sh, sw, _p(y), _p(stats),
-                               (EPI_RELU if relu else 0) | (256 if nostore else 0), _stream()), "htrvt_conv_fwd")
+                               (EPI_RELU if relu else 0) | (256 if nostore else 0), _p(bias), _stream()),
+          "htrvt_conv_fwd")
     return y
 
 
@@ -460,7 +461,8 @@ def pack_conv_weight(w, dst=None):
 
 
 def pack_weights(items, pad_rows=None, names=None):
-    """items: list of (src fp32 tensor, kind) with kind 'cast' ([out,in]) or 'conv' (OIHW -> [Cout, taps, Cin]).
+    """items: list of (src fp32 tensor, kind[, scale]) with kind 'cast' ([out,in]), 'conv' (OIHW -> [Cout, taps, Cin];
+    optional scale fp32 [Cout] folded in per output channel: eval-mode BatchNorm folding) or 'convT'.
     One launch for all of them.  pad_rows: {name: rows} allocates that 'cast' output with extra zero rows.
     Returns the list of bf16 tensors."""
     n = len(items)
@@ -470,7 +472,10 @@ def pack_weights(items, pad_rows=None, names=None):
     numel = (ctypes.c_longlong * n)()
     cin = (ctypes.c_int * n)()
     taps = (ctypes.c_int * n)()
-    for i, (t, kind) in enumerate(items):
+    scale = (ctypes.c_void_p * n)()
+    for i, item in enumerate(items):
+        t, kind = item[0], item[1]
+        scale[i] = item[2].data_ptr() if (len(item) > 2 and item[2] is not None) else None
         if kind == "conv":
             Cout, Ci, kh, kw = t.shape
             o = torch.empty((Cout, kh * kw, Ci), dtype=torch.bfloat16, device=t.device)
@@ -488,7 +493,7 @@ def pack_weights(items, pad_rows=None, names=None):
             cin[i], taps[i] = 1, 0
         outs.append(o)
         src[i], dst[i], numel[i] = t.data_ptr(), o.data_ptr(), t.numel()
-    check(lib().htrvt_pack_weights(n, src, dst, numel, cin, taps, _stream()), "htrvt_pack_weights")
+    check(lib().htrvt_pack_weights(n, src, dst, numel, cin, taps, scale, _stream()), "htrvt_pack_weights")
     return outs
 
 

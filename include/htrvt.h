@@ -73,7 +73,7 @@ int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X, long long 
  * stats_partial (optional): fp32 [htrvt_conv_fwd_stats_rows()][2][Cout] zero-initialised by the caller;
  * receives per-warp-quadrant column sum / sum of squares of the stored bf16 output (BatchNorm batch statistics). */
 int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks, int sh, int sw,
-                   void* y, float* stats_partial, int flags, void* stream);
+                   void* y, float* stats_partial, int flags, const float* bias, void* stream);
 int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw);
 int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* w, const void* w_t, int Cout, int ks,
                      int sh, int sw, void* dx, int accumulate, void* stream);
@@ -159,7 +159,7 @@ int htrvt_cast_bf16(const float* src, void* dst, long long n, void* stream);
 int htrvt_dropout_bf16(void* x, long long n, long long per_sample, float p, unsigned long long seed, unsigned site,
                        const float* dp, void* stream);
 int htrvt_pack_weights(int n, const void* const* src, void* const* dst, const long long* numel, const int* cin,
-                       const int* taps, void* stream);
+                       const int* taps, const void* const* scale, void* stream);
 int htrvt_pack_conv_weight(const float* w_oihw, void* dst, int Cout, int Cin, int taps, void* stream);
 
 /* ---- conv stem: first conv, BatchNorm, ReLU, max-pool ------------------------------------------------------
