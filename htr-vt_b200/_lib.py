@@ -51,7 +51,7 @@ SIGNATURES = {
     "htrvt_gemm_nn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _F, _P]),
     "htrvt_wgrad_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "htrvt_linear_wgrad": (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _Z, _P]),
-    "htrvt_conv_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
+    "htrvt_conv_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
     "htrvt_conv_fwd_stats_rows": (_I, [_I, _I, _I, _I, _I, _I]),
     "htrvt_conv_dgrad": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "htrvt_transpose_px": (_I, [_P, _P, _L, _I, _I, _P]),

@@ -404,10 +404,23 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
             }
           }
+          uint4 rq[4] = {};
+          if (KIND == 0 && (P.flags & EPI_RES)) {            // this thread's output pixel, 32 consecutive channels
+            const int w = tc.w0 + r;
+            if (w < P.Wo && col < P.N_valid) {
+              const uint4* rp = reinterpret_cast<const uint4*>(
+                  static_cast<const __nv_bfloat16*>(P.res) +
+                  ((static_cast<long long>(tc.n) * P.Ho + tc.h) * P.Wo + w) * P.N_valid + col);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) rq[i] = __ldg(rp + i);
+            }
+          }
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rq);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float a = __uint_as_float(raw[i]) * P.alpha, c = __uint_as_float(raw[i + 1]) * P.alpha;
             if (P.flags & EPI_BIAS) { a += bv[i]; c += bv[i + 1]; }
+            if (KIND == 0 && (P.flags & EPI_RES)) { const float2 rr = unpack_bf16(rw[i >> 1]); a += rr.x; c += rr.y; }
             if (P.flags & EPI_RELU) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
             packed[i >> 1] = pack_bf16(a, c);
           }
@@ -844,10 +857,11 @@ extern "C" int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, i
                             // per-CTA rows + a fixed-order finalise keep the train-mode FORWARD bit-reproducible
 }
 
-// bias (nullable, fp32 [Cout]): added in the epilogue before the optional ReLU (eval mode: the folded BatchNorm shift)
+// bias (nullable, fp32 [Cout]): added in the epilogue before the optional ReLU (eval mode: the folded BatchNorm shift);
+// res (nullable, bf16 [NB,Ho,Wo,Cout]): residual added there too (eval mode: the block's skip connection)
 extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks,
                               int sh, int sw, void* y, float* stats_partial, int flags, const float* bias,
-                              cudaStream_t stream) {
+                              const void* res, cudaStream_t stream) {
   const int pad = ks / 2;
   if ((Cin % 64) || (Cout & 7) || (W % sw) || (ks != 1 && ks != 3)) return HTRVT_ERR_SHAPE;
   const int Ho = (H + 2 * pad - ks) / sh + 1, Wo = (W + 2 * pad - ks) / sw + 1;
@@ -871,8 +885,10 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
   P.splits = 1; P.k_chunks = Cin / kBK; P.a_sh = sh; P.b_tap_stride = Cin;
   P.M_valid = 0; P.N_valid = Cout;
   if (bias && ((Cout & 3) || stats_partial)) return HTRVT_ERR_SHAPE;
-  P.flags = EPI_BF16 | (flags & (EPI_RELU | EPI_NOSTORE)) | (stats_partial ? EPI_STATS : 0) | (bias ? EPI_BIAS : 0);
-  P.stats = stats_partial; P.bias = bias; P.alpha = 1.f;
+  if (res && ((Cout & 31) || stats_partial || (reinterpret_cast<uintptr_t>(res) & 15))) return HTRVT_ERR_SHAPE;
+  P.flags = EPI_BF16 | (flags & (EPI_RELU | EPI_NOSTORE)) | (stats_partial ? EPI_STATS : 0) | (bias ? EPI_BIAS : 0) |
+            (res ? EPI_RES : 0);
+  P.stats = stats_partial; P.bias = bias; P.res = res; P.alpha = 1.f;
   if (reuse) return launch_reuse(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
   return launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }

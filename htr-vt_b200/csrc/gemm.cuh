@@ -18,6 +18,7 @@ enum : int {
   EPI_STATS = 1 << 5,      // column sum / sum of squares of the stored tile -> stats[cta*4+quadrant][2][N] (+=)
   EPI_RELU = 1 << 7,       // max(x, 0)
   EPI_NOSTORE = 1 << 8,    // measurement aid: skip the epilogue body (main-loop-only timing)
+  EPI_RES = 1 << 9,        // kind 0, bf16 out: + res[n,h,w,col] (same NHWC geometry as the output) before the ReLU
 };
 
 struct GemmP {
@@ -33,6 +34,7 @@ struct GemmP {
   int a_taps, a_atoms_per_tap;   // KIND 3: the M axis is (tap, 64-channel atom of x): real tap count, Cin / 64
   int flags;
   const float* bias;
+  const void* res;         // EPI_RES: bf16 residual, laid out like the output
   float* stats;
   float alpha;             // scale applied to the accumulator
 };

@@ -395,10 +395,11 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
     }
     return;
   }
-  if (taps <= 1) {                                      // plain cast ([out,in] linears, 1x1 convs)
+  if (taps <= 1) {                                      // plain cast ([out,in] linears, 1x1 convs [Cout][Cin])
+    const float* __restrict__ sc1 = T.scale[t];           // 1x1 conv with a folded per-output-channel factor
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
-      dst[i] = __float2bfloat16_rn(src[i]);
+      dst[i] = __float2bfloat16_rn(sc1 ? src[i] * sc1[i / Cin] : src[i]);
     return;
   }
   // OIHW -> [Cout][taps][Cin]: per output channel a [Cin][taps] -> [taps][Cin] transpose through smem, so both the
@@ -662,7 +663,7 @@ extern "C" int htrvt_pack_weights(int n, const void* const* src, void* const* ds
       T.cin[i] = cin[base + i] > 0 ? cin[base + i] : 1;
       T.taps[i] = taps[base + i];
       T.scale[i] = scale ? static_cast<const float*>(scale[base + i]) : nullptr;
-      if (T.scale[i] && T.taps[i] <= 1) return HTRVT_ERR_SHAPE;      // folding is wired for the k x k conv repack only
+      if (T.scale[i] && T.taps[i] < 1) return HTRVT_ERR_SHAPE;       // folding is wired for the conv repacks only
     }
     int smem = 0;
     for (int i = 0; i < cnt; ++i)

@@ -107,8 +107,11 @@ class Engine(object):
             if fold:
                 bnst = {k[:-len(".running_mean")]: self._bn(sd, k[:-len(".running_mean")], None, 1, False)
                         for k in sd if k.startswith("patch_embed.") and k.endswith(".running_mean")}
-                items = [(v, kind, bnst[n[:-len(".conv1.weight")] + ".bn1"][2])
-                         if (kind == "conv" and n.endswith(".conv1.weight") and n.count(".") == 4) else (v, kind)
+                def bn_of(n):                     # conv parameter name -> the BatchNorm that follows it
+                    if n.endswith(".downsample.0.weight"):
+                        return n[:-len("0.weight")] + "1"
+                    return n[:-len(".convX.weight")] + ".bn" + n[-len("X.weight")]
+                items = [(v, kind, bnst[bn_of(n)][2]) if kind == "conv" else (v, kind)
                          for n, (v, kind) in zip(names, items)]
             wp = dict(zip(names, ops.pack_weights(items, pad_rows={"head.weight": C8} if C8 != C else None,
                                                   names=names)))    # one launch for all 36 weight tensors
@@ -136,12 +139,17 @@ class Engine(object):
             for bi in range(2):
                 p = "patch_embed.%s.%d" % (lname, bi)
                 s = stride if bi == 0 else (1, 1)
-                if fold:        # conv1 with bn1 folded in: one kernel writes relu(bn1(conv1(x)))
-                    r1 = k1 = None
-                    sa = bnst[p + ".bn1"]
-                    a1 = ops.conv_fwd(x, wp[p + ".conv1.weight"], 3, s[0], s[1], relu=True, bias=sa[3])
-                    r2, pt2 = self._conv(a1, wp[p + ".conv2.weight"], 3, (1, 1), False, None)
-                    sb = bnst[p + ".bn2"]
+                if fold:
+                    # every BatchNorm of the block is folded (scale in the weights, shift as an epilogue bias): conv1
+                    # writes relu(bn1(conv1 x)), the 1x1 downsample writes bn_d(ds x), conv2's epilogue adds the skip
+                    # connection and applies the ReLU - three kernels per block, no BatchNorm pass
+                    a1 = ops.conv_fwd(x, wp[p + ".conv1.weight"], 3, s[0], s[1], relu=True, bias=bnst[p + ".bn1"][3])
+                    skip = x
+                    if (p + ".downsample.0.weight") in sd:
+                        skip = ops.conv_fwd(x, wp[p + ".downsample.0.weight"], 1, s[0], s[1],
+                                            bias=bnst[p + ".downsample.1"][3])
+                    x = ops.conv_fwd(a1, wp[p + ".conv2.weight"], 3, 1, 1, relu=True, bias=bnst[p + ".bn2"][3], res=skip)
+                    continue
                 else:
                     r1, pt1 = self._conv(x, wp[p + ".conv1.weight"], 3, s, training, zpool)
                     cnt = r1.numel() // r1.shape[-1]

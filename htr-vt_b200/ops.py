@@ -134,9 +134,10 @@ def conv_out_hw(H, W, ks, sh, sw):
     return (H + 2 * pad - ks) // sh + 1, (W + 2 * pad - ks) // sw + 1
 
 
-def conv_fwd(x, w, ks, sh, sw, y=None, stats=None, relu=False, nostore=False, bias=None):
+def conv_fwd(x, w, ks, sh, sw, y=None, stats=None, relu=False, nostore=False, bias=None, res=None):
     """x [N,H,W,Cin] bf16 NHWC, w [Cout, ks*ks, Cin] bf16 -> y [N,Ho,Wo,Cout] bf16 (raw conv output).
-    stats: optional fp32 [rows, 2, Cout] per-tile column sum / sum-of-squares partials."""
+    stats: optional fp32 [rows, 2, Cout] per-tile column sum / sum-of-squares partials.
+    bias fp32 [Cout] / res bf16 like y: y = [relu](conv + bias + res) in the epilogue (eval-mode BatchNorm folding)."""
     _need_cuda(x, w)
     N, H, W, Cin = x.shape
     Cout = w.shape[0]
@@ -144,7 +145,7 @@ def conv_fwd(x, w, ks, sh, sw, y=None, stats=None, relu=False, nostore=False, bi
     if y is None:
         y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
     check(lib().htrvt_conv_fwd(_p(x), N, H, W, Cin, _p(w), Cout, ks, sh, sw, _p(y), _p(stats),
-                               (EPI_RELU if relu else 0) | (256 if nostore else 0), _p(bias), _stream()),
+                               (EPI_RELU if relu else 0) | (256 if nostore else 0), _p(bias), _p(res), _stream()),
           "htrvt_conv_fwd")
     return y
 

@@ -73,7 +73,7 @@ int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X, long long 
  * stats_partial (optional): fp32 [htrvt_conv_fwd_stats_rows()][2][Cout] zero-initialised by the caller;
  * receives per-warp-quadrant column sum / sum of squares of the stored bf16 output (BatchNorm batch statistics). */
 int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks, int sh, int sw,
-                   void* y, float* stats_partial, int flags, const float* bias, void* stream);
+                   void* y, float* stats_partial, int flags, const float* bias, const void* res, void* stream);
 int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw);
 int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* w, const void* w_t, int Cout, int ks,
                      int sh, int sw, void* dx, int accumulate, void* stream);
