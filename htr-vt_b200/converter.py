@@ -26,6 +26,20 @@ class CTCLabelConverter(object):
         return (torch.IntTensor(flat).to(self.device), torch.IntTensor(length).to(self.device))
 
     def _to_strings(self, ids, lens):
+        """ids int32 [B, T] (kept class ids, compacted), lens [B] -> list of str (utils.py:80-84's join)."""
+        lut = getattr(self, "_lut", None)
+        if lut is None:
+            # single-code-point alphabets (all the reference's): id -> UTF-32 code unit, so a whole batch becomes ONE
+            # bytes -> str decode + B slices instead of B*T Python-level lookups
+            import numpy as np
+            ok = all(len(ch) == 1 for ch in self.character[1:])
+            self._lut = lut = (np.array([32] + [ord(ch) for ch in self.character[1:]], dtype=np.uint32) if ok else False)
+        if lut is not False:
+            a = ids.cpu().numpy()
+            n = lens.cpu().tolist()
+            T = a.shape[1]
+            flat = lut[a].astype("<u4", copy=False).tobytes().decode("utf-32-le")
+            return [flat[b * T:b * T + n[b]] for b in range(a.shape[0])]
         ids = ids.cpu().tolist()
         lens = lens.cpu().tolist()
         table = self.character
