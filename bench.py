@@ -335,7 +335,20 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner / debug lines to stdout while the communicator comes up; rank 0's stdout must
+        # carry ONE JSON line, so file descriptor 1 points at stderr until the first collective has completed
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from importlib import import_module
     import __graft_entry__ as ge
     ge.ensure_built()
