@@ -262,7 +262,17 @@ __device__ __forceinline__ void ctc_rec_fast(uint32_t pk_s, int ldp, int C, cons
       }
     }
   };
-  store_row(a);
+  // REV (beta) rows are stored WITHOUT the row's own emission probability: beta'_t(s) = beta_t(s) / p_t(l_s) is exactly
+  // the sum the recursion forms before its multiply, and alpha_t(s) * beta'_t(s) is the posterior numerator - the
+  // collect pass then needs no division (and no probability lookup) per state.  The boundary row's sums are 1.
+  if (REV) {
+    double one[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { const int r = lane * K + j; one[j] = (r == 0 || (r == 1 && S > 1)) ? 1.0 : 0.0; }
+    store_row(one);
+  } else {
+    store_row(a);
+  }
   int c = 0;
   if (lane == 0) sts32(off_s + t0 * 4, 0u);
   int sh = fast_row_shift<K>(a);
@@ -276,13 +286,14 @@ __device__ __forceinline__ void ctc_rec_fast(uint32_t pk_s, int ldp, int C, cons
     double pd[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) pd[j] = unpack_pd(q[j]);
+    const int c_prev = c;                            // scale of the incoming row = scale of this row's sums
     if (sh != 0) {                                   // warp-uniform; exact power of two, off the dependency chain
       const double sc = pow2_neg(sh);
 #pragma unroll
       for (int j = 0; j < K; ++j) pd[j] *= sc;
       c += sh;
     }
-    if (lane == 0) sts32(off_s + t * 4, static_cast<uint32_t>(c));
+    if (lane == 0) sts32(off_s + t * 4, static_cast<uint32_t>(REV ? c_prev : c));
     double up1 = shfl_up_d(a[K - 1], 1);             // previous lane's last state
     if (lane == 0) up1 = 0.0;
     prow += row_step;
@@ -290,19 +301,20 @@ __device__ __forceinline__ void ctc_rec_fast(uint32_t pk_s, int ldp, int C, cons
 #pragma unroll
       for (int j = 0; j < K; ++j) q[j] = lds32(prow + lo4[j]);
     }
-    double n[K];
+    double n[K], su[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
       const double p1 = (j >= 1) ? a[j >= 1 ? j - 1 : 0] : up1;
       if (j & 1) {
         const double p2 = (j >= 2) ? a[j >= 2 ? j - 2 : 0] : up1;    // j == 1: two behind = previous lane's last state
-        n[j] = fma(msk[j >> 1], p2, a[j] + p1) * pd[j];
+        su[j] = fma(msk[j >> 1], p2, a[j] + p1);
       } else {
-        n[j] = (a[j] + p1) * pd[j];
+        su[j] = a[j] + p1;
       }
+      n[j] = su[j] * pd[j];
     }
     st += st_row;
-    store_row(n);
+    if (REV) store_row(su); else store_row(n);
 #pragma unroll
     for (int j = 0; j < K; ++j) a[j] = n[j];
     sh = ((i & (kFastRenorm - 1)) == 0) ? fast_row_shift<K>(n) : 0;
@@ -503,7 +515,9 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
       __syncthreads();
       // ---- likelihood from both ends --------------------------------------------------------------
       const double za = unpack_pd(Au[(Tb - 1) * SP + S - 1]) + (S > 1 ? unpack_pd(Au[(Tb - 1) * SP + S - 2]) : 0.0);
-      const double zb = unpack_pd(Bu[0]) + (S > 1 ? unpack_pd(Bu[1]) : 0.0);
+      // beta rows hold beta' = beta / p: put row 0's emission probabilities back for the two start states
+      const double zb = unpack_pd(Bu[0]) * unpack_pd(lds32(pk_s)) +
+                        (S > 1 ? unpack_pd(Bu[1]) * unpack_pd(lds32(pk_s + ext[1] * 4)) : 0.0);
       const bool feasible = za > 0.0;
       bool bad = (za > 0.0) != (zb > 0.0);
       double ll2 = 0.0;
@@ -541,14 +555,15 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
           auto load_state = [&](int s, int c, uint32_t& wa, uint32_t& wb, uint32_t& wp) {
             wa = P.scratch_in_smem ? lds32(ab_s + (t * SP + s) * 4) : ar[s];
             wb = P.scratch_in_smem ? lds32(ab_s + ((T + t) * SP + s) * 4) : br[s];
-            wp = lds32(pr_s + c * 4);                          // != 0 wherever alpha is
+            wp = 0u; (void)c;                                  // beta rows are stored without p: no lookup
           };
           auto add_state = [&](int s, int c, bool ok, uint32_t wa, uint32_t wb, uint32_t wp) {
-            const int k = pk_exp(wa) + pk_exp(wb) - pk_exp(wp) + rowk;
+            (void)wp;
+            const int k = pk_exp(wa) + pk_exp(wb) + rowk;      // alpha_t(s) * beta'_t(s) / Z
             ok = ok && wa != 0u && wb != 0u && k >= -60;
             if (ok && k > 4) s_bad = 1;                        // cannot happen with consistent rows
             const int kc = min(max(k, -60), 4);
-            const float q = pk_mant(wa) * pk_mant(wb) * __fdividef(rz, pk_mant(wp));
+            const float q = pk_mant(wa) * pk_mant(wb) * rz;
             // gamma * 2^30, k <= ~1: the scale 2^(k+30) is an exact fp32 power of two
             const uint32_t u = ok ? __float2uint_rn(q * __uint_as_float(static_cast<uint32_t>(kc + 30 + 127) << 23)) : 0u;
             tot += u;
