@@ -168,7 +168,9 @@ __device__ __forceinline__ void ctc_beta(const float* __restrict__ l2p, int ldp,
 //            probabilities (off the chain); the integer shifts accumulate in off[t], so alpha_t = a * 2^off[t];
 //   probs  = softmax values as "packed doubles": bits 61..30 of the IEEE double (10 exponent bits + 22 mantissa
 //            bits), one 32-bit word per (t, c): unpack = two shifts; 0 = exact zero;
-//   stored = alpha / beta rows in the same packed format (22-bit mantissa, |rel err| < 2.4e-7).
+//   stored = alpha / beta' rows in the same packed format (22-bit mantissa, |rel err| < 2.4e-7); the posterior pass
+//            unpacks them back to doubles (two shifts each) and forms alpha * beta' * scale on the FP64 pipe, so the
+//            full exponent range survives without any per-state exponent arithmetic.
 // Linear fp64 can flush states that sit > ~2^-1000 below their row maximum; log space cannot.  Such a loss is
 // only relevant when the other recursion is correspondingly huge there, and then it shows: every row of
 // posteriors must sum to 1 (sum_s alpha_t(s) beta_t(s) / p_t(l_s) = Z for all t; flushing only ever removes mass)
@@ -326,8 +328,9 @@ __device__ __forceinline__ float pk_mant(uint32_t w) { return __uint_as_float(0x
 __device__ __forceinline__ int pk_exp(uint32_t w) { return static_cast<int>(w >> 22) - 1023; }
 // packed probability -> fp32 (flushes below 2^-126: only used for the softmax term of the gradient)
 __device__ __forceinline__ float pk_to_float(uint32_t w) {
-  const int e = static_cast<int>(w >> 22) - 896;          // fp32 biased exponent
-  return e > 0 ? __uint_as_float((static_cast<uint32_t>(e) << 23) | ((w & 0x3FFFFFu) << 1)) : 0.f;
+  // exponents 897..1023 all carry bit 9, so (w << 1) keeps them modulo 512 and re-biasing is one subtraction;
+  // anything at or below 2^-127 is clamped to the exponent field 0 (a denormal below 2^-126: nothing)
+  return __uint_as_float((max(w, 896u << 22) << 1) - (384u << 23));
 }
 
 struct CtcParams {
@@ -530,14 +533,18 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
       }
       if (!bad && gb) {
         // ---- phase 2: posterior collect (fixed point, integer smem atomics) + gradient rows -------
-        const uint32_t wz = feasible ? pack_pd(za) : 0u;
-        const float rz = feasible ? __fdividef(1.0f, pk_mant(wz)) : 0.f;
-        const int ez = feasible ? pk_exp(wz) + ioffA[Tb - 1] : 0;
+        // gamma_t(s) * 2^30 = (alpha_t(s) * c_t) * beta'_t(s) with ONE double constant per row,
+        // c_t = 2^(30 + offA[t] + offB[t] - offA[Tb-1]) / za: two DMULs per state on the FP64 pipe keep the whole
+        // exponent range of the packed rows (alpha * c_t overflows only where beta' sits at the flush boundary), and
+        // adding 2^52 leaves round(gamma * 2^30) in the low word - no conversion instruction, no exponent arithmetic.
+        // A lane takes (blank, label) state PAIRS: one 64-bit load per row, pair and direction.
+        const double rza = feasible ? 1.0 / za : 0.0;
         const uint32_t pw_s = smem_u32(post + warp * ldp);
-        constexpr int kSU = 5;                                // states per lane handled with labels in registers
-        int labr[kSU];
+        const int NP = L + 1;                                 // pairs (2i, 2i+1); the last one has no label state
+        constexpr int kPU = 3;                                // pairs per lane handled with labels in registers
+        uint32_t lab4[kPU];
 #pragma unroll
-        for (int i = 0; i < kSU; ++i) labr[i] = (lane + 32 * i < S) ? ext[lane + 32 * i] : 0;
+        for (int i = 0; i < kPU; ++i) lab4[i] = (lane + 32 * i < L) ? static_cast<uint32_t>(ext[2 * (lane + 32 * i) + 1]) * 4u : 0u;
         for (int c = lane; c < C; c += 32) sts32(pw_s + c * 4, 0u);
         __syncwarp();
         for (int t = warp; t < T; t += NW) {
@@ -548,43 +555,43 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
           }
           if (warp == 5 && t == 5) CTC_STAMP(7);
           const uint32_t pr_s = pk_s + t * ldp * 4;
-          const uint32_t* ar = Au + t * SP;
-          const uint32_t* br = Bu + t * SP;
-          const int rowk = ioffA[t] + ioffB[t] - ez;
+          const uint32_t ar_s = ab_s + t * SP * 4, br_s = ab_s + (T + t) * SP * 4;
+          const uint2* ar = reinterpret_cast<const uint2*>(Au + t * SP);
+          const uint2* br = reinterpret_cast<const uint2*>(Bu + t * SP);
+          int kk = ioffA[t] + ioffB[t] - ioffA[Tb - 1] + 30;
+          if (kk > 1000 || kk < -1000) { s_bad = 1; kk = 0; }  // cannot happen with consistent rows
+          const double crow = rza * __hiloint2double((1023 + kk) << 20, 0);
           uint32_t blank = 0u, tot = 0u;
-          auto load_state = [&](int s, int c, uint32_t& wa, uint32_t& wb, uint32_t& wp) {
-            wa = P.scratch_in_smem ? lds32(ab_s + (t * SP + s) * 4) : ar[s];
-            wb = P.scratch_in_smem ? lds32(ab_s + ((T + t) * SP + s) * 4) : br[s];
-            wp = 0u; (void)c;                                  // beta rows are stored without p: no lookup
+          auto load_pair = [&](int pi, uint2& wa, uint2& wb) {
+            if (P.scratch_in_smem) {
+              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wa.x), "=r"(wa.y) : "r"(ar_s + pi * 8));
+              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wb.x), "=r"(wb.y) : "r"(br_s + pi * 8));
+            } else {
+              wa = ar[pi]; wb = br[pi];
+            }
           };
-          auto add_state = [&](int s, int c, bool ok, uint32_t wa, uint32_t wb, uint32_t wp) {
-            (void)wp;
-            const int k = pk_exp(wa) + pk_exp(wb) + rowk;      // alpha_t(s) * beta'_t(s) / Z
-            ok = ok && wa != 0u && wb != 0u && k >= -60;
-            if (ok && k > 4) s_bad = 1;                        // cannot happen with consistent rows
-            const int kc = min(max(k, -60), 4);
-            const float q = pk_mant(wa) * pk_mant(wb) * rz;
-            // gamma * 2^30, k <= ~1: the scale 2^(k+30) is an exact fp32 power of two
-            const uint32_t u = ok ? __float2uint_rn(q * __uint_as_float(static_cast<uint32_t>(kc + 30 + 127) << 23)) : 0u;
-            tot += u;
-            if (s & 1) { if (u) reds_add_u32(pw_s + c * 4, u); }
-            else blank += u;
+          auto fix30 = [&](uint32_t wa, uint32_t wb) -> uint32_t {
+            const double q = (unpack_pd(wa) * crow) * unpack_pd(wb) + 4503599627370496.0;   // + 2^52
+            return static_cast<uint32_t>(__double2loint(q));
+          };
+          auto add_pair = [&](bool okb, bool okl, uint32_t c4, uint2 wa, uint2 wb) {
+            const uint32_t u0 = okb ? fix30(wa.x, wb.x) : 0u;
+            const uint32_t u1 = okl ? fix30(wa.y, wb.y) : 0u;
+            blank += u0;
+            tot += u0 + u1;
+            if (u1) reds_add_u32(pw_s + c4, u1);
           };
           {
-            uint32_t wa[kSU], wb[kSU], wp[kSU];
+            uint2 wa[kPU], wb[kPU];
 #pragma unroll
-            for (int i = 0; i < kSU; ++i) {                    // all loads first: the states are independent
-              const int s = min(lane + 32 * i, S - 1);
-              load_state(s, labr[i], wa[i], wb[i], wp[i]);
-            }
+            for (int i = 0; i < kPU; ++i) load_pair(min(lane + 32 * i, NP - 1), wa[i], wb[i]);   // all loads first
 #pragma unroll
-            for (int i = 0; i < kSU; ++i) add_state(lane + 32 * i, labr[i], lane + 32 * i < S, wa[i], wb[i], wp[i]);
+            for (int i = 0; i < kPU; ++i) add_pair(lane + 32 * i < NP, lane + 32 * i < L, lab4[i], wa[i], wb[i]);
           }
-          for (int s = lane + 32 * kSU; s < S; s += 32) {
-            uint32_t wa, wb, wp;
-            const int c = ext[s];
-            load_state(s, c, wa, wb, wp);
-            add_state(s, c, true, wa, wb, wp);
+          for (int pi = lane + 32 * kPU; pi < NP; pi += 32) {
+            uint2 wa, wb;
+            load_pair(pi, wa, wb);
+            add_pair(true, pi < L, pi < L ? static_cast<uint32_t>(ext[2 * pi + 1]) * 4u : 0u, wa, wb);
           }
           if (warp == 5 && t == 5) CTC_STAMP(8);
           blank = __reduce_add_sync(0xffffffffu, blank);
