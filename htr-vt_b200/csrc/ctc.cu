@@ -227,7 +227,7 @@ __device__ __forceinline__ void reds_add_u32(uint32_t a, uint32_t v) {
 // AB: row storage [T][SP] (shared address when SM, else a global pointer).
 template <int K, bool REV, bool SM>
 __device__ __forceinline__ void ctc_rec_fast(uint32_t pk_s, int ldp, int C, const int* __restrict__ ext, int S, int Tb,
-                                             uint32_t ab_s, uint32_t* ab_g, int SP, uint32_t off_s) {
+                                             uint32_t ab_s, uint32_t* ab_g, int SP, uint32_t off_s, uint32_t prog_s) {
   static_assert((K & 1) == 0, "even K");
   const int lane = threadIdx.x & 31;
   double a[K], msk[K / 2];
@@ -275,8 +275,26 @@ __device__ __forceinline__ void ctc_rec_fast(uint32_t pk_s, int ldp, int C, cons
   } else {
     store_row(a);
   }
+  // progress: one single-use mbarrier per 4 recursion steps (prog_s = shared address of this direction's array; the
+  // two words in front of it hold the named-barrier thread counts).  Called after the rows of step i are stored, for
+  // i % 4 == 0 (the renormalisation steps) and for the last step: the row of step t is covered by barrier (t+3)/4.
+  // The arrive (release.cta) after a __syncwarp makes the rows and offsets visible to the collecting warps, which
+  // sleep on named barriers until then (no polling while the recursions run alone): barrier 1 opens when both
+  // directions have passed the middle row, barrier 2 when both are done.
+  auto publish = [&](int i) {
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(prog_s + ((i + 3) >> 2) * 8) : "memory");
+    const int lo = (Tb - 1) >> 1;
+    const int mid = min(((REV ? Tb - 1 - lo : lo) + 3) & ~3, Tb - 1);
+    if (i == mid) asm volatile("barrier.arrive 1, %0;" ::"r"(lds32(prog_s - 8)) : "memory");
+    if (i == Tb - 1) {
+      const uint32_t n_end = lds32(prog_s - 4);
+      if (n_end > 64u) asm volatile("barrier.arrive 2, %0;" ::"r"(n_end) : "memory");
+    }
+  };
   int c = 0;
   if (lane == 0) sts32(off_s + t0 * 4, 0u);
+  publish(0);
   int sh = fast_row_shift<K>(a);
   prow += row_step;
   if (Tb > 1) {
@@ -319,8 +337,13 @@ __device__ __forceinline__ void ctc_rec_fast(uint32_t pk_s, int ldp, int C, cons
     if (REV) store_row(su); else store_row(n);
 #pragma unroll
     for (int j = 0; j < K; ++j) a[j] = n[j];
-    sh = ((i & (kFastRenorm - 1)) == 0) ? fast_row_shift<K>(n) : 0;
+    sh = 0;
+    if ((i & (kFastRenorm - 1)) == 0) {
+      sh = fast_row_shift<K>(n);
+      publish(i);
+    }
   }
+  if (Tb > 1 && ((Tb - 1) & 3) != 0) publish(Tb - 1);
 }
 
 // packed word -> (mantissa float in [1, 2), exponent relative to 2^0); w != 0
@@ -346,7 +369,7 @@ struct CtcParams {
   const float* grad_scale;   // [B] per-sample upstream gradient, or null
   float grad_scale_const;    // used when grad_scale == null
   float* scratch;            // global alpha/beta scratch when they do not fit in shared memory
-  int B, T, C, kmax, is_logprob, scratch_in_smem, force_slow, dbg;
+  int B, T, C, kmax, is_logprob, scratch_in_smem, force_slow, dbg, ovl;
 };
 
 #define CTC_DISPATCH(FN, ...)                 \
@@ -395,7 +418,9 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
   float* red = reinterpret_cast<float*>(ext + 32 * P.kmax);   // [40] reductions / broadcast
   double* offA = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(red + 40) + 7) & ~uintptr_t(7));         // [T] renormalisation offsets of alpha rows
   double* offB = offA + T;                                    // [T] ... of beta rows
-  float* AB = reinterpret_cast<float*>(offB + T);  // alpha | beta when they fit in shared memory
+  const int NB = ((T + 2) >> 2) + 2;                          // per direction: 1 count slot + progress barriers (4 steps each)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(offB + T);     // [2][NB]: {n_mid, n_end} | barriers
+  float* AB = reinterpret_cast<float*>(bars + 2 * NB);        // alpha | beta when they fit in shared memory
   volatile int& s_bad = *reinterpret_cast<volatile int*>(red + 36);   // fast path: "recompute in log space" flag
 
   // ---- per-sequence metadata -------------------------------------------------------------------
@@ -421,7 +446,19 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
   float* gb = P.grad ? P.grad + static_cast<long long>(b) * P.g_sb : nullptr;
   const float gs = P.grad_scale ? P.grad_scale[b] : P.grad_scale_const;
 
-  if (tid == 0) s_bad = 0;
+  if (tid == 0) {
+    s_bad = 0;
+    red[35] = __int_as_float(0);                                // row ticket of the collecting warps
+  }
+  for (int i = tid; i < 2 * NB; i += kCtcThreads) {
+    if (i == 0 || i == NB) {
+      // P.ovl: bit w set = warp w starts collecting at the middle row, clear = after the recursions (developer knob)
+      const int n_early = P.grad ? __popc(static_cast<uint32_t>(P.ovl) & 0xFFFCu) : 0;
+      reinterpret_cast<int2*>(bars)[i] = make_int2(32 * (2 + n_early), 32 * (2 + (P.grad ? 14 - n_early : 0)));
+    } else {
+      mbar_init(bars + i, 1);
+    }
+  }
   if (tid == 0) CTC_STAMP(0);
   if (fits) {
     for (int s = tid; s < SP; s += kCtcThreads) ext[s] = (s < S && (s & 1)) ? P.targets[toff + (s >> 1)] : 0;
@@ -504,41 +541,34 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
     __syncthreads();
     if (tid == 0) CTC_STAMP(2);
     if (!s_bad) {
-      // ---- phase 1: alpha on warp 0, beta on warp 1, concurrently --------------------------------
+      // ---- phase 1: alpha on warp 0, beta on warp 1, concurrently; every 4 steps they publish their progress ----
+      // ---- phase 2 (overlapped): the other warps collect posterior rows as soon as BOTH directions have produced
+      // them - from the middle of the sequence outwards while the recursions run their second half.  Rows are handed
+      // out in completion order by an smem ticket; the likelihood the posteriors are normalised with comes from the
+      // middle row (Z = sum_s alpha_m(s) beta'_m(s)), every warp computing the same sum for itself.
+      const uint32_t progA_s = smem_u32(bars + 1), progB_s = smem_u32(bars + NB + 1);
       if (warp == 0) {
-        if (P.scratch_in_smem) { CTC_DISPATCH_FAST(false, true, pk_s, ldp, C, ext, S, Tb, ab_s, Au, SP, smem_u32(ioffA)) }
-        else { CTC_DISPATCH_FAST(false, false, pk_s, ldp, C, ext, S, Tb, 0u, Au, SP, smem_u32(ioffA)) }
+        if (P.scratch_in_smem) { CTC_DISPATCH_FAST(false, true, pk_s, ldp, C, ext, S, Tb, ab_s, Au, SP, smem_u32(ioffA), progA_s) }
+        else { CTC_DISPATCH_FAST(false, false, pk_s, ldp, C, ext, S, Tb, 0u, Au, SP, smem_u32(ioffA), progA_s) }
         CTC_STAMP(3);
       } else if (warp == 1) {
-        if (P.scratch_in_smem) { CTC_DISPATCH_FAST(true, true, pk_s, ldp, C, ext, S, Tb, ab_s + T * SP * 4, Bu, SP, smem_u32(ioffB)) }
-        else { CTC_DISPATCH_FAST(true, false, pk_s, ldp, C, ext, S, Tb, 0u, Bu, SP, smem_u32(ioffB)) }
+        if (P.scratch_in_smem) { CTC_DISPATCH_FAST(true, true, pk_s, ldp, C, ext, S, Tb, ab_s + T * SP * 4, Bu, SP, smem_u32(ioffB), progB_s) }
+        else { CTC_DISPATCH_FAST(true, false, pk_s, ldp, C, ext, S, Tb, 0u, Bu, SP, smem_u32(ioffB), progB_s) }
         CTC_STAMP(4);
       }
-      if (!P.scratch_in_smem) __threadfence_block();
-      __syncthreads();
-      // ---- likelihood from both ends --------------------------------------------------------------
-      const double za = unpack_pd(Au[(Tb - 1) * SP + S - 1]) + (S > 1 ? unpack_pd(Au[(Tb - 1) * SP + S - 2]) : 0.0);
-      // beta rows hold beta' = beta / p: put row 0's emission probabilities back for the two start states
-      const double zb = unpack_pd(Bu[0]) * unpack_pd(lds32(pk_s)) +
-                        (S > 1 ? unpack_pd(Bu[1]) * unpack_pd(lds32(pk_s + ext[1] * 4)) : 0.0);
-      const bool feasible = za > 0.0;
-      bool bad = (za > 0.0) != (zb > 0.0);
-      double ll2 = 0.0;
-      if (feasible && !bad) {
-        // log2 of a packed value: exponent + lg2 of the 22-bit mantissa (abs err ~2e-7 of a bit)
-        const uint32_t wa2 = pack_pd(za), wb2 = pack_pd(zb);
-        ll2 = static_cast<double>(pk_exp(wa2) + ioffA[Tb - 1]) + static_cast<double>(lg2f(pk_mant(wa2)));
-        const double ll2b = static_cast<double>(pk_exp(wb2) + ioffB[0]) + static_cast<double>(lg2f(pk_mant(wb2)));
-        bad = fabs(ll2 - ll2b) > 3.0e-5;
-      }
-      if (!bad && gb) {
-        // ---- phase 2: posterior collect (fixed point, integer smem atomics) + gradient rows -------
-        // gamma_t(s) * 2^30 = (alpha_t(s) * c_t) * beta'_t(s) with ONE double constant per row,
-        // c_t = 2^(30 + offA[t] + offB[t] - offA[Tb-1]) / za: two DMULs per state on the FP64 pipe keep the whole
-        // exponent range of the packed rows (alpha * c_t overflows only where beta' sits at the flush boundary), and
-        // adding 2^52 leaves round(gamma * 2^30) in the low word - no conversion instruction, no exponent arithmetic.
-        // A lane takes (blank, label) state PAIRS: one 64-bit load per row, pair and direction.
-        const double rza = feasible ? 1.0 / za : 0.0;
+      if (gb) {
+        auto wait_row = [&](int t) {             // alpha stores row t at step t, beta' at step Tb-1-t
+          uint64_t* ba = bars + 1 + ((t + 3) >> 2);
+          uint64_t* bb = bars + NB + 1 + ((Tb - 1 - t + 3) >> 2);
+          while (!mbar_try_wait(ba, 0)) __nanosleep(100);
+          while (!mbar_try_wait(bb, 0)) __nanosleep(100);
+        };
+        const int lo = (Tb - 1) >> 1, hi = Tb >> 1;           // first row(s) both directions reach
+        if (warp >= 2) {
+          const int2 cnt = reinterpret_cast<const int2*>(bars)[0];
+          if ((static_cast<uint32_t>(P.ovl) >> warp) & 1u) asm volatile("barrier.sync 1, %0;" ::"r"(cnt.x) : "memory");
+          else asm volatile("barrier.sync 2, %0;" ::"r"(cnt.y) : "memory");
+        }
         const uint32_t pw_s = smem_u32(post + warp * ldp);
         const int NP = L + 1;                                 // pairs (2i, 2i+1); the last one has no label state
         constexpr int kPU = 3;                                // pairs per lane handled with labels in registers
@@ -547,29 +577,63 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
         for (int i = 0; i < kPU; ++i) lab4[i] = (lane + 32 * i < L) ? static_cast<uint32_t>(ext[2 * (lane + 32 * i) + 1]) * 4u : 0u;
         for (int c = lane; c < C; c += 32) sts32(pw_s + c * 4, 0u);
         __syncwarp();
-        for (int t = warp; t < T; t += NW) {
+        auto load_pair = [&](int t, int pi, uint2& wa, uint2& wb) {
+          if (P.scratch_in_smem) {
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wa.x), "=r"(wa.y) : "r"(ab_s + (t * SP) * 4 + pi * 8));
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wb.x), "=r"(wb.y) : "r"(ab_s + ((T + t) * SP) * 4 + pi * 8));
+          } else {
+            wa = reinterpret_cast<const uint2*>(Au + t * SP)[pi];
+            wb = reinterpret_cast<const uint2*>(Bu + t * SP)[pi];
+          }
+        };
+        // ---- likelihood from the middle row ------------------------------------------------------
+        wait_row(lo);
+        double zsum = 0.0;
+        for (int pi = lane; pi < NP; pi += 32) {
+          uint2 wa, wb;
+          load_pair(lo, pi, wa, wb);
+          zsum += unpack_pd(wa.x) * unpack_pd(wb.x);
+          if (pi < L) zsum += unpack_pd(wa.y) * unpack_pd(wb.y);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1)
+          zsum += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(zsum), d),
+                                   __shfl_xor_sync(0xffffffffu, __double2loint(zsum), d));
+        const bool feas_m = zsum > 0.0;
+        const int offm = ioffA[lo] + ioffB[lo];
+        if (warp == 2 && lane == 0) {
+          red[37] = __int_as_float(__double2hiint(zsum));
+          red[38] = __int_as_float(__double2loint(zsum));
+          red[39] = __int_as_float(offm);
+        }
+        // gamma_t(s) * 2^30 = (alpha_t(s) * c_t) * beta'_t(s) with ONE double constant per row,
+        // c_t = 2^(30 + offA[t] + offB[t] - offA[m] - offB[m]) / Z_m: two DMULs per state on the FP64 pipe keep the
+        // whole exponent range of the packed rows (alpha * c_t overflows only where beta' sits at the flush boundary),
+        // and adding 2^52 leaves round(gamma * 2^30) in the low word - no conversion, no exponent arithmetic.
+        // A lane takes (blank, label) state PAIRS: one 64-bit load per row, pair and direction.
+        const double rza = feas_m ? 1.0 / zsum : 0.0;
+        int* ticket = reinterpret_cast<int*>(red + 35);
+        for (;;) {
+          int k = 0;
+          if (lane == 0) k = atomicAdd(ticket, 1);
+          k = __shfl_sync(0xffffffffu, k, 0);
+          if (k >= T) break;
+          int t = k;
+          if (k < Tb) {                                       // completion order: middle row(s) first, then outwards
+            const int kq = k + (Tb & 1), j = kq >> 1;
+            t = (kq & 1) ? hi + j : lo - j;
+          }
           float* gr = gb + static_cast<long long>(t) * P.g_st;
-          if (t >= Tb || !feasible) {
+          if (t >= Tb || !feas_m) {
             for (int c = lane; c < C; c += 32) gr[c] = 0.f;
             continue;
           }
-          if (warp == 5 && t == 5) CTC_STAMP(7);
+          wait_row(t);
           const uint32_t pr_s = pk_s + t * ldp * 4;
-          const uint32_t ar_s = ab_s + t * SP * 4, br_s = ab_s + (T + t) * SP * 4;
-          const uint2* ar = reinterpret_cast<const uint2*>(Au + t * SP);
-          const uint2* br = reinterpret_cast<const uint2*>(Bu + t * SP);
-          int kk = ioffA[t] + ioffB[t] - ioffA[Tb - 1] + 30;
+          int kk = ioffA[t] + ioffB[t] - offm + 30;
           if (kk > 1000 || kk < -1000) { s_bad = 1; kk = 0; }  // cannot happen with consistent rows
           const double crow = rza * __hiloint2double((1023 + kk) << 20, 0);
           uint32_t blank = 0u, tot = 0u;
-          auto load_pair = [&](int pi, uint2& wa, uint2& wb) {
-            if (P.scratch_in_smem) {
-              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wa.x), "=r"(wa.y) : "r"(ar_s + pi * 8));
-              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wb.x), "=r"(wb.y) : "r"(br_s + pi * 8));
-            } else {
-              wa = ar[pi]; wb = br[pi];
-            }
-          };
           auto fix30 = [&](uint32_t wa, uint32_t wb) -> uint32_t {
             const double q = (unpack_pd(wa) * crow) * unpack_pd(wb) + 4503599627370496.0;   // + 2^52
             return static_cast<uint32_t>(__double2loint(q));
@@ -584,19 +648,17 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
           {
             uint2 wa[kPU], wb[kPU];
 #pragma unroll
-            for (int i = 0; i < kPU; ++i) load_pair(min(lane + 32 * i, NP - 1), wa[i], wb[i]);   // all loads first
+            for (int i = 0; i < kPU; ++i) load_pair(t, min(lane + 32 * i, NP - 1), wa[i], wb[i]);   // all loads first
 #pragma unroll
             for (int i = 0; i < kPU; ++i) add_pair(lane + 32 * i < NP, lane + 32 * i < L, lab4[i], wa[i], wb[i]);
           }
           for (int pi = lane + 32 * kPU; pi < NP; pi += 32) {
             uint2 wa, wb;
-            load_pair(pi, wa, wb);
+            load_pair(t, pi, wa, wb);
             add_pair(true, pi < L, pi < L ? static_cast<uint32_t>(ext[2 * pi + 1]) * 4u : 0u, wa, wb);
           }
-          if (warp == 5 && t == 5) CTC_STAMP(8);
           blank = __reduce_add_sync(0xffffffffu, blank);
           tot = __reduce_add_sync(0xffffffffu, tot);
-          if (warp == 5 && t == 5) CTC_STAMP(9);
           const int dev1 = static_cast<int>(tot) - (1 << 30);
           if (dev1 > 21475 || dev1 < -21475) s_bad = 1;    // the row's posteriors do not sum to 1 (2e-5): mass was flushed
           __syncwarp();
@@ -606,11 +668,32 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
             gr[c] = (pk_to_float(lds32(pr_s + c * 4)) - static_cast<float>(pc) * 9.313225746154785e-10f) * gs;
           }
           __syncwarp();
-          if (warp == 5 && t == 5) CTC_STAMP(10);
-          if (warp == 5 && t == 21) CTC_STAMP(11);
         }
       }
       if (warp == 5) CTC_STAMP(5);
+      if (!P.scratch_in_smem) __threadfence_block();
+      __syncthreads();
+      // ---- likelihood from both ends; all three (alpha end, beta start, middle row) must agree -------------
+      const double za = unpack_pd(Au[(Tb - 1) * SP + S - 1]) + (S > 1 ? unpack_pd(Au[(Tb - 1) * SP + S - 2]) : 0.0);
+      // beta rows hold beta' = beta / p: put row 0's emission probabilities back for the two start states
+      const double zb = unpack_pd(Bu[0]) * unpack_pd(lds32(pk_s)) +
+                        (S > 1 ? unpack_pd(Bu[1]) * unpack_pd(lds32(pk_s + ext[1] * 4)) : 0.0);
+      const double zm = gb ? __hiloint2double(__float_as_int(red[37]), __float_as_int(red[38])) : za;
+      const bool feasible = za > 0.0;
+      bool bad = (za > 0.0) != (zb > 0.0) || (za > 0.0) != (zm > 0.0);
+      double ll2 = 0.0;
+      if (feasible && !bad) {
+        // log2 of a packed value: exponent + lg2 of the 22-bit mantissa (abs err ~2e-7 of a bit)
+        const uint32_t wa2 = pack_pd(za), wb2 = pack_pd(zb);
+        ll2 = static_cast<double>(pk_exp(wa2) + ioffA[Tb - 1]) + static_cast<double>(lg2f(pk_mant(wa2)));
+        const double ll2b = static_cast<double>(pk_exp(wb2) + ioffB[0]) + static_cast<double>(lg2f(pk_mant(wb2)));
+        bad = fabs(ll2 - ll2b) > 3.0e-5;
+        if (gb) {
+          const uint32_t wm2 = pack_pd(zm);
+          const double ll2m = static_cast<double>(pk_exp(wm2) + __float_as_int(red[39])) + static_cast<double>(lg2f(pk_mant(wm2)));
+          bad = bad || fabs(ll2 - ll2m) > 3.0e-5;
+        }
+      }
       if (bad) s_bad = 1;
       __syncthreads();
       if (tid == 0) CTC_STAMP(6);
@@ -721,7 +804,8 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
 
 size_t ctc_smem_bytes(int T, int C, int kmax, bool scratch_in_smem) {
   const int ldp = (C + 1) | 1;
-  size_t words = static_cast<size_t>(T) * ldp + (kCtcThreads / 32) * ldp + 32 * kmax + 40 + 4 * T + 2;
+  size_t words = static_cast<size_t>(T) * ldp + (kCtcThreads / 32) * ldp + 32 * kmax + 40 + 4 * T + 2 +
+                 4 * (((T + 2) >> 2) + 2);                  // + the progress barriers of the fast path
   if (scratch_in_smem) words += static_cast<size_t>(2) * T * 32 * kmax;
   return words * 4;
 }
@@ -766,7 +850,9 @@ extern "C" int htrvt_ctc_loss_grad(const float* x, long long x_stride_b, long lo
   static const int force_slow = (getenv("HTRVT_CTC_SLOW") && atoi(getenv("HTRVT_CTC_SLOW")) != 0) ? 1 : 0;
   P.force_slow = force_slow;
   static const int dbg = getenv("HTRVT_CTC_DEBUG") ? 1 : 0;
-  P.dbg = dbg;   // developer knob: run the log-space path only
+  P.dbg = dbg;
+  static const int ovl = getenv("HTRVT_CTC_OVL") ? static_cast<int>(strtol(getenv("HTRVT_CTC_OVL"), nullptr, 0)) : 0xFFFC;
+  P.ovl = ovl;   // developer knob: run the log-space path only
   P.scratch_in_smem = ctc_smem_bytes(T, C, P.kmax, true) <= 227 * 1024 ? 1 : 0;
   P.scratch = static_cast<float*>(workspace);
   const size_t smem = ctc_smem_bytes(T, C, P.kmax, P.scratch_in_smem);

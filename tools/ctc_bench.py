@@ -40,8 +40,6 @@ for (B, T, C, lo, hi) in [(128, 128, 80, 16, 64), (1024, 128, 80, 16, 64), (4096
         st = list(buf)
         print("  clocks from CTA0 start: sync0a %d, phase0 %d, alpha %d, beta %d, phase2(w5) %d, end %d  (L0=%d)" %
               (st[1] - st[0], st[2] - st[0], st[3] - st[0], st[4] - st[0], st[5] - st[0], st[6] - st[0], int(tl[0])))
-        print("  phase2 warp5: row5 start %d, states done +%d, redux +%d, classes +%d ; row21 end +%d" %
-              (st[7] - st[0], st[8] - st[7], st[9] - st[8], st[10] - st[9], st[11] - st[10]))
         torch.cuda.synchronize()
     print("B=%d T=%d C=%d L<=%d: %.1f us/batch  %.0f GB/s algorithmic  fallbacks %d" %
           (B, T, C, hi, us, byts / us / 1e3, lib.htrvt_ctc_fallback_count() - n0))
