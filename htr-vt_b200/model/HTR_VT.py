@@ -155,10 +155,26 @@ class MaskedAutoencoderViT(nn.Module):
         """Stochastic-regularisation state of one train-mode forward (None: model_v1 has no dropout / DropPath)."""
         return None
 
+    def _slots(self):
+        """(full name, owning module, key, is_parameter) of every parameter and buffer, in named_parameters() /
+        named_buffers() order.  The module tree is fixed after construction, so the walk is done once; the tensors are
+        looked up in their owners' dicts every forward (`.to()` / `load_state_dict(assign=True)` may replace them)."""
+        slots = self.__dict__.get("_slot_cache")
+        if slots is None:
+            slots = []
+            for prefix, mod in self.named_modules():
+                for key in mod._parameters:
+                    if mod._parameters[key] is not None:
+                        slots.append((prefix + "." + key if prefix else key, mod, key, True))
+            for prefix, mod in self.named_modules():
+                for key in mod._buffers:
+                    if mod._buffers[key] is not None:
+                        slots.append((prefix + "." + key if prefix else key, mod, key, False))
+            self.__dict__["_slot_cache"] = slots
+        return slots
+
     def _tensor_table(self):
-        table = {k: v for k, v in self.named_parameters()}
-        table.update({k: v for k, v in self.named_buffers()})
-        return table
+        return {name: (mod._parameters[key] if is_p else mod._buffers[key]) for name, mod, key, is_p in self._slots()}
 
     def enable_data_parallel(self, group=None):
         """Average gradients over the ranks of `group` inside backward (batch sharding, one process per GPU)."""
@@ -171,6 +187,8 @@ class MaskedAutoencoderViT(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
+            if k == "_slot_cache":
+                continue                    # holds references to THIS tree's modules
             new.__dict__[k] = v if k == "grad_sync" else copy.deepcopy(v, memo)
         return new
 
@@ -194,7 +212,7 @@ class MaskedAutoencoderViT(nn.Module):
         if use_masking:
             L = x.shape[-1] // 4
             mask = self.span_mask(L, mask_ratio, max_span_length).to(x.device, non_blocking=True)
-        names, params = zip(*[(k, v) for k, v in self.named_parameters()])
+        names, params = zip(*[(name, mod._parameters[key]) for name, mod, key, is_p in self._slots() if is_p])
         save = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         return _EncoderFn.apply(self, x, mask, names, save, widths, *params)
 
