@@ -265,42 +265,79 @@ __global__ void __launch_bounds__(256) tokens_bwd_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------------
 // GELU backward: du = da * (Phi(u) + u phi(u)), erf form (nn.GELU default)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_grad(float u) {
-  const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
-  return cdf + u * pdf;
+// Phi(u) (standard normal CDF, i.e. the erf form of nn.GELU) and e = exp(-u^2/2) with two MUFU ops and six FMAs:
+// erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z)  (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7 - far
+// below the bf16 output resolution).  libm's erff costs ~2x the instructions, which made these two streaming kernels
+// instruction bound (~3.3 TB/s); the exponential is shared with the density term of the backward.
+__device__ __forceinline__ void gelu_parts(float u, float& cdf, float& e) {
+  const float z = fabsf(u) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  e = ex2f(u * u * -0.72134752044448170f);          // exp(-u^2 / 2)
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float h = 0.5f * p * t * e;                 // 1 - Phi(|u|)
+  cdf = u >= 0.f ? 1.0f - h : h;
 }
-// a = gelu(u), exact erf form (nn.GELU default used by timm Mlp); separate full-occupancy kernel because the
-// GEMM epilogue is run by 8 warps only
-__global__ void gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ a, long long n8) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const uint4 b = *reinterpret_cast<const uint4*>(u + i * 8);
+__device__ __forceinline__ float gelu_val(float u) {
+  float c, e;
+  gelu_parts(u, c, e);
+  return u * c;
+}
+__device__ __forceinline__ float gelu_grad(float u) {
+  float c, e;
+  gelu_parts(u, c, e);
+  return fmaf(u * 0.3989422804014327f, e, c);
+}
+__device__ __forceinline__ uint32_t gelu2(uint32_t w) {
+  const float2 y = unpack_bf16(w);
+  return pack_bf16(gelu_val(y.x), gelu_val(y.y));
+}
+__device__ __forceinline__ uint32_t gelu_grad2(uint32_t g, uint32_t w) {
+  const float2 x = unpack_bf16(g), y = unpack_bf16(w);
+  return pack_bf16(x.x * gelu_grad(y.x), x.y * gelu_grad(y.y));
+}
+// a = gelu(u), erf form (nn.GELU default used by timm Mlp); separate full-occupancy kernel because the GEMM epilogue
+// is run by 8 warps only.  Two 16-byte loads in flight per thread.
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ a,
+                                                        long long n8) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8; i += 2 * stride) {
+    const bool two = i + stride < n8;
+    const uint4 b0 = *reinterpret_cast<const uint4*>(u + i * 8);
+    uint4 b1 = make_uint4(0u, 0u, 0u, 0u);
+    if (two) b1 = *reinterpret_cast<const uint4*>(u + (i + stride) * 8);
     uint4 o;
-    float2 y;
-#define HTRVT_G(v) (0.5f * (v) * (1.0f + erff((v) * 0.70710678118654752f)))
-    y = unpack_bf16(b.x); o.x = pack_bf16(HTRVT_G(y.x), HTRVT_G(y.y));
-    y = unpack_bf16(b.y); o.y = pack_bf16(HTRVT_G(y.x), HTRVT_G(y.y));
-    y = unpack_bf16(b.z); o.z = pack_bf16(HTRVT_G(y.x), HTRVT_G(y.y));
-    y = unpack_bf16(b.w); o.w = pack_bf16(HTRVT_G(y.x), HTRVT_G(y.y));
-#undef HTRVT_G
+    o.x = gelu2(b0.x); o.y = gelu2(b0.y); o.z = gelu2(b0.z); o.w = gelu2(b0.w);
     *reinterpret_cast<uint4*>(a + i * 8) = o;
+    if (two) {
+      o.x = gelu2(b1.x); o.y = gelu2(b1.y); o.z = gelu2(b1.z); o.w = gelu2(b1.w);
+      *reinterpret_cast<uint4*>(a + (i + stride) * 8) = o;
+    }
   }
 }
 
-__global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ u,
-                                __nv_bfloat16* __restrict__ du, long long n8) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const uint4 a = *reinterpret_cast<const uint4*>(da + i * 8);
-    const uint4 b = *reinterpret_cast<const uint4*>(u + i * 8);
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ u,
+                                                        __nv_bfloat16* __restrict__ du, long long n8) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8; i += 2 * stride) {
+    const bool two = i + stride < n8;
+    const uint4 a0 = *reinterpret_cast<const uint4*>(da + i * 8);
+    const uint4 b0 = *reinterpret_cast<const uint4*>(u + i * 8);
+    uint4 a1 = make_uint4(0u, 0u, 0u, 0u), b1 = a1;
+    if (two) {
+      a1 = *reinterpret_cast<const uint4*>(da + (i + stride) * 8);
+      b1 = *reinterpret_cast<const uint4*>(u + (i + stride) * 8);
+    }
     uint4 o;
-    float2 x, y;
-    x = unpack_bf16(a.x); y = unpack_bf16(b.x); o.x = pack_bf16(x.x * gelu_grad(y.x), x.y * gelu_grad(y.y));
-    x = unpack_bf16(a.y); y = unpack_bf16(b.y); o.y = pack_bf16(x.x * gelu_grad(y.x), x.y * gelu_grad(y.y));
-    x = unpack_bf16(a.z); y = unpack_bf16(b.z); o.z = pack_bf16(x.x * gelu_grad(y.x), x.y * gelu_grad(y.y));
-    x = unpack_bf16(a.w); y = unpack_bf16(b.w); o.w = pack_bf16(x.x * gelu_grad(y.x), x.y * gelu_grad(y.y));
+    o.x = gelu_grad2(a0.x, b0.x); o.y = gelu_grad2(a0.y, b0.y); o.z = gelu_grad2(a0.z, b0.z); o.w = gelu_grad2(a0.w, b0.w);
     *reinterpret_cast<uint4*>(du + i * 8) = o;
+    if (two) {
+      o.x = gelu_grad2(a1.x, b1.x); o.y = gelu_grad2(a1.y, b1.y); o.z = gelu_grad2(a1.z, b1.z); o.w = gelu_grad2(a1.w, b1.w);
+      *reinterpret_cast<uint4*>(du + (i + stride) * 8) = o;
+    }
   }
 }
 
