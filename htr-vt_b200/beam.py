@@ -1,0 +1,69 @@
+"""LM-rescored CTC decoding with the reference's contract (model_window/test_with_kenlm.py:25-59).
+
+`simple_ctc_beam_search_with_lm(log_probs[T,C], converter, lm_scorer, beam_size=5) -> str` keeps the reference's
+signature and result; the per-frame beam (T * K^2 Python list operations and a D2H copy per frame per line in the
+reference) runs as one kernel for the whole batch (csrc/beam.cu), one D2H copy brings back the K collapsed candidate
+id rows per line, and only what must stay on the host stays there: id -> char and `lm_scorer.score(text)` (KenLM in
+the reference; any object with a `.score(str) -> float` method).
+`beam_search_with_lm_batch(preds_log[T,B,C], ...) -> list[str]` is the loop of validation_with_kenlm (:85-88).
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _candidate_strings(ids_row, n, converter):
+    """converter.decode(np.array(text), [len(text)]) of the reference (utils.py:72-86) on ONE already collapsed id
+    row: decode() filters blanks / repeats / out-of-alphabet ids AGAIN (so a doubled letter that survived the path
+    collapse through a blank is merged here - reference behaviour, kept)."""
+    a = ids_row[:n]
+    if n == 0:
+        return ""
+    keep = (a != 0) & (a < len(converter.character))
+    keep[1:] &= a[1:] != a[:-1]
+    table = converter.character
+    return "".join(table[i] for i in a[keep].tolist())
+
+
+def kbest_candidates(log_probs, converter, beam_size=5, lengths=None, layout="tbc"):
+    """-> per line: list of (string, path score) for the surviving beams with a non-empty string, in the reference's
+    order (test_with_kenlm.py:42-53)."""
+    ids, lens, scores = ops.ctc_kbest_paths(log_probs, beam_size, lengths, layout)
+    ids, lens, scores = ids.cpu().numpy(), lens.cpu().numpy(), scores.cpu().numpy()
+    out = []
+    for b in range(ids.shape[0]):
+        cands = []
+        for r in range(ids.shape[1]):
+            if lens[b, r] < 0:
+                continue
+            s = _candidate_strings(ids[b, r], int(lens[b, r]), converter)
+            if s:
+                cands.append((s, float(scores[b, r])))
+        out.append(cands)
+    return out
+
+
+def _pick(cands, lm_scorer):
+    if not cands:
+        return ""
+    lm_scores = [lm_scorer.score(c[0]) for c in cands]
+    return cands[int(np.argmax(lm_scores))][0]
+
+
+def simple_ctc_beam_search_with_lm(log_probs, converter, lm_scorer, beam_size=5):
+    """Reference signature: log_probs [T, C] of ONE line -> best string by LM score."""
+    if not log_probs.is_cuda:
+        raise ops.HtrvtError("simple_ctc_beam_search_with_lm needs a CUDA tensor (no CPU fallback)")
+    lp = log_probs.float().unsqueeze(1)                       # [T, 1, C]
+    return _pick(kbest_candidates(lp, converter, beam_size)[0], lm_scorer)
+
+
+def beam_search_with_lm_batch(preds_log, converter, lm_scorer, beam_size=5, lengths=None):
+    """preds_log [T, B, C] (validation_with_kenlm's `preds_log`) -> list of B strings: one kernel, one D2H copy."""
+    if not preds_log.is_cuda:
+        raise ops.HtrvtError("beam_search_with_lm_batch needs a CUDA tensor (no CPU fallback)")
+    lp = preds_log.float()
+    if lp.stride(-1) != 1:
+        lp = lp.contiguous()
+    return [_pick(c, lm_scorer) for c in kbest_candidates(lp, converter, beam_size, lengths)]

@@ -54,6 +54,17 @@ int htrvt_greedy_decode(const float* logits, long long stride_b, long long strid
 int htrvt_ctc_collapse(const void* index, int index_is_int64, const int* lengths, int B, int Tmax, int n_character,
                        int* ids, int* lens, void* stream);
 
+/* ---- K-best CTC alignment paths (LM-rescoring evaluation) ---------------------------------------------------
+ * htrvt_ctc_kbest_paths replaces the per-frame beam of `simple_ctc_beam_search_with_lm`
+ * (model_window/test_with_kenlm.py:25-51): per frame the K most probable classes extend every beam, the K best
+ * (float64 score sums, Python's stable descending order on ties) survive; every surviving path is collapsed
+ * (blanks and repeats dropped, :44-51).  One warp per line.  log_probs fp32 through element strides (class axis
+ * contiguous); ids int32 [B, K, T] zero padded, lens int32 [B, K] (-1: fewer than K paths exist), scores float64
+ * [B, K], beams in the reference's final order.  K <= 8, C <= 256.  id -> char and the language model stay on the
+ * host (htr-vt_b200/beam.py). */
+int htrvt_ctc_kbest_paths(const float* log_probs, long long stride_b, long long stride_t, const int* lengths, int B,
+                          int T, int C, int K, int* ids, int* lens, double* scores, void* stream);
+
 /* ---- tcgen05 tap-GEMM: nn.Linear / nn.Conv2d forward, input gradient, weight gradient ------------------
  * flags (epilogue, run by 8 warps and kept light): 1 bf16 out (else fp32), 2 +bias, 16 accumulate into out
  * (TMA reduce-add store), 32 column statistics (conv fwd), 128 ReLU.  Outputs leave through TMA stores.

@@ -440,6 +440,51 @@ def error_rates(preds_str, labels):
 
 
 # ----------------------------------------------------------------------------------------------
+# K-best alignment paths + LM rescoring (model_window/test_with_kenlm.py:25-59)
+# ----------------------------------------------------------------------------------------------
+def kbest_paths(log_probs: np.ndarray, beam_size: int, acc_dtype=np.float64):
+    """`simple_ctc_beam_search_with_lm` up to its collapse step (test_with_kenlm.py:30-51): returns
+    [(collapsed id list, path score)] for the surviving beams in the reference's order.
+    Per frame the beam_size most probable classes (np.argsort(probs)[-k:][::-1]; a stable sort here, so equal
+    values rank by DEscending index) extend every beam; sorted(..., reverse=True) is stable, so among equal scores
+    the earlier (beam, class) pair survives.  acc_dtype: the reference's `score + probs[c]` starts from the Python
+    float 0.0, which numpy 1.24 (environment.yaml:58) promotes to float64."""
+    T = log_probs.shape[0]
+    beams = [([], acc_dtype(0.0))]
+    for t in range(T):
+        probs = log_probs[t]
+        top_c = np.argsort(probs, kind="stable")[-beam_size:][::-1]
+        new_beams = []
+        for seq, score in beams:
+            for c in top_c:
+                new_beams.append((seq + [int(c)], acc_dtype(score + acc_dtype(probs[c]))))
+        beams = sorted(new_beams, key=lambda x: x[1], reverse=True)[:beam_size]
+    out = []
+    for seq, score in beams:
+        text, prev = [], None
+        for idx in seq:                                          # :46-51
+            if idx != 0 and idx != prev:
+                text.append(idx)
+            prev = idx
+        out.append((text, float(score)))
+    return out
+
+
+def beam_search_with_lm(log_probs: np.ndarray, alphabet: str, lm_score, beam_size: int = 5) -> str:
+    """The whole reference function: candidates -> converter.decode (which filters blanks / repeats / ids beyond the
+    alphabet AGAIN, utils.py:72-86) -> empty strings dropped -> arg-max of the LM score (:52-59)."""
+    cands = []
+    for text, score in kbest_paths(log_probs, beam_size):
+        s = decode_strings(np.array(text, dtype=np.int64), np.array([len(text)]), alphabet)
+        if s and s[0]:
+            cands.append((s[0], score))
+    if not cands:
+        return ""
+    lm = [lm_score(c[0]) for c in cands]
+    return cands[int(np.argmax(lm))][0]
+
+
+# ----------------------------------------------------------------------------------------------
 # One training step (loss + parameter gradients), the unit bench.py's reference arm times
 # ----------------------------------------------------------------------------------------------
 def train_step(sd, image, targets, target_lengths, mask, variant="v1", num_heads=6):

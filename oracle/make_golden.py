@@ -210,6 +210,62 @@ def line_prep_cases():
     print("line_prep", float(y.abs().max()))
 
 
+class StubLM(object):
+    """Deterministic stand-in for KenLMTextScorer (kenlm is not installed here): any object with .score(text)."""
+
+    def score(self, text):
+        return sum(((ord(ch) * 31 + i * 17) % 97) / 97.0 for i, ch in enumerate(text)) - 0.6 * len(text)
+
+
+def reference_beam_function():
+    """The reference's `simple_ctc_beam_search_with_lm`, taken from its source file UNMODIFIED (the module itself
+    cannot be imported: it needs kenlm at import time) and exec'd with numpy in scope."""
+    import ast
+    path = os.path.join(refload.REF_ROOT, "model_window", "test_with_kenlm.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "simple_ctc_beam_search_with_lm"][0]
+    ns = {"np": np, "torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns["simple_ctc_beam_search_with_lm"]
+
+
+def beam_cases():
+    """Best strings of the reference's LM-rescored per-frame beam (model_window/test_with_kenlm.py:25-59) on random
+    and peaked log-prob lines, with the reference's own CTCLabelConverter.  The reference accumulates path scores as
+    `0.0 + np.float32` - float64 under its pinned numpy 1.24, float32 under the numpy 2 of this container; the cases
+    are kept only if the oracle's float64 restatement and a float32 variant agree on every candidate list, so the
+    fixtures do not depend on the promotion rule."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import htrvt_oracle as O
+    _, utl = refload.load_variant("model_window")
+    beam_fn = reference_beam_function()
+    alphabet = "abcdefghijklmnopqrstuvwxyz .,'"
+    conv = utl.CTCLabelConverter(alphabet)
+    lm = StubLM()
+    rs = np.random.RandomState(17)
+    T, C = 40, len(alphabet) + 1
+    lines, best, ks = [], [], []
+    tries = 0
+    while len(lines) < 12 and tries < 200:
+        tries += 1
+        kind = len(lines) % 3
+        x = rs.randn(T, C).astype(np.float32) * (1.0, 3.0, 6.0)[kind]
+        if kind == 2:
+            x[:, 0] += 4.0                                     # blank-heavy, as a trained network emits
+        lp = torch.from_numpy(x).log_softmax(1)
+        K = (5, 3, 8)[kind]
+        c64 = O.kbest_paths(lp.numpy(), K, np.float64)
+        c32 = O.kbest_paths(lp.numpy(), K, np.float32)
+        if [c[0] for c in c64] != [c[0] for c in c32]:
+            continue
+        s = beam_fn(lp, conv, lm, beam_size=K)
+        lines.append(lp.numpy()); best.append(s); ks.append(K)
+    np.savez_compressed(os.path.join(OUT, "beam_cases.npz"), alphabet=np.array(alphabet), log_probs=np.stack(lines),
+                        beam=np.array(ks, dtype=np.int32), best=np.array(best))
+    print("beam", len(lines), "cases;", tries, "draws;", best[:4])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -224,3 +280,4 @@ if __name__ == "__main__":
     argmax_cases()
     metrics_cases()
     line_prep_cases()
+    beam_cases()

@@ -177,3 +177,63 @@ def test_argmax_semantics_and_fused_decode():
     ids, lens = ids.cpu().numpy(), lens.cpu().numpy()
     got = [ids[b, : lens[b]].tolist() for b in range(B)]
     assert got == want
+
+
+class _StubLM(object):
+    """Same deterministic scorer as oracle/make_golden.py::StubLM (stands in for KenLM: any .score(text))."""
+
+    def score(self, text):
+        return sum(((ord(ch) * 31 + i * 17) % 97) / 97.0 for i, ch in enumerate(text)) - 0.6 * len(text)
+
+
+def test_kbest_paths_match_oracle_and_reference_strings():
+    """K-best per-frame beam (model_window/test_with_kenlm.py:25-59): candidate id rows and float64 scores against the
+    oracle restatement, best strings against the fixtures produced by the reference's own function."""
+    h = _pkg()
+    from importlib import import_module
+    ops = import_module("htr-vt_b200.ops")
+    g = np.load(os.path.join(G, "beam_cases.npz"))
+    alphabet = str(g["alphabet"])
+    conv = h.CTCLabelConverter(alphabet)
+    lm = _StubLM()
+    for i in range(len(g["best"])):
+        lp, K = g["log_probs"][i], int(g["beam"][i])
+        x = torch.from_numpy(lp).cuda()
+        assert h.simple_ctc_beam_search_with_lm(x, conv, lm, beam_size=K) == str(g["best"][i])
+        ids, lens, sc = ops.ctc_kbest_paths(x.unsqueeze(1), K)
+        want = O.kbest_paths(lp, K)
+        got = [(ids[0, r, : int(lens[0, r])].cpu().tolist(), float(sc[0, r])) for r in range(K)]
+        assert [a[0] for a in got] == [w[0] for w in want]
+        np.testing.assert_allclose([a[1] for a in got], [w[1] for w in want], rtol=0, atol=1e-9)
+    # one launch for a batch in the reference's [T, B, C] layout == line by line
+    lpb = torch.from_numpy(np.ascontiguousarray(g["log_probs"][0::3].transpose(1, 0, 2))).cuda()   # the K = 5 cases
+    assert h.beam_search_with_lm_batch(lpb, conv, lm, beam_size=5) == [str(s) for s in g["best"][0::3]]
+
+
+@pytest.mark.parametrize("T,C,K", [(1, 7, 5), (9, 3, 8), (128, 80, 5), (256, 90, 8), (64, 228, 1)])
+def test_kbest_paths_edge_shapes(T, C, K):
+    """T = 1, fewer classes than beams (C < K), the BASELINE line shapes, K = 1 (= the greedy path), ragged lengths,
+    and exact ties (quantised log-probs): ids, lens, scores and the order of equal-score beams match the oracle."""
+    from importlib import import_module
+    ops = import_module("htr-vt_b200.ops")
+    rs = np.random.RandomState(T + C + K)
+    B = 5
+    x = rs.randn(B, T, C).astype(np.float32) * 2.0
+    x[1] = np.round(x[1] * 2) / 2                                   # many exactly equal candidates
+    x[2, :, 0] += 5.0
+    lengths = np.array([T, T, max(1, T // 2), T, max(1, T - 1)], dtype=np.int32)
+    ids, lens, sc = ops.ctc_kbest_paths(torch.from_numpy(x).cuda(), K, torch.from_numpy(lengths), layout="btc")
+    ids, lens, sc = ids.cpu().numpy(), lens.cpu().numpy(), sc.cpu().numpy()
+    for b in range(B):
+        want = O.kbest_paths(x[b, : lengths[b]], K)
+        assert (lens[b] >= 0).sum() == len(want)
+        for r, (text, score) in enumerate(want):
+            assert ids[b, r, : lens[b, r]].tolist() == text, (b, r)
+            assert abs(sc[b, r] - score) < 1e-9
+            assert not ids[b, r, lens[b, r]:].any()
+    if K == 1:                                                       # the single best path is the arg-max path
+        am = O.argmax_first(x)
+        for b in range(B):
+            want = [int(v) for i, v in enumerate(am[b, : lengths[b]]) if v != 0 and not (i > 0 and am[b, i - 1] == v)]
+            if not (np.round(x[b] * 2) / 2 == x[b]).all():          # (ties: argmax takes the LOWEST index, argsort the highest)
+                assert ids[b, 0, : lens[b, 0]].tolist() == want

@@ -132,3 +132,22 @@ def test_line_prep_oracle_matches_reference_ops():
     y2 = O.line_prep_u8(g["img"])
     x = torch.from_numpy(g["img"]).float() / 255.
     np.testing.assert_allclose(y2, torch.nn.functional.layer_norm(x, x.shape[1:], eps=1e-5).numpy(), atol=1e-6)
+
+
+def test_beam_restatement_matches_reference_function():
+    """kbest_paths / beam_search_with_lm vs the strings the reference's own `simple_ctc_beam_search_with_lm`
+    (model_window/test_with_kenlm.py:25-59, exec'd from its source by oracle/make_golden.py) returned."""
+    g = np.load(os.path.join(G, "beam_cases.npz"))
+
+    def lm(text):
+        return sum(((ord(ch) * 31 + i * 17) % 97) / 97.0 for i, ch in enumerate(text)) - 0.6 * len(text)
+
+    for i in range(len(g["best"])):
+        got = O.beam_search_with_lm(g["log_probs"][i], str(g["alphabet"]), lm, int(g["beam"][i]))
+        assert got == str(g["best"][i])
+    # K = 1 is the greedy path; float32 and float64 accumulation agree on these fixtures (they were selected so)
+    lp = g["log_probs"][0]
+    am = O.argmax_first(lp[None])[0]
+    greedy = [int(v) for i, v in enumerate(am) if v != 0 and not (i > 0 and am[i - 1] == v)]
+    assert O.kbest_paths(lp, 1)[0][0] == greedy
+    assert [c[0] for c in O.kbest_paths(lp, 5, np.float32)] == [c[0] for c in O.kbest_paths(lp, 5)]
