@@ -212,6 +212,21 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
                              "what": "edit distances of 512 decoded id rows vs label ids, one launch (valid.py:49-55)"}
     except Exception as e:
         out["cer_device"] = {"error": repr(e)[:200]}
+    # ---- LM-rescoring evaluation (model_window/test_with_kenlm.py:25-59): K-best paths of 512 lines in one launch +
+    # one D2H copy + the host-side string building / scorer calls, against the reference's per-frame Python beam
+    try:
+        class _LenLM(object):
+            def score(self, text):
+                return -0.1 * len(text)
+
+        lp = torch.randn(IMG_W // 4, Bi, NB_CLS, device=dev).log_softmax(2)
+        ms_k = timed_ms(lambda: ops.ctc_kbest_paths(lp, 5), 20)
+        ms_b = timed_ms(lambda: h.beam_search_with_lm_batch(lp, conv, _LenLM(), beam_size=5), 3, warm=1)
+        out["kbest_beam"] = {"kernel_us_per_batch": ms_k * 1e3, "with_host_strings_ms_per_batch": ms_b, "lines": Bi,
+                             "beam": 5, "what": "K-best CTC paths on device + LM pick on host (test_with_kenlm.py:25-59)"}
+        del lp
+    except Exception as e:
+        out["kbest_beam"] = {"error": repr(e)[:200]}
     model.train()
     del img
 

@@ -13,17 +13,23 @@ import torch
 from . import ops
 
 
-def _candidate_strings(ids_row, n, converter):
-    """converter.decode(np.array(text), [len(text)]) of the reference (utils.py:72-86) on ONE already collapsed id
-    row: decode() filters blanks / repeats / out-of-alphabet ids AGAIN (so a doubled letter that survived the path
-    collapse through a blank is merged here - reference behaviour, kept)."""
-    a = ids_row[:n]
-    if n == 0:
-        return ""
-    keep = (a != 0) & (a < len(converter.character))
-    keep[1:] &= a[1:] != a[:-1]
+def _candidate_strings(ids, lens, converter):
+    """converter.decode(np.array(text), [len(text)]) of the reference (utils.py:72-86) on every already collapsed id
+    row at once: decode() filters blanks / repeats / out-of-alphabet ids AGAIN (so a doubled letter that survived the
+    path collapse through a blank is merged here - reference behaviour, kept).  ids [R, T], lens [R] -> R strings."""
+    R, T = ids.shape
+    keep = (np.arange(T)[None, :] < lens[:, None]) & (ids != 0) & (ids < len(converter.character))
+    keep[:, 1:] &= ids[:, 1:] != ids[:, :-1]
+    counts = keep.sum(1)
+    ends = np.cumsum(counts)
+    kept = ids[keep]                                          # row-major: row 0's survivors, then row 1's ...
     table = converter.character
-    return "".join(table[i] for i in a[keep].tolist())
+    if all(len(ch) == 1 for ch in table[1:]):                 # single code points: one UTF-32 decode for the batch
+        lut = np.array([32] + [ord(ch) for ch in table[1:]], dtype=np.uint32)
+        flat = lut[kept].astype("<u4", copy=False).tobytes().decode("utf-32-le")
+        return [flat[e - c:e] for c, e in zip(counts.tolist(), ends.tolist())]
+    kept = kept.tolist()
+    return ["".join(table[i] for i in kept[e - c:e]) for c, e in zip(counts.tolist(), ends.tolist())]
 
 
 def kbest_candidates(log_probs, converter, beam_size=5, lengths=None, layout="tbc"):
@@ -31,17 +37,11 @@ def kbest_candidates(log_probs, converter, beam_size=5, lengths=None, layout="tb
     order (test_with_kenlm.py:42-53)."""
     ids, lens, scores = ops.ctc_kbest_paths(log_probs, beam_size, lengths, layout)
     ids, lens, scores = ids.cpu().numpy(), lens.cpu().numpy(), scores.cpu().numpy()
-    out = []
-    for b in range(ids.shape[0]):
-        cands = []
-        for r in range(ids.shape[1]):
-            if lens[b, r] < 0:
-                continue
-            s = _candidate_strings(ids[b, r], int(lens[b, r]), converter)
-            if s:
-                cands.append((s, float(scores[b, r])))
-        out.append(cands)
-    return out
+    B, K, T = ids.shape
+    strings = _candidate_strings(ids.reshape(B * K, T), np.maximum(lens.reshape(-1), 0), converter)
+    sc = scores.tolist()
+    alive = (lens >= 0).tolist()
+    return [[(strings[b * K + r], sc[b][r]) for r in range(K) if alive[b][r] and strings[b * K + r]] for b in range(B)]
 
 
 def _pick(cands, lm_scorer):

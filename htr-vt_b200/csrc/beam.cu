@@ -48,15 +48,23 @@ __global__ void __launch_bounds__(128) ctc_kbest_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < kBeamMaxK; ++i) bs[i] = 0.0;
   int nb = 1;                                                  // live beams
-  for (int t = 0; t < Tb; ++t) {
-    // ---- the frame's KC best classes (value desc, index desc) ----------------------------------
-    const float* xr = xb + static_cast<long long>(t) * st;
-    float v[kBeamCpl];
+  float v[kBeamCpl], vn[kBeamCpl];                            // this frame's log-probs, the next frame's (prefetch)
 #pragma unroll
-    for (int i = 0; i < kBeamCpl; ++i) {
-      const int c = lane + 32 * i;
-      v[i] = c < C ? __ldg(xr + c) : -INFINITY;
+  for (int i = 0; i < kBeamCpl; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = (c < C && Tb > 0) ? __ldg(xb + c) : -INFINITY;
+    vn[i] = -INFINITY;
+  }
+  for (int t = 0; t < Tb; ++t) {
+    if (t + 1 < Tb) {
+      const float* xr = xb + static_cast<long long>(t + 1) * st;
+#pragma unroll
+      for (int i = 0; i < kBeamCpl; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) vn[i] = __ldg(xr + c);
+      }
     }
+    // ---- the frame's KC best classes (value desc, index desc) ----------------------------------
     unsigned taken = 0u;
     float topv[kBeamMaxK];
     int topc[kBeamMaxK];
@@ -138,6 +146,8 @@ __global__ void __launch_bounds__(128) ctc_kbest_kernel(const float* __restrict_
     }
 #pragma unroll
     for (int r = 0; r < kBeamMaxK; ++r) bs[r] = nbs[r];
+#pragma unroll
+    for (int i = 0; i < kBeamCpl; ++i) v[i] = vn[i];
     nb = nnew;
   }
   __syncwarp();
