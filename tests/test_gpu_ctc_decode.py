@@ -145,6 +145,29 @@ def test_ctc_fast_path_is_taken_and_fallback_is_exact():
         np.testing.assert_allclose(x.grad.cpu().numpy(), ref_grad, rtol=1e-4, atol=atol)
 
 
+@pytest.mark.parametrize("T,C", [(128, 81), (37, 13), (5, 2), (256, 90)])
+def test_ctc_odd_shapes_ragged_lengths(T, C):
+    """Class counts that are not a multiple of 4 (scalar staging path), ragged input lengths (rows beyond a line's
+    length get zero gradient), label lengths at the state-per-lane boundaries (S = 31, 33, 63, 65, 127, 129 ...) and
+    lines that end while the posterior pass already runs (overlapped collection): nll / gradient vs float64."""
+    h = _pkg()
+    rs = np.random.RandomState(T * 7 + C)
+    want_L = [0, 1, 15, 16, 31, 32, 47, 48, 63, 64, 65, 100]
+    il = np.array([T, T, T, max(1, T - 1), T, max(1, T // 2 + 1), T, T, T, max(1, T - 3), T, T], dtype=np.int32)
+    tl = np.array([min(L, int(t) // 2 if C == 2 else int(t) * 3 // 4) for L, t in zip(want_L, il)], dtype=np.int32)
+    B = len(tl)
+    labels = rs.randint(1, C, size=int(tl.sum())).astype(np.int32)
+    lg = (rs.randn(B, T, C) * 2.0).astype(np.float32)
+    x = torch.from_numpy(lg).cuda().requires_grad_(True)
+    nll = h.ctc_loss_from_logits(x, torch.from_numpy(labels).cuda(), torch.from_numpy(tl), torch.from_numpy(il))
+    nll.sum().backward()
+    ref_nll, ref_grad = _ctc_ref64(lg, labels, il, tl)
+    np.testing.assert_allclose(nll.detach().cpu().numpy(), ref_nll, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), ref_grad, rtol=1e-4, atol=2e-6)
+    for b in range(B):
+        assert not x.grad[b, int(il[b]):].any()
+
+
 def test_decode_golden_strings():
     h = _pkg()
     g = np.load(os.path.join(G, "decode_cases.npz"))
