@@ -1,7 +1,12 @@
-// CTC loss forward-backward for sm_100a: one CTA per sequence, the alpha and the beta recursion
-// each run by ONE warp (warp-per-recursion, neighbour states exchanged with shuffles), log-space
-// (base 2: ex2/lg2 MUFU), log-probabilities staged once in shared memory, gradient w.r.t. the
-// LOGITS (softmax - posterior) written in a single coalesced pass.
+// CTC loss forward-backward for sm_100a: one CTA per sequence, the alpha and the beta recursion each run by ONE warp
+// (neighbour states exchanged with shuffles), probabilities staged once in shared memory, gradient w.r.t. the LOGITS
+// (softmax - posterior) written in coalesced rows.
+//   fast path : linear domain on the FP64 pipe with exact power-of-two row renormalisation (below: "Fast path");
+//               the other 14 warps collect posterior rows WHILE the recursions run their second half (rows are
+//               complete from the middle of the sequence outwards), normalised with the middle row's likelihood;
+//   guard     : posterior rows must sum to 1 and the alpha-end / beta-start / middle-row likelihoods must agree,
+//               else the sequence is recomputed by the
+//   log path  : log2 domain (ex2/lg2 MUFU), renormalised every 8 steps with a float64 offset - any input.
 //
 // Replaces, for the reference call site model_v1/train.py:21-30 / model_v1/valid.py:32-38:
 //   preds.float().permute(1,0,2).log_softmax(2) -> nn.CTCLoss(reduction='none', zero_infinity=True)
