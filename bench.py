@@ -96,6 +96,14 @@ def cpu_reference_rate(steps, warmup, B=8, seed=0):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import htrvt_oracle as O
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would
+    # quietly turn the multi-threaded CPU arm into a single-threaded one
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
     torch.manual_seed(123)
     sd = O.init_state_dict(NB_CLS, [IMG_H, IMG_W], seed=123)
     img, tg, tl = synth_batch(B, seed)
