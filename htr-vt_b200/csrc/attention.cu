@@ -358,12 +358,7 @@ extern "C" int htrvt_attention_fwd(const void* qkv, int B, int H, int T, int hd,
   AttnP P = {};
   P.B = B; P.H = H; P.T = T; P.scale = scale; P.out = static_cast<__nv_bfloat16*>(out); P.lse = lse;
   const int smem = 6 * kImg + 1024 + 128;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return HTRVT_ERR_LAUNCH;
-    configured = true;
-  }
+  if (!HTRVT_ENSURE_SMEM(attn_fwd_kernel, smem)) return HTRVT_ERR_LAUNCH;
   attn_fwd_kernel<<<B * H, kAttnThreads, smem, stream>>>(tm, P);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
@@ -384,12 +379,7 @@ extern "C" int htrvt_attention_bwd(const void* qkv, const void* out, const void*
   P.o = static_cast<const __nv_bfloat16*>(out); P.dout = static_cast<const __nv_bfloat16*>(dout);
   P.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   const int smem = 12 * kImg + 1024 + 128;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return HTRVT_ERR_LAUNCH;
-    configured = true;
-  }
+  if (!HTRVT_ENSURE_SMEM(attn_bwd_kernel, smem)) return HTRVT_ERR_LAUNCH;
   attn_bwd_kernel<<<B * H, kAttnThreads, smem, stream>>>(tm, tdo, P);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;

@@ -599,12 +599,8 @@ extern "C" int htrvt_attention2_fwd(const void* qkv, int B, int H, int T, int hd
   P.table = table; P.out = static_cast<__nv_bfloat16*>(out); P.lse = lse; P.drop_p = drop_p; P.seed = seed;
   const int smem = 2 * kChunk128 + 4 * nkb * kChunk128 + 2048 + 128 + 1024;
   auto kern = nkb == 1 ? attn2_fwd_kernel<1> : attn2_fwd_kernel<2>;
-  static int configured[2] = {0, 0};
-  if (!configured[nkb - 1]) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return HTRVT_ERR_LAUNCH;
-    configured[nkb - 1] = 1;
-  }
+  if (!(nkb == 1 ? HTRVT_ENSURE_SMEM(attn2_fwd_kernel<1>, smem) : HTRVT_ENSURE_SMEM(attn2_fwd_kernel<2>, smem)))
+    return HTRVT_ERR_LAUNCH;
   kern<<<B * H * nblk, kA2Threads, smem, stream>>>(tq, tqt, tkv, P);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
@@ -644,12 +640,7 @@ extern "C" int htrvt_attention2_bwd(const void* qkv, const void* out, const void
   P.dqkv = static_cast<__nv_bfloat16*>(dqkv); P.dq_part = static_cast<__nv_bfloat16*>(workspace);
   P.drop_p = drop_p; P.seed = seed;
   const int smem = 12 * kChunk128 + 4096 + 128 + 1024;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(attn2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return HTRVT_ERR_LAUNCH;
-    configured = true;
-  }
+  if (!HTRVT_ENSURE_SMEM(attn2_bwd_kernel, smem)) return HTRVT_ERR_LAUNCH;
   attn2_bwd_kernel<<<B * H * nblk, kA2Threads, smem, stream>>>(tq, tqt, tdo, tdot, P);
   HTRVT_LAUNCH_CHECK();
   if (need) {

@@ -194,12 +194,7 @@ extern "C" int htrvt_ctc_kbest_paths(const float* log_probs, long long stride_b,
   const int warps = 4;
   const size_t smem = static_cast<size_t>(warps) * T * kBeamMaxK * sizeof(uint32_t);
   if (smem > 227 * 1024) return HTRVT_ERR_SHAPE;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    if (cudaFuncSetAttribute(ctc_kbest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      return HTRVT_ERR_LAUNCH;
-    configured = 227 * 1024;
-  }
+  if (smem > 48 * 1024 && !HTRVT_ENSURE_SMEM(ctc_kbest_kernel, 227 * 1024)) return HTRVT_ERR_LAUNCH;
   ctc_kbest_kernel<<<(B + warps - 1) / warps, warps * 32, smem, stream>>>(log_probs, stride_b, stride_t, lengths, B, T, C,
                                                                         K, ids, lens, scores);
   HTRVT_LAUNCH_CHECK();

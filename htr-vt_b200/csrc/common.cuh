@@ -23,6 +23,23 @@ extern "C" unsigned long long htrvt_launch_counter;
     if (e__ != cudaSuccess) return HTRVT_ERR_LAUNCH;           \
   } while (0)
 
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember what was set per (call site, device)
+// so that one process driving several GPUs configures the kernel on each of them.  Evaluates to true on success.
+#define HTRVT_ENSURE_SMEM(kern, bytes)                                                                       \
+  ([&]() -> bool {                                                                                           \
+    static int done__[64] = {0};                                                                             \
+    int dev__ = 0;                                                                                           \
+    cudaGetDevice(&dev__);                                                                                   \
+    dev__ &= 63;                                                                                             \
+    const int want__ = static_cast<int>(bytes);                                                              \
+    if (done__[dev__] >= want__ && done__[dev__] > 0) return true;                                           \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, want__) != cudaSuccess)      \
+      return false;                                                                                          \
+    done__[dev__] = want__;                                                                                  \
+    return true;                                                                                             \
+  }())
+
 namespace htrvt {
 
 constexpr float kLog2e = 1.4426950408889634f;

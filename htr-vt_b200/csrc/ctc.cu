@@ -427,6 +427,7 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
   uint64_t* bars = reinterpret_cast<uint64_t*>(offB + T);     // [2][NB]: {n_mid, n_end} | barriers
   float* AB = reinterpret_cast<float*>(bars + 2 * NB);        // alpha | beta when they fit in shared memory
   volatile int& s_bad = *reinterpret_cast<volatile int*>(red + 36);   // fast path: "recompute in log space" flag
+  volatile int& s_badlabel = *reinterpret_cast<volatile int*>(red + 34);   // a target id outside [0, C)
 
   // ---- per-sequence metadata -------------------------------------------------------------------
   int Tb = P.input_lengths ? P.input_lengths[b] : T;
@@ -453,6 +454,7 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
 
   if (tid == 0) {
     s_bad = 0;
+    s_badlabel = 0;
     red[35] = __int_as_float(0);                                // row ticket of the collecting warps
   }
   for (int i = tid; i < 2 * NB; i += kCtcThreads) {
@@ -465,8 +467,15 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
     }
   }
   if (tid == 0) CTC_STAMP(0);
+  __syncthreads();                                              // flags and barriers initialised before anyone uses them
   if (fits) {
-    for (int s = tid; s < SP; s += kCtcThreads) ext[s] = (s < S && (s & 1)) ? P.targets[toff + (s >> 1)] : 0;
+    // labels index the staged probability rows and the per-class shared-memory atomics: an id outside [0, C) is clamped
+    // (memory safety) and the sequence's nll comes back NaN - loud, like torch's device-side assert for such targets
+    for (int s = tid; s < SP; s += kCtcThreads) {
+      int lab = (s < S && (s & 1)) ? P.targets[toff + (s >> 1)] : 0;
+      if (lab < 0 || lab >= C) { lab = min(max(lab, 0), C - 1); s_badlabel = 1; }
+      ext[s] = lab;
+    }
   }
   const bool run = fits && Tb > 0;
 
@@ -703,7 +712,8 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
       __syncthreads();
       if (tid == 0) CTC_STAMP(6);
       if (!s_bad) {
-        if (tid == 0) P.nll[b] = feasible ? static_cast<float>(-ll2 * 0.6931471805599453) : 0.f;   // zero_infinity=True
+        if (tid == 0) P.nll[b] = s_badlabel ? __int_as_float(0x7fc00000)
+                                 : feasible ? static_cast<float>(-ll2 * 0.6931471805599453) : 0.f;   // zero_infinity=True
         return;
       }
     }
@@ -769,7 +779,7 @@ __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const Ctc
   if (tid == 0) {
     float out = feasible ? static_cast<float>(-ll2 * 0.6931471805599453) : 0.f;      // zero_infinity=True
     if (L > Tb) out = 0.f;
-    else if (K > P.kmax) out = __int_as_float(0x7fc00000);   // provisioning error: be loud
+    else if (K > P.kmax || s_badlabel) out = __int_as_float(0x7fc00000);   // provisioning error / bad target id: be loud
     P.nll[b] = out;
   }
   if (!gb) return;
@@ -866,13 +876,7 @@ extern "C" int htrvt_ctc_loss_grad(const float* x, long long x_stride_b, long lo
     const size_t need = static_cast<size_t>(B) * 2 * T * 32 * P.kmax * sizeof(float);
     if (!workspace || workspace_bytes < need) return HTRVT_ERR_WORKSPACE;
   }
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(ctc_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             227 * 1024) != cudaSuccess)
-      return HTRVT_ERR_LAUNCH;
-    configured = 227 * 1024;
-  }
+  if (!HTRVT_ENSURE_SMEM(ctc_loss_grad_kernel, 227 * 1024)) return HTRVT_ERR_LAUNCH;
   ctc_loss_grad_kernel<<<B, kCtcThreads, smem, stream>>>(P);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;

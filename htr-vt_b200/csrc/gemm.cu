@@ -598,13 +598,8 @@ template <int BN, int KIND, bool B_MN, int CL, bool RE = false>
 int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
                cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CL, RE, KIND == 4>;
-  static bool configured = false;
   auto kern = tapgemm_kernel<BN, KIND, B_MN, CL, RE>;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
-      return HTRVT_ERR_LAUNCH;
-    configured = true;
-  }
+  if (!HTRVT_ENSURE_SMEM(kern, Cfg::kSmemBytes)) return HTRVT_ERR_LAUNCH;
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   if (CL == 1) {
     kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, c, P);

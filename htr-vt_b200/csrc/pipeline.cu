@@ -170,12 +170,7 @@ extern "C" int htrvt_edit_distance(const int* a, const int* a_off, int a_stride,
   if (n <= 0) return HTRVT_OK;
   if (!a_len || !b_len || !out || max_b_len < 0 || max_b_len > 4095) return HTRVT_ERR_SHAPE;
   const int smem = kEdWarps * 2 * (max_b_len + 1) * static_cast<int>(sizeof(int));
-  static int configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    if (cudaFuncSetAttribute(edit_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return HTRVT_ERR_LAUNCH;
-    configured = smem;
-  }
+  if (smem > 48 * 1024 && !HTRVT_ENSURE_SMEM(edit_distance_kernel, smem)) return HTRVT_ERR_LAUNCH;
   edit_distance_kernel<<<(n + kEdWarps - 1) / kEdWarps, kEdWarps * 32, smem, stream>>>(a, a_off, a_stride, a_len, b,
                                                                                       b_off, b_stride, b_len, n,
                                                                                       max_b_len, out);

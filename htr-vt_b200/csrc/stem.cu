@@ -657,11 +657,7 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, 
   const int ctas = htrvt_bn_bwd_ctas(P);
   const int rows = static_cast<int>((P + ctas - 1) / ctas);
   const size_t smem = static_cast<size_t>(R) * 3 * C * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    configured = true;
-  }
+  if (!HTRVT_ENSURE_SMEM(bn_bwd_reduce_kernel, 96 * 1024)) return HTRVT_ERR_LAUNCH;
   if (smem > 96 * 1024) return HTRVT_ERR_SHAPE;
   if (cudaMemsetAsync(partial, 0, static_cast<size_t>(3) * C * sizeof(float), stream) != cudaSuccess)
     return HTRVT_ERR_LAUNCH;

@@ -443,12 +443,7 @@ extern "C" int htrvt_stem_head_bwd(const void* g, const void* code, const float*
   int smem = 2 * stage;
   if (smem < 11 * C * 4) smem = 11 * C * 4;
   if (smem > 220 * 1024) return HTRVT_ERR_SHAPE;
-  static int configured = 0;
-  if (configured < smem) {
-    if (cudaFuncSetAttribute(stem_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return HTRVT_ERR_LAUNCH;
-    configured = smem;
-  }
+  if (!HTRVT_ENSURE_SMEM(stem_head_bwd_kernel, smem)) return HTRVT_ERR_LAUNCH;
   stem_head_bwd_kernel<<<ctas, C, smem, stream>>>(static_cast<const __nv_bfloat16*>(g),
                                                   static_cast<const uint8_t*>(code), x, w, partial, B, H, W, C);
   HTRVT_LAUNCH_CHECK();

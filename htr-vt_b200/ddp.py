@@ -34,6 +34,24 @@ class GradAllReduce(object):
         self.pending = []
 
 
+def broadcast_tensors(tensors, group=None, src=0):
+    """Make every rank start from rank `src`'s values (what torch DDP does at construction): parameters AND buffers
+    (BatchNorm running statistics, counters).  Tensors are packed per dtype so the exchange is a handful of collectives."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    by_dtype = {}
+    for t in tensors:
+        by_dtype.setdefault((t.dtype, t.device), []).append(t)
+    with torch.no_grad():
+        for (_dtype, _dev), ts in by_dtype.items():
+            flat = torch.cat([t.detach().reshape(-1) for t in ts])
+            dist.broadcast(flat, src=src, group=group)
+            off = 0
+            for t in ts:
+                t.copy_(flat[off:off + t.numel()].view(t.shape))
+                off += t.numel()
+
+
 def segment_bounds(names, numels, first_transformer_prefix="blocks."):
     """Offsets of the [stem | transformer] split of the flat gradient buffer.  Every tensor starts on a 256-byte
     boundary (64 floats): weight-gradient GEMMs reduce-add into these views through TMA tensor maps, which need

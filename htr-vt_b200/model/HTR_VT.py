@@ -139,6 +139,7 @@ class MaskedAutoencoderViT(nn.Module):
         eps = getattr(self.norm, "eps", 1e-6)
         self.engine = Engine(embed_dim, depth, num_heads, nb_cls, ln_eps=eps, variant="v1")
         self.grad_sync = None           # set by enable_data_parallel(): NCCL all-reduce inside backward
+        self.dp_rank = 0
         self._init_parameters()
 
     def _init_parameters(self):
@@ -176,9 +177,20 @@ class MaskedAutoencoderViT(nn.Module):
     def _tensor_table(self):
         return {name: (mod._parameters[key] if is_p else mod._buffers[key]) for name, mod, key, is_p in self._slots()}
 
-    def enable_data_parallel(self, group=None):
-        """Average gradients over the ranks of `group` inside backward (batch sharding, one process per GPU)."""
+    def enable_data_parallel(self, group=None, broadcast=True):
+        """Average gradients over the ranks of `group` inside backward (batch sharding, one process per GPU).
+        Like torch DDP, every parameter and buffer is first broadcast from rank 0, so replicas start identical even
+        when the ranks were seeded differently (e.g. for augmentation).  Randomness under DP: the span mask comes from
+        torch's CPU generator exactly as in the reference (ranks with the same seed draw the same mask, differently
+        seeded ranks different ones - both are faithful, the reference draws a fresh mask per forward);
+        the window variant's dropout / DropPath streams are offset by the rank so that no two ranks share a mask."""
+        import torch.distributed as dist
+        from ..ddp import broadcast_tensors
         self.grad_sync = GradAllReduce(group)
+        self.dp_rank = dist.get_rank(group) if (dist.is_available() and dist.is_initialized()) else 0
+        if broadcast:
+            broadcast_tensors(list(self._tensor_table().values()), group, src=0)
+            ops.weights_changed()
         return self
 
     def __deepcopy__(self, memo):           # EMA deep-copies the model (utils.py:130): keep comm objects shared

@@ -78,6 +78,7 @@ class MaskedAutoencoderViT(_BaseViT):
         eps = getattr(self.norm, "eps", 1e-6)
         self.engine = Engine(embed_dim, depth, num_heads, nb_cls, ln_eps=eps, variant="window", windows=windows)
         self.grad_sync = None
+        self.dp_rank = 0
         nn.init.normal_(self.mask_token, std=.02)
         for m in self.modules():
             if isinstance(m, nn.Linear):
@@ -95,6 +96,10 @@ class MaskedAutoencoderViT(_BaseViT):
         if self.drop <= 0 and self.attn_drop <= 0 and max(self.drop_path) <= 0:
             return None
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        gen = None
+        if self.dp_rank:                            # data parallel: every rank its own dropout / DropPath stream
+            seed = (seed + 0x9E3779B97F4A7C15 * self.dp_rank) % (2 ** 62)
+            gen = torch.Generator().manual_seed(seed)
         dps = []
         for rate in self.drop_path:                 # timm DropPath: per-sample Bernoulli(keep) / keep
             if rate <= 0:
@@ -103,7 +108,7 @@ class MaskedAutoencoderViT(_BaseViT):
             keep = 1.0 - rate
             pair = []
             for _ in range(2):
-                pair.append(((torch.rand(batch) < keep).float() / keep).to(device, non_blocking=True))
+                pair.append(((torch.rand(batch, generator=gen) < keep).float() / keep).to(device, non_blocking=True))
             dps.append(tuple(pair))
         return {"seed": seed, "drop": self.drop, "attn_drop": self.attn_drop, "drop_path": dps}
 

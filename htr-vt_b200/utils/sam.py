@@ -7,8 +7,9 @@ per-tensor (or foreach) update in `second_step` - ~10^3 launches per iteration f
 Here each pass (gradient norm, climb, restore + AdamW) is one launch per <= 48 tensors and the norm never visits the
 host.  Same call sequence as model_v1/train.py:117-126: `first_step(zero_grad=True)`, forward/backward,
 `second_step(zero_grad=True)`; `param_groups` (lr set by utils.update_lr_cos), `state_dict()` and `zero_grad()` behave
-as in the reference.  Only AdamW (the optimizer the reference trains with, train.py:93) has a fused path; any other
-base optimizer falls back to calling its own `.step()` after the fused restore.
+as in the reference.  Only plain AdamW (the optimizer the reference trains with, train.py:93) has a fused path; any other
+base optimizer - or AdamW with amsgrad / maximize in any group - takes the reference sequence: restore, then the base
+optimizer's own `.step()`.
 """
 import ctypes
 
@@ -99,18 +100,30 @@ class SAM(torch.optim.Optimizer):
         if zero_grad:
             self.zero_grad()
 
+    def _group_fusable(self, group):
+        """The fused restore + AdamW kernel implements plain decoupled-weight-decay Adam only."""
+        return (self._fused_adamw and not group.get("amsgrad", False) and not group.get("maximize", False)
+                and not group.get("capturable", False) and not group.get("differentiable", False))
+
     @torch.no_grad()
     def second_step(self, zero_grad=False):
-        for group in self.param_groups:
-            ps = self._live(group)
+        live = [(group, self._live(group)) for group in self.param_groups]
+        if not all(self._group_fusable(g) for g, ps in live if ps):
+            # any group the fused kernel cannot express (other base optimizer, amsgrad / maximize, ...): the reference
+            # sequence for EVERY group - back to "w" from "w + e(w)", then the base optimizer's own update (sam.py:31-37)
+            for _, ps in live:
+                for p in ps:
+                    p.data.copy_(self.state[p]["old_p"])
+            self.base_optimizer.step()
+            _ops.weights_changed()
+            if zero_grad:
+                self.zero_grad()
+            return
+        bst = self.base_optimizer.state
+        for group, ps in live:
             if not ps:
                 continue
             olds = [self.state[p]["old_p"] for p in ps]
-            if not self._fused_adamw or group.get("amsgrad", False) or group.get("maximize", False):
-                for p, o in zip(ps, olds):                    # get back to "w" from "w + e(w)"
-                    p.data.copy_(o)
-                continue
-            bst = self.base_optimizer.state
             ms, vs = [], []
             for p in ps:
                 st = bst[p]
@@ -125,14 +138,11 @@ class SAM(torch.optim.Optimizer):
             if len(steps) != 1:
                 raise RuntimeError("htr-vt_b200 SAM: parameters of one group must share their step count")
             b1, b2 = group["betas"]
-            lr = group["lr"]
             check(lib().htrvt_mt_adamw(len(ps), _ptrs([p.data for p in ps]), _ptrs([p.grad for p in ps]), _ptrs(ms),
-                                       _ptrs(vs), _ptrs(olds), _numels(ps), float(lr), float(b1), float(b2),
+                                       _ptrs(vs), _ptrs(olds), _numels(ps), float(group["lr"]), float(b1), float(b2),
                                        float(group["eps"]), float(group["weight_decay"]), steps.pop(), _stream()),
                   "htrvt_mt_adamw")
         _ops.weights_changed()
-        if not self._fused_adamw:
-            self.base_optimizer.step()                        # do the actual "sharpness-aware" update
         if zero_grad:
             self.zero_grad()
 

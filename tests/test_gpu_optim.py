@@ -109,3 +109,58 @@ def test_model_ema_matches_reference():
             assert torch.equal(got[k], want[k]), k
     assert not any(p.requires_grad for p in ema.ema.parameters())
     assert copy.deepcopy(ema.ema) is not None
+
+
+@pytest.mark.parametrize("kw", [dict(amsgrad=True), dict(maximize=True)])
+def test_sam_unfusable_adamw_flags_still_update(kw):
+    """AdamW options the fused kernel does not express take the reference sequence (restore + base_optimizer.step());
+    the weights must move exactly as the reference's do (they used to be silently skipped)."""
+    sam, _ = _mods()
+    torch.manual_seed(2)
+    base = [torch.randn(33, 17, device="cuda"), torch.randn(129, device="cuda")]
+    ours = [torch.nn.Parameter(t.clone()) for t in base]
+    ref = [torch.nn.Parameter(t.clone()) for t in base]
+    o = sam.SAM(ours, torch.optim.AdamW, rho=0.05, lr=1e-2, weight_decay=0.1, **kw)
+    r = _RefSAM(ref, torch.optim.AdamW, rho=0.05, lr=1e-2, weight_decay=0.1, **kw)
+    for _ in range(2):
+        g1 = [torch.randn_like(t) for t in base]
+        g2 = [torch.randn_like(t) for t in base]
+        for ps in (ours, ref):
+            for p, g in zip(ps, g1):
+                p.grad = g.clone()
+        o.first_step(zero_grad=True)
+        r.first_step()
+        for ps in (ours, ref):
+            for p, g in zip(ps, g2):
+                p.grad = g.clone()
+        o.second_step(zero_grad=True)
+        r.second_step()
+    for a, b, t in zip(ours, ref, base):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+        assert float((a - t).abs().max()) > 1e-3           # the weights did change
+
+
+def test_install_fused_update_on_a_foreign_ema_class():
+    """`install_fused_update` swaps only `update` on a class with the reference's attributes (the integration route
+    that restates nothing of model_v1/utils/utils.py)."""
+    _, U = _mods()
+
+    class ForeignEma(object):
+        def __init__(self, model, decay):
+            self.ema = copy.deepcopy(model).eval()
+            self.decay, self.device, self.ema_has_module = decay, '', False
+
+        def update(self, model, num_updates=-1):
+            raise AssertionError("should have been replaced")
+
+    U.install_fused_update(ForeignEma)
+    m = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.BatchNorm1d(8)).cuda()
+    e = ForeignEma(m, 0.5)
+    before = {k: v.clone() for k, v in e.ema.state_dict().items()}
+    with torch.no_grad():
+        m[0].weight.add_(1.0)
+        m[1].num_batches_tracked.add_(4)
+    e.update(m)
+    got = e.ema.state_dict()
+    assert torch.allclose(got["0.weight"], before["0.weight"] + 0.5)
+    assert int(got["1.num_batches_tracked"]) == 2
