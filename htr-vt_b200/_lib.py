@@ -67,28 +67,28 @@ SIGNATURES = {
     "htrvt_gelu_fwd": (_I, [_P, _P, _L, _P]),
     "htrvt_row_ln_bwd_ctas": (_I, [_I]),
     "htrvt_row_ln_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P]),
-    "htrvt_tokens_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "htrvt_tokens_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_tokens_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "htrvt_gelu_bwd": (_I, [_P, _P, _P, _L, _P]),
     "htrvt_colsum_rows": (_I, [_I]),
     "htrvt_colsum_bf16": (_I, [_P, _L, _I, _I, _P, _I, _P, _P]),
     "htrvt_cast_bf16": (_I, [_P, _P, _L, _P]),
     "htrvt_dropout_bf16": (_I, [_P, _L, _L, _F, ctypes.c_ulonglong, ctypes.c_uint, _P, _P]),
-    "htrvt_pack_weights": (_I, [_I, _P, _P, _P, _P, _P, _P, _P]),
+    "htrvt_pack_weights": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "htrvt_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "htrvt_conv1_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_bn_finalize": (_I, [_P, _I, ctypes.c_double, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P, _I, _P]),
-    "htrvt_bn_act_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
-    "htrvt_pool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "htrvt_pool_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_bn_act_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P]),
+    "htrvt_pool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "htrvt_pool_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "htrvt_bn_bwd_ctas": (_I, [_L]),
-    "htrvt_bn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _P]),
+    "htrvt_bn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _P]),
     "htrvt_conv1_wgrad_ctas": (_I, []),
     "htrvt_conv1_wgrad": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P]),
     "htrvt_stem_head_moment_ctas": (_I, []),
     "htrvt_stem_head_bwd_ctas": (_I, []),
     "htrvt_stem_head_moments": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "htrvt_stem_head_fwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_stem_head_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "htrvt_stem_head_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_mt_sqnorm": (_I, [_I, _P, _P, _P, _I, _P, _P]),
     "htrvt_mt_sam_first": (_I, [_I, _P, _P, _P, _P, _P, _F, _I, _P]),
@@ -100,6 +100,14 @@ SIGNATURES = {
     "htrvt_attention2_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _I, _I, _I, _F, ctypes.c_ulonglong, _P, _P, _P,
                                   _Z, _P]),
     "htrvt_attention_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _P]),
+    # fp32-parity mode (csrc/exact.cu)
+    "htrvt_split3": (_I, [_P, _P, _L, _P]),
+    "htrvt_bn_act_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "htrvt_maxpool_f32": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_tokens_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "htrvt_row_ln_f32": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "htrvt_gelu_split": (_I, [_P, _P, _L, _P]),
+    "htrvt_attention_f32": (_I, [_P, _I, _I, _I, _I, _F, _P, _P]),
 }
 
 

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #define HTRVT_OK 0
@@ -95,6 +96,19 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+
+// IEEE fp16 pairs: the storage format of the FORWARD stem tensors (activations, raw conv outputs, forward weight
+// copies).  Same 16 bits and the same tensor-core rate as bf16 with 3 more mantissa bits; these quantities are
+// bounded (BatchNorm keeps them O(1)), gradients stay bf16 for their range.  Conversions saturate at +-65504.
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t u) {
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+__device__ __forceinline__ float f16_bits_to_float(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier

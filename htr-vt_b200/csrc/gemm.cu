@@ -255,7 +255,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0 && crank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM * CL, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      // operand formats live in bits [7,10) (A) and [10,13) (B) of the instruction descriptor: 1 = bf16, 0 = fp16
+      const uint32_t idesc = umma_idesc_bf16(kBM * CL, BN, A_MN ? 1 : 0, B_MN ? 1 : 0) &
+                             ~((P.a_f16 ? (1u << 7) : 0u) | (P.b_f16 ? (1u << 10) : 0u));
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
       for (int id = first_tile; id < total_tiles; id += tile_step) {
@@ -342,7 +344,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;                // column half handled by this warp
     const int r = quad * 32 + lane;          // tile row owned in the register phase
     constexpr int kColsPerWarp = BN / 2;
-    const bool out_bf16 = (P.flags & EPI_BF16) != 0;
+    const bool out_bf16 = (P.flags & EPI_BF16) != 0;      // 16-bit output (bf16, or fp16 with EPI_F16)
+    const bool f16 = (P.flags & EPI_F16) != 0;
     const int box_cols = out_bf16 ? 32 : 16;
     uint8_t* stg = stage_out + ew * 4096;                   // 2 x [32 rows][64 B], SWIZZLE_64B
     const int sw_r = (lane >> 1) & 3;
@@ -420,9 +423,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; i += 2) {
             float a = __uint_as_float(raw[i]) * P.alpha, c = __uint_as_float(raw[i + 1]) * P.alpha;
             if (P.flags & EPI_BIAS) { a += bv[i]; c += bv[i + 1]; }
-            if (KIND == 0 && (P.flags & EPI_RES)) { const float2 rr = unpack_bf16(rw[i >> 1]); a += rr.x; c += rr.y; }
+            if (KIND == 0 && (P.flags & EPI_RES)) {
+              const float2 rr = f16 ? unpack_f16(rw[i >> 1]) : unpack_bf16(rw[i >> 1]);
+              a += rr.x; c += rr.y;
+            }
             if (P.flags & EPI_RELU) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-            packed[i >> 1] = pack_bf16(a, c);
+            packed[i >> 1] = f16 ? pack_f16(a, c) : pack_bf16(a, c);
           }
         } else {
 #pragma unroll
@@ -478,7 +484,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int rr = 0; rr < 32; ++rr) {
             uint16_t hv;
             asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(base + rr * 64 + (((lane >> 3) ^ ((rr >> 1) & 3)) << 4)));
-            const float f = __uint_as_float(static_cast<uint32_t>(hv) << 16);
+            const float f = f16 ? f16_bits_to_float(hv) : __uint_as_float(static_cast<uint32_t>(hv) << 16);
             sacc += f;
             qacc = fmaf(f, f, qacc);
           }
@@ -853,7 +859,10 @@ extern "C" int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, i
 }
 
 // bias (nullable, fp32 [Cout]): added in the epilogue before the optional ReLU (eval mode: the folded BatchNorm shift);
-// res (nullable, bf16 [NB,Ho,Wo,Cout]): residual added there too (eval mode: the block's skip connection)
+// res (nullable, 16-bit [NB,Ho,Wo,Cout]): residual added there too (eval mode: the block's skip connection).
+// flags: EPI_RELU (128), EPI_NOSTORE (256), EPI_F16 (1024): x, w, y and res are IEEE fp16 instead of bf16 - the
+// storage format of the forward stem (the engine's choice; bf16 is kept for callers / tests that want it);
+// 2048: y is fp32 (no res / stats), with EPI_ACCUM (16) the launch adds into y (split-operand fp32-parity mode)
 extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks,
                               int sh, int sw, void* y, float* stats_partial, int flags, const float* bias,
                               const void* res, cudaStream_t stream) {
@@ -870,7 +879,8 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
   r = make_map_matrix(&tb, w, Cout, static_cast<long long>(ks) * ks * Cin, static_cast<long long>(ks) * ks * Cin, kBK,
                       bn / cl);
   if (r) return r;
-  r = make_map_out(&tc, y, 2, Cout, Wo, Ho, NB, Cout, static_cast<long long>(Wo) * Cout,
+  const bool y_f32 = (flags & 2048) != 0;                 // fp32-parity mode: raw fp32 output, optionally accumulated
+  r = make_map_out(&tc, y, y_f32 ? 4 : 2, Cout, Wo, Ho, NB, Cout, static_cast<long long>(Wo) * Cout,
                    static_cast<long long>(Ho) * Wo * Cout);
   if (r) return r;
   GemmP P = {};
@@ -881,8 +891,11 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
   P.M_valid = 0; P.N_valid = Cout;
   if (bias && ((Cout & 3) || stats_partial)) return HTRVT_ERR_SHAPE;
   if (res && ((Cout & 31) || stats_partial || (reinterpret_cast<uintptr_t>(res) & 15))) return HTRVT_ERR_SHAPE;
-  P.flags = EPI_BF16 | (flags & (EPI_RELU | EPI_NOSTORE)) | (stats_partial ? EPI_STATS : 0) | (bias ? EPI_BIAS : 0) |
-            (res ? EPI_RES : 0);
+  if (y_f32 && (res || stats_partial)) return HTRVT_ERR_SHAPE;
+  P.flags = (y_f32 ? (flags & EPI_ACCUM) : EPI_BF16) | (flags & (EPI_RELU | EPI_NOSTORE | EPI_F16)) |
+            (stats_partial ? EPI_STATS : 0) | (bias ? EPI_BIAS : 0) | (res ? EPI_RES : 0);
+  P.a_f16 = P.b_f16 = (flags & EPI_F16) ? 1 : 0;        // forward stem tensors: x, w, y (and res) are fp16
+  if (y_f32) P.flags &= ~EPI_F16;                       // (the operand format stays in a_f16 / b_f16)
   P.stats = stats_partial; P.bias = bias; P.res = res; P.alpha = 1.f;
   if (reuse) return launch_reuse(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
   return launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
@@ -891,6 +904,9 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
 // dx[NB,H,W,Cin] (= or +=) conv_transpose(dy[NB,Ho,Wo,Cout], w): one GEMM per output parity class.
 // w_t (optional): the weights as bf16 [Cin][ks*ks][Cout] (htrvt_pack_weights transposed mode): B becomes a K-major
 // operand, which lets BN = 192 tiles run as cta_group::2 pairs (an MN-major B cannot be split at 96 columns).
+// dy, w, w_t and dx are bf16: gradients keep bf16's range, and tcgen05 kind::f16 wants both operands of an MMA in the
+// SAME 16-bit format (a bf16 x fp16 instruction descriptor raised "illegal instruction" on B200) - so the backward
+// GEMMs never see the forward pass's fp16 tensors (the engine keeps bf16 copies of what they need).
 extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* w, const void* w_t, int Cout,
                                 int ks, int sh, int sw, void* dx, int accumulate, cudaStream_t stream) {
   const int pad = ks / 2;
@@ -1006,6 +1022,7 @@ static int conv_wgrad_impl(const void* dy, const void* dy_t, const void* x, int 
   return HTRVT_OK;
 }
 
+// (all weight-gradient entry points: dy and x are bf16 - see htrvt_conv_dgrad)
 extern "C" int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin,
                                 int Cout, int ks, int sh, int sw, float* grad_oihw, int accumulate, void* workspace,
                                 size_t workspace_bytes, cudaStream_t stream) {

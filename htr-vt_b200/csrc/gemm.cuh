@@ -18,7 +18,8 @@ enum : int {
   EPI_STATS = 1 << 5,      // column sum / sum of squares of the stored tile -> stats[cta*4+quadrant][2][N] (+=)
   EPI_RELU = 1 << 7,       // max(x, 0)
   EPI_NOSTORE = 1 << 8,    // measurement aid: skip the epilogue body (main-loop-only timing)
-  EPI_RES = 1 << 9,        // kind 0, bf16 out: + res[n,h,w,col] (same NHWC geometry as the output) before the ReLU
+  EPI_RES = 1 << 9,        // kind 0, 16-bit out: + res[n,h,w,col] (same NHWC geometry as the output) before the ReLU
+  EPI_F16 = 1 << 10,       // the 16-bit output (and the EPI_RES residual) is IEEE fp16, not bf16 (forward stem tensors)
 };
 
 struct GemmP {
@@ -33,6 +34,8 @@ struct GemmP {
   int M_valid, N_valid;    // kind 1: rows (Cout) valid; columns valid
   int a_taps, a_atoms_per_tap;   // KIND 3: the M axis is (tap, 64-channel atom of x): real tap count, Cin / 64
   int flags;
+  int a_f16, b_f16;        // operand element formats of the MMA: 0 = bf16, 1 = fp16 (must be equal: a mixed descriptor
+                           // is an illegal instruction on B200)
   const float* bias;
   const void* res;         // EPI_RES: bf16 residual, laid out like the output
   float* stats;

@@ -218,6 +218,7 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partial, int R,
 // ------------------------------------------------------------------------------------------------
 // tokens: x = (mask ? tok : mask_token) + pos      (fp32 residual stream from the bf16 stem output)
 // ------------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void tokens_fwd_kernel(const __nv_bfloat16* __restrict__ tok, const float* __restrict__ mask,
                                   const float* __restrict__ mask_token, const float* __restrict__ pos,
                                   float* __restrict__ x, int B, int T, int D) {
@@ -228,7 +229,7 @@ __global__ void tokens_fwd_kernel(const __nv_bfloat16* __restrict__ tok, const f
     const int d = static_cast<int>(e % D);
     const int t = static_cast<int>((e / D) % T);
     const uint2 u = *reinterpret_cast<const uint2*>(tok + e);
-    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    float2 a = F16 ? unpack_f16(u.x) : unpack_bf16(u.x), b = F16 ? unpack_f16(u.y) : unpack_bf16(u.y);
     float4 v = make_float4(a.x, a.y, b.x, b.y);
     if (mask) {
       const float m = mask[t];
@@ -400,7 +401,13 @@ struct PackTable {
   int cin[kMaxPack];
   int taps[kMaxPack];
   const float* scale[kMaxPack];          // conv repack only: per-output-channel factor (BatchNorm folding), or null
+  unsigned char f16[kMaxPack];           // destination format: 0 = bf16, 1 = IEEE fp16 (forward conv weights)
 };
+__device__ __forceinline__ __nv_bfloat16 to16(float v, bool f16) {      // 16-bit pattern carried in a bf16-typed word
+  if (!f16) return __float2bfloat16_rn(v);
+  const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  return *reinterpret_cast<const __nv_bfloat16*>(&h);
+}
 __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackTable T) {
   extern __shared__ float pk_stage[];                   // one output channel's [Cin][taps] block (conv repack)
   const int t = blockIdx.y;
@@ -408,6 +415,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
   __nv_bfloat16* __restrict__ dst = T.dst[t];
   const long long n = T.numel[t];
   const int Cin = T.cin[t], taps = T.taps[t];
+  const bool f16 = T.f16[t] != 0;
   if (taps < 0) {
     // transposed cast [R][K] fp32 -> [K][R] bf16 (R = Cin field): OIHW [Cout][Cin*taps] -> [Cin][taps][Cout], the
     // K-major B operand of the input-gradient GEMM.  32 x 32 tiles through smem: both sides contiguous.
@@ -427,7 +435,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int k = k0 + ty + 8 * j, r = r0 + tx;
-        if (r < R && k < K) dst[static_cast<long long>(k) * R + r] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
+        if (r < R && k < K) dst[static_cast<long long>(k) * R + r] = to16(tile[tx][ty + 8 * j], f16);
       }
     }
     return;
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
     const float* __restrict__ sc1 = T.scale[t];           // 1x1 conv with a folded per-output-channel factor
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
-      dst[i] = __float2bfloat16_rn(sc1 ? src[i] * sc1[i / Cin] : src[i]);
+      dst[i] = to16(sc1 ? src[i] * sc1[i / Cin] : src[i], f16);
     return;
   }
   // OIHW -> [Cout][taps][Cin]: per output channel a [Cin][taps] -> [taps][Cin] transpose through smem, so both the
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
     __syncthreads();
     for (int i = threadIdx.x; i < per; i += blockDim.x) {
       const int tap = i / Cin, ci = i - tap * Cin;
-      dst[static_cast<long long>(co) * per + i] = __float2bfloat16_rn(pk_stage[ci * taps + tap] * f);
+      dst[static_cast<long long>(co) * per + i] = to16(pk_stage[ci * taps + tap] * f, f16);
     }
   }
 }
@@ -605,12 +613,13 @@ extern "C" int htrvt_row_ln_bwd(const void* dy_bf16, const float* x, const float
   return HTRVT_OK;
 }
 
-extern "C" int htrvt_tokens_fwd(const void* tok_bf16, const float* mask, const float* mask_token, const float* pos,
-                                float* x, int B, int T, int D, cudaStream_t stream) {
+// tok: the stem output, 16-bit [B,T,D] (fp16 when tok_f16, else bf16)
+extern "C" int htrvt_tokens_fwd(const void* tok, const float* mask, const float* mask_token, const float* pos,
+                                float* x, int B, int T, int D, int tok_f16, cudaStream_t stream) {
   if (B <= 0 || T <= 0 || (D & 3)) return HTRVT_ERR_SHAPE;
   const long long n4 = static_cast<long long>(B) * T * D / 4;
-  tokens_fwd_kernel<<<grid_for(n4, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(tok_bf16), mask,
-                                                           mask_token, pos, x, B, T, D);
+  auto kern = tok_f16 ? tokens_fwd_kernel<true> : tokens_fwd_kernel<false>;
+  kern<<<grid_for(n4, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(tok), mask, mask_token, pos, x, B, T, D);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
@@ -687,8 +696,10 @@ extern "C" int htrvt_pack_conv_weight(const float* w_oihw, void* dst, int Cout, 
 // per-output-channel factor folded into a conv repack (eval-mode BatchNorm folding);
 // taps[i] == 0 -> cast, > 0 -> OIHW -> [Cout][taps][Cin],
 // < 0 -> transposed cast [cin[i]][numel/cin[i]] -> [numel/cin[i]][cin[i]] (cin[i] = rows of the source matrix)
+// f16 (nullable): per-tensor destination format, 0 = bf16, 1 = IEEE fp16 (the forward stem's conv weights)
 extern "C" int htrvt_pack_weights(int n, const void* const* src, void* const* dst, const long long* numel,
-                                  const int* cin, const int* taps, const void* const* scale, cudaStream_t stream) {
+                                  const int* cin, const int* taps, const void* const* scale, const int* f16,
+                                  cudaStream_t stream) {
   if (n <= 0) return HTRVT_OK;
   for (int base = 0; base < n; base += kMaxPack) {
     PackTable T = {};
@@ -700,6 +711,7 @@ extern "C" int htrvt_pack_weights(int n, const void* const* src, void* const* ds
       T.cin[i] = cin[base + i] > 0 ? cin[base + i] : 1;
       T.taps[i] = taps[base + i];
       T.scale[i] = scale ? static_cast<const float*>(scale[base + i]) : nullptr;
+      T.f16[i] = (f16 && f16[base + i]) ? 1 : 0;
       if (T.scale[i] && T.taps[i] < 1) return HTRVT_ERR_SHAPE;       // folding is wired for the conv repacks only
     }
     int smem = 0;

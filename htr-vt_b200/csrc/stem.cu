@@ -30,6 +30,29 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
   return u;
 }
+// F16 = true: the FORWARD stem tensors (activations / raw conv outputs) are IEEE fp16; gradients are always bf16.
+// The 16-bit element type is only a bit pattern to these kernels, so pointers stay __nv_bfloat16* ("16-bit word").
+template <bool F16>
+__device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
+  if (!F16) { unpack8(u, f); return; }
+  float2 t;
+  t = unpack_f16(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_f16(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_f16(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_f16(u.w); f[6] = t.x; f[7] = t.y;
+}
+template <bool F16>
+__device__ __forceinline__ uint4 pack8f(const float (&f)[8]) {
+  if (!F16) return pack8(f);
+  uint4 u;
+  u.x = pack_f16(f[0], f[1]); u.y = pack_f16(f[2], f[3]);
+  u.z = pack_f16(f[4], f[5]); u.w = pack_f16(f[6], f[7]);
+  return u;
+}
+template <bool F16>
+__device__ __forceinline__ float round16(float v) {      // the value a 16-bit store of v would hold
+  return F16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
+}
 
 // ------------------------------------------------------------------------------------------------
 // conv1: x [B,H,W] bf16 (one channel) -> raw [B,H/2,W,C] bf16, stride (2,1), pad 1, + channel statistics
@@ -152,17 +175,19 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------------
 // y = [relu](raw*scale + shift [+ res | + raw2*scale2 + shift2])       8 channels per thread
 // ------------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ scale,
                                   const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                                   const __nv_bfloat16* __restrict__ raw2, const float* __restrict__ scale2,
                                   const float* __restrict__ shift2, __nv_bfloat16* __restrict__ y,
-                                  uint8_t* __restrict__ mask, long long n8, int C, int relu) {
+                                  __nv_bfloat16* __restrict__ y_bf, uint8_t* __restrict__ mask, long long n8, int C,
+                                  int relu) {
   const int G = C / 8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % G) * 8;
     float v[8], s[8], b[8];
-    unpack8(*reinterpret_cast<const uint4*>(raw + i * 8), v);
+    unpack8f<F16>(*reinterpret_cast<const uint4*>(raw + i * 8), v);
     *reinterpret_cast<float4*>(s) = *reinterpret_cast<const float4*>(scale + c);
     *reinterpret_cast<float4*>(s + 4) = *reinterpret_cast<const float4*>(scale + c + 4);
     *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(shift + c);
@@ -171,12 +196,12 @@ __global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const f
     for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], s[k], b[k]);
     if (res) {
       float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(res + i * 8), r);
+      unpack8f<F16>(*reinterpret_cast<const uint4*>(res + i * 8), r);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] += r[k];
     } else if (raw2) {
       float r[8];
-      unpack8(*reinterpret_cast<const uint4*>(raw2 + i * 8), r);
+      unpack8f<F16>(*reinterpret_cast<const uint4*>(raw2 + i * 8), r);
       *reinterpret_cast<float4*>(s) = *reinterpret_cast<const float4*>(scale2 + c);
       *reinterpret_cast<float4*>(s + 4) = *reinterpret_cast<const float4*>(scale2 + c + 4);
       *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(shift2 + c);
@@ -193,7 +218,8 @@ __global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const f
       }
       if (mask) mask[i] = static_cast<uint8_t>(m);       // ReLU mask bits for the backward (1 byte per 8 channels)
     }
-    *reinterpret_cast<uint4*>(y + i * 8) = pack8(v);
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8f<F16>(v);
+    if (y_bf) *reinterpret_cast<uint4*>(y_bf + i * 8) = pack8(v);   // bf16 copy: operand of the next conv's weight gradient
   }
 }
 
@@ -201,6 +227,7 @@ __global__ void bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const f
 // max-pool 3x3, stride (2,1), pad 1 over a = relu(raw*scale+shift) (scale == null: a = raw as is)
 // out [B,Ho,W,C]; idx (optional) = kh*3+kw of the first maximum (torch's arg-max rule)
 // ------------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void pool_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const float* __restrict__ scale,
                                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ out,
                                 uint8_t* __restrict__ idx, int B, int H, int W, int C) {
@@ -233,15 +260,15 @@ __global__ void pool_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const flo
         const int ww = wo + kw - 1;
         if (ww < 0 || ww >= W) continue;
         float v[8];
-        unpack8(*reinterpret_cast<const uint4*>(raw + ((static_cast<long long>(n) * H + hh) * W + ww) * C + g * 8), v);
+        unpack8f<F16>(*reinterpret_cast<const uint4*>(raw + ((static_cast<long long>(n) * H + hh) * W + ww) * C + g * 8), v);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          if (scale) v[k] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(v[k], s[k], b[k]), 0.f)));
+          if (scale) v[k] = round16<F16>(fmaxf(fmaf(v[k], s[k], b[k]), 0.f));
           if (v[k] > best[k]) { best[k] = v[k]; bi[k] = kh * 3 + kw; }
         }
       }
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack8(best);
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8f<F16>(best);
     if (idx) {
       uint2 u;
       u.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
@@ -253,7 +280,7 @@ __global__ void pool_fwd_kernel(const __nv_bfloat16* __restrict__ raw, const flo
 
 // gin[n,h,w,c] = sum over windows (ho,wo) containing (h,w) of gout[ho,wo] * [idx[ho,wo] == position code]
 // optional relu mask: multiply by (relu(raw*scale+shift) > 0); optional fp32 gout (token gradient).
-template <typename GT>
+template <typename GT, bool F16>
 __global__ void pool_bwd_kernel(const GT* __restrict__ gout, const uint8_t* __restrict__ idx,
                                 const __nv_bfloat16* __restrict__ raw, const float* __restrict__ scale,
                                 const float* __restrict__ shift, __nv_bfloat16* __restrict__ gin, int B, int H,
@@ -297,7 +324,7 @@ __global__ void pool_bwd_kernel(const GT* __restrict__ gout, const uint8_t* __re
     }
     if (scale) {
       float v[8];
-      unpack8(*reinterpret_cast<const uint4*>(raw + i * 8), v);
+      unpack8f<F16>(*reinterpret_cast<const uint4*>(raw + i * 8), v);
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         if (!(fmaf(v[k], scale[g * 8 + k], shift[g * 8 + k]) > 0.f)) acc[k] = 0.f;
@@ -310,6 +337,7 @@ __global__ void pool_bwd_kernel(const GT* __restrict__ gout, const uint8_t* __re
 // BatchNorm backward, stage 1: per-CTA partial sums of g' = g * [y > 0] and g' * xhat (one or two BNs)
 // partial [cta][3][C] : sum g', sum g' xhat_a, sum g' xhat_b
 // ------------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ mask,
                                      const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mean_a,
                                      const float* __restrict__ rstd_a, const __nv_bfloat16* __restrict__ raw_b,
@@ -345,7 +373,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const 
       for (int u = 0; u < 4; ++u) {
         float gv[8], xa[8];
         unpack8(gq[u], gv);
-        unpack8(xq[u], xa);
+        unpack8f<F16>(xq[u], xa);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           if (!((mk[u] >> k) & 1u)) gv[k] = 0.f;
@@ -354,7 +382,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const 
         }
         if (raw_b) {
           float xb[8];
-          unpack8(bq[u], xb);
+          unpack8f<F16>(bq[u], xb);
 #pragma unroll
           for (int k = 0; k < 8; ++k) s2[k] = fmaf(gv[k] * rb[k], xb[k] - mb[k], s2[k]);
         }
@@ -434,6 +462,7 @@ __device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
   *reinterpret_cast<float4*>(f) = *reinterpret_cast<const float4*>(p);
   *reinterpret_cast<float4*>(f + 4) = *reinterpret_cast<const float4*>(p + 4);
 }
+template <bool F16>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ mask, const __nv_bfloat16* __restrict__ raw_a,
     const float* __restrict__ coef_a, __nv_bfloat16* __restrict__ d_a, const __nv_bfloat16* __restrict__ raw_b,
@@ -460,7 +489,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
       const int c = static_cast<int>(i % G) * 8;
       float gv[8], xa[8], o[8], A[8], Bc[8], Cc[8];
       unpack8(gq[u], gv);
-      unpack8(xq[u], xa);
+      unpack8f<F16>(xq[u], xa);
 #pragma unroll
       for (int k = 0; k < 8; ++k) if (!((mk[u] >> k) & 1u)) gv[k] = 0.f;
       if (gz) *reinterpret_cast<uint4*>(gz + i * 8) = pack8(gv);
@@ -470,7 +499,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
       *reinterpret_cast<uint4*>(d_a + i * 8) = pack8(o);
       if (raw_b) {
         float xb[8];
-        unpack8(bq[u], xb);
+        unpack8f<F16>(bq[u], xb);
         load8(coef_b + c, A); load8(coef_b + C + c, Bc); load8(coef_b + 2 * C + c, Cc);
 #pragma unroll
         for (int k = 0; k < 8; ++k) o[k] = fmaf(A[k], gv[k], fmaf(Bc[k], xb[k], Cc[k]));
@@ -594,42 +623,49 @@ extern "C" int htrvt_bn_finalize(const float* partial, int R, double count, cons
 }
 
 extern "C" int htrvt_bn_act_fwd(const void* raw, const float* scale, const float* shift, const void* res,
-                                const void* raw2, const float* scale2, const float* shift2, void* y, void* mask,
-                                long long P, int C, int relu, cudaStream_t stream) {
+                                const void* raw2, const float* scale2, const float* shift2, void* y, void* y_bf16,
+                                void* mask, long long P, int C, int relu, int f16, cudaStream_t stream) {
   if (P <= 0 || (C & 7)) return HTRVT_ERR_SHAPE;
   const long long n8 = P * C / 8;
-  bn_act_fwd_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(
+  auto kern = f16 ? bn_act_fwd_kernel<true> : bn_act_fwd_kernel<false>;     // f16: raw / res / raw2 / y are fp16
+  kern<<<grid_for(n8, 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(raw), scale, shift, static_cast<const __nv_bfloat16*>(res),
       static_cast<const __nv_bfloat16*>(raw2), scale2, shift2, static_cast<__nv_bfloat16*>(y),
-      static_cast<uint8_t*>(mask), n8, C, relu);
+      static_cast<__nv_bfloat16*>(y_bf16), static_cast<uint8_t*>(mask), n8, C, relu);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
 
 extern "C" int htrvt_pool_fwd(const void* raw, const float* scale, const float* shift, void* out, void* idx, int B,
-                              int H, int W, int C, cudaStream_t stream) {
+                              int H, int W, int C, int f16, cudaStream_t stream) {
   if (B <= 0 || H <= 0 || W <= 0 || (C & 7)) return HTRVT_ERR_SHAPE;
   const int Ho = (H - 1) / 2 + 1;
   const long long n8 = static_cast<long long>(B) * Ho * W * C / 8;
-  pool_fwd_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(raw), scale, shift,
-                                                         static_cast<__nv_bfloat16*>(out),
-                                                         static_cast<uint8_t*>(idx), B, H, W, C);
+  auto kern = f16 ? pool_fwd_kernel<true> : pool_fwd_kernel<false>;         // f16: raw and out are fp16
+  kern<<<grid_for(n8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(raw), scale, shift,
+                                              static_cast<__nv_bfloat16*>(out), static_cast<uint8_t*>(idx), B, H, W, C);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
 
 extern "C" int htrvt_pool_bwd(const void* gout, int gout_is_f32, const void* idx, const void* raw, const float* scale,
-                              const float* shift, void* gin, int B, int H, int W, int C, cudaStream_t stream) {
+                              const float* shift, void* gin, int B, int H, int W, int C, int raw_f16,
+                              cudaStream_t stream) {
   if (B <= 0 || H <= 0 || W <= 0 || (C & 7) || !idx) return HTRVT_ERR_SHAPE;
   const long long n8 = static_cast<long long>(B) * H * W * C / 8;
-  if (gout_is_f32)
-    pool_bwd_kernel<float><<<grid_for(n8, 256), 256, 0, stream>>>(
-        static_cast<const float*>(gout), static_cast<const uint8_t*>(idx), static_cast<const __nv_bfloat16*>(raw),
-        scale, shift, static_cast<__nv_bfloat16*>(gin), B, H, W, C);
-  else
-    pool_bwd_kernel<__nv_bfloat16><<<grid_for(n8, 256), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(gout), static_cast<const uint8_t*>(idx),
-        static_cast<const __nv_bfloat16*>(raw), scale, shift, static_cast<__nv_bfloat16*>(gin), B, H, W, C);
+  const uint8_t* ix = static_cast<const uint8_t*>(idx);
+  const __nv_bfloat16* rw = static_cast<const __nv_bfloat16*>(raw);
+  __nv_bfloat16* gi = static_cast<__nv_bfloat16*>(gin);
+  const int grid = grid_for(n8, 256);
+  if (gout_is_f32) {
+    const float* go = static_cast<const float*>(gout);
+    if (raw_f16) pool_bwd_kernel<float, true><<<grid, 256, 0, stream>>>(go, ix, rw, scale, shift, gi, B, H, W, C);
+    else pool_bwd_kernel<float, false><<<grid, 256, 0, stream>>>(go, ix, rw, scale, shift, gi, B, H, W, C);
+  } else {
+    const __nv_bfloat16* go = static_cast<const __nv_bfloat16*>(gout);
+    if (raw_f16) pool_bwd_kernel<__nv_bfloat16, true><<<grid, 256, 0, stream>>>(go, ix, rw, scale, shift, gi, B, H, W, C);
+    else pool_bwd_kernel<__nv_bfloat16, false><<<grid, 256, 0, stream>>>(go, ix, rw, scale, shift, gi, B, H, W, C);
+  }
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
@@ -648,7 +684,7 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, 
                             const float* rstd_a, const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a,
                             const void* raw_b, const float* mean_b, const float* rstd_b, const float* gamma_b,
                             float* dgamma_b, float* dbeta_b, void* d_b, void* gz, long long P, int C,
-                            float* partial, float* coef, cudaStream_t stream) {
+                            float* partial, float* coef, int raw_f16, cudaStream_t stream) {
   if (P <= 0 || (C & 7) || C > 2048) return HTRVT_ERR_SHAPE;
   const int G = C / 8;
   if (G > 256) return HTRVT_ERR_SHAPE;
@@ -657,11 +693,15 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, 
   const int ctas = htrvt_bn_bwd_ctas(P);
   const int rows = static_cast<int>((P + ctas - 1) / ctas);
   const size_t smem = static_cast<size_t>(R) * 3 * C * sizeof(float);
-  if (!HTRVT_ENSURE_SMEM(bn_bwd_reduce_kernel, 96 * 1024)) return HTRVT_ERR_LAUNCH;
+  if (!(raw_f16 ? HTRVT_ENSURE_SMEM(bn_bwd_reduce_kernel<true>, 96 * 1024)
+                : HTRVT_ENSURE_SMEM(bn_bwd_reduce_kernel<false>, 96 * 1024)))
+    return HTRVT_ERR_LAUNCH;
+  auto k_reduce = raw_f16 ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>;
+  auto k_apply = raw_f16 ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>;
   if (smem > 96 * 1024) return HTRVT_ERR_SHAPE;
   if (cudaMemsetAsync(partial, 0, static_cast<size_t>(3) * C * sizeof(float), stream) != cudaSuccess)
     return HTRVT_ERR_LAUNCH;
-  bn_bwd_reduce_kernel<<<ctas, threads, smem, stream>>>(
+  k_reduce<<<ctas, threads, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(g), static_cast<const uint8_t*>(mask),
       static_cast<const __nv_bfloat16*>(raw_a), mean_a, rstd_a, static_cast<const __nv_bfloat16*>(raw_b), mean_b,
       rstd_b, partial, P, C, rows);
@@ -673,7 +713,7 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, 
                                                              coef_b, dgamma_b, dbeta_b);
   HTRVT_LAUNCH_CHECK();
   const long long n8 = P * C / 8;
-  bn_bwd_apply_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(
+  k_apply<<<grid_for(n8, 256), 256, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(g), static_cast<const uint8_t*>(mask),
       static_cast<const __nv_bfloat16*>(raw_a), coef_a, static_cast<__nv_bfloat16*>(d_a),
       static_cast<const __nv_bfloat16*>(raw_b), coef_b, static_cast<__nv_bfloat16*>(d_b),

@@ -103,12 +103,13 @@ __global__ void conv1_moments_finalize_kernel(const float* __restrict__ partial,
 // forward: x fp32 [B,H,W] -> out bf16 [B,Ho,W,C] (Ho = (H/2 - 1)/2 + 1), code nibbles [B,Ho,W,C/2]
 // grid (ceil(W/64), ceil(Ho/2), B); blockDim = C: thread -> channel pair (tid % (C/2)), column half (tid / (C/2))
 // ------------------------------------------------------------------------------------------------
-template <bool CODE>      // CODE = false (inference): no arg-max bookkeeping, the pooled value alone
+template <bool CODE, int FMT>       // CODE = false (inference): no arg-max bookkeeping; FMT: output 0 bf16, 1 fp16, 2 fp32
 __global__ void __launch_bounds__(256) stem_head_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ scale,
                                                              const float* __restrict__ shift,
-                                                             __nv_bfloat16* __restrict__ out, uint8_t* __restrict__ code,
-                                                             int B, int H, int W, int C) {
+                                                             __nv_bfloat16* __restrict__ out,
+                                                             __nv_bfloat16* __restrict__ out_bf,
+                                                             uint8_t* __restrict__ code, int B, int H, int W, int C) {
   __shared__ float in[11][kHeadInW];
   const int Hp = H / 2, Ho = (Hp - 1) / 2 + 1;
   const int w0 = blockIdx.x * 64, rp = blockIdx.y, n = blockIdx.z;
@@ -199,7 +200,9 @@ __global__ void __launch_bounds__(256) stem_head_fwd_kernel(const float* __restr
             bb = fmaxf(bb, fmaxf(cvb[q][(s + 2) % 3], cvb[q][s % 3]));
           }
           const long long o = ((static_cast<long long>(n) * Ho + ho) * W + wo);
-          *reinterpret_cast<uint32_t*>(out + o * C + 2 * cp) = pack_bf16(ba, bb);
+          if (FMT == 2) *reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + o * C + 2 * cp) = make_float2(ba, bb);
+          else *reinterpret_cast<uint32_t*>(out + o * C + 2 * cp) = FMT == 1 ? pack_f16(ba, bb) : pack_bf16(ba, bb);
+          if (out_bf) *reinterpret_cast<uint32_t*>(out_bf + o * C + 2 * cp) = pack_bf16(ba, bb);
           if (CODE && code) {
             const unsigned na = ba > 0.f ? static_cast<unsigned>(kha * 3 + kwa) : 15u;
             const unsigned nb = bb > 0.f ? static_cast<unsigned>(khb * 3 + kwb) : 15u;
@@ -419,14 +422,22 @@ extern "C" int htrvt_stem_head_moments(const float* x, const float* w, float* pa
   return HTRVT_OK;
 }
 
-// out bf16 [B,Ho,W,C]; code (nullable: eval mode) uint8 [B,Ho,W,C/2]
+// out [B,Ho,W,C]: out_fmt 0 = bf16, 1 = fp16 (the engine's forward stem format), 2 = fp32 (fp32-parity mode);
+// out_bf16 (nullable): a bf16 copy of out (train mode: operand of layer1.0's weight-gradient GEMMs);
+// code (nullable: eval mode) uint8 [B,Ho,W,C/2]
 extern "C" int htrvt_stem_head_fwd(const float* x, const float* w, const float* scale, const float* shift, void* out,
-                                   void* code, int B, int H, int W, int C, cudaStream_t stream) {
+                                   void* out_bf16, void* code, int B, int H, int W, int C, int out_fmt,
+                                   cudaStream_t stream) {
   if (!head_shape_ok(B, H, W, C)) return HTRVT_ERR_SHAPE;
   const int Ho = (H / 2 - 1) / 2 + 1;
   dim3 grid((W + 63) / 64, (Ho + 1) / 2, B);
-  (code ? stem_head_fwd_kernel<true> : stem_head_fwd_kernel<false>)<<<grid, C, 0, stream>>>(x, w, scale, shift, static_cast<__nv_bfloat16*>(out),
-                                               static_cast<uint8_t*>(code), B, H, W, C);
+  if (out_fmt < 0 || out_fmt > 2) return HTRVT_ERR_SHAPE;
+  auto kern = code ? (out_fmt == 1 ? stem_head_fwd_kernel<true, 1> : out_fmt == 2 ? stem_head_fwd_kernel<true, 2>
+                                                                                  : stem_head_fwd_kernel<true, 0>)
+                   : (out_fmt == 1 ? stem_head_fwd_kernel<false, 1> : out_fmt == 2 ? stem_head_fwd_kernel<false, 2>
+                                                                                   : stem_head_fwd_kernel<false, 0>);
+  kern<<<grid, C, 0, stream>>>(x, w, scale, shift, static_cast<__nv_bfloat16*>(out),
+                               static_cast<__nv_bfloat16*>(out_bf16), static_cast<uint8_t*>(code), B, H, W, C);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }

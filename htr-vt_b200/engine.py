@@ -36,6 +36,9 @@ class Engine(object):
         self.variant = variant
         # window variant: (window_size, shift) per block (model_window/model/HTR_VT.py:274-275)
         self.windows = list(windows) if windows is not None else [(0, 0)] * depth
+        # "bf16": 16-bit tensor-core operands (the product path); "fp32": the fp32-parity eval forward (split-bf16
+        # operands, fp32 everywhere else - csrc/exact.cu), logits within 1e-4 of the fp32 reference
+        self.precision = "bf16"
         if self.hd != 128:
             raise ops.HtrvtError("attention kernel is specialised for head_dim 128 (got %d)" % self.hd)
         if embed_dim % 256 or nb_cls < 2:
@@ -70,6 +73,11 @@ class Engine(object):
             raise ValueError("expected image [B, 1, H, W]")
         if not image.is_cuda:
             raise ops.HtrvtError("htr-vt_b200 runs on CUDA only (no CPU fallback)")
+        if self.precision == "fp32":
+            if training or save:
+                raise ops.HtrvtError("precision='fp32' is the eval-mode parity forward: call model.eval() and run under "
+                                     "torch.no_grad() (training runs with 16-bit tensor-core operands)")
+            return self.forward_fp32(sd, image, mask, widths), None
         B, _, Hi, Wi = image.shape
         D, C = self.D, self.C
         ctx = _Ctx() if save else None
@@ -128,8 +136,15 @@ class Engine(object):
         if training:
             moments, part = ops.stem_head_moments(x0, w1)
         st1 = bnst["patch_embed.bn1"] if fold else self._bn(sd, "patch_embed.bn1", part, B * (Hi // 2) * Wi, training)
-        x, code1 = ops.stem_head_fwd(x0, w1, st1, save)
+        # forward stem tensors are fp16 (ops.STEM_DTYPE); with `save` every activation that feeds a convolution also
+        # gets a bf16 copy (x_bf / a1_bf) from the kernel that writes it: the weight-gradient GEMMs need the format of dY
+        x_bf = None
+        if save:
+            x, code1, x_bf = ops.stem_head_fwd(x0, w1, st1, True, want_bf16=True)
+        else:
+            x, code1 = ops.stem_head_fwd(x0, w1, st1, False)
         blocks = []
+        last_block = "patch_embed.%s.1" % STEM_LAYERS[-1][0]
         zpool = None
         if training:            # one memset for the statistics partials of all 15 stem convolutions
             rows = ops.conv_stats_rows(B, Hi, Wi, 3, 1, 1)
@@ -154,22 +169,31 @@ class Engine(object):
                     r1, pt1 = self._conv(x, wp[p + ".conv1.weight"], 3, s, training, zpool)
                     cnt = r1.numel() // r1.shape[-1]
                     sa = self._bn(sd, p + ".bn1", pt1, cnt, training)
-                    a1, k1 = ops.bn_act_fwd(r1, sa, True, want_mask=save) if save else (ops.bn_act_fwd(r1, sa, True), None)
+                    a1_bf = None
+                    if save:
+                        a1, k1, a1_bf = ops.bn_act_fwd(r1, sa, True, want_mask=True, want_bf16=True)
+                    else:
+                        a1, k1 = ops.bn_act_fwd(r1, sa, True), None
                     r2, pt2 = self._conv(a1, wp[p + ".conv2.weight"], 3, (1, 1), training, zpool)
                     sb = self._bn(sd, p + ".bn2", pt2, cnt, training)
                 rd = sdn = None
                 if (p + ".downsample.0.weight") in sd:
                     rd, ptd = self._conv(x, wp[p + ".downsample.0.weight"], 1, s, training, zpool)
                     sdn = bnst[p + ".downsample.1"] if fold else self._bn(sd, p + ".downsample.1", ptd, cnt, training)
-                    y = ops.bn_act_fwd(r2, sb, True, raw2=rd, st2=sdn, want_mask=save)
+                    y = ops.bn_act_fwd(r2, sb, True, raw2=rd, st2=sdn, want_mask=save,
+                                       want_bf16=save and p != last_block)
                 else:
-                    y = ops.bn_act_fwd(r2, sb, True, res=x, want_mask=save)
-                k2 = None
+                    y = ops.bn_act_fwd(r2, sb, True, res=x, want_mask=save, want_bf16=save and p != last_block)
+                k2 = y_bf = None
                 if save:
-                    y, k2 = y
-                if save:
-                    blocks.append((p, s, x, r1, sa, a1, k1, r2, sb, rd, sdn, k2))
-                x = y
+                    if p != last_block:
+                        y, k2, y_bf = y
+                    else:
+                        y, k2 = y
+                    # the backward reads the bf16 copies (weight gradients) and the raw conv outputs / mask bits
+                    # (BatchNorm backward); the fp16 activations are not kept
+                    blocks.append((p, s, x_bf, r1, sa, a1_bf, k1, r2, sb, rd, sdn, k2))
+                x, x_bf = y, y_bf
         Bx, Hx, Wx, Cx = x.shape
         tok, idx2 = ops.pool_fwd(x, None, save)                  # [B, Hx/2, T, D]
         if tok.shape[1] != 1 or Cx != D:
@@ -239,6 +263,97 @@ class Engine(object):
             ctx.tblocks, ctx.x_final, ctx.hf, ctx.mf, ctx.rf = tblocks, xs, hf, mf, rf
             ctx.logits, ctx.rl, ctx.rng = logits, rl, rng
         return logits, ctx
+
+    # ------------------------------------------------------------------------------------------
+    def _planes_fp32(self, sd):
+        """bf16 plane triples of every GEMM weight (conv weights as [Cout, taps, Cin]; head padded to 8 classes),
+        cached while no parameter changes."""
+        key = (ops.WEIGHT_EPOCH, tuple((v.data_ptr(), v._version) for v in sd.values()))
+        cached = getattr(self, "_fp32_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        wp = {}
+        C8 = (self.C + 7) // 8 * 8
+        for k, v in sd.items():
+            if k.startswith("patch_embed.") and k.endswith("weight") and v.dim() == 4 and v.shape[1] > 1:
+                co, ci, kh, kw = v.shape
+                wp[k] = ops.split3(v.detach().permute(0, 2, 3, 1).reshape(co, kh * kw, ci))
+            elif v.dim() == 2 and k.endswith(".weight"):
+                w = v.detach()
+                if k == "head.weight" and C8 != self.C:
+                    w = torch.nn.functional.pad(w, (0, 0, 0, C8 - self.C))
+                wp[k] = ops.split3(w)
+        bn = {k[:-len(".running_mean")]: self._bn(sd, k[:-len(".running_mean")], None, 1, False)
+              for k in sd if k.startswith("patch_embed.") and k.endswith(".running_mean")}
+        self._fp32_cache = (key, (wp, bn))
+        return wp, bn
+
+    def forward_fp32(self, sd, image, mask=None, widths=None, chunk=32):
+        """Eval-mode forward with fp32 tensors between kernels and split-bf16 tensor-core contractions (csrc/exact.cu;
+        model_v1/model/HTR_VT.py:222-241, model_v1/model/resnet18.py:73-84 with running statistics).
+        -> logits fp32 [B, T, C].  model_v1 only."""
+        if self.variant != "v1":
+            raise ops.HtrvtError("precision='fp32' is implemented for model_v1 (north_star parity row)")
+        if image.shape[0] > chunk:                      # fp32 activations: bound the working set
+            return torch.cat([self.forward_fp32(sd, image[i:i + chunk], mask,
+                                                None if widths is None else widths[i:i + chunk], chunk)
+                              for i in range(0, image.shape[0], chunk)])
+        wp, bn = self._planes_fp32(sd)
+        B, _, Hi, Wi = image.shape
+        D, C = self.D, self.C
+        if image.dtype == torch.uint8:
+            x0, _, _ = ops.line_prep_u8(image[:, 0], widths, 1e-5)
+        else:
+            x0, _, _ = ops.sample_ln_fwd(image.contiguous().float().view(B, Hi, Wi), torch.float32, 1e-5)
+        x, _ = ops.stem_head_fwd(x0, sd["patch_embed.conv1.weight"], bn["patch_embed.bn1"], False,
+                                 out_dtype=torch.float32)
+        xp = ops.split3(x)
+        for lname, stride in STEM_LAYERS:
+            for bi in range(2):
+                p = "patch_embed.%s.%d" % (lname, bi)
+                s = stride if bi == 0 else (1, 1)
+                r1 = ops.conv_fwd_split(xp, wp[p + ".conv1.weight"], 3, s[0], s[1])
+                _, a1p = ops.bn_act_f32(r1, bn[p + ".bn1"], True, want_y=False)
+                r2 = ops.conv_fwd_split(a1p, wp[p + ".conv2.weight"], 3, 1, 1)
+                if (p + ".downsample.0.weight") in sd:
+                    rd = ops.conv_fwd_split(xp, wp[p + ".downsample.0.weight"], 1, s[0], s[1])
+                    x, xp = ops.bn_act_f32(r2, bn[p + ".bn2"], True, raw2=rd, st2=bn[p + ".downsample.1"])
+                else:
+                    x, xp = ops.bn_act_f32(r2, bn[p + ".bn2"], True, res=x)
+        tok = ops.maxpool_f32(x)
+        if tok.shape[1] != 1 or tok.shape[3] != D:
+            raise ValueError("stem output height must pool to 1 (image height 64)")
+        T = tok.shape[2]
+        M = B * T
+        pos = sd.get("pos_embed")
+        if pos is not None and pos.shape[1] != T:
+            raise ValueError("pos_embed has %d positions, sequence has %d" % (pos.shape[1], T))
+        xs = ops.tokens_f32(tok, mask, sd["mask_token"], pos, B, T, D)
+        dev = xs.device
+        pend = None
+        for i in range(self.depth):
+            p = "blocks.%d" % i
+            h1p, x1 = ops.row_ln_f32(xs, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], self.ln_eps, pend)
+            qkv = torch.empty((M, 3 * D), dtype=torch.float32, device=dev)
+            ops.gemm_tn_split(h1p, wp[p + ".attn.qkv.weight"], qkv, sd[p + ".attn.qkv.bias"])
+            op = ops.split3(ops.attention_f32(qkv, B, self.H, T, self.hd, self.hd ** -0.5))
+            y1 = torch.empty((M, D), dtype=torch.float32, device=dev)
+            ops.gemm_tn_split(op, wp[p + ".attn.proj.weight"], y1, sd[p + ".attn.proj.bias"])
+            h2p, x2 = ops.row_ln_f32(x1, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], self.ln_eps, y1)
+            u = torch.empty((M, wp[p + ".mlp.fc1.weight"].shape[1]), dtype=torch.float32, device=dev)
+            ops.gemm_tn_split(h2p, wp[p + ".mlp.fc1.weight"], u, sd[p + ".mlp.fc1.bias"])
+            y2 = torch.empty((M, D), dtype=torch.float32, device=dev)
+            ops.gemm_tn_split(ops.gelu_split(u), wp[p + ".mlp.fc2.weight"], y2, sd[p + ".mlp.fc2.bias"])
+            xs, pend = x2, y2
+        hfp, _ = ops.row_ln_f32(xs, sd["norm.weight"], sd["norm.bias"], self.ln_eps, pend)
+        C8 = (C + 7) // 8 * 8
+        raw_logits = torch.empty((M, C8), dtype=torch.float32, device=dev)
+        hb = sd["head.bias"] if C8 == C else torch.nn.functional.pad(sd["head.bias"].detach(), (0, C8 - C))
+        ops.gemm_tn_split(hfp, wp["head.weight"], raw_logits, hb)
+        if C8 != C:
+            raw_logits = raw_logits[:, :C].contiguous()
+        logits, _, _ = ops.sample_ln_fwd(raw_logits.view(B, T, C), torch.float32, 1e-5)
+        return logits
 
     # ------------------------------------------------------------------------------------------
     def backward(self, sd, ctx, dlogits, grads, on_stage=None):

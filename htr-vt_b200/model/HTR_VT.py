@@ -177,6 +177,15 @@ class MaskedAutoencoderViT(nn.Module):
     def _tensor_table(self):
         return {name: (mod._parameters[key] if is_p else mod._buffers[key]) for name, mod, key, is_p in self._slots()}
 
+    def set_precision(self, precision):
+        """"bf16" (default): 16-bit tensor-core operands, fp32 accumulation - the product path.  "fp32": eval-mode
+        parity forward (fp32 tensors, split-bf16 contractions): logits within 1e-4 of the fp32 reference and greedy
+        decode strings identical to it (north_star); forward only, under model.eval() + torch.no_grad()."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.engine.precision = precision
+        return self
+
     def enable_data_parallel(self, group=None, broadcast=True):
         """Average gradients over the ranks of `group` inside backward (batch sharding, one process per GPU).
         Like torch DDP, every parameter and buffer is first broadcast from rank 0, so replicas start identical even

@@ -9,6 +9,14 @@ import torch
 from ._lib import HtrvtError, check, lib
 
 EPI_BF16, EPI_BIAS, _EPI_2, _EPI_3, EPI_ACCUM, EPI_STATS, _EPI_6, EPI_RELU = (1 << i for i in range(8))
+EPI_F16 = 1 << 10
+# storage format of the FORWARD stem tensors (activations, raw conv outputs, forward conv-weight copies): IEEE fp16 -
+# same 16 bits / tensor-core rate as bf16 with 3 more mantissa bits; gradients stay bf16
+STEM_DTYPE = torch.float16
+
+
+def _is_f16(t):
+    return int(t is not None and t.dtype == torch.float16)
 
 
 def _p(t):
@@ -84,9 +92,17 @@ def linear_wgrad(dy, x, grad, *, accumulate=True):
     return grad
 
 
+def _need_bf16(*ts):
+    for t in ts:
+        if t is not None and t.dtype != torch.bfloat16:
+            raise HtrvtError("backward GEMM operands must be bf16 (tcgen05 takes one 16-bit format per MMA; pass the "
+                             "bf16 copy of a forward activation)")
+
+
 def conv_wgrad_acc(dy, x, ks, sh, sw, grad_tapmajor):
     """grad_tapmajor fp32 [Cout, ks*ks, Cin] += dy^T x_shifted (split-K slices reduce-add in place, no reduce kernel)."""
     _need_cuda(dy, x, grad_tapmajor)
+    _need_bf16(dy, x)
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     check(lib().htrvt_conv_wgrad_acc(_p(dy), _p(None), _p(x), N, H, W, Cin, Cout, ks, sh, sw, _p(grad_tapmajor),
@@ -97,6 +113,7 @@ def conv_wgrad_acc(dy, x, ks, sh, sw, grad_tapmajor):
 def conv_wgrad_acc_t(dy, x, ks, sh, sw, grad_tco):
     """grad_tco fp32 [ks*ks, Cin, Cout] += x_shifted^T dy (transposed weight-gradient GEMM, CTA pairs for every shape)."""
     _need_cuda(dy, x, grad_tco)
+    _need_bf16(dy, x)
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     check(lib().htrvt_conv_wgrad_acc_t(_p(dy), _p(x), N, H, W, Cin, Cout, ks, sh, sw, _p(grad_tco), _stream()),
@@ -108,6 +125,7 @@ def conv_wgrad_acc_w(dy, x, sh, grad_atoms):
     """3x3 conv, horizontal stride 1: grad_atoms fp32 [3, Cin/64, 3, 64, Cout] += (two-accumulator, window-sharing
     weight-gradient GEMM).  unpack_conv_grads(..., layout="atoms") permutes it into OIHW."""
     _need_cuda(dy, x, grad_atoms)
+    _need_bf16(dy, x)
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     check(lib().htrvt_conv_wgrad_acc_w(_p(dy), _p(x), N, H, W, Cin, Cout, sh, _p(grad_atoms), _stream()),
@@ -143,17 +161,21 @@ def conv_out_hw(H, W, ks, sh, sw):
 
 
 def conv_fwd(x, w, ks, sh, sw, y=None, stats=None, relu=False, nostore=False, bias=None, res=None):
-    """x [N,H,W,Cin] bf16 NHWC, w [Cout, ks*ks, Cin] bf16 -> y [N,Ho,Wo,Cout] bf16 (raw conv output).
+    """x [N,H,W,Cin] NHWC, w [Cout, ks*ks, Cin] -> y [N,Ho,Wo,Cout] (raw conv output); x, w, y (and res) share ONE
+    16-bit format: fp16 (the engine's forward stem) or bf16.
     stats: optional fp32 [rows, 2, Cout] per-tile column sum / sum-of-squares partials.
-    bias fp32 [Cout] / res bf16 like y: y = [relu](conv + bias + res) in the epilogue (eval-mode BatchNorm folding)."""
+    bias fp32 [Cout] / res like y: y = [relu](conv + bias + res) in the epilogue (eval-mode BatchNorm folding)."""
     _need_cuda(x, w)
     N, H, W, Cin = x.shape
     Cout = w.shape[0]
     Ho, Wo = conv_out_hw(H, W, ks, sh, sw)
     if y is None:
-        y = torch.empty((N, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+        y = torch.empty((N, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
+    if not (x.dtype == w.dtype == y.dtype and (res is None or res.dtype == x.dtype)):
+        raise HtrvtError("conv_fwd: x, w, y and res must share one 16-bit format")
     check(lib().htrvt_conv_fwd(_p(x), N, H, W, Cin, _p(w), Cout, ks, sh, sw, _p(y), _p(stats),
-                               (EPI_RELU if relu else 0) | (256 if nostore else 0), _p(bias), _p(res), _stream()),
+                               (EPI_RELU if relu else 0) | (256 if nostore else 0) | (EPI_F16 if _is_f16(x) else 0),
+                               _p(bias), _p(res), _stream()),
           "htrvt_conv_fwd")
     return y
 
@@ -163,13 +185,17 @@ def conv_stats_rows(N, H, W, ks, sh, sw):
 
 
 def conv_dgrad(dy, w, x_shape, ks, sh, sw, dx=None, accumulate=False, w_t=None):
-    """w bf16 [Cout, taps, Cin]; w_t (optional) bf16 [Cin, taps, Cout]: K-major B operand (CTA-pair kernel)."""
+    """dy, dx bf16; w bf16 [Cout, taps, Cin] (not read when w_t is given, so the forward pass's fp16 copy may be passed
+    along with it); w_t (optional) bf16 [Cin, taps, Cout]: K-major B operand (CTA-pair kernel)."""
     _need_cuda(dy, w)
     N, H, W, Cin = x_shape
     Cout = w.shape[0]
     if dx is None:
         dx = torch.zeros(x_shape, dtype=torch.bfloat16, device=dy.device) if (ks == 1 and (sh > 1 or sw > 1)) \
             else torch.empty(x_shape, dtype=torch.bfloat16, device=dy.device)
+    if dy.dtype != torch.bfloat16 or (w_t is None and w.dtype != torch.bfloat16) or \
+            (w_t is not None and w_t.dtype != torch.bfloat16):
+        raise HtrvtError("conv_dgrad operands must be bf16 (one 16-bit format per MMA; gradients are bf16)")
     check(lib().htrvt_conv_dgrad(_p(dy), N, H, W, Cin, _p(w), _p(w_t), Cout, ks, sh, sw, _p(dx), int(accumulate),
                                  _stream()),
           "htrvt_conv_dgrad")
@@ -186,6 +212,7 @@ def transpose_px(dy):
 
 def conv_wgrad(dy, x, ks, sh, sw, grad_oihw, accumulate=True, transpose=False):
     _need_cuda(dy, x, grad_oihw)
+    _need_bf16(dy, x)
     N, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     Ho, Wo = conv_out_hw(H, W, ks, sh, sw)
@@ -435,7 +462,7 @@ def row_ln_bwd(dy, x, mean, rstd, gamma, gx, accumulate, dgamma, dbeta):
 def tokens_fwd(tok, mask, mask_token, pos, B, T, D):
     x = torch.empty((B * T, D), dtype=torch.float32, device=tok.device)
     check(lib().htrvt_tokens_fwd(_p(tok), _p(mask), _p(mask_token if mask is not None else None), _p(pos), _p(x), B, T,
-                                 D, _stream()), "htrvt_tokens_fwd")
+                                 D, _is_f16(tok), _stream()), "htrvt_tokens_fwd")
     return x
 
 
@@ -493,11 +520,13 @@ def pack_conv_weight(w, dst=None):
     return dst
 
 
-def pack_weights(items, pad_rows=None, names=None):
+def pack_weights(items, pad_rows=None, names=None, conv_dtype=None):
     """items: list of (src fp32 tensor, kind[, scale]) with kind 'cast' ([out,in]), 'conv' (OIHW -> [Cout, taps, Cin];
     optional scale fp32 [Cout] folded in per output channel: eval-mode BatchNorm folding) or 'convT'.
     One launch for all of them.  pad_rows: {name: rows} allocates that 'cast' output with extra zero rows.
-    Returns the list of bf16 tensors."""
+    Returns the list of 16-bit tensors: 'conv' copies in `conv_dtype` (default STEM_DTYPE = fp16, the forward stem's
+    format), 'cast' and 'convT' (backward-only) copies in bf16."""
+    conv_dtype = conv_dtype or STEM_DTYPE
     n = len(items)
     outs = []
     src = (ctypes.c_void_p * n)()
@@ -506,13 +535,15 @@ def pack_weights(items, pad_rows=None, names=None):
     cin = (ctypes.c_int * n)()
     taps = (ctypes.c_int * n)()
     scale = (ctypes.c_void_p * n)()
+    f16 = (ctypes.c_int * n)()
     for i, item in enumerate(items):
         t, kind = item[0], item[1]
         scale[i] = item[2].data_ptr() if (len(item) > 2 and item[2] is not None) else None
         if kind == "conv":
             Cout, Ci, kh, kw = t.shape
-            o = torch.empty((Cout, kh * kw, Ci), dtype=torch.bfloat16, device=t.device)
+            o = torch.empty((Cout, kh * kw, Ci), dtype=conv_dtype, device=t.device)
             cin[i], taps[i] = Ci, kh * kw
+            f16[i] = int(conv_dtype == torch.float16)
         elif kind == "convT":                 # OIHW -> [Cin, taps, Cout] = plain transpose of [Cout, Cin*taps]
             Cout, Ci, kh, kw = t.shape
             o = torch.empty((Ci, kh * kw, Cout), dtype=torch.bfloat16, device=t.device)
@@ -526,7 +557,7 @@ def pack_weights(items, pad_rows=None, names=None):
             cin[i], taps[i] = 1, 0
         outs.append(o)
         src[i], dst[i], numel[i] = t.data_ptr(), o.data_ptr(), t.numel()
-    check(lib().htrvt_pack_weights(n, src, dst, numel, cin, taps, scale, _stream()), "htrvt_pack_weights")
+    check(lib().htrvt_pack_weights(n, src, dst, numel, cin, taps, scale, f16, _stream()), "htrvt_pack_weights")
     return outs
 
 
@@ -555,25 +586,34 @@ def bn_finalize(partial, count, gamma, beta, running_mean, running_var, nbt, tra
     return out
 
 
-def bn_act_fwd(raw, st, relu, res=None, raw2=None, st2=None, want_mask=False):
-    """-> y, or (y, mask) with want_mask: mask uint8 [P, C/8] = ReLU mask bits consumed by bn_bwd."""
+def bn_act_fwd(raw, st, relu, res=None, raw2=None, st2=None, want_mask=False, want_bf16=False):
+    """-> y, or (y, mask) with want_mask: mask uint8 [P, C/8] = ReLU mask bits consumed by bn_bwd.
+    want_bf16 (train mode, fp16 forward tensors): also returns a bf16 copy of y as the LAST element - the operand of the
+    next convolution's weight-gradient GEMM (which needs the format of dY); y itself when it already is bf16."""
     C = raw.shape[-1]
     P = raw.numel() // C
     y = torch.empty_like(raw)
     mask = torch.empty((P, C // 8), dtype=torch.uint8, device=raw.device) if want_mask else None
+    y_bf = None
+    if want_bf16:
+        y_bf = y if raw.dtype == torch.bfloat16 else torch.empty(raw.shape, dtype=torch.bfloat16, device=raw.device)
     check(lib().htrvt_bn_act_fwd(_p(raw), _p(st[2]), _p(st[3]), _p(res), _p(raw2),
                                  _p(st2[2] if st2 is not None else None), _p(st2[3] if st2 is not None else None),
-                                 _p(y), _p(mask), P, C, int(relu), _stream()), "htrvt_bn_act_fwd")
-    return (y, mask) if want_mask else y
+                                 _p(y), _p(y_bf if (y_bf is not None and y_bf is not y) else None), _p(mask), P, C,
+                                 int(relu), _is_f16(raw), _stream()), "htrvt_bn_act_fwd")
+    out = (y, mask) if want_mask else (y,)
+    if want_bf16:
+        out = out + (y_bf,)
+    return out if len(out) > 1 else out[0]
 
 
 def pool_fwd(raw, st, want_idx):
     B, H, W, C = raw.shape
     Ho = (H - 1) // 2 + 1
-    out = torch.empty((B, Ho, W, C), dtype=torch.bfloat16, device=raw.device)
+    out = torch.empty((B, Ho, W, C), dtype=raw.dtype, device=raw.device)
     idx = torch.empty((B, Ho, W, C), dtype=torch.uint8, device=raw.device) if want_idx else None
     check(lib().htrvt_pool_fwd(_p(raw), _p(st[2] if st is not None else None), _p(st[3] if st is not None else None),
-                               _p(out), _p(idx), B, H, W, C, _stream()), "htrvt_pool_fwd")
+                               _p(out), _p(idx), B, H, W, C, _is_f16(raw), _stream()), "htrvt_pool_fwd")
     return out, idx
 
 
@@ -582,19 +622,22 @@ def pool_bwd(gout, idx, in_shape, raw=None, st=None):
     gin = torch.empty(in_shape, dtype=torch.bfloat16, device=gout.device)
     check(lib().htrvt_pool_bwd(_p(gout), int(gout.dtype == torch.float32), _p(idx), _p(raw),
                                _p(st[2] if st is not None else None), _p(st[3] if st is not None else None), _p(gin),
-                               B, H, W, C, _stream()), "htrvt_pool_bwd")
+                               B, H, W, C, _is_f16(raw), _stream()), "htrvt_pool_bwd")
     return gin
 
 
 def bn_bwd(g, mask, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=None, gamma_b=None, dgamma_b=None,
            dbeta_b=None, want_gz=False):
-    """-> (d_a, d_b | None, gz | None), all bf16 with the shape of raw_a."""
+    """-> (d_a, d_b | None, gz | None), all bf16 with the shape of raw_a.  g bf16; raw_a / raw_b in the forward
+    stem's format (fp16, or bf16)."""
     C = raw_a.shape[-1]
     P = raw_a.numel() // C
     dev = raw_a.device
-    d_a = torch.empty_like(raw_a)
-    d_b = torch.empty_like(raw_a) if raw_b is not None else None
-    gz = torch.empty_like(raw_a) if want_gz else None
+    d_a = torch.empty(raw_a.shape, dtype=torch.bfloat16, device=dev)
+    d_b = torch.empty(raw_a.shape, dtype=torch.bfloat16, device=dev) if raw_b is not None else None
+    gz = torch.empty(raw_a.shape, dtype=torch.bfloat16, device=dev) if want_gz else None
+    if g.dtype != torch.bfloat16 or (raw_b is not None and raw_b.dtype != raw_a.dtype):
+        raise HtrvtError("bn_bwd: gradient must be bf16, raw_a / raw_b one format")
     ctas = lib().htrvt_bn_bwd_ctas(P)
     partial = workspace(ctas * 3 * C * 4 + 6 * C * 4, dev)
     coef = partial[ctas * 3 * C * 4:]
@@ -602,7 +645,7 @@ def bn_bwd(g, mask, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=No
     check(lib().htrvt_bn_bwd(_p(g), _p(mask), _p(raw_a), _p(st_a[0]), _p(st_a[1]), _p(gamma_a), _p(dgamma_a),
                              _p(dbeta_a), _p(d_a), _p(raw_b), _p(st_b[0] if st_b is not None else z),
                              _p(st_b[1] if st_b is not None else z), _p(gamma_b), _p(dgamma_b), _p(dbeta_b), _p(d_b),
-                             _p(gz), P, C, _p(partial), _p(coef), _stream()), "htrvt_bn_bwd")
+                             _p(gz), P, C, _p(partial), _p(coef), _is_f16(raw_a), _stream()), "htrvt_bn_bwd")
     return d_a, d_b, gz
 
 
@@ -620,17 +663,23 @@ def stem_head_moments(x, w):
     return moments, stats
 
 
-def stem_head_fwd(x, w, st, want_code):
-    """conv1 -> BN(scale/shift of st) -> ReLU -> MaxPool(3,(2,1),1).  -> (out bf16 [B,Ho,W,C], code uint8 | None)."""
+def stem_head_fwd(x, w, st, want_code, out_dtype=None, want_bf16=False):
+    """conv1 -> BN(scale/shift of st) -> ReLU -> MaxPool(3,(2,1),1).  -> (out [B,Ho,W,C] in STEM_DTYPE (fp16) unless
+    out_dtype says otherwise, code uint8 | None[, bf16 copy of out with want_bf16: weight-gradient operand])."""
     _need_cuda(x, w)
     B, H, W = x.shape
     C = w.shape[0]
     Ho = (H // 2 - 1) // 2 + 1
-    out = torch.empty((B, Ho, W, C), dtype=torch.bfloat16, device=x.device)
+    out = torch.empty((B, Ho, W, C), dtype=out_dtype or STEM_DTYPE, device=x.device)
     code = torch.empty((B, Ho, W, C // 2), dtype=torch.uint8, device=x.device) if want_code else None
-    check(lib().htrvt_stem_head_fwd(_p(x), _p(w), _p(st[2]), _p(st[3]), _p(out), _p(code), B, H, W, C, _stream()),
-          "htrvt_stem_head_fwd")
-    return out, code
+    fmt = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[out.dtype]
+    out_bf = None
+    if want_bf16:
+        out_bf = out if out.dtype == torch.bfloat16 else torch.empty(out.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().htrvt_stem_head_fwd(_p(x), _p(w), _p(st[2]), _p(st[3]), _p(out),
+                                    _p(out_bf if (out_bf is not None and out_bf is not out) else None), _p(code), B, H, W,
+                                    C, fmt, _stream()), "htrvt_stem_head_fwd")
+    return (out, code, out_bf) if want_bf16 else (out, code)
 
 
 def stem_head_bwd(g, code, x, w, moments, gamma, st, dgamma, dbeta, dw):
@@ -654,6 +703,91 @@ def conv1_wgrad(dy, x, grad, accumulate=True):
     check(lib().htrvt_conv1_wgrad(_p(dy), _p(x), _p(grad), int(accumulate), _p(partial), B, H, W, C, _stream()),
           "htrvt_conv1_wgrad")
     return grad
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32-parity mode (csrc/exact.cu): split-bf16 operands on the tensor pipe, fp32 everywhere else
+# ------------------------------------------------------------------------------------------------
+# (activation plane, weight plane) products kept, smallest first so the fp32 output accumulates upwards;
+# dropped: m.l', l.m', l.l' (<= 2^-24 relative)
+SPLIT_TERMS = ((2, 0), (0, 2), (1, 1), (1, 0), (0, 1), (0, 0))
+
+
+def split3(src):
+    """fp32 tensor -> bf16 planes [3, *shape] with h + m + l == src to 24 bits."""
+    _need_cuda(src)
+    src = src.contiguous()
+    planes = torch.empty((3,) + tuple(src.shape), dtype=torch.bfloat16, device=src.device)
+    check(lib().htrvt_split3(_p(src), _p(planes), src.numel(), _stream()), "htrvt_split3")
+    return planes
+
+
+def gemm_tn_split(xp, wp, out, bias=None):
+    """out fp32 [M,N] = x @ w^T (+ bias) from bf16 planes xp [3,M,K], wp [3,N,K]: six accumulating tcgen05 GEMMs."""
+    for n, (i, j) in enumerate(SPLIT_TERMS):
+        gemm_tn(xp[i], wp[j], out, accumulate=n > 0, bias=bias if n == len(SPLIT_TERMS) - 1 else None)
+    return out
+
+
+def conv_fwd_split(xp, wp, ks, sh, sw):
+    """fp32 raw conv output [N,Ho,Wo,Cout] from bf16 planes xp [3,N,H,W,Cin], wp [3,Cout,ks*ks,Cin]."""
+    _, N, H, W, Cin = xp.shape
+    Cout = wp.shape[1]
+    Ho, Wo = conv_out_hw(H, W, ks, sh, sw)
+    y = torch.empty((N, Ho, Wo, Cout), dtype=torch.float32, device=xp.device)
+    for n, (i, j) in enumerate(SPLIT_TERMS):
+        check(lib().htrvt_conv_fwd(_p(xp[i]), N, H, W, Cin, _p(wp[j]), Cout, ks, sh, sw, _p(y), _p(None),
+                                   2048 | (EPI_ACCUM if n > 0 else 0), _p(None), _p(None), _stream()),
+              "htrvt_conv_fwd (fp32 output)")
+    return y
+
+
+def bn_act_f32(raw, st, relu, res=None, raw2=None, st2=None, want_y=True, want_planes=True):
+    """fp32 BatchNorm(eval coefficients st[2], st[3]) + residual / second BN + ReLU -> (y fp32 | None, planes | None)."""
+    C = raw.shape[-1]
+    P = raw.numel() // C
+    y = torch.empty_like(raw) if want_y else None
+    planes = torch.empty((3,) + tuple(raw.shape), dtype=torch.bfloat16, device=raw.device) if want_planes else None
+    check(lib().htrvt_bn_act_f32(_p(raw), _p(st[2]), _p(st[3]), _p(res), _p(raw2),
+                                 _p(st2[2] if st2 is not None else None), _p(st2[3] if st2 is not None else None),
+                                 _p(y), _p(planes), P, C, int(relu), _stream()), "htrvt_bn_act_f32")
+    return y, planes
+
+
+def maxpool_f32(x):
+    B, H, W, C = x.shape
+    out = torch.empty((B, (H - 1) // 2 + 1, W, C), dtype=torch.float32, device=x.device)
+    check(lib().htrvt_maxpool_f32(_p(x), _p(out), B, H, W, C, _stream()), "htrvt_maxpool_f32")
+    return out
+
+
+def tokens_f32(tok, mask, mask_token, pos, B, T, D):
+    x = torch.empty((B * T, D), dtype=torch.float32, device=tok.device)
+    check(lib().htrvt_tokens_f32(_p(tok), _p(mask), _p(mask_token if mask is not None else None), _p(pos), _p(x), B, T,
+                                 D, _stream()), "htrvt_tokens_f32")
+    return x
+
+
+def row_ln_f32(x, gamma, beta, eps, addend=None):
+    """-> (planes bf16 [3,M,D] of LN(x + addend), x + addend fp32)."""
+    M, D = x.shape
+    planes = torch.empty((3, M, D), dtype=torch.bfloat16, device=x.device)
+    x_new = torch.empty_like(x) if addend is not None else None
+    check(lib().htrvt_row_ln_f32(_p(x), _p(addend), _p(x_new), _p(gamma), _p(beta), _p(None), _p(planes), M, D, eps,
+                                 _stream()), "htrvt_row_ln_f32")
+    return planes, (x_new if addend is not None else x)
+
+
+def gelu_split(u):
+    planes = torch.empty((3,) + tuple(u.shape), dtype=torch.bfloat16, device=u.device)
+    check(lib().htrvt_gelu_split(_p(u), _p(planes), u.numel(), _stream()), "htrvt_gelu_split")
+    return planes
+
+
+def attention_f32(qkv, B, H, T, hd, scale):
+    out = torch.empty((B * T, H * hd), dtype=torch.float32, device=qkv.device)
+    check(lib().htrvt_attention_f32(_p(qkv), B, H, T, hd, scale, _p(out), _stream()), "htrvt_attention_f32")
+    return out
 
 
 def launch_count() -> int:

@@ -86,6 +86,13 @@ int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X, long long 
 int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, const void* w, int Cout, int ks, int sh, int sw,
                    void* y, float* stats_partial, int flags, const float* bias, const void* res, void* stream);
 int htrvt_conv_fwd_stats_rows(int NB, int H, int W, int ks, int sh, int sw);
+/* Forward stem tensors (activations, raw conv outputs, forward weight copies) are IEEE fp16 in the engine: same 16
+ * bits and tensor-core rate as bf16, 3 more mantissa bits - train-mode BatchNorm on bf16 tensors alone costs ~3e-2 on
+ * the logits.  htrvt_conv_fwd takes the fp16 form with flags bit 1024.  Gradients (dy, dx) stay bf16
+ * for their range, and because tcgen05 kind::f16 needs BOTH operands of an MMA in one format (a bf16 x fp16 descriptor
+ * is an illegal instruction on B200) the backward GEMMs take bf16 only: the engine keeps bf16 copies of the
+ * activations for the weight gradients (written by the same kernels that write the fp16 tensors) and bf16 transposed
+ * weights for the input gradients. */
 int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, const void* w, const void* w_t, int Cout, int ks,
                      int sh, int sw, void* dx, int accumulate, void* stream);
 int htrvt_conv_wgrad(const void* dy, const void* dy_t, const void* x, int NB, int H, int W, int Cin, int Cout, int ks,
@@ -154,8 +161,8 @@ int htrvt_row_ln_bwd_ctas(int M);
 int htrvt_row_ln_bwd(const void* dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma,
                      float* gx, int accumulate, float* dgamma, float* dbeta, float* partial, int M, int D,
                      void* stream);
-int htrvt_tokens_fwd(const void* tok_bf16, const float* mask, const float* mask_token, const float* pos, float* x,
-                     int B, int T, int D, void* stream);
+int htrvt_tokens_fwd(const void* tok, const float* mask, const float* mask_token, const float* pos, float* x,
+                     int B, int T, int D, int tok_f16, void* stream);
 int htrvt_tokens_bwd(const float* gx, const float* mask, void* dtok_bf16, float* dmask_token, float* partial, int B,
                      int T, int D, void* stream);
 int htrvt_gelu_fwd(const void* u, void* a, long long n, void* stream);
@@ -170,7 +177,7 @@ int htrvt_cast_bf16(const float* src, void* dst, long long n, void* stream);
 int htrvt_dropout_bf16(void* x, long long n, long long per_sample, float p, unsigned long long seed, unsigned site,
                        const float* dp, void* stream);
 int htrvt_pack_weights(int n, const void* const* src, void* const* dst, const long long* numel, const int* cin,
-                       const int* taps, const void* const* scale, void* stream);
+                       const int* taps, const void* const* scale, const int* f16, void* stream);
 int htrvt_pack_conv_weight(const float* w_oihw, void* dst, int Cout, int Cin, int taps, void* stream);
 
 /* ---- conv stem: first conv, BatchNorm, ReLU, max-pool ------------------------------------------------------
@@ -186,17 +193,17 @@ int htrvt_bn_finalize(const float* partial, int R, double count, const float* ga
                       float eps, int training, float* mean, float* rstd, float* scale, float* shift, int C,
                       void* stream);
 int htrvt_bn_act_fwd(const void* raw, const float* scale, const float* shift, const void* res, const void* raw2,
-                     const float* scale2, const float* shift2, void* y, void* relu_mask_bits, long long P, int C, int relu,
-                     void* stream);
+                     const float* scale2, const float* shift2, void* y, void* y_bf16 /*nullable*/, void* relu_mask_bits,
+                     long long P, int C, int relu, int f16, void* stream);
 int htrvt_pool_fwd(const void* raw, const float* scale, const float* shift, void* out, void* idx, int B, int H,
-                   int W, int C, void* stream);
+                   int W, int C, int f16, void* stream);
 int htrvt_pool_bwd(const void* gout, int gout_is_f32, const void* idx, const void* raw, const float* scale,
-                   const float* shift, void* gin, int B, int H, int W, int C, void* stream);
+                   const float* shift, void* gin, int B, int H, int W, int C, int raw_f16, void* stream);
 int htrvt_bn_bwd_ctas(long long P);
 int htrvt_bn_bwd(const void* g, const void* relu_mask_bits, const void* raw_a, const float* mean_a, const float* rstd_a,
                  const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a, const void* raw_b,
                  const float* mean_b, const float* rstd_b, const float* gamma_b, float* dgamma_b, float* dbeta_b,
-                 void* d_b, void* gz, long long P, int C, float* partial, float* coef, void* stream);
+                 void* d_b, void* gz, long long P, int C, float* partial, float* coef, int raw_f16, void* stream);
 /* ---- fused stem head: conv1 -> BatchNorm -> ReLU -> MaxPool without materialising the conv output -----------
  * Replaces model_v1/model/resnet18.py:74-77 (conv1, bn1, relu, maxpool) and their backward.  The conv has one
  * input channel and K = 9, so its output is recomputed from the fp32 image wherever it is needed:
@@ -209,8 +216,8 @@ int htrvt_stem_head_moment_ctas(void);
 int htrvt_stem_head_bwd_ctas(void);
 int htrvt_stem_head_moments(const float* x, const float* w, float* partial, float* moments, float* stats, int B,
                             int H, int W, int C, void* stream);
-int htrvt_stem_head_fwd(const float* x, const float* w, const float* scale, const float* shift, void* out, void* code,
-                        int B, int H, int W, int C, void* stream);
+int htrvt_stem_head_fwd(const float* x, const float* w, const float* scale, const float* shift, void* out,
+                        void* out_bf16 /*nullable*/, void* code, int B, int H, int W, int C, int out_fmt, void* stream);
 int htrvt_stem_head_bwd(const void* g, const void* code, const float* x, const float* w, const float* moments,
                         const float* gamma, const float* mean, const float* rstd, float* dgamma, float* dbeta,
                         float* dw, float* partial, int B, int H, int W, int C, void* stream);
@@ -243,6 +250,28 @@ int htrvt_line_prep_u8(const void* img, long long sample_stride, int ld, const i
                        float* y, float* mean, float* rstd, float eps, void* stream);
 int htrvt_edit_distance(const int* a, const int* a_off, int a_stride, const int* a_len, const int* b, const int* b_off,
                         int b_stride, const int* b_len, int n, int max_b_len, int* out, void* stream);
+
+/* ---- fp32-parity mode (eval forward; csrc/exact.cu) -------------------------------------------------------------
+ * north_star: logits within 1e-4 of the fp32 reference and greedy-decode strings identical end to end.  Every tensor
+ * between kernels is fp32; the dense contractions stay on the tcgen05 tap GEMM with SPLIT-bf16 operands
+ * (x = h + m + l, three bf16 planes; six accumulating launches h.h' + h.m' + m.h' + m.m' + h.l' + l.h' into an fp32
+ * output: htrvt_gemm_tn with EPI_ACCUM, htrvt_conv_fwd with flags 2048 | 16).  These entry points are the fp32
+ * element-wise steps in between; `planes` = bf16 [3][n] (nullable where noted).
+ * Reference lines: model_v1/model/HTR_VT.py:27-39 (attention), :68-83 (block), :134-136 / :224 / :236-239 (LayerNorms),
+ * model_v1/model/resnet18.py:23-39,73-84 (BatchNorm eval, ReLU, residual, max-pool), timm Mlp (erf GELU). */
+int htrvt_split3(const float* src, void* planes_bf16, long long n, void* stream);
+int htrvt_bn_act_f32(const float* raw, const float* scale, const float* shift, const float* res, const float* raw2,
+                     const float* scale2, const float* shift2, float* y /*nullable*/, void* planes_bf16 /*nullable*/,
+                     long long P, int C, int relu, void* stream);
+int htrvt_maxpool_f32(const float* in, float* out, int B, int H, int W, int C, void* stream);
+int htrvt_tokens_f32(const float* tok, const float* mask, const float* mask_token, const float* pos, float* x, int B,
+                     int T, int D, void* stream);
+int htrvt_row_ln_f32(const float* x, const float* addend /*nullable*/, float* x_out /*nullable*/, const float* gamma,
+                     const float* beta, float* y /*nullable*/, void* planes_bf16 /*nullable*/, int M, int D, float eps,
+                     void* stream);
+int htrvt_gelu_split(const float* u, void* planes_bf16, long long n, void* stream);
+int htrvt_attention_f32(const float* qkv /*[B,T,3,H,hd]*/, int B, int H, int T, int hd, float scale,
+                        float* out /*[B,T,H*hd]*/, void* stream);
 
 #ifdef __cplusplus
 }

@@ -195,7 +195,7 @@ def _attention(sd, p, x, num_heads, window=0, shift=0):
     bias and 1-D window partition (model_window/model/HTR_VT.py:33-62, 114-154)."""
     has_bias = (p + ".relative_position_bias_table") in sd
 
-    def attend(z):
+    def attend(z, key_mask=None):
         Bz, N, C = z.shape
         hd = C // num_heads
         qkv = F.linear(z, sd[p + ".qkv.weight"], sd[p + ".qkv.bias"])
@@ -205,20 +205,33 @@ def _attention(sd, p, x, num_heads, window=0, shift=0):
         if has_bias:
             idx = sd[p + ".relative_position_index"][:N, :N]
             attn = attn + sd[p + ".relative_position_bias_table"][idx].permute(2, 0, 1).unsqueeze(0)
+        if key_mask is not None:                       # True = valid key (model_window/model/HTR_VT.py:49-56)
+            attn = attn.masked_fill(~key_mask.reshape(Bz, 1, 1, N), torch.finfo(attn.dtype).min)
         attn = attn.softmax(dim=-1)
+        if key_mask is not None:
+            attn = torch.nan_to_num(attn, nan=0.0)
         z = (attn @ v).transpose(1, 2).reshape(Bz, N, C)
         return F.linear(z, sd[p + ".proj.weight"], sd[p + ".proj.bias"])
 
     if window <= 0:
         return attend(x)
-    B, N, C = x.shape
-    assert N % window == 0, "oracle restates the no-padding case (T multiple of the window)"
+    # Block._attend (model_window/model/HTR_VT.py:114-154): zero-pad to a multiple of the window, roll tokens and
+    # the validity mask by -shift, attend inside consecutive windows with the padded keys masked, undo, strip
+    B, N0, C = x.shape
+    pad = (window - N0 % window) % window
+    if pad:
+        x = torch.cat([x, x.new_zeros(B, pad, C)], dim=1)
+    N = N0 + pad
+    valid = torch.ones(B, N, dtype=torch.bool, device=x.device)
+    if pad:
+        valid[:, -pad:] = False
     if shift > 0:
         x = torch.roll(x, shifts=(-shift,), dims=1)
-    x = attend(x.reshape(B * (N // window), window, C)).reshape(B, N, C)
+        valid = torch.roll(valid, shifts=(-shift,), dims=1)
+    x = attend(x.reshape(B * (N // window), window, C), valid.reshape(B * (N // window), window)).reshape(B, N, C)
     if shift > 0:
         x = torch.roll(x, shifts=(shift,), dims=1)
-    return x
+    return x[:, :N0]
 
 
 def _mlp(sd, p, x):
@@ -487,6 +500,15 @@ def beam_search_with_lm(log_probs: np.ndarray, alphabet: str, lm_score, beam_siz
 # ----------------------------------------------------------------------------------------------
 # One training step (loss + parameter gradients), the unit bench.py's reference arm times
 # ----------------------------------------------------------------------------------------------
+def grad_sample_index(name, numel, n=8192):
+    """Reproducible element sample of a gradient tensor for the committed goldens (full gradients are 214 MB; 8192
+    elements per tensor estimate a cosine to ~1e-3): sorted indices from a RandomState seeded by the tensor NAME."""
+    if numel <= n:
+        return np.arange(numel)
+    rs = np.random.RandomState(sum((i + 1) * ord(ch) for i, ch in enumerate(name)) % (2 ** 31))
+    return np.sort(rs.choice(numel, size=n, replace=False))
+
+
 def train_step(sd, image, targets, target_lengths, mask, variant="v1", num_heads=6):
     """compute_loss + backward (model_v1/train.py:21-30,122-123) with an explicit span mask.
     Returns (loss, {name: grad}) for every floating-point parameter except pos_embed."""

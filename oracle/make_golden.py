@@ -83,6 +83,72 @@ def model_case(variant, tag, nb_cls, W, B, seed, cfg, train_seed=7, mask_ratio=0
     print("wrote", tag, {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+grad_sample_index = O.grad_sample_index
+
+
+def train_batch_case(tag="v1_train_b32", nb_cls=80, W=512, B=32, seed=777, train_seed=9):
+    """model_v1, FULL architecture, a batch where BatchNorm batch statistics are well conditioned (B = 32):
+    train-mode logits / loss / per-sample nll / gradient samples of all 101 trainable tensors through the reference's
+    own compute_loss sequence (model_v1/train.py:21-30), plus eval-mode logits and the strings the reference's
+    valid.py:40-42 + CTCLabelConverter.decode produce from them."""
+    htr, utl = refload.load_variant("model_v1")
+    ref = htr.create_model(nb_cls=nb_cls, img_size=[64, W])
+    sd = O.init_state_dict(nb_cls, [64, W], seed=seed)
+    ref.load_state_dict(sd, strict=True)
+    x = images(seed + 1, B, W)
+    tg, tl = labels(seed + 2, B, nb_cls, 16, 64)
+    out = {"meta": np.array([nb_cls, W, B, seed, train_seed])}
+    ref.eval()
+    alphabet = "".join(chr(33 + i) for i in range(nb_cls - 1))
+    conv = utl.CTCLabelConverter(alphabet)
+    with torch.no_grad():
+        pe = ref(x).float()
+        out["logits_eval"] = pe.numpy()
+        preds = pe.permute(1, 0, 2).log_softmax(2)                      # valid.py:32,35
+        _, idx = preds.max(2)                                           # valid.py:40
+        idx = idx.transpose(1, 0).contiguous().view(-1)                 # valid.py:41
+        out["strings_eval"] = np.array(conv.decode(idx.data, torch.IntTensor([pe.size(1)] * B)))   # valid.py:42
+        out["index_eval"] = idx.numpy().astype(np.int16)
+    ref.train()
+    torch.manual_seed(train_seed)
+    preds = ref(x, 0.4, 8, use_masking=True)
+    lp = preds.float().permute(1, 0, 2).log_softmax(2)
+    nll = torch.nn.CTCLoss(reduction="none", zero_infinity=True)(lp, tg, torch.IntTensor([preds.size(1)] * B), tl)
+    loss = nll.mean()
+    loss.backward()
+    torch.manual_seed(train_seed)
+    out["mask"] = O.draw_span_mask(W // 4, 0.4, 8).numpy()
+    out.update(logits_train=preds.detach().numpy(), loss=np.float64(loss.item()), nll=nll.detach().numpy())
+    names = [k for k, p in ref.named_parameters() if p.grad is not None]
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array([float(dict(ref.named_parameters())[k].grad.double().norm()) for k in names])
+    params = dict(ref.named_parameters())
+    out["grad_samples"] = np.concatenate(
+        [params[k].grad.reshape(-1)[torch.from_numpy(grad_sample_index(k, params[k].numel()))].numpy() for k in names])
+    out["grad_sample_counts"] = np.array([len(grad_sample_index(k, params[k].numel())) for k in names])
+    msd = ref.state_dict()
+    out["bn_running"] = np.concatenate([msd[k].numpy().reshape(-1) for k in msd if "running_" in k])
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    print("wrote", tag, float(loss), out["strings_eval"][:2])
+
+
+def window_ragged_case(tag, W, B, seed, nb_cls=90):
+    """model_window at a width whose token count is NOT a multiple of the 16-token window: exercises the zero-pad +
+    rolled key-padding-mask branch (model_window/model/HTR_VT.py:121-131,49-56).  Eval-mode logits of the reference."""
+    htr, _ = refload.load_variant("model_window")
+    ref = htr.create_model(nb_cls=nb_cls, img_size=[W, 64])
+    sd = O.init_state_dict(nb_cls, [64, W], seed=seed, variant="window")
+    assert sorted(ref.state_dict().keys()) == sorted(sd.keys())
+    ref.load_state_dict(sd, strict=True)
+    x = images(seed + 1, B, W)
+    ref.eval()
+    with torch.no_grad():
+        lg = ref(x).numpy()
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), logits_eval=lg, meta=np.array([nb_cls, W, B, seed]),
+                        keys=np.array(list(ref.state_dict().keys())))
+    print("wrote", tag, lg.shape)
+
+
 def ctc_cases():
     """torch.nn.CTCLoss (the reference's criterion, model_v1/train.py:95) on CPU."""
     specs = [  # name, B, T, C, (Lmin, Lmax), special
@@ -269,6 +335,11 @@ def beam_cases():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "r2":           # the round-2 additions only
+        window_ragged_case("win_w1000", 1000, 2, 411)
+        window_ragged_case("win_w600", 600, 2, 412)
+        train_batch_case()
+        sys.exit(0)
     small = dict(embed_dim=64, depth=2, num_heads=2)
     full = dict(embed_dim=768, depth=4, num_heads=6)
     model_case("v1", "v1_small", 20, 128, 3, 11, small)
@@ -281,3 +352,6 @@ if __name__ == "__main__":
     metrics_cases()
     line_prep_cases()
     beam_cases()
+    window_ragged_case("win_w1000", 1000, 2, 411)
+    window_ragged_case("win_w600", 600, 2, 412)
+    train_batch_case()

@@ -112,35 +112,52 @@ def _conv_ref(x_nhwc, w_oihw, ks, sh, sw):
     return F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w_oihw.float(), None, (sh, sw), ks // 2)
 
 
+@pytest.mark.parametrize("fwd", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("NB,H,W,Cin,Cout,ks,sh,sw", CONVS)
-def test_conv_fwd_dgrad_wgrad(NB, H, W, Cin, Cout, ks, sh, sw):
+def test_conv_fwd_dgrad_wgrad(NB, H, W, Cin, Cout, ks, sh, sw, fwd):
+    """fwd = storage format of the FORWARD tensors (x, w, y): fp16 is what the engine uses, bf16 the all-bf16 form.
+    The backward GEMMs always take bf16 (tcgen05 needs one 16-bit format per MMA): bf16 copies of x and w."""
     o = ops()
     torch.manual_seed(4)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    x = torch.randn(NB, H, W, Cin, device="cuda").bfloat16()
-    w = (torch.randn(Cout, Cin, ks, ks, device="cuda") / (Cin * ks * ks) ** 0.5).bfloat16()
+    x = torch.randn(NB, H, W, Cin, device="cuda").to(fwd)
+    w = (torch.randn(Cout, Cin, ks, ks, device="cuda") / (Cin * ks * ks) ** 0.5).to(fwd)
     wk = w.permute(0, 2, 3, 1).reshape(Cout, ks * ks, Cin).contiguous()
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     wr = w.float().requires_grad_(True)
     yr = F.conv2d(xr, wr, None, (sh, sw), ks // 2)
     rows = o.conv_stats_rows(NB, H, W, ks, sh, sw)
     stats = torch.zeros(rows, 2, Cout, device="cuda")
-    y = torch.full((NB, yr.shape[2], yr.shape[3], Cout), 7.0, device="cuda", dtype=torch.bfloat16)
+    y = torch.full((NB, yr.shape[2], yr.shape[3], Cout), 7.0, device="cuda", dtype=fwd)
     y = o.conv_fwd(x, wk, ks, sh, sw, y=y, stats=stats)
     assert y.shape == (NB, yr.shape[2], yr.shape[3], Cout)
     assert _rel(y.permute(0, 3, 1, 2), yr) < 1e-2
     yf = y.float()
     assert _rel(stats[:, 0].sum(0), yf.sum((0, 1, 2))) < 1e-3 or float((stats[:, 0].sum(0) - yf.sum((0, 1, 2))).abs().max()) < 0.5
     assert _rel(stats[:, 1].sum(0), (yf * yf).sum((0, 1, 2))) < 1e-3
-    dy = torch.randn_like(y)
+    dy = torch.randn_like(y).bfloat16()                                       # gradients are always bf16
+    if fwd != torch.bfloat16:                 # reference gradients at the bf16 copies the backward GEMMs consume
+        xr = x.bfloat16().float().permute(0, 3, 1, 2).requires_grad_(True)
+        wr = w.bfloat16().float().requires_grad_(True)
+        yr = F.conv2d(xr, wr, None, (sh, sw), ks // 2)
     yr.backward(dy.float().permute(0, 3, 1, 2))
-    dx = o.conv_dgrad(dy, wk, (NB, H, W, Cin), ks, sh, sw)
+    if fwd != torch.bfloat16:
+        with pytest.raises(Exception):                                        # mixed bf16 x fp16 MMAs are refused
+            o.conv_dgrad(dy, wk, (NB, H, W, Cin), ks, sh, sw)
+        with pytest.raises(Exception):
+            o.conv_wgrad_acc_t(dy, x, ks, sh, sw, torch.zeros(ks * ks, Cin, Cout, device="cuda"))
+    x_fwd, wk_fwd = x, wk
+    x, wk = x.bfloat16(), wk.bfloat16()                                       # the backward's bf16 copies
+    dx = o.conv_dgrad(dy, wk, (NB, H, W, Cin), ks, sh, sw)                    # MN-major B operand
     assert _rel(dx.permute(0, 3, 1, 2), xr.grad) < 1e-2
     # K-major B operand from the transposed pack [Cin, taps, Cout] (CTA-pair kernel where the tile grid allows)
-    packed = o.pack_weights([(w.float().contiguous(), "conv"), (w.float().contiguous(), "convT")])
-    assert torch.equal(packed[0], wk)
-    wt = w.permute(1, 2, 3, 0).reshape(Cin, ks * ks, Cout).contiguous()
+    packed = o.pack_weights([(w.float().contiguous(), "conv"), (w.float().contiguous(), "convT")], conv_dtype=fwd)
+    assert torch.equal(packed[0], wk_fwd) and packed[0].dtype == fwd
+    wt = w.float().permute(1, 2, 3, 0).reshape(Cin, ks * ks, Cout).contiguous().bfloat16()   # backward copy: bf16
+    if fwd != torch.bfloat16:
+        wt = wk.permute(2, 1, 0).contiguous()                                   # (bf16 of the fp16-rounded weights)
+        packed[1] = wt
     assert torch.equal(packed[1], wt)
     dx2 = o.conv_dgrad(dy, wk, (NB, H, W, Cin), ks, sh, sw, w_t=wt)
     assert _rel(dx2.permute(0, 3, 1, 2), xr.grad) < 1e-2

@@ -116,9 +116,118 @@ def test_train_step_matches_oracle(cfg):
         b = ref_grads[name].double().reshape(-1)
         cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
         ratio = float(a.norm() / (b.norm() + 1e-30))
-        if not (cos > 0.85 and 0.85 < ratio < 1.15):
+        # tiny batches (B = 2 / 3): batch statistics amplify bf16 noise in the stem, so the stem bound is looser here;
+        # test_train_batch32_vs_reference_golden holds the tight per-family bounds at a well-conditioned batch
+        lo_cos, tol = (0.99, 0.05) if _family(name) == "transformer" else (0.93, 0.10)
+        if not (cos > lo_cos and abs(ratio - 1.0) < tol):
             bad.append((name, round(cos, 4), round(ratio, 4)))
     assert not bad, bad
+
+
+def _family(name):
+    """Tensor classes of the gradient check: stem convolution / BatchNorm tensors vs transformer tensors."""
+    return "stem" if name.startswith("patch_embed.") else "transformer"
+
+
+def test_train_batch32_vs_reference_golden():
+    """train mode at a batch where BatchNorm batch statistics are well conditioned (B = 32,
+    full architecture) against the committed output of the UNMODIFIED reference (oracle/make_golden.py
+    train_batch_case, model_v1/train.py:21-30): logits within the north-star bf16 bound of 2e-2 with no calibration
+    escape hatch, loss within 1 %, and per-tensor-class gradient bounds on all 101 trainable tensors."""
+    import htrvt_b200 as h
+    g = np.load(os.path.join(G, "v1_train_b32.npz"))
+    nb_cls, W, B, seed, train_seed = [int(v) for v in g["meta"]]
+    m, sd = _build(nb_cls, W, 768, 4, 6, seed)
+    m.train()
+    x = _images(seed + 1, B, W)
+    tg, tl = _labels(seed + 2, B, nb_cls, 16, 64)
+    torch.manual_seed(train_seed)
+    preds = m(x.cuda(), 0.4, 8, use_masking=True)
+    lp = preds.float().permute(1, 0, 2).log_softmax(2)
+    crit = h.CTCLoss(reduction="none", zero_infinity=True).to("cuda")
+    nll = crit(lp, tg.cuda(), torch.IntTensor([preds.size(1)] * B).cuda(), tl.cuda())
+    loss = nll.mean()
+    loss.backward()
+    err = _relerr(preds.detach().float().cpu().numpy(), g["logits_train"])
+    assert err < 2e-2, err
+    assert abs(loss.item() - float(g["loss"])) < 1e-2 * abs(float(g["loss"]))
+    np.testing.assert_allclose(nll.detach().cpu().numpy(), g["nll"], rtol=3e-2)
+    offs = np.concatenate([[0], np.cumsum(g["grad_sample_counts"])])
+    where = {n: i for i, n in enumerate(g["grad_names"].tolist())}
+
+    def ref_of(name, a):
+        i = where[name]
+        return torch.from_numpy(g["grad_samples"][offs[i]:offs[i + 1]]).double(), float(g["grad_norms"][i])
+
+    named = []
+    for name, p in m.named_parameters():
+        if name == "pos_embed":
+            assert p.grad is None
+            continue
+        assert p.grad is not None, name
+        named.append((name, p.grad.detach().float().cpu()))
+    assert len(named) == 101
+
+    # sampled cosine (8192 reproducible elements per tensor) + exact norm ratio against the reference's full norm
+    bad = []
+    for name, a in named:
+        i = where[name]
+        idx = torch.from_numpy(O.grad_sample_index(name, a.numel()))
+        a_s = a.reshape(-1)[idx].double()
+        b_s, bnorm = ref_of(name, a)
+        cos = float((a_s @ b_s) / (a_s.norm() * b_s.norm() + 1e-30))
+        ratio = float(a.double().norm() / (bnorm + 1e-30))
+        lo_cos, tol = (0.995, 0.03) if _family(name) == "transformer" else (0.98, 0.05)
+        if not (cos >= lo_cos and abs(ratio - 1.0) <= tol):
+            bad.append((name, round(cos, 4), round(ratio, 4)))
+    assert not bad, bad
+    msd = m.state_dict()
+    got_bn = np.concatenate([msd[k].float().cpu().numpy().reshape(-1) for k in msd if "running_" in k])
+    assert _relerr(got_bn, g["bn_running"]) < 1e-2
+
+
+def test_stem_gradients_match_finite_differences_of_the_oracle():
+    """Finite differences of the ORACLE's float64 loss (float64 forward + the float64 CTC restatement: no autograd
+    anywhere) along OUR gradient's direction, for directions confined to (a) the fused stem head's tensors (conv1 /
+    bn1: stem_head_bwd), (b) every other BatchNorm's affine parameters (bn_bwd) and (c) the stem convolutions.
+    With d = g_ours / |g_ours| the derivative of the true loss along d is |g_true| cos(g_ours, g_true), so
+    FD / |g_ours| = cos x (norm ratio): a dropped or mis-scaled term in a backward kernel shows up here."""
+    import htrvt_b200 as h
+    cfg = dict(nb_cls=24, W=128, D=256, depth=1, heads=2, B=8, seed=15)
+    m, sd = _build(cfg["nb_cls"], cfg["W"], cfg["D"], cfg["depth"], cfg["heads"], cfg["seed"])
+    m.train()
+    B, W = cfg["B"], cfg["W"]
+    x = _images(cfg["seed"] + 1, B, W)
+    tg, tl = _labels(cfg["seed"] + 2, B, cfg["nb_cls"], 4, 12)
+    preds = m(x.cuda())                                        # no span mask: a deterministic function of the weights
+    loss = h.ctc_loss_from_logits(preds.float(), tg.cuda(), tl).mean()
+    loss.backward()
+    grads = {n: p.grad.detach().double().cpu() for n, p in m.named_parameters() if p.grad is not None}
+
+    def oracle_loss(sd64):
+        with torch.no_grad():
+            lg = O.forward({k: v.clone() for k, v in sd64.items()}, x.double(), training=True, num_heads=cfg["heads"])
+        nll, _ = O.ctc_loss_grad(lg.numpy(), tg.numpy(), np.full(B, lg.shape[1]), tl.numpy())
+        return float(np.mean(nll))
+
+    sd64 = {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+    assert abs(oracle_loss(sd64) - loss.item()) < 2e-2 * abs(loss.item())
+    groups = {
+        "stem_head": [k for k in grads if k in ("patch_embed.conv1.weight", "patch_embed.bn1.weight", "patch_embed.bn1.bias")],
+        "bn_affine": [k for k in grads if k.startswith("patch_embed.layer") and (".bn" in k or ".downsample.1." in k)],
+        "stem_convs": [k for k in grads if k.startswith("patch_embed.layer") and k.endswith(".weight") and ".conv" in k],
+    }
+    for gname, names in groups.items():
+        assert names, gname
+        gnorm = sum(float((grads[k] ** 2).sum()) for k in names) ** 0.5
+        wnorm = sum(float((sd64[k] ** 2).sum()) for k in names) ** 0.5
+        step = 1e-5 * wnorm                                   # a 1e-5 relative move of the group's weights
+        plus, minus = dict(sd64), dict(sd64)
+        for k in names:
+            plus[k] = sd64[k] + step * grads[k] / gnorm
+            minus[k] = sd64[k] - step * grads[k] / gnorm
+        fd = (oracle_loss(plus) - oracle_loss(minus)) / (2 * step)
+        assert 0.95 <= fd / gnorm <= 1.03, (gname, fd, gnorm)
 
 
 def test_end_to_end_decode_strings():
@@ -204,7 +313,10 @@ def test_window_train_step_matches_oracle(cfg):
         b = ref_grads[name].double().reshape(-1)
         cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
         ratio = float(a.norm() / (b.norm() + 1e-30))
-        if not (cos > 0.85 and 0.85 < ratio < 1.15):
+        # tiny batches (B = 2 / 3): batch statistics amplify bf16 noise in the stem, so the stem bound is looser here;
+        # test_train_batch32_vs_reference_golden holds the tight per-family bounds at a well-conditioned batch
+        lo_cos, tol = (0.99, 0.05) if _family(name) == "transformer" else (0.93, 0.10)
+        if not (cos > lo_cos and abs(ratio - 1.0) < tol):
             bad.append((name, round(cos, 4), round(ratio, 4)))
     assert not bad, bad
 

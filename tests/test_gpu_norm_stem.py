@@ -62,11 +62,12 @@ def test_row_ln_fwd_bwd():
     assert _rel(dg, 2 * g.grad) < 1e-4
 
 
-def test_tokens_gelu_colsum_cast():
+@pytest.mark.parametrize("fwd", [torch.float16, torch.bfloat16])
+def test_tokens_gelu_colsum_cast(fwd):
     o = ops()
     torch.manual_seed(2)
     B, T, D = 6, 32, 256
-    tok = torch.randn(B, T, D, device="cuda").bfloat16()
+    tok = torch.randn(B, T, D, device="cuda").to(fwd)
     mask = (torch.rand(T, device="cuda") > 0.4).float()
     mt = torch.randn(D, device="cuda")
     pos = torch.randn(T, D, device="cuda")
@@ -141,15 +142,16 @@ def test_stem_head_conv1_bn_pool():
     assert _rel(gw, wr.grad) < 1e-3
 
 
+@pytest.mark.parametrize("fwd", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("ds", [False, True])
-def test_bn_act_and_bn_bwd_block(ds):
+def test_bn_act_and_bn_bwd_block(ds, fwd):
     o = ops()
     torch.manual_seed(4)
     B, H, W, C = 2, 8, 64, 128
     P = B * H * W
-    r2 = torch.randn(B, H, W, C, device="cuda").bfloat16()
-    rd = torch.randn(B, H, W, C, device="cuda").bfloat16()
-    xin = torch.randn(B, H, W, C, device="cuda").bfloat16()
+    r2 = torch.randn(B, H, W, C, device="cuda").to(fwd)
+    rd = torch.randn(B, H, W, C, device="cuda").to(fwd)
+    xin = torch.randn(B, H, W, C, device="cuda").to(fwd)
     g2 = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
     b2 = (torch.randn(C, device="cuda") * 0.1).requires_grad_(True)
     gd = (torch.rand(C, device="cuda") + 0.5).requires_grad_(True)
@@ -170,12 +172,13 @@ def test_bn_act_and_bn_bwd_block(ds):
 
     if ds:
         ref = F.relu(bn(r2f, g2, b2) + bn(rdf, gd, bd))
-        y, km = o.bn_act_fwd(r2, s2, True, raw2=rd, st2=sdn, want_mask=True)
+        y, km, ybf = o.bn_act_fwd(r2, s2, True, raw2=rd, st2=sdn, want_mask=True, want_bf16=True)
     else:
         ref = F.relu(bn(r2f, g2, b2) + xf)
-        y, km = o.bn_act_fwd(r2, s2, True, res=xin, want_mask=True)
-    assert _rel(y, ref) < 1e-2
-    g = torch.randn_like(y)
+        y, km, ybf = o.bn_act_fwd(r2, s2, True, res=xin, want_mask=True, want_bf16=True)
+    assert _rel(y, ref) < 1e-2 and y.dtype == fwd
+    assert ybf.dtype == torch.bfloat16 and _rel(ybf, ref) < 1e-2 and (ybf is y) == (fwd == torch.bfloat16)
+    g = torch.randn_like(y).bfloat16()
     ref.backward(g.float())
     dg2, db2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     dgd, dbd = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
@@ -187,13 +190,15 @@ def test_bn_act_and_bn_bwd_block(ds):
         d2, dd, gz = o.bn_bwd(g, km, r2, s2, g2.detach(), dg2, db2, want_gz=True)
         assert _rel(gz, xf.grad) < 2e-2
     assert _rel(d2, r2f.grad) < 3e-2 and _rel(dg2, g2.grad) < 2e-2 and _rel(db2, b2.grad) < 2e-2
+    assert d2.dtype == torch.bfloat16
 
 
-def test_final_pool_fwd_bwd():
+@pytest.mark.parametrize("fwd", [torch.float16, torch.bfloat16])
+def test_final_pool_fwd_bwd(fwd):
     o = ops()
     torch.manual_seed(5)
     B, H, W, C = 4, 2, 32, 256
-    x = torch.relu(torch.randn(B, H, W, C, device="cuda")).bfloat16()
+    x = torch.relu(torch.randn(B, H, W, C, device="cuda")).to(fwd)
     xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     ref = F.max_pool2d(xf, 3, (2, 1), 1)
     out, idx = o.pool_fwd(x, None, True)
@@ -206,8 +211,9 @@ def test_final_pool_fwd_bwd():
     assert _rel(gin, want) < 2e-2
 
 
+@pytest.mark.parametrize("fwd", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W,C", [(3, 64, 128, 64), (2, 64, 512, 192), (2, 12, 72, 64)])
-def test_stem_head_fused(B, H, W, C):
+def test_stem_head_fused(B, H, W, C, fwd):
     """conv1 -> bn1(train) -> relu -> maxpool fused (conv output never materialised) vs the fp32 torch graph
     (model_v1/model/resnet18.py:74-77): pooled activation, batch statistics, and dW / dgamma / dbeta."""
     o = ops()
@@ -234,10 +240,13 @@ def test_stem_head_fused(B, H, W, C):
     nbt = torch.zeros((), dtype=torch.int64, device="cuda")
     st = o.bn_finalize(stats, cnt, gamma.detach(), beta.detach(), rm2, rv2, nbt, True)
     assert _rel(rm2, rm) < 1e-4 and _rel(rv2, rv) < 1e-4
-    out, code = o.stem_head_fwd(x3, w.detach(), st, True)
-    assert out.shape == (B, ref.shape[2], W, C)
-    assert _rel(out.permute(0, 3, 1, 2), ref.detach()) < 1e-2          # bf16 storage of an fp32 computation
-    out2, none = o.stem_head_fwd(x3, w.detach(), st, False)
+    out, code = o.stem_head_fwd(x3, w.detach(), st, True, out_dtype=fwd)
+    assert out.shape == (B, ref.shape[2], W, C) and out.dtype == fwd
+    assert _rel(out.permute(0, 3, 1, 2), ref.detach()) < (1e-2 if fwd == torch.bfloat16 else 2e-3)   # 16-bit storage of an fp32 computation
+    out3, code3, out_bf = o.stem_head_fwd(x3, w.detach(), st, True, out_dtype=fwd, want_bf16=True)
+    assert torch.equal(out3, out) and torch.equal(code3, code) and out_bf.dtype == torch.bfloat16
+    assert _rel(out_bf.permute(0, 3, 1, 2), ref.detach()) < 1e-2
+    out2, none = o.stem_head_fwd(x3, w.detach(), st, False, out_dtype=fwd)
     assert none is None and torch.equal(out, out2)
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     dw = torch.zeros(C, 1, 3, 3, device="cuda")

@@ -55,6 +55,53 @@ def test_train_step_matches_reference(tag):
     assert int(sd["patch_embed.bn1.num_batches_tracked"]) == int(g["nbt"]) == 1
 
 
+@pytest.mark.parametrize("tag", ["win_w1000", "win_w600"])
+def test_window_pad_and_key_mask_path_matches_reference(tag):
+    """Token counts that are not a multiple of the 16-token window (T = 250 / 150): zero padding + rolled key
+    padding mask (model_window/model/HTR_VT.py:121-131,49-56)."""
+    g = np.load(os.path.join(G, tag + ".npz"))
+    nb_cls, W, B, seed = [int(v) for v in g["meta"]]
+    sd = O.init_state_dict(nb_cls, [64, W], seed=seed, variant="window")
+    with torch.no_grad():
+        y = O.forward(sd, _images(seed + 1, B, W), training=False, variant="window")
+    assert y.shape[1] % 16 != 0
+    np.testing.assert_allclose(y.numpy(), g["logits_eval"], rtol=0, atol=3e-4)
+
+
+def test_train_batch32_matches_reference():
+    """Full architecture, B = 32 (well-conditioned batch statistics): logits, loss, per-sample nll, sampled gradients of
+    all 101 trainable tensors and the decoded strings of valid.py:40-42."""
+    g = np.load(os.path.join(G, "v1_train_b32.npz"))
+    nb_cls, W, B, seed, train_seed = [int(v) for v in g["meta"]]
+    sd = O.init_state_dict(nb_cls, [64, W], seed=seed)
+    x = _images(seed + 1, B, W)
+    with torch.no_grad():
+        ye = O.forward(sd, x, training=False).numpy()
+    np.testing.assert_allclose(ye, g["logits_eval"], rtol=0, atol=3e-4)
+    alphabet = "".join(chr(33 + i) for i in range(nb_cls - 1))
+    idx = O.argmax_first(g["logits_eval"]).reshape(-1)
+    np.testing.assert_array_equal(idx, g["index_eval"].astype(np.int64))
+    assert O.decode_strings(idx, [W // 4] * B, alphabet) == g["strings_eval"].tolist()
+    torch.manual_seed(train_seed)
+    mask = O.draw_span_mask(W // 4, 0.4, 8)
+    np.testing.assert_array_equal(mask.numpy(), g["mask"])
+    tg, tl = _labels(seed + 2, B, nb_cls, 16, 64)
+    loss, grads, logits = O.train_step(sd, x, tg, tl, mask)
+    np.testing.assert_allclose(logits.numpy(), g["logits_train"], rtol=0, atol=3e-4)
+    assert abs(loss - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    off = 0
+    for name, cnt, norm in zip(g["grad_names"].tolist(), g["grad_sample_counts"].tolist(), g["grad_norms"].tolist()):
+        want = g["grad_samples"][off:off + cnt]
+        off += cnt
+        got = grads[name].reshape(-1)[torch.from_numpy(O.grad_sample_index(name, grads[name].numel()))].numpy()
+        cos = float(got.astype(np.float64) @ want.astype(np.float64) /
+                    (np.linalg.norm(got.astype(np.float64)) * np.linalg.norm(want.astype(np.float64)) + 1e-30))
+        assert cos > 0.9999, (name, cos)
+        assert abs(float(grads[name].double().norm()) - norm) <= 5e-3 * norm + 1e-7, name
+    got_bn = np.concatenate([sd[k].numpy().reshape(-1) for k in sd if "running_" in k])
+    np.testing.assert_allclose(got_bn, g["bn_running"], rtol=1e-4, atol=1e-6)
+
+
 def test_ctc_f64_restatement_matches_torch_ctcloss():
     g = np.load(os.path.join(G, "ctc_cases.npz"))
     for name in g["names"].tolist():
