@@ -4,7 +4,10 @@
 //   * global   (window == 0): every query attends to all T keys (two 128-key blocks);
 //   * windowed (window == 16): the sequence is rolled by -shift, cut into 16-token windows, attention runs inside
 //     each window (bias indexed by the intra-window offset, the wrap-around window mixes head and tail tokens),
-//     results roll back.  One CTA handles 128 consecutive ROLLED positions = 8 windows as ONE 128 x 128 tcgen05
+//     results roll back.  T need not be a multiple of 16: the reference zero-pads to Tp = ceil16(T), rolls tokens AND
+//     the validity mask, masks the padded keys and strips the padded queries (:121-131, :49-56) - here padded tokens
+//     are TMA out-of-bounds zeros, padded keys get -inf scores, padded query rows are never stored.
+//     One CTA handles 128 consecutive ROLLED positions = 8 windows as ONE 128 x 128 tcgen05
 //     score tile with a block-diagonal mask: the tensor core wastes 7/8 of a tile that is 0.03 % of the step, and
 //     the kernel stays a single TMA -> tcgen05 -> TMEM pipeline instead of thousands of 16 x 16 problems.
 // Attention dropout (attn_drop = 0.05 in train mode) is a counter-based hash of (seed, b, h, query token,
@@ -26,6 +29,7 @@ constexpr int kChunk128 = 128 * 128;       // bytes of a [128 rows][64 bf16] swi
 
 struct Attn2P {
   int B, H, T;
+  int Tp;                      // windowed: T padded to a multiple of the window (16); else T
   int nblk;                    // ceil(T / 128)
   int window, shift;           // window 0 (global) or 16
   int Prel;                    // relative-position table has 2 * Prel - 1 rows
@@ -64,20 +68,28 @@ __device__ __forceinline__ uint64_t d_mnmajor(uint32_t img, int chunk_bytes, int
   return umma_desc_sw128(img + k16 * 2048, chunk_bytes, 1024);
 }
 
-// Load `rows` (128 or 256) token rows x 128 head columns starting at rolled position pos0 into a two-chunk image.
-// window mode with a shift: tokens (pos + shift) mod T; the box pair (128 - shift rows, shift rows) covers the wrap.
-__device__ __forceinline__ void load_rows(uint8_t* dst, int chunk_bytes, const CUtensorMap* mapMain,
-                                          const CUtensorMap* mapTail, uint64_t* bar, int col0, int pos0, int b, int T,
-                                          int shift) {
-  const int t0 = pos0 + shift;                       // first token (may exceed T only through the tail box)
+// Load 128 (or 256: global keys) token rows x 128 head columns starting at rolled position pos0 into a two-chunk image.
+// Windowed with a shift: row r holds token (pos0 + r + shift) mod Tp.  Only the LAST 128-position block contains the
+// wrap (shift < 16 <= window): its rows [0, nmain) are tokens [pos0 + shift, Tp) and rows [nmain, nmain + shift) are
+// tokens [0, shift), nmain = Tp - shift - pos0.  The full box goes first (tokens >= T are out of bounds = zeros, which
+// also clears every row the block does not own), the wrap rows land on top of it in a second, ordered phase.
+// Returns the number of barrier phases used (1 or 2); the caller waits for them in order.
+__device__ __forceinline__ int load_rows(uint8_t* dst, int chunk_bytes, const CUtensorMap* mapMain,
+                                         const CUtensorMap* mapTail, uint64_t* bar, uint32_t& phase, int col0, int pos0,
+                                         int b, int Tp, int shift, int box_bytes) {
+  const int t0 = pos0 + shift;
+  mbar_arrive_expect_tx(bar, 2 * box_bytes);
   tma_load_3d(dst, mapMain, bar, col0, t0, b);
   tma_load_3d(dst + chunk_bytes, mapMain, bar, col0 + 64, t0, b);
-  if (shift > 0) {
-    int t1 = t0 + 128 - shift;
-    if (t1 >= T) t1 -= T;
-    tma_load_3d(dst + (128 - shift) * 128, mapTail, bar, col0, t1, b);
-    tma_load_3d(dst + chunk_bytes + (128 - shift) * 128, mapTail, bar, col0 + 64, t1, b);
+  if (shift > 0 && t0 + 128 > Tp) {                   // this block holds the wrap-around rows
+    const int nmain = Tp - t0;
+    mbar_wait(bar, phase);                            // the zero-filled rows must be down before the wrap rows land
+    phase ^= 1;
+    mbar_arrive_expect_tx(bar, 2 * shift * 128);
+    tma_load_3d(dst + nmain * 128, mapTail, bar, col0, 0, b);
+    tma_load_3d(dst + chunk_bytes + nmain * 128, mapTail, bar, col0 + 64, 0, b);
   }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -95,8 +107,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint8_t* sV = sK + 2 * kKVChunk;                   // NKB * 32 KB
   float* sBias = reinterpret_cast<float*>(sV + 2 * kKVChunk);        // [512] (2*Prel-1 <= 511), log2 domain
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 512);
-  uint64_t* bar_load = bars, *bar_s = bars + 1, *bar_p = bars + 2, *bar_o = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* bar_load = bars, *bar_s = bars + 1, *bar_p = bars + 2, *bar_o = bars + 3, *bar_lk = bars + 4, *bar_lv = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = blockIdx.x % P.nblk;
@@ -106,6 +118,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmKV);
     mbar_init(bar_load, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_o, 1);
+    mbar_init(bar_lk, 1); mbar_init(bar_lv, 1);
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(tmem_slot, 512);
@@ -121,17 +134,20 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_load, 2 * kChunk128 + 4 * kKVChunk);
+      // three independent load barriers (Q, K, V): each may need a second, ordered phase for the wrap-around rows
+      uint32_t phq = 0, phk = 0, phv = 0;
       if (windowed) {                                 // keys/values = the same 128 rolled positions as the queries
-        load_rows(sQ, kChunk128, &tmQ, &tmQtail, bar_load, h * kA2Hd, qb * 128, b, P.T, P.shift);
-        load_rows(sK, kKVChunk, &tmQ, &tmQtail, bar_load, D + h * kA2Hd, qb * 128, b, P.T, P.shift);
-        load_rows(sV, kKVChunk, &tmQ, &tmQtail, bar_load, 2 * D + h * kA2Hd, qb * 128, b, P.T, P.shift);
+        load_rows(sQ, kChunk128, &tmQ, &tmQtail, bar_load, phq, h * kA2Hd, qb * 128, b, P.Tp, P.shift, kChunk128);
+        load_rows(sK, kKVChunk, &tmQ, &tmQtail, bar_lk, phk, D + h * kA2Hd, qb * 128, b, P.Tp, P.shift, kChunk128);
+        load_rows(sV, kKVChunk, &tmQ, &tmQtail, bar_lv, phv, 2 * D + h * kA2Hd, qb * 128, b, P.Tp, P.shift, kChunk128);
       } else {
-        load_rows(sQ, kChunk128, &tmQ, &tmQtail, bar_load, h * kA2Hd, qb * 128, b, P.T, 0);
-        load_rows(sK, kKVChunk, &tmKV, &tmKV, bar_load, D + h * kA2Hd, 0, b, P.T, 0);
-        load_rows(sV, kKVChunk, &tmKV, &tmKV, bar_load, 2 * D + h * kA2Hd, 0, b, P.T, 0);
+        load_rows(sQ, kChunk128, &tmQ, &tmQtail, bar_load, phq, h * kA2Hd, qb * 128, b, P.Tp, 0, kChunk128);
+        load_rows(sK, kKVChunk, &tmKV, &tmKV, bar_lk, phk, D + h * kA2Hd, 0, b, P.Tp, 0, kKVChunk);
+        load_rows(sV, kKVChunk, &tmKV, &tmKV, bar_lv, phv, 2 * D + h * kA2Hd, 0, b, P.Tp, 0, kKVChunk);
       }
-      mbar_wait(bar_load, 0);
+      mbar_wait(bar_load, phq);
+      mbar_wait(bar_lk, phk);
+      mbar_wait(bar_lv, phv);
       tc_fence_after();
       const uint32_t q = smem_u32(sQ), k = smem_u32(sK);
 #pragma unroll
@@ -150,8 +166,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int r = warp * 32 + lane;
     const int pi = qb * 128 + r;                                   // rolled position of this query
     int ti = pi + (windowed ? P.shift : 0);
-    if (ti >= P.T) ti -= P.T;
-    const bool rok = pi < P.T;
+    if (ti >= P.Tp) ti -= P.Tp;
+    const bool rok = pi < P.Tp && ti < P.T;                        // a real (not padded) query token
     const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const float sl2 = P.scale * kLog2e;
     const float inv_keep = P.drop_p > 0.f ? 1.0f / (1.0f - P.drop_p) : 1.0f;
@@ -171,18 +187,23 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       float e[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const bool ok = qb * 128 + wb + j < P.T;
+        const int pj = qb * 128 + wb + j;
+        int tj = pj + P.shift;
+        if (tj >= P.Tp) tj -= P.Tp;
+        const bool ok = pj < P.Tp && tj < P.T;                     // key padding mask (True = valid), rolled like the tokens
         const float sv = __uint_as_float(upper ? rawb[j] : rawa[j]);
         e[j] = ok ? fmaf(sv, sl2, sBias[j - ri + P.Prel - 1]) : -INFINITY;
         m = fmaxf(m, e[j]);
       }
+      if (!rok) m = 0.f;                                           // padded query row: all-zero probabilities, no NaN
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { e[j] = ex2f(e[j] - m); sum += e[j]; }
+      for (int j = 0; j < 16; ++j) { e[j] = rok ? ex2f(e[j] - m) : 0.f; sum += e[j]; }
+      if (!rok) sum = 1.f;
       if (P.drop_p > 0.f) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           int tj = qb * 128 + wb + j + P.shift;
-          if (tj >= P.T) tj -= P.T;
+          if (tj >= P.Tp) tj -= P.Tp;
           e[j] *= attn_keep(P.seed, bh, ti, tj, P.drop_p, inv_keep);
         }
       }
@@ -286,7 +307,8 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   float* sDB = sBias + 512;                                           // [512] bias-gradient bins
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDB + 512);
   uint64_t* bar_kv = bars, *bar_q = bars + 1, *bar_s = bars + 2, *bar_p = bars + 3, *bar_g = bars + 4, *bar_free = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_v = bars + 6, *bar_do = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb = blockIdx.x % P.nblk;
@@ -298,7 +320,7 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmDO);
     mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_s, 1); mbar_init(bar_p, 128); mbar_init(bar_g, 1);
-    mbar_init(bar_free, 128);
+    mbar_init(bar_free, 128); mbar_init(bar_v, 1); mbar_init(bar_do, 1);
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc(tmem_slot, 512);
@@ -317,20 +339,20 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(bar_kv, 4 * kChunk128);
-      load_rows(sK, kChunk128, &tmQ, &tmQtail, bar_kv, D + h * kA2Hd, kb * 128, b, P.T, shift);
-      load_rows(sV, kChunk128, &tmQ, &tmQtail, bar_kv, 2 * D + h * kA2Hd, kb * 128, b, P.T, shift);
+      uint32_t phk = 0, phv = 0, phq = 0, phdo = 0;    // running phases of the four load barriers
+      load_rows(sK, kChunk128, &tmQ, &tmQtail, bar_kv, phk, D + h * kA2Hd, kb * 128, b, P.Tp, shift, kChunk128);
+      load_rows(sV, kChunk128, &tmQ, &tmQtail, bar_v, phv, 2 * D + h * kA2Hd, kb * 128, b, P.Tp, shift, kChunk128);
       const uint32_t q = smem_u32(sQ), k = smem_u32(sK), v = smem_u32(sV), d_o = smem_u32(sDO);
       const uint32_t pp = smem_u32(sP), ds = smem_u32(sDS);
       for (int it = 0; it < q_count; ++it) {
         const int qb = q_first + it;
         const uint32_t ph = it & 1;
         if (it > 0) mbar_wait(bar_free, ph ^ 1);                  // previous dQ read out, Q / dO / P / dS images free
-        mbar_arrive_expect_tx(bar_q, 4 * kChunk128);
-        load_rows(sQ, kChunk128, &tmQ, &tmQtail, bar_q, h * kA2Hd, qb * 128, b, P.T, shift);
-        load_rows(sDO, kChunk128, &tmDO, &tmDOtail, bar_q, h * kA2Hd, qb * 128, b, P.T, shift);
-        if (it == 0) mbar_wait(bar_kv, 0);
-        mbar_wait(bar_q, ph);
+        load_rows(sQ, kChunk128, &tmQ, &tmQtail, bar_q, phq, h * kA2Hd, qb * 128, b, P.Tp, shift, kChunk128);
+        load_rows(sDO, kChunk128, &tmDO, &tmDOtail, bar_do, phdo, h * kA2Hd, qb * 128, b, P.Tp, shift, kChunk128);
+        if (it == 0) { mbar_wait(bar_kv, phk); mbar_wait(bar_v, phv); }
+        mbar_wait(bar_q, phq); phq ^= 1;
+        mbar_wait(bar_do, phdo); phdo ^= 1;
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -364,8 +386,8 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t ph = it & 1;
       const int pi = qb * 128 + r;
       int ti = pi + shift;
-      if (ti >= P.T) ti -= P.T;
-      const bool rok = pi < P.T;
+      if (ti >= P.Tp) ti -= P.Tp;
+      const bool rok = pi < P.Tp && ti < P.T;
       float delta = 0.f;
       if (rok) {
         const uint4* po = reinterpret_cast<const uint4*>(P.o + (static_cast<long long>(b) * P.T + ti) * D + h * kA2Hd);
@@ -398,14 +420,14 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int pj = kb * 128 + c + j;
-            const bool ok = rok && mine && pj < P.T;
+            int tkey = pj + shift;
+            if (tkey >= P.Tp) tkey -= P.Tp;
+            const bool ok = rok && mine && pj < P.Tp && tkey < P.T;
             const int bidx = max(pj - pi + P.Prel - 1, 0);
             const float pr = ok ? ex2f(fmaf(__uint_as_float(rs[j]), sl2, sBias[bidx]) - lse2) : 0.f;
             float keep = 1.f;
             if (P.drop_p > 0.f && ok) {
-              int tj = pj + shift;
-              if (tj >= P.T) tj -= P.T;
-              keep = attn_keep(P.seed, bh, ti, tj, P.drop_p, inv_keep);
+              keep = attn_keep(P.seed, bh, ti, tkey, P.drop_p, inv_keep);
             }
             const float dsr = pr * (__uint_as_float(rp[j]) * keep - delta);    // d(score incl. bias)
             p[j] = pr * keep;
@@ -463,8 +485,8 @@ attn2_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     {
       const int pj = kb * 128 + r;
       int tj = pj + shift;
-      if (tj >= P.T) tj -= P.T;
-      const bool kok = pj < P.T;
+      if (tj >= P.Tp) tj -= P.Tp;
+      const bool kok = pj < P.Tp && tj < P.T;
       __nv_bfloat16* base = P.dqkv + (static_cast<long long>(b) * P.T + tj) * (3 * D) + h * kA2Hd;
       const uint32_t cols[2] = {256u, 384u};           // dK, dV
 #pragma unroll 1
@@ -568,7 +590,7 @@ int a2_check(int B, int H, int T, int hd, int window, int shift, int Prel, const
   if (hd != kA2Hd || T < 1 || T > 256 || B < 1 || H < 1) return HTRVT_ERR_SHAPE;
   if (window != 0 && window != 16) return HTRVT_ERR_SHAPE;
   if (window == 0 && shift != 0) return HTRVT_ERR_SHAPE;
-  if (window && ((T % 16) || shift < 0 || shift >= 128 || (shift % 8) || (shift > 0 && (T % 128)))) return HTRVT_ERR_SHAPE;
+  if (window && (shift < 0 || shift >= window || (shift % 8))) return HTRVT_ERR_SHAPE;   // any T <= 256: padded + masked
   if (table && (Prel < T || 2 * Prel - 1 > 511)) return HTRVT_ERR_SHAPE;
   if (!table && Prel != 0 && Prel < T) return HTRVT_ERR_SHAPE;
   return HTRVT_OK;
@@ -588,14 +610,14 @@ extern "C" int htrvt_attention2_fwd(const void* qkv, int B, int H, int T, int hd
   const int nblk = (T + 127) / 128;
   const int nkb = window ? 1 : nblk;
   CUtensorMap tq, tqt, tkv;
-  r = a2_map3(&tq, qkv, ld, T, B, ld, static_cast<long long>(T) * ld, 128 - shift);
+  r = a2_map3(&tq, qkv, ld, T, B, ld, static_cast<long long>(T) * ld, 128);
   if (r) return r;
   r = a2_map3(&tqt, qkv, ld, T, B, ld, static_cast<long long>(T) * ld, shift > 0 ? shift : 8);
   if (r) return r;
   r = a2_map3(&tkv, qkv, ld, T, B, ld, static_cast<long long>(T) * ld, nkb * 128);
   if (r) return r;
   Attn2P P = {};
-  P.B = B; P.H = H; P.T = T; P.nblk = nblk; P.window = window; P.shift = shift; P.Prel = Prel; P.scale = scale;
+  P.B = B; P.H = H; P.T = T; P.Tp = window ? (T + window - 1) / window * window : T; P.nblk = nblk; P.window = window; P.shift = shift; P.Prel = Prel; P.scale = scale;
   P.table = table; P.out = static_cast<__nv_bfloat16*>(out); P.lse = lse; P.drop_p = drop_p; P.seed = seed;
   const int smem = 2 * kChunk128 + 4 * nkb * kChunk128 + 2048 + 128 + 1024;
   auto kern = nkb == 1 ? attn2_fwd_kernel<1> : attn2_fwd_kernel<2>;
@@ -625,16 +647,17 @@ extern "C" int htrvt_attention2_bwd(const void* qkv, const void* out, const void
   const size_t need = htrvt_attention2_bwd_workspace_bytes(B, H, T, window);
   if (need && (!workspace || workspace_bytes < need)) return HTRVT_ERR_WORKSPACE;
   CUtensorMap tq, tqt, tdo, tdot;
-  r = a2_map3(&tq, qkv, ld, T, B, ld, static_cast<long long>(T) * ld, 128 - shift);
+  r = a2_map3(&tq, qkv, ld, T, B, ld, static_cast<long long>(T) * ld, 128);
   if (r) return r;
   r = a2_map3(&tqt, qkv, ld, T, B, ld, static_cast<long long>(T) * ld, shift > 0 ? shift : 8);
   if (r) return r;
-  r = a2_map3(&tdo, dout, ldo, T, B, ldo, static_cast<long long>(T) * ldo, 128 - shift);
+  r = a2_map3(&tdo, dout, ldo, T, B, ldo, static_cast<long long>(T) * ldo, 128);
   if (r) return r;
   r = a2_map3(&tdot, dout, ldo, T, B, ldo, static_cast<long long>(T) * ldo, shift > 0 ? shift : 8);
   if (r) return r;
   Attn2P P = {};
-  P.B = B; P.H = H; P.T = T; P.nblk = nblk; P.window = window; P.shift = shift; P.Prel = Prel; P.scale = scale;
+  P.B = B; P.H = H; P.T = T; P.Tp = window ? (T + window - 1) / window * window : T; P.nblk = nblk;
+  P.window = window; P.shift = shift; P.Prel = Prel; P.scale = scale;
   P.table = table; P.dtable = dtable; P.lse = const_cast<float*>(lse);
   P.o = static_cast<const __nv_bfloat16*>(out); P.dout = static_cast<const __nv_bfloat16*>(dout);
   P.dqkv = static_cast<__nv_bfloat16*>(dqkv); P.dq_part = static_cast<__nv_bfloat16*>(workspace);

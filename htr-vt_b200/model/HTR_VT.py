@@ -229,9 +229,12 @@ class MaskedAutoencoderViT(nn.Module):
         /255, pad-to-W with 1.0 for columns >= widths[b] (optional) and the input LayerNorm."""
         if not x.is_cuda:
             raise ops.HtrvtError("htr-vt_b200 MaskedAutoencoderViT.forward needs CUDA tensors (no CPU fallback)")
+        if x.shape[-1] % 4:
+            raise ValueError("line image width must be a multiple of 4 (the stem halves the width twice; got %d)"
+                             % x.shape[-1])
         mask = None
         if use_masking:
-            L = x.shape[-1] // 4
+            L = x.shape[-1] // 4                 # tokens = stem output columns (exact: the width is a multiple of 4)
             mask = self.span_mask(L, mask_ratio, max_span_length).to(x.device, non_blocking=True)
         names, params = zip(*[(name, mod._parameters[key]) for name, mod, key, is_p in self._slots() if is_p])
         save = torch.is_grad_enabled() and any(p.requires_grad for p in params)

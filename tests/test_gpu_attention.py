@@ -45,26 +45,39 @@ def test_attention_fwd_bwd(B, H, T):
 
 def _ref_attention2(qkv_tm, table, prel, window, shift, scale):
     """fp32 torch restatement of model_window Attention.forward + Block._attend (model_window/model/HTR_VT.py:33-62,
-    114-154) on given q, k, v (token-major [B,T,3,H,hd]); no padding case (T multiple of the window)."""
+    114-154) on given q, k, v (token-major [B,T,3,H,hd]), INCLUDING the branch for T not a multiple of the window:
+    pad to Tp with tokens whose keys are masked (key_padding_mask rolled with the tokens, finfo.min fill, :49-56,
+    :121-131) and whose query rows are stripped."""
     B, T, _, H, hd = qkv_tm.shape
     qkv = qkv_tm.float()
-    if window > 0 and shift > 0:
-        qkv = torch.roll(qkv, shifts=(-shift,), dims=1)
+    Tp = T
+    valid = torch.ones(B, T, dtype=torch.bool, device=qkv.device)
+    if window > 0:
+        pad = (window - T % window) % window
+        Tp = T + pad
+        if pad:
+            qkv = torch.cat([qkv, qkv.new_zeros(B, pad, 3, H, hd)], dim=1)
+            valid = torch.cat([valid, valid.new_zeros(B, pad)], dim=1)
+        if shift > 0:
+            qkv = torch.roll(qkv, shifts=(-shift,), dims=1)
+            valid = torch.roll(valid, shifts=(-shift,), dims=1)
     N = window if window > 0 else T
-    z = qkv.reshape(B * (T // N), N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    z = qkv.reshape(B * (Tp // N), N, 3, H, hd).permute(2, 0, 3, 1, 4)
     q, k, v = z[0], z[1], z[2]
     attn = (q @ k.transpose(-2, -1)) * scale
     if table is not None:
         coords = torch.arange(prel, device=qkv.device)
         idx = (coords[None, :] - coords[:, None]) + prel - 1
         attn = attn + table[idx[:N, :N]].permute(2, 0, 1).unsqueeze(0)
+    if window > 0:
+        attn = attn.masked_fill(~valid.reshape(B * (Tp // N), 1, 1, N), torch.finfo(attn.dtype).min)
     lse = torch.logsumexp(attn, -1)                                    # [Bw, H, N]
-    out = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B, T, H * hd)
-    lse = lse.reshape(B, T // N, H, N).permute(0, 2, 1, 3).reshape(B, H, T)
+    out = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B, Tp, H * hd)
+    lse = lse.reshape(B, Tp // N, H, N).permute(0, 2, 1, 3).reshape(B, H, Tp)
     if window > 0 and shift > 0:
         out = torch.roll(out, shifts=(shift,), dims=1)
         lse = torch.roll(lse, shifts=(shift,), dims=2)
-    return out, lse
+    return out[:, :T], lse[:, :, :T]
 
 
 @pytest.mark.parametrize("B,H,T,prel,window,shift,bias", [
@@ -76,6 +89,17 @@ def _ref_attention2(qkv_tm, table, prel, window, shift, scale):
     (2, 2, 208, 256, 0, 0, True),      # ragged: T not a multiple of 128
     (2, 2, 48, 64, 16, 0, True),
     (2, 2, 256, 0, 0, 0, False),       # no bias table
+    # token counts that are not a multiple of the 16-token window (W = 1000 / 600 / 808 / 360 lines): zero padding,
+    # rolled key-padding mask, padded queries stripped (model_window/model/HTR_VT.py:121-131, 49-56)
+    (2, 6, 250, 250, 16, 0, True),
+    (2, 6, 250, 250, 16, 8, True),
+    (2, 2, 150, 150, 16, 8, True),
+    (2, 2, 202, 256, 16, 8, True),
+    (3, 2, 90, 128, 16, 8, True),
+    (2, 2, 90, 128, 16, 0, True),
+    (2, 2, 200, 200, 16, 8, True),     # Tp = 208: multiple of 16 but not of 128
+    (1, 2, 7, 16, 16, 8, True),        # shorter than one window
+    (2, 2, 250, 250, 0, 0, True),      # global attention at the same ragged length
 ])
 def test_attention2_fwd_bwd(B, H, T, prel, window, shift, bias):
     o = ops()

@@ -90,14 +90,10 @@ def test_train_step_matches_oracle(cfg):
         g = np.load(os.path.join(G, "v1_full.npz"))
         np.testing.assert_allclose(ref_logits.numpy(), g["logits_train"], atol=3e-4)
         assert abs(ref_loss - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
-    # train mode normalises with batch statistics of a tiny batch; calibrate the bf16 tolerance on the box:
-    # the same oracle graph under torch.autocast(bf16) (library bf16 kernels) vs the fp32 reference
-    sd_gpu = {k: v.clone().cuda() for k, v in sd.items()}
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-        ac = O.forward(sd_gpu, x.cuda(), mask=mask.cuda(), training=True, num_heads=cfg["heads"]).float().cpu()
-    lib_err = _relerr(ac.numpy(), ref_logits.numpy())
+    # north_star bound for 16-bit operands, no calibration against a library path (the forward stem is fp16: a
+    # bf16-only stem sits at 3-4e-2 here)
     err = _relerr(preds.detach().cpu().numpy(), ref_logits.numpy())
-    assert err < max(2e-2, 1.25 * lib_err) and err < 6e-2, (err, lib_err)
+    assert err < 2e-2, err
     assert abs(loss.item() - ref_loss) < 2e-2 * abs(ref_loss)
     # BN running statistics and counters updated in place, as nn.BatchNorm2d does
     msd = m.state_dict()
@@ -279,6 +275,47 @@ def test_window_eval_logits_match_reference_golden():
     assert _relerr(got, g["logits_eval"]) < 2e-2, _relerr(got, g["logits_eval"])
 
 
+@pytest.mark.parametrize("tag", ["win_w1000", "win_w600"])
+def test_window_ragged_widths_match_reference_golden(tag):
+    """Line widths whose token count is not a multiple of the 16-token window (T = 250 / 150): the reference pads, rolls
+    the key-padding mask and strips the pad (model_window/model/HTR_VT.py:121-131, 49-56); goldens from the unmodified
+    reference (oracle/make_golden.py window_ragged_case).  Eval logits + a train step's gradients vs the oracle."""
+    import htrvt_b200 as h
+    g = np.load(os.path.join(G, tag + ".npz"))
+    nb_cls, W, B, seed = [int(v) for v in g["meta"]]
+    Wm = import_module("htr-vt_b200.model_window.HTR_VT")
+    m = Wm.create_model(nb_cls, [W, 64])                 # the reference's convention for this variant: img_size = [W, H]
+    sd = O.init_state_dict(nb_cls, [64, W], seed=seed, variant="window")
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    assert [str(k) for k in g["keys"]] == list(m.state_dict().keys())
+    m.eval()
+    x = _images(seed + 1, B, W)
+    with torch.no_grad():
+        got = m(x.cuda()).float().cpu().numpy()
+    assert got.shape == g["logits_eval"].shape == (B, W // 4, nb_cls) and (W // 4) % 16 != 0
+    assert _relerr(got, g["logits_eval"]) < 2e-2, _relerr(got, g["logits_eval"])
+    # backward through the padded / masked windows
+    m.train().set_stochastic(0.0, 0.0, 0.0)
+    tg, tl = _labels(seed + 2, B, nb_cls, 4, 40)
+    torch.manual_seed(7)
+    preds = m(x.cuda(), 0.4, 8, use_masking=True)
+    h.ctc_loss_from_logits(preds.float(), tg.cuda(), tl).mean().backward()
+    torch.manual_seed(7)
+    mask = O.draw_span_mask(W // 4, 0.4, 8)
+    ref_loss, ref_grads, ref_logits = O.train_step({k: v.clone() for k, v in sd.items()}, x, tg, tl, mask,
+                                                   variant="window", num_heads=6)
+    assert _relerr(preds.detach().float().cpu().numpy(), ref_logits.numpy()) < 2e-2
+    bad = []
+    for name, p in m.named_parameters():
+        a = p.grad.detach().float().cpu().double().reshape(-1)
+        b = ref_grads[name].double().reshape(-1)
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+        if not cos > (0.99 if _family(name) == "transformer" else 0.93):
+            bad.append((name, round(cos, 4)))
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("cfg", [dict(nb_cls=20, W=512, D=256, depth=4, heads=2, B=3, seed=9),
                                  dict(nb_cls=90, W=1024, D=768, depth=4, heads=6, B=2, seed=321)])
 def test_window_train_step_matches_oracle(cfg):
@@ -298,13 +335,8 @@ def test_window_train_step_matches_oracle(cfg):
     mask = O.draw_span_mask(W // 4, 0.4, 8)
     sd_ref = {k: v.clone() for k, v in sd.items()}
     ref_loss, ref_grads, ref_logits = O.train_step(sd_ref, x, tg, tl, mask, variant="window", num_heads=cfg["heads"])
-    sd_gpu = {k: v.clone().cuda() for k, v in sd.items()}
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-        ac = O.forward(sd_gpu, x.cuda(), mask=mask.cuda(), training=True, num_heads=cfg["heads"],
-                       variant="window").float().cpu()
-    lib_err = _relerr(ac.numpy(), ref_logits.numpy())
     err = _relerr(preds.detach().cpu().numpy(), ref_logits.numpy())
-    assert err < max(2e-2, 1.25 * lib_err) and err < 6e-2, (err, lib_err)
+    assert err < 2e-2, err
     assert abs(loss.item() - ref_loss) < 2e-2 * abs(ref_loss)
     bad = []
     for name, p in m.named_parameters():
