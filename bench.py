@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the HTR-VT hot path on B200 (driver contract: one JSON line on stdout from rank 0).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our sm_100a path
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our sm_100a path, training step (headline)
+  python bench.py --workload infer [--gpus N] ...                batched inference + greedy CTC decode (config 4)
   python bench.py --impl reference ...                           the reference algorithm on the host CPU
 
 Workload (BASELINE.json configs[1]): one HTR-VT IAM-shape training step = encoder forward (train mode,
@@ -124,6 +125,19 @@ def run_reference(args):
     if rank != 0:
         return
     B = 8
+    if args.workload == "infer":
+        rate, per, threads = cpu_reference_infer_rate(args.steps, max(args.warmup, 1), B=B)
+        print(json.dumps({
+            "impl": "reference", "metric": "line images/sec (inference)", "value": rate, "unit": "img/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "v1_infer_greedy_decode_512_lines_per_gpu_64x512_c80",
+                       "sample": "%d lines per step on the host CPU" % B},
+            "cpu_baseline": {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
+                             "sample": "oracle port of model_v1 eval forward + reference decode, %d lines/step, %d steps"
+                                       % (B, args.steps)},
+            "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
     rate, per, threads = cpu_reference_rate(args.steps, max(args.warmup, 1), B=B)
     line = {
         "impl": "reference", "metric": "line images/sec (train step)", "value": rate, "unit": "img/s",
@@ -135,6 +149,114 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def inference_metrics(torch, dist, dev, h, ops, model, world, rank, steps, lines_per_gpu=512):
+    """BASELINE.json config 4: batched inference + greedy CTC decode, 512 synthetic lines per GPU (4096 over 8 GPUs),
+    sharded by batch with NO collective on the data path (ddp.shard_batch); each rank decodes its own shard to Python
+    strings.  Two timings, both max over ranks between barriers:
+      value : images resident in HBM, eval forward + decode kernels (ids stay on the device);
+      e2e   : through the public API with HOST buffers - pinned fp32 images -> H2D -> model(image) ->
+              converter.decode_logits (argmax + collapse on device, ONE D2H copy of ids + lengths, id -> str)."""
+    conv = h.CTCLabelConverter("".join(chr(33 + i) for i in range(NB_CLS - 1)))
+    img_h = synth_batch(lines_per_gpu, 1000 + rank)[0].pin_memory()
+    img_d = img_h.to(dev)
+    was_training = model.training
+    model.eval()
+
+    def resident():
+        with torch.no_grad():
+            return h.greedy_decode(model(img_d).float(), NB_CLS)
+
+    def e2e():
+        with torch.no_grad():
+            return conv.decode_logits(model(img_h.to(dev, non_blocking=True)).float())
+
+    def timed(fn, iters):
+        for _ in range(3):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    n0 = ops.launch_count()
+    ms = timed(resident, steps)
+    launches = (ops.launch_count() - n0) // (steps + 3)
+    ms_e2e = timed(e2e, steps)
+    strings = e2e()
+    T = IMG_W // 4
+    if was_training:
+        model.train()
+    return {"img_per_s": world * lines_per_gpu / (ms * 1e-3), "ms_per_batch": ms, "lines_per_gpu": lines_per_gpu,
+            "n_gpus": world, "gpu_launches_per_batch": launches,
+            "e2e": {"value": world * lines_per_gpu / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_batch": ms_e2e,
+                    "h2d_bytes_per_step": img_h.numel() * 4, "d2h_bytes_per_step": lines_per_gpu * (T + 1) * 4},
+            "decoded_lines": len(strings), "collective": "none (batch sharding; strings stay on their rank)",
+            "what": "eval-mode forward + greedy CTC decode (BASELINE config 4: 512 lines per GPU)"}
+
+
+def gpu_eager_baseline(torch, dev, B=128, steps=3):
+    """GPU-side baseline on the SAME box: the reference's graph (the oracle's functional restatement of
+    model_v1/model/HTR_VT.py + resnet18.py, pinned to the reference by tests/test_oracle.py) run by torch eager with the
+    stock library kernels - cuDNN convolutions, cuBLAS GEMMs, ATen LayerNorm / softmax / native CTC ("the existing
+    Blackwell path").  None of this repo's kernels run here; it is a reported baseline like cpu_baseline, ~10 s."""
+    import torch.nn.functional as F
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import htrvt_oracle as O
+    sd0 = O.init_state_dict(NB_CLS, [IMG_H, IMG_W], seed=123)
+    img, tg, tl = synth_batch(B, 0)
+    img, tg_d, tl_d = img.to(dev), tg.to(dev), tl.to(dev)
+    T = IMG_W // 4
+    mask = O.draw_span_mask(T, MASK_RATIO, MAX_SPAN).to(dev)
+    in_len = torch.full((B,), T, dtype=torch.int32, device=dev)
+    out = {}
+    for mode, autocast in (("fp32", False), ("bf16_autocast", True)):
+        sd = {k: v.to(dev) for k, v in sd0.items()}
+        for k, v in sd.items():
+            if v.is_floating_point() and "running_" not in k and k != "pos_embed":
+                sd[k] = v.clone().requires_grad_(True)
+
+        def step():
+            for v in sd.values():
+                if v.requires_grad:
+                    v.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                logits = O.forward(sd, img, mask=mask, training=True)
+            lp = logits.float().permute(1, 0, 2).log_softmax(2)
+            prev = torch.backends.cudnn.enabled
+            torch.backends.cudnn.enabled = False                     # model_v1/train.py:26
+            loss = F.ctc_loss(lp, tg_d, in_len, tl_d, blank=0, reduction="none", zero_infinity=True).mean()
+            torch.backends.cudnn.enabled = prev
+            loss.backward()
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[mode] = {"train_step_ms": ms, "img_per_s": B / (ms * 1e-3)}
+        del sd
+        torch.cuda.empty_cache()
+    out["what"] = ("the reference graph (oracle restatement) through torch %s eager on this GPU: cuDNN / cuBLAS / ATen "
+                   "CTC, batch %d; fp32 = the reference's own arithmetic (TF32 convs as torch defaults), bf16 = autocast"
+                   % (torch.__version__, B))
+    return out
 
 
 def extra_metrics(torch, dev, h, ops, H, model, peaks):
@@ -193,6 +315,45 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
     out["ctc_loss_grad"]["batch_4096"] = {"us_per_batch": ms * 1e3, "achieved_gbs": bl / (ms * 1e-3) / 1e9,
                                           "frac_of_hbm_roofline": bl / (ms * 1e-3) / 1e9 / hbm}
     del xl
+    # the wide-line shape (BASELINE config 5): T = 256, C = 90, labels 64..200 -> up to 401 states per sequence
+    try:
+        import numpy as np
+        Bw, Tw, Cw = 128, 256, 90
+        xw = torch.randn(Bw, Tw, Cw, device=dev)
+        rsw = np.random.RandomState(5)
+        lw = rsw.randint(64, 201, size=Bw).astype("int32")
+        tgw = torch.from_numpy(rsw.randint(1, Cw, size=int(lw.sum())).astype("int32")).to(dev)
+        tlw = torch.from_numpy(lw).to(dev)
+        ms = timed_ms(lambda: ops.ctc_loss_grad(xw, tgw, None, tlw, layout="btc", is_logprob=False, want_grad=True,
+                                                max_target_len=int(lw.max()), grad_scale_const=1.0 / Bw), 20)
+        bw = 2.0 * Bw * Tw * Cw * 4 + float(tgw.numel()) * 4 + 12.0 * Bw
+        out["ctc_loss_grad"]["wide_T256_C90_L200"] = {"us_per_batch": ms * 1e3, "batch": Bw,
+                                                      "achieved_gbs": bw / (ms * 1e-3) / 1e9,
+                                                      "frac_of_hbm_roofline": bw / (ms * 1e-3) / 1e9 / hbm}
+        del xw
+    except Exception as e:
+        out["ctc_loss_grad"]["wide_T256_C90_L200"] = {"error": repr(e)[:200]}
+
+    # ---- greedy decode kernel alone (argmax + collapse): 512 lines x 128 frames x 80 classes of fp32 logits; 8
+    # rotating buffers (168 MB > 126 MB L2) so every call streams from HBM
+    try:
+        Bd, Td = 512, IMG_W // 4
+        dbufs = [torch.randn(Bd, Td, NB_CLS, device=dev) for _ in range(8)]
+        dstate = {"i": 0}
+
+        def dec_once():
+            x = dbufs[dstate["i"] % len(dbufs)]
+            dstate["i"] += 1
+            ops.greedy_decode_ids(x, NB_CLS)
+
+        ms = timed_ms(dec_once, 64)
+        bytes_dec = Bd * Td * NB_CLS * 4.0 + Bd * Td * 4.0 + Bd * 4.0
+        out["greedy_decode"] = {"us_per_batch": ms * 1e3, "lines": Bd, "T": Td, "C": NB_CLS,
+                                "algorithmic_bytes": bytes_dec, "achieved_gbs": bytes_dec / (ms * 1e-3) / 1e9,
+                                "hbm_peak_gbs": hbm, "frac_of_hbm_roofline": bytes_dec / (ms * 1e-3) / 1e9 / hbm}
+        del dbufs
+    except Exception as e:
+        out["greedy_decode"] = {"error": repr(e)[:200]}
 
     # ---- inference: eval forward + greedy decode (argmax + collapse on device, one D2H copy), 512 lines per GPU
     Bi = 512
@@ -205,9 +366,7 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
             preds = model(img)
             return conv.decode_logits(preds.float())
 
-    ms = timed_ms(infer_once, 5, warm=2)
-    out["inference"] = {"img_per_s": Bi / (ms * 1e-3), "ms_per_batch": ms, "batch_per_gpu": Bi,
-                        "what": "eval-mode forward + greedy CTC decode to Python strings (BASELINE config 4 share)"}
+    infer_once()
     # validation metrics on device: Levenshtein of the decoded ids against the label ids
     try:
         with torch.no_grad():
@@ -346,7 +505,8 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
     return out
 
 
-def run_ours(args):
+def setup_ours():
+    """One process per GPU (RANK / LOCAL_RANK / WORLD_SIZE from torchrun), NCCL up, package imported."""
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -378,6 +538,98 @@ def run_ours(args):
     import htrvt_b200 as h
     ops = import_module("htr-vt_b200.ops")
     H = import_module("htr-vt_b200.model.HTR_VT")
+    return torch, dist, world, rank, local, dev, h, ops, H
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def run_infer(args):
+    """--workload infer: BASELINE.json config 4 as its own JSON line (batched inference + greedy CTC decode, 512
+    lines per GPU, batch sharding, no collective)."""
+    torch, dist, world, rank, local, dev, h, ops, H = setup_ours()
+    torch.manual_seed(123)
+    model = H.create_model(NB_CLS, [IMG_H, IMG_W]).to(dev).eval()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    m = inference_metrics(torch, dist, dev, h, ops, model, world, rank, steps=args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    # roofline of the tap-GEMM family inside one inference batch (CUDA events per op on the launching stream)
+    img = synth_batch(m["lines_per_gpu"], 1000 + rank)[0].to(dev)
+    ops.PROFILE = []
+    with torch.no_grad():
+        h.greedy_decode(model(img).float(), NB_CLS)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    g_ms = sum(a.elapsed_time(b) for n, fl, a, b in prof if n in ("gemm_tn", "conv_fwd"))
+    g_fl = sum(fl for n, fl, a, b in prof if n in ("gemm_tn", "conv_fwd"))
+    all_ms = sum(a.elapsed_time(b) for n, fl, a, b in prof)
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    ach = g_fl / (g_ms * 1e-3) / 1e12 if g_ms else 0.0
+    by = {}
+    for n, fl, a, b in prof:
+        by[n] = by.get(n, 0.0) + a.elapsed_time(b)
+    line = {"metric": "line images/sec (inference)", "value": m["img_per_s"], "unit": "img/s", "n_gpus": world,
+            "steps": args.steps, "warmup": 3, "ms_per_step": m["ms_per_batch"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "v1_infer_greedy_decode_512_lines_per_gpu_64x512_c80", "lines_per_gpu": m["lines_per_gpu"],
+                       "img": [1, IMG_H, IMG_W], "nb_cls": NB_CLS, "parallelism": "dp%d (batch sharding, no collective)" % world,
+                       "l2": "one batch's activations (~1.5 GB) >> 126 MB L2; no flush needed",
+                       "algorithmic_tflop_per_step": GFLOP_FWD_PER_IMG * m["lines_per_gpu"] / 1e3},
+            "clocks": clk, "e2e": m["e2e"], "gpu_launches": m["gpu_launches_per_batch"] * args.steps,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": ach / peak_tf if peak_tf else None, "traffic": None,
+                         "kernel": "tapgemm_kernel (conv / linear forward launches of one inference batch)",
+                         "ms_in_step": g_ms, "share_of_step": g_ms / all_ms if all_ms else None,
+                         "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"},
+            "breakdown_ms": {k: round(v, 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1])}}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, per, threads = cpu_reference_infer_rate(5, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
+                                "sample": "oracle port of model_v1 eval forward + reference decode, 8 lines/step, 5 steps"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_reference_infer_rate(steps, warmup, B=8, seed=0):
+    """Reference inference on the host cores: eval forward (oracle port) + log_softmax / max / decode as valid.py:31-42."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import htrvt_oracle as O
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    if torch.get_num_threads() < ncpu:
+        torch.set_num_threads(ncpu)
+    sd = O.init_state_dict(NB_CLS, [IMG_H, IMG_W], seed=123)
+    img = synth_batch(B, seed)[0]
+    alphabet = "".join(chr(33 + i) for i in range(NB_CLS - 1))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            lg = O.forward(sd, img, training=False)
+        idx = O.argmax_first(lg.numpy()).reshape(-1)
+        O.decode_strings(idx, [lg.shape[1]] * B, alphabet)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    per = sum(times) / len(times)
+    return B / per, per, torch.get_num_threads()
+
+
+def run_ours(args):
+    torch, dist, world, rank, local, dev, h, ops, H = setup_ours()
 
     B = args.batch
     torch.manual_seed(123)
@@ -464,19 +716,28 @@ def run_ours(args):
     g_n = sum(by[n][2] for n in gemm_names if n in by)
     all_ms = sum(v[0] for v in by.values())
 
+    # BASELINE config 4 at this N (every rank takes part: max-over-ranks timing between barriers)
+    infer = None
+    if not args.no_extras:
+        try:
+            infer = inference_metrics(torch, dist, dev, h, ops, model, world, rank, steps=5)
+        except Exception as e:
+            infer = {"error": repr(e)[:200]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = {}
-    for cand in (os.path.join(ROOT, "MEASURED_PEAKS.json"),):
-        if os.path.exists(cand):
-            peaks = json.load(open(cand))
-    traffic = None          # DRAM bytes of the tap-GEMM launches of one step, from the committed ncu counters (profiles/)
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["tapgemm_dram_bytes_per_step"]
-    except Exception:
-        pass
+    peaks = load_peaks()
+    # DRAM bytes of the tap-GEMM launches of one step: STATIC, from the committed ncu counters of this build's profile
+    # run (profiles/*_traffic.json, `tools/ncu_step.sh`) - hardware counters cannot be read inside an unprofiled run
+    traffic, traffic_src = None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", name)))["tapgemm_dram_bytes_per_step"]
+            traffic_src = "static from profiles/" + name
+            break
+        except Exception:
+            pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md sustained)"
     ach_tf = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
@@ -499,15 +760,24 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                     "traffic_note": "ncu dram bytes (read + write) summed over the family's launches of one step; "
-                                     "algorithmic = flops, the operands are re-read from L2",
+                     "traffic_note": "%s: ncu dram bytes (read + write) summed over the family's launches of one step; "
+                                     "algorithmic = flops, the operands are re-read from L2" % traffic_src,
                      "kernel": "tapgemm_kernel (all conv / linear fwd, dgrad, wgrad launches of one step)",
                      "launches": g_n, "ms_in_step": g_ms, "share_of_step": g_ms / all_ms if all_ms else None,
                      "peak_source": peak_src},
         "breakdown_ms": {k: round(v[0], 3) for k, v in sorted(by.items(), key=lambda kv: -kv[1][0])},
     }
+    line["config"]["precision"] = ("16-bit tensor-core operands, fp32 accumulation: bf16 everywhere except the forward "
+                                   "stem tensors (activations, raw conv outputs, forward conv weights), which are fp16 "
+                                   "- same width and MMA rate, 3 more mantissa bits (train-mode parity, DESIGN.md 4)")
+    if infer is not None:
+        line["inference"] = infer
     if world == 1 and not args.no_extras:
         line["extra"] = extra_metrics(torch, dev, h, ops, H, model, peaks)
+        try:
+            line["extra"]["gpu_eager_baseline"] = gpu_eager_baseline(torch, dev)
+        except Exception as e:
+            line["extra"]["gpu_eager_baseline"] = {"error": repr(e)[:200]}
     if world == 1 and not args.no_cpu_baseline:
         rate, per, threads = cpu_reference_rate(20, 1, B=8)          # ~10 s of host work
         line["cpu_baseline"] = {"value": rate, "unit": "img/s", "cores": threads, "kind": "port",
@@ -524,11 +794,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=128, help="images per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train: fwd+bwd+CTC step, batch 128/GPU (headline, BASELINE configs 2-3); "
+                         "infer: eval forward + greedy decode, 512 lines/GPU (config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the CTC / inference / window-variant side metrics")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "infer":
+        run_infer(args)
     else:
         run_ours(args)
 

@@ -61,21 +61,36 @@ def _worker(rank, world, port, out):
     same = all(torch.equal(a, b) for a, b in zip(dp.state_dict().values(), build(100).state_dict().values())) \
         if rank == 0 else True
     g_dp = step(dp, rank)
-    worst = 0.0
+    worst, worst_cos, noise = 0.0, 1.0, 0.0
     if rank == 0:
         sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
-        g0 = step(ref, 0)
-        ref.load_state_dict(sd0)                              # undo the BatchNorm running-stat update
-        g1 = step(ref, 1)
+
+        def rerun(r):
+            ref.load_state_dict(sd0)                          # undo the BatchNorm running-stat update
+            return step(ref, r)
+
+        g0, g1, g0b = rerun(0), rerun(1), rerun(0)
+        # noise floor: the backward sums split-K slices / per-CTA partials in a free order (fp32 atomics, TMA
+        # reduce-add), and some stem gradients are small residuals of large cancelling sums (a BatchNorm follows), so
+        # two IDENTICAL single-GPU runs differ by up to ~1e-2 in those tensors (tools/repro_probe.py)
+        num = den = nnum = 0.0
         for n in g_dp:
-            want = 0.5 * (g0[n] + g1[n])
-            err = float((g_dp[n] - want).abs().max() / (want.abs().max() + 1e-20))
-            worst = max(worst, err)
+            want = 0.5 * (g0[n] + g1[n]).double()
+            got = g_dp[n].double()
+            num += float(((got - want) ** 2).sum())
+            den += float((want ** 2).sum())
+            nnum += float(((g0[n].double() - g0b[n].double()) ** 2).sum())
+            worst = max(worst, float((got - want).norm() / (want.norm() + 1e-30)))
+            worst_cos = min(worst_cos, float((got.reshape(-1) @ want.reshape(-1)) / (got.norm() * want.norm() + 1e-30)))
+        total = (num / den) ** 0.5
+        noise = (nnum / den) ** 0.5
+        worst = max(worst, 0.0)
+        out["detail"] = (total, noise)
     # every rank holds the same averaged gradient
     digest = torch.stack([v.double().sum() for v in g_dp.values()])
     both = [torch.zeros_like(digest) for _ in range(world)]
     dist.all_gather(both, digest)
-    out[rank] = (bool(same), worst, bool(torch.equal(both[0], both[1])), len(g_dp))
+    out[rank] = (bool(same), worst, bool(torch.equal(both[0], both[1])), len(g_dp), worst_cos)
     dist.destroy_process_group()
 
 
@@ -87,9 +102,12 @@ def test_dp_gradients_equal_mean_of_shard_gradients():
     out = mgr.dict()
     port = 29600 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
-    same, worst, equal_across_ranks, n = out[0]
+    same, worst, equal_across_ranks, n, worst_cos = out[0]
+    total, noise = out["detail"]
     assert same                                  # broadcast left rank 0's weights untouched
     assert n > 50
-    # split-K slices / atomics sum in a free order: equal up to fp32 summation order, not bit for bit
-    assert worst < 2e-5, worst
-    assert equal_across_ranks and out[1][2]
+    # averaged gradient == mean of the two shard gradients, up to the run-to-run noise of the backward's free summation
+    # order (a sum instead of a mean, a dropped segment or a stale shard would be off by O(1))
+    assert total <= 4.0 * noise + 1e-5, (total, noise)
+    assert worst < 5e-2 and worst_cos > 0.999, (worst, worst_cos)
+    assert equal_across_ranks and out[1][2]      # bit-identical on both ranks after the all-reduce
