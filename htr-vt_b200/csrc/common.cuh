@@ -111,6 +111,36 @@ __device__ __forceinline__ float2 unpack_f16(uint32_t u) {
 __device__ __forceinline__ float f16_bits_to_float(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 
 // ---------------------------------------------------------------------------------------------
+// GELU (erf form, nn.GELU default used by timm Mlp) - shared by the fused GEMM epilogues and the stand-alone kernels
+// ---------------------------------------------------------------------------------------------
+// Phi(u) (standard normal CDF, i.e. the erf form of nn.GELU) and e = exp(-u^2/2) with two MUFU ops and six FMAs:
+// erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z)  (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7 - far
+// below the bf16 output resolution).  libm's erff costs ~2x the instructions, which made these two streaming kernels
+// instruction bound (~3.3 TB/s); the exponential is shared with the density term of the backward.
+__device__ __forceinline__ void gelu_parts(float u, float& cdf, float& e) {
+  const float z = fabsf(u) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  e = ex2f(u * u * -0.72134752044448170f);          // exp(-u^2 / 2)
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float h = 0.5f * p * t * e;                 // 1 - Phi(|u|)
+  cdf = u >= 0.f ? 1.0f - h : h;
+}
+__device__ __forceinline__ float gelu_val(float u) {
+  float c, e;
+  gelu_parts(u, c, e);
+  return u * c;
+}
+__device__ __forceinline__ float gelu_grad(float u) {
+  float c, e;
+  gelu_parts(u, c, e);
+  return fmaf(u * 0.3989422804014327f, e, c);
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -1,6 +1,7 @@
 // Greedy CTC decoding for sm_100a: per-frame argmax + collapse (drop blanks, repeats and
-// out-of-alphabet ids) + compaction in ONE kernel, one CTA per line; a single D2H copy of
-// ids[B,T] / lens[B] then replaces the reference's per-element device syncs.
+// out-of-alphabet ids) + compaction in ONE kernel, one CTA per line (the line's logits staged in shared memory by
+// 16-byte asynchronous copies); a single D2H copy of ids[B,T] / lens[B] then replaces the reference's per-element
+// device syncs.
 //
 // Replaces model_v1/valid.py:40-42 (`preds.max(2)`, transpose, view) and the id filtering of
 // CTCLabelConverter.decode (model_v1/utils/utils.py:72-86); id -> char stays on the host.
@@ -42,29 +43,71 @@ __device__ __forceinline__ int collapse_compact(const int* raw, int Tb, int n_ch
   return count;
 }
 
-__global__ void __launch_bounds__(kDecThreads) greedy_decode_kernel(
+// ---------------------------------------------------------------------------------------------
+// arg-max + collapse, one CTA (256 threads) per line.  The kernel is pure streaming (B*T*C*4 bytes in, B*T*4 out), so
+// the whole line is brought into shared memory with 16-byte cp.async copies that are ALL in flight at once (rows in
+// chunks when T*C*4 exceeds the staging budget), then two threads scan each frame from shared memory (lower / upper
+// half of the class axis; strict comparisons keep the lowest index, a NaN wins), and warp 0 compacts.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGdThreads = 256;
+constexpr int kGdStageBytes = 96 * 1024;
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(kGdThreads) greedy_decode_kernel(
     const float* __restrict__ x, long long sb, long long st, int B, int T, int C, const int* __restrict__ lengths,
-    int n_character, int* __restrict__ ids, int* __restrict__ lens, int* __restrict__ raw_out) {
-  extern __shared__ int raw[];                     // [T]
+    int n_character, int* __restrict__ ids, int* __restrict__ lens, int* __restrict__ raw_out, int rows_per_chunk,
+    int vec_ok) {
+  extern __shared__ __align__(16) unsigned char gd_smem[];
+  int* raw = reinterpret_cast<int*>(gd_smem);                               // [T] arg-max ids
+  const int ldc = (C + 3) & ~3;                                             // staged row stride (floats), 16-byte rows
+  float* stage = reinterpret_cast<float*>(gd_smem + ((static_cast<size_t>(T) * 4 + 15) & ~size_t(15)));
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int Tb = lengths ? lengths[b] : T;
   Tb = min(max(Tb, 0), T);
   const float* xb = x + static_cast<long long>(b) * sb;
-  for (int t = warp; t < Tb; t += kDecThreads / 32) {
-    const float* xr = xb + static_cast<long long>(t) * st;
-    Best best{-INFINITY, 0x7fffffff};
-    for (int c = lane; c < C; c += 32) {
-      Best cand{xr[c], c};
-      if (best.i == 0x7fffffff || better(cand, best)) best = cand;
+  const int half = (C + 1) >> 1;
+  for (int t0 = 0; t0 < Tb; t0 += rows_per_chunk) {
+    const int nr = min(rows_per_chunk, Tb - t0);
+    if (t0 > 0) __syncthreads();                                            // previous chunk fully scanned
+    if (vec_ok) {
+      const int v_per_row = C >> 2, nv = nr * v_per_row;
+      for (int i = threadIdx.x; i < nv; i += kGdThreads) {
+        const int r = i / v_per_row, v = i - r * v_per_row;
+        cp_async_16(smem_u32(stage + r * ldc + 4 * v), xb + static_cast<long long>(t0 + r) * st + 4 * v);
+      }
+    } else {
+      const int n = nr * C;
+      for (int i = threadIdx.x; i < n; i += kGdThreads) {
+        const int r = i / C, c = i - r * C;
+        cp_async_4(smem_u32(stage + r * ldc + c), xb + static_cast<long long>(t0 + r) * st + c);
+      }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      Best other{__shfl_xor_sync(0xffffffffu, best.v, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // two threads per frame: thread pair (2r, 2r+1) scans classes [0, half) and [half, C)
+    for (int base = 0; base < 2 * nr; base += kGdThreads) {                 // uniform trip count: the shuffle needs whole warps
+      const int i = base + threadIdx.x;
+      const bool act = i < 2 * nr;
+      const int r = act ? i >> 1 : 0, hi = i & 1;
+      const float* row = stage + r * ldc;
+      const int c0 = hi ? half : 0, c1 = act ? (hi ? C : half) : 0;
+      Best best{-INFINITY, 0x7fffffff};
+      for (int c = c0; c < c1; ++c) {
+        const Best cand{row[c], c};
+        if (best.i == 0x7fffffff || better(cand, best)) best = cand;
+      }
+      const Best other{__shfl_xor_sync(0xffffffffu, best.v, 1), __shfl_xor_sync(0xffffffffu, best.i, 1)};
       if (other.i != 0x7fffffff && (best.i == 0x7fffffff || better(other, best))) best = other;
-    }
-    if (lane == 0) {
-      raw[t] = best.i;
-      if (raw_out) raw_out[static_cast<long long>(b) * T + t] = best.i;
+      if (act && !hi) {
+        raw[t0 + r] = best.i;
+        if (raw_out) raw_out[static_cast<long long>(b) * T + t0 + r] = best.i;
+      }
     }
   }
   __syncthreads();
@@ -79,15 +122,13 @@ __global__ void __launch_bounds__(kDecThreads) greedy_decode_kernel(
 // Collapse an already-argmaxed index stream (the reference decode() input: [sum T_b] sample-major).
 template <typename IdxT>
 __global__ void __launch_bounds__(kDecThreads) collapse_kernel(const IdxT* __restrict__ index,
-                                                               const int* __restrict__ lengths, int B, int Tmax,
+                                                               const int* __restrict__ lengths,
+                                                               const long long* __restrict__ offsets, int B, int Tmax,
                                                                int n_character, int* __restrict__ ids,
                                                                int* __restrict__ lens) {
   extern __shared__ int raw[];                     // [Tmax]
-  __shared__ float red[40];
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float part = 0.f;
-  for (int i = threadIdx.x; i < b; i += kDecThreads) part += static_cast<float>(lengths[i]);
-  const long long off = static_cast<long long>(block_sum(part, red) + 0.5f);
+  const long long off = offsets[b];                // exclusive prefix sum of the lengths (int64, one scan by the caller)
   const int Tb = min(max(lengths[b], 0), Tmax);
   for (int t = threadIdx.x; t < Tb; t += kDecThreads) {
     const long long v = static_cast<long long>(index[off + t]);
@@ -111,22 +152,32 @@ extern "C" int htrvt_greedy_decode(const float* logits, long long stride_b, long
                                    cudaStream_t stream) {
   if (B <= 0 || T <= 0 || C <= 0 || !logits || !ids || !lens) return HTRVT_ERR_SHAPE;
   if (static_cast<size_t>(T) * 4 > 40 * 1024) return HTRVT_ERR_SHAPE;
-  greedy_decode_kernel<<<B, kDecThreads, T * sizeof(int), stream>>>(logits, stride_b, stride_t, B, T, C, lengths,
-                                                                    n_character, ids, lens, raw_index);
+  const int ldc = (C + 3) & ~3;
+  if (static_cast<size_t>(ldc) * 4 > static_cast<size_t>(kGdStageBytes)) return HTRVT_ERR_SHAPE;
+  int rows = static_cast<int>(kGdStageBytes / (static_cast<size_t>(ldc) * 4));
+  if (rows > T) rows = T;
+  // 16-byte copies need every row start on a 16-byte boundary
+  const int vec_ok = ((C & 3) == 0) && ((stride_b & 3) == 0) && ((stride_t & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const size_t smem = ((static_cast<size_t>(T) * 4 + 15) & ~size_t(15)) + static_cast<size_t>(rows) * ldc * 4;
+  if (smem > 48 * 1024 && !HTRVT_ENSURE_SMEM(greedy_decode_kernel, 160 * 1024)) return HTRVT_ERR_LAUNCH;
+  greedy_decode_kernel<<<B, kGdThreads, smem, stream>>>(logits, stride_b, stride_t, B, T, C, lengths, n_character, ids,
+                                                        lens, raw_index, rows, vec_ok);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
 
-extern "C" int htrvt_ctc_collapse(const void* index, int index_is_int64, const int* lengths, int B, int Tmax,
-                                  int n_character, int* ids, int* lens, cudaStream_t stream) {
-  if (B <= 0 || Tmax <= 0 || !index || !lengths || !ids || !lens) return HTRVT_ERR_SHAPE;
+// offsets: int64 [B] device array, exclusive prefix sum of `lengths` (start of each line in the index stream)
+extern "C" int htrvt_ctc_collapse(const void* index, int index_is_int64, const int* lengths, const long long* offsets,
+                                  int B, int Tmax, int n_character, int* ids, int* lens, cudaStream_t stream) {
+  if (B <= 0 || Tmax <= 0 || !index || !lengths || !offsets || !ids || !lens) return HTRVT_ERR_SHAPE;
   if (static_cast<size_t>(Tmax) * 4 > 40 * 1024) return HTRVT_ERR_SHAPE;
   if (index_is_int64)
     collapse_kernel<long long><<<B, kDecThreads, Tmax * sizeof(int), stream>>>(
-        static_cast<const long long*>(index), lengths, B, Tmax, n_character, ids, lens);
+        static_cast<const long long*>(index), lengths, offsets, B, Tmax, n_character, ids, lens);
   else
-    collapse_kernel<int><<<B, kDecThreads, Tmax * sizeof(int), stream>>>(static_cast<const int*>(index), lengths, B,
-                                                                         Tmax, n_character, ids, lens);
+    collapse_kernel<int><<<B, kDecThreads, Tmax * sizeof(int), stream>>>(static_cast<const int*>(index), lengths,
+                                                                         offsets, B, Tmax, n_character, ids, lens);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }

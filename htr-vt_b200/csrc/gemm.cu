@@ -37,33 +37,23 @@ constexpr int kBK = 64;
 constexpr int kWinRows = 136;
 constexpr int kWin4Rows = 72;                  // KIND 4: 64 pixels + 2 of halo, padded to whole 1024-byte swizzle atoms
 constexpr int kWin4Bytes = kWin4Rows * 128;
-template <int BN, int CL, bool RE = false, bool W4 = false>
+// DUAL (fc1 in train mode): the epilogue stores TWO boxes per step (pre-activation u and gelu(u)), so each epilogue
+// warp gets four staging buffers instead of two and the ring gives up one stage.
+template <int BN, int CL, bool RE = false, bool W4 = false, bool DUAL = false>
 struct GemmCfg {
   static constexpr int kABytes = W4 ? 2 * kWin4Bytes : RE ? kWinRows * kBK * 2 : kBM * kBK * 2;
   static constexpr int kBTile = (BN / CL) * kBK * 2;                  // one tap's B bytes staged by THIS CTA
   static constexpr int kBBytes = RE ? 3 * kBTile : kBTile;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = W4 ? (BN >= 256 ? 3 : 4) : RE ? (BN >= 256 ? 2 : 3) : (CL == 2) ? 6 : ((BN <= 128) ? 6 : 4);
+  static constexpr int kStages = (W4 ? (BN >= 256 ? 3 : 4) : RE ? (BN >= 256 ? 2 : 3) : (CL == 2) ? 6 : ((BN <= 128) ? 6 : 4)) -
+                                 (DUAL ? 1 : 0);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kStagingBytes = 8 * 2 * 2048;   // per epilogue warp: two [32 rows][64 B] output boxes
+  static constexpr int kWarpStaging = DUAL ? 4 * 2048 : 2 * 2048;   // per epilogue warp: [32 rows][64 B] output boxes
+  static constexpr int kStagingBytes = 8 * kWarpStaging;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert(kStageBytes % 1024 == 0, "SWIZZLE_128B stage alignment");
 };
-
-__device__ __forceinline__ float gelu_erf(float x) {
-  // 0.5 x (1 + erf(x / sqrt2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 eps)
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = 1.0f - poly * ex2f(-z * z * kLog2e);
-  const float erfv = copysignf(e, x);
-  return 0.5f * x * (1.0f + erfv);
-}
 
 struct TileCoord {
   int m_tile, n_tile, tap, split;
@@ -93,12 +83,14 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmP& P, int id) {
   return c;
 }
 
-template <int BN, int KIND, bool B_MN, int CL, bool RE = false>
+template <int BN, int KIND, bool B_MN, int CL, bool RE = false, bool DUAL = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ GemmP P) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+               const __grid_constant__ GemmP P) {
   constexpr bool W4 = (KIND == 4);
-  using Cfg = GemmCfg<BN, CL, RE, W4>;
+  using Cfg = GemmCfg<BN, CL, RE, W4, DUAL>;
+  static_assert(!DUAL || (KIND == 0 && !RE), "dual-output epilogue: linear forward only");
   static_assert(!RE || (KIND == 0 && !B_MN && CL == 2), "window reuse: kind 0, K-major weights, CTA pairs");
   static_assert(!W4 || (B_MN && CL == 1 && !RE), "two-accumulator weight gradient: single CTA, MN-major operands");
   constexpr bool A_MN = (KIND == 1 || KIND == 3 || KIND == 4);
@@ -127,6 +119,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
+    if (DUAL) tma_prefetch_desc(&tmC2);
     for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8 * CL); }
     fence_barrier_init();
@@ -347,7 +340,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool out_bf16 = (P.flags & EPI_BF16) != 0;      // 16-bit output (bf16, or fp16 with EPI_F16)
     const bool f16 = (P.flags & EPI_F16) != 0;
     const int box_cols = out_bf16 ? 32 : 16;
-    uint8_t* stg = stage_out + ew * 4096;                   // 2 x [32 rows][64 B], SWIZZLE_64B
+    uint8_t* stg = stage_out + ew * Cfg::kWarpStaging;      // 2 (DUAL: 2 x 2) x [32 rows][64 B], SWIZZLE_64B
     const int sw_r = (lane >> 1) & 3;
     int sbuf = 0;
     float ssum[4] = {0.f, 0.f, 0.f, 0.f}, qsum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -397,6 +390,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; ++i) raw[i] = 0u;
         }
         uint32_t packed[16];
+        uint32_t packed2[DUAL ? 16 : 1];
         if (out_bf16) {
           float bv[32];
           if (P.flags & EPI_BIAS) {
@@ -408,7 +402,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           uint4 rq[4] = {};
-          if (KIND == 0 && (P.flags & EPI_RES)) {            // this thread's output pixel, 32 consecutive channels
+          if (KIND == 0 && (P.flags & (EPI_RES | EPI_GELU_BWD))) {   // this thread's output pixel, 32 consecutive channels
             const int w = tc.w0 + r;
             if (w < P.Wo && col < P.N_valid) {
               const uint4* rp = reinterpret_cast<const uint4*>(
@@ -423,6 +417,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; i += 2) {
             float a = __uint_as_float(raw[i]) * P.alpha, c = __uint_as_float(raw[i + 1]) * P.alpha;
             if (P.flags & EPI_BIAS) { a += bv[i]; c += bv[i + 1]; }
+            if (P.flags & EPI_GELU) {                        // timm Mlp: fc1 -> nn.GELU (erf form), fused
+              if (DUAL) packed2[i >> 1] = pack_bf16(a, c);   // the pre-activation u, kept for the backward
+              a = gelu_val(a); c = gelu_val(c);
+            }
+            if (KIND == 0 && (P.flags & EPI_GELU_BWD)) {     // du = da * gelu'(u), u = the saved pre-activation
+              const float2 uu = unpack_bf16(rw[i >> 1]);
+              a *= gelu_grad(uu.x); c *= gelu_grad(uu.y);
+            }
             if (KIND == 0 && (P.flags & EPI_RES)) {
               const float2 rr = f16 ? unpack_f16(rw[i >> 1]) : unpack_bf16(rw[i >> 1]);
               a += rr.x; c += rr.y;
@@ -447,13 +449,17 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the store issued from this buffer two boxes ago must have finished READING it
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
-        const uint32_t sbase = smem_u32(stg) + sbuf * 2048;
+        const uint32_t sbase = smem_u32(stg) + sbuf * (DUAL ? 4096 : 2048);
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
           const uint32_t addr = sbase + lane * 64 + ((c16 ^ sw_r) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * c16]),
                        "r"(packed[4 * c16 + 1]), "r"(packed[4 * c16 + 2]), "r"(packed[4 * c16 + 3])
                        : "memory");
+          if (DUAL)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2048), "r"(packed2[4 * c16]),
+                         "r"(packed2[4 * c16 + 1]), "r"(packed2[4 * c16 + 2]), "r"(packed2[4 * c16 + 3])
+                         : "memory");
         }
         fence_proxy_async();
         __syncwarp();
@@ -471,6 +477,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               asm volatile(
                   "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
                   ::"l"(reinterpret_cast<uint64_t>(&tmC)), "r"(sbase), "r"(col), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                  : "memory");
+            if (DUAL)                                        // the pre-activation box, same coordinates, second tensor
+              asm volatile(
+                  "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                  ::"l"(reinterpret_cast<uint64_t>(&tmC2)), "r"(sbase + 2048), "r"(col), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                   : "memory");
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (possibly empty) keeps the buffer <-> group pairing
@@ -600,15 +611,16 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int KIND, bool B_MN, int CL, bool RE = false>
+template <int BN, int KIND, bool B_MN, int CL, bool RE = false, bool DUAL = false>
 int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
-               cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CL, RE, KIND == 4>;
-  auto kern = tapgemm_kernel<BN, KIND, B_MN, CL, RE>;
+               cudaStream_t stream, const CUtensorMap* c2p = nullptr) {
+  using Cfg = GemmCfg<BN, CL, RE, KIND == 4, DUAL>;
+  auto kern = tapgemm_kernel<BN, KIND, B_MN, CL, RE, DUAL>;
+  const CUtensorMap& c2 = c2p ? *c2p : c;
   if (!HTRVT_ENSURE_SMEM(kern, Cfg::kSmemBytes)) return HTRVT_ERR_LAUNCH;
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
   if (CL == 1) {
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, c, P);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, c, c2, P);
   } else {
     grid &= ~1;
     cudaLaunchConfig_t cfg = {};
@@ -621,7 +633,7 @@ int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, kern, a, b, c, P) != cudaSuccess) return HTRVT_ERR_LAUNCH;
+    if (cudaLaunchKernelEx(&cfg, kern, a, b, c, c2, P) != cudaSuccess) return HTRVT_ERR_LAUNCH;
   }
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
@@ -717,11 +729,15 @@ int choose_splits(int base_tiles, long long q_total, long long out_elems) {
 }  // namespace
 
 // Y[M,N] = epilogue(alpha * X[M,K] W[N,K]^T): nn.Linear forward (both operands K-major).
-// flags: EPI_BF16 (else fp32 out), EPI_BIAS, EPI_RELU, EPI_ACCUM (out += via TMA reduce-add)
+// flags: EPI_BF16 (else fp32 out), EPI_BIAS, EPI_RELU, EPI_ACCUM (out += via TMA reduce-add),
+// EPI_GELU (4096; bf16 out): out = gelu(alpha * X W^T + bias) - timm Mlp's fc1 + nn.GELU in one kernel; with `pre`
+// (nullable, bf16 [M, N], row stride ldp) the pre-activation is stored too (train mode: the backward needs it).
 extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long long ldw, int M, int N, int K,
-                             int flags, const float* bias, void* out, long long ldo, float alpha,
-                             cudaStream_t stream) {
+                             int flags, const float* bias, void* out, long long ldo, float alpha, void* pre,
+                             long long ldp, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (N & 3)) return HTRVT_ERR_SHAPE;
+  if ((flags & EPI_GELU) && !(flags & EPI_BF16)) return HTRVT_ERR_SHAPE;
+  if (pre && (!(flags & EPI_GELU) || (N % 256) != 0 || (flags & EPI_ACCUM))) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(N);
   const int esz = (flags & EPI_BF16) ? 2 : 4;
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + bn - 1) / bn;
@@ -742,15 +758,28 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
   P.kind = 0; P.Wo = M; P.Ho = 1; P.NB = 1;
   P.tiles_per_row = tiles_m; P.tiles_m = tiles_m; P.tiles_n = tiles_n;
   P.n_taps = 1; P.splits = 1; P.k_chunks = (K + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = 0;
-  P.M_valid = M; P.N_valid = N; P.flags = flags & (EPI_BF16 | EPI_BIAS | EPI_RELU | EPI_ACCUM | EPI_NOSTORE);
+  P.M_valid = M; P.N_valid = N;
+  P.flags = (flags & (EPI_BF16 | EPI_BIAS | EPI_RELU | EPI_ACCUM | EPI_NOSTORE | EPI_GELU)) | (pre ? EPI_DUAL : 0);
   P.bias = bias; P.alpha = alpha;
+  if (pre) {                                               // N % 256 == 0 => bn == 256
+    CUtensorMap tc2;
+    int r = make_map_out(&tc2, pre, 2, N, M, 1, 1, ldp, ldp * M, ldp * M);
+    if (r) return r;
+    if (cl == 2) return launch_one<256, 0, false, 2, false, true>(ta, tb, tc, P, P.tiles_m * P.tiles_n, stream, &tc2);
+    return launch_one<256, 0, false, 1, false, true>(ta, tb, tc, P, P.tiles_m * P.tiles_n, stream, &tc2);
+  }
   return launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
 
 // dX[M,N] = dY[M,K] W[K,N]: nn.Linear input gradient (B operand MN-major, no transpose copy).
+// gelu_u (nullable, bf16 [M, N] contiguous): dX = (dY W) * gelu'(gelu_u) - the backward of timm Mlp's activation fused
+// into fc2's input-gradient GEMM (gelu_u = fc1's saved pre-activation).
 extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long long ldw, int M, int N, int K,
-                             int flags, void* out, long long ldo, float alpha, cudaStream_t stream) {
+                             int flags, void* out, long long ldo, float alpha, const void* gelu_u,
+                             cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (N & 7)) return HTRVT_ERR_SHAPE;
+  if (gelu_u && (!(flags & EPI_BF16) || (flags & EPI_ACCUM) || (N & 31) || (reinterpret_cast<uintptr_t>(gelu_u) & 15)))
+    return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(N);
   const int esz = (flags & EPI_BF16) ? 2 : 4;
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + bn - 1) / bn;
@@ -771,8 +800,8 @@ extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long
   P.kind = 0; P.Wo = M; P.Ho = 1; P.NB = 1;
   P.tiles_per_row = tiles_m; P.tiles_m = tiles_m; P.tiles_n = tiles_n;
   P.n_taps = 1; P.splits = 1; P.k_chunks = (K + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = 0;
-  P.M_valid = M; P.N_valid = N; P.flags = flags & (EPI_BF16 | EPI_ACCUM | EPI_NOSTORE);
-  P.alpha = alpha;
+  P.M_valid = M; P.N_valid = N; P.flags = (flags & (EPI_BF16 | EPI_ACCUM | EPI_NOSTORE)) | (gelu_u ? EPI_GELU_BWD : 0);
+  P.alpha = alpha; P.res = gelu_u;
   return launch_bn<0, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
 

@@ -20,6 +20,9 @@ enum : int {
   EPI_NOSTORE = 1 << 8,    // measurement aid: skip the epilogue body (main-loop-only timing)
   EPI_RES = 1 << 9,        // kind 0, 16-bit out: + res[n,h,w,col] (same NHWC geometry as the output) before the ReLU
   EPI_F16 = 1 << 10,       // the 16-bit output (and the EPI_RES residual) is IEEE fp16, not bf16 (forward stem tensors)
+  EPI_GELU = 1 << 12,      // bf16 out: out = gelu(acc * alpha + bias) (erf form) - timm Mlp fc1 -> act
+  EPI_DUAL = 1 << 13,      // with EPI_GELU (kernel built with DUAL): the pre-activation goes to a second output (tmC2)
+  EPI_GELU_BWD = 1 << 14,  // bf16 out, kind 0: out = acc * gelu'(res[row, col]) (res = the saved pre-activation u)
 };
 
 struct GemmP {

@@ -266,32 +266,7 @@ __global__ void __launch_bounds__(256) tokens_bwd_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------------
 // GELU backward: du = da * (Phi(u) + u phi(u)), erf form (nn.GELU default)
 // ------------------------------------------------------------------------------------------------
-// Phi(u) (standard normal CDF, i.e. the erf form of nn.GELU) and e = exp(-u^2/2) with two MUFU ops and six FMAs:
-// erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z)  (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7 - far
-// below the bf16 output resolution).  libm's erff costs ~2x the instructions, which made these two streaming kernels
-// instruction bound (~3.3 TB/s); the exponential is shared with the density term of the backward.
-__device__ __forceinline__ void gelu_parts(float u, float& cdf, float& e) {
-  const float z = fabsf(u) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  e = ex2f(u * u * -0.72134752044448170f);          // exp(-u^2 / 2)
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float h = 0.5f * p * t * e;                 // 1 - Phi(|u|)
-  cdf = u >= 0.f ? 1.0f - h : h;
-}
-__device__ __forceinline__ float gelu_val(float u) {
-  float c, e;
-  gelu_parts(u, c, e);
-  return u * c;
-}
-__device__ __forceinline__ float gelu_grad(float u) {
-  float c, e;
-  gelu_parts(u, c, e);
-  return fmaf(u * 0.3989422804014327f, e, c);
-}
+// (gelu_parts / gelu_val / gelu_grad live in common.cuh: the GEMM epilogues use them too)
 __device__ __forceinline__ uint32_t gelu2(uint32_t w) {
   const float2 y = unpack_bf16(w);
   return pack_bf16(gelu_val(y.x), gelu_val(y.y));

@@ -234,9 +234,11 @@ class Engine(object):
                 ops.dropout_(y1, T * D, drop, seed, 8 * i + 1, dp1)
             h2, m2, r2s, x2 = ops.row_ln_fwd(x1, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], self.ln_eps, y1)
             hid = wp[p + ".mlp.fc1.weight"].shape[0]
-            u = torch.empty((M, hid), dtype=torch.bfloat16, device=xs.device)
-            ops.gemm_tn(h2, wp[p + ".mlp.fc1.weight"], u, bias=sd[p + ".mlp.fc1.bias"])
-            a = ops.gelu_fwd(u)
+            # timm Mlp: fc1 -> nn.GELU in ONE kernel (GELU in the GEMM epilogue); with `save` the epilogue also stores
+            # the pre-activation u (a second TMA store per box) for the backward
+            a = torch.empty((M, hid), dtype=torch.bfloat16, device=xs.device)
+            u = torch.empty((M, hid), dtype=torch.bfloat16, device=xs.device) if save else None
+            ops.gemm_tn(h2, wp[p + ".mlp.fc1.weight"], a, bias=sd[p + ".mlp.fc1.bias"], gelu=True, pre=u)
             if rng:
                 ops.dropout_(a, T * hid, drop, seed, 8 * i + 2)
             y2 = torch.empty((M, D), dtype=torch.bfloat16, device=xs.device)
@@ -397,11 +399,14 @@ class Engine(object):
                 ops.dropout_(gy, T * D, drop, seed, 8 * i + 3, dp2)
             ops.linear_wgrad(gy, a, grads[p + ".mlp.fc2.weight"])
             ops.colsum_bf16(gy, grads[p + ".mlp.fc2.bias"])
-            da = torch.empty_like(a)
-            ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], da)
-            if rng:
+            if rng and drop > 0.0:       # dropout sits between the activation and fc2: its mask applies to da first
+                da = torch.empty_like(a)
+                ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], da)
                 ops.dropout_(da, T * hid, drop, seed, 8 * i + 2)
-            du = ops.gelu_bwd(da, u)
+                du = ops.gelu_bwd(da, u)
+            else:                        # fc2's input gradient and the activation's backward in one kernel
+                du = torch.empty_like(a)
+                ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], du, gelu_u=u)
             ops.linear_wgrad(du, h2, grads[p + ".mlp.fc1.weight"])
             ops.colsum_bf16(du, grads[p + ".mlp.fc1.bias"])
             dh2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)

@@ -10,6 +10,7 @@ from ._lib import HtrvtError, check, lib
 
 EPI_BF16, EPI_BIAS, _EPI_2, _EPI_3, EPI_ACCUM, EPI_STATS, _EPI_6, EPI_RELU = (1 << i for i in range(8))
 EPI_F16 = 1 << 10
+EPI_GELU = 1 << 12
 # storage format of the FORWARD stem tensors (activations, raw conv outputs, forward conv-weight copies): IEEE fp16 -
 # same 16 bits / tensor-core rate as bf16 with 3 more mantissa bits; gradients stay bf16
 STEM_DTYPE = torch.float16
@@ -57,26 +58,30 @@ def workspace(nbytes: int, device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # GEMMs
 # ------------------------------------------------------------------------------------------------
-def gemm_tn(x, w, out, *, bias=None, relu=False, accumulate=False, flags=0, alpha=1.0):
-    """out[M,N] (+)= epilogue(alpha * x[M,K] @ w[N,K]^T).  x, w bf16 row-major; out bf16 or fp32 [M, N] view."""
+def gemm_tn(x, w, out, *, bias=None, relu=False, accumulate=False, flags=0, alpha=1.0, gelu=False, pre=None):
+    """out[M,N] (+)= epilogue(alpha * x[M,K] @ w[N,K]^T).  x, w bf16 row-major; out bf16 or fp32 [M, N] view.
+    gelu: out = gelu(... + bias) (erf form, bf16 out); pre (bf16 [M,N]): also receives the pre-activation."""
     _need_cuda(x, w, out)
     M, K = x.shape
     N = w.shape[0]
     f = flags | (EPI_BF16 if out.dtype == torch.bfloat16 else 0) | (EPI_BIAS if bias is not None else 0) \
-        | (EPI_RELU if relu else 0) | (EPI_ACCUM if accumulate else 0)
+        | (EPI_RELU if relu else 0) | (EPI_ACCUM if accumulate else 0) | (EPI_GELU if gelu else 0)
     check(lib().htrvt_gemm_tn(_p(x), x.stride(0), _p(w), w.stride(0), M, N, K, f, _p(bias), _p(out), out.stride(0),
-                              alpha, _stream()), "htrvt_gemm_tn")
+                              alpha, _p(pre), pre.stride(0) if pre is not None else 0, _stream()), "htrvt_gemm_tn")
     return out
 
 
-def gemm_nn(dy, w, out, *, accumulate=False, alpha=1.0):
-    """out[M,N] (+)= dy[M,K] @ w[K,N]   (w row-major [K,N]: the nn.Linear weight itself for dgrad)."""
+def gemm_nn(dy, w, out, *, accumulate=False, alpha=1.0, gelu_u=None):
+    """out[M,N] (+)= dy[M,K] @ w[K,N]   (w row-major [K,N]: the nn.Linear weight itself for dgrad).
+    gelu_u (bf16 [M,N] contiguous): out = (dy @ w) * gelu'(gelu_u)."""
     _need_cuda(dy, w, out)
     M, K = dy.shape
     N = w.shape[1]
     f = (EPI_BF16 if out.dtype == torch.bfloat16 else 0) | (EPI_ACCUM if accumulate else 0)
+    if gelu_u is not None and (not gelu_u.is_contiguous() or gelu_u.shape != out.shape or not out.is_contiguous()):
+        raise HtrvtError("gemm_nn: gelu_u must be a contiguous bf16 [M, N] tensor like out")
     check(lib().htrvt_gemm_nn(_p(dy), dy.stride(0), _p(w), w.stride(0), M, N, K, f, _p(out), out.stride(0), alpha,
-                              _stream()), "htrvt_gemm_nn")
+                              _p(gelu_u), _stream()), "htrvt_gemm_nn")
     return out
 
 
@@ -363,13 +368,14 @@ def ctc_collapse(index_flat, lengths, n_character):
     B = int(ln_host.numel())
     Tmax = int(ln_host.max()) if B else 0
     ln = ln_host.to(device=dev, dtype=torch.int32)
+    offs = (torch.cumsum(ln_host, 0) - ln_host).to(device=dev, dtype=torch.int64)      # start of each line (one scan)
     idx = index_flat.contiguous()
     if idx.dtype not in (torch.int64, torch.int32):
         idx = idx.to(torch.int64)
     ids = torch.empty((B, max(Tmax, 1)), dtype=torch.int32, device=dev)
     lens = torch.empty(B, dtype=torch.int32, device=dev)
-    check(lib().htrvt_ctc_collapse(_p(idx), int(idx.dtype == torch.int64), _p(ln), B, max(Tmax, 1), n_character,
-                                   _p(ids), _p(lens), _stream()), "htrvt_ctc_collapse")
+    check(lib().htrvt_ctc_collapse(_p(idx), int(idx.dtype == torch.int64), _p(ln), _p(offs), B, max(Tmax, 1),
+                                   n_character, _p(ids), _p(lens), _stream()), "htrvt_ctc_collapse")
     return ids, lens
 
 

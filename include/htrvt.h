@@ -48,11 +48,12 @@ long long htrvt_ctc_fallback_count(void);
 /* ---- greedy CTC decode ---------------------------------------------------------------------------------
  * htrvt_greedy_decode replaces `preds.max(2)` + transpose (model_v1/valid.py:40-41) AND the filtering loop of
  * CTCLabelConverter.decode (model_v1/utils/utils.py:72-86): ids[b, 0:lens[b]] are the kept class ids.
- * htrvt_ctc_collapse takes the already arg-maxed sample-major index stream decode() receives. */
+ * htrvt_ctc_collapse takes the already arg-maxed sample-major index stream decode() receives; offsets = int64 [B]
+ * exclusive prefix sum of lengths (where each line starts in the stream). */
 int htrvt_greedy_decode(const float* logits, long long stride_b, long long stride_t, int B, int T, int C,
                         const int* lengths, int n_character, int* ids, int* lens, int* raw_index, void* stream);
-int htrvt_ctc_collapse(const void* index, int index_is_int64, const int* lengths, int B, int Tmax, int n_character,
-                       int* ids, int* lens, void* stream);
+int htrvt_ctc_collapse(const void* index, int index_is_int64, const int* lengths, const long long* offsets, int B,
+                       int Tmax, int n_character, int* ids, int* lens, void* stream);
 
 /* ---- K-best CTC alignment paths (LM-rescoring evaluation) ---------------------------------------------------
  * htrvt_ctc_kbest_paths replaces the per-frame beam of `simple_ctc_beam_search_with_lm`
@@ -71,11 +72,16 @@ int htrvt_ctc_kbest_paths(const float* log_probs, long long stride_b, long long 
  * htrvt_gemm_tn : Y = X W^T          nn.Linear fwd: attn.qkv / attn.proj (model_v1/model/HTR_VT.py:29,37),
  *                                    timm Mlp fc1 (+GELU) / fc2 (:76), head (:238)
  * htrvt_gemm_nn : dX = dY W          the same layers' input gradient (autograd of F.linear)
- * htrvt_linear_wgrad : dW (+)= dY^T X  the same layers' weight gradient, fp32, split-K workspace */
+ * htrvt_linear_wgrad : dW (+)= dY^T X  the same layers' weight gradient, fp32, split-K workspace
+ * Fused activation of timm Mlp (fc1 -> nn.GELU, erf form; model_v1/model/HTR_VT.py:76):
+ *   gemm_tn flags 4096: out = gelu(X W^T + bias) (bf16); `pre` (nullable bf16 [M,N], row stride ldp, N % 256 == 0)
+ *   additionally receives the pre-activation u (train mode: two TMA stores per epilogue box);
+ *   gemm_nn gelu_u (nullable, bf16 [M,N] contiguous): dX = (dY W) * gelu'(gelu_u) - fc2's input gradient and the
+ *   activation's backward in one kernel. */
 int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long long ldw, int M, int N, int K, int flags,
-                  const float* bias, void* out, long long ldo, float alpha, void* stream);
+                  const float* bias, void* out, long long ldo, float alpha, void* pre, long long ldp, void* stream);
 int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long long ldw, int M, int N, int K, int flags,
-                  void* out, long long ldo, float alpha, void* stream);
+                  void* out, long long ldo, float alpha, const void* gelu_u, void* stream);
 size_t htrvt_wgrad_workspace_bytes(int Cout, int Cin, int n_taps, int M_pixels);
 int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X, long long ldx, int M, int Nout, int Kin,
                        float* grad, int accumulate, void* workspace, size_t workspace_bytes, void* stream);

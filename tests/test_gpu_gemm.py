@@ -35,6 +35,42 @@ def test_gemm_tn_bias(M, N, K):
     assert _rel(out32, ref) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(16384, 3072, 768), (384, 1024, 256), (130, 256, 64), (256, 768, 256)])
+def test_gemm_fused_gelu_forward_and_backward(M, N, K):
+    """timm Mlp's fc1 -> nn.GELU (erf form) fused into the GEMM epilogue (model_v1/model/HTR_VT.py:76): single store
+    (eval), dual store with the pre-activation (train), and the activation's backward fused into fc2's input-gradient
+    GEMM: dX = (dY W) * gelu'(u)."""
+    o = ops()
+    torch.manual_seed(5)
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    b = torch.randn(N, device="cuda") * 0.5
+    u_ref = x.float() @ w.float().t() + b
+    a_ref = F.gelu(u_ref)
+    a1 = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    o.gemm_tn(x, w, a1, bias=b, gelu=True)                                  # eval: the activation only
+    assert _rel(a1, a_ref) < 1e-2
+    if N % 256 == 0:
+        a2 = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+        u2 = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+        o.gemm_tn(x, w, a2, bias=b, gelu=True, pre=u2)                      # train: activation + pre-activation
+        assert torch.equal(a1, a2)
+        assert _rel(u2, u_ref) < 1e-2
+    # backward: N here plays fc1's hidden width; dY [M, Kd] @ W2 [Kd, N]
+    Kd = 256
+    dy = torch.randn(M, Kd, device="cuda").bfloat16()
+    w2 = (torch.randn(Kd, N, device="cuda") / Kd ** 0.5).bfloat16()
+    u = (torch.randn(M, N, device="cuda") * 1.5).bfloat16()
+    uf = u.float().requires_grad_(True)
+    F.gelu(uf).backward(dy.float() @ w2.float())
+    du = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    o.gemm_nn(dy, w2, du, gelu_u=u)
+    assert _rel(du, uf.grad) < 1.5e-2
+    da = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    o.gemm_nn(dy, w2, da)
+    assert _rel(o.gelu_bwd(da, u), uf.grad) < 1.5e-2                         # the stand-alone pair agrees
+
+
 def test_gemm_tn_relu_accumulate():
     o = ops()
     torch.manual_seed(1)
