@@ -83,14 +83,24 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmP& P, int id) {
   return c;
 }
 
-template <int BN, int KIND, bool B_MN, int CL, bool RE = false, bool DUAL = false>
+// EPI: compile-time epilogue variant, so that the common epilogue carries none of the others' code or registers
+// (a runtime-flag version of the GELU / fp16 paths cost every KIND 0 kernel 15-40 % - measured):
+//   0 plain (bias / ReLU / residual / statistics / accumulate; bf16 or fp32 out)
+//   1 plain with IEEE fp16 output + residual (forward stem convolutions)
+//   2 gelu(acc + bias), bf16 out            3 the same + the pre-activation to a second tensor (DUAL)
+//   4 acc * gelu'(res), bf16 out (fc2 input gradient + activation backward)
+constexpr int kEpiPlain = 0, kEpiF16 = 1, kEpiGelu = 2, kEpiGeluDual = 3, kEpiGeluBwd = 4;
+template <int BN, int KIND, bool B_MN, int CL, bool RE = false, int EPI = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                const __grid_constant__ GemmP P) {
   constexpr bool W4 = (KIND == 4);
+  constexpr bool DUAL = (EPI == kEpiGeluDual), F16 = (EPI == kEpiF16);
+  constexpr bool GELU = (EPI == kEpiGelu || EPI == kEpiGeluDual), GELUB = (EPI == kEpiGeluBwd);
   using Cfg = GemmCfg<BN, CL, RE, W4, DUAL>;
-  static_assert(!DUAL || (KIND == 0 && !RE), "dual-output epilogue: linear forward only");
+  static_assert(EPI == 0 || KIND == 0, "epilogue variants exist for kind 0 only");
+  static_assert(!(GELU || GELUB) || !RE, "GELU epilogues: linear layers only");
   static_assert(!RE || (KIND == 0 && !B_MN && CL == 2), "window reuse: kind 0, K-major weights, CTA pairs");
   static_assert(!W4 || (B_MN && CL == 1 && !RE), "two-accumulator weight gradient: single CTA, MN-major operands");
   constexpr bool A_MN = (KIND == 1 || KIND == 3 || KIND == 4);
@@ -337,8 +347,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;                // column half handled by this warp
     const int r = quad * 32 + lane;          // tile row owned in the register phase
     constexpr int kColsPerWarp = BN / 2;
-    const bool out_bf16 = (P.flags & EPI_BF16) != 0;      // 16-bit output (bf16, or fp16 with EPI_F16)
-    const bool f16 = (P.flags & EPI_F16) != 0;
+    const bool out_bf16 = (EPI != kEpiPlain) || (P.flags & EPI_BF16) != 0;   // 16-bit output (bf16, or fp16 with EPI 1)
     const int box_cols = out_bf16 ? 32 : 16;
     uint8_t* stg = stage_out + ew * Cfg::kWarpStaging;      // 2 (DUAL: 2 x 2) x [32 rows][64 B], SWIZZLE_64B
     const int sw_r = (lane >> 1) & 3;
@@ -402,7 +411,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           uint4 rq[4] = {};
-          if (KIND == 0 && (P.flags & (EPI_RES | EPI_GELU_BWD))) {   // this thread's output pixel, 32 consecutive channels
+          if (KIND == 0 && (GELUB || (!GELU && (P.flags & EPI_RES)))) {   // this thread's output pixel, 32 consecutive channels
             const int w = tc.w0 + r;
             if (w < P.Wo && col < P.N_valid) {
               const uint4* rp = reinterpret_cast<const uint4*>(
@@ -417,20 +426,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; i += 2) {
             float a = __uint_as_float(raw[i]) * P.alpha, c = __uint_as_float(raw[i + 1]) * P.alpha;
             if (P.flags & EPI_BIAS) { a += bv[i]; c += bv[i + 1]; }
-            if (P.flags & EPI_GELU) {                        // timm Mlp: fc1 -> nn.GELU (erf form), fused
+            if (GELU) {                                      // timm Mlp: fc1 -> nn.GELU (erf form), fused
               if (DUAL) packed2[i >> 1] = pack_bf16(a, c);   // the pre-activation u, kept for the backward
               a = gelu_val(a); c = gelu_val(c);
             }
-            if (KIND == 0 && (P.flags & EPI_GELU_BWD)) {     // du = da * gelu'(u), u = the saved pre-activation
+            if (GELUB) {                                     // du = da * gelu'(u), u = the saved pre-activation
               const float2 uu = unpack_bf16(rw[i >> 1]);
               a *= gelu_grad(uu.x); c *= gelu_grad(uu.y);
             }
-            if (KIND == 0 && (P.flags & EPI_RES)) {
-              const float2 rr = f16 ? unpack_f16(rw[i >> 1]) : unpack_bf16(rw[i >> 1]);
+            if (KIND == 0 && !GELU && !GELUB && (P.flags & EPI_RES)) {
+              const float2 rr = F16 ? unpack_f16(rw[i >> 1]) : unpack_bf16(rw[i >> 1]);
               a += rr.x; c += rr.y;
             }
-            if (P.flags & EPI_RELU) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
-            packed[i >> 1] = f16 ? pack_f16(a, c) : pack_bf16(a, c);
+            if (!GELU && !GELUB && (P.flags & EPI_RELU)) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+            packed[i >> 1] = F16 ? pack_f16(a, c) : pack_bf16(a, c);
           }
         } else {
 #pragma unroll
@@ -495,7 +504,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int rr = 0; rr < 32; ++rr) {
             uint16_t hv;
             asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(base + rr * 64 + (((lane >> 3) ^ ((rr >> 1) & 3)) << 4)));
-            const float f = f16 ? f16_bits_to_float(hv) : __uint_as_float(static_cast<uint32_t>(hv) << 16);
+            const float f = F16 ? f16_bits_to_float(hv) : __uint_as_float(static_cast<uint32_t>(hv) << 16);
             sacc += f;
             qacc = fmaf(f, f, qacc);
           }
@@ -611,11 +620,11 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int KIND, bool B_MN, int CL, bool RE = false, bool DUAL = false>
+template <int BN, int KIND, bool B_MN, int CL, bool RE = false, int EPI = 0>
 int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
                cudaStream_t stream, const CUtensorMap* c2p = nullptr) {
-  using Cfg = GemmCfg<BN, CL, RE, KIND == 4, DUAL>;
-  auto kern = tapgemm_kernel<BN, KIND, B_MN, CL, RE, DUAL>;
+  using Cfg = GemmCfg<BN, CL, RE, KIND == 4, EPI == kEpiGeluDual>;
+  auto kern = tapgemm_kernel<BN, KIND, B_MN, CL, RE, EPI>;
   const CUtensorMap& c2 = c2p ? *c2p : c;
   if (!HTRVT_ENSURE_SMEM(kern, Cfg::kSmemBytes)) return HTRVT_ERR_LAUNCH;
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
@@ -639,21 +648,21 @@ int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
   return HTRVT_OK;
 }
 
-template <int KIND, bool B_MN>
+template <int KIND, bool B_MN, int EPI = 0>
 int launch_bn(int bn, int cl, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P,
               int total, cudaStream_t s) {
   if (cl == 2) {
     switch (bn) {
-      case 128: return launch_one<128, KIND, B_MN, 2>(a, b, c, P, total, s);
-      case 192: return launch_one<192, KIND, B_MN, 2>(a, b, c, P, total, s);
-      case 256: return launch_one<256, KIND, B_MN, 2>(a, b, c, P, total, s);
+      case 128: return launch_one<128, KIND, B_MN, 2, false, EPI>(a, b, c, P, total, s);
+      case 192: return launch_one<192, KIND, B_MN, 2, false, EPI>(a, b, c, P, total, s);
+      case 256: return launch_one<256, KIND, B_MN, 2, false, EPI>(a, b, c, P, total, s);
     }
     return HTRVT_ERR_SHAPE;
   }
   switch (bn) {
-    case 128: return launch_one<128, KIND, B_MN, 1>(a, b, c, P, total, s);
-    case 192: return launch_one<192, KIND, B_MN, 1>(a, b, c, P, total, s);
-    case 256: return launch_one<256, KIND, B_MN, 1>(a, b, c, P, total, s);
+    case 128: return launch_one<128, KIND, B_MN, 1, false, EPI>(a, b, c, P, total, s);
+    case 192: return launch_one<192, KIND, B_MN, 1, false, EPI>(a, b, c, P, total, s);
+    case 256: return launch_one<256, KIND, B_MN, 1, false, EPI>(a, b, c, P, total, s);
   }
   return HTRVT_ERR_SHAPE;
 }
@@ -669,10 +678,11 @@ bool use_window_reuse(int ks, int sw, int cl, int bn, int n_taps) {
   static const int off = dbg_env("HTRVT_NOREUSE");
   return !off && ks == 3 && sw == 1 && cl == 2 && n_taps >= 3 && (n_taps % 3) == 0 && (bn == 192 || bn == 256);
 }
+template <int EPI = 0>
 int launch_reuse(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total,
                  cudaStream_t s) {
-  if (bn == 192) return launch_one<192, 0, false, 2, true>(a, b, c, P, total, s);
-  return launch_one<256, 0, false, 2, true>(a, b, c, P, total, s);
+  if (bn == 192) return launch_one<192, 0, false, 2, true, EPI>(a, b, c, P, total, s);
+  return launch_one<256, 0, false, 2, true, EPI>(a, b, c, P, total, s);
 }
 
 // CTA pairs (cta_group::2) need tile pairs (2p, 2p+1) on the same n-tile: tiles_m even; an MN-major B operand is
@@ -737,7 +747,8 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
                              long long ldp, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (N & 3)) return HTRVT_ERR_SHAPE;
   if ((flags & EPI_GELU) && !(flags & EPI_BF16)) return HTRVT_ERR_SHAPE;
-  if (pre && (!(flags & EPI_GELU) || (N % 256) != 0 || (flags & EPI_ACCUM))) return HTRVT_ERR_SHAPE;
+  if ((flags & EPI_GELU) && ((N % 256) != 0 || (flags & (EPI_ACCUM | EPI_RELU)))) return HTRVT_ERR_SHAPE;
+  if (pre && !(flags & EPI_GELU)) return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(N);
   const int esz = (flags & EPI_BF16) ? 2 : 4;
   const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (N + bn - 1) / bn;
@@ -761,14 +772,20 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
   P.M_valid = M; P.N_valid = N;
   P.flags = (flags & (EPI_BF16 | EPI_BIAS | EPI_RELU | EPI_ACCUM | EPI_NOSTORE | EPI_GELU)) | (pre ? EPI_DUAL : 0);
   P.bias = bias; P.alpha = alpha;
+  const int total = P.tiles_m * P.tiles_n;
   if (pre) {                                               // N % 256 == 0 => bn == 256
     CUtensorMap tc2;
     int r = make_map_out(&tc2, pre, 2, N, M, 1, 1, ldp, ldp * M, ldp * M);
     if (r) return r;
-    if (cl == 2) return launch_one<256, 0, false, 2, false, true>(ta, tb, tc, P, P.tiles_m * P.tiles_n, stream, &tc2);
-    return launch_one<256, 0, false, 1, false, true>(ta, tb, tc, P, P.tiles_m * P.tiles_n, stream, &tc2);
+    if (cl == 2) return launch_one<256, 0, false, 2, false, kEpiGeluDual>(ta, tb, tc, P, total, stream, &tc2);
+    return launch_one<256, 0, false, 1, false, kEpiGeluDual>(ta, tb, tc, P, total, stream, &tc2);
   }
-  return launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+  if (flags & EPI_GELU) {
+    if (bn != 256) return HTRVT_ERR_SHAPE;                 // the fused activation is built for 256-column tiles
+    if (cl == 2) return launch_one<256, 0, false, 2, false, kEpiGelu>(ta, tb, tc, P, total, stream);
+    return launch_one<256, 0, false, 1, false, kEpiGelu>(ta, tb, tc, P, total, stream);
+  }
+  return launch_bn<0, false>(bn, cl, ta, tb, tc, P, total, stream);
 }
 
 // dX[M,N] = dY[M,K] W[K,N]: nn.Linear input gradient (B operand MN-major, no transpose copy).
@@ -778,7 +795,7 @@ extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long
                              int flags, void* out, long long ldo, float alpha, const void* gelu_u,
                              cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0 || (N & 7)) return HTRVT_ERR_SHAPE;
-  if (gelu_u && (!(flags & EPI_BF16) || (flags & EPI_ACCUM) || (N & 31) || (reinterpret_cast<uintptr_t>(gelu_u) & 15)))
+  if (gelu_u && (!(flags & EPI_BF16) || (flags & EPI_ACCUM) || (N % 256) || (reinterpret_cast<uintptr_t>(gelu_u) & 15)))
     return HTRVT_ERR_SHAPE;
   const int bn = pick_bn(N);
   const int esz = (flags & EPI_BF16) ? 2 : 4;
@@ -802,6 +819,10 @@ extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long
   P.n_taps = 1; P.splits = 1; P.k_chunks = (K + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = 0;
   P.M_valid = M; P.N_valid = N; P.flags = (flags & (EPI_BF16 | EPI_ACCUM | EPI_NOSTORE)) | (gelu_u ? EPI_GELU_BWD : 0);
   P.alpha = alpha; P.res = gelu_u;
+  if (gelu_u) {                                            // N % 256 == 0 => bn == 256
+    if (cl == 2) return launch_one<256, 0, true, 2, false, kEpiGeluBwd>(ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+    return launch_one<256, 0, true, 1, false, kEpiGeluBwd>(ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+  }
   return launch_bn<0, true>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
 
@@ -926,6 +947,10 @@ extern "C" int htrvt_conv_fwd(const void* x, int NB, int H, int W, int Cin, cons
   P.a_f16 = P.b_f16 = (flags & EPI_F16) ? 1 : 0;        // forward stem tensors: x, w, y (and res) are fp16
   if (y_f32) P.flags &= ~EPI_F16;                       // (the operand format stays in a_f16 / b_f16)
   P.stats = stats_partial; P.bias = bias; P.res = res; P.alpha = 1.f;
+  if ((P.flags & EPI_F16) != 0) {                          // fp16 output / residual: its own epilogue instantiation
+    if (reuse) return launch_reuse<kEpiF16>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+    return launch_bn<0, false, kEpiF16>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
+  }
   if (reuse) return launch_reuse(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
   return launch_bn<0, false>(bn, cl, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
