@@ -49,7 +49,7 @@ SIGNATURES = {
     "htrvt_ctc_collapse": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
     "htrvt_ctc_kbest_paths": (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "htrvt_gemm_tn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _L, _F, _P, _L, _P]),
-    "htrvt_gemm_nn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _F, _P, _P]),
+    "htrvt_gemm_nn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _F, _P, _P, _P]),
     "htrvt_wgrad_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "htrvt_linear_wgrad": (_I, [_P, _L, _P, _L, _I, _I, _I, _P, _I, _P, _Z, _P]),
     "htrvt_conv_fwd": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
@@ -73,6 +73,7 @@ SIGNATURES = {
     "htrvt_colsum_rows": (_I, [_I]),
     "htrvt_colsum_bf16": (_I, [_P, _L, _I, _I, _P, _I, _P, _P]),
     "htrvt_cast_bf16": (_I, [_P, _P, _L, _P]),
+    "htrvt_cast_colsum_bf16": (_I, [_P, _P, _P, _I, _I, _P]),
     "htrvt_dropout_bf16": (_I, [_P, _L, _L, _F, ctypes.c_ulonglong, ctypes.c_uint, _P, _P]),
     "htrvt_pack_weights": (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "htrvt_pack_conv_weight": (_I, [_P, _P, _I, _I, _I, _P]),

@@ -354,15 +354,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int sbuf = 0;
     float ssum[4] = {0.f, 0.f, 0.f, 0.f}, qsum[4] = {0.f, 0.f, 0.f, 0.f};
     int stats_ntile = -1;
+    // GELUB + EPI_COLSUM: column sums of the stored tile go straight into P.stats[N] (+=, atomics): fc1's bias gradient
+    const bool colsum = GELUB && (P.flags & EPI_COLSUM) != 0;
     auto flush_stats = [&](int n_tile) {
       if (n_tile < 0) return;
-      float* dst = P.stats + static_cast<long long>(blockIdx.x * 4 + quad) * 2 * P.N_valid;
+      float* dst = P.stats + (colsum ? 0ll : static_cast<long long>(blockIdx.x * 4 + quad) * 2 * P.N_valid);
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int col = n_tile * BN + half * kColsPerWarp + b * 32 + lane;
         if (b * 32 < kColsPerWarp && col < P.N_valid) {
-          dst[col] += ssum[b];
-          dst[P.N_valid + col] += qsum[b];
+          if (colsum) {
+            atomicAdd(dst + col, ssum[b]);
+          } else {
+            dst[col] += ssum[b];
+            dst[P.N_valid + col] += qsum[b];
+          }
         }
         ssum[b] = 0.f; qsum[b] = 0.f;
       }
@@ -371,7 +377,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int id = first_tile; id < total_tiles; id += tile_step) {
       const TileCoord tc = decode_tile(P, id);
       const int n0 = tc.n_tile * BN;
-      if ((P.flags & EPI_STATS) && tc.n_tile != stats_ntile) { flush_stats(stats_ntile); stats_ntile = tc.n_tile; }
+      if (((P.flags & EPI_STATS) || colsum) && tc.n_tile != stats_ntile) { flush_stats(stats_ntile); stats_ntile = tc.n_tile; }
 #pragma unroll 1
       for (int sub = 0; sub < (W4 ? 2 : 1); ++sub) {          // KIND 4: a unit = two accumulators = two 128-row tiles
       const int m_tile = W4 ? 2 * tc.m_tile + sub : tc.m_tile;
@@ -495,7 +501,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (possibly empty) keeps the buffer <-> group pairing
         }
-        if (P.flags & EPI_STATS) {
+        if ((P.flags & EPI_STATS) || colsum) {
           // column `lane` of this warp's 32 staged rows (bf16 box = 32 columns); rows outside the image are
           // exact zeros (their A rows were TMA zero-filled and convolutions carry no bias)
           float sacc = 0.f, qacc = 0.f;
@@ -516,7 +522,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       as ^= 1; if (as == 0) aphase ^= 1;
       }
     }
-    if (P.flags & EPI_STATS) flush_stats(stats_ntile);
+    if ((P.flags & EPI_STATS) || colsum) flush_stats(stats_ntile);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
@@ -791,9 +797,11 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
 // dX[M,N] = dY[M,K] W[K,N]: nn.Linear input gradient (B operand MN-major, no transpose copy).
 // gelu_u (nullable, bf16 [M, N] contiguous): dX = (dY W) * gelu'(gelu_u) - the backward of timm Mlp's activation fused
 // into fc2's input-gradient GEMM (gelu_u = fc1's saved pre-activation).
+// colsum (nullable, with gelu_u): fp32 [N] += column sums of the stored dX - fc1's bias gradient from the same epilogue.
 extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long long ldw, int M, int N, int K,
-                             int flags, void* out, long long ldo, float alpha, const void* gelu_u,
+                             int flags, void* out, long long ldo, float alpha, const void* gelu_u, float* colsum,
                              cudaStream_t stream) {
+  if (colsum && !gelu_u) return HTRVT_ERR_SHAPE;
   if (M <= 0 || N <= 0 || K <= 0 || (N & 7)) return HTRVT_ERR_SHAPE;
   if (gelu_u && (!(flags & EPI_BF16) || (flags & EPI_ACCUM) || (N % 256) || (reinterpret_cast<uintptr_t>(gelu_u) & 15)))
     return HTRVT_ERR_SHAPE;
@@ -817,8 +825,9 @@ extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long
   P.kind = 0; P.Wo = M; P.Ho = 1; P.NB = 1;
   P.tiles_per_row = tiles_m; P.tiles_m = tiles_m; P.tiles_n = tiles_n;
   P.n_taps = 1; P.splits = 1; P.k_chunks = (K + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = 0;
-  P.M_valid = M; P.N_valid = N; P.flags = (flags & (EPI_BF16 | EPI_ACCUM | EPI_NOSTORE)) | (gelu_u ? EPI_GELU_BWD : 0);
-  P.alpha = alpha; P.res = gelu_u;
+  P.M_valid = M; P.N_valid = N;
+  P.flags = (flags & (EPI_BF16 | EPI_ACCUM | EPI_NOSTORE)) | (gelu_u ? EPI_GELU_BWD : 0) | (colsum ? EPI_COLSUM : 0);
+  P.alpha = alpha; P.res = gelu_u; P.stats = colsum;
   if (gelu_u) {                                            // N % 256 == 0 => bn == 256
     if (cl == 2) return launch_one<256, 0, true, 2, false, kEpiGeluBwd>(ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
     return launch_one<256, 0, true, 1, false, kEpiGeluBwd>(ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);

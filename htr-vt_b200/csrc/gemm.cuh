@@ -23,6 +23,7 @@ enum : int {
   EPI_GELU = 1 << 12,      // bf16 out: out = gelu(acc * alpha + bias) (erf form) - timm Mlp fc1 -> act
   EPI_DUAL = 1 << 13,      // with EPI_GELU (kernel built with DUAL): the pre-activation goes to a second output (tmC2)
   EPI_GELU_BWD = 1 << 14,  // bf16 out, kind 0: out = acc * gelu'(res[row, col]) (res = the saved pre-activation u)
+  EPI_COLSUM = 1 << 15,    // with EPI_GELU_BWD: stats[N] += column sums of the stored tile (bias gradient)
 };
 
 struct GemmP {

@@ -352,6 +352,51 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);
 }
+// dst = bf16(src) for a row-major [M, N] fp32 matrix AND colsum[n] += sum_m dst[m, n] (of the rounded values): the
+// residual-stream gradient becomes the bf16 dY of fc2 / proj and their bias gradients in one pass (the separate
+// column-sum kernel re-read the bf16 copy).  Thread -> 8 consecutive columns, row lanes strided; N % 8 == 0.
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                          float* __restrict__ colsum, int M, int N, int rows_per_cta) {
+  extern __shared__ float cs_sm[];                       // [R][N]
+  const int G = N / 8, R = blockDim.x / G;
+  const int grp = threadIdx.x % G, lane_r = threadIdx.x / G;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (lane_r < R) {
+    for (int r = r0 + lane_r; r < r1; r += 2 * R) {
+      float4 v[2][2];
+      const bool two = r + R < r1;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float* p = src + static_cast<long long>(r + u * R) * N + grp * 8;
+        const bool ok = u == 0 || two;
+        v[u][0] = ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u][1] = ok ? __ldg(reinterpret_cast<const float4*>(p) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        uint4 o;
+        o.x = pack_bf16(v[u][0].x, v[u][0].y); o.y = pack_bf16(v[u][0].z, v[u][0].w);
+        o.z = pack_bf16(v[u][1].x, v[u][1].y); o.w = pack_bf16(v[u][1].z, v[u][1].w);
+        *reinterpret_cast<uint4*>(dst + static_cast<long long>(r + u * R) * N + grp * 8) = o;
+        float2 t;
+        t = unpack_bf16(o.x); acc[0] += t.x; acc[1] += t.y;
+        t = unpack_bf16(o.y); acc[2] += t.x; acc[3] += t.y;
+        t = unpack_bf16(o.z); acc[4] += t.x; acc[5] += t.y;
+        t = unpack_bf16(o.w); acc[6] += t.x; acc[7] += t.y;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cs_sm[lane_r * N + grp * 8 + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    float s = 0.f;
+    for (int rr = 0; rr < R; ++rr) s += cs_sm[rr * N + c];
+    atomicAdd(colsum + c, s);
+  }
+}
 // OIHW fp32 [Cout, Cin, taps] -> bf16 [Cout, taps, Cin]
 __global__ void pack_conv_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cout,
                                         int Cin, int taps) {
@@ -654,6 +699,21 @@ extern "C" int htrvt_colsum_bf16(const void* a, long long ld, int M, int N, floa
 extern "C" int htrvt_cast_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
   if (n <= 0) return HTRVT_ERR_SHAPE;
   cast_bf16_kernel<<<grid_for(n, 256), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+// dst bf16 [M, N] = bf16(src fp32 [M, N]); colsum fp32 [N] += column sums of dst (N % 8 == 0, N <= 2048)
+extern "C" int htrvt_cast_colsum_bf16(const float* src, void* dst, float* colsum, int M, int N, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || (N & 7) || N > 2048 || !src || !dst || !colsum) return HTRVT_ERR_SHAPE;
+  const int G = N / 8;
+  const int R = 256 / G;                      // >= 1 for N <= 2048
+  const int threads = G * R;
+  int ctas = (M + 31) / 32;
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  const int rows = (M + ctas - 1) / ctas;
+  cast_colsum_kernel<<<ctas, threads, static_cast<size_t>(R) * N * sizeof(float), stream>>>(
+      src, static_cast<__nv_bfloat16*>(dst), colsum, M, N, rows);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }

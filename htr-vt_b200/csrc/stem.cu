@@ -403,71 +403,50 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const 
   }
 }
 
-// stage 2: dgamma += sum g' xhat, dbeta += sum g'; per-channel affine coefficients of stage 3:
+// stage 2 (inside the apply kernel): dgamma += sum g' xhat, dbeta += sum g'; per-channel affine coefficients of stage 3:
 //   d_raw = gamma*rstd*(g' - k1 - xhat*k2) = A*g' + Bc*raw + Cc,  k1 = sum g'/N, k2 = sum g' xhat / N,
-//   A = gamma*rstd, Bc = -A*rstd*k2, Cc = -A*k1 + A*rstd*k2*mean.         coef layout [3][C]
-__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int R, double count, int C,
-                                       const float* __restrict__ gamma_a, const float* __restrict__ mean_a,
-                                       const float* __restrict__ rstd_a, float* __restrict__ coef_a,
-                                       float* __restrict__ dgamma_a, float* __restrict__ dbeta_a,
-                                       const float* __restrict__ gamma_b, const float* __restrict__ mean_b,
-                                       const float* __restrict__ rstd_b, float* __restrict__ coef_b,
-                                       float* __restrict__ dgamma_b, float* __restrict__ dbeta_b) {
-  __shared__ double sh[3][32][32];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lr = threadIdx.x >> 5;      // 32 channels x 32 row lanes
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  if (c < C) {
-    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
-    int r = lr;
-    for (; r + 96 < R; r += 128) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float* p = partial + static_cast<long long>(r + 32 * u) * 3 * C;
-        a0[u] += p[c]; a1[u] += p[C + c]; a2[u] += p[2 * C + c];
-      }
-    }
-    for (; r < R; r += 32) {
-      const float* p = partial + static_cast<long long>(r) * 3 * C;
-      a0[0] += p[c]; a1[0] += p[C + c]; a2[0] += p[2 * C + c];
-    }
-    s0 = (static_cast<double>(a0[0]) + a0[1]) + (static_cast<double>(a0[2]) + a0[3]);
-    s1 = (static_cast<double>(a1[0]) + a1[1]) + (static_cast<double>(a1[2]) + a1[3]);
-    s2 = (static_cast<double>(a2[0]) + a2[1]) + (static_cast<double>(a2[2]) + a2[3]);
-  }
-  sh[0][lr][threadIdx.x & 31] = s0; sh[1][lr][threadIdx.x & 31] = s1; sh[2][lr][threadIdx.x & 31] = s2;
-  __syncthreads();
-  if (lr != 0 || c >= C) return;
-  s0 = s1 = s2 = 0.0;
-  for (int k = 0; k < 32; ++k) { s0 += sh[0][k][threadIdx.x]; s1 += sh[1][k][threadIdx.x]; s2 += sh[2][k][threadIdx.x]; }
-  {
-    const float k1 = static_cast<float>(s0 / count), k2 = static_cast<float>(s1 / count);
-    const float A = gamma_a[c] * rstd_a[c];
-    coef_a[c] = A;
-    coef_a[C + c] = -A * rstd_a[c] * k2;
-    coef_a[2 * C + c] = -A * k1 + A * rstd_a[c] * k2 * mean_a[c];
-    if (dgamma_a) { dgamma_a[c] += static_cast<float>(s1); dbeta_a[c] += static_cast<float>(s0); }
-  }
-  if (coef_b) {
-    const float k1 = static_cast<float>(s0 / count), k2 = static_cast<float>(s2 / count);
-    const float A = gamma_b[c] * rstd_b[c];
-    coef_b[c] = A;
-    coef_b[C + c] = -A * rstd_b[c] * k2;
-    coef_b[2 * C + c] = -A * k1 + A * rstd_b[c] * k2 * mean_b[c];
-    if (dgamma_b) { dgamma_b[c] += static_cast<float>(s2); dbeta_b[c] += static_cast<float>(s0); }
-  }
-}
-
+//   A = gamma*rstd, Bc = -A*rstd*k2, Cc = -A*k1 + A*rstd*k2*mean.
 // stage 3: d_raw = A*g' + Bc*raw + Cc for one or two BNs; optional gz = g' (identity-residual gradient)
 __device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
   *reinterpret_cast<float4*>(f) = *reinterpret_cast<const float4*>(p);
   *reinterpret_cast<float4*>(f + 4) = *reinterpret_cast<const float4*>(p + 4);
 }
+// The per-channel coefficients (stage 2 above) are recomputed by every CTA from the [3][C] sums into shared memory -
+// a few flops per channel - so no finalise launch sits between the reduction and this pass; CTA 0 also accumulates
+// dgamma / dbeta.
+struct BnBwdSide {
+  const float* gamma; const float* mean; const float* rstd; float* dgamma; float* dbeta;
+};
 template <bool F16>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ mask, const __nv_bfloat16* __restrict__ raw_a,
-    const float* __restrict__ coef_a, __nv_bfloat16* __restrict__ d_a, const __nv_bfloat16* __restrict__ raw_b,
-    const float* __restrict__ coef_b, __nv_bfloat16* __restrict__ d_b, __nv_bfloat16* __restrict__ gz, long long n8,
-    int C) {
+    const float* __restrict__ sums, double count, BnBwdSide sa, __nv_bfloat16* __restrict__ d_a,
+    const __nv_bfloat16* __restrict__ raw_b, BnBwdSide sb, __nv_bfloat16* __restrict__ d_b,
+    __nv_bfloat16* __restrict__ gz, long long n8, int C) {
+  extern __shared__ float coef_sm[];                    // [2][3][C]: A, Bc, Cc of BN a and BN b
+  float* coef_a = coef_sm;
+  float* coef_b = coef_sm + 3 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float s0 = sums[c], s1 = sums[C + c], s2 = sums[2 * C + c];
+    const float k1 = static_cast<float>(static_cast<double>(s0) / count);
+    {
+      const float k2 = static_cast<float>(static_cast<double>(s1) / count);
+      const float A = sa.gamma[c] * sa.rstd[c];
+      coef_a[c] = A;
+      coef_a[C + c] = -A * sa.rstd[c] * k2;
+      coef_a[2 * C + c] = -A * k1 + A * sa.rstd[c] * k2 * sa.mean[c];
+      if (blockIdx.x == 0 && sa.dgamma) { sa.dgamma[c] += s1; sa.dbeta[c] += s0; }
+    }
+    if (raw_b) {
+      const float k2 = static_cast<float>(static_cast<double>(s2) / count);
+      const float A = sb.gamma[c] * sb.rstd[c];
+      coef_b[c] = A;
+      coef_b[C + c] = -A * sb.rstd[c] * k2;
+      coef_b[2 * C + c] = -A * k1 + A * sb.rstd[c] * k2 * sb.mean[c];
+      if (blockIdx.x == 0 && sb.dgamma) { sb.dgamma[c] += s2; sb.dbeta[c] += s0; }
+    }
+  }
+  __syncthreads();
   const int G = C / 8;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < n8; i0 += 2 * stride) {
@@ -679,7 +658,8 @@ extern "C" int htrvt_bn_bwd_ctas(long long P) {
 // upstream gradient: the downsample branch).  g: gradient w.r.t. the post-activation output; `mask` (optional) holds
 // the ReLU mask bits written by htrvt_bn_act_fwd (1 byte per 8 channels).  Writes d_a (/d_b) = gradient w.r.t. the raw conv outputs, accumulates
 // dgamma / dbeta, optionally writes gz = masked g (identity-residual gradient).
-// partial: fp32 [htrvt_bn_bwd_ctas(P)][3][C]; coef: fp32 [2][3][C] scratch.
+// partial: fp32 [3][C] column sums, ZEROED by the caller (two launches: reduce -> apply; the apply pass derives the
+// per-channel coefficients itself); coef: unused, kept for ABI stability.
 extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, const float* mean_a,
                             const float* rstd_a, const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a,
                             const void* raw_b, const float* mean_b, const float* rstd_b, const float* gamma_b,
@@ -699,24 +679,20 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, 
   auto k_reduce = raw_f16 ? bn_bwd_reduce_kernel<true> : bn_bwd_reduce_kernel<false>;
   auto k_apply = raw_f16 ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>;
   if (smem > 96 * 1024) return HTRVT_ERR_SHAPE;
-  if (cudaMemsetAsync(partial, 0, static_cast<size_t>(3) * C * sizeof(float), stream) != cudaSuccess)
-    return HTRVT_ERR_LAUNCH;
+  // partial: [3][C] sums, ZERO on entry (the caller hands out slices of one buffer it cleared once per backward)
   k_reduce<<<ctas, threads, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(g), static_cast<const uint8_t*>(mask),
       static_cast<const __nv_bfloat16*>(raw_a), mean_a, rstd_a, static_cast<const __nv_bfloat16*>(raw_b), mean_b,
       rstd_b, partial, P, C, rows);
   HTRVT_LAUNCH_CHECK();
-  float* coef_a = coef;
-  float* coef_b = raw_b ? coef + 3 * C : nullptr;
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 1024, 0, stream>>>(partial, 1, static_cast<double>(P), C, gamma_a, mean_a,
-                                                             rstd_a, coef_a, dgamma_a, dbeta_a, gamma_b, mean_b, rstd_b,
-                                                             coef_b, dgamma_b, dbeta_b);
-  HTRVT_LAUNCH_CHECK();
+  (void)coef;
   const long long n8 = P * C / 8;
-  k_apply<<<grid_for(n8, 256), 256, 0, stream>>>(
+  const BnBwdSide sa = {gamma_a, mean_a, rstd_a, dgamma_a, dbeta_a};
+  const BnBwdSide sb = {gamma_b, mean_b, rstd_b, dgamma_b, dbeta_b};
+  k_apply<<<grid_for(n8, 256), 256, static_cast<size_t>(6) * C * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(g), static_cast<const uint8_t*>(mask),
-      static_cast<const __nv_bfloat16*>(raw_a), coef_a, static_cast<__nv_bfloat16*>(d_a),
-      static_cast<const __nv_bfloat16*>(raw_b), coef_b, static_cast<__nv_bfloat16*>(d_b),
+      static_cast<const __nv_bfloat16*>(raw_a), partial, static_cast<double>(P), sa, static_cast<__nv_bfloat16*>(d_a),
+      static_cast<const __nv_bfloat16*>(raw_b), sb, static_cast<__nv_bfloat16*>(d_b),
       static_cast<__nv_bfloat16*>(gz), n8, C);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;

@@ -394,11 +394,14 @@ class Engine(object):
         for (i, p, x1, h1, m1, r1s, qkv, o, lse, x2, h2, m2, r2s, a, u) in reversed(ctx.tblocks):
             dp1, dp2 = rng["drop_path"][i] if rng else (None, None)
             hid = a.shape[1]
-            gy = ops.cast_bf16(gx)
-            if rng:                      # same counter-based masks as the forward
+            if rng and (drop > 0.0 or dp2 is not None):   # same counter-based masks as the forward
+                gy = ops.cast_bf16(gx)
                 ops.dropout_(gy, T * D, drop, seed, 8 * i + 3, dp2)
+                ops.colsum_bf16(gy, grads[p + ".mlp.fc2.bias"])
+            else:                        # bf16 dY of fc2 and fc2's bias gradient in one pass over the residual gradient
+                gy = ops.cast_colsum_bf16(gx, grads[p + ".mlp.fc2.bias"])
             ops.linear_wgrad(gy, a, grads[p + ".mlp.fc2.weight"])
-            ops.colsum_bf16(gy, grads[p + ".mlp.fc2.bias"])
+            fused_bias = False
             if rng and drop > 0.0:       # dropout sits between the activation and fc2: its mask applies to da first
                 da = torch.empty_like(a)
                 ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], da)
@@ -406,18 +409,22 @@ class Engine(object):
                 du = ops.gelu_bwd(da, u)
             else:                        # fc2's input gradient and the activation's backward in one kernel
                 du = torch.empty_like(a)
-                ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], du, gelu_u=u)
+                ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], du, gelu_u=u, colsum=grads[p + ".mlp.fc1.bias"])
+                fused_bias = True
             ops.linear_wgrad(du, h2, grads[p + ".mlp.fc1.weight"])
-            ops.colsum_bf16(du, grads[p + ".mlp.fc1.bias"])
+            if not fused_bias:
+                ops.colsum_bf16(du, grads[p + ".mlp.fc1.bias"])
             dh2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
             ops.gemm_nn(du, wp[p + ".mlp.fc1.weight"], dh2)
             ops.row_ln_bwd(dh2, x2, m2, r2s, sd[p + ".norm2.weight"], gx, True, grads[p + ".norm2.weight"],
                            grads[p + ".norm2.bias"])
-            gy = ops.cast_bf16(gx)
-            if rng:
+            if rng and (drop > 0.0 or dp1 is not None):
+                gy = ops.cast_bf16(gx)
                 ops.dropout_(gy, T * D, drop, seed, 8 * i + 1, dp1)
+                ops.colsum_bf16(gy, grads[p + ".attn.proj.bias"])
+            else:
+                gy = ops.cast_colsum_bf16(gx, grads[p + ".attn.proj.bias"])
             ops.linear_wgrad(gy, o, grads[p + ".attn.proj.weight"])
-            ops.colsum_bf16(gy, grads[p + ".attn.proj.bias"])
             do = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
             ops.gemm_nn(gy, wp[p + ".attn.proj.weight"], do)
             dqkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
@@ -474,17 +481,27 @@ class Engine(object):
                 ops.conv_wgrad_acc_t(dy, x, ks, sh, sw, gt[name])
             else:
                 ops.conv_wgrad_acc(dy, x, ks, sh, sw, gt[name])
+        # [3][C] reduction targets of the 12 BatchNorm backward passes: one zeroed buffer per backward
+        zs_total = sum(2 * 3 * blk[3].shape[-1] for blk in ctx.blocks)
+        zs_pool, zs_off = torch.zeros(zs_total, dtype=torch.float32, device=dev), 0
+
+        def zsum(C):
+            nonlocal zs_off
+            v = zs_pool[zs_off:zs_off + 3 * C]
+            zs_off += 3 * C
+            return v
         for (p, s, xin, r1, sa, a1, k1, r2, sb, rd, sdn, k2) in reversed(ctx.blocks):
             has_ds = rd is not None
             d2, dd, gz = ops.bn_bwd(
                 g, k2, r2, sb, sd[p + ".bn2.weight"], grads[p + ".bn2.weight"], grads[p + ".bn2.bias"],
                 raw_b=rd, st_b=sdn, gamma_b=sd[p + ".downsample.1.weight"] if has_ds else None,
                 dgamma_b=grads[p + ".downsample.1.weight"] if has_ds else None,
-                dbeta_b=grads[p + ".downsample.1.bias"] if has_ds else None, want_gz=not has_ds)
+                dbeta_b=grads[p + ".downsample.1.bias"] if has_ds else None, want_gz=not has_ds,
+                zero_sums=zsum(r2.shape[-1]))
             wgrad(d2, a1, 3, 1, 1, p + ".conv2.weight")
             da1 = ops.conv_dgrad(d2, wp[p + ".conv2.weight"], tuple(a1.shape), 3, 1, 1, w_t=wp.get("T:" + p + ".conv2.weight"))
             d1, _, _ = ops.bn_bwd(da1, k1, r1, sa, sd[p + ".bn1.weight"], grads[p + ".bn1.weight"],
-                                  grads[p + ".bn1.bias"])
+                                  grads[p + ".bn1.bias"], zero_sums=zsum(r1.shape[-1]))
             wgrad(d1, xin, 3, s[0], s[1], p + ".conv1.weight")
             if has_ds:
                 gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1],

@@ -71,9 +71,10 @@ def gemm_tn(x, w, out, *, bias=None, relu=False, accumulate=False, flags=0, alph
     return out
 
 
-def gemm_nn(dy, w, out, *, accumulate=False, alpha=1.0, gelu_u=None):
+def gemm_nn(dy, w, out, *, accumulate=False, alpha=1.0, gelu_u=None, colsum=None):
     """out[M,N] (+)= dy[M,K] @ w[K,N]   (w row-major [K,N]: the nn.Linear weight itself for dgrad).
-    gelu_u (bf16 [M,N] contiguous): out = (dy @ w) * gelu'(gelu_u)."""
+    gelu_u (bf16 [M,N] contiguous): out = (dy @ w) * gelu'(gelu_u); colsum (fp32 [N], with gelu_u) += column sums of
+    out (the bias gradient of the layer in front of the activation)."""
     _need_cuda(dy, w, out)
     M, K = dy.shape
     N = w.shape[1]
@@ -81,7 +82,7 @@ def gemm_nn(dy, w, out, *, accumulate=False, alpha=1.0, gelu_u=None):
     if gelu_u is not None and (not gelu_u.is_contiguous() or gelu_u.shape != out.shape or not out.is_contiguous()):
         raise HtrvtError("gemm_nn: gelu_u must be a contiguous bf16 [M, N] tensor like out")
     check(lib().htrvt_gemm_nn(_p(dy), dy.stride(0), _p(w), w.stride(0), M, N, K, f, _p(out), out.stride(0), alpha,
-                              _p(gelu_u), _stream()), "htrvt_gemm_nn")
+                              _p(gelu_u), _p(colsum), _stream()), "htrvt_gemm_nn")
     return out
 
 
@@ -517,6 +518,14 @@ def cast_bf16(src, dst=None):
     return dst
 
 
+def cast_colsum_bf16(src, colsum):
+    """-> bf16 copy of src fp32 [M, N]; colsum fp32 [N] += its column sums (bias gradient of the layer whose dY it is)."""
+    M, N = src.shape
+    dst = torch.empty((M, N), dtype=torch.bfloat16, device=src.device)
+    check(lib().htrvt_cast_colsum_bf16(_p(src), _p(dst), _p(colsum), M, N, _stream()), "htrvt_cast_colsum_bf16")
+    return dst
+
+
 def pack_conv_weight(w, dst=None):
     """fp32 OIHW -> bf16 [Cout, kh*kw, Cin]."""
     Cout, Cin, kh, kw = w.shape
@@ -633,7 +642,7 @@ def pool_bwd(gout, idx, in_shape, raw=None, st=None):
 
 
 def bn_bwd(g, mask, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=None, gamma_b=None, dgamma_b=None,
-           dbeta_b=None, want_gz=False):
+           dbeta_b=None, want_gz=False, zero_sums=None):
     """-> (d_a, d_b | None, gz | None), all bf16 with the shape of raw_a.  g bf16; raw_a / raw_b in the forward
     stem's format (fp16, or bf16)."""
     C = raw_a.shape[-1]
@@ -644,9 +653,10 @@ def bn_bwd(g, mask, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=No
     gz = torch.empty(raw_a.shape, dtype=torch.bfloat16, device=dev) if want_gz else None
     if g.dtype != torch.bfloat16 or (raw_b is not None and raw_b.dtype != raw_a.dtype):
         raise HtrvtError("bn_bwd: gradient must be bf16, raw_a / raw_b one format")
-    ctas = lib().htrvt_bn_bwd_ctas(P)
-    partial = workspace(ctas * 3 * C * 4 + 6 * C * 4, dev)
-    coef = partial[ctas * 3 * C * 4:]
+    if zero_sums is None:                 # [3, C] fp32 zeros (engine: slices of one buffer cleared once per backward)
+        zero_sums = torch.zeros(3 * C, dtype=torch.float32, device=dev)
+    partial = zero_sums
+    coef = None
     z = None
     check(lib().htrvt_bn_bwd(_p(g), _p(mask), _p(raw_a), _p(st_a[0]), _p(st_a[1]), _p(gamma_a), _p(dgamma_a),
                              _p(dbeta_a), _p(d_a), _p(raw_b), _p(st_b[0] if st_b is not None else z),
@@ -863,7 +873,7 @@ def _instrument():
     g = globals()
     names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc", "conv_wgrad_acc_t", "conv_wgrad_acc_w", "unpack_conv_grads", "attention_fwd",
              "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "ctc_kbest_paths", "sample_ln_fwd", "sample_ln_bwd", "line_prep_u8", "edit_distance",
-             "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16", "dropout_",
+             "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16", "cast_colsum_bf16", "dropout_",
              "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",
              "conv1_wgrad", "stem_head_moments", "stem_head_fwd", "stem_head_bwd"]
     for name in names:

@@ -81,7 +81,8 @@ int htrvt_ctc_kbest_paths(const float* log_probs, long long stride_b, long long 
 int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long long ldw, int M, int N, int K, int flags,
                   const float* bias, void* out, long long ldo, float alpha, void* pre, long long ldp, void* stream);
 int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long long ldw, int M, int N, int K, int flags,
-                  void* out, long long ldo, float alpha, const void* gelu_u, void* stream);
+                  void* out, long long ldo, float alpha, const void* gelu_u, float* colsum /*nullable: fp32 [N] +=
+                  column sums of dX (with gelu_u): fc1's bias gradient*/, void* stream);
 size_t htrvt_wgrad_workspace_bytes(int Cout, int Cin, int n_taps, int M_pixels);
 int htrvt_linear_wgrad(const void* dY, long long lddy, const void* X, long long ldx, int M, int Nout, int Kin,
                        float* grad, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
@@ -177,6 +178,9 @@ int htrvt_colsum_rows(int M);
 int htrvt_colsum_bf16(const void* a, long long ld, int M, int N, float* out, int accumulate, float* partial,
                       void* stream);
 int htrvt_cast_bf16(const float* src, void* dst, long long n, void* stream);
+/* dst bf16 [M,N] = bf16(src); colsum fp32 [N] += column sums of dst: the residual-stream gradient becomes fc2's /
+ * proj's dY and their bias gradients in one pass (N % 8 == 0, N <= 2048) */
+int htrvt_cast_colsum_bf16(const float* src, void* dst, float* colsum, int M, int N, void* stream);
 /* in-place inverted dropout (+ per-sample DropPath scale dp[b], nullable) on bf16 x[n]; counter-based mask keyed by
  * (seed, site, element index): the same call on the gradient regenerates the mask.  Replaces nn.Dropout / timm
  * DropPath of model_window (model_window/model/HTR_VT.py:21-23, 100-110, 263-273) in train mode. */

@@ -64,8 +64,10 @@ def test_gemm_fused_gelu_forward_and_backward(M, N, K):
     uf = u.float().requires_grad_(True)
     F.gelu(uf).backward(dy.float() @ w2.float())
     du = torch.full((M, N), 7.0, device="cuda", dtype=torch.bfloat16)
-    o.gemm_nn(dy, w2, du, gelu_u=u)
+    bias_grad = torch.ones(N, device="cuda")
+    o.gemm_nn(dy, w2, du, gelu_u=u, colsum=bias_grad)                       # + fc1's bias gradient from the epilogue
     assert _rel(du, uf.grad) < 1.5e-2
+    assert _rel(bias_grad - 1.0, du.float().sum(0)) < 1e-4
     da = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     o.gemm_nn(dy, w2, da)
     assert _rel(o.gelu_bwd(da, u), uf.grad) < 1.5e-2                         # the stand-alone pair agrees

@@ -257,3 +257,14 @@ def test_stem_head_fused(B, H, W, C, fwd):
     assert _rel(dw, w.grad) < 2e-3
     o.stem_head_bwd(g_nhwc, code, x3, w.detach(), moments, gamma.detach(), st, dg, db, dw)      # += semantics
     assert _rel(dw, 2 * w.grad) < 2e-3
+
+
+@pytest.mark.parametrize("M,N", [(16384, 768), (1000, 256), (37, 2048), (5, 8)])
+def test_cast_colsum(M, N):
+    o = ops()
+    torch.manual_seed(9)
+    src = torch.randn(M, N, device="cuda")
+    cs = torch.ones(N, device="cuda")
+    dst = o.cast_colsum_bf16(src, cs)
+    assert torch.equal(dst, src.bfloat16())
+    assert _rel(cs - 1.0, dst.float().sum(0)) < 1e-4
