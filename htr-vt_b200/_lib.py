@@ -40,6 +40,7 @@ _P, _I, _L, _F, _Z = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_
 SIGNATURES = {
     # name: (restype, argtypes)
     "htrvt_version": (_I, []),
+    "htrvt_ctc_set_mode": (_I, [_I]),
     "htrvt_ctc_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "htrvt_ctc_loss_grad": (_I, [_P, _L, _L, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _L, _L, _P, _F, _P, _Z, _P]),
     "htrvt_ctc_fallback_count": (_L, []),

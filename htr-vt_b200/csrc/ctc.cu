@@ -12,6 +12,7 @@
 //   preds.float().permute(1,0,2).log_softmax(2) -> nn.CTCLoss(reduction='none', zero_infinity=True)
 // (ATen _ctc_loss / _ctc_loss_backward; blank = 0).  Semantics: SURVEY.md 8a / 9.14-9.16.
 #include "common.cuh"
+#include "ctc.cuh"
 #include <cstdlib>
 
 namespace htrvt {
@@ -182,22 +183,6 @@ __device__ __forceinline__ void ctc_beta(const float* __restrict__ l2p, int ldp,
 // and the beta-side likelihood must equal the alpha-side one.  A sequence failing either check (> 2e-5) is
 // recomputed by the log-space path above, so the result never depends on the fast path's range.
 // =================================================================================================
-constexpr int kFastRenorm = 4;
-constexpr int kFastTargetExp = 1023 - 16;
-
-__device__ __forceinline__ double unpack_pd(uint32_t w) { return __hiloint2double(static_cast<int>(w >> 2), static_cast<int>(w << 30)); }
-__device__ __forceinline__ uint32_t pack_pd(double v) {
-  const uint32_t hi = static_cast<uint32_t>(__double2hiint(v)), lo = static_cast<uint32_t>(__double2loint(v));
-  return __funnelshift_l(lo, hi, 2);        // bits 61..30 (values are in [0, 2): sign and exponent MSB are 0)
-}
-__device__ __forceinline__ double shfl_up_d(double v, int d) {
-  return __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), d), __shfl_up_sync(0xffffffffu, __double2loint(v), d));
-}
-__device__ __forceinline__ double shfl_down_d(double v, int d) {
-  return __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(v), d), __shfl_down_sync(0xffffffffu, __double2loint(v), d));
-}
-// exact 2^-sh as a double (|sh| < 1000)
-__device__ __forceinline__ double pow2_neg(int sh) { return __hiloint2double((1023 - sh) << 20, 0); }
 
 // shift (in binades) that moves the row maximum to 2^-16; 0 for an all-zero row
 template <int K>
@@ -361,22 +346,6 @@ __device__ __forceinline__ float pk_to_float(uint32_t w) {
   return __uint_as_float((max(w, 896u << 22) << 1) - (384u << 23));
 }
 
-struct CtcParams {
-  const float* x;            // logits (or log-probs when is_logprob) [.., C] with strides below
-  long long x_sb, x_st;      // element strides of the batch and time axes (class axis contiguous)
-  float* grad;               // same logical shape as x, own strides; may be null (loss only)
-  long long g_sb, g_st;
-  const int* targets;        // concatenated (tgt_stride == 0) or padded [B, tgt_stride]
-  int tgt_stride;
-  const int* input_lengths;  // [B] or null (=> T)
-  const int* target_lengths; // [B]
-  float* nll;                // [B]
-  const float* grad_scale;   // [B] per-sample upstream gradient, or null
-  float grad_scale_const;    // used when grad_scale == null
-  float* scratch;            // global alpha/beta scratch when they do not fit in shared memory
-  int B, T, C, kmax, is_logprob, scratch_in_smem, force_slow, dbg, ovl;
-};
-
 #define CTC_DISPATCH(FN, ...)                 \
   switch (K) {                                \
     case 1: FN<1>(__VA_ARGS__); break;        \
@@ -412,6 +381,7 @@ __device__ long long g_ctc_stamps[16];                      // HTRVT_CTC_DEBUG=1
 __global__ void __launch_bounds__(kCtcThreads, 1) ctc_loss_grad_kernel(const CtcParams P) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.x;
+  if (P.only && !P.only[b]) return;                 // fix-up pass: the throughput kernel already did this sequence
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = kCtcThreads / 32;
   const int T = P.T, C = P.C;
@@ -829,9 +799,38 @@ size_t ctc_smem_bytes(int T, int C, int kmax, bool scratch_in_smem) {
 
 using namespace htrvt;
 
+namespace {
+// Large batches go to the warp-per-sequence throughput kernel (ctc_tput.cu) when every label fits its register budget
+// (<= 6 states per lane); HTRVT_CTC_TPUT=0 keeps the CTA-per-sequence kernel, =1 forces the throughput kernel at any B.
+int g_tput_mode = -2;                                 // -2: not set (read HTRVT_CTC_TPUT), -1 auto, 0 off, 1 force
+bool use_tput(int B, int T, int C, int kmax) {
+  if (g_tput_mode == -2) {
+    const char* env = getenv("HTRVT_CTC_TPUT");
+    g_tput_mode = env ? atoi(env) : -1;
+  }
+  const int mode = g_tput_mode;
+  if (mode == 0 || kmax > 6) return false;
+  if (ctc_tput_smem_bytes(T, C, kmax) > 200 * 1024) return false;
+  // measured on B200 (tools/ctc_bench.py): the warp-per-sequence kernel keeps 11-12 sequences resident per SM and needs
+  // ~320 k clk per sequence, the CTA-per-sequence kernel 1 per SM at ~43 k clk: break-even near B = 2400
+  return mode == 1 || B >= 3072;
+}
+size_t tput_flag_bytes(int B) { return (static_cast<size_t>(2 * B) * sizeof(int) + 255) & ~size_t(255); }   // flags + offsets
+}  // namespace
+
+// kernel selection: -1 automatic (throughput kernel for B >= 3072), 0 CTA-per-sequence kernel only, 1 throughput kernel
+// at any batch size (tests).  Returns the previous mode.
+extern "C" int htrvt_ctc_set_mode(int mode) {
+  const int prev = g_tput_mode == -2 ? -1 : g_tput_mode;
+  g_tput_mode = mode < -1 || mode > 1 ? -1 : mode;
+  return prev;
+}
+
 extern "C" size_t htrvt_ctc_workspace_bytes(int B, int T, int C, int max_target_len) {
   int lmax = max_target_len < 0 || max_target_len > T ? T : max_target_len;
   const int kmax = ctc_round_k((2 * lmax + 1 + 31) / 32);
+  if (use_tput(B, T, C, kmax))      // per-sequence flags + the fix-up pass's alpha / beta rows (touched only for flagged sequences)
+    return tput_flag_bytes(B) + static_cast<size_t>(B) * 2 * T * 32 * kmax * sizeof(float);
   if (ctc_smem_bytes(T, C, kmax, true) <= 227 * 1024) return 0;
   return static_cast<size_t>(B) * 2 * T * 32 * kmax * sizeof(float);
 }
@@ -868,6 +867,26 @@ extern "C" int htrvt_ctc_loss_grad(const float* x, long long x_stride_b, long lo
   P.dbg = dbg;
   static const int ovl = getenv("HTRVT_CTC_OVL") ? static_cast<int>(strtol(getenv("HTRVT_CTC_OVL"), nullptr, 0)) : 0xFFFC;
   P.ovl = ovl;   // developer knob: run the log-space path only
+  P.only = nullptr;
+  if (!force_slow && use_tput(B, T, C, P.kmax)) {
+    // throughput path: warp-per-sequence kernel, then the CTA-per-sequence kernel as a fix-up pass that exits at once
+    // for every sequence the first kernel completed (flags[b] == 0); its rows live in the global scratch
+    const size_t fb = tput_flag_bytes(B);
+    const size_t need = fb + static_cast<size_t>(B) * 2 * T * 32 * P.kmax * sizeof(float);
+    if (!workspace || workspace_bytes < need) return HTRVT_ERR_WORKSPACE;
+    int* flags = static_cast<int*>(workspace);
+    P.scratch = nullptr; P.scratch_in_smem = 0;
+    int r = ctc_tput_launch(P, flags, flags + B, stream);
+    if (r) return r;
+    P.only = flags;
+    P.scratch = reinterpret_cast<float*>(static_cast<char*>(workspace) + fb);
+    const size_t smem_fix = ctc_smem_bytes(T, C, P.kmax, false);
+    if (smem_fix > 227 * 1024) return HTRVT_ERR_SHAPE;
+    if (!HTRVT_ENSURE_SMEM(ctc_loss_grad_kernel, 227 * 1024)) return HTRVT_ERR_LAUNCH;
+    ctc_loss_grad_kernel<<<B, kCtcThreads, smem_fix, stream>>>(P);
+    HTRVT_LAUNCH_CHECK();
+    return HTRVT_OK;
+  }
   P.scratch_in_smem = ctc_smem_bytes(T, C, P.kmax, true) <= 227 * 1024 ? 1 : 0;
   P.scratch = static_cast<float*>(workspace);
   const size_t smem = ctc_smem_bytes(T, C, P.kmax, P.scratch_in_smem);

@@ -16,6 +16,21 @@ def _pkg():
     return htrvt_b200
 
 
+@pytest.fixture(params=["cta_per_sequence", "warp_per_sequence"], autouse=True)
+def _ctc_kernel(request):
+    """Every CTC test runs against BOTH kernels: the CTA-per-sequence one (mode 0) and the warp-per-sequence throughput
+    kernel forced at any batch size (mode 1; sequences it flags are redone by the first kernel's fix-up launch)."""
+    if "ctc" not in request.node.name:
+        yield
+        return
+    from importlib import import_module
+    import htrvt_b200  # noqa: F401
+    lib = import_module("htr-vt_b200._lib").lib()
+    prev = lib.htrvt_ctc_set_mode(0 if request.param == "cta_per_sequence" else 1)
+    yield
+    lib.htrvt_ctc_set_mode(prev)
+
+
 def _ctc_ref64(logits, tg, il, tl):
     """float64 torch CPU CTC (same recursion as the float64 numpy oracle it is pinned to in test_oracle)."""
     lg = torch.from_numpy(logits).double().requires_grad_(True)
@@ -85,13 +100,48 @@ def test_ctc_full_size_properties(B, T, C, lo, hi):
     x2 = torch.from_numpy(logits).cuda().requires_grad_(True)
     nll2 = h.ctc_loss_from_logits(x2, torch.from_numpy(tg).cuda(), torch.from_numpy(tl).cuda())
     nll2.sum().backward()
-    np.testing.assert_allclose(nll2.detach().cpu().numpy(), nll.detach().cpu().numpy(), rtol=1e-6)
-    np.testing.assert_allclose(x2.grad.cpu().numpy(), gr, rtol=1e-5, atol=1e-7)
+    # (with the warp-per-sequence kernel forced, the unprovisioned call may be served by the other kernel: two
+    # implementations, so equal to rounding rather than bit for bit)
+    np.testing.assert_allclose(nll2.detach().cpu().numpy(), nll.detach().cpu().numpy(), rtol=2e-5)
+    np.testing.assert_allclose(x2.grad.cpu().numpy(), gr, rtol=1e-4, atol=2e-6)
 
 
 def _fallbacks():
     from importlib import import_module
     return import_module("htr-vt_b200._lib").lib().htrvt_ctc_fallback_count()
+
+
+def test_ctc_large_batch_kernels_agree():
+    """The warp-per-sequence kernel (forced: the automatic switch sits at B >= 3072) against the CTA-per-sequence kernel
+    on the same 1024 sequences, and against the float64 reference on a subset; infeasible / empty / ragged sequences mixed in."""
+    from importlib import import_module
+    h = _pkg()
+    lib = import_module("htr-vt_b200._lib").lib()
+    B, T, C = 1024, 128, 80
+    rs = np.random.RandomState(7)
+    logits = (rs.randn(B, T, C) * 1.5).astype(np.float32)
+    tl = rs.randint(0, 65, size=B).astype(np.int32)
+    il = rs.randint(40, T + 1, size=B).astype(np.int32)
+    il[::3] = T
+    tg = rs.randint(1, C, size=int(tl.sum())).astype(np.int32)
+    tg[1::2] = tg[0::2][: len(tg[1::2])]                    # many adjacent repeats: some sequences become infeasible
+    res = {}
+    for mode in (0, 1):
+        prev = lib.htrvt_ctc_set_mode(mode)
+        x = torch.from_numpy(logits).cuda().requires_grad_(True)
+        nll = h.ctc_loss_from_logits(x, torch.from_numpy(tg).cuda(), torch.from_numpy(tl),
+                                     input_lengths=torch.from_numpy(il).cuda(), max_target_len=int(tl.max()))
+        nll.sum().backward()
+        res[mode] = (nll.detach().cpu().numpy(), x.grad.cpu().numpy())
+        lib.htrvt_ctc_set_mode(prev)
+    np.testing.assert_allclose(res[1][0], res[0][0], rtol=2e-5, atol=1e-4)
+    np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-4, atol=2e-6)
+    assert (res[1][0] == 0).sum() > 5 and (res[1][0] > 0).sum() > 500          # both kinds present
+    sub = slice(0, 24)
+    offs = np.concatenate([[0], np.cumsum(tl)])
+    ref_nll, ref_grad = _ctc_ref64(logits[sub], tg[:offs[24]], il[sub], tl[sub])
+    np.testing.assert_allclose(res[1][0][sub], ref_nll, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(res[1][1][sub], ref_grad, rtol=1e-4, atol=1e-5)
 
 
 def test_ctc_fast_path_is_taken_and_fallback_is_exact():
