@@ -329,7 +329,7 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
                                     "recursion runs in the linear domain on the FP64 pipe (fallbacks to log space: %d)"
                                     % ops.lib().htrvt_ctc_fallback_count()}
     del bufs
-    # the same kernel when the batch fills the chip (one CTA per sequence, 148 SMs): throughput, not latency
+    # a batch that fills the chip: the lane-group throughput kernel (ctc_grp.cu, automatic for B >= 1200)
     Bl = 4096
     xl = torch.randn(Bl, T, C, device=dev)
     _, tgl, tll = synth_batch(Bl, 3)
@@ -338,7 +338,10 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
                                             max_target_len=mtl_l, grad_scale_const=1.0 / Bl), 10)
     bl = 2.0 * Bl * T * C * 4 + float(tgl.numel()) * 4 + 12.0 * Bl
     out["ctc_loss_grad"]["batch_4096"] = {"us_per_batch": ms * 1e3, "achieved_gbs": bl / (ms * 1e-3) / 1e9,
-                                          "frac_of_hbm_roofline": bl / (ms * 1e-3) / 1e9 / hbm}
+                                          "frac_of_hbm_roofline": bl / (ms * 1e-3) / 1e9 / hbm,
+                                          "kernel": "ctc_grp_kernel<8, 3> (8 lanes per sequence, fp32 linear domain) + "
+                                                    "fix-up launch",
+                                          "flagged_for_fixup": int(ops.lib().htrvt_ctc_flagged_count())}
     del xl
     # the wide-line shape (BASELINE config 5): T = 256, C = 90, labels 64..200 -> up to 401 states per sequence
     try:

@@ -44,6 +44,7 @@ SIGNATURES = {
     "htrvt_ctc_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "htrvt_ctc_loss_grad": (_I, [_P, _L, _L, _I, _P, _I, _P, _P, _I, _I, _I, _I, _P, _P, _L, _L, _P, _F, _P, _Z, _P]),
     "htrvt_ctc_fallback_count": (_L, []),
+    "htrvt_ctc_flagged_count": (_L, []),
     "htrvt_line_prep_u8": (_I, [_P, _L, _I, _P, _I, _I, _I, _P, _P, _P, _F, _P]),
     "htrvt_edit_distance": (_I, [_P, _P, _I, _P, _P, _P, _I, _P, _I, _I, _P, _P]),
     "htrvt_greedy_decode": (_I, [_P, _L, _L, _I, _I, _I, _P, _I, _P, _P, _P, _P]),

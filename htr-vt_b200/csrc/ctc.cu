@@ -800,26 +800,32 @@ size_t ctc_smem_bytes(int T, int C, int kmax, bool scratch_in_smem) {
 using namespace htrvt;
 
 namespace {
-// Large batches go to the warp-per-sequence throughput kernel (ctc_tput.cu) when every label fits its register budget
-// (<= 6 states per lane); HTRVT_CTC_TPUT=0 keeps the CTA-per-sequence kernel, =1 forces the throughput kernel at any B.
-int g_tput_mode = -2;                                 // -2: not set (read HTRVT_CTC_TPUT), -1 auto, 0 off, 1 force
-bool use_tput(int B, int T, int C, int kmax) {
+// Large batches go to the lane-group throughput kernel (ctc_grp.cu: G lanes per sequence, fp32 linear domain; labels up to
+// 256).  HTRVT_CTC_TPUT / htrvt_ctc_set_mode: -1 automatic, 0 CTA-per-sequence kernel only, 1 lane-group kernel at any B.
+int g_tput_mode = -2;                                 // -2: not set (read HTRVT_CTC_TPUT)
+int tput_mode() {
   if (g_tput_mode == -2) {
     const char* env = getenv("HTRVT_CTC_TPUT");
     g_tput_mode = env ? atoi(env) : -1;
+    if (g_tput_mode < -1 || g_tput_mode > 1) g_tput_mode = -1;
   }
-  const int mode = g_tput_mode;
-  if (mode == 0 || kmax > 6) return false;
-  if (ctc_tput_smem_bytes(T, C, kmax) > 200 * 1024) return false;
-  // measured on B200 (tools/ctc_bench.py): the warp-per-sequence kernel keeps 11-12 sequences resident per SM and needs
-  // ~320 k clk per sequence, the CTA-per-sequence kernel 1 per SM at ~43 k clk: break-even near B = 2400
-  return mode == 1 || B >= 3072;
+  return g_tput_mode;
+}
+// measured on B200 (tools/ctc_grp_probe.py, T = 128, C = 80): the CTA-per-sequence kernel takes 23 us per wave of 148
+// sequences (169 us at B = 1024, 334 us at 2048), the lane-group kernel ~170 us for anything up to one resident wave
+// (B <= ~2400) and 270 us at B = 4096: break-even just above B = 1024
+constexpr int kGrpMinBatch = 1200;
+bool use_grp(int B, int T, int C, int lmax) {
+  const int mode = tput_mode();
+  if (mode == 0 || !ctc_grp_supported(T, C, lmax)) return false;
+  return mode == 1 || B >= kGrpMinBatch;
 }
 size_t tput_flag_bytes(int B) { return (static_cast<size_t>(2 * B) * sizeof(int) + 255) & ~size_t(255); }   // flags + offsets
+size_t fixup_bytes(int B, int T, int kmax) { return (static_cast<size_t>(B) * 2 * T * 32 * kmax * sizeof(float) + 255) & ~size_t(255); }
 }  // namespace
 
-// kernel selection: -1 automatic (throughput kernel for B >= 3072), 0 CTA-per-sequence kernel only, 1 throughput kernel
-// at any batch size (tests).  Returns the previous mode.
+// kernel selection: -1 automatic (lane-group throughput kernel for B >= 1200), 0 CTA-per-sequence kernel only,
+// 1 lane-group kernel at any batch size (tests).  Returns the previous mode.
 extern "C" int htrvt_ctc_set_mode(int mode) {
   const int prev = g_tput_mode == -2 ? -1 : g_tput_mode;
   g_tput_mode = mode < -1 || mode > 1 ? -1 : mode;
@@ -829,8 +835,8 @@ extern "C" int htrvt_ctc_set_mode(int mode) {
 extern "C" size_t htrvt_ctc_workspace_bytes(int B, int T, int C, int max_target_len) {
   int lmax = max_target_len < 0 || max_target_len > T ? T : max_target_len;
   const int kmax = ctc_round_k((2 * lmax + 1 + 31) / 32);
-  if (use_tput(B, T, C, kmax))      // per-sequence flags + the fix-up pass's alpha / beta rows (touched only for flagged sequences)
-    return tput_flag_bytes(B) + static_cast<size_t>(B) * 2 * T * 32 * kmax * sizeof(float);
+  if (use_grp(B, T, C, lmax))       // flags + the fix-up pass's rows (touched only for flagged sequences) + the alpha slots
+    return tput_flag_bytes(B) + fixup_bytes(B, T, kmax) + ctc_grp_scratch_bytes(B, T, C, lmax, ctc_num_sms());
   if (ctc_smem_bytes(T, C, kmax, true) <= 227 * 1024) return 0;
   return static_cast<size_t>(B) * 2 * T * 32 * kmax * sizeof(float);
 }
@@ -868,15 +874,19 @@ extern "C" int htrvt_ctc_loss_grad(const float* x, long long x_stride_b, long lo
   static const int ovl = getenv("HTRVT_CTC_OVL") ? static_cast<int>(strtol(getenv("HTRVT_CTC_OVL"), nullptr, 0)) : 0xFFFC;
   P.ovl = ovl;   // developer knob: run the log-space path only
   P.only = nullptr;
-  if (!force_slow && use_tput(B, T, C, P.kmax)) {
-    // throughput path: warp-per-sequence kernel, then the CTA-per-sequence kernel as a fix-up pass that exits at once
-    // for every sequence the first kernel completed (flags[b] == 0); its rows live in the global scratch
-    const size_t fb = tput_flag_bytes(B);
-    const size_t need = fb + static_cast<size_t>(B) * 2 * T * 32 * P.kmax * sizeof(float);
+  if (!force_slow && use_grp(B, T, C, lmax)) {
+    // throughput path: lane-group kernel, then the CTA-per-sequence kernel as a fix-up pass that exits at once for every
+    // sequence the first kernel completed (flags[b] == 0)
+    const size_t fb = tput_flag_bytes(B), fx = fixup_bytes(B, T, P.kmax);
+    const size_t need = fb + fx + ctc_grp_scratch_bytes(B, T, C, lmax, ctc_num_sms());
     if (!workspace || workspace_bytes < need) return HTRVT_ERR_WORKSPACE;
     int* flags = static_cast<int*>(workspace);
     P.scratch = nullptr; P.scratch_in_smem = 0;
-    int r = ctc_tput_launch(P, flags, flags + B, stream);
+    if (P.tgt_stride <= 0) {
+      int r0 = ctc_offsets_launch(P.target_lengths, B, flags + B, stream);
+      if (r0) return r0;
+    }
+    int r = ctc_grp_launch(P, lmax, flags, flags + B, static_cast<char*>(workspace) + fb + fx, ctc_num_sms(), stream);
     if (r) return r;
     P.only = flags;
     P.scratch = reinterpret_cast<float*>(static_cast<char*>(workspace) + fb);

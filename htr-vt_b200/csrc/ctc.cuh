@@ -1,4 +1,4 @@
-// Shared pieces of the CTC kernels (ctc.cu: one CTA per sequence, latency-optimised; ctc_tput.cu: one warp per
+// Shared pieces of the CTC kernels (ctc.cu: one CTA per sequence, latency-optimised; ctc_grp.cu: a group of lanes per
 // sequence, throughput-optimised): parameter block and the "packed double" helpers.
 #pragma once
 #include "common.cuh"
@@ -41,9 +41,16 @@ struct CtcParams {
 };
 
 
-// throughput kernel (ctc_tput.cu): handles every sequence it can on the linear fp64 path and sets flags[b] = 1 for the
-// rest (label too long for its register budget, or the fast path's consistency guard tripped)
-int ctc_tput_launch(const CtcParams& P, int* flags, int* offsets, cudaStream_t stream);
-size_t ctc_tput_smem_bytes(int T, int C, int kmax);
+// exclusive prefix sum of the label lengths -> start of every sequence's labels in the concatenated target stream
+int ctc_offsets_launch(const int* lengths, int B, int* offsets, cudaStream_t stream);
+
+// lane-group throughput kernel (ctc_grp.cu): G lanes per sequence, fp32 linear domain, alpha rows in a per-warp global
+// scratch.  Handles every sequence it can and sets flags[b] = 1 for the rest (label longer than 8 G, or the consistency
+// guard tripped): those are redone by ctc.cu's kernel in a fix-up launch.  lmax = longest label of the batch (<= 256)
+bool ctc_grp_supported(int T, int C, int lmax);
+size_t ctc_grp_scratch_bytes(int B, int T, int C, int lmax, int sms);
+int ctc_grp_launch(const CtcParams& P, int lmax, int* flags, const int* offsets, void* scratch, int sms,
+                   cudaStream_t stream);
+int ctc_num_sms();
 
 }  // namespace htrvt

@@ -34,11 +34,14 @@ unsigned long long htrvt_launch_count(void); /* kernels launched so far by this 
  * max_target_len: host-side hint (max label length) or -1 = unknown (worst-case provisioning).
  * nll[b] = 0 and grad = 0 for infeasible samples; grad may be NULL (loss only).
  * grad is scaled by grad_scale[b] (device, may be NULL) or grad_scale_const. */
-/* Two kernels serve htrvt_ctc_loss_grad: one CTA per sequence (latency: B <= ~2 sequences per SM) and one warp per
- * sequence (throughput: large B, labels up to 95 symbols; anything it cannot finish on the fp64 fast path is flagged
- * and redone by the first kernel in a fix-up launch).  htrvt_ctc_set_mode: -1 automatic, 0 CTA-per-sequence only,
- * 1 warp-per-sequence at any batch size; returns the previous mode. */
+/* Two kernels serve htrvt_ctc_loss_grad: one CTA per sequence (latency: B up to a few sequences per SM; fp64 linear
+ * domain with a log-space fallback) and a group of 4-32 lanes per sequence (throughput: B >= 1200, labels up to 256
+ * symbols, fp32 linear domain with a consistency guard); whatever the throughput kernel cannot finish is flagged and
+ * redone by the first kernel in a fix-up launch.  htrvt_ctc_set_mode: -1 automatic, 0 CTA-per-sequence only, 1 lane-group
+ * kernel at any batch size; returns the previous mode.  htrvt_ctc_flagged_count: sequences the lane-group kernel handed
+ * to the fix-up launch since the library was loaded (synchronous read). */
 int htrvt_ctc_set_mode(int mode);
+long long htrvt_ctc_flagged_count(void);
 size_t htrvt_ctc_workspace_bytes(int B, int T, int C, int max_target_len);
 int htrvt_ctc_loss_grad(const float* x, long long x_stride_b, long long x_stride_t, int is_logprob,
                         const int* targets, int tgt_stride, const int* input_lengths, const int* target_lengths,

@@ -16,17 +16,17 @@ def _pkg():
     return htrvt_b200
 
 
-@pytest.fixture(params=["cta_per_sequence", "warp_per_sequence"], autouse=True)
+@pytest.fixture(params=["cta_per_sequence", "lane_group"], autouse=True)
 def _ctc_kernel(request):
-    """Every CTC test runs against BOTH kernels: the CTA-per-sequence one (mode 0) and the warp-per-sequence throughput
-    kernel forced at any batch size (mode 1; sequences it flags are redone by the first kernel's fix-up launch)."""
+    """Every CTC test runs against BOTH kernels: the CTA-per-sequence one (mode 0) and the lane-group throughput kernel
+    forced at any batch size (mode 1; sequences it flags are redone by the first kernel's fix-up launch)."""
     if "ctc" not in request.node.name:
         yield
         return
     from importlib import import_module
     import htrvt_b200  # noqa: F401
     lib = import_module("htr-vt_b200._lib").lib()
-    prev = lib.htrvt_ctc_set_mode(0 if request.param == "cta_per_sequence" else 1)
+    prev = lib.htrvt_ctc_set_mode({"cta_per_sequence": 0, "lane_group": 1}[request.param])
     yield
     lib.htrvt_ctc_set_mode(prev)
 
@@ -100,7 +100,7 @@ def test_ctc_full_size_properties(B, T, C, lo, hi):
     x2 = torch.from_numpy(logits).cuda().requires_grad_(True)
     nll2 = h.ctc_loss_from_logits(x2, torch.from_numpy(tg).cuda(), torch.from_numpy(tl).cuda())
     nll2.sum().backward()
-    # (with the warp-per-sequence kernel forced, the unprovisioned call may be served by the other kernel: two
+    # (with the lane-group kernel forced, the unprovisioned call may be served by the other kernel: two
     # implementations, so equal to rounding rather than bit for bit)
     np.testing.assert_allclose(nll2.detach().cpu().numpy(), nll.detach().cpu().numpy(), rtol=2e-5)
     np.testing.assert_allclose(x2.grad.cpu().numpy(), gr, rtol=1e-4, atol=2e-6)
@@ -111,8 +111,14 @@ def _fallbacks():
     return import_module("htr-vt_b200._lib").lib().htrvt_ctc_fallback_count()
 
 
+def _flagged():
+    """sequences the lane-group kernel (fp32 linear domain) handed to the CTA-per-sequence kernel's fix-up launch"""
+    from importlib import import_module
+    return import_module("htr-vt_b200._lib").lib().htrvt_ctc_flagged_count()
+
+
 def test_ctc_large_batch_kernels_agree():
-    """The warp-per-sequence kernel (forced: the automatic switch sits at B >= 3072) against the CTA-per-sequence kernel
+    """The lane-group kernel (forced: the automatic switch sits at B >= 1200) against the CTA-per-sequence kernel
     on the same 1024 sequences, and against the float64 reference on a subset; infeasible / empty / ragged sequences mixed in."""
     from importlib import import_module
     h = _pkg()
@@ -134,14 +140,16 @@ def test_ctc_large_batch_kernels_agree():
         nll.sum().backward()
         res[mode] = (nll.detach().cpu().numpy(), x.grad.cpu().numpy())
         lib.htrvt_ctc_set_mode(prev)
-    np.testing.assert_allclose(res[1][0], res[0][0], rtol=2e-5, atol=1e-4)
-    np.testing.assert_allclose(res[1][1], res[0][1], rtol=1e-4, atol=2e-6)
+    for mode in (1,):
+        np.testing.assert_allclose(res[mode][0], res[0][0], rtol=2e-5, atol=1e-4)
+        np.testing.assert_allclose(res[mode][1], res[0][1], rtol=1e-4, atol=2e-6)
     assert (res[1][0] == 0).sum() > 5 and (res[1][0] > 0).sum() > 500          # both kinds present
     sub = slice(0, 24)
     offs = np.concatenate([[0], np.cumsum(tl)])
     ref_nll, ref_grad = _ctc_ref64(logits[sub], tg[:offs[24]], il[sub], tl[sub])
-    np.testing.assert_allclose(res[1][0][sub], ref_nll, rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(res[1][1][sub], ref_grad, rtol=1e-4, atol=1e-5)
+    for mode in (1,):
+        np.testing.assert_allclose(res[mode][0][sub], ref_nll, rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(res[mode][1][sub], ref_grad, rtol=1e-4, atol=1e-5)
 
 
 def test_ctc_fast_path_is_taken_and_fallback_is_exact():
@@ -156,12 +164,14 @@ def test_ctc_fast_path_is_taken_and_fallback_is_exact():
     # (a) ordinary and moderately peaked logits: no fallback
     for scale in (1.0, 8.0):
         logits = (rs.randn(B, T, C) * scale).astype(np.float32)
-        n0 = _fallbacks()
+        n0, f0 = _fallbacks(), _flagged()
         x = torch.from_numpy(logits).cuda().requires_grad_(True)
         nll = h.ctc_loss_from_logits(x, torch.from_numpy(tg).cuda(), torch.from_numpy(tl))
         nll.sum().backward()
         torch.cuda.synchronize()
         assert _fallbacks() == n0, scale
+        if scale == 1.0:                  # ordinary logits stay on the lane-group kernel's fp32 path too
+            assert _flagged() == f0
         ref_nll, ref_grad = _ctc_ref64(logits, tg, il, tl)
         np.testing.assert_allclose(nll.detach().cpu().numpy(), ref_nll, rtol=1e-4)
         np.testing.assert_allclose(x.grad.cpu().numpy(), ref_grad, rtol=1e-4, atol=1e-5)
@@ -183,13 +193,15 @@ def test_ctc_fast_path_is_taken_and_fallback_is_exact():
     for labels, scale, expect_fallback, atol in ((tg, 1.0, False, 1e-5), (wrong, 1.0, None, 1e-5),
                                                  (wrong, 2.0, None, 2e-5), (wrong, 4.0, True, 5e-4)):
         lg = (logits * scale).astype(np.float32)
-        n0 = _fallbacks()
+        n0, f0 = _fallbacks(), _flagged()
         x = torch.from_numpy(lg).cuda().requires_grad_(True)
         nll = h.ctc_loss_from_logits(x, torch.from_numpy(labels).cuda(), torch.from_numpy(tl))
         nll.sum().backward()
         torch.cuda.synchronize()
         if expect_fallback is not None:
             assert (_fallbacks() > n0) == expect_fallback, scale
+        if labels is tg:                  # a confident network on its OWN labels: the fp32 lane-group path serves it
+            assert _flagged() == f0
         ref_nll, ref_grad = _ctc_ref64(lg, labels, il, tl)
         np.testing.assert_allclose(nll.detach().cpu().numpy(), ref_nll, rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(x.grad.cpu().numpy(), ref_grad, rtol=1e-4, atol=atol)

@@ -40,12 +40,6 @@ for (B, T, C, lo, hi) in [(128, 128, 80, 16, 64), (1024, 128, 80, 16, 64), (4096
         st = list(buf)
         print("  clocks from CTA0 start: sync0a %d, phase0 %d, alpha %d, beta %d, phase2(w5) %d, end %d  (L0=%d)" %
               (st[1] - st[0], st[2] - st[0], st[3] - st[0], st[4] - st[0], st[5] - st[0], st[6] - st[0], int(tl[0])))
-        buf8 = (ctypes.c_longlong * 8)()
-        lib.htrvt_ctc_tput_debug_stamps.argtypes = [ctypes.c_void_p]
-        lib.htrvt_ctc_tput_debug_stamps(ctypes.cast(buf8, ctypes.c_void_p))
-        s8 = list(buf8)
-        print("  warp-per-sequence kernel, sequence 0: setup %d, alpha sweep %d, backward sweep %d clk" %
-              (s8[1] - s8[0], s8[2] - s8[1], s8[3] - s8[2]))
         torch.cuda.synchronize()
     print("B=%d T=%d C=%d L<=%d: %.1f us/batch  %.0f GB/s algorithmic  fallbacks %d" %
           (B, T, C, hi, us, byts / us / 1e3, lib.htrvt_ctc_fallback_count() - n0))
