@@ -743,7 +743,7 @@ def run_ours(args):
         d[0] += a.elapsed_time(b)
         d[1] += fl
         d[2] += 1
-    gemm_names = ("gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc",
+    gemm_names = ("gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_dgrad_bn", "conv_wgrad", "conv_wgrad_acc",
                   "conv_wgrad_acc_t", "conv_wgrad_acc_w")
     g_ms = sum(by[n][0] for n in gemm_names if n in by)
     g_fl = sum(by[n][1] for n in gemm_names if n in by)

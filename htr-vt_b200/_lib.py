@@ -85,6 +85,8 @@ SIGNATURES = {
     "htrvt_pool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "htrvt_pool_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "htrvt_bn_bwd_ctas": (_I, [_L]),
+    "htrvt_conv_dgrad_bn": (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "htrvt_bn_bwd_apply": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _I, _P]),
     "htrvt_bn_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P, _P, _I, _P]),
     "htrvt_conv1_wgrad_ctas": (_I, []),
     "htrvt_conv1_wgrad": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _P]),

@@ -39,7 +39,7 @@ constexpr int kWin4Rows = 72;                  // KIND 4: 64 pixels + 2 of halo,
 constexpr int kWin4Bytes = kWin4Rows * 128;
 // DUAL (fc1 in train mode): the epilogue stores TWO boxes per step (pre-activation u and gelu(u)), so each epilogue
 // warp gets four staging buffers instead of two and the ring gives up one stage.
-template <int BN, int CL, bool RE = false, bool W4 = false, bool DUAL = false>
+template <int BN, int CL, bool RE = false, bool W4 = false, bool DUAL = false, bool STG2 = false>
 struct GemmCfg {
   static constexpr int kABytes = W4 ? 2 * kWin4Bytes : RE ? kWinRows * kBK * 2 : kBM * kBK * 2;
   static constexpr int kBTile = (BN / CL) * kBK * 2;                  // one tap's B bytes staged by THIS CTA
@@ -48,7 +48,9 @@ struct GemmCfg {
   static constexpr int kStages = (W4 ? (BN >= 256 ? 3 : 4) : RE ? (BN >= 256 ? 2 : 3) : (CL == 2) ? 6 : ((BN <= 128) ? 6 : 4)) -
                                  (DUAL ? 1 : 0);
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kWarpStaging = DUAL ? 4 * 2048 : 2 * 2048;   // per epilogue warp: [32 rows][64 B] output boxes
+  // per epilogue warp: [32 rows][64 B] output boxes, two buffers; DUAL / STG2 (BatchNorm-backward epilogue: a second box
+  // per step that only feeds the column sums) double them
+  static constexpr int kWarpStaging = (DUAL || STG2) ? 4 * 2048 : 2 * 2048;
   static constexpr int kStagingBytes = 8 * kWarpStaging;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -89,7 +91,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmP& P, int id) {
 //   1 plain with IEEE fp16 output + residual (forward stem convolutions)
 //   2 gelu(acc + bias), bf16 out            3 the same + the pre-activation to a second tensor (DUAL)
 //   4 acc * gelu'(res), bf16 out (fc2 input gradient + activation backward)
-constexpr int kEpiPlain = 0, kEpiF16 = 1, kEpiGelu = 2, kEpiGeluDual = 3, kEpiGeluBwd = 4;
+//   5 acc * relu_mask, bf16 out, + the BatchNorm-backward column sums of the layer in front (EPI_BN_BWD)
+constexpr int kEpiPlain = 0, kEpiF16 = 1, kEpiGelu = 2, kEpiGeluDual = 3, kEpiGeluBwd = 4, kEpiBnBwd = 5;
 template <int BN, int KIND, bool B_MN, int CL, bool RE = false, int EPI = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -98,7 +101,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr bool W4 = (KIND == 4);
   constexpr bool DUAL = (EPI == kEpiGeluDual), F16 = (EPI == kEpiF16);
   constexpr bool GELU = (EPI == kEpiGelu || EPI == kEpiGeluDual), GELUB = (EPI == kEpiGeluBwd);
-  using Cfg = GemmCfg<BN, CL, RE, W4, DUAL>;
+  constexpr bool BNB = (EPI == kEpiBnBwd);
+  constexpr bool BOX2 = DUAL || BNB;                   // a second staged box per step
+  using Cfg = GemmCfg<BN, CL, RE, W4, DUAL, BNB>;
   static_assert(EPI == 0 || KIND == 0, "epilogue variants exist for kind 0 only");
   static_assert(!(GELU || GELUB) || !RE, "GELU epilogues: linear layers only");
   static_assert(!RE || (KIND == 0 && !B_MN && CL == 2), "window reuse: kind 0, K-major weights, CTA pairs");
@@ -355,7 +360,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float ssum[4] = {0.f, 0.f, 0.f, 0.f}, qsum[4] = {0.f, 0.f, 0.f, 0.f};
     int stats_ntile = -1;
     // GELUB + EPI_COLSUM: column sums of the stored tile go straight into P.stats[N] (+=, atomics): fc1's bias gradient
-    const bool colsum = GELUB && (P.flags & EPI_COLSUM) != 0;
+    const bool colsum = (GELUB && (P.flags & EPI_COLSUM) != 0) || BNB;
     auto flush_stats = [&](int n_tile) {
       if (n_tile < 0) return;
       float* dst = P.stats + (colsum ? 0ll : static_cast<long long>(blockIdx.x * 4 + quad) * 2 * P.N_valid);
@@ -365,12 +370,26 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (b * 32 < kColsPerWarp && col < P.N_valid) {
           if (colsum) {
             atomicAdd(dst + col, ssum[b]);
+            if (BNB) atomicAdd(dst + P.N_valid + col, qsum[b]);
           } else {
             dst[col] += ssum[b];
             dst[P.N_valid + col] += qsum[b];
           }
         }
         ssum[b] = 0.f; qsum[b] = 0.f;
+      }
+    };
+    uint4 rq_nxt[4] = {};
+    auto res_load = [&](const TileCoord& tc, int col, uint4 (&dst)[4]) {
+      const int w = tc.w0 + r;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (w < P.Wo && col < P.N_valid) {
+        const uint4* rp = reinterpret_cast<const uint4*>(
+            static_cast<const __nv_bfloat16*>(P.res) +
+            ((static_cast<long long>(tc.n) * P.Ho + tc.h) * P.Wo + w) * P.N_valid + col);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = __ldg(rp + i);
       }
     };
     int as = 0; uint32_t aphase = 0;
@@ -399,13 +418,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) { if (CL == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]); }
         }
         if (P.flags & EPI_NOSTORE) continue;                 // measurement aid: main loop only
-        if ((P.flags & EPI_STATS) && KIND == 0 && tc.w0 + r >= P.Wo) {
+        if (((P.flags & EPI_STATS) || BNB) && KIND == 0 && tc.w0 + r >= P.Wo) {
           // rows past the end of the image row can pick up shifted-window data: keep them out of the statistics
 #pragma unroll
           for (int i = 0; i < 32; ++i) raw[i] = 0u;
         }
         uint32_t packed[16];
-        uint32_t packed2[DUAL ? 16 : 1];
+        uint32_t packed2[BOX2 ? 16 : 1];
         if (out_bf16) {
           float bv[32];
           if (P.flags & EPI_BIAS) {
@@ -417,17 +436,24 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           uint4 rq[4] = {};
-          if (KIND == 0 && (GELUB || (!GELU && (P.flags & EPI_RES)))) {   // this thread's output pixel, 32 consecutive channels
-            const int w = tc.w0 + r;
-            if (w < P.Wo && col < P.N_valid) {
-              const uint4* rp = reinterpret_cast<const uint4*>(
-                  static_cast<const __nv_bfloat16*>(P.res) +
-                  ((static_cast<long long>(tc.n) * P.Ho + tc.h) * P.Wo + w) * P.N_valid + col);
+          if (KIND == 0 && (GELUB || BNB || (!GELU && (P.flags & EPI_RES)))) {   // this thread's output pixel, 32 consecutive channels
+            // the 64 bytes of box b were requested one box earlier (rq_nxt): an L2 / DRAM round trip per box would
+            // otherwise sit between the TMEM load and the store of every box of this warp
+            if (b == 0) res_load(tc, col, rq);
+            else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) rq[i] = __ldg(rp + i);
+              for (int i = 0; i < 4; ++i) rq[i] = rq_nxt[i];
             }
+            if (b + 1 < nboxes) res_load(tc, col + box_cols, rq_nxt);
           }
           const uint32_t* rw = reinterpret_cast<const uint32_t*>(rq);
+          uint32_t mword = 0u;                               // BNB: ReLU mask bits of this pixel's 32 channels
+          if (BNB) {
+            const int w = tc.w0 + r;
+            if (w < P.Wo && col < P.N_valid)
+              mword = __ldg(reinterpret_cast<const uint32_t*>(
+                  P.mask + ((((static_cast<long long>(tc.n) * P.Ho + tc.h) * P.Wo + w) * P.N_valid + col) >> 3)));
+          }
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             float a = __uint_as_float(raw[i]) * P.alpha, c = __uint_as_float(raw[i + 1]) * P.alpha;
@@ -440,11 +466,20 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float2 uu = unpack_bf16(rw[i >> 1]);
               a *= gelu_grad(uu.x); c *= gelu_grad(uu.y);
             }
-            if (KIND == 0 && !GELU && !GELUB && (P.flags & EPI_RES)) {
+            if (BNB) {                                       // g' = g * [y > 0]; q = g' * xhat for the column sums
+              a = ((mword >> i) & 1u) ? a : 0.f;
+              c = ((mword >> (i + 1)) & 1u) ? c : 0.f;
+              const uint32_t pk = pack_bf16(a, c);
+              const float2 gr = unpack_bf16(pk), xr = unpack_f16(rw[i >> 1]);
+              const float2 mv = (col + i < P.N_valid) ? __ldg(reinterpret_cast<const float2*>(P.bn_mean + col + i)) : make_float2(0.f, 0.f);
+              const float2 rv = (col + i < P.N_valid) ? __ldg(reinterpret_cast<const float2*>(P.bn_rstd + col + i)) : make_float2(0.f, 0.f);
+              packed2[i >> 1] = pack_bf16(gr.x * ((xr.x - mv.x) * rv.x), gr.y * ((xr.y - mv.y) * rv.y));
+            }
+            if (KIND == 0 && !GELU && !GELUB && !BNB && (P.flags & EPI_RES)) {
               const float2 rr = F16 ? unpack_f16(rw[i >> 1]) : unpack_bf16(rw[i >> 1]);
               a += rr.x; c += rr.y;
             }
-            if (!GELU && !GELUB && (P.flags & EPI_RELU)) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+            if (!GELU && !GELUB && !BNB && (P.flags & EPI_RELU)) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
             packed[i >> 1] = F16 ? pack_f16(a, c) : pack_bf16(a, c);
           }
         } else {
@@ -464,14 +499,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // the store issued from this buffer two boxes ago must have finished READING it
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
-        const uint32_t sbase = smem_u32(stg) + sbuf * (DUAL ? 4096 : 2048);
+        const uint32_t sbase = smem_u32(stg) + sbuf * (BOX2 ? 4096 : 2048);
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
           const uint32_t addr = sbase + lane * 64 + ((c16 ^ sw_r) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(packed[4 * c16]),
                        "r"(packed[4 * c16 + 1]), "r"(packed[4 * c16 + 2]), "r"(packed[4 * c16 + 3])
                        : "memory");
-          if (DUAL)
+          if (BOX2)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2048), "r"(packed2[4 * c16]),
                          "r"(packed2[4 * c16 + 1]), "r"(packed2[4 * c16 + 2]), "r"(packed2[4 * c16 + 3])
                          : "memory");
@@ -512,7 +547,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(base + rr * 64 + (((lane >> 3) ^ ((rr >> 1) & 3)) << 4)));
             const float f = F16 ? f16_bits_to_float(hv) : __uint_as_float(static_cast<uint32_t>(hv) << 16);
             sacc += f;
-            qacc = fmaf(f, f, qacc);
+            if (BNB) {                                       // second box: g' * xhat
+              uint16_t hq;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hq) : "r"(base + 2048 + rr * 64 + (((lane >> 3) ^ ((rr >> 1) & 3)) << 4)));
+              qacc += __uint_as_float(static_cast<uint32_t>(hq) << 16);
+            } else {
+              qacc = fmaf(f, f, qacc);
+            }
           }
           ssum[b] += sacc;
           qsum[b] += qacc;
@@ -629,7 +670,7 @@ int num_sms() {
 template <int BN, int KIND, bool B_MN, int CL, bool RE = false, int EPI = 0>
 int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
                cudaStream_t stream, const CUtensorMap* c2p = nullptr) {
-  using Cfg = GemmCfg<BN, CL, RE, KIND == 4, EPI == kEpiGeluDual>;
+  using Cfg = GemmCfg<BN, CL, RE, KIND == 4, EPI == kEpiGeluDual, EPI == kEpiBnBwd>;
   auto kern = tapgemm_kernel<BN, KIND, B_MN, CL, RE, EPI>;
   const CUtensorMap& c2 = c2p ? *c2p : c;
   if (!HTRVT_ENSURE_SMEM(kern, Cfg::kSmemBytes)) return HTRVT_ERR_LAUNCH;
@@ -1026,6 +1067,48 @@ extern "C" int htrvt_conv_dgrad(const void* dy, int NB, int H, int W, int Cin, c
       if (r) return r;
     }
   return HTRVT_OK;
+}
+
+// Input gradient of a 3x3 stride-1 convolution FUSED with the first half of the BatchNorm backward of the layer in front
+// (conv -> BN -> ReLU -> [this conv]): the epilogue masks the gradient with that layer's ReLU bits (dx = g' = g * [y > 0])
+// and accumulates sums[0][Cin] += sum g', sums[1][Cin] += sum g' * xhat (xhat from raw = the layer's raw fp16 conv output,
+// mean / rstd its batch statistics) - exactly what htrvt_bn_bwd's reduction pass would compute from dx, so
+// htrvt_bn_bwd_apply can follow directly.  Only the window-sharing CTA-pair kernel carries this epilogue: returns
+// HTRVT_ERR_SHAPE for shapes it does not serve (the caller then runs htrvt_conv_dgrad + htrvt_bn_bwd).
+extern "C" int htrvt_conv_dgrad_bn(const void* dy, int NB, int H, int W, int Cin, const void* w_t, int Cout, void* dx,
+                                   const void* raw_f16, const void* relu_mask_bits, const float* mean, const float* rstd,
+                                   float* sums, cudaStream_t stream) {
+  const int ks = 3;
+  if ((Cout % 64) || (Cin % 64) || !w_t || !raw_f16 || !relu_mask_bits || !mean || !rstd || !sums) return HTRVT_ERR_SHAPE;
+  const int bn = pick_bn(Cin);
+  GemmP P = {};
+  int n = 0;
+  for (int kh = 0; kh < ks; ++kh)
+    for (int kw = 0; kw < ks; ++kw) {
+      P.tap.dh[n] = static_cast<int8_t>(1 - kh);
+      P.tap.dw[n] = static_cast<int8_t>(1 - kw);
+      P.tap.pw[n] = 0;
+      P.tap.widx[n] = static_cast<int8_t>(kh * ks + kw);
+      ++n;
+    }
+  P.kind = 0; P.Wo = W; P.Ho = H; P.NB = NB;
+  P.tiles_per_row = (W + kBM - 1) / kBM; P.tiles_m = P.tiles_per_row * H * NB; P.tiles_n = (Cin + bn - 1) / bn;
+  P.n_taps = n; P.splits = 1; P.k_chunks = (Cout + kBK - 1) / kBK; P.a_sh = 1; P.b_tap_stride = Cout;
+  P.N_valid = Cin; P.flags = EPI_BF16 | EPI_BN_BWD;
+  P.alpha = 1.f;
+  P.res = raw_f16; P.mask = static_cast<const uint8_t*>(relu_mask_bits); P.bn_mean = mean; P.bn_rstd = rstd; P.stats = sums;
+  const int cl = pick_cluster(P.tiles_m, P.tiles_m * P.tiles_n, bn, false);
+  if (!use_window_reuse(ks, 1, cl, bn, n) || (Cin % 32)) return HTRVT_ERR_SHAPE;
+  CUtensorMap ta, tb, tc;
+  int r = make_map_act(&ta, dy, NB, H, W, Cout, 1, kBK, kWinRows);
+  if (r) return r;
+  r = make_map_matrix(&tb, w_t, Cin, static_cast<long long>(ks) * ks * Cout, static_cast<long long>(ks) * ks * Cout, kBK,
+                      bn / cl);
+  if (r) return r;
+  r = make_map_out(&tc, dx, 2, Cin, W, H, NB, static_cast<long long>(Cin), static_cast<long long>(W) * Cin,
+                   static_cast<long long>(H) * W * Cin);
+  if (r) return r;
+  return launch_reuse<kEpiBnBwd>(bn, ta, tb, tc, P, P.tiles_m * P.tiles_n, stream);
 }
 
 // dw (+)= sum_pixels dy^T x_shifted.  Two output modes:

@@ -24,6 +24,9 @@ enum : int {
   EPI_DUAL = 1 << 13,      // with EPI_GELU (kernel built with DUAL): the pre-activation goes to a second output (tmC2)
   EPI_GELU_BWD = 1 << 14,  // bf16 out, kind 0: out = acc * gelu'(res[row, col]) (res = the saved pre-activation u)
   EPI_COLSUM = 1 << 15,    // with EPI_GELU_BWD: stats[N] += column sums of the stored tile (bias gradient)
+  EPI_BN_BWD = 1 << 16,    // bf16 out, kind 0 (input gradient of a 3x3 conv): out = g' = acc * relu_mask, and the BatchNorm
+                           // backward reduction of the layer in front rides along: stats[0][N] += sum g', stats[1][N] +=
+                           // sum g' * (res - bn_mean) * bn_rstd  (res = that layer's raw fp16 conv output)
 };
 
 struct GemmP {
@@ -43,6 +46,9 @@ struct GemmP {
   const float* bias;
   const void* res;         // EPI_RES: bf16 residual, laid out like the output
   float* stats;
+  const uint8_t* mask;     // EPI_BN_BWD: ReLU mask bits of the output pixels, 1 byte per 8 channels
+  const float* bn_mean;    // EPI_BN_BWD: batch mean / 1 / sqrt(var + eps) per channel
+  const float* bn_rstd;
   float alpha;             // scale applied to the accumulator
 };
 

@@ -698,6 +698,23 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, 
   return HTRVT_OK;
 }
 
+// Second half of htrvt_bn_bwd alone: the [3][C] sums were produced elsewhere (htrvt_conv_dgrad_bn's epilogue) and g is
+// already masked (g' = g * [y > 0]).  d_a = A g' + B raw + C, dgamma += sum g' xhat, dbeta += sum g'.
+extern "C" int htrvt_bn_bwd_apply(const void* g_masked, const void* raw_a, const float* mean_a, const float* rstd_a,
+                                  const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a, long long P, int C,
+                                  const float* sums, int raw_f16, cudaStream_t stream) {
+  if (P <= 0 || (C & 7) || C > 2048 || !sums) return HTRVT_ERR_SHAPE;
+  auto k_apply = raw_f16 ? bn_bwd_apply_kernel<true> : bn_bwd_apply_kernel<false>;
+  const long long n8 = P * C / 8;
+  const BnBwdSide sa = {gamma_a, mean_a, rstd_a, dgamma_a, dbeta_a};
+  const BnBwdSide sb = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  k_apply<<<grid_for(n8, 256), 256, static_cast<size_t>(6) * C * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(g_masked), nullptr, static_cast<const __nv_bfloat16*>(raw_a), sums,
+      static_cast<double>(P), sa, static_cast<__nv_bfloat16*>(d_a), nullptr, sb, nullptr, nullptr, n8, C);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
 extern "C" int htrvt_conv1_wgrad_ctas() { return 148 * 4; }
 
 // grad [C][1][3][3] fp32 (+=); partial: fp32 [htrvt_conv1_wgrad_ctas()][9*C]

@@ -10,11 +10,15 @@ every trainable parameter.  Data layout in HBM:
                        because SAM perturbs the masters in place twice per iteration.
 Reference semantics: model_v1/model/HTR_VT.py:222-241 and model_v1/model/resnet18.py:73-84.
 """
+import os
+
 import torch
 
 from . import ops
 
 STEM_LAYERS = (("layer1", (2, 1)), ("layer2", (2, 2)), ("layer3", (2, 2)))
+# BatchNorm-backward reduction in the epilogue of the GEMM that produces the gradient (HTRVT_FUSE_BN_BWD=0: two-pass route)
+FUSE_BN_BWD = os.environ.get("HTRVT_FUSE_BN_BWD", "1") != "0"
 
 
 class _Ctx(object):
@@ -499,9 +503,18 @@ class Engine(object):
                 dbeta_b=grads[p + ".downsample.1.bias"] if has_ds else None, want_gz=not has_ds,
                 zero_sums=zsum(r2.shape[-1]))
             wgrad(d2, a1, 3, 1, 1, p + ".conv2.weight")
-            da1 = ops.conv_dgrad(d2, wp[p + ".conv2.weight"], tuple(a1.shape), 3, 1, 1, w_t=wp.get("T:" + p + ".conv2.weight"))
-            d1, _, _ = ops.bn_bwd(da1, k1, r1, sa, sd[p + ".bn1.weight"], grads[p + ".bn1.weight"],
-                                  grads[p + ".bn1.bias"], zero_sums=zsum(r1.shape[-1]))
+            # conv2's input gradient with bn1's backward reduction in its epilogue (masked gradient + [2][C] sums), then
+            # the apply pass alone; shapes the fused kernel does not serve take the two-pass route
+            zs1 = zsum(r1.shape[-1])
+            w2t = wp.get("T:" + p + ".conv2.weight")
+            da1 = ops.conv_dgrad_bn(d2, w2t, tuple(a1.shape), r1, k1, sa, zs1) if (w2t is not None and FUSE_BN_BWD) else None
+            if da1 is not None:
+                d1 = ops.bn_bwd_apply(da1, r1, sa, sd[p + ".bn1.weight"], grads[p + ".bn1.weight"],
+                                      grads[p + ".bn1.bias"], zs1)
+            else:
+                da1 = ops.conv_dgrad(d2, wp[p + ".conv2.weight"], tuple(a1.shape), 3, 1, 1, w_t=w2t)
+                d1, _, _ = ops.bn_bwd(da1, k1, r1, sa, sd[p + ".bn1.weight"], grads[p + ".bn1.weight"],
+                                      grads[p + ".bn1.bias"], zero_sums=zs1)
             wgrad(d1, xin, 3, s[0], s[1], p + ".conv1.weight")
             if has_ds:
                 gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1],

@@ -665,6 +665,35 @@ def bn_bwd(g, mask, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, raw_b=None, st_b=No
     return d_a, d_b, gz
 
 
+def conv_dgrad_bn(dy, w_t, x_shape, raw, mask, st, sums):
+    """Input gradient of a 3x3 stride-1 conv fused with the reduction pass of the BatchNorm backward of the layer in
+    front: -> g' = (conv_transpose(dy, w)) * relu_mask as bf16 with the shape of `raw`, sums[0] += sum g',
+    sums[1] += sum g' xhat (sums: fp32 [3*C] zeros).  Returns None when the fused kernel does not serve the shape."""
+    _need_cuda(dy, w_t, raw)
+    N, H, W, Cin = x_shape
+    Cout = dy.shape[-1]
+    if dy.dtype != torch.bfloat16 or w_t.dtype != torch.bfloat16 or raw.dtype != torch.float16 or mask is None:
+        return None
+    dx = torch.empty(x_shape, dtype=torch.bfloat16, device=dy.device)
+    r = lib().htrvt_conv_dgrad_bn(_p(dy), N, H, W, Cin, _p(w_t), Cout, _p(dx), _p(raw), _p(mask), _p(st[0]), _p(st[1]),
+                                  _p(sums), _stream())
+    if r == -1:
+        return None
+    check(r, "htrvt_conv_dgrad_bn")
+    return dx
+
+
+def bn_bwd_apply(g_masked, raw_a, st_a, gamma_a, dgamma_a, dbeta_a, sums):
+    """Second pass of bn_bwd on a masked gradient whose [3, C] sums already exist (conv_dgrad_bn) -> d_a bf16."""
+    C = raw_a.shape[-1]
+    P = raw_a.numel() // C
+    d_a = torch.empty(raw_a.shape, dtype=torch.bfloat16, device=raw_a.device)
+    check(lib().htrvt_bn_bwd_apply(_p(g_masked), _p(raw_a), _p(st_a[0]), _p(st_a[1]), _p(gamma_a), _p(dgamma_a),
+                                   _p(dbeta_a), _p(d_a), P, C, _p(sums), _is_f16(raw_a), _stream()),
+          "htrvt_bn_bwd_apply")
+    return d_a
+
+
 def stem_head_moments(x, w):
     """x fp32 [B,H,W], w fp32 [C,1,3,3] -> (moments fp32 [54], stats fp32 [1,2,C]): 3x3-patch moments of the image and
     the exact per-channel sum / sum of squares of the (never materialised) conv1 output."""
@@ -842,6 +871,9 @@ def _flops(name, a, kw):
         if name == "conv_dgrad":
             dy, w, xs, ks = a[:4]
             return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * ks * ks * xs[3]
+        if name == "conv_dgrad_bn":
+            dy, w_t, xs = a[:3]
+            return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * 9 * xs[3]
         if name == "conv_wgrad_acc_w":
             dy, x = a[:2]
             return 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * 9 * x.shape[3]
@@ -871,10 +903,10 @@ def _flops(name, a, kw):
 def _instrument():
     import functools
     g = globals()
-    names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgrad_acc", "conv_wgrad_acc_t", "conv_wgrad_acc_w", "unpack_conv_grads", "attention_fwd",
+    names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_dgrad_bn", "conv_wgrad", "conv_wgrad_acc", "conv_wgrad_acc_t", "conv_wgrad_acc_w", "unpack_conv_grads", "attention_fwd",
              "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "ctc_kbest_paths", "sample_ln_fwd", "sample_ln_bwd", "line_prep_u8", "edit_distance",
              "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16", "cast_colsum_bf16", "dropout_",
-             "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd",
+             "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd", "bn_bwd_apply",
              "conv1_wgrad", "stem_head_moments", "stem_head_fwd", "stem_head_bwd"]
     for name in names:
         fn = g[name]

@@ -217,6 +217,17 @@ int htrvt_pool_fwd(const void* raw, const float* scale, const float* shift, void
                    int W, int C, int f16, void* stream);
 int htrvt_pool_bwd(const void* gout, int gout_is_f32, const void* idx, const void* raw, const float* scale,
                    const float* shift, void* gin, int B, int H, int W, int C, int raw_f16, void* stream);
+/* BatchNorm-backward reduction fused into the epilogue of the GEMM that produces the gradient:
+ * htrvt_conv_dgrad_bn = htrvt_conv_dgrad of a 3x3 stride-1 conv whose epilogue masks the gradient with the ReLU bits of
+ * the layer in front (dx = g') and accumulates sums[0][Cin] += sum g', sums[1][Cin] += sum g' xhat (zeroed by the
+ * caller; [3][Cin] like htrvt_bn_bwd's `partial`); htrvt_bn_bwd_apply is htrvt_bn_bwd's second pass on such a pair.
+ * htrvt_conv_dgrad_bn returns HTRVT_ERR_SHAPE (-1) for shapes its kernel does not serve: run the unfused pair then. */
+int htrvt_conv_dgrad_bn(const void* dy, int NB, int H, int W, int Cin, const void* w_t, int Cout, void* dx,
+                        const void* raw_f16, const void* relu_mask_bits, const float* mean, const float* rstd,
+                        float* sums, void* stream);
+int htrvt_bn_bwd_apply(const void* g_masked, const void* raw_a, const float* mean_a, const float* rstd_a,
+                       const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a, long long P, int C,
+                       const float* sums, int raw_f16, void* stream);
 int htrvt_bn_bwd_ctas(long long P);
 int htrvt_bn_bwd(const void* g, const void* relu_mask_bits, const void* raw_a, const float* mean_a, const float* rstd_a,
                  const float* gamma_a, float* dgamma_a, float* dbeta_a, void* d_a, const void* raw_b,

@@ -231,3 +231,45 @@ def test_conv_fwd_dgrad_wgrad(NB, H, W, Cin, Cout, ks, sh, sw, fwd):
     gw2 = torch.zeros(Cout, Cin, ks, ks, device="cuda")
     o.conv_wgrad(dy, x, ks, sh, sw, gw2, accumulate=False, transpose=False)    # both operands pixel-major
     assert _rel(gw2, wr.grad) < 1e-3
+
+
+@pytest.mark.parametrize("NB,H,W,C", [(2, 8, 256, 192), (2, 4, 128, 384), (3, 2, 200, 768)])
+def test_conv_dgrad_with_bn_backward_epilogue(NB, H, W, C):
+    """conv2's input gradient with the BatchNorm-backward reduction of the layer in front in its epilogue (ReLU-masked
+    gradient + [2][C] column sums) followed by the apply pass, against the two-pass route (conv_dgrad -> bn_bwd) and an
+    fp32 torch graph (conv -> BN(train) -> ReLU -> conv)."""
+    o = ops()
+    torch.manual_seed(NB + C)
+    Cout = C
+    x = torch.randn(NB, H, W, C, device="cuda").half()                       # raw conv1 output (fp16)
+    w2 = (torch.randn(Cout, C, 3, 3, device="cuda") / (3 * C ** 0.5))
+    gamma = (torch.rand(C, device="cuda") + 0.5)
+    beta = torch.randn(C, device="cuda") * 0.1
+    P = NB * H * W
+    f = x.float().view(P, C)
+    part = torch.stack([f.sum(0), (f * f).sum(0)]).view(1, 2, C).contiguous()
+    st = o.bn_finalize(part, P, gamma, beta, None, None, None, True)
+    a1, km, a1_bf = o.bn_act_fwd(x, st, True, want_mask=True, want_bf16=True)
+    dy = (torch.randn(NB, H, W, Cout, device="cuda") * 0.1).bfloat16()
+    packed = o.pack_weights([(w2.contiguous(), "conv"), (w2.contiguous(), "convT")])
+    wk, wt = packed[0], packed[1]
+    # two-pass route
+    g = o.conv_dgrad(dy, wk, (NB, H, W, C), 3, 1, 1, w_t=wt)
+    dg_a, db_a = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    d_a, _, _ = o.bn_bwd(g, km, x, st, gamma, dg_a, db_a)
+    # fused route
+    sums = torch.zeros(3 * C, device="cuda")
+    gm = o.conv_dgrad_bn(dy, wt, (NB, H, W, C), x, km, st, sums)
+    assert gm is not None, "the window-sharing CTA-pair kernel serves these shapes"
+    dg_b, db_b = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    d_b = o.bn_bwd_apply(gm, x, st, gamma, dg_b, db_b, sums)
+    bits = ((km.view(P, C // 8, 1).int() >> torch.arange(8, device="cuda").view(1, 1, 8)) & 1).view(NB, H, W, C)
+    assert torch.equal(gm.float(), g.float() * bits)                        # same GEMM, masked in the epilogue
+    assert _rel(d_b, d_a) < 1e-2 and _rel(dg_b, dg_a) < 2e-3 and _rel(db_b, db_a) < 2e-3
+    # fp32 torch graph
+    xf = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    gam, bet = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y = F.conv2d(F.relu(F.batch_norm(xf, None, None, gam, bet, True, 0.1, 1e-5)), w2, padding=1)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(d_b, xf.grad.permute(0, 2, 3, 1)) < 3e-2
+    assert _rel(dg_b, gam.grad) < 2e-2 and _rel(db_b, bet.grad) < 2e-2
