@@ -93,6 +93,7 @@ SIGNATURES = {
     "htrvt_stem_head_moment_ctas": (_I, []),
     "htrvt_stem_head_bwd_ctas": (_I, []),
     "htrvt_stem_head_moments": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "htrvt_stem_head_set_mode": (_I, [_I]),
     "htrvt_stem_head_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "htrvt_stem_head_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_mt_sqnorm": (_I, [_I, _P, _P, _P, _I, _P, _P]),

@@ -8,7 +8,7 @@
 //     output pixel p, S = sum_p v and R = sum_p v v^T give  sum_p raw_c = w_c . S,  sum_p raw_c^2 = w_c^T R w_c
 //     exactly (54 numbers for the whole batch, one cheap pass over the image);
 //   * the forward recomputes the conv in fp32 per pooled output (sliding 3-column window in registers) and
-//     writes only the pooled activation + a 4-bit arg-max code (15 = ReLU inactive);
+//     writes only the pooled activation + a 4-bit arg-max code (4 kh + kw; 15 = ReLU inactive);
 //   * the backward needs no per-pixel gradient tensor at all: with g the gradient of the pooled output,
 //       dbeta_c = sum_o g,  dgamma_c = sum_o g xhat(argmax o),  G3[c][t] = sum_o g v_t(argmax o)
 //     are accumulated in ONE pass over g, and the conv weight gradient follows in closed form from the
@@ -204,8 +204,8 @@ __global__ void __launch_bounds__(256) stem_head_fwd_kernel(const float* __restr
           else *reinterpret_cast<uint32_t*>(out + o * C + 2 * cp) = FMT == 1 ? pack_f16(ba, bb) : pack_bf16(ba, bb);
           if (out_bf) *reinterpret_cast<uint32_t*>(out_bf + o * C + 2 * cp) = pack_bf16(ba, bb);
           if (CODE && code) {
-            const unsigned na = ba > 0.f ? static_cast<unsigned>(kha * 3 + kwa) : 15u;
-            const unsigned nb = bb > 0.f ? static_cast<unsigned>(khb * 3 + kwb) : 15u;
+            const unsigned na = ba > 0.f ? static_cast<unsigned>(kha * 4 + kwa) : 15u;     // code = 4 kh + kw, 15 = no gradient
+            const unsigned nb = bb > 0.f ? static_cast<unsigned>(khb * 4 + kwb) : 15u;
             code[o * half_c + cp] = static_cast<uint8_t>(na | (nb << 4));
           }
         }
@@ -288,9 +288,9 @@ __global__ void __launch_bounds__(256) stem_head_bwd_kernel(const __nv_bfloat16*
       const unsigned nb = sc[pl * half_c + cp];
       {
         unsigned cd = nb & 15u;
-        const float ga = cd < 9u ? gv.x : 0.f;
-        cd = cd < 9u ? cd : 0u;
-        const unsigned kh = (cd * 11u) >> 5, kw = cd - 3u * kh;
+        const float ga = cd < 11u ? gv.x : 0.f;
+        cd = cd < 11u ? cd : 0u;
+        const unsigned kh = cd >> 2, kw = cd & 3u;
         const float* base = sin + (2 * kh) * kHeadInW + pl + kw;
         float raw = 0.f;
 #pragma unroll
@@ -306,9 +306,9 @@ __global__ void __launch_bounds__(256) stem_head_bwd_kernel(const __nv_bfloat16*
       }
       {
         unsigned cd = nb >> 4;
-        const float gb = cd < 9u ? gv.y : 0.f;
-        cd = cd < 9u ? cd : 0u;
-        const unsigned kh = (cd * 11u) >> 5, kw = cd - 3u * kh;
+        const float gb = cd < 11u ? gv.y : 0.f;
+        cd = cd < 11u ? cd : 0u;
+        const unsigned kh = cd >> 2, kw = cd & 3u;
         const float* base = sin + (2 * kh) * kHeadInW + pl + kw;
         float raw = 0.f;
 #pragma unroll
@@ -402,6 +402,12 @@ __global__ void __launch_bounds__(512) stem_head_bwd_finalize_kernel(
 
 using namespace htrvt;
 
+namespace htrvt {
+int stem_head_tc_supported(int B, int H, int W, int C, int out_fmt);
+int stem_head_tc_launch(const float* x, const float* w, const float* scale, const float* shift, void* out, void* out_bf,
+                        void* code, int B, int H, int W, int C, int out_fmt, cudaStream_t stream);
+}  // namespace htrvt
+
 extern "C" int htrvt_stem_head_moment_ctas() { return 148 * 2; }
 extern "C" int htrvt_stem_head_bwd_ctas() { return 148 * 3; }
 
@@ -432,6 +438,10 @@ extern "C" int htrvt_stem_head_fwd(const float* x, const float* w, const float* 
   const int Ho = (H / 2 - 1) / 2 + 1;
   dim3 grid((W + 63) / 64, (Ho + 1) / 2, B);
   if (out_fmt < 0 || out_fmt > 2) return HTRVT_ERR_SHAPE;
+  // the tensor-pipe kernel (stemhead_tc.cu) where the shape allows; the FP32-pipe kernel below for the rest (widths
+  // that are not a multiple of 64, fp32 output of the fp32-parity mode)
+  if (htrvt::stem_head_tc_supported(B, H, W, C, out_fmt))
+    return htrvt::stem_head_tc_launch(x, w, scale, shift, out, out_bf16, code, B, H, W, C, out_fmt, stream);
   auto kern = code ? (out_fmt == 1 ? stem_head_fwd_kernel<true, 1> : out_fmt == 2 ? stem_head_fwd_kernel<true, 2>
                                                                                   : stem_head_fwd_kernel<true, 0>)
                    : (out_fmt == 1 ? stem_head_fwd_kernel<false, 1> : out_fmt == 2 ? stem_head_fwd_kernel<false, 2>

@@ -245,6 +245,10 @@ int htrvt_stem_head_moment_ctas(void);
 int htrvt_stem_head_bwd_ctas(void);
 int htrvt_stem_head_moments(const float* x, const float* w, float* partial, float* moments, float* stats, int B,
                             int H, int W, int C, void* stream);
+/* htrvt_stem_head_fwd runs the convolution on the tensor pipe (stemhead_tc.cu: fp16 hi/lo split operands, the fp32
+ * result to ~2^-21) when W % 64 == 0 and the output is 16-bit, on the FP32 pipe otherwise; htrvt_stem_head_set_mode(0)
+ * forces the FP32-pipe kernel (tests), (1) restores the default; returns the previous mode. */
+int htrvt_stem_head_set_mode(int mode);
 int htrvt_stem_head_fwd(const float* x, const float* w, const float* scale, const float* shift, void* out,
                         void* out_bf16 /*nullable*/, void* code, int B, int H, int W, int C, int out_fmt, void* stream);
 int htrvt_stem_head_bwd(const void* g, const void* code, const float* x, const float* w, const float* moments,

@@ -211,9 +211,47 @@ def test_final_pool_fwd_bwd(fwd):
     assert _rel(gin, want) < 2e-2
 
 
+@pytest.fixture(params=["tensor_pipe", "fp32_pipe"])
+def head_kernel(request):
+    """stem-head forward kernel: stemhead_tc.cu (tcgen05, default where W % 64 == 0) or stemhead.cu (FP32 pipe)"""
+    lib = import_module("htr-vt_b200._lib").lib()
+    prev = lib.htrvt_stem_head_set_mode(1 if request.param == "tensor_pipe" else 0)
+    yield request.param
+    lib.htrvt_stem_head_set_mode(prev)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 64, 512, 192), (3, 64, 128, 64), (1, 8, 64, 128), (2, 20, 192, 256)])
+def test_stem_head_tensor_pipe_matches_fp32_pipe(B, H, W, C):
+    """The tcgen05 stem head (fp16 hi/lo split operands) against the FP32-pipe kernel on the same inputs: pooled
+    activations equal up to the last fp16 bit, arg-max codes equal except on near-ties."""
+    o = ops()
+    lib = import_module("htr-vt_b200._lib").lib()
+    torch.manual_seed(B + W)
+    x3 = torch.randn(B, H, W, device="cuda")
+    w = torch.randn(C, 1, 3, 3, device="cuda") * 0.4
+    scale, shift = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.3
+    scale[::3] *= -1.0                                              # negative BatchNorm scales too
+    st = (None, None, scale, shift)
+    res = {}
+    for mode in (0, 1):
+        prev = lib.htrvt_stem_head_set_mode(mode)
+        res[mode] = o.stem_head_fwd(x3, w, st, True, out_dtype=torch.float16, want_bf16=True)
+        res[mode] += o.stem_head_fwd(x3, w, st, False, out_dtype=torch.float16)[:1]
+        lib.htrvt_stem_head_set_mode(prev)
+    (a0, c0, b0, e0), (a1, c1, b1, e1) = res[0], res[1]
+    assert torch.isfinite(a1.float()).all()
+    d = (a1.float() - a0.float()).abs()
+    assert float(d.max()) <= 2e-3 * float(a0.float().abs().max()) and float((d > 0).float().mean()) < 0.01
+    # the eval-mode variant (no arg-max tags in the low mantissa bits) may differ from the train-mode one in the last fp16 bit
+    de = (e1.float() - a1.float()).abs()
+    assert float(de.max()) <= 2e-3 * float(a1.float().abs().max()) and float((de > 0).float().mean()) < 0.01
+    assert float((b1.float() - a1.float()).abs().max()) <= 1e-2 * float(a1.float().abs().max())
+    assert float((c0 != c1).float().mean()) < 1e-3
+
+
 @pytest.mark.parametrize("fwd", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("B,H,W,C", [(3, 64, 128, 64), (2, 64, 512, 192), (2, 12, 72, 64)])
-def test_stem_head_fused(B, H, W, C, fwd):
+def test_stem_head_fused(B, H, W, C, fwd, head_kernel):
     """conv1 -> bn1(train) -> relu -> maxpool fused (conv output never materialised) vs the fp32 torch graph
     (model_v1/model/resnet18.py:74-77): pooled activation, batch statistics, and dW / dgamma / dbeta."""
     o = ops()
@@ -247,16 +285,25 @@ def test_stem_head_fused(B, H, W, C, fwd):
     assert torch.equal(out3, out) and torch.equal(code3, code) and out_bf.dtype == torch.bfloat16
     assert _rel(out_bf.permute(0, 3, 1, 2), ref.detach()) < 1e-2
     out2, none = o.stem_head_fwd(x3, w.detach(), st, False, out_dtype=fwd)
-    assert none is None and torch.equal(out, out2)
+    assert none is None
+    if head_kernel == "fp32_pipe" or W % 64:
+        assert torch.equal(out, out2)
+    else:                                   # tensor pipe: the train-mode kernel tags the low mantissa bits (arg-max code)
+        assert _rel(out2, out) < 4e-3 and float((out2 != out).float().mean()) < 0.01
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     dw = torch.zeros(C, 1, 3, 3, device="cuda")
     g_nhwc = gout.permute(0, 2, 3, 1).contiguous().bfloat16()
     o.stem_head_bwd(g_nhwc, code, x3, w.detach(), moments, gamma.detach(), st, dg, db, dw)
     assert _rel(db, beta.grad) < 2e-3
     assert _rel(dg, gamma.grad) < 2e-3
-    assert _rel(dw, w.grad) < 2e-3
+    # The tensor-pipe kernel resolves the arg-max among candidates within 2^-19 (relative) of each other by position
+    # (its tags live in the four low mantissa bits): a handful of the ~4e5 pooled outputs of these small cases route
+    # their gradient to an (equally maximal, to fp32 conv rounding) neighbour, each moving one dW entry by ~1 %.
+    tol_w = 2e-3 if (head_kernel == "fp32_pipe" or W % 64) else 4e-2
+    assert _rel(dw, w.grad) < tol_w
+    assert float((dw - w.grad).abs().median() / w.grad.abs().median()) < 2e-3
     o.stem_head_bwd(g_nhwc, code, x3, w.detach(), moments, gamma.detach(), st, dg, db, dw)      # += semantics
-    assert _rel(dw, 2 * w.grad) < 2e-3
+    assert _rel(dw, 2 * w.grad) < tol_w
 
 
 @pytest.mark.parametrize("M,N", [(16384, 768), (1000, 256), (37, 2048), (5, 8)])
