@@ -13,7 +13,8 @@
 //              (16-byte chunk c of row r at chunk c ^ (r & 7)); the image is not a TMA operand (1 channel, im2col'd
 //              by two producer warps from 7 staged image rows);
 //   roles      warps 0-7: epilogue (warp w reads TMEM lane quadrant w & 3 = 32 channels, pooled columns 32 (w >> 2) ..
-//              +31 of the tile), warps 8-9: im2col producers, warp 10: TMEM allocation + MMA issue (one thread);
+//              +31 of the tile), two im2col producer warps, one warp for TMEM allocation + MMA issue (one thread); for
+//              C <= 192 the fourth lane quadrant is empty and those three roles sit on ITS scheduler (warps 3, 7, 11);
 //   pipeline   work item = (unit, channel group): unit = 64 pooled outputs of one pooled row, group = C / 2 channels on
 //              an M = 128 tile (C = 192: 96 real rows, the 4th lane quadrant idles).  TMEM holds two items (2 x 240
 //              columns), shared memory two units' patch tiles: the MMAs of item k+1 and the im2col of unit u+1 run
@@ -26,7 +27,7 @@
 namespace htrvt {
 namespace {
 
-constexpr int kTcThreads = 352;                 // 11 warps
+constexpr int kTcThreads = 384;                 // 12 warps
 constexpr int kTcN = 80;                        // conv columns per tile
 constexpr int kTcOut = 64;                      // pooled outputs per tile row
 constexpr int kTcRowBytes = 128;                // SWIZZLE_128B K-major row pitch (64 halfs; K = 32 of them are used)
@@ -82,10 +83,10 @@ struct TcHeadP {
   const float* x; const float* w; const float* scale; const float* shift;
   void* out; void* out_bf; uint8_t* code;
   int B, H, W, C, Ho, Hc, ngroups, cg, tiles_w;
-  long long units;
+  int units;
 };
 
-template <bool CODE, int FMT>      // FMT: 0 = bf16 out, 1 = fp16 out
+template <bool CODE, int FMT, bool BFC>      // FMT: 0 = bf16 out, 1 = fp16 out; BFC: + a bf16 copy of an fp16 out
 __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHeadP P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,29 +111,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
     const int g = i >> 7, r = i & 127;
     uint32_t v[9], o[16];
     const bool real = g < P.ngroups && r < cg;
+    // channels with a negative BatchNorm scale get NEGATED weights: y = scale * conv + shift = |scale| * conv' + shift is
+    // then non-decreasing in conv' for every channel, so the vertical maximum can be taken on the raw accumulators
+    const float sgn = (real && __ldg(P.scale + g * cg + r) < 0.f) ? -1.f : 1.f;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) v[t] = real ? split_hl(__ldg(P.w + (g * cg + r) * 9 + t)) : 0u;
+    for (int t = 0; t < 9; ++t) v[t] = real ? split_hl(sgn * __ldg(P.w + (g * cg + r) * 9 + t)) : 0u;
     build_row<true>(v, o);
     store_row(smem_u32(sA) + g * kTcATile + r * kTcRowBytes, r, o);
   }
   fence_proxy_async();
-  if (warp == 10) tmem_alloc(tmem_slot, 512);
+  // C <= 192: the fourth lane quadrant of the M = 128 tile holds no channels, so its scheduler (warps 3, 7, 11) takes the
+  // producers and the MMA issue instead of sharing the epilogue warps' issue slots
+  const bool q3free = cg <= 96;
+  const int prod_a = q3free ? 3 : 8, prod_b = q3free ? 7 : 9, mma_w = q3free ? 11 : 10;
+  if (warp == mma_w) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8 || warp == 9) {
+  if (warp == prod_a || warp == prod_b) {
     // =========================== im2col producers (64 threads) ===========================
-    const int t = threadIdx.x - 256;
+    const int t = (warp == prod_a ? 0 : 32) + lane;
     // image rows 4 ho - 3 .. 4 ho + 3, columns w0 - 9 .. w0 + 72 of a unit (zero outside the image: the conv's padding):
     // thread t takes column t (and t + 64 for t < 18) of all seven rows.  The loads of unit u + 1 are issued before
     // the patch rows of unit u are built, so their latency hides under the build.
     float v0[7], v1[7];
-    auto load_unit = [&](long long u) {
-      const int wt = static_cast<int>(u % P.tiles_w);
-      const int ho = static_cast<int>((u / P.tiles_w) % P.Ho);
-      const int n = static_cast<int>(u / (static_cast<long long>(P.tiles_w) * P.Ho));
+    auto load_unit = [&](int u) {
+      const int wt = u % P.tiles_w, rw = u / P.tiles_w;
+      const int ho = rw % P.Ho, n = rw / P.Ho;
       const int ww0 = wt * kTcOut - 9 + t, ww1 = ww0 + 64;
       const bool c0ok = ww0 >= 0 && ww0 < W, c1ok = t < 18 && ww1 < W;
 #pragma unroll
@@ -144,9 +151,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
         v1[r] = (rok && c1ok) ? __ldg(rowp + ww1) : 0.f;
       }
     };
-    if (static_cast<long long>(blockIdx.x) < P.units) load_unit(blockIdx.x);
+    if (static_cast<int>(blockIdx.x) < P.units) load_unit(blockIdx.x);
     int it = 0;
-    for (long long u = blockIdx.x; u < P.units; u += gridDim.x, ++it) {
+    for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++it) {
       const int buf = it & 1;
       asm volatile("bar.sync 1, 64;" ::: "memory");     // the previous unit's tile build is done with img
 #pragma unroll
@@ -154,7 +161,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
         img[r * kTcStageCols + t] = split_hl(v0[r]);
         if (t < 18) img[r * kTcStageCols + t + 64] = split_hl(v1[r]);
       }
-      if (u + gridDim.x < P.units) load_unit(u + gridDim.x);
+      if (u + static_cast<int>(gridDim.x) < P.units) load_unit(u + gridDim.x);
       asm volatile("bar.sync 1, 64;" ::: "memory");
       if (it >= 2) mbar_wait_relaxed(&bempty[buf], ((it >> 1) - 1) & 1);
       // patch rows: conv row j (image rows 2j .. 2j+2 of the staged seven), pixel p (conv column w0 - 8 + p)
@@ -173,12 +180,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
       __syncwarp();
       if (lane == 0) mbar_arrive(&bfull[buf]);
     }
-  } else if (warp == 10) {
+  } else if (warp == mma_w) {
     // =========================== MMA issue (one thread) ===========================
     if (lane == 0) {
       constexpr uint32_t idesc = idesc_f16(128, kTcN);
       int it = 0, item = 0;
-      for (long long u = blockIdx.x; u < P.units; u += gridDim.x, ++it) {
+      for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++it) {
         const int buf = it & 1;
         mbar_wait_relaxed(&bfull[buf], (it >> 1) & 1);
         tc_fence_after();
@@ -205,10 +212,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
     int it = 0, item = 0;
     // a lane quadrant without real channels (C = 192: rows 96-127 of the M = 128 tile) has nothing to do and is not
     // counted in tempty
-    for (long long u = (32 * q < cg) ? static_cast<long long>(blockIdx.x) : P.units; u < P.units; u += gridDim.x, ++it) {
-      const int wt = static_cast<int>(u % P.tiles_w);
-      const int ho = static_cast<int>((u / P.tiles_w) % P.Ho);
-      const int n = static_cast<int>(u / (static_cast<long long>(P.tiles_w) * P.Ho));
+    for (int u = (warp < 8 && 32 * q < cg) ? static_cast<int>(blockIdx.x) : P.units; u < P.units; u += gridDim.x, ++it) {
+      const int wt = u % P.tiles_w, rw = u / P.tiles_w;
+      const int ho = rw % P.Ho, n = rw / P.Ho;
       const int w0 = wt * kTcOut;
       for (int g = 0; g < P.ngroups; ++g, ++item) {
         const int tb = item & 1;
@@ -216,42 +222,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
         tc_fence_after();
         {
           const int c = g * cg + 32 * q + lane;          // this thread's channel
-          const float sc = __ldg(P.scale + c), sh = __ldg(P.shift + c);
+          const float asc = fabsf(__ldg(P.scale + c)), sh = __ldg(P.shift + c);      // (sign folded into the weights)
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + tb * kTcAcc + 32 * hc;
-          // a conv row outside the image (pool padding) turns into kNeg through its affine: y = acc * 0 + kNeg
           constexpr float kNeg = -3.0e38f;               // finite: the arg-max tag below lives in the low mantissa bits
-          float scj[3], shj[3];
+          // a conv row outside the image (pool padding) is replaced by the middle row (always inside): the maximum and
+          // its first-maximum position are unchanged
+          uint32_t roff[3], rtag[3];                    // (the stand-in keeps the middle row's tag: a tie decodes to kh = 1)
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
             const int cr = 2 * ho - 1 + j;
-            const bool ok = cr >= 0 && cr < P.Hc;
-            scj[j] = ok ? sc : 0.f;
-            shj[j] = ok ? sh : kNeg;
+            const int src = (cr >= 0 && cr < P.Hc) ? j : 1;
+            roff[j] = static_cast<uint32_t>(src) * kTcN;
+            rtag[j] = static_cast<uint32_t>(3 - src) << 2;
           }
-          // column maxima m[i] of the conv columns w0 + 32 hc - 1 + i, i = 0 .. 33.  With CODE the low four mantissa bits
-          // of every candidate carry (3 - kh) << 2 | (3 - kw): a plain maximum then returns torch's first maximum in
-          // (kh, kw) order, and the winner's tag is the arg-max code (values move by < 2^-19 relative: below fp16 / bf16)
+          // column maxima m[i] of the conv columns w0 + 32 hc - 1 + i, i = 0 .. 33: vertical maximum of the raw
+          // accumulators, then ONE affine per column.  With CODE the low four mantissa bits of every candidate carry
+          // (3 - kh) << 2 | (3 - kw): a plain maximum then returns torch's first maximum in (kh, kw) order, and the
+          // winner's tag is the arg-max code (values move by < 2^-19 relative: below fp16 / bf16 resolution)
           float m[34];
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
             uint32_t r0[16], r1[16], r2[16];
-            tmem_ld16(taddr + 0 * kTcN + 16 * ch, r0);
-            tmem_ld16(taddr + 1 * kTcN + 16 * ch, r1);
-            tmem_ld16(taddr + 2 * kTcN + 16 * ch, r2);
+            tmem_ld16(taddr + roff[0] + 16 * ch, r0);
+            tmem_ld16(taddr + roff[1] + 16 * ch, r1);
+            tmem_ld16(taddr + roff[2] + 16 * ch, r2);
             tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const int i = 16 * ch + e - 7;             // index into m[]
               if (i < 0 || i >= 34) continue;
-              float y0 = fmaf(__uint_as_float(r0[e]), scj[0], shj[0]);
-              float y1 = fmaf(__uint_as_float(r1[e]), scj[1], shj[1]);
-              float y2 = fmaf(__uint_as_float(r2[e]), scj[2], shj[2]);
               if (CODE) {
-                y0 = __uint_as_float((__float_as_uint(y0) & ~15u) | 12u);
-                y1 = __uint_as_float((__float_as_uint(y1) & ~15u) | 8u);
-                y2 = __uint_as_float((__float_as_uint(y2) & ~15u) | 4u);
+                const float x0 = __uint_as_float((r0[e] & ~15u) | rtag[0]);
+                const float x1 = __uint_as_float((r1[e] & ~15u) | rtag[1]);
+                const float x2 = __uint_as_float((r2[e] & ~15u) | rtag[2]);
+                const float xm = fmaxf(x0, fmaxf(x1, x2));
+                const float y = fmaf(xm, asc, sh);
+                m[i] = __uint_as_float((__float_as_uint(y) & ~15u) | (__float_as_uint(xm) & 12u));
+              } else {
+                m[i] = fmaf(fmaxf(__uint_as_float(r0[e]), fmaxf(__uint_as_float(r1[e]), __uint_as_float(r2[e]))), asc, sh);
               }
-              m[i] = fmaxf(y0, fmaxf(y1, y2));
             }
           }
           if (w0 + 32 * hc - 1 < 0) m[0] = kNeg;         // conv column -1 / W: pool padding
@@ -259,8 +268,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
           // pooled outputs o = 0 .. 31 (conv columns o-1, o, o+1 = m[o], m[o+1], m[o+2]); pairs of outputs per store
           const long long gp0 = (static_cast<long long>(n) * P.Ho + ho) * W + w0 + 32 * hc;
           const int odd = lane & 1;
-          const long long off0 = (gp0 + odd) * C + (c - odd);
-          const long long cof0 = (gp0 + odd) * (C >> 1) + ((c - odd) >> 1);
+          char* po = static_cast<char*>(P.out) + ((gp0 + odd) * C + (c - odd)) * 2;
+          char* pb = BFC ? static_cast<char*>(P.out_bf) + ((gp0 + odd) * C + (c - odd)) * 2 : nullptr;
+          uint8_t* pc = CODE ? P.code + (gp0 + odd) * (C >> 1) + ((c - odd) >> 1) : nullptr;
+          const long long ostep = 4LL * C;               // two pixels further, in bytes of a 16-bit tensor
+          const uint32_t psel = odd ? 0x3276u : 0x5410u; // byte_perm: even lane (mine.lo, partner.lo), odd (partner.hi, mine.hi)
 #pragma unroll
           for (int o = 0; o < 32; o += 2) {
             float val[2];
@@ -282,19 +294,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
               }
             }
             // even lane keeps output o (channels c, c+1), odd lane output o+1 (channels c-1, c)
-            const float send = odd ? val[0] : val[1];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            const float lo = odd ? recv : val[0], hi = odd ? val[1] : recv;
-            const long long off = off0 + static_cast<long long>(o) * C;
-            if (FMT == 1) *reinterpret_cast<uint32_t*>(static_cast<__half*>(P.out) + off) = pack_f16(lo, hi);
-            else *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(P.out) + off) = pack_bf16(lo, hi);
-            if (P.out_bf) *reinterpret_cast<uint32_t*>(static_cast<__nv_bfloat16*>(P.out_bf) + off) = pack_bf16(lo, hi);
-            if (CODE) {
+            if (CODE) {                                    // one float exchange serves both tensors and the codes
+              const float send = odd ? val[0] : val[1];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+              const float lo = odd ? recv : val[0], hi = odd ? val[1] : recv;
+              *reinterpret_cast<uint32_t*>(po) = FMT == 1 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+              if (BFC) *reinterpret_cast<uint32_t*>(pb) = pack_bf16(lo, hi);
               const uint32_t csend = odd ? cd[0] : cd[1];
               const uint32_t crecv = __shfl_xor_sync(0xffffffffu, csend, 1);
               const uint32_t byte = odd ? (crecv | (cd[1] << 4)) : (cd[0] | (crecv << 4));
-              if (P.code) P.code[cof0 + static_cast<long long>(o) * (C >> 1)] = static_cast<uint8_t>(byte);
+              *pc = static_cast<uint8_t>(byte);
+              pc += C;
+            } else {                                       // pack first, exchange the packed word, pick halves by PRMT
+              const uint32_t pk = FMT == 1 ? pack_f16(val[0], val[1]) : pack_bf16(val[0], val[1]);
+              *reinterpret_cast<uint32_t*>(po) = __byte_perm(pk, __shfl_xor_sync(0xffffffffu, pk, 1), psel);
+              if (BFC) {
+                const uint32_t pk2 = pack_bf16(val[0], val[1]);
+                *reinterpret_cast<uint32_t*>(pb) = __byte_perm(pk2, __shfl_xor_sync(0xffffffffu, pk2, 1), psel);
+              }
             }
+            po += ostep;
+            if (BFC) pb += ostep;
           }
         }
         tc_fence_before();
@@ -305,14 +325,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) tmem_dealloc(tmem_base, 512);
+  if (warp == mma_w) tmem_dealloc(tmem_base, 512);
 }
 
 int g_head_tc_mode = -1;            // -1: read HTRVT_STEMHEAD_TC (default on), 0 off, 1 on
 
-template <bool CODE, int FMT>       // one function per kernel: HTRVT_ENSURE_SMEM remembers per call site
+template <bool CODE, int FMT, bool BFC>       // one function per kernel: HTRVT_ENSURE_SMEM remembers per call site
 int tc_launch_one(const TcHeadP& P, int grid, cudaStream_t stream) {
-  auto kern = stem_head_tc_kernel<CODE, FMT>;
+  auto kern = stem_head_tc_kernel<CODE, FMT, BFC>;
   if (!HTRVT_ENSURE_SMEM(kern, kTcSmem)) return HTRVT_ERR_LAUNCH;
   kern<<<grid, kTcThreads, kTcSmem, stream>>>(P);
   HTRVT_LAUNCH_CHECK();
@@ -342,13 +362,19 @@ int stem_head_tc_launch(const float* x, const float* w, const float* scale, cons
   P.x = x; P.w = w; P.scale = scale; P.shift = shift; P.out = out; P.out_bf = out_bf; P.code = static_cast<uint8_t*>(code);
   P.B = B; P.H = H; P.W = W; P.C = C; P.Hc = H / 2; P.Ho = (P.Hc - 1) / 2 + 1;
   P.ngroups = C > 128 ? 2 : 1; P.cg = C / P.ngroups; P.tiles_w = W / kTcOut;
-  P.units = static_cast<long long>(B) * P.Ho * P.tiles_w;
+  const long long units = static_cast<long long>(B) * P.Ho * P.tiles_w;
+  if (units > 0x7fffffffLL) return HTRVT_ERR_SHAPE;
+  P.units = static_cast<int>(units);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = P.units < sms ? static_cast<int>(P.units) : sms;
-  if (code) return out_fmt == 1 ? tc_launch_one<true, 1>(P, grid, stream) : tc_launch_one<true, 0>(P, grid, stream);
-  return out_fmt == 1 ? tc_launch_one<false, 1>(P, grid, stream) : tc_launch_one<false, 0>(P, grid, stream);
+  if (out_fmt == 0) {                                  // bf16 output: it is its own bf16 copy
+    P.out_bf = nullptr;
+    return code ? tc_launch_one<true, 0, false>(P, grid, stream) : tc_launch_one<false, 0, false>(P, grid, stream);
+  }
+  if (code) return out_bf ? tc_launch_one<true, 1, true>(P, grid, stream) : tc_launch_one<true, 1, false>(P, grid, stream);
+  return out_bf ? tc_launch_one<false, 1, true>(P, grid, stream) : tc_launch_one<false, 1, false>(P, grid, stream);
 }
 
 }  // namespace htrvt
