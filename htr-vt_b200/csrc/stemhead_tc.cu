@@ -79,10 +79,14 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 
+// u / d for u < 2^21, d <= 2048 with m = ceil(2^32 / d)
+__device__ __forceinline__ int fast_div(int u, uint32_t m, int d) { return d == 1 ? u : static_cast<int>(__umulhi(static_cast<uint32_t>(u), m)); }
+
 struct TcHeadP {
   const float* x; const float* w; const float* scale; const float* shift;
   void* out; void* out_bf; uint8_t* code;
   int B, H, W, C, Ho, Hc, ngroups, cg, tiles_w;
+  uint32_t mul_tw, mul_ho;       // ceil(2^32 / tiles_w), ceil(2^32 / Ho): exact quotients for the unit counts admitted below
   int units;
 };
 
@@ -138,8 +142,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
     // the patch rows of unit u are built, so their latency hides under the build.
     float v0[7], v1[7];
     auto load_unit = [&](int u) {
-      const int wt = u % P.tiles_w, rw = u / P.tiles_w;
-      const int ho = rw % P.Ho, n = rw / P.Ho;
+      const int rw = fast_div(u, P.mul_tw, P.tiles_w), wt = u - rw * P.tiles_w;
+      const int n = fast_div(rw, P.mul_ho, P.Ho), ho = rw - n * P.Ho;
       const int ww0 = wt * kTcOut - 9 + t, ww1 = ww0 + 64;
       const bool c0ok = ww0 >= 0 && ww0 < W, c1ok = t < 18 && ww1 < W;
 #pragma unroll
@@ -213,8 +217,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) stem_head_tc_kernel(const TcHea
     // a lane quadrant without real channels (C = 192: rows 96-127 of the M = 128 tile) has nothing to do and is not
     // counted in tempty
     for (int u = (warp < 8 && 32 * q < cg) ? static_cast<int>(blockIdx.x) : P.units; u < P.units; u += gridDim.x, ++it) {
-      const int wt = u % P.tiles_w, rw = u / P.tiles_w;
-      const int ho = rw % P.Ho, n = rw / P.Ho;
+      const int rw = fast_div(u, P.mul_tw, P.tiles_w), wt = u - rw * P.tiles_w;
+      const int n = fast_div(rw, P.mul_ho, P.Ho), ho = rw - n * P.Ho;
       const int w0 = wt * kTcOut;
       for (int g = 0; g < P.ngroups; ++g, ++item) {
         const int tb = item & 1;
@@ -353,6 +357,8 @@ int stem_head_tc_supported(int B, int H, int W, int C, int out_fmt) {
   const int ng = C > 128 ? 2 : 1;
   if (C % ng) return 0;
   const int cg = C / ng;
+  const int Ho = (H / 2 - 1) / 2 + 1;
+  if (static_cast<long long>(B) * Ho * (W / kTcOut) >= (1LL << 21) || Ho > 2048 || W / kTcOut > 2048) return 0;   // fast_div range
   return (cg % 32) == 0;
 }
 
@@ -363,7 +369,9 @@ int stem_head_tc_launch(const float* x, const float* w, const float* scale, cons
   P.B = B; P.H = H; P.W = W; P.C = C; P.Hc = H / 2; P.Ho = (P.Hc - 1) / 2 + 1;
   P.ngroups = C > 128 ? 2 : 1; P.cg = C / P.ngroups; P.tiles_w = W / kTcOut;
   const long long units = static_cast<long long>(B) * P.Ho * P.tiles_w;
-  if (units > 0x7fffffffLL) return HTRVT_ERR_SHAPE;
+  if (units >= (1LL << 21) || P.tiles_w > 2048 || P.Ho > 2048) return HTRVT_ERR_SHAPE;
+  P.mul_tw = static_cast<uint32_t>(((1ULL << 32) + P.tiles_w - 1) / P.tiles_w);
+  P.mul_ho = static_cast<uint32_t>(((1ULL << 32) + P.Ho - 1) / P.Ho);
   P.units = static_cast<int>(units);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
