@@ -392,10 +392,25 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < 4; ++i) dst[i] = __ldg(rp + i);
       }
     };
+    uint32_t mw_nxt = 0u;
+    auto mask_load = [&](const TileCoord& tc, int col) -> uint32_t {      // BNB: ReLU mask bits of 32 channels of a pixel
+      const int w = tc.w0 + r;
+      if (w < P.Wo && col < P.N_valid)
+        return __ldg(reinterpret_cast<const uint32_t*>(
+            P.mask + ((((static_cast<long long>(tc.n) * P.Ho + tc.h) * P.Wo + w) * P.N_valid + col) >> 3)));
+      return 0u;
+    };
+    constexpr bool kResEpi = GELUB || BNB;              // epilogues that always read a second tensor
     int as = 0; uint32_t aphase = 0;
     for (int id = first_tile; id < total_tiles; id += tile_step) {
       const TileCoord tc = decode_tile(P, id);
       const int n0 = tc.n_tile * BN;
+      if (kResEpi && KIND == 0) {
+        // the first box's rows of the second tensor are requested BEFORE the wait for the accumulator: their L2 / DRAM
+        // round trip runs under the tile's MMAs
+        res_load(tc, n0 + half * kColsPerWarp, rq_nxt);
+        if (BNB) mw_nxt = mask_load(tc, n0 + half * kColsPerWarp);
+      }
       if (((P.flags & EPI_STATS) || colsum) && tc.n_tile != stats_ntile) { flush_stats(stats_ntile); stats_ntile = tc.n_tile; }
 #pragma unroll 1
       for (int sub = 0; sub < (W4 ? 2 : 1); ++sub) {          // KIND 4: a unit = two accumulators = two 128-row tiles
@@ -439,7 +454,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (KIND == 0 && (GELUB || BNB || (!GELU && (P.flags & EPI_RES)))) {   // this thread's output pixel, 32 consecutive channels
             // the 64 bytes of box b were requested one box earlier (rq_nxt): an L2 / DRAM round trip per box would
             // otherwise sit between the TMEM load and the store of every box of this warp
-            if (b == 0) res_load(tc, col, rq);
+            if (b == 0 && !kResEpi) res_load(tc, col, rq);
             else {
 #pragma unroll
               for (int i = 0; i < 4; ++i) rq[i] = rq_nxt[i];
@@ -449,10 +464,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t* rw = reinterpret_cast<const uint32_t*>(rq);
           uint32_t mword = 0u;                               // BNB: ReLU mask bits of this pixel's 32 channels
           if (BNB) {
-            const int w = tc.w0 + r;
-            if (w < P.Wo && col < P.N_valid)
-              mword = __ldg(reinterpret_cast<const uint32_t*>(
-                  P.mask + ((((static_cast<long long>(tc.n) * P.Ho + tc.h) * P.Wo + w) * P.N_valid + col) >> 3)));
+            mword = mw_nxt;
+            if (b + 1 < nboxes) mw_nxt = mask_load(tc, col + box_cols);
           }
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
