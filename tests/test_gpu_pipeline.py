@@ -150,3 +150,30 @@ def test_eval_weight_cache_follows_parameter_updates():
         ema.update(m)                                      # raw-pointer kernel: epoch bump
         e1 = ema.ema(x)
         assert float((e1 - e0).abs().max()) > 1e-3
+
+
+def test_host_prefetcher_double_buffers_batches_in_order():
+    """HostPrefetcher: the copies of batch i+1 run on a side stream under batch i's kernels; every get() returns the
+    values of the batch put last, also when a slot is refilled while the compute stream is still busy with it."""
+    import htrvt_b200 as h
+    pf = h.HostPrefetcher("cuda")
+    batches = [(torch.full((64, 1, 64, 512), float(i)).pin_memory(), torch.arange(i, i + 7, dtype=torch.int32).pin_memory())
+               for i in range(6)]
+    busy = torch.randn(4096, 4096, device="cuda")
+    pf.put(*batches[0])
+    sums = []
+    for i in range(6):
+        img, ids = pf.get()
+        if i + 1 < 6:
+            pf.put(*batches[i + 1])
+        for _ in range(4):                        # keep the compute stream busy with work that READS the batch afterwards
+            busy = busy @ busy * 1e-3
+        sums.append((img.sum() / img.numel(), ids.clone()))
+    torch.cuda.synchronize()
+    for i, (s, ids) in enumerate(sums):
+        assert float(s) == float(i) and torch.equal(ids.cpu(), batches[i][1])
+    with pytest.raises(RuntimeError):
+        pf.get()
+    dev_t = torch.ones(3, device="cuda")
+    pf.put(dev_t)                                 # device tensors pass through
+    assert pf.get() is dev_t
