@@ -334,7 +334,7 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
                                     "recursion runs in the linear domain on the FP64 pipe (fallbacks to log space: %d)"
                                     % ops.lib().htrvt_ctc_fallback_count()}
     del bufs
-    # a batch that fills the chip: the lane-group throughput kernel (ctc_grp.cu, automatic for B >= 1200)
+    # a batch that fills the chip: the lane-group throughput kernel (ctc_grp.cu, automatic for B >= 1024)
     Bl = 4096
     xl = torch.randn(Bl, T, C, device=dev)
     _, tgl, tll = synth_batch(Bl, 3)

@@ -813,18 +813,18 @@ int tput_mode() {
 }
 // measured on B200 (tools/ctc_grp_probe.py, T = 128, C = 80): the CTA-per-sequence kernel takes 23 us per wave of 148
 // sequences (169 us at B = 1024, 334 us at 2048), the lane-group kernel ~170 us for anything up to one resident wave
-// (B <= ~2400) and 270 us at B = 4096: break-even just above B = 1024
-constexpr int kGrpMinBatch = 1200;
+// (B <= ~2400; 160 us with 8 states per lane) and 270 us at B = 4096: break-even at B ~ 1000
+constexpr int kGrpMinBatch = 1024;
 bool use_grp(int B, int T, int C, int lmax) {
   const int mode = tput_mode();
-  if (mode == 0 || !ctc_grp_supported(T, C, lmax)) return false;
+  if (mode == 0 || !ctc_grp_supported(B, T, C, lmax)) return false;
   return mode == 1 || B >= kGrpMinBatch;
 }
 size_t tput_flag_bytes(int B) { return (static_cast<size_t>(2 * B) * sizeof(int) + 255) & ~size_t(255); }   // flags + offsets
 size_t fixup_bytes(int B, int T, int kmax) { return (static_cast<size_t>(B) * 2 * T * 32 * kmax * sizeof(float) + 255) & ~size_t(255); }
 }  // namespace
 
-// kernel selection: -1 automatic (lane-group throughput kernel for B >= 1200), 0 CTA-per-sequence kernel only,
+// kernel selection: -1 automatic (lane-group throughput kernel for B >= 1024), 0 CTA-per-sequence kernel only,
 // 1 lane-group kernel at any batch size (tests).  Returns the previous mode.
 extern "C" int htrvt_ctc_set_mode(int mode) {
   const int prev = g_tput_mode == -2 ? -1 : g_tput_mode;

@@ -47,7 +47,7 @@ int ctc_offsets_launch(const int* lengths, int B, int* offsets, cudaStream_t str
 // lane-group throughput kernel (ctc_grp.cu): G lanes per sequence, fp32 linear domain, alpha rows in a per-warp global
 // scratch.  Handles every sequence it can and sets flags[b] = 1 for the rest (label longer than 8 G, or the consistency
 // guard tripped): those are redone by ctc.cu's kernel in a fix-up launch.  lmax = longest label of the batch (<= 256)
-bool ctc_grp_supported(int T, int C, int lmax);
+bool ctc_grp_supported(int B, int T, int C, int lmax);
 size_t ctc_grp_scratch_bytes(int B, int T, int C, int lmax, int sms);
 int ctc_grp_launch(const CtcParams& P, int lmax, int* flags, const int* offsets, void* scratch, int sms,
                    cudaStream_t stream);

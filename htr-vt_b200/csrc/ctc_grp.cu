@@ -5,7 +5,7 @@
 // issued 55 k warp instructions per sequence at 0.45 IPC; it is gone): the cost of CTC at B >> #SMs is instruction issue and per-step latency, so the layout minimises
 // instructions per (t, s) cell, keeps the loop-carried chain of a step to three FP32 instructions and software-pipelines
 // everything else around it:
-//   states    16 CONSECUTIVE states per lane in registers (state s = 1 + 16 j + i on lane j: even i = label, odd i =
+//   states    K = 16 (or 8) CONSECUTIVE states per lane in registers (state s = 1 + K j + i on lane j: even i = label, odd i =
 //             blank), state 0 rides on lane 0 as a scalar.  A step is 2 (blank) / 3 (label) FP32 instructions per state,
 //             two shuffles per lane for alpha and one for beta; the 16 updates of a lane are independent (ILP 16);
 //   domain    linear fp32 with an exact power-of-two rescale every step.  The scale applied at step t comes from the row
@@ -69,6 +69,19 @@ __device__ __forceinline__ float grp_sum(float v, unsigned m) {
   for (int d = G / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(m, v, d);
   return v;
 }
+// reductions of a register array as balanced trees (a sequential `acc = op(acc, x[i])` chain is N dependent
+// instructions: FP addition is not reassociated by the compiler)
+template <int N, int STRIDE = 1>
+__device__ __forceinline__ float tree_max(const float* x) {
+  if constexpr (N == 1) return x[0];
+  else return fmaxf(tree_max<N / 2, STRIDE>(x), tree_max<N - N / 2, STRIDE>(x + (N / 2) * STRIDE));
+}
+template <int N, int STRIDE = 1>
+__device__ __forceinline__ float tree_sum(const float* x) {
+  if constexpr (N == 1) return x[0];
+  else return tree_sum<N / 2, STRIDE>(x) + tree_sum<N - N / 2, STRIDE>(x + (N / 2) * STRIDE);
+}
+
 // exact 2^e as a float, e clamped to the normal range
 __device__ __forceinline__ float grp_pow2(int e) { return __int_as_float((127 + min(max(e, -126), 127)) << 23); }
 // deadbeat rescale: mx = reduced row maximum measured two steps ago, kprev = shift applied since then.
@@ -131,26 +144,29 @@ constexpr int kGrpPF = 12;                     // rows ahead of the sweeps that 
 // One sequence on the G lanes of a group.  Returns false if it must be redone by the fix-up kernel.
 // NQ > 0: every lane handles exactly NQ 16-byte chunks of a row (index clamped to the last chunk: duplicates are
 // harmless for max / identical stores, `clive` masks sums); NQ == 0: runtime chunk loops.
-template <int G, int NQ>
+template <int G, int NQ, int K>
 __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restrict__ tg, int j, unsigned gm, float* nll_out) {
   const int L = q.L, Tb = q.Tb, C = q.C;
   const int C4v = (C + 3) >> 2;                         // 16-byte chunks of a row that hold classes
   constexpr int NGw = 32 / G;
   constexpr int NR = kGrpNR, NX = kGrpNX;
+  constexpr int KL = K / 2;                             // labels per lane
+  constexpr int KQ = K / 4;                             // float4 quarters of a lane's alpha row
+  static_assert(K == 8 || K == 16, "states per lane");
   constexpr int NQs = NQ > 0 ? NQ : 1;
   const uint32_t ldr4 = static_cast<uint32_t>(q.ldr) * 4u;
   // ---- labels of this lane: k = 8 j + i; byte offset of the emission column (pad column C: emission 0 for k >= L) -------
-  uint32_t lab4[8];
-  float mk[9];                                          // mk[i]: skip transition INTO label k allowed (label k != label k-1)
+  uint32_t lab4[KL];
+  float mk[KL + 1];                                          // mk[i]: skip transition INTO label k allowed (label k != label k-1)
   {
     int prev = -1;
-    if (8 * j - 1 >= 0 && 8 * j - 1 < L) prev = min(max(tg[8 * j - 1], 0), C - 1);
+    if (KL * j - 1 >= 0 && KL * j - 1 < L) prev = min(max(tg[KL * j - 1], 0), C - 1);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const int k = 8 * j + i;
+    for (int i = 0; i < KL + 1; ++i) {
+      const int k = KL * j + i;
       int v = -2;
       if (k < L) v = min(max(tg[k], 0), C - 1);
-      if (i < 8) lab4[i] = static_cast<uint32_t>(k < L ? v : C) * 4u;
+      if (i < KL) lab4[i] = static_cast<uint32_t>(k < L ? v : C) * 4u;
       mk[i] = (k < L && k >= 1 && v != prev) ? 1.f : 0.f;
       prev = v;
     }
@@ -162,11 +178,11 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
     clive[u] = j + G * u < C4v;
     coff[u] = static_cast<uint32_t>(clive[u] ? j + G * u : C4v - 1) * 16u;
   }
-  const bool own = 16 * j + 1 <= 2 * L;                 // the lane holds at least one real state
-  const int s0 = 1 + 16 * j;                            // state of a[0]
+  const bool own = K * j + 1 <= 2 * L;                  // the lane holds at least one real state
+  const int s0 = 1 + K * j;                             // state of a[0]
   if (!own) {                                           // its slice of the alpha ring reads as zeros
 #pragma unroll
-    for (int u = 0; u < 4 * NR; ++u) sts_z4(q.aring + u * 512);
+    for (int u = 0; u < KQ * NR; ++u) sts_z4(q.aring + u * 512);
   }
   const int pfl = static_cast<int>(threadIdx.x & 31);   // L2 prefetch: lane l pulls 128-byte line l of a row
 
@@ -190,10 +206,10 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
   auto stage_a = [&](int r) {                           // alpha row r -> ring (no commit)
     if (r >= 0 && r < Tb) {
       if (own) {
-        const uint32_t d = q.aring + static_cast<uint32_t>(r & (NR - 1)) * 2048u;
-        const float4* src = q.arow + r * 128;
+        const uint32_t d = q.aring + static_cast<uint32_t>(r & (NR - 1)) * (KQ * 512u);
+        const float4* src = q.arow + r * (KQ * 32);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) grp_cp16(d + u * 512, src + u * 32);
+        for (int u = 0; u < KQ; ++u) grp_cp16(d + u * 512, src + u * 32);
       }
       if (j == 0) grp_cp8(q.a0ring + static_cast<uint32_t>(r & (NR - 1)) * 8u, q.a0row + r * NGw);
     }
@@ -204,24 +220,24 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
   };
 
   // ================================ alpha sweep =========================================================================
-  float a[16];
+  float a[K];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) a[i] = 0.f;
+  for (int i = 0; i < K; ++i) a[i] = 0.f;
   float a0 = j == 0 ? grp_pow2(kGrpTgt) : 0.f;          // "alpha_{-1}": all mass in front of state 0, pre-scaled
   int KA = -kGrpTgt;                                    // stored alpha = alpha_e * 2^-KA
   int ksc = 0;                                          // shift applied in the current step
   float sc = 1.f;
   float mx_old = grp_pow2(kGrpTgt);                     // reduced maximum measured one step ago
-  float ecb = 0.f, ec[8];                               // raw emissions of the row the alpha step consumes
+  float ecb = 0.f, ec[KL];                              // raw emissions of the row the alpha step consumes
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ec[i] = 0.f;
+  for (int i = 0; i < KL; ++i) ec[i] = 0.f;
 
   // iteration t: [row maximum + raw emissions of row t + 1] | [alpha step of row t]
   auto fwd_iter = [&](bool do_g, bool do_s, int t) {
-    float xb = 0.f, xg[8];
+    float xb = 0.f, xg[KL];
     float m = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xg[i] = 0.f;
+    for (int i = 0; i < KL; ++i) xg[i] = 0.f;
     if (do_g) {                                         // loads first
       const uint32_t row = q.ring + static_cast<uint32_t>((t + 1) & (NX - 1)) * ldr4;
       if (NQ > 0) {
@@ -230,13 +246,13 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
         for (int u = 0; u < NQs; ++u) v[u] = lds_f4(row + coff[u]);
         xb = lds_f(row);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xg[i] = lds_f(row + lab4[i]);
+        for (int i = 0; i < KL; ++i) xg[i] = lds_f(row + lab4[i]);
 #pragma unroll
         for (int u = 0; u < NQs; ++u) m = fmaxf(fmaxf(m, fmaxf(v[u].x, v[u].y)), fmaxf(v[u].z, v[u].w));
       } else {
         xb = lds_f(row);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xg[i] = lds_f(row + lab4[i]);
+        for (int i = 0; i < KL; ++i) xg[i] = lds_f(row + lab4[i]);
         for (int c4 = j; c4 < C4v; c4 += G) {
           const float4 v = lds_f4(row + 16 * c4);
           m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
@@ -246,14 +262,14 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
     }
     if (do_s) {
       const float eb = ecb * sc;
-      float e[8];
+      float e[KL];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) e[i] = ec[i] * sc;
+      for (int i = 0; i < KL; ++i) e[i] = ec[i] * sc;
       KA += ksc;
-      float p1 = __shfl_up_sync(gm, a[15], 1, G), p2 = __shfl_up_sync(gm, a[14], 1, G);
+      float p1 = __shfl_up_sync(gm, a[K - 1], 1, G), p2 = __shfl_up_sync(gm, a[K - 2], 1, G);
       if (j == 0) { p1 = a0; p2 = 0.f; }
 #pragma unroll
-      for (int i = 15; i >= 0; --i) {                   // descending: a[i-1], a[i-2] are still the previous row
+      for (int i = K - 1; i >= 0; --i) {                // descending: a[i-1], a[i-2] are still the previous row
         const float x1 = i >= 1 ? a[i >= 1 ? i - 1 : 0] : p1;
         if (i & 1) {
           a[i] = (a[i] + x1) * eb;
@@ -263,15 +279,13 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
         }
       }
       a0 *= eb;
-      float4* dst = q.arow + t * 128;
+      float4* dst = q.arow + t * (KQ * 32);
       if (own) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) dst[u * 32] = make_float4(a[4 * u], a[4 * u + 1], a[4 * u + 2], a[4 * u + 3]);
+        for (int u = 0; u < KQ; ++u) dst[u * 32] = make_float4(a[4 * u], a[4 * u + 1], a[4 * u + 2], a[4 * u + 3]);
       }
       if (j == 0) q.a0row[t * NGw] = make_float2(a0, __int_as_float(KA));
-      float mx = a0;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) mx = fmaxf(mx, a[i]);
+      float mx = fmaxf(a0, tree_max<K>(a));
       mx = grp_max<G>(mx, gm);                          // consumed one step later
       ksc = grp_shift(mx_old, ksc);                     // shift for the next step: measured at t - 1, minus the shift of t
       sc = grp_pow2(-ksc);
@@ -282,7 +296,7 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
       if (j == 0) sts_f(q.mrow + (t + 1) * 4, mL);
       ecb = ex2f(fmaf(xb, kLog2e, -mL));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ec[i] = ex2f(fmaf(xg[i], kLog2e, -mL));
+      for (int i = 0; i < KL; ++i) ec[i] = ex2f(fmaf(xg[i], kLog2e, -mL));
     }
   };
 
@@ -301,7 +315,7 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
   // likelihood (emission domain): Z_e = (alpha(2L) + alpha(2L - 1)) * 2^KA
   float z = (j == 0 && L == 0) ? a0 : 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < K; ++i) {
     const int s = s0 + i;
     if (s == 2 * L || s == 2 * L - 1) z += a[i];
   }
@@ -343,9 +357,9 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
     return true;
   }
 
-  float bp[16];                                         // beta'_t (without the emission of row t), scaled by 2^-KB
+  float bp[K];                                          // beta'_t (without the emission of row t), scaled by 2^-KB
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < K; ++i) {
     const int s = s0 + i;
     bp[i] = (s == 2 * L || s == 2 * L - 1) ? grp_pow2(kGrpTgt) : 0.f;
   }
@@ -371,8 +385,8 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
     float4 xv[NQs], ev[NQs];
     int4 bv[NQs];
     float mLd = 0.f;
-    float an[16], an0 = 0.f;
-    float eg[8], egb = 0.f;
+    float an[K], an0 = 0.f;
+    float eg[KL], egb = 0.f;
     int KAt = 0;
 #pragma unroll
     for (int u = 0; u < NQs; ++u) {
@@ -381,9 +395,9 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
       bv[u] = make_int4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) an[i] = 0.f;
+    for (int i = 0; i < K; ++i) an[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) eg[i] = 0.f;
+    for (int i = 0; i < KL; ++i) eg[i] = 0.f;
     if (do_d) {
       const uint32_t row = q.ring + static_cast<uint32_t>((t - 1) & (NX - 1)) * ldr4;
       mLd = lds_f(q.mrow + (t - 1) * 4);
@@ -393,9 +407,9 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
       }
     }
     if (do_s) {
-      const uint32_t ar = q.aring + static_cast<uint32_t>(t & (NR - 1)) * 2048u;
+      const uint32_t ar = q.aring + static_cast<uint32_t>(t & (NR - 1)) * (KQ * 512u);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < KQ; ++u) {
         const float4 v = lds_f4(ar + u * 512);
         an[4 * u] = v.x; an[4 * u + 1] = v.y; an[4 * u + 2] = v.z; an[4 * u + 3] = v.w;
       }
@@ -404,7 +418,7 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
       KAt = __float_as_int(a0k.y);
       egb = lds_f(e_cur);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) eg[i] = lds_f(e_cur + lab4[i]);
+      for (int i = 0; i < KL; ++i) eg[i] = lds_f(e_cur + lab4[i]);
     }
     if (do_g && q.gvec && NQ > 0) {
 #pragma unroll
@@ -447,40 +461,38 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
       const int E = 22 - ez + (KAt + KB - Kfin);
       if (E < -126 || E > 126) ok = false;           // the row's posterior mass lies > 2^100 below the row maxima: fp64 kernel
       const float rr = rzm * grp_pow2(E);
-      float tot = an0 * bp0, blank = an0 * bp0;
+      float ab[K];
+      const float ab0 = an0 * bp0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float ab = an[i] * bp[i];
-        tot += ab;
-        if (i & 1) blank += ab;
-        else red_s(b_cur + lab4[i >> 1], __float_as_int(fmaf(ab, rr, kGrpMagic)) - kGrpMagicBits);
-      }
+      for (int i = 0; i < K; ++i) ab[i] = an[i] * bp[i];
+#pragma unroll
+      for (int i = 0; i < K; i += 2) red_s(b_cur + lab4[i >> 1], __float_as_int(fmaf(ab[i], rr, kGrpMagic)) - kGrpMagicBits);
+      const float blank = tree_sum<KL, 2>(ab + 1) + ab0;
+      const float tot = tree_sum<KL, 2>(ab) + blank;
       red_s(b_cur, __float_as_int(fmaf(blank, rr, kGrpMagic)) - kGrpMagicBits);
       // deferred guard: the previous row's posteriors must sum to 2^22 counts
       if (!(fabsf(tot_chk - kGrpFix) < kGrpTolCounts)) ok = false;
       tot_chk = grp_sum<G>(tot, gm) * rr;
       const float ebs = egb * scb;
-      float bb[16];
+      float bb[K];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) bb[i] = bp[i] * ((i & 1) ? ebs : eg[i >> 1] * scb);
+      for (int i = 0; i < K; ++i) bb[i] = bp[i] * ((i & 1) ? ebs : eg[i >> 1] * scb);
       const float b0 = bp0 * ebs;
       float n1 = __shfl_down_sync(gm, bb[0], 1, G);
       if (j == G - 1) n1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float y1 = i + 1 < 16 ? bb[i + 1 < 16 ? i + 1 : 0] : n1;
+      for (int i = 0; i < K; ++i) {
+        const float y1 = i + 1 < K ? bb[i + 1 < K ? i + 1 : 0] : n1;
         if (i & 1) {
           bp[i] = bb[i] + y1;
         } else {
-          const float y2 = i + 2 < 16 ? bb[i + 2 < 16 ? i + 2 : 0] : n1;
+          const float y2 = i + 2 < K ? bb[i + 2 < K ? i + 2 : 0] : n1;
           bp[i] = fmaf(mk[(i >> 1) + 1], y2, bb[i] + y1);
         }
       }
       bp0 = j == 0 ? b0 + bb[0] : 0.f;
       KB += kscb;
-      float mx = bp0;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) mx = fmaxf(mx, bp[i]);
+      float mx = fmaxf(bp0, tree_max<K>(bp));
       mx = grp_max<G>(mx, gm);                          // consumed one step later
       kscb = grp_shift(mxb_old, kscb);
       scb = grp_pow2(-kscb);
@@ -542,8 +554,8 @@ __device__ __forceinline__ bool grp_sequence(const GrpSeq& q, const int* __restr
     stage_a(t + 1 - NR);
     grp_commit();
     pull_x(t - kGrpPF);
-    if (t - kGrpPF >= 0 && pfl < 16)
-      prefetch_l2(reinterpret_cast<const char*>(q.arow - pfl + (t - kGrpPF) * 128) + pfl * 128);
+    if (t - kGrpPF >= 0 && pfl < KQ * 4)
+      prefetch_l2(reinterpret_cast<const char*>(q.arow - pfl + (t - kGrpPF) * (KQ * 32)) + pfl * 128);
     if (t >= 1 && t + 1 < Tb) bwd_iter(true, true, true, t);       // steady state: the three stages in one basic block
     else bwd_iter(t >= 1, t >= 0 && t < Tb, t + 1 < Tb, t);
     s_old = s_mid; s_mid = s_new;
@@ -562,12 +574,16 @@ static __host__ __device__ inline size_t grp_group_floats(int T, int C) {
   const int ldr = (C + 4) & ~3;
   return static_cast<size_t>(kGrpNX + 3 + 2) * ldr + ((T + 3) & ~3) + 2 * kGrpNR;
 }
-static __host__ __device__ inline size_t grp_warp_floats(int T, int C, int G) {
-  return static_cast<size_t>(kGrpNR) * 4 * 32 * 4 + (32 / G) * grp_group_floats(T, C);
+// per warp: the alpha ring (kGrpNR rows of 32 lanes x K floats) + the groups' private buffers
+static __host__ __device__ inline size_t grp_warp_floats(int T, int C, int G, int K) {
+  return static_cast<size_t>(kGrpNR) * 32 * K + (32 / G) * grp_group_floats(T, C);
 }
 
-template <int G, int NQ>
-__global__ void __launch_bounds__(kGrpWarps * 32, 4) ctc_grp_kernel(const CtcParams P, int* __restrict__ flags,
+// resident CTAs per SM the register budget is sized for: K = 16 -> 4 (255 registers), K = 8 -> 7 (146 registers)
+constexpr int grp_min_ctas(int K) { return K == 8 ? 7 : 4; }
+
+template <int G, int NQ, int K>
+__global__ void __launch_bounds__(kGrpWarps * 32, grp_min_ctas(K)) ctc_grp_kernel(const CtcParams P, int* __restrict__ flags,
                                                                const int* __restrict__ offsets,
                                                                float4* __restrict__ ascr, float2* __restrict__ a0scr) {
   extern __shared__ __align__(16) unsigned char grp_smem[];
@@ -577,8 +593,8 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) ctc_grp_kernel(const CtcPar
   const unsigned gm = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
   const int T = P.T, C = P.C;
   const int ldr = (C + 4) & ~3;
-  float* wbase = reinterpret_cast<float*>(grp_smem) + warp * grp_warp_floats(T, C, G);
-  float* gbase = wbase + kGrpNR * 4 * 32 * 4 + grp * grp_group_floats(T, C);
+  float* wbase = reinterpret_cast<float*>(grp_smem) + warp * grp_warp_floats(T, C, G, K);
+  float* gbase = wbase + kGrpNR * 32 * K + grp * grp_group_floats(T, C);
   GrpSeq q;
   float* erow_p = gbase + kGrpNX * ldr;
   int* bins_p = reinterpret_cast<int*>(erow_p + 3 * ldr);
@@ -596,7 +612,7 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) ctc_grp_kernel(const CtcPar
   for (int c = j; c < 2 * ldr; c += G) bins_p[c] = 0;
   __syncwarp(gm);
   const int slot = blockIdx.x * kGrpWarps + warp, nslots = gridDim.x * kGrpWarps;
-  q.arow = ascr + static_cast<size_t>(slot) * T * 128 + lane;
+  q.arow = ascr + static_cast<size_t>(slot) * T * (K * 8) + lane;
   q.a0row = a0scr + static_cast<size_t>(slot) * T * NGw + grp;
   const int npacks = (P.B + NGw - 1) / NGw;
   for (int pack = slot; pack < npacks; pack += nslots) {
@@ -606,7 +622,7 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) ctc_grp_kernel(const CtcPar
     Tb = min(max(Tb, 0), T);
     const int L = P.target_lengths[b];
     float* gb = P.grad ? P.grad + static_cast<long long>(b) * P.g_sb : nullptr;
-    if (L < 0 || L > 8 * G) {                            // not provisioned here: the CTA-per-sequence kernel takes it
+    if (L < 0 || L > (K / 2) * G) {                            // not provisioned here: the CTA-per-sequence kernel takes it
       if (j == 0) flags[b] = 1;
       continue;
     }
@@ -639,7 +655,7 @@ __global__ void __launch_bounds__(kGrpWarps * 32, 4) ctc_grp_kernel(const CtcPar
     q.gvec = gb && ((C & 3) == 0) && ((P.g_st & 3) == 0) && ((reinterpret_cast<uintptr_t>(gb) & 15) == 0);
     q.gs = P.grad_scale ? P.grad_scale[b] : P.grad_scale_const;
     float nll = 0.f;
-    bool ok = grp_sequence<G, NQ>(q, tg, j, gm, &nll);
+    bool ok = grp_sequence<G, NQ, K>(q, tg, j, gm, &nll);
     ok = __all_sync(gm, ok);
     if (!ok) {                                           // leave the shared-memory state clean for the next sequence
       for (int c = j; c < 2 * ldr; c += G) bins_p[c] = 0;
@@ -706,58 +722,93 @@ int ctc_num_sms() {
   return n[dev];
 }
 
-int ctc_grp_lanes(int lmax) { return lmax <= 32 ? 4 : (lmax <= 64 ? 8 : (lmax <= 128 ? 16 : (lmax <= 256 ? 32 : 0))); }
-
-static size_t grp_smem_bytes(int T, int C, int G) { return kGrpWarps * grp_warp_floats(T, C, G) * sizeof(float); }
-
-// resident CTAs per SM: shared memory (227 KB) and the register file (255 registers x 64 threads fit 4 times)
-static int grp_ctas_per_sm(int T, int C, int G) {
-  const size_t smem = grp_smem_bytes(T, C, G) + 1024;
-  int n = static_cast<int>((227 * 1024) / smem);
-  return n < 1 ? 0 : (n > 4 ? 4 : n);
+// Configuration: K states per lane (8 or 16) and G lanes per sequence (labels up to (K / 2) G).  K = 16 issues the fewest
+// instructions per sequence (4 sequences per warp at L <= 64); K = 8 halves a warp's work per time step and doubles the
+// warps - the better trade while the batch cannot fill the SMs with K = 16 warps (measured: tools/ctc_grp_probe.py).
+struct GrpCfgHost { int G, K; };
+static int g_grp_force_k = -1;                          // HTRVT_CTC_K = 8 / 16 (developer knob), 0 = automatic
+static GrpCfgHost grp_config(int B, int lmax, int sms) {
+  if (g_grp_force_k < 0) {
+    const char* e = getenv("HTRVT_CTC_K");
+    g_grp_force_k = e ? atoi(e) : 0;
+  }
+  auto lanes = [](int lm, int K) {
+    const int per = K / 2;
+    for (int G = 4; G <= 32; G *= 2)
+      if (lm <= per * G) return G;
+    return 0;
+  };
+  const int g16 = lanes(lmax, 16), g8 = lanes(lmax, 8);
+  GrpCfgHost c = {g16, 16};
+  if (g16 == 0) return c;
+  if (g8 != 0) {
+    const long long warps16 = (static_cast<long long>(B) * g16 + 31) / 32;
+    // measured (T = 128, C = 80, L <= 64): K = 8 wins up to B = 2048 (160 / 181 us against 179 / 188 us at B = 1024 / 2048:
+    // per-warp latency), K = 16 from B = 4096 (273 against 281 us: instruction count)
+    const bool want8 = g_grp_force_k == 8 || (g_grp_force_k != 16 && warps16 <= 4LL * sms);
+    if (want8) { c.G = g8; c.K = 8; }
+  }
+  return c;
 }
 
-static int grp_grid(int B, int T, int C, int G, int sms) {
+static size_t grp_smem_bytes(int T, int C, int G, int K) { return kGrpWarps * grp_warp_floats(T, C, G, K) * sizeof(float); }
+
+// resident CTAs per SM: shared memory (227 KB) and the register file (255 registers x 64 threads fit 4 times)
+static int grp_ctas_per_sm(int T, int C, int G, int K) {
+  const size_t smem = grp_smem_bytes(T, C, G, K) + 1024;
+  int n = static_cast<int>((227 * 1024) / smem);
+  const int cap = grp_min_ctas(K);
+  return n < 1 ? 0 : (n > cap ? cap : n);
+}
+
+static int grp_grid(int B, int T, int C, int G, int K, int sms) {
   const int npacks = (B + 32 / G - 1) / (32 / G);
   const int ctas = (npacks + kGrpWarps - 1) / kGrpWarps;
-  const int cap = grp_ctas_per_sm(T, C, G) * sms;
+  const int cap = grp_ctas_per_sm(T, C, G, K) * sms;
   return ctas < cap ? ctas : cap;
 }
 
-bool ctc_grp_supported(int T, int C, int lmax) {
-  const int G = ctc_grp_lanes(lmax);
-  return G != 0 && T >= 1 && grp_ctas_per_sm(T, C, G) >= 1;
+bool ctc_grp_supported(int B, int T, int C, int lmax) {
+  const GrpCfgHost c = grp_config(B, lmax, ctc_num_sms());
+  return c.G != 0 && T >= 1 && grp_ctas_per_sm(T, C, c.G, c.K) >= 1;
 }
 
-// bytes of alpha scratch the launch needs (per resident warp: T rows of 32 lanes x 16 floats + {alpha(0), exponent})
+// bytes of alpha scratch the launch needs (per resident warp: T rows of 32 lanes x K floats + {alpha(0), exponent})
 size_t ctc_grp_scratch_bytes(int B, int T, int C, int lmax, int sms) {
-  const int G = ctc_grp_lanes(lmax);
-  if (!G) return 0;
-  const size_t slots = static_cast<size_t>(grp_grid(B, T, C, G, sms)) * kGrpWarps;
-  return slots * T * (2048 + (32 / G) * 8) + 256;
+  const GrpCfgHost c = grp_config(B, lmax, sms);
+  if (!c.G) return 0;
+  const size_t slots = static_cast<size_t>(grp_grid(B, T, C, c.G, c.K, sms)) * kGrpWarps;
+  return slots * T * (static_cast<size_t>(128) * c.K + (32 / c.G) * 8) + 256;
 }
 
-template <int G, int NQ>
+template <int G, int NQ, int K>
 static int grp_launch_q(const CtcParams& P, int* flags, const int* offsets, void* scratch, int sms, cudaStream_t stream) {
-  const size_t smem = grp_smem_bytes(P.T, P.C, G);
-  if (smem > 48 * 1024 && !HTRVT_ENSURE_SMEM((ctc_grp_kernel<G, NQ>), smem)) return HTRVT_ERR_LAUNCH;
-  const int grid = grp_grid(P.B, P.T, P.C, G, sms);
+  const size_t smem = grp_smem_bytes(P.T, P.C, G, K);
+  if (smem > 48 * 1024 && !HTRVT_ENSURE_SMEM((ctc_grp_kernel<G, NQ, K>), smem)) return HTRVT_ERR_LAUNCH;
+  const int grid = grp_grid(P.B, P.T, P.C, G, K, sms);
   const size_t slots = static_cast<size_t>(grid) * kGrpWarps;
   float4* ascr = static_cast<float4*>(scratch);
-  float2* a0scr = reinterpret_cast<float2*>(static_cast<char*>(scratch) + slots * P.T * 2048);
-  ctc_grp_kernel<G, NQ><<<grid, kGrpWarps * 32, smem, stream>>>(P, flags, offsets, ascr, a0scr);
+  float2* a0scr = reinterpret_cast<float2*>(static_cast<char*>(scratch) + slots * P.T * 128 * K);
+  ctc_grp_kernel<G, NQ, K><<<grid, kGrpWarps * 32, smem, stream>>>(P, flags, offsets, ascr, a0scr);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
 
-template <int G>
-static int grp_launch_t(const CtcParams& P, int* flags, const int* offsets, void* scratch, int sms, cudaStream_t stream) {
-  const int nq = (((P.C + 3) >> 2) + G - 1) / G;        // 16-byte chunks of a row per lane
-  switch (nq) {
-    case 1: return grp_launch_q<G, 1>(P, flags, offsets, scratch, sms, stream);
-    case 2: return grp_launch_q<G, 2>(P, flags, offsets, scratch, sms, stream);
-    case 3: return grp_launch_q<G, 3>(P, flags, offsets, scratch, sms, stream);
-    default: return grp_launch_q<G, 0>(P, flags, offsets, scratch, sms, stream);
+// NQ = 16-byte chunks of a logits row per lane: the natural counts of C = 80 / 90 (and C = 228 at G = 32) are compiled,
+// anything else takes the runtime-loop instance
+template <int K>
+static int grp_launch_k(const CtcParams& P, int G, int* flags, const int* offsets, void* scratch, int sms, cudaStream_t stream) {
+  const int nq = (((P.C + 3) >> 2) + G - 1) / G;
+  switch (G) {
+    case 4: return grp_launch_q<4, 0, K>(P, flags, offsets, scratch, sms, stream);
+    case 8: return nq == 3 ? grp_launch_q<8, 3, K>(P, flags, offsets, scratch, sms, stream)
+                           : grp_launch_q<8, 0, K>(P, flags, offsets, scratch, sms, stream);
+    case 16: return nq == 2 ? grp_launch_q<16, 2, K>(P, flags, offsets, scratch, sms, stream)
+                            : grp_launch_q<16, 0, K>(P, flags, offsets, scratch, sms, stream);
+    case 32: return nq == 1 ? grp_launch_q<32, 1, K>(P, flags, offsets, scratch, sms, stream)
+                   : nq == 2 ? grp_launch_q<32, 2, K>(P, flags, offsets, scratch, sms, stream)
+                             : grp_launch_q<32, 0, K>(P, flags, offsets, scratch, sms, stream);
+    default: return HTRVT_ERR_SHAPE;
   }
 }
 
@@ -765,13 +816,10 @@ static int grp_launch_t(const CtcParams& P, int* flags, const int* offsets, void
 // concatenated); scratch: ctc_grp_scratch_bytes, 16-byte aligned
 int ctc_grp_launch(const CtcParams& P, int lmax, int* flags, const int* offsets, void* scratch, int sms,
                    cudaStream_t stream) {
-  switch (ctc_grp_lanes(lmax)) {
-    case 4: return grp_launch_t<4>(P, flags, offsets, scratch, sms, stream);
-    case 8: return grp_launch_t<8>(P, flags, offsets, scratch, sms, stream);
-    case 16: return grp_launch_t<16>(P, flags, offsets, scratch, sms, stream);
-    case 32: return grp_launch_t<32>(P, flags, offsets, scratch, sms, stream);
-    default: return HTRVT_ERR_SHAPE;
-  }
+  const GrpCfgHost c = grp_config(P.B, lmax, sms);
+  if (!c.G) return HTRVT_ERR_SHAPE;
+  return c.K == 8 ? grp_launch_k<8>(P, c.G, flags, offsets, scratch, sms, stream)
+                  : grp_launch_k<16>(P, c.G, flags, offsets, scratch, sms, stream);
 }
 
 }  // namespace htrvt

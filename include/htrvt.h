@@ -35,7 +35,7 @@ unsigned long long htrvt_launch_count(void); /* kernels launched so far by this 
  * nll[b] = 0 and grad = 0 for infeasible samples; grad may be NULL (loss only).
  * grad is scaled by grad_scale[b] (device, may be NULL) or grad_scale_const. */
 /* Two kernels serve htrvt_ctc_loss_grad: one CTA per sequence (latency: B up to a few sequences per SM; fp64 linear
- * domain with a log-space fallback) and a group of 4-32 lanes per sequence (throughput: B >= 1200, labels up to 256
+ * domain with a log-space fallback) and a group of 4-32 lanes per sequence (throughput: B >= 1024, labels up to 256
  * symbols, fp32 linear domain with a consistency guard); whatever the throughput kernel cannot finish is flagged and
  * redone by the first kernel in a fix-up launch.  htrvt_ctc_set_mode: -1 automatic, 0 CTA-per-sequence only, 1 lane-group
  * kernel at any batch size; returns the previous mode.  htrvt_ctc_flagged_count: sequences the lane-group kernel handed

@@ -118,7 +118,7 @@ def _flagged():
 
 
 def test_ctc_large_batch_kernels_agree():
-    """The lane-group kernel (forced: the automatic switch sits at B >= 1200) against the CTA-per-sequence kernel
+    """The lane-group kernel (forced: the automatic switch sits at B >= 1024) against the CTA-per-sequence kernel
     on the same 1024 sequences, and against the float64 reference on a subset; infeasible / empty / ragged sequences mixed in."""
     from importlib import import_module
     h = _pkg()
