@@ -2,9 +2,9 @@
 
 The reference is single-GPU; this is the B200-native scale-out of its training step.
 The encoder's backward writes every parameter gradient into ONE flat fp32 buffer laid out in
-named_parameters() order, so the exchange is two NCCL calls: the transformer segment is reduced as
+named_parameters() order, so the exchange is three or four NCCL calls: the transformer segment is reduced as
 soon as the transformer backward finishes (overlapping the stem backward, which is ~80 % of the
-step), the stem segment at the end.  BatchNorm statistics stay per rank (the reference has no SyncBN).
+step), the last stem layer when its blocks are done, the small remainder of the stem at the end.  BatchNorm statistics stay per rank (the reference has no SyncBN).
 """
 import torch
 import torch.distributed as dist

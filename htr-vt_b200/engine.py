@@ -485,6 +485,15 @@ class Engine(object):
                 ops.conv_wgrad_acc_t(dy, x, ks, sh, sw, gt[name])
             else:
                 ops.conv_wgrad_acc(dy, x, ks, sh, sw, gt[name])
+        unpacked = set()
+
+        def unpack(pred):                # staged conv weight gradients -> the OIHW .grad tensors, one launch per layout
+            sel = [k for k in cnames if k not in unpacked and pred(k)]
+            unpacked.update(sel)
+            for lay, kw in (("atoms", dict(layout="atoms")), ("tco", dict(transposed=True)), ("ctc", dict())):
+                part = [(gt[k], grads[k]) for k in sel if layout[k] == lay]
+                if part:
+                    ops.unpack_conv_grads(part, **kw)
         # [3][C] reduction targets of the 12 BatchNorm backward passes: one zeroed buffer per backward
         zs_total = sum(2 * 3 * blk[3].shape[-1] for blk in ctx.blocks)
         zs_pool, zs_off = torch.zeros(zs_total, dtype=torch.float32, device=dev), 0
@@ -526,9 +535,12 @@ class Engine(object):
                 gin = ops.conv_dgrad(d1, wp[p + ".conv1.weight"], tuple(xin.shape), 3, s[0], s[1], dx=gz,
                                      accumulate=True, w_t=wp.get("T:" + p + ".conv1.weight"))
             g = gin
-        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames if layout[k] == "atoms"], layout="atoms")
-        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames if layout[k] == "tco"], transposed=True)
-        ops.unpack_conv_grads([(gt[k], grads[k]) for k in cnames if layout[k] == "ctc"])
+            if on_stage is not None and p == "patch_embed.%s.0" % STEM_LAYERS[-1][0]:
+                # the last stem layer holds 3/4 of the stem's parameters: its gradients are final here, long before the
+                # rest of the stem backward - unpack them now so that their all-reduce can start (data parallel)
+                unpack(lambda k: k.startswith("patch_embed.%s." % STEM_LAYERS[-1][0]))
+                on_stage("stem:" + STEM_LAYERS[-1][0])
+        unpack(lambda k: k not in unpacked)
         # ---- stem head: pool -> relu -> bn1 -> conv1 ---------------------------------------------
         if ctx.moments is None:
             raise ops.HtrvtError("backward needs a train-mode forward (batch statistics)")

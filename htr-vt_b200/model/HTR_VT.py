@@ -107,13 +107,27 @@ class _EncoderFn(torch.autograd.Function):
                  for i, (n, (shape, _)) in enumerate(zip(ctx.names, ctx.shapes))}
         sync = module.grad_sync
 
-        def on_stage(stage):
-            if sync is not None and stage == "transformer":
-                sync.reduce_async(flat[split:])          # overlaps the stem backward
+        done = []                                        # [lo, hi) ranges of the stem segment already handed to NCCL
 
-        module.engine.backward(ctx.sd, ctx.ectx, dlogits, grads, on_stage)
+        def on_stage(stage):
+            if sync is None:
+                return
+            if stage == "transformer":
+                sync.reduce_async(flat[split:])          # overlaps the stem backward
+            elif stage.startswith("stem:"):              # a finished stem layer: overlaps the rest of the stem backward
+                pre = "patch_embed.%s." % stage[5:]
+                idx = [i for i, n in enumerate(ctx.names) if n.startswith(pre)]
+                if idx and offs[idx[-1] + 1] <= split:
+                    sync.reduce_async(flat[offs[idx[0]]:offs[idx[-1] + 1]])
+                    done.append((offs[idx[0]], offs[idx[-1] + 1]))
+
+        module.engine.backward(ctx.sd, ctx.ectx, dlogits, grads, on_stage if sync is not None else None)
         if sync is not None:
-            sync.reduce_async(flat[:split])
+            lo = 0
+            for a, b in sorted(done) + [(split, split)]:  # what is left of the stem segment
+                if a > lo:
+                    sync.reduce_async(flat[lo:a])
+                lo = max(lo, b)
             sync.finish()
         ctx.ectx = None
         out = tuple(grads[n] if req else None for n, (_, req) in zip(ctx.names, ctx.shapes))
