@@ -125,9 +125,22 @@ class Engine(object):
                     return n[:-len(".convX.weight")] + ".bn" + n[-len("X.weight")]
                 items = [(v, kind, bnst[bn_of(n)][2]) if kind == "conv" else (v, kind)
                          for n, (v, kind) in zip(names, items)]
-            wp = dict(zip(names, ops.pack_weights(items, pad_rows={"head.weight": C8} if C8 != C else None,
-                                                  names=names)))    # one launch for all 36 weight tensors
+            # train mode: the ~50 packed tensors of the previous step are overwritten in place when no recorded forward
+            # still waits for its backward (stream order protects the kernels already enqueued); a second forward before
+            # the first one's backward (gradient accumulation over graphs) gets fresh tensors
+            sig = (tuple(names), tuple(v.data_ptr() for v, *_ in items), str(image.device))
+            pool = getattr(self, "_wp_pool", None)
+            reuse = None
+            if not fold and pool is not None and pool[0] == sig and getattr(self, "_wp_busy", 0) == 0:
+                reuse = pool[1]
+            packed = ops.pack_weights(items, pad_rows={"head.weight": C8} if C8 != C else None, names=names,
+                                      reuse=reuse)                  # one launch for all 36 weight tensors
+            wp = dict(zip(names, packed))
+            if not fold:
+                self._wp_pool = (sig, packed)
             self._wp_cache = (key, wp, bnst) if key is not None else None
+        if save:
+            self._wp_busy = getattr(self, "_wp_busy", 0) + 1          # released by backward()
 
         # ---- stem -----------------------------------------------------------------------------
         if u8:
@@ -547,4 +560,5 @@ class Engine(object):
         ops.stem_head_bwd(g, ctx.code1, ctx.x0, sd["patch_embed.conv1.weight"], ctx.moments,
                           sd["patch_embed.bn1.weight"], ctx.st1, grads["patch_embed.bn1.weight"],
                           grads["patch_embed.bn1.bias"], grads["patch_embed.conv1.weight"])
+        self._wp_busy = max(0, getattr(self, "_wp_busy", 0) - 1)       # this forward's packed weights are free again
         return grads

@@ -535,14 +535,18 @@ def pack_conv_weight(w, dst=None):
     return dst
 
 
-def pack_weights(items, pad_rows=None, names=None, conv_dtype=None):
+def pack_weights(items, pad_rows=None, names=None, conv_dtype=None, reuse=None):
     """items: list of (src fp32 tensor, kind[, scale]) with kind 'cast' ([out,in]), 'conv' (OIHW -> [Cout, taps, Cin];
     optional scale fp32 [Cout] folded in per output channel: eval-mode BatchNorm folding) or 'convT'.
     One launch for all of them.  pad_rows: {name: rows} allocates that 'cast' output with extra zero rows.
     Returns the list of 16-bit tensors: 'conv' copies in `conv_dtype` (default STEM_DTYPE = fp16, the forward stem's
-    format), 'cast' and 'convT' (backward-only) copies in bf16."""
+    format), 'cast' and 'convT' (backward-only) copies in bf16.  reuse: the list a previous call with the same items
+    returned - its tensors are overwritten instead of allocating ~50 new ones (the caller guarantees that nothing still
+    reads them)."""
     conv_dtype = conv_dtype or STEM_DTYPE
     n = len(items)
+    if reuse is not None and len(reuse) != n:
+        reuse = None
     outs = []
     src = (ctypes.c_void_p * n)()
     dst = (ctypes.c_void_p * n)()
@@ -554,21 +558,25 @@ def pack_weights(items, pad_rows=None, names=None, conv_dtype=None):
     for i, item in enumerate(items):
         t, kind = item[0], item[1]
         scale[i] = item[2].data_ptr() if (len(item) > 2 and item[2] is not None) else None
+        o = reuse[i] if reuse is not None else None
         if kind == "conv":
             Cout, Ci, kh, kw = t.shape
-            o = torch.empty((Cout, kh * kw, Ci), dtype=conv_dtype, device=t.device)
+            if o is None:
+                o = torch.empty((Cout, kh * kw, Ci), dtype=conv_dtype, device=t.device)
             cin[i], taps[i] = Ci, kh * kw
             f16[i] = int(conv_dtype == torch.float16)
         elif kind == "convT":                 # OIHW -> [Cin, taps, Cout] = plain transpose of [Cout, Cin*taps]
             Cout, Ci, kh, kw = t.shape
-            o = torch.empty((Ci, kh * kw, Cout), dtype=torch.bfloat16, device=t.device)
+            if o is None:
+                o = torch.empty((Ci, kh * kw, Cout), dtype=torch.bfloat16, device=t.device)
             cin[i], taps[i] = Cout, -1
         else:
             rows = pad_rows.get(names[i]) if (pad_rows and names) else None
-            if rows is not None and rows != t.shape[0]:
-                o = torch.zeros((rows, t.shape[1]), dtype=torch.bfloat16, device=t.device)
-            else:
-                o = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+            if o is None:
+                if rows is not None and rows != t.shape[0]:      # (the pad rows are zero and stay zero: never written)
+                    o = torch.zeros((rows, t.shape[1]), dtype=torch.bfloat16, device=t.device)
+                else:
+                    o = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
             cin[i], taps[i] = 1, 0
         outs.append(o)
         src[i], dst[i], numel[i] = t.data_ptr(), o.data_ptr(), t.numel()
