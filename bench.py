@@ -430,6 +430,15 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
         ms_b = timed_ms(lambda: h.beam_search_with_lm_batch(lp, conv, _LenLM(), beam_size=5), 3, warm=1)
         out["kbest_beam"] = {"kernel_us_per_batch": ms_k * 1e3, "with_host_strings_ms_per_batch": ms_b, "lines": Bi,
                              "beam": 5, "what": "K-best CTC paths on device + LM pick on host (test_with_kenlm.py:25-59)"}
+        # the true prefix beam search: labellings instead of alignment paths
+        out["prefix_beam"] = {}
+        for Kb in (5, 16):
+            ms_p = timed_ms(lambda: ops.ctc_prefix_beam(lp, Kb), 10)
+            out["prefix_beam"]["beam_%d_us_per_batch" % Kb] = ms_p * 1e3
+        ms_pb = timed_ms(lambda: h.beam_search_with_lm_batch(lp, conv, _LenLM(), beam_size=5, search="prefix"), 3, warm=1)
+        out["prefix_beam"].update({"with_host_strings_ms_per_batch_beam_5": ms_pb, "lines": Bi, "T": IMG_W // 4,
+                                   "C": NB_CLS, "what": "CTC prefix beam search, one warp per line, all classes "
+                                   "extended every frame, float64 log-space scores (csrc/prefix_beam.cu)"})
         del lp
     except Exception as e:
         out["kbest_beam"] = {"error": repr(e)[:200]}

@@ -361,6 +361,31 @@ def ctc_kbest_paths(log_probs, beam_size, lengths=None, layout="tbc"):
     return ids, lens, scores
 
 
+def ctc_prefix_beam(log_probs, beam_size, lengths=None, layout="tbc"):
+    """CTC prefix beam search (csrc/prefix_beam.cu): the K most probable LABELLINGS per line, every beam entry carrying
+    the summed probability of all its alignments - the search SURVEY.md 8(f) row 4 puts in place of the per-frame path
+    beam of model_window/test_with_kenlm.py:25-59.  Same arguments and buffers as ctc_kbest_paths.
+    Returns (ids [B,K,T] int32 zero padded, lens [B,K] int32 (-1 = no such prefix), scores [B,K] float64, best first)."""
+    _need_cuda(log_probs)
+    if log_probs.dtype != torch.float32 or log_probs.stride(-1) != 1:
+        raise HtrvtError("ctc_prefix_beam expects fp32 log-probs with a contiguous class axis")
+    if layout == "btc":
+        B, T, C = log_probs.shape
+        sb, st = log_probs.stride(0), log_probs.stride(1)
+    else:
+        T, B, C = log_probs.shape
+        sb, st = log_probs.stride(1), log_probs.stride(0)
+    dev = log_probs.device
+    K = int(beam_size)
+    ids = torch.empty((B, K, T), dtype=torch.int32, device=dev)
+    lens = torch.empty((B, K), dtype=torch.int32, device=dev)
+    scores = torch.empty((B, K), dtype=torch.float64, device=dev)
+    ln = None if lengths is None else lengths.to(device=dev, dtype=torch.int32).contiguous()
+    check(lib().htrvt_ctc_prefix_beam(_p(log_probs), sb, st, _p(ln), B, T, C, K, _p(ids), _p(lens), _p(scores),
+                                      _stream()), "htrvt_ctc_prefix_beam")
+    return ids, lens, scores
+
+
 def ctc_collapse(index_flat, lengths, n_character):
     """Collapse a sample-major index stream (reference decode() input).  -> (ids [B,Tmax], lens [B])."""
     _need_cuda(index_flat)
@@ -912,7 +937,7 @@ def _instrument():
     import functools
     g = globals()
     names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_dgrad_bn", "conv_wgrad", "conv_wgrad_acc", "conv_wgrad_acc_t", "conv_wgrad_acc_w", "unpack_conv_grads", "attention_fwd",
-             "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "ctc_kbest_paths", "sample_ln_fwd", "sample_ln_bwd", "line_prep_u8", "edit_distance",
+             "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "ctc_kbest_paths", "ctc_prefix_beam", "sample_ln_fwd", "sample_ln_bwd", "line_prep_u8", "edit_distance",
              "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16", "cast_colsum_bf16", "dropout_",
              "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd", "bn_bwd_apply",
              "conv1_wgrad", "stem_head_moments", "stem_head_fwd", "stem_head_bwd"]

@@ -74,6 +74,17 @@ int htrvt_ctc_collapse(const void* index, int index_is_int64, const int* lengths
 int htrvt_ctc_kbest_paths(const float* log_probs, long long stride_b, long long stride_t, const int* lengths, int B,
                           int T, int C, int K, int* ids, int* lens, double* scores, void* stream);
 
+/* ---- CTC prefix beam search (the search that replaces the toy per-frame beam) --------
+ * htrvt_ctc_prefix_beam ranks LABELLINGS where htrvt_ctc_kbest_paths (the reference's
+ * `simple_ctc_beam_search_with_lm`, model_window/test_with_kenlm.py:25-59) ranks alignment paths: every beam entry
+ * is a collapsed prefix with the summed probability of all its alignments (blank-ending / label-ending parts, float64
+ * log space); per frame every entry stays or is extended by every label, an extension that spells an entry of the
+ * beam is added to that entry, the K most probable survive (ties: stay entries by rank, then extensions by parent
+ * rank and label).  Same buffers as htrvt_ctc_kbest_paths: ids int32 [B, K, T] zero padded, lens int32 [B, K]
+ * (-1: fewer than K prefixes exist), scores float64 [B, K] best first.  K <= 16, C <= 256, T * K < 65535. */
+int htrvt_ctc_prefix_beam(const float* log_probs, long long stride_b, long long stride_t, const int* lengths, int B,
+                          int T, int C, int K, int* ids, int* lens, double* scores, void* stream);
+
 /* ---- tcgen05 tap-GEMM: nn.Linear / nn.Conv2d forward, input gradient, weight gradient ------------------
  * flags (epilogue, run by 8 warps and kept light): 1 bf16 out (else fp32), 2 +bias, 16 accumulate into out
  * (TMA reduce-add store), 32 column statistics (conv fwd), 128 ReLU.  Outputs leave through TMA stores.

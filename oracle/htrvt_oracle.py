@@ -498,6 +498,85 @@ def beam_search_with_lm(log_probs: np.ndarray, alphabet: str, lm_score, beam_siz
 
 
 # ----------------------------------------------------------------------------------------------
+# CTC prefix beam search (the search that replaces the toy per-frame beam of
+# model_window/test_with_kenlm.py:25-59).  The reference holds no such function (its beam ranks alignment paths, see
+# kbest_paths above), so this restates the published algorithm - Hannun et al., "First-Pass Large Vocabulary Continuous
+# Speech Recognition using Bi-Directional Recurrent DNNs", 2014, algorithm 1 without the language-model term - and is
+# pinned by `labelling_logprobs_bruteforce` (an enumeration of all C^T alignments): with a beam that holds every prefix
+# the search returns the exact posterior of every labelling.  Parity of the CUDA kernel = this function.
+# ----------------------------------------------------------------------------------------------
+def _lae(a: float, b: float) -> float:
+    if a == -math.inf:
+        return b
+    if b == -math.inf:
+        return a
+    return max(a, b) + math.log1p(math.exp(-abs(a - b)))
+
+
+def ctc_prefix_beam_search(log_probs: np.ndarray, beam_size: int):
+    """log_probs [T, C] (blank = 0) -> [(label list, log P(labelling | frames))], best first, at most beam_size.
+    Beam entry = collapsed prefix with (pb, pnb): log-mass of its alignments ending in blank / in its last label.
+    Per frame every entry stays (pb' = tot + lp[0], pnb' = pnb + lp[last]) and is extended by every label c >= 1
+    (pnb' = (pb if c == last else tot) + lp[c]); an extension that spells a prefix of the beam adds to that entry.
+    Survivors: the beam_size largest lae(pb', pnb'); ties by candidate number - stay entries (rank in the beam) before
+    extensions (parent rank, then label)."""
+    T, C = log_probs.shape
+    K = int(beam_size)
+    beam = [((), 0.0, -math.inf)]
+    for t in range(T):
+        lp = [float(v) for v in log_probs[t]]
+        cand = {}                                             # prefix -> [pb', pnb', candidate number]
+        for i, (p, pb, pnb) in enumerate(beam):
+            tot = _lae(pb, pnb)
+            cand[p] = [tot + lp[0], (pnb + lp[p[-1]]) if p else -math.inf, i]
+        for i, (p, pb, pnb) in enumerate(beam):
+            tot = _lae(pb, pnb)
+            for c in range(1, C):
+                s = (pb if (p and p[-1] == c) else tot) + lp[c]
+                q = p + (c,)
+                if q in cand:                                 # q is an entry of the beam (extensions never collide)
+                    cand[q][1] = _lae(cand[q][1], s)
+                else:
+                    cand[q] = [-math.inf, s, K + i * C + c]
+        ranked = sorted(((-_lae(v[0], v[1]), v[2], q, v[0], v[1]) for q, v in cand.items()))
+        beam = [(q, pb, pnb) for _, _, q, pb, pnb in ranked[:K]]
+    return [(list(q), _lae(pb, pnb)) for q, pb, pnb in beam]
+
+
+def labelling_logprobs_bruteforce(log_probs: np.ndarray):
+    """{labelling tuple: log sum of exp(path score) over ALL C^T alignment paths that collapse to it} (small T, C)."""
+    import itertools
+    T, C = log_probs.shape
+    acc = {}
+    for path in itertools.product(range(C), repeat=T):
+        s = float(sum(float(log_probs[t, c]) for t, c in enumerate(path)))
+        lab, prev = [], None
+        for c in path:
+            if c != 0 and c != prev:
+                lab.append(c)
+            prev = c
+        k = tuple(lab)
+        acc[k] = _lae(acc.get(k, -math.inf), s)
+    return acc
+
+
+def prefix_beam_search_with_lm(log_probs: np.ndarray, alphabet: str, lm_score, beam_size: int = 5) -> str:
+    """beam_search_with_lm with the prefix search as the candidate generator: labellings -> strings (no second
+    repeat filter: a doubled label IS a doubled letter; ids beyond the alphabet dropped), empty strings dropped,
+    arg-max of the LM score."""
+    table = ["[blank]"] + list(alphabet)
+    cands = []
+    for lab, _ in ctc_prefix_beam_search(log_probs, beam_size):
+        s = "".join(table[i] for i in lab if i < len(table))
+        if s:
+            cands.append(s)
+    if not cands:
+        return ""
+    lm = [lm_score(c) for c in cands]
+    return cands[int(np.argmax(lm))]
+
+
+# ----------------------------------------------------------------------------------------------
 # One training step (loss + parameter gradients), the unit bench.py's reference arm times
 # ----------------------------------------------------------------------------------------------
 def grad_sample_index(name, numel, n=8192):

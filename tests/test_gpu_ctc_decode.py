@@ -322,3 +322,71 @@ def test_kbest_paths_edge_shapes(T, C, K):
             want = [int(v) for i, v in enumerate(am[b, : lengths[b]]) if v != 0 and not (i > 0 and am[b, i - 1] == v)]
             if not (np.round(x[b] * 2) / 2 == x[b]).all():          # (ties: argmax takes the LOWEST index, argsort the highest)
                 assert ids[b, 0, : lens[b, 0]].tolist() == want
+
+
+@pytest.mark.parametrize("T,C,K", [(1, 7, 5), (9, 3, 8), (6, 4, 16), (128, 80, 5), (128, 80, 16), (256, 90, 8),
+                                   (64, 228, 1), (40, 33, 3)])
+def test_prefix_beam_matches_oracle(T, C, K):
+    """CTC prefix beam search kernel (csrc/prefix_beam.cu) vs the float64 oracle restatement (itself pinned to a
+    brute-force enumeration, tests/test_oracle.py): labellings, their order and float64 scores for every surviving
+    entry, on random / peaked / blank-heavy / quantised (exact ties) log-probs and ragged lengths."""
+    from importlib import import_module
+    ops = import_module("htr-vt_b200.ops")
+    rs = np.random.RandomState(7 * T + C + K)
+    B = 6
+    x = rs.randn(B, T, C).astype(np.float32) * 2.0
+    x[1] = np.round(x[1] * 2) / 2                                   # many exactly equal candidates
+    x[2, :, 0] += 5.0                                               # blank-dominated
+    x[3] *= 4.0                                                     # peaked: merges of doubled labels matter
+    x[5] = np.repeat(x[5, ::2], 2, axis=0)[:T]                      # every frame twice: repeats / stay-vs-extend
+    lp = torch.from_numpy(x).log_softmax(-1).numpy()
+    lengths = np.array([T, T, max(1, T // 2), T, max(1, T - 1), T], dtype=np.int32)
+    ids, lens, sc = ops.ctc_prefix_beam(torch.from_numpy(lp).cuda(), K, torch.from_numpy(lengths), layout="btc")
+    ids, lens, sc = ids.cpu().numpy(), lens.cpu().numpy(), sc.cpu().numpy()
+    for b in range(B):
+        want = O.ctc_prefix_beam_search(lp[b, : lengths[b]], K)
+        assert (lens[b] >= 0).sum() == len(want), b
+        for r, (lab, score) in enumerate(want):
+            assert ids[b, r, : lens[b, r]].tolist() == lab, (b, r)
+            if np.isfinite(score):
+                assert abs(sc[b, r] - score) < 1e-9 * max(1.0, abs(score)), (b, r)
+            else:
+                assert sc[b, r] == score
+            assert not ids[b, r, lens[b, r]:].any()
+        assert (lens[b, len(want):] == -1).all() and not ids[b, len(want):].any()
+    # [T, B, C] layout without lengths == [B, T, C]
+    ids2, lens2, sc2 = ops.ctc_prefix_beam(torch.from_numpy(np.ascontiguousarray(lp.transpose(1, 0, 2))).cuda(), K)
+    full = [b for b in range(B) if lengths[b] == T]
+    assert (ids2.cpu().numpy()[full] == ids[full]).all() and (lens2.cpu().numpy()[full] == lens[full]).all()
+
+
+def test_prefix_beam_exact_posterior_and_lm_entry_points():
+    """Small lines where K = 16 holds every prefix: the kernel's scores are the brute-force labelling posterior.
+    The LM entry points with search='prefix' agree with the oracle's pick; doubled letters survive."""
+    h = _pkg()
+    from importlib import import_module
+    ops = import_module("htr-vt_b200.ops")
+    rs = np.random.RandomState(11)
+    for T, C in [(2, 3), (3, 3), (5, 2)]:
+        x = rs.randn(1, T, C).astype(np.float32) * 1.5
+        lp = torch.from_numpy(x).log_softmax(-1)
+        exact = O.labelling_logprobs_bruteforce(lp[0].numpy())
+        ids, lens, sc = ops.ctc_prefix_beam(lp.cuda(), 16, layout="btc")
+        got = {tuple(ids[0, r, : int(lens[0, r])].cpu().tolist()): float(sc[0, r]) for r in range(16) if lens[0, r] >= 0}
+        for lab, s in exact.items():
+            assert abs(got[lab] - s) < 1e-9, (T, C, lab)
+    alphabet = "abcdefghij"
+    conv = h.CTCLabelConverter(alphabet)
+    lm = _StubLM()
+    x = rs.randn(40, 7, len(alphabet) + 1).astype(np.float32) * 3
+    lp = torch.from_numpy(x).log_softmax(-1)
+    got = h.beam_search_with_lm_batch(lp.cuda(), conv, lm, beam_size=8, search="prefix")
+    want = [O.prefix_beam_search_with_lm(lp[:, b].numpy(), alphabet, lm.score, 8) for b in range(7)]
+    assert got == want
+    assert h.simple_ctc_beam_search_with_lm(lp[:, 2].cuda(), conv, lm, beam_size=8, search="prefix") == want[2]
+    peaked = np.full((7, 4), -30.0, dtype=np.float32)
+    for t, c in enumerate([1, 1, 0, 1, 2, 2, 0]):
+        peaked[t, c] = 0.0
+    cands = h.kbest_candidates(torch.from_numpy(peaked).unsqueeze(1).cuda(), h.CTCLabelConverter("abc"), 3,
+                               search="prefix")[0]
+    assert cands[0][0] == "aab"

@@ -198,3 +198,59 @@ def test_beam_restatement_matches_reference_function():
     greedy = [int(v) for i, v in enumerate(am) if v != 0 and not (i > 0 and am[i - 1] == v)]
     assert O.kbest_paths(lp, 1)[0][0] == greedy
     assert [c[0] for c in O.kbest_paths(lp, 5, np.float32)] == [c[0] for c in O.kbest_paths(lp, 5)]
+
+
+def test_prefix_beam_search_is_the_exact_labelling_posterior():
+    """ctc_prefix_beam_search pinned by brute force: with a beam that holds every prefix, the score of every
+    labelling equals the log-sum over all C^T alignment paths collapsing to it, and the order is the posterior order;
+    the best labelling's score is bounded by the CTC likelihood identity (-nll of ctc_loss_grad on that labelling)."""
+    rs = np.random.RandomState(5)
+    for T, C in [(1, 3), (2, 3), (4, 3), (5, 4), (6, 2), (3, 5)]:
+        x = rs.randn(T, C) * 1.5
+        lp = (x - np.log(np.exp(x).sum(1, keepdims=True))).astype(np.float32)
+        exact = O.labelling_logprobs_bruteforce(lp)
+        got = O.ctc_prefix_beam_search(lp, 10 ** 6)
+        assert len(got) >= len(exact)                       # prefixes longer than T carry -inf and rank last
+        gd = {tuple(l): s for l, s in got}
+        for lab, s in exact.items():
+            assert abs(gd[lab] - s) < 1e-9, (T, C, lab)
+        for lab, s in gd.items():
+            if lab not in exact:
+                assert s == -np.inf
+        want_order = sorted(exact.items(), key=lambda kv: -kv[1])
+        assert [tuple(l) for l, _ in got[:3]] == [k for k, _ in want_order[:3]]
+        # total mass = 1
+        assert abs(np.log(sum(np.exp(s) for s in exact.values()))) < 1e-5
+    # the score of a labelling = -CTC nll of that labelling (the float64 alpha recursion of ctc_loss_grad)
+    T, C = 7, 4
+    x = rs.randn(1, T, C).astype(np.float32)
+    lp = x[0] - np.log(np.exp(x[0].astype(np.float64)).sum(1, keepdims=True))
+    best = O.ctc_prefix_beam_search(lp.astype(np.float32), 10 ** 6)[:4]
+    for lab, s in best:
+        if not lab:
+            continue
+        nll, _ = O.ctc_loss_grad(x, np.array(lab, dtype=np.int32), np.array([T]), np.array([len(lab)], dtype=np.int32))
+        assert abs(-float(nll[0]) - s) < 2e-5 * max(1.0, abs(s)), (lab, nll, s)
+
+
+def test_prefix_beam_narrow_beam_and_lm_pick():
+    """A narrow beam returns at most K entries, best first, every score <= the exact posterior of its labelling
+    (pruned mass only ever lowers a score); K = 1 on peaked frames is the greedy labelling; the LM pick keeps doubled
+    letters."""
+    rs = np.random.RandomState(6)
+    T, C = 6, 4
+    x = rs.randn(T, C) * 2
+    lp = (x - np.log(np.exp(x).sum(1, keepdims=True))).astype(np.float32)
+    exact = O.labelling_logprobs_bruteforce(lp)
+    for K in (1, 2, 5):
+        got = O.ctc_prefix_beam_search(lp, K)
+        assert len(got) == K
+        assert all(got[i][1] >= got[i + 1][1] for i in range(K - 1))
+        for lab, s in got:
+            assert s <= exact[tuple(lab)] + 1e-9
+    peaked = np.full((7, 4), -30.0, dtype=np.float32)
+    for t, c in enumerate([1, 1, 0, 1, 2, 2, 0]):
+        peaked[t, c] = 0.0
+    assert O.ctc_prefix_beam_search(peaked, 1)[0][0] == [1, 1, 2]
+    assert O.prefix_beam_search_with_lm(peaked, "abc", lambda s: len(s), 3) in ("aab", "aabb", "aaab", "aabc", "aaba")
+    assert O.prefix_beam_search_with_lm(peaked, "abc", lambda s: -abs(len(s) - 3) + (s == "aab"), 3) == "aab"
