@@ -442,6 +442,40 @@ def extra_metrics(torch, dev, h, ops, H, model, peaks):
         del lp
     except Exception as e:
         out["kbest_beam"] = {"error": repr(e)[:200]}
+    # ---- training-time augmentation (dataset.py:13-45): all three stages on 128 uint8 lines
+    try:
+        import types
+        import numpy as np
+        aug = import_module("htr-vt_b200.augment")
+        a_args = types.SimpleNamespace(proj=8.0, dila_ero_max_kernel=3, dila_ero_iter=1, jitter_contrast=0.4,
+                                       jitter_brightness=0.4, jitter_saturation=0.4, jitter_hue=0.2)
+        st_np, st_t = np.random.get_state(), torch.random.get_rng_state()
+        xa = torch.randint(0, 256, (128, IMG_H, IMG_W), dtype=torch.uint8, device=dev)
+        seed = 0
+        while True:
+            seed += 1
+            np.random.seed(seed); torch.manual_seed(seed)
+            pa = aug.draw_collate_params(128, IMG_H, IMG_W, a_args)
+            if all(pa[k] is not None for k in ("warp", "morph", "jitter")):
+                break
+        t0 = time.perf_counter()
+        for _ in range(5):
+            np.random.seed(seed); torch.manual_seed(seed)
+            aug.draw_collate_params(128, IMG_H, IMG_W, a_args)
+            rec, morph = aug.pack_params(pa, 128, IMG_H, IMG_W)
+        host_ms = (time.perf_counter() - t0) / 5 * 1e3
+        recd = torch.from_numpy(rec).to(dev)
+        ms_a = timed_ms(lambda: ops.augment_lines(xa, recd, morph), 20)
+        np.random.set_state(st_np); torch.random.set_rng_state(st_t)
+        out["augment"] = {"kernel_us_per_batch": ms_a * 1e3, "host_draws_and_records_ms_per_batch": host_ms,
+                          "lines": 128, "img": [IMG_H, IMG_W],
+                          "what": "SameTrCollate's projective warp + resize, erosion / dilation and brightness / "
+                                  "contrast jitter on 128 uint8 lines in one launch; random decisions drawn on the "
+                                  "host in the reference's order (dataset.py:13-45 runs PIL / OpenCV / scikit-image "
+                                  "per image)"}
+        del xa
+    except Exception as e:
+        out["augment"] = {"error": repr(e)[:200]}
     model.train()
     del img
 

@@ -386,6 +386,23 @@ def ctc_prefix_beam(log_probs, beam_size, lengths=None, layout="tbc"):
     return ids, lens, scores
 
 
+def augment_lines(img_u8, records, morph):
+    """SameTrCollate's pixel work on a uint8 batch (csrc/augment.cu; model_v1/data/dataset.py:13-45).
+    img_u8: CUDA uint8 [B, H, W] with contiguous rows; records: uint8 [B, 128] (CPU or CUDA; augment.py::pack_params);
+    morph: (0 none | 1 erode | 2 dilate, k_rows, k_cols, iterations).  -> CUDA uint8 [B, H, W]."""
+    _need_cuda(img_u8)
+    if img_u8.dtype != torch.uint8 or img_u8.dim() != 3 or img_u8.stride(2) != 1 or img_u8.stride(1) != img_u8.shape[2]:
+        raise HtrvtError("augment_lines expects uint8 [B, H, W] with contiguous images")
+    B, H, W = img_u8.shape
+    if records.dtype != torch.uint8 or tuple(records.shape) != (B, 128):
+        raise HtrvtError("augment_lines expects one 128-byte record per image")
+    rec = records.to(device=img_u8.device, non_blocking=True).contiguous()
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=img_u8.device)
+    check(lib().htrvt_augment_lines(_p(img_u8), img_u8.stride(0), _p(out), _p(rec), B, H, W, int(morph[0]),
+                                    int(morph[1]), int(morph[2]), int(morph[3]), _stream()), "htrvt_augment_lines")
+    return out
+
+
 def ctc_collapse(index_flat, lengths, n_character):
     """Collapse a sample-major index stream (reference decode() input).  -> (ids [B,Tmax], lens [B])."""
     _need_cuda(index_flat)
@@ -937,7 +954,7 @@ def _instrument():
     import functools
     g = globals()
     names = ["gemm_tn", "gemm_nn", "linear_wgrad", "conv_fwd", "conv_dgrad", "conv_dgrad_bn", "conv_wgrad", "conv_wgrad_acc", "conv_wgrad_acc_t", "conv_wgrad_acc_w", "unpack_conv_grads", "attention_fwd",
-             "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "ctc_kbest_paths", "ctc_prefix_beam", "sample_ln_fwd", "sample_ln_bwd", "line_prep_u8", "edit_distance",
+             "attention_bwd", "attention2_fwd", "attention2_bwd", "ctc_loss_grad", "greedy_decode_ids", "ctc_collapse", "ctc_kbest_paths", "ctc_prefix_beam", "augment_lines", "sample_ln_fwd", "sample_ln_bwd", "line_prep_u8", "edit_distance",
              "row_ln_fwd", "row_ln_bwd", "tokens_fwd", "tokens_bwd", "gelu_fwd", "gelu_bwd", "colsum_bf16", "cast_bf16", "cast_colsum_bf16", "dropout_",
              "pack_conv_weight", "pack_weights", "conv1_fwd", "bn_finalize", "bn_act_fwd", "pool_fwd", "pool_bwd", "bn_bwd", "bn_bwd_apply",
              "conv1_wgrad", "stem_head_moments", "stem_head_fwd", "stem_head_bwd"]

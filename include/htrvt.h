@@ -85,6 +85,19 @@ int htrvt_ctc_kbest_paths(const float* log_probs, long long stride_b, long long 
 int htrvt_ctc_prefix_beam(const float* log_probs, long long stride_b, long long stride_t, const int* lengths, int B,
                           int T, int C, int K, int* ids, int* lens, double* scores, void* stream);
 
+/* ---- training-time augmentation of a uint8 batch of line images ----------------------
+ * htrvt_augment_lines replaces the per-image PIL / OpenCV / scikit-image work of `SameTrCollate`
+ * (model_v1/data/dataset.py:13-45): RandomTransform's projective warp + resize (model_v1/data/transform.py:164-230),
+ * cv2 erode / dilate with an all-ones rectangle (transform.py:11-33) and torchvision ColorJitter's brightness /
+ * contrast on grey images, one CTA per image, one launch per batch.  The random decisions are drawn on the host in the
+ * reference's order (htr-vt_b200/augment.py::draw_collate_params) and passed as one 128-byte record per image:
+ *   double m[9] (inverse projective map), double w0, w1 (anti-aliasing weights), int warp, rows, cols (shape of the
+ *   intermediate warped image), gauss, jit_n, jit_op[2] (0 brightness, 1 contrast), float jit_f[2], int pad.
+ * in uint8 [B, H, W] (stride_b bytes between images), out uint8 [B, H, W]; morph 0 none / 1 erode / 2 dilate, the same
+ * k_rows x k_cols rectangle and iteration count for the whole batch.  2 * H * W <= 220 KB of shared memory. */
+int htrvt_augment_lines(const void* in, long long stride_b, void* out, const void* recs, int B, int H, int W,
+                        int morph, int k_rows, int k_cols, int iterations, void* stream);
+
 /* ---- tcgen05 tap-GEMM: nn.Linear / nn.Conv2d forward, input gradient, weight gradient ------------------
  * flags (epilogue, run by 8 warps and kept light): 1 bf16 out (else fp32), 2 +bias, 16 accumulate into out
  * (TMA reduce-add store), 32 column statistics (conv fwd), 128 ReLU.  Outputs leave through TMA stores.
