@@ -153,23 +153,22 @@ __global__ void __launch_bounds__(128) ctc_prefix_beam_kernel(const float* __res
     }
 
     // ---- K selection rounds ---------------------------------------------------------------------------------
-    // scores are compared as order-preserving 64-bit integer images of the doubles (integer compares run at full
-    // rate, DSETP does not); the sentinel (LLONG_MIN, INT_MAX) loses against every real candidate
-    long long pk = pb_key(INFINITY);                         // previous winner (nothing precedes the first one)
-    int pn = -1;
-    int nnew = 0;
-    for (int r = 0; r < K; ++r) {
-      // one (key, number) accumulator per class slot: CPL independent compare chains per lane instead of one
+    // Scores are compared as order-preserving 64-bit integer images of the doubles; the sentinel (LLONG_MIN, INT_MAX)
+    // loses against every real candidate.  Every lane scans ITS candidates (its class slots x all entries, + its
+    // stay candidate) ONCE per frame for its local best; a round is then a warp arg-max over the 32 local bests, and
+    // only the winner's lane needs a new local best (the best of its candidates that comes after the winner in the
+    // strict order) - found by all 32 lanes together, <= ceil((nb * CPL + 1) / 32) candidates each, from the smem
+    // copy of the frame's log-probs.  K scans of nb * CPL candidates per lane become one.
+    long long lk = LLONG_MIN;                                // this lane's best remaining candidate
+    int ln = 0x7fffffff;
+    {
       long long bku[CPL];
       int bnu[CPL];
 #pragma unroll
       for (int u = 0; u < CPL; ++u) { bku[u] = LLONG_MIN; bnu[u] = 0x7fffffff; }
-      if (lane < nb) {
-        const long long k = pb_key(W->stot[lane]);
-        if (pb_before(pk, pn, k, lane)) { bku[0] = k; bnu[0] = lane; }
-      }
-#pragma unroll 4                                                // loads, adds and key images of four entries in flight;
-      for (int i = 0; i < nb; ++i) {                          // only the compare-and-keep step is a serial chain
+      if (lane < nb) { bku[0] = pb_key(W->stot[lane]); bnu[0] = lane; }
+#pragma unroll 4
+      for (int i = 0; i < nb; ++i) {
         const double ti = g.tot[i], pbi = g.pb[i];
         const int li = g.len[i] > 0 ? g.last[i] : -1;
         const int n0 = K + i * C;
@@ -178,16 +177,19 @@ __global__ void __launch_bounds__(128) ctc_prefix_beam_kernel(const float* __res
           const int c = lane + 32 * u;
           if (!((excl[u] >> i) & 1u)) {
             const long long k = pb_key((c == li ? pbi : ti) + static_cast<double>(v[u]));
-            const int n = n0 + c;
-            if (pb_before(pk, pn, k, n) && pb_before(k, n, bku[u], bnu[u])) { bku[u] = k; bnu[u] = n; }
+            if (pb_before(k, n0 + c, bku[u], bnu[u])) { bku[u] = k; bnu[u] = n0 + c; }
           }
         }
       }
-      long long bk = bku[0];
-      int bn = bnu[0];
+      lk = bku[0]; ln = bnu[0];
 #pragma unroll
       for (int u = 1; u < CPL; ++u)
-        if (pb_before(bku[u], bnu[u], bk, bn)) { bk = bku[u]; bn = bnu[u]; }
+        if (pb_before(bku[u], bnu[u], lk, ln)) { lk = bku[u]; ln = bnu[u]; }
+    }
+    int nnew = 0;
+    for (int r = 0; r < K; ++r) {
+      long long bk = lk;
+      int bn = ln;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
@@ -196,8 +198,45 @@ __global__ void __launch_bounds__(128) ctc_prefix_beam_kernel(const float* __res
       }
       if (bn == 0x7fffffff) break;                            // fewer than K candidates exist
       if (lane == 0) { W->win_s[r] = pb_unkey(bk); W->win_n[r] = bn; }
-      pk = bk; pn = bn;
       nnew = r + 1;
+      if (r + 1 == K) break;
+      // the owner lane of the winner and its class slots' fold masks
+      const int own = bn < K ? bn : (((bn - K) % C) & 31);
+      unsigned oex[CPL];
+#pragma unroll
+      for (int u = 0; u < CPL; ++u) oex[u] = __shfl_sync(0xffffffffu, excl[u], own);
+      long long ck = LLONG_MIN;
+      int cn = 0x7fffffff;
+      const int M = nb * CPL;
+      for (int idx = lane; idx <= M; idx += 32) {
+        long long k;
+        int n;
+        bool ok;
+        if (idx == M) {                                       // the owner's stay candidate
+          ok = own < nb;
+          k = ok ? pb_key(W->stot[own]) : LLONG_MIN;
+          n = own;
+        } else {
+          const int i = idx / CPL, u = idx - i * CPL;
+          const int c = own + 32 * u;
+          unsigned ex = 0u;
+#pragma unroll
+          for (int q = 0; q < CPL; ++q)
+            if (q == u) ex = oex[q];
+          ok = !((ex >> i) & 1u);                             // (invalid classes carry an all-ones mask)
+          const int li = g.len[i] > 0 ? g.last[i] : -1;
+          k = ok ? pb_key((c == li ? g.pb[i] : g.tot[i]) + static_cast<double>(W->lp[c])) : LLONG_MIN;
+          n = K + i * C + c;
+        }
+        if (ok && pb_before(bk, bn, k, n) && pb_before(k, n, ck, cn)) { ck = k; cn = n; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const long long ok2 = __shfl_xor_sync(0xffffffffu, ck, o);
+        const int on = __shfl_xor_sync(0xffffffffu, cn, o);
+        if (pb_before(ok2, on, ck, cn)) { ck = ok2; cn = on; }
+      }
+      if (lane == own) { lk = ck; ln = cn; }
     }
     __syncwarp();
 
