@@ -20,7 +20,10 @@
 namespace htrvt {
 
 constexpr int kMom = 54;               // 9 first moments + 45 upper-triangular second moments
-constexpr int kHeadInW = 72;           // smem row pitch of the staged image tile (68 used)
+constexpr int kHeadInW = 68;           // smem row pitch of the staged image tile: 68 columns used; 68 = 4 mod 32 keeps the
+                                       // backward's per-lane window reads (rows 2 kh + i, columns kw + j, kh / kw from the arg-max
+                                       // code) on distinct banks - a pitch of 72 put kh = 0 and kh = 2 on the same bank
+static_assert((7 * kHeadInW * 4) % 16 == 0, "stage alignment");
 
 // ------------------------------------------------------------------------------------------------
 // patch moments: x fp32 [B,H,W] -> partial [gridDim.x][54]
