@@ -130,22 +130,25 @@ __global__ void __launch_bounds__(256) row_ln_fwd_kernel(const float* __restrict
 // gx (+)= rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); per-CTA partial dgamma / dbeta.
 // If accumulate == 0 the result overwrites gx (used for the final norm, whose input grad starts the stream).
 template <int D>
-__global__ void __launch_bounds__(256) row_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+__global__ void __launch_bounds__(256, D >= 512 ? 2 : 1) row_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                          const float* __restrict__ x, const float* __restrict__ mean,
                                                          const float* __restrict__ rstd,
                                                          const float* __restrict__ gamma, float* __restrict__ gx,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int M,
                                                          int rows_per_cta, int accumulate) {
   constexpr int V = D / 128;
-  __shared__ float sg[8][D], sb[8][D];
+  __shared__ __align__(16) float sg[8][D], sb[8][D];
+  float* sgm = &sg[0][0];                                // gamma, read per row from smem instead of living in 4 V
+                                                         // registers; aliases the reduction buffer (barrier below)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 dg[V], db[V], gm[V];
+  float4 dg[V], db[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    gm[i] = *reinterpret_cast<const float4*>(gamma + lane * 4 + 128 * i);
   }
+  for (int c = threadIdx.x; c < D; c += 256) sgm[c] = gamma[c];
+  __syncthreads();
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(M, r0 + rows_per_cta);
   for (int row = r0 + warp; row < r1; row += 8) {
@@ -163,7 +166,8 @@ __global__ void __launch_bounds__(256) row_ln_bwd_kernel(const __nv_bfloat16* __
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       dg[i].x += d01.x * xh[i].x; dg[i].y += d01.y * xh[i].y; dg[i].z += d23.x * xh[i].z; dg[i].w += d23.y * xh[i].w;
       db[i].x += d01.x; db[i].y += d01.y; db[i].z += d23.x; db[i].w += d23.y;
-      gy[i] = make_float4(d01.x * gm[i].x, d01.y * gm[i].y, d23.x * gm[i].z, d23.y * gm[i].w);
+      const float4 gmv = *reinterpret_cast<const float4*>(sgm + c);
+      gy[i] = make_float4(d01.x * gmv.x, d01.y * gmv.y, d23.x * gmv.z, d23.y * gmv.w);
       s1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
       s2 += (gy[i].x * xh[i].x + gy[i].y * xh[i].y) + (gy[i].z * xh[i].z + gy[i].w * xh[i].w);
     }
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(256) row_ln_bwd_kernel(const __nv_bfloat16* __
       *reinterpret_cast<float4*>(gr + c) = o;
     }
   }
+  __syncthreads();                                       // every warp is done with gamma (sgm aliases sg[0])
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = lane * 4 + 128 * i;

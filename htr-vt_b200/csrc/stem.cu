@@ -338,7 +338,8 @@ __global__ void pool_bwd_kernel(const GT* __restrict__ gout, const uint8_t* __re
 // partial [cta][3][C] : sum g', sum g' xhat_a, sum g' xhat_b
 // ------------------------------------------------------------------------------------------------
 template <bool F16>
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ mask,
+__global__ void __launch_bounds__(256, 2)             // <= 128 registers: two CTAs per SM keep enough loads in flight
+bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ mask,
                                      const __nv_bfloat16* __restrict__ raw_a, const float* __restrict__ mean_a,
                                      const float* __restrict__ rstd_a, const __nv_bfloat16* __restrict__ raw_b,
                                      const float* __restrict__ mean_b, const float* __restrict__ rstd_b,
@@ -346,12 +347,12 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const 
   extern __shared__ float sm[];                         // [R][3][C]
   const int G = C / 8, R = blockDim.x / G;
   const int grp = threadIdx.x % G, lane_r = threadIdx.x / G;
-  float s0[8], s1[8], s2[8], ma[8], ra[8], mb[8], rb[8];
+  float s0[8], s1[8], s2[8], ma[8], mb[8];               // s1 / s2 accumulate g' (x - mean); rstd multiplies once at the end
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     s0[k] = s1[k] = s2[k] = 0.f;
-    ma[k] = mean_a[grp * 8 + k]; ra[k] = rstd_a[grp * 8 + k];
-    mb[k] = raw_b ? mean_b[grp * 8 + k] : 0.f; rb[k] = raw_b ? rstd_b[grp * 8 + k] : 0.f;
+    ma[k] = mean_a[grp * 8 + k];
+    mb[k] = raw_b ? mean_b[grp * 8 + k] : 0.f;
   }
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
   const long long r1 = r0 + rows_per_cta < P ? r0 + rows_per_cta : P;
@@ -378,21 +379,21 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const 
         for (int k = 0; k < 8; ++k) {
           if (!((mk[u] >> k) & 1u)) gv[k] = 0.f;
           s0[k] += gv[k];
-          s1[k] = fmaf(gv[k] * ra[k], xa[k] - ma[k], s1[k]);
+          s1[k] = fmaf(gv[k], xa[k] - ma[k], s1[k]);
         }
         if (raw_b) {
           float xb[8];
           unpack8f<F16>(bq[u], xb);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) s2[k] = fmaf(gv[k] * rb[k], xb[k] - mb[k], s2[k]);
+          for (int k = 0; k < 8; ++k) s2[k] = fmaf(gv[k], xb[k] - mb[k], s2[k]);
         }
       }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       sm[(lane_r * 3 + 0) * C + grp * 8 + k] = s0[k];
-      sm[(lane_r * 3 + 1) * C + grp * 8 + k] = s1[k];
-      sm[(lane_r * 3 + 2) * C + grp * 8 + k] = s2[k];
+      sm[(lane_r * 3 + 1) * C + grp * 8 + k] = s1[k] * rstd_a[grp * 8 + k];
+      sm[(lane_r * 3 + 2) * C + grp * 8 + k] = raw_b ? s2[k] * rstd_b[grp * 8 + k] : 0.f;
     }
   }
   __syncthreads();
@@ -418,9 +419,9 @@ struct BnBwdSide {
   const float* gamma; const float* mean; const float* rstd; float* dgamma; float* dbeta;
 };
 template <bool F16>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ g, const uint8_t* __restrict__ mask, const __nv_bfloat16* __restrict__ raw_a,
-    const float* __restrict__ sums, double count, BnBwdSide sa, __nv_bfloat16* __restrict__ d_a,
+    const float* __restrict__ sums, double inv_count, BnBwdSide sa, __nv_bfloat16* __restrict__ d_a,
     const __nv_bfloat16* __restrict__ raw_b, BnBwdSide sb, __nv_bfloat16* __restrict__ d_b,
     __nv_bfloat16* __restrict__ gz, long long n8, int C) {
   extern __shared__ float coef_sm[];                    // [2][3][C]: A, Bc, Cc of BN a and BN b
@@ -428,9 +429,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   float* coef_b = coef_sm + 3 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float s0 = sums[c], s1 = sums[C + c], s2 = sums[2 * C + c];
-    const float k1 = static_cast<float>(static_cast<double>(s0) / count);
+    const float k1 = static_cast<float>(static_cast<double>(s0) * inv_count);      // (1 / N from the host: no fp64 divide per channel per CTA)
     {
-      const float k2 = static_cast<float>(static_cast<double>(s1) / count);
+      const float k2 = static_cast<float>(static_cast<double>(s1) * inv_count);
       const float A = sa.gamma[c] * sa.rstd[c];
       coef_a[c] = A;
       coef_a[C + c] = -A * sa.rstd[c] * k2;
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
       if (blockIdx.x == 0 && sa.dgamma) { sa.dgamma[c] += s1; sa.dbeta[c] += s0; }
     }
     if (raw_b) {
-      const float k2 = static_cast<float>(static_cast<double>(s2) / count);
+      const float k2 = static_cast<float>(static_cast<double>(s2) * inv_count);
       const float A = sb.gamma[c] * sb.rstd[c];
       coef_b[c] = A;
       coef_b[C + c] = -A * sb.rstd[c] * k2;
@@ -649,6 +650,13 @@ extern "C" int htrvt_pool_bwd(const void* gout, int gout_is_f32, const void* idx
   return HTRVT_OK;
 }
 
+// the apply pass: every CTA first derives the per-channel coefficients (C channels), so one resident wave of CTAs
+// (4 per SM) strides over the tensor instead of up to 16 waves repeating that prologue
+static inline int apply_grid(long long n8) {
+  const long long g = (n8 + 511) / 512;
+  return static_cast<int>(g < 1 ? 1 : (g > 148LL * 4 ? 148LL * 4 : g));
+}
+
 extern "C" int htrvt_bn_bwd_ctas(long long P) {
   long long c = (P + 63) / 64;
   return static_cast<int>(c > 592 ? 592 : (c < 1 ? 1 : c));
@@ -689,9 +697,9 @@ extern "C" int htrvt_bn_bwd(const void* g, const void* mask, const void* raw_a, 
   const long long n8 = P * C / 8;
   const BnBwdSide sa = {gamma_a, mean_a, rstd_a, dgamma_a, dbeta_a};
   const BnBwdSide sb = {gamma_b, mean_b, rstd_b, dgamma_b, dbeta_b};
-  k_apply<<<grid_for(n8, 256), 256, static_cast<size_t>(6) * C * sizeof(float), stream>>>(
+  k_apply<<<apply_grid(n8), 256, static_cast<size_t>(6) * C * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(g), static_cast<const uint8_t*>(mask),
-      static_cast<const __nv_bfloat16*>(raw_a), partial, static_cast<double>(P), sa, static_cast<__nv_bfloat16*>(d_a),
+      static_cast<const __nv_bfloat16*>(raw_a), partial, 1.0 / static_cast<double>(P), sa, static_cast<__nv_bfloat16*>(d_a),
       static_cast<const __nv_bfloat16*>(raw_b), sb, static_cast<__nv_bfloat16*>(d_b),
       static_cast<__nv_bfloat16*>(gz), n8, C);
   HTRVT_LAUNCH_CHECK();
@@ -708,9 +716,9 @@ extern "C" int htrvt_bn_bwd_apply(const void* g_masked, const void* raw_a, const
   const long long n8 = P * C / 8;
   const BnBwdSide sa = {gamma_a, mean_a, rstd_a, dgamma_a, dbeta_a};
   const BnBwdSide sb = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  k_apply<<<grid_for(n8, 256), 256, static_cast<size_t>(6) * C * sizeof(float), stream>>>(
+  k_apply<<<apply_grid(n8), 256, static_cast<size_t>(6) * C * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(g_masked), nullptr, static_cast<const __nv_bfloat16*>(raw_a), sums,
-      static_cast<double>(P), sa, static_cast<__nv_bfloat16*>(d_a), nullptr, sb, nullptr, nullptr, n8, C);
+      1.0 / static_cast<double>(P), sa, static_cast<__nv_bfloat16*>(d_a), nullptr, sb, nullptr, nullptr, n8, C);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
