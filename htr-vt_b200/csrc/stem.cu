@@ -120,36 +120,41 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                    long long* __restrict__ num_batches_tracked, float momentum, float eps,
                                    int training, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                    float* __restrict__ scale_out, float* __restrict__ shift_out, int C) {
-  // block = 32 channels x 32 row lanes; four independent accumulators per lane keep the partial-row loads in flight
-  __shared__ double sh[2][32][32];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lr = threadIdx.x >> 5;
+  // block = 8 channels x 128 row lanes (C / 8 blocks: 24 at C = 192 instead of the 6 a 32-channel block gives - the
+  // pass reads up to 6 MB of partial rows and was limited by the number of SMs it reached); a warp reads four rows x
+  // 32-byte segments; four independent accumulators per lane keep the loads in flight
+  __shared__ double sh[2][32][8];
+  const int c8 = threadIdx.x & 7, lr = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + c8;
   if (blockIdx.x == 0 && threadIdx.x == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
   double s = 0.0, q = 0.0;
   if (training && c < C) {
     float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
     int r = lr;
-    for (; r + 96 < R; r += 128) {
+    for (; r + 384 < R; r += 512) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        s4[u] += partial[(static_cast<long long>(r + 32 * u) * 2) * C + c];
-        q4[u] += partial[(static_cast<long long>(r + 32 * u) * 2 + 1) * C + c];
+        s4[u] += partial[(static_cast<long long>(r + 128 * u) * 2) * C + c];
+        q4[u] += partial[(static_cast<long long>(r + 128 * u) * 2 + 1) * C + c];
       }
     }
-    for (; r < R; r += 32) {
+    for (; r < R; r += 128) {
       s4[0] += partial[(static_cast<long long>(r) * 2) * C + c];
       q4[0] += partial[(static_cast<long long>(r) * 2 + 1) * C + c];
     }
     s = (static_cast<double>(s4[0]) + s4[1]) + (static_cast<double>(s4[2]) + s4[3]);
     q = (static_cast<double>(q4[0]) + q4[1]) + (static_cast<double>(q4[2]) + q4[3]);
   }
-  sh[0][lr][threadIdx.x & 31] = s;
-  sh[1][lr][threadIdx.x & 31] = q;
+  // lanes with the same channel inside a warp differ in lane bits 3 and 4
+  s += __shfl_xor_sync(0xffffffffu, s, 8);  q += __shfl_xor_sync(0xffffffffu, q, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16); q += __shfl_xor_sync(0xffffffffu, q, 16);
+  if ((threadIdx.x & 31) < 8) { sh[0][threadIdx.x >> 5][c8] = s; sh[1][threadIdx.x >> 5][c8] = q; }
   __syncthreads();
-  if (lr != 0 || c >= C) return;
+  if (threadIdx.x >= 8 || c >= C) return;
   float mean, var;
   if (training) {
     s = 0.0; q = 0.0;
-    for (int k = 0; k < 32; ++k) { s += sh[0][k][threadIdx.x]; q += sh[1][k][threadIdx.x]; }
+    for (int k = 0; k < 32; ++k) { s += sh[0][k][c8]; q += sh[1][k][c8]; }
     const double m = s / count;
     double v = q / count - m * m;
     if (v < 0.0) v = 0.0;
@@ -595,7 +600,7 @@ extern "C" int htrvt_bn_finalize(const float* partial, int R, double count, cons
                                  float momentum, float eps, int training, float* mean, float* rstd, float* scale,
                                  float* shift, int C, cudaStream_t stream) {
   if (C <= 0 || (training && (!partial || R <= 0))) return HTRVT_ERR_SHAPE;
-  bn_finalize_kernel<<<(C + 31) / 32, 1024, 0, stream>>>(partial, R, count, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<(C + 7) / 8, 1024, 0, stream>>>(partial, R, count, gamma, beta, running_mean, running_var,
                                                           num_batches_tracked, momentum, eps, training, mean, rstd,
                                                           scale, shift, C);
   HTRVT_LAUNCH_CHECK();
