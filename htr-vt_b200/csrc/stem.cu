@@ -454,8 +454,10 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
   }
   __syncthreads();
   const int G = C / 8;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < n8; i0 += 2 * stride) {
+  // a CTA walks 2 x 256 ADJACENT groups per iteration (8 KB per stream: same DRAM pages), then jumps by the grid
+  const long long stride = static_cast<long long>(blockDim.x);
+  const long long jump = 2 * static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i0 = 2 * blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < n8; i0 += jump) {
     uint4 gq[2], xq[2], bq[2];
     unsigned mk[2];
 #pragma unroll
