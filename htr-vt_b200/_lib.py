@@ -74,6 +74,7 @@ SIGNATURES = {
     "htrvt_tokens_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "htrvt_tokens_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "htrvt_gelu_bwd": (_I, [_P, _P, _P, _L, _P]),
+    "htrvt_mul_bf16": (_I, [_P, _P, _P, _L, _P]),
     "htrvt_colsum_rows": (_I, [_I]),
     "htrvt_colsum_bf16": (_I, [_P, _L, _I, _I, _P, _I, _P, _P]),
     "htrvt_cast_bf16": (_I, [_P, _P, _L, _P]),

@@ -139,6 +139,13 @@ __device__ __forceinline__ float gelu_grad(float u) {
   gelu_parts(u, c, e);
   return fmaf(u * 0.3989422804014327f, e, c);
 }
+// gelu(u) and gelu'(u) from one evaluation of (Phi, exp): the training forward stores both
+__device__ __forceinline__ void gelu_val_grad(float u, float& val, float& grad) {
+  float c, e;
+  gelu_parts(u, c, e);
+  val = u * c;
+  grad = fmaf(u * 0.3989422804014327f, e, c);
+}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier

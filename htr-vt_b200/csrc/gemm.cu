@@ -37,7 +37,7 @@ constexpr int kBK = 64;
 constexpr int kWinRows = 136;
 constexpr int kWin4Rows = 72;                  // KIND 4: 64 pixels + 2 of halo, padded to whole 1024-byte swizzle atoms
 constexpr int kWin4Bytes = kWin4Rows * 128;
-// DUAL (fc1 in train mode): the epilogue stores TWO boxes per step (pre-activation u and gelu(u)), so each epilogue
+// DUAL (fc1 in train mode): the epilogue stores TWO boxes per step (gelu(u) and the derivative gelu'(u)), so each epilogue
 // warp gets four staging buffers instead of two and the ring gives up one stage.
 template <int BN, int CL, bool RE = false, bool W4 = false, bool DUAL = false, bool STG2 = false>
 struct GemmCfg {
@@ -89,8 +89,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmP& P, int id) {
 // (a runtime-flag version of the GELU / fp16 paths cost every KIND 0 kernel 15-40 % - measured):
 //   0 plain (bias / ReLU / residual / statistics / accumulate; bf16 or fp32 out)
 //   1 plain with IEEE fp16 output + residual (forward stem convolutions)
-//   2 gelu(acc + bias), bf16 out            3 the same + the pre-activation to a second tensor (DUAL)
-//   4 acc * gelu'(res), bf16 out (fc2 input gradient + activation backward)
+//   2 gelu(acc + bias), bf16 out            3 the same + gelu'(acc + bias) to a second tensor (DUAL)
+//   4 acc * res, bf16 out (fc2 input gradient + activation backward: res = the saved gelu')
 //   5 acc * relu_mask, bf16 out, + the BatchNorm-backward column sums of the layer in front (EPI_BN_BWD)
 constexpr int kEpiPlain = 0, kEpiF16 = 1, kEpiGelu = 2, kEpiGeluDual = 3, kEpiGeluBwd = 4, kEpiBnBwd = 5;
 template <int BN, int KIND, bool B_MN, int CL, bool RE = false, int EPI = 0>
@@ -472,12 +472,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float a = __uint_as_float(raw[i]) * P.alpha, c = __uint_as_float(raw[i + 1]) * P.alpha;
             if (P.flags & EPI_BIAS) { a += bv[i]; c += bv[i + 1]; }
             if (GELU) {                                      // timm Mlp: fc1 -> nn.GELU (erf form), fused
-              if (DUAL) packed2[i >> 1] = pack_bf16(a, c);   // the pre-activation u, kept for the backward
-              a = gelu_val(a); c = gelu_val(c);
+              if (DUAL) {                                    // train: gelu'(u) goes to the second tensor - the backward's
+                float ga, gc;                                // epilogue is then ONE multiply per element (evaluating gelu'
+                gelu_val_grad(a, a, ga);                     // from a saved u there left fc2's input-gradient GEMM at 29 %
+                gelu_val_grad(c, c, gc);                     // tensor-pipe activity: eight epilogue warps, instruction bound)
+                packed2[i >> 1] = pack_bf16(ga, gc);
+              } else {
+                a = gelu_val(a); c = gelu_val(c);
+              }
             }
-            if (GELUB) {                                     // du = da * gelu'(u), u = the saved pre-activation
-              const float2 uu = unpack_bf16(rw[i >> 1]);
-              a *= gelu_grad(uu.x); c *= gelu_grad(uu.y);
+            if (GELUB) {                                     // du = da * gelu'(u), gelu'(u) saved by the forward epilogue
+              const float2 gd = unpack_bf16(rw[i >> 1]);
+              a *= gd.x; c *= gd.y;
             }
             if (BNB) {                                       // g' = g * [y > 0]; q = g' * xhat for the column sums
               a = ((mword >> i) & 1u) ? a : 0.f;
@@ -801,7 +807,8 @@ int choose_splits(int base_tiles, long long q_total, long long out_elems) {
 // Y[M,N] = epilogue(alpha * X[M,K] W[N,K]^T): nn.Linear forward (both operands K-major).
 // flags: EPI_BF16 (else fp32 out), EPI_BIAS, EPI_RELU, EPI_ACCUM (out += via TMA reduce-add),
 // EPI_GELU (4096; bf16 out): out = gelu(alpha * X W^T + bias) - timm Mlp's fc1 + nn.GELU in one kernel; with `pre`
-// (nullable, bf16 [M, N], row stride ldp) the pre-activation is stored too (train mode: the backward needs it).
+// (nullable, bf16 [M, N], row stride ldp) the derivative gelu'(alpha * X W^T + bias) is stored too (train mode: the
+// backward multiplies by it - htrvt_gemm_nn's gelu_u, or htrvt_mul_bf16).
 extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long long ldw, int M, int N, int K,
                              int flags, const float* bias, void* out, long long ldo, float alpha, void* pre,
                              long long ldp, cudaStream_t stream) {
@@ -849,8 +856,8 @@ extern "C" int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long l
 }
 
 // dX[M,N] = dY[M,K] W[K,N]: nn.Linear input gradient (B operand MN-major, no transpose copy).
-// gelu_u (nullable, bf16 [M, N] contiguous): dX = (dY W) * gelu'(gelu_u) - the backward of timm Mlp's activation fused
-// into fc2's input-gradient GEMM (gelu_u = fc1's saved pre-activation).
+// gelu_u (nullable, bf16 [M, N] contiguous): dX = (dY W) * gelu_u - the backward of timm Mlp's activation fused
+// into fc2's input-gradient GEMM (gelu_u = gelu'(pre-activation), saved by fc1's forward epilogue through `pre`).
 // colsum (nullable, with gelu_u): fp32 [N] += column sums of the stored dX - fc1's bias gradient from the same epilogue.
 extern "C" int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long long ldw, int M, int N, int K,
                              int flags, void* out, long long ldo, float alpha, const void* gelu_u, float* colsum,

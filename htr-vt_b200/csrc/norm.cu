@@ -322,6 +322,24 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __re
   }
 }
 
+// out = a * b (bf16): the activation backward when gelu'(u) was saved by the forward epilogue and a dropout mask sits
+// between the activation and fc2 (model_window: da is masked first, then multiplied)
+__global__ void __launch_bounds__(256) mul_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                        __nv_bfloat16* __restrict__ out, long long n8) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8; i += stride) {
+    const uint4 x = *reinterpret_cast<const uint4*>(a + i * 8), y = *reinterpret_cast<const uint4*>(b + i * 8);
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 p = unpack_bf16(xs[k]), q = unpack_bf16(ys[k]);
+      o[k] = pack_bf16(p.x * q.x, p.y * q.y);
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Column sums of a bf16 matrix [M, N] (bias gradients): partial[cta][N]
 // ------------------------------------------------------------------------------------------------
@@ -677,6 +695,15 @@ extern "C" int htrvt_gelu_bwd(const void* da, const void* u, void* du, long long
   gelu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(da),
                                                             static_cast<const __nv_bfloat16*>(u),
                                                             static_cast<__nv_bfloat16*>(du), n / 8);
+  HTRVT_LAUNCH_CHECK();
+  return HTRVT_OK;
+}
+
+extern "C" int htrvt_mul_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t stream) {
+  if (n <= 0 || (n & 7)) return HTRVT_ERR_SHAPE;
+  mul_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(a),
+                                                            static_cast<const __nv_bfloat16*>(b),
+                                                            static_cast<__nv_bfloat16*>(out), n / 8);
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }

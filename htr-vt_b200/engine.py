@@ -252,7 +252,7 @@ class Engine(object):
             h2, m2, r2s, x2 = ops.row_ln_fwd(x1, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], self.ln_eps, y1)
             hid = wp[p + ".mlp.fc1.weight"].shape[0]
             # timm Mlp: fc1 -> nn.GELU in ONE kernel (GELU in the GEMM epilogue); with `save` the epilogue also stores
-            # the pre-activation u (a second TMA store per box) for the backward
+            # u = gelu'(pre-activation) (a second TMA store per box): the backward multiplies by it
             a = torch.empty((M, hid), dtype=torch.bfloat16, device=xs.device)
             u = torch.empty((M, hid), dtype=torch.bfloat16, device=xs.device) if save else None
             ops.gemm_tn(h2, wp[p + ".mlp.fc1.weight"], a, bias=sd[p + ".mlp.fc1.bias"], gelu=True, pre=u)
@@ -423,7 +423,7 @@ class Engine(object):
                 da = torch.empty_like(a)
                 ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], da)
                 ops.dropout_(da, T * hid, drop, seed, 8 * i + 2)
-                du = ops.gelu_bwd(da, u)
+                du = ops.mul_bf16(da, u)             # u holds gelu'(pre-activation)
             else:                        # fc2's input gradient and the activation's backward in one kernel
                 du = torch.empty_like(a)
                 ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], du, gelu_u=u, colsum=grads[p + ".mlp.fc1.bias"])

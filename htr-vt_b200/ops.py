@@ -60,7 +60,8 @@ def workspace(nbytes: int, device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 def gemm_tn(x, w, out, *, bias=None, relu=False, accumulate=False, flags=0, alpha=1.0, gelu=False, pre=None):
     """out[M,N] (+)= epilogue(alpha * x[M,K] @ w[N,K]^T).  x, w bf16 row-major; out bf16 or fp32 [M, N] view.
-    gelu: out = gelu(... + bias) (erf form, bf16 out); pre (bf16 [M,N]): also receives the pre-activation."""
+    gelu: out = gelu(... + bias) (erf form, bf16 out); pre (bf16 [M,N]): also receives gelu'(... + bias), the factor the
+    backward multiplies by (gemm_nn's gelu_u / mul_bf16)."""
     _need_cuda(x, w, out)
     M, K = x.shape
     N = w.shape[0]
@@ -73,7 +74,8 @@ def gemm_tn(x, w, out, *, bias=None, relu=False, accumulate=False, flags=0, alph
 
 def gemm_nn(dy, w, out, *, accumulate=False, alpha=1.0, gelu_u=None, colsum=None):
     """out[M,N] (+)= dy[M,K] @ w[K,N]   (w row-major [K,N]: the nn.Linear weight itself for dgrad).
-    gelu_u (bf16 [M,N] contiguous): out = (dy @ w) * gelu'(gelu_u); colsum (fp32 [N], with gelu_u) += column sums of
+    gelu_u (bf16 [M,N] contiguous): out = (dy @ w) * gelu_u, gelu_u = the gelu' saved by gemm_tn(gelu=True, pre=...);
+    colsum (fp32 [N], with gelu_u) += column sums of
     out (the bias gradient of the layer in front of the activation)."""
     _need_cuda(dy, w, out)
     M, K = dy.shape
@@ -527,6 +529,13 @@ def gelu_fwd(u):
     a = torch.empty_like(u)
     check(lib().htrvt_gelu_fwd(_p(u), _p(a), u.numel(), _stream()), "htrvt_gelu_fwd")
     return a
+
+
+def mul_bf16(a, b):
+    """a * b (bf16): the activation backward from the saved gelu' when a dropout mask sits between activation and fc2."""
+    out = torch.empty_like(a)
+    check(lib().htrvt_mul_bf16(_p(a), _p(b), _p(out), a.numel(), _stream()), "htrvt_mul_bf16")
+    return out
 
 
 def gelu_bwd(da, u):

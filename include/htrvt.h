@@ -107,9 +107,10 @@ int htrvt_augment_lines(const void* in, long long stride_b, void* out, const voi
  * htrvt_linear_wgrad : dW (+)= dY^T X  the same layers' weight gradient, fp32, split-K workspace
  * Fused activation of timm Mlp (fc1 -> nn.GELU, erf form; model_v1/model/HTR_VT.py:76):
  *   gemm_tn flags 4096: out = gelu(X W^T + bias) (bf16); `pre` (nullable bf16 [M,N], row stride ldp, N % 256 == 0)
- *   additionally receives the pre-activation u (train mode: two TMA stores per epilogue box);
- *   gemm_nn gelu_u (nullable, bf16 [M,N] contiguous): dX = (dY W) * gelu'(gelu_u) - fc2's input gradient and the
- *   activation's backward in one kernel. */
+ *   additionally receives the DERIVATIVE gelu'(X W^T + bias) (train mode: two TMA stores per epilogue box; gelu and
+ *   gelu' share one evaluation of Phi and exp);
+ *   gemm_nn gelu_u (nullable, bf16 [M,N] contiguous): dX = (dY W) * gelu_u, gelu_u = that saved derivative - fc2's
+ *   input gradient and the activation's backward in one kernel, one multiply per element in the epilogue. */
 int htrvt_gemm_tn(const void* X, long long ldx, const void* W, long long ldw, int M, int N, int K, int flags,
                   const float* bias, void* out, long long ldo, float alpha, void* pre, long long ldp, void* stream);
 int htrvt_gemm_nn(const void* dY, long long lddy, const void* W, long long ldw, int M, int N, int K, int flags,
@@ -206,6 +207,8 @@ int htrvt_tokens_bwd(const float* gx, const float* mask, void* dtok_bf16, float*
                      int T, int D, void* stream);
 int htrvt_gelu_fwd(const void* u, void* a, long long n, void* stream);
 int htrvt_gelu_bwd(const void* da, const void* u, void* du, long long n, void* stream);
+/* out = a * b (bf16, n % 8 == 0): the activation backward from the gelu'(u) the fused fc1 forward saved (`pre`). */
+int htrvt_mul_bf16(const void* a, const void* b, void* out, long long n, void* stream);
 int htrvt_colsum_rows(int M);
 int htrvt_colsum_bf16(const void* a, long long ld, int M, int N, float* out, int accumulate, float* partial,
                       void* stream);
