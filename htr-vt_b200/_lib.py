@@ -52,6 +52,7 @@ SIGNATURES = {
     "htrvt_ctc_kbest_paths": (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "htrvt_augment_lines": (_I, [_P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "htrvt_ctc_prefix_beam": (_I, [_P, _L, _L, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "htrvt_set_pdl": (_I, [_I]),
     "htrvt_gemm_tn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _P, _L, _F, _P, _L, _P]),
     "htrvt_gemm_nn": (_I, [_P, _L, _P, _L, _I, _I, _I, _I, _P, _L, _F, _P, _P, _P]),
     "htrvt_wgrad_workspace_bytes": (_Z, [_I, _I, _I, _I]),

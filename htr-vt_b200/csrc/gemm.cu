@@ -145,6 +145,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CL == 2) cluster_sync_all();           // the peer's barriers must be initialised before anything lands on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch, the pair's
+  // cluster sync) touches no global memory and may run under the tail of the kernel in front; from here on the kernel
+  // reads and writes tensors, so it waits for that kernel's completion + flush.  The trigger right behind it lets the
+  // NEXT launch do the same under this kernel's tail (its CTAs become resident as ours exit).  Both are no-ops for a
+  // launch without the programmatic-serialisation attribute.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -686,6 +693,16 @@ int num_sms() {
   return n;
 }
 
+// Programmatic dependent launch of the tap GEMMs (HTRVT_PDL=0 or htrvt_set_pdl(0): plain stream order)
+int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("HTRVT_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+
 template <int BN, int KIND, bool B_MN, int CL, bool RE = false, int EPI = 0>
 int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
                cudaStream_t stream, const CUtensorMap* c2p = nullptr) {
@@ -694,22 +711,27 @@ int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
   const CUtensorMap& c2 = c2p ? *c2p : c;
   if (!HTRVT_ENSURE_SMEM(kern, Cfg::kSmemBytes)) return HTRVT_ERR_LAUNCH;
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  if (CL == 1) {
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(a, b, c, c2, P);
-  } else {
-    grid &= ~1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, kern, a, b, c, c2, P) != cudaSuccess) return HTRVT_ERR_LAUNCH;
+  if (CL == 2) grid &= ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL == 2) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
   }
+  if (pdl_enabled()) {                       // the kernel's prologue may overlap the tail of the launch in front
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  if (cudaLaunchKernelEx(&cfg, kern, a, b, c, c2, P) != cudaSuccess) return HTRVT_ERR_LAUNCH;
   HTRVT_LAUNCH_CHECK();
   return HTRVT_OK;
 }
@@ -803,6 +825,15 @@ int choose_splits(int base_tiles, long long q_total, long long out_elems) {
 }
 
 }  // namespace
+
+// Programmatic dependent launch of every tap-GEMM launch (default on; HTRVT_PDL=0 in the environment turns it off):
+// 1 = the kernel's prologue may run under the tail of the launch in front of it, 0 = plain stream order.  Returns the
+// previous setting.  Results do not depend on it.
+extern "C" int htrvt_set_pdl(int on) {
+  const int old = pdl_enabled() ? 1 : 0;
+  g_pdl = on ? 1 : 0;
+  return old;
+}
 
 // Y[M,N] = epilogue(alpha * X[M,K] W[N,K]^T): nn.Linear forward (both operands K-major).
 // flags: EPI_BF16 (else fp32 out), EPI_BIAS, EPI_RELU, EPI_ACCUM (out += via TMA reduce-add),

@@ -19,6 +19,46 @@ from . import ops
 STEM_LAYERS = (("layer1", (2, 1)), ("layer2", (2, 2)), ("layer3", (2, 2)))
 # BatchNorm-backward reduction in the epilogue of the GEMM that produces the gradient (HTRVT_FUSE_BN_BWD=0: two-pass route)
 FUSE_BN_BWD = os.environ.get("HTRVT_FUSE_BN_BWD", "1") != "0"
+# Weight-gradient GEMMs on a second stream (HTRVT_WGRAD_STREAM=0: everything on the caller's stream).  They depend only on
+# a layer's dY and its saved input, nothing in the backward reads them before the gradients are handed over, so they fill
+# the SMs the input-gradient chain leaves idle: kernel tails, grids smaller than the machine, and the HBM-bound
+# BatchNorm / LayerNorm passes whose CTAs fit beside a resident GEMM CTA.
+WGRAD_STREAM = os.environ.get("HTRVT_WGRAD_STREAM", "1") != "0"
+
+
+class _SideStream(object):
+    """Runs independent launches of the backward on a per-device second stream.  Every submission waits for what the
+    caller's stream has enqueued so far (its inputs were produced there); `join()` makes the caller's stream wait for
+    the side work and only then drops the references that kept the inputs' memory from being reused."""
+    _streams = {}
+
+    def __init__(self, device, enabled):
+        self.on = bool(enabled) and device.type == "cuda"
+        self.keep = []
+        self.pending = False
+        if self.on:
+            key = device.index if device.index is not None else torch.cuda.current_device()
+            st = _SideStream._streams.get(key)
+            if st is None:
+                st = _SideStream._streams[key] = (torch.cuda.Stream(device=device), torch.cuda.Event())
+            self.side, self.ev = st
+            self.main = torch.cuda.current_stream(device)
+
+    def run(self, fn, *args):
+        if not self.on:
+            return fn(*args)
+        self.ev.record(self.main)
+        self.side.wait_event(self.ev)
+        self.keep.append(args)
+        self.pending = True
+        with torch.cuda.stream(self.side):
+            return fn(*args)
+
+    def join(self):
+        if self.on and self.pending:
+            self.main.wait_stream(self.side)
+            self.pending = False
+        self.keep = []
 
 
 class _Ctx(object):
@@ -112,6 +152,7 @@ class Engine(object):
             stem = [v for k, v in sd.items() if k.startswith("patch_embed.")]
             key = (ops.WEIGHT_EPOCH, tuple((v.data_ptr(), v._version) for v, _ in items),
                    tuple((v.data_ptr(), v._version) for v in stem))
+        pack_side = None
         cached = getattr(self, "_wp_cache", None)
         if key is not None and cached is not None and cached[0] == key:
             wp, bnst = cached[1], cached[2]
@@ -133,8 +174,12 @@ class Engine(object):
             reuse = None
             if not fold and pool is not None and pool[0] == sig and getattr(self, "_wp_busy", 0) == 0:
                 reuse = pool[1]
-            packed = ops.pack_weights(items, pad_rows={"head.weight": C8} if C8 != C else None, names=names,
-                                      reuse=reuse)                  # one launch for all 36 weight tensors
+            # steady-state train steps (in-place re-pack, no allocation): the pack runs on the side stream under the
+            # stem head, which reads conv1's fp32 weights only; joined in front of the first stem block
+            pack_side = _SideStream(image.device, WGRAD_STREAM and reuse is not None)
+            packed = pack_side.run(lambda: ops.pack_weights(
+                items, pad_rows={"head.weight": C8} if C8 != C else None, names=names,
+                reuse=reuse))                                       # one launch for all 36 weight tensors
             wp = dict(zip(names, packed))
             if not fold:
                 self._wp_pool = (sig, packed)
@@ -160,6 +205,8 @@ class Engine(object):
             x, code1, x_bf = ops.stem_head_fwd(x0, w1, st1, True, want_bf16=True)
         else:
             x, code1 = ops.stem_head_fwd(x0, w1, st1, False)
+        if pack_side is not None:
+            pack_side.join()
         blocks = []
         last_block = "patch_embed.%s.1" % STEM_LAYERS[-1][0]
         zpool = None
@@ -381,6 +428,7 @@ class Engine(object):
         M = B * T
         wp = ctx.wp
         dev = dlogits.device
+        side = _SideStream(dev, WGRAD_STREAM)
         dlogits = dlogits.contiguous().float()
         ldc = (C + 7) // 8 * 8
         if self.variant == "v1":
@@ -389,7 +437,7 @@ class Engine(object):
             draw = torch.zeros((M, ldc), dtype=torch.bfloat16, device=dev)
             draw[:, :C] = ops.cast_bf16(dlogits.view(M, C))
         if ldc == C:
-            ops.linear_wgrad(draw, ctx.hf, grads["head.weight"])
+            side.run(ops.linear_wgrad, draw, ctx.hf, grads["head.weight"])
             ops.colsum_bf16(draw, grads["head.bias"])
         else:                            # class axis padded to a multiple of 8: gradients of the zero rows are dropped
             gw = torch.zeros((ldc, D), dtype=torch.float32, device=dev)
@@ -417,7 +465,7 @@ class Engine(object):
                 ops.colsum_bf16(gy, grads[p + ".mlp.fc2.bias"])
             else:                        # bf16 dY of fc2 and fc2's bias gradient in one pass over the residual gradient
                 gy = ops.cast_colsum_bf16(gx, grads[p + ".mlp.fc2.bias"])
-            ops.linear_wgrad(gy, a, grads[p + ".mlp.fc2.weight"])
+            side.run(ops.linear_wgrad, gy, a, grads[p + ".mlp.fc2.weight"])
             fused_bias = False
             if rng and drop > 0.0:       # dropout sits between the activation and fc2: its mask applies to da first
                 da = torch.empty_like(a)
@@ -428,7 +476,7 @@ class Engine(object):
                 du = torch.empty_like(a)
                 ops.gemm_nn(gy, wp[p + ".mlp.fc2.weight"], du, gelu_u=u, colsum=grads[p + ".mlp.fc1.bias"])
                 fused_bias = True
-            ops.linear_wgrad(du, h2, grads[p + ".mlp.fc1.weight"])
+            side.run(ops.linear_wgrad, du, h2, grads[p + ".mlp.fc1.weight"])
             if not fused_bias:
                 ops.colsum_bf16(du, grads[p + ".mlp.fc1.bias"])
             dh2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
@@ -441,7 +489,7 @@ class Engine(object):
                 ops.colsum_bf16(gy, grads[p + ".attn.proj.bias"])
             else:
                 gy = ops.cast_colsum_bf16(gx, grads[p + ".attn.proj.bias"])
-            ops.linear_wgrad(gy, o, grads[p + ".attn.proj.weight"])
+            side.run(ops.linear_wgrad, gy, o, grads[p + ".attn.proj.weight"])
             do = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
             ops.gemm_nn(gy, wp[p + ".attn.proj.weight"], do)
             dqkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
@@ -455,13 +503,14 @@ class Engine(object):
                 ops.attention2_bwd(qkv.view(B, T, 3, self.H, self.hd), o.view(B, T, D), do.view(B, T, D), lse,
                                    dqkv.view(B, T, 3, self.H, self.hd), scale, tbl, (tbl.shape[0] + 1) // 2, ws, sh,
                                    grads.get(tname), attn_drop, seed + 16 * i)
-            ops.linear_wgrad(dqkv, h1, grads[p + ".attn.qkv.weight"])
-            ops.colsum_bf16(dqkv, grads[p + ".attn.qkv.bias"])
+            side.run(ops.linear_wgrad, dqkv, h1, grads[p + ".attn.qkv.weight"])
+            ops.colsum_bf16(dqkv, grads[p + ".attn.qkv.bias"])      # (uses the shared scratch: stays on this stream)
             dh1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
             ops.gemm_nn(dqkv, wp[p + ".attn.qkv.weight"], dh1)
             ops.row_ln_bwd(dh1, x1, m1, r1s, sd[p + ".norm1.weight"], gx, True, grads[p + ".norm1.weight"],
                            grads[p + ".norm1.bias"])
         if on_stage is not None:
+            side.join()
             on_stage("transformer")          # every blocks.* / norm / head gradient is final
         dtok = ops.tokens_bwd(gx, ctx.mask, grads["mask_token"].view(-1), B, T, D)
         g = ops.pool_bwd(dtok.view(B, 1, T, D), ctx.idx2, ctx.l3_shape)
@@ -492,6 +541,9 @@ class Engine(object):
             off += wp[k].numel()
 
         def wgrad(dy, x, ks, sh, sw, name):
+            side.run(wgrad_main, dy, x, ks, sh, sw, name)
+
+        def wgrad_main(dy, x, ks, sh, sw, name):
             if layout[name] == "atoms":
                 ops.conv_wgrad_acc_w(dy, x, sh, gt[name])
             elif layout[name] == "tco":
@@ -503,6 +555,7 @@ class Engine(object):
         def unpack(pred):                # staged conv weight gradients -> the OIHW .grad tensors, one launch per layout
             sel = [k for k in cnames if k not in unpacked and pred(k)]
             unpacked.update(sel)
+            side.join()                  # the staged gradients come from the side stream
             for lay, kw in (("atoms", dict(layout="atoms")), ("tco", dict(transposed=True)), ("ctc", dict())):
                 part = [(gt[k], grads[k]) for k in sel if layout[k] == lay]
                 if part:

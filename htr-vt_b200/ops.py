@@ -42,6 +42,11 @@ def _need_cuda(*ts):
             raise HtrvtError("htr-vt_b200 kernels need CUDA tensors (there is no CPU fallback)")
 
 
+def set_pdl(on) -> bool:
+    """Programmatic dependent launch of the tap-GEMM family (htrvt_set_pdl); returns the previous setting."""
+    return bool(lib().htrvt_set_pdl(int(bool(on))))
+
+
 _ws_cache = {}
 
 
@@ -93,10 +98,10 @@ def linear_wgrad(dy, x, grad, *, accumulate=True):
     _need_cuda(dy, x, grad)
     M, N = dy.shape
     K = x.shape[1]
-    nbytes = lib().htrvt_wgrad_workspace_bytes(N, K, 1, M)
-    ws = workspace(nbytes, dy.device)
+    # split-K slices reduce-add straight into `grad`: the entry point takes no scratch (its workspace arguments are kept
+    # for the ABI), so the call is safe on any stream
     check(lib().htrvt_linear_wgrad(_p(dy), dy.stride(0), _p(x), x.stride(0), M, N, K, _p(grad), int(accumulate),
-                                   _p(ws), ws.numel(), _stream()), "htrvt_linear_wgrad")
+                                   _p(None), 0, _stream()), "htrvt_linear_wgrad")
     return grad
 
 

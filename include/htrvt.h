@@ -98,6 +98,13 @@ int htrvt_ctc_prefix_beam(const float* log_probs, long long stride_b, long long 
 int htrvt_augment_lines(const void* in, long long stride_b, void* out, const void* recs, int B, int H, int W,
                         int morph, int k_rows, int k_cols, int iterations, void* stream);
 
+/* Launch policy of the tensor-core GEMM family (all htrvt_gemm_*, htrvt_linear_wgrad, htrvt_conv_* entry points): with
+ * programmatic dependent launch (default; HTRVT_PDL=0 in the environment disables it) a GEMM's prologue - barrier
+ * initialisation, TMEM allocation, descriptor prefetch - runs under the tail of the launch in front of it on the same
+ * stream; its first access to a tensor waits for that launch to complete.  Results do not depend on the setting.  There
+ * is no counterpart in the reference (cuBLAS / cuDNN pick their own launch attributes).  Returns the previous setting. */
+int htrvt_set_pdl(int on);
+
 /* ---- tcgen05 tap-GEMM: nn.Linear / nn.Conv2d forward, input gradient, weight gradient ------------------
  * flags (epilogue, run by 8 warps and kept light): 1 bf16 out (else fp32), 2 +bias, 16 accumulate into out
  * (TMA reduce-add store), 32 column statistics (conv fwd), 128 ReLU.  Outputs leave through TMA stores.

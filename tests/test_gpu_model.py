@@ -120,6 +120,50 @@ def test_train_step_matches_oracle(cfg):
     assert not bad, bad
 
 
+def test_side_stream_weight_gradients_equal_single_stream():
+    """engine.WGRAD_STREAM: weight-gradient GEMMs (and the steady-state weight re-pack) on a second stream.  Same
+    kernels, same inputs: every gradient must equal the single-stream schedule's up to the split-K reduce-add order
+    (fp32 atomics), over several steps so that the in-place re-pack path and buffer reuse are exercised."""
+    import htrvt_b200 as h
+    eng = import_module("htr-vt_b200.engine")
+    cfg = dict(nb_cls=80, W=512, D=768, depth=4, heads=6, B=4, seed=31)
+    x = _images(cfg["seed"] + 1, cfg["B"], cfg["W"]).cuda()
+    tg, tl = _labels(cfg["seed"] + 2, cfg["B"], cfg["nb_cls"], 4, 12)
+    crit = h.CTCLoss(reduction="none", zero_infinity=True).to("cuda")
+    out = []
+    old = eng.WGRAD_STREAM
+    try:
+        for flag in (False, False, True):
+            eng.WGRAD_STREAM = flag
+            m, _ = _build(cfg["nb_cls"], cfg["W"], cfg["D"], cfg["depth"], cfg["heads"], cfg["seed"])
+            m.train()
+            for it in range(3):
+                for p in m.parameters():
+                    p.grad = None
+                torch.manual_seed(7 + it)
+                preds = m(x, 0.4, 8, use_masking=True).float()
+                lp = preds.permute(1, 0, 2).log_softmax(2)
+                loss = crit(lp, tg.cuda(), torch.IntTensor([preds.size(1)] * cfg["B"]).cuda(), tl.cuda()).mean()
+                loss.backward()
+            torch.cuda.synchronize()
+            out.append((preds.detach().clone(), {n: p.grad.detach().double() for n, p in m.named_parameters()
+                                                 if p.grad is not None}))
+    finally:
+        eng.WGRAD_STREAM = old
+    (l0, g0), (l0b, g0b), (l1, g1) = out
+    assert torch.equal(l0, l1) and torch.equal(l0, l0b)                  # the forward (incl. the re-pack) is identical
+    assert g0.keys() == g1.keys() and len(g0) > 50
+    # noise floor: two IDENTICAL single-stream runs differ (free summation order of split-K slices and BatchNorm sums)
+    den = sum(float((g0[n] ** 2).sum()) for n in g0)
+    noise = (sum(float(((g0[n] - g0b[n]) ** 2).sum()) for n in g0) / den) ** 0.5
+    diff = (sum(float(((g0[n] - g1[n]) ** 2).sum()) for n in g0) / den) ** 0.5
+    assert diff <= 4.0 * noise + 1e-6, (diff, noise)
+    for n in g0:
+        a, b = g0[n].reshape(-1), g1[n].reshape(-1)
+        cos = float(a @ b / (a.norm() * b.norm() + 1e-30))
+        assert cos > 0.999, (n, cos)
+
+
 def _family(name):
     """Tensor classes of the gradient check: stem convolution / BatchNorm tensors vs transformer tensors."""
     return "stem" if name.startswith("patch_embed.") else "transformer"

@@ -1,5 +1,6 @@
 """A/B timing of the training step inside ONE process (same box, same clocks): alternates blocks of steps with a module
-flag off / on and prints the per-variant medians.  Usage: python tools/ab_step.py engine.FUSE_BN_BWD [rounds] [steps]"""
+flag off / on and prints the per-variant medians.  Usage: python tools/ab_step.py engine.FUSE_BN_BWD [rounds] [steps]
+(a callable attribute, e.g. ops.set_pdl, is called with False / True instead of being assigned)"""
 import os
 import statistics
 import sys
@@ -32,14 +33,21 @@ def step():
     loss.backward()
 
 
+_target = getattr(mod, attr)
+if callable(_target):
+    def _set(v):
+        _target(v)
+else:
+    def _set(v):
+        setattr(mod, attr, v)
 res = {False: [], True: []}
 for v in (False, True):
-    setattr(mod, attr, v)
+    _set(v)
     for _ in range(3):
         step()
 for r in range(rounds):
     for v in (False, True) if r % 2 == 0 else (True, False):
-        setattr(mod, attr, v)
+        _set(v)
         step()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
