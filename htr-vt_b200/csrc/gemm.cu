@@ -39,20 +39,34 @@ constexpr int kWin4Rows = 72;                  // KIND 4: 64 pixels + 2 of halo,
 constexpr int kWin4Bytes = kWin4Rows * 128;
 // DUAL (fc1 in train mode): the epilogue stores TWO boxes per step (gelu(u) and the derivative gelu'(u)), so each epilogue
 // warp gets four staging buffers instead of two and the ring gives up one stage.
-template <int BN, int CL, bool RE = false, bool W4 = false, bool DUAL = false, bool STG2 = false>
+// RESQ (fc2's input gradient times the saved gelu'; the BatchNorm-backward epilogue at BN <= 192): the second input tensor
+// of the epilogue is staged in shared memory - every epilogue warp copies ITS [32 rows][BN / 2 columns] of the tile with
+// coalesced 16-byte cp.async transfers before it waits for the accumulator (16-byte chunks XOR-swizzled by the row, or a
+// row pitch of BN + 16 bytes when the row is not a power of two: the per-row reads of 8 consecutive rows fall on 8
+// distinct 16-byte bank groups; the operand ring gives up one or two stages).
+// Per-thread row loads (32 lanes x 64 B at a row pitch of several KB = 32 sectors per request) had left these GEMMs at
+// 38 % / 58 % tensor-pipe activity with the L1 data pipe as their busiest unit and most of the epilogue's stall samples
+// on those loads.
+template <int BN, int CL, bool RE = false, bool W4 = false, bool DUAL = false, bool STG2 = false, bool RESQ = false>
 struct GemmCfg {
   static constexpr int kABytes = W4 ? 2 * kWin4Bytes : RE ? kWinRows * kBK * 2 : kBM * kBK * 2;
   static constexpr int kBTile = (BN / CL) * kBK * 2;                  // one tap's B bytes staged by THIS CTA
   static constexpr int kBBytes = RE ? 3 * kBTile : kBTile;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  // bytes per staged row: BN / 2 16-bit columns; a power-of-two row (BN = 256) is XOR-swizzled at 16-byte granularity,
+  // any other gets one 16-byte pad
+  static constexpr bool kResXor = ((BN / 2) & (BN / 2 - 1)) == 0;
+  static constexpr int kResPitch = kResXor ? BN : BN + 16;
+  static constexpr int kResBytes = RESQ ? 8 * 32 * kResPitch : 0;
   static constexpr int kStages = (W4 ? (BN >= 256 ? 3 : 4) : RE ? (BN >= 256 ? 2 : 3) : (CL == 2) ? 6 : ((BN <= 128) ? 6 : 4)) -
-                                 (DUAL ? 1 : 0);
+                                 (DUAL ? 1 : 0) - (RESQ ? (RE ? 1 : 2) : 0);
+  static_assert(kStages >= 2, "operand ring");
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
   // per epilogue warp: [32 rows][64 B] output boxes, two buffers; DUAL / STG2 (BatchNorm-backward epilogue: a second box
   // per step that only feeds the column sums) double them
   static constexpr int kWarpStaging = (DUAL || STG2) ? 4 * 2048 : 2 * 2048;
   static constexpr int kStagingBytes = 8 * kWarpStaging;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 256 /*barriers*/ + kResBytes;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert(kStageBytes % 1024 == 0, "SWIZZLE_128B stage alignment");
 };
@@ -103,7 +117,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr bool GELU = (EPI == kEpiGelu || EPI == kEpiGeluDual), GELUB = (EPI == kEpiGeluBwd);
   constexpr bool BNB = (EPI == kEpiBnBwd);
   constexpr bool BOX2 = DUAL || BNB;                   // a second staged box per step
-  using Cfg = GemmCfg<BN, CL, RE, W4, DUAL, BNB>;
+  constexpr bool RESQ = GELUB || (BNB && BN <= 192);   // second input tensor staged in shared memory by cp.async
+  using Cfg = GemmCfg<BN, CL, RE, W4, DUAL, BNB, RESQ>;
   static_assert(EPI == 0 || KIND == 0, "epilogue variants exist for kind 0 only");
   static_assert(!(GELU || GELUB) || !RE, "GELU epilogues: linear layers only");
   static_assert(!RE || (KIND == 0 && !B_MN && CL == 2), "window reuse: kind 0, K-major weights, CTA pairs");
@@ -407,11 +422,33 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             P.mask + ((((static_cast<long long>(tc.n) * P.Ho + tc.h) * P.Wo + w) * P.N_valid + col) >> 3)));
       return 0u;
     };
-    constexpr bool kResEpi = GELUB || BNB;              // epilogues that always read a second tensor
+    constexpr bool kResEpi = (GELUB || BNB) && !RESQ;   // epilogues that read a second tensor row by row from global
+    // RESQ: this warp's [32 rows][kColsPerWarp] of the second tensor, row pitch Cfg::kResPitch bytes
+    const uint32_t resq = RESQ ? smem_u32(stage_out + Cfg::kStagingBytes + 256) + ew * (32 * Cfg::kResPitch) : 0u;
     int as = 0; uint32_t aphase = 0;
     for (int id = first_tile; id < total_tiles; id += tile_step) {
       const TileCoord tc = decode_tile(P, id);
       const int n0 = tc.n_tile * BN;
+      if (RESQ) {
+        // requested before the wait for the accumulator: the round trip runs under the tile's MMAs.  Chunk 32 j + lane of
+        // the slice (row-major, kChunksPerRow 16-byte chunks per row): a warp-wide copy reads whole contiguous row pieces
+        constexpr int kChunksPerRow = kColsPerWarp / 8;
+        __syncwarp();                                          // every lane is done with the previous tile's rows
+#pragma unroll
+        for (int j = 0; j < kChunksPerRow; ++j) {
+          const int idx = 32 * j + lane;
+          const int q = idx / kChunksPerRow, ch = idx - q * kChunksPerRow;     // row of the warp's 32, chunk of the row
+          const int col = n0 + half * kColsPerWarp + ch * 8;
+          const int w = tc.w0 + quad * 32 + q;
+          const bool ok = w < P.Wo && col < P.N_valid;
+          const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(P.res) +
+              (ok ? ((static_cast<long long>(tc.n) * P.Ho + tc.h) * P.Wo + w) * P.N_valid + col : 0ll);
+          const uint32_t dst = resq + q * Cfg::kResPitch + ((Cfg::kResXor ? (ch ^ (q & 7)) : ch) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (BNB) mw_nxt = mask_load(tc, n0 + half * kColsPerWarp);
+      }
       if (kResEpi && KIND == 0) {
         // the first box's rows of the second tensor are requested BEFORE the wait for the accumulator: their L2 / DRAM
         // round trip runs under the tile's MMAs
@@ -424,6 +461,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_tile = W4 ? 2 * tc.m_tile + sub : tc.m_tile;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+      if (RESQ) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();                                          // the rows were copied by other lanes
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * kColsPerWarp;
       const int nboxes = kColsPerWarp / box_cols;
 #pragma unroll 1
@@ -458,6 +499,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           uint4 rq[4] = {};
+          if (RESQ) {                                        // this thread's row of the staged slice, chunks 4b .. 4b + 3
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t a = resq + lane * Cfg::kResPitch + ((Cfg::kResXor ? ((4 * b + i) ^ (lane & 7)) : (4 * b + i)) << 4);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(rq[i].x), "=r"(rq[i].y), "=r"(rq[i].z), "=r"(rq[i].w) : "r"(a));
+            }
+          } else
           if (KIND == 0 && (GELUB || BNB || (!GELU && (P.flags & EPI_RES)))) {   // this thread's output pixel, 32 consecutive channels
             // the 64 bytes of box b were requested one box earlier (rq_nxt): an L2 / DRAM round trip per box would
             // otherwise sit between the TMEM load and the store of every box of this warp
@@ -581,8 +630,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               qacc = fmaf(f, f, qacc);
             }
           }
-          ssum[b] += sacc;
-          qsum[b] += qacc;
+          // (static indices: `ssum[b]` with the runtime box index put both arrays in local memory - an LDL / STL round
+          // trip per box behind the L1 queue of the epilogue's global loads)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (b == k) { ssum[k] += sacc; qsum[k] += qacc; }
         }
         sbuf ^= 1;
       }
@@ -706,7 +758,8 @@ bool pdl_enabled() {
 template <int BN, int KIND, bool B_MN, int CL, bool RE = false, int EPI = 0>
 int launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmP& P, int total_tiles,
                cudaStream_t stream, const CUtensorMap* c2p = nullptr) {
-  using Cfg = GemmCfg<BN, CL, RE, KIND == 4, EPI == kEpiGeluDual, EPI == kEpiBnBwd>;
+  using Cfg = GemmCfg<BN, CL, RE, KIND == 4, EPI == kEpiGeluDual, EPI == kEpiBnBwd,
+                      EPI == kEpiGeluBwd || (EPI == kEpiBnBwd && BN <= 192)>;
   auto kern = tapgemm_kernel<BN, KIND, B_MN, CL, RE, EPI>;
   const CUtensorMap& c2 = c2p ? *c2p : c;
   if (!HTRVT_ENSURE_SMEM(kern, Cfg::kSmemBytes)) return HTRVT_ERR_LAUNCH;
