@@ -75,7 +75,6 @@ __global__ void __launch_bounds__(1024) line_prep_u8_kernel(const uint8_t* __res
   }
   __syncthreads();
   const float mean = stat[0], rstd = stat[1];
-  constexpr float k = 1.0f / 255.0f;
   for (int i = threadIdx.x; i < n4; i += 1024) {
     const uchar4 v = load4(i);
     const int r = i / W4, c = (i - r * W4) * 4;
@@ -84,7 +83,6 @@ __global__ void __launch_bounds__(1024) line_prep_u8_kernel(const uint8_t* __res
                                  (__fdiv_rn(static_cast<float>(v.y), 255.0f) - mean) * rstd,
                                  (__fdiv_rn(static_cast<float>(v.z), 255.0f) - mean) * rstd,
                                  (__fdiv_rn(static_cast<float>(v.w), 255.0f) - mean) * rstd);
-    (void)k;
     *reinterpret_cast<float4*>(yb + static_cast<long long>(r) * W + c) = o;
   }
 }
