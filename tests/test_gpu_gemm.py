@@ -279,3 +279,31 @@ def test_conv_dgrad_with_bn_backward_epilogue(NB, H, W, C):
     y.backward(dy.float().permute(0, 3, 1, 2))
     assert _rel(d_b, xf.grad.permute(0, 2, 3, 1)) < 3e-2
     assert _rel(dg_b, gam.grad) < 2e-2 and _rel(db_b, bet.grad) < 2e-2
+
+
+def test_programmatic_dependent_launch_does_not_change_results():
+    """htrvt_set_pdl: the tap GEMMs' prologue may run under the tail of the kernel in front; a chain of dependent GEMMs
+    (each reads what the previous one wrote) must give bit-identical results with and without it."""
+    o = ops()
+    torch.manual_seed(3)
+    M, K = 4096, 768
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    ws = [(torch.randn(K, K, device="cuda") / K ** 0.5).bfloat16() for _ in range(6)]
+    outs = {}
+    prev = o.set_pdl(True)
+    try:
+        for flag in (False, True, False):
+            assert o.set_pdl(flag) in (True, False)
+            h = x
+            for w in ws:                                   # back-to-back launches on one stream, no host sync
+                y = torch.empty(M, K, device="cuda", dtype=torch.bfloat16)
+                o.gemm_tn(h, w, y)
+                h = y
+            torch.cuda.synchronize()
+            outs.setdefault(flag, []).append(h.clone())
+        assert o.set_pdl(True) is False                    # returns the previous setting
+    finally:
+        o.set_pdl(prev)
+    assert torch.equal(outs[False][0], outs[False][1])
+    assert torch.equal(outs[False][0], outs[True][0])
+    assert torch.isfinite(outs[True][0].float()).all()
