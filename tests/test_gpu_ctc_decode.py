@@ -390,3 +390,24 @@ def test_prefix_beam_exact_posterior_and_lm_entry_points():
     cands = h.kbest_candidates(torch.from_numpy(peaked).unsqueeze(1).cuda(), h.CTCLabelConverter("abc"), 3,
                                search="prefix")[0]
     assert cands[0][0] == "aab"
+
+
+def test_decode_logits_async_matches_sync_and_reuses_pinned_buffers():
+    """CTCLabelConverter.decode_logits_async: same strings as decode_logits, several handles in flight, the pinned
+    host pair of a resolved handle is reused by the next call."""
+    import htrvt_b200 as h
+    conv = h.CTCLabelConverter("".join(chr(33 + i) for i in range(79)))
+    torch.manual_seed(2)
+    batches = [torch.randn(64, 128, 80, device="cuda") * 3 for _ in range(4)]
+    want = [conv.decode_logits(x) for x in batches]
+    handles = [conv.decode_logits_async(x) for x in batches[:3]]            # three in flight
+    got = [hd.strings() for hd in handles]
+    assert got == want[:3]
+    assert handles[0].strings() is got[0] and handles[0].done()             # resolved once, cached
+    pool = conv._pinned[((64, 128), torch.cuda.current_device())]
+    assert len(pool) == 3
+    hd = conv.decode_logits_async(batches[3])
+    assert len(pool) == 2                                                   # took a pinned pair back out of the pool
+    assert hd.strings() == want[3] and len(pool) == 3
+    lens = torch.randint(1, 129, (64,), dtype=torch.int32)
+    assert conv.decode_logits_async(batches[0], lens).strings() == conv.decode_logits(batches[0], lens)
