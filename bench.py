@@ -41,9 +41,13 @@ def synth_batch(B, seed):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  nvidia-smi needs
+    0.1-0.5 s before its first sample, about as long as a 20-step timed region: the sampler is therefore started in
+    front of the warm-up steps, every sample carries nvidia-smi's own wall-clock time stamp, and only the samples between
+    mark() (timed region starts) and stop() are reported; if none fell inside (a very short region), the samples of
+    the warm-up (same kernels, same load) are reported and `window` says so."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -51,6 +55,7 @@ class ClockSampler(object):
         self.gpu = gpu_index
         self.path = tempfile.mktemp(prefix="htrvt_clocks_", suffix=".csv")
         self.proc = None
+        self.t0 = None
 
     def start(self):
         try:
@@ -60,8 +65,23 @@ class ClockSampler(object):
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+            return
+        t_end = time.time() + 3.0                  # nvidia-smi's first sample: the loop is running from here on
+        while time.time() < t_end:
+            try:
+                self.fh.flush()
+                if os.path.getsize(self.path) > 0:
+                    break
+            except Exception:
+                break
+            time.sleep(0.02)
+
+    def mark(self):
+        self.t0 = time.time()
 
     def stop(self):
+        import datetime
+        t1 = time.time()
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -71,23 +91,33 @@ class ClockSampler(object):
         except Exception:
             self.proc.kill()
         self.fh.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [v.strip() for v in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                try:
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except Exception:
+                    ts = None
+                rows.append((ts, float(f[2]), float(f[3]),
+                             [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                       "sw_power_cap"), f[6:10]) if v.lower().startswith("active")]))
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if self.t0 is not None and r[0] is not None and self.t0 <= r[0] <= t1]
+        window = "timed region"
+        if not inside:
+            inside, window = rows, "warm-up + timed region (no sample fell inside the timed region)"
+        if inside:
+            sm = sorted(r[1] for r in inside)
+            reasons = set()
+            for r in inside:
+                reasons.update(r[3])
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(r[2] for r in inside), reasons=sorted(reasons),
+                       samples=len(inside), window=window)
         return out
 
 
@@ -657,6 +687,7 @@ def run_infer(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    clocks.mark()                         # (inference_metrics warms up inside; its two timed legs follow back to back)
     m = inference_metrics(torch, dist, dev, h, ops, model, world, rank, steps=args.steps)
     clk = clocks.stop() if rank == 0 else None
     # roofline of the tap-GEMM family inside one inference batch (CUDA events per op on the launching stream)
@@ -793,11 +824,12 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    clocks.mark()
     n0 = ops.launch_count()
     total_ms = timed(step_resident, args.steps)
     launches = ops.launch_count() - n0
