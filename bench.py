@@ -796,6 +796,17 @@ def run_ours(args):
     pf = h.HostPrefetcher(dev)
     pf.put(img_h, tg_h, tl_h)
 
+    def step_e2e_sync():
+        for p in params:
+            p.grad = None
+        image, text, length = pf.get()
+        pf.put(img_h, tg_h, tl_h)                # the next step's inputs
+        loss = compute_loss(image, text, length)
+        loss.backward()
+        return loss.item()                       # train.py:129 as written: a device sync every step
+
+    meter = h.RunningLoss()
+
     def step_e2e():
         for p in params:
             p.grad = None
@@ -803,19 +814,21 @@ def run_ours(args):
         pf.put(img_h, tg_h, tl_h)                # the next step's inputs
         loss = compute_loss(image, text, length)
         loss.backward()
-        return loss.item()                       # D2H read of the step's result, every step
+        meter.add(loss)                          # D2H read of the step's result, every step, without stalling the host
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn, steps, drain=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
+        if drain is not None:
+            drain()                              # every outstanding result is on the host before the region ends
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -835,7 +848,11 @@ def run_ours(args):
     launches = ops.launch_count() - n0
     clk = clocks.stop() if rank == 0 else None
     step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
+    e2e_ms = timed(step_e2e, args.steps, meter.total)
+    import math
+    assert meter.count == args.steps + 1 and math.isfinite(meter.total())            # every step's loss was read
+    step_e2e_sync()
+    e2e_sync_ms = timed(step_e2e_sync, args.steps)
 
     # ---- roofline of the dominant kernel family (tcgen05 tap-GEMM), one extra profiled step -----------
     # The timed region above overlaps the weight-gradient GEMMs with the input-gradient chain on a second stream
@@ -903,7 +920,13 @@ def run_ours(args):
                    "algorithmic_tflop_per_step": 3 * GFLOP_FWD_PER_IMG * B / 1e3},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps,
+                "how": "pinned host batch -> HostPrefetcher (H2D of step i+1 under step i) -> model.forward -> CTCLoss -> "
+                       "backward -> RunningLoss.add(loss): every step's loss is copied to pinned host memory and summed "
+                       "on the host, the last ones inside the timed region; no per-step device sync",
+                "sync_every_step": {"value": world * B / (e2e_sync_ms / args.steps * 1e-3),
+                                    "ms_per_step": e2e_sync_ms / args.steps,
+                                    "how": "the same with train.py:129's `loss.item()` every step"}},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": ach_tf / peak_tf if peak_tf else None, "traffic": traffic,

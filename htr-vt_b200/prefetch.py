@@ -67,3 +67,52 @@ class HostPrefetcher(object):
         ev.record(cur)
         self._released[other] = ev
         return outs if len(outs) != 1 else outs[0]
+
+
+class RunningLoss(object):
+    """`train_loss += loss.item()` (model_v1/train.py:129) without the device synchronisation of every step.
+
+    `.item()` stalls the host until the step has finished; the next step's ~200 launches are then enqueued into an empty
+    queue, and wherever kernels are shorter than their enqueue the GPU waits for the host (0.5-0.7 ms of a 17 ms step,
+    tools/e2e_probe.py).  `add(loss)` copies the scalar into a pinned ring on the current stream and returns at once;
+    every value is still read back - when its copy has landed (harvested by later add() calls) or, at the latest, by
+    `total()` / `mean()`, which wait for what is outstanding (train.py:133 reads the sum every print_iter steps)."""
+
+    def __init__(self, slots=64):
+        self._buf = torch.zeros(slots, dtype=torch.float32, pin_memory=True)
+        self._pending = []                   # (slot, event), oldest first
+        self._sum, self._count, self._next = 0.0, 0, 0
+
+    def _harvest(self, wait_all=False, make_room=False):
+        while self._pending:
+            slot, ev = self._pending[0]
+            if not (wait_all or (make_room and len(self._pending) >= self._buf.numel()) or ev.query()):
+                break
+            ev.synchronize()
+            self._sum += float(self._buf[slot])
+            self._pending.pop(0)
+
+    def add(self, loss):
+        self._harvest(make_room=True)
+        slot = self._next
+        self._next = (slot + 1) % self._buf.numel()
+        self._buf[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(loss.device))
+        self._pending.append((slot, ev))
+        self._count += 1
+
+    def total(self):
+        self._harvest(wait_all=True)
+        return self._sum
+
+    @property
+    def count(self):
+        return self._count
+
+    def mean(self):
+        return self.total() / self._count if self._count else 0.0
+
+    def reset(self):
+        self._harvest(wait_all=True)
+        self._sum, self._count = 0.0, 0

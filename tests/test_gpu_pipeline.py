@@ -177,3 +177,20 @@ def test_host_prefetcher_double_buffers_batches_in_order():
     dev_t = torch.ones(3, device="cuda")
     pf.put(dev_t)                                 # device tensors pass through
     assert pf.get() is dev_t
+
+
+def test_running_loss_reads_every_value_without_a_sync_per_step():
+    """RunningLoss: the sum equals the sum of `.item()` of every scalar handed in (train.py:129), also past the size of
+    the pinned ring and across reset()."""
+    import htrvt_b200 as h
+    torch.manual_seed(0)
+    vals = torch.randn(150, device="cuda")
+    m = h.RunningLoss(slots=16)
+    for i in range(150):
+        m.add(vals[i] * 2.0)
+    want = float((vals.double() * 2.0).sum())
+    assert m.count == 150 and abs(m.total() - want) < 1e-3 and abs(m.mean() - want / 150) < 1e-5
+    m.reset()
+    assert m.count == 0 and m.total() == 0.0 and m.mean() == 0.0
+    m.add(vals[3])
+    assert abs(m.total() - float(vals[3])) < 1e-6
