@@ -157,7 +157,9 @@ def test_side_stream_weight_gradients_equal_single_stream():
     den = sum(float((g0[n] ** 2).sum()) for n in g0)
     noise = (sum(float(((g0[n] - g0b[n]) ** 2).sum()) for n in g0) / den) ** 0.5
     diff = (sum(float(((g0[n] - g1[n]) ** 2).sum()) for n in g0) / den) ** 0.5
-    assert diff <= 4.0 * noise + 1e-6, (diff, noise)
+    # (a missing dependency between the streams reads stale or half-written tensors: O(1) errors; the floor covers a box
+    # on which two single-stream runs happen to sum in the same order)
+    assert diff <= 4.0 * noise + 2e-3, (diff, noise)
     for n in g0:
         a, b = g0[n].reshape(-1), g1[n].reshape(-1)
         cos = float(a @ b / (a.norm() * b.norm() + 1e-30))
