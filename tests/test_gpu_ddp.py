@@ -108,6 +108,6 @@ def test_dp_gradients_equal_mean_of_shard_gradients():
     assert n > 50
     # averaged gradient == mean of the two shard gradients, up to the run-to-run noise of the backward's free summation
     # order (a sum instead of a mean, a dropped segment or a stale shard would be off by O(1))
-    assert total <= 4.0 * noise + 1e-5, (total, noise)
+    assert total <= 4.0 * noise + 2e-3, (total, noise)      # (floor: a pair of reruns that happens to be bit-identical)
     assert worst < 5e-2 and worst_cos > 0.999, (worst, worst_cos)
     assert equal_across_ranks and out[1][2]      # bit-identical on both ranks after the all-reduce
