@@ -13,15 +13,13 @@ namespace htrvt {
 
 constexpr int kDecThreads = 128;
 
-struct Best {
-  float v;
-  int i;
-};
-__device__ __forceinline__ bool better(const Best& a, const Best& b) {   // is a strictly preferred over b
-  const bool an = a.v != a.v, bn = b.v != b.v;
-  if (an != bn) return an;
-  if (an) return a.i < b.i;
-  return a.v > b.v || (a.v == b.v && a.i < b.i);
+// Order-preserving integer image of a logit for the arg-max: a > b as floats <=> okey(a) > okey(b), -0 and +0 share one
+// key (equal floats tie, and ties keep the lowest index), every NaN maps to the largest key (a NaN beats any number;
+// the first NaN wins).  0 is not the key of any float.
+__device__ __forceinline__ unsigned okey(float v) {
+  const unsigned u = __float_as_uint(__fadd_rn(v, 0.0f));                    // -0 -> +0
+  const unsigned k = u ^ (static_cast<unsigned>(static_cast<int>(u) >> 31) | 0x80000000u);
+  return (u & 0x7fffffffu) > 0x7f800000u ? 0xffffffffu : k;
 }
 
 // Shared tail: collapse + compact raw[0..Tb) (shared memory) into ids_out, return count (warp 0 only).
@@ -46,8 +44,11 @@ __device__ __forceinline__ int collapse_compact(const int* raw, int Tb, int n_ch
 // ---------------------------------------------------------------------------------------------
 // arg-max + collapse, one CTA (256 threads) per line.  The kernel is pure streaming (B*T*C*4 bytes in, B*T*4 out), so
 // the whole line is brought into shared memory with 16-byte cp.async copies that are ALL in flight at once (rows in
-// chunks when T*C*4 exceeds the staging budget), then two threads scan each frame from shared memory (lower / upper
-// half of the class axis; strict comparisons keep the lowest index, a NaN wins), and warp 0 compacts.
+// chunks when T*C*4 exceeds the staging budget), issued as four commit groups that are scanned as they land: eight
+// lanes per frame read the staged row with 16-byte loads (strict comparisons keep the lowest index, a NaN wins), and
+// warp 0 compacts.  512 x 128 x 80: 10.4 us per launch back to back (same-box A/B against the two-threads-per-frame scan
+// with its 8-way bank conflicts: 10.6 us) - the scan is NOT what bounds this kernel; launch + the DRAM ramp of a
+// 21 MB single-wave grid is (tools/decode_probe.py).
 // ---------------------------------------------------------------------------------------------
 constexpr int kGdThreads = 256;
 constexpr int kGdStageBytes = 96 * 1024;
@@ -71,42 +72,69 @@ __global__ void __launch_bounds__(kGdThreads) greedy_decode_kernel(
   int Tb = lengths ? lengths[b] : T;
   Tb = min(max(Tb, 0), T);
   const float* xb = x + static_cast<long long>(b) * sb;
-  const int half = (C + 1) >> 1;
+  const int nv_row = ldc >> 2, l8 = lane & 7, fr = lane >> 3;
   for (int t0 = 0; t0 < Tb; t0 += rows_per_chunk) {
     const int nr = min(rows_per_chunk, Tb - t0);
     if (t0 > 0) __syncthreads();                                            // previous chunk fully scanned
-    if (vec_ok) {
-      const int v_per_row = C >> 2, nv = nr * v_per_row;
-      for (int i = threadIdx.x; i < nv; i += kGdThreads) {
-        const int r = i / v_per_row, v = i - r * v_per_row;
-        cp_async_16(smem_u32(stage + r * ldc + 4 * v), xb + static_cast<long long>(t0 + r) * st + 4 * v);
+    // the chunk's rows go out as four cp.async groups (multiples of 32 rows; all in flight at once): group g is scanned
+    // as soon as it has landed, under the copies of the groups behind it
+    const int rg = (((nr + 3) >> 2) + 31) & ~31;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int r_lo = min(g * rg, nr), r_hi = min(r_lo + rg, nr);
+      if (vec_ok) {
+        const int v_per_row = C >> 2;
+        for (int i = r_lo * v_per_row + threadIdx.x; i < r_hi * v_per_row; i += kGdThreads) {
+          const int r = i / v_per_row, v = i - r * v_per_row;
+          cp_async_16(smem_u32(stage + r * ldc + 4 * v), xb + static_cast<long long>(t0 + r) * st + 4 * v);
+        }
+      } else {
+        for (int i = r_lo * C + threadIdx.x; i < r_hi * C; i += kGdThreads) {
+          const int r = i / C, c = i - r * C;
+          cp_async_4(smem_u32(stage + r * ldc + c), xb + static_cast<long long>(t0 + r) * st + c);
+        }
       }
-    } else {
-      const int n = nr * C;
-      for (int i = threadIdx.x; i < n; i += kGdThreads) {
-        const int r = i / C, c = i - r * C;
-        cp_async_4(smem_u32(stage + r * ldc + c), xb + static_cast<long long>(t0 + r) * st + c);
-      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    // two threads per frame: thread pair (2r, 2r+1) scans classes [0, half) and [half, C)
-    for (int base = 0; base < 2 * nr; base += kGdThreads) {                 // uniform trip count: the shuffle needs whole warps
-      const int i = base + threadIdx.x;
-      const bool act = i < 2 * nr;
-      const int r = act ? i >> 1 : 0, hi = i & 1;
-      const float* row = stage + r * ldc;
-      const int c0 = hi ? half : 0, c1 = act ? (hi ? C : half) : 0;
-      Best best{-INFINITY, 0x7fffffff};
-      for (int c = c0; c < c1; ++c) {
-        const Best cand{row[c], c};
-        if (best.i == 0x7fffffff || better(cand, best)) best = cand;
-      }
-      const Best other{__shfl_xor_sync(0xffffffffu, best.v, 1), __shfl_xor_sync(0xffffffffu, best.i, 1)};
-      if (other.i != 0x7fffffff && (best.i == 0x7fffffff || better(other, best))) best = other;
-      if (act && !hi) {
-        raw[t0 + r] = best.i;
-        if (raw_out) raw_out[static_cast<long long>(b) * T + t0 + r] = best.i;
+    // eight lanes per frame, four frames per warp and pass (32 rows per pass): lane l of a frame reads the 16-byte groups
+    // l, l + 8, ... of the staged row, so every quarter warp of an LDS.128 covers 128 contiguous bytes of one row (no
+    // bank conflicts).  A lane walks its classes in ascending order on order-preserving integer keys (okey), so a strict
+    // comparison keeps the lowest index; three shuffle rounds merge the eight partial results by (key desc, index asc)
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
+      if (g == 1) asm volatile("cp.async.wait_group 2;" ::: "memory");
+      if (g == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      if (g == 3) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      const int r_lo = min(g * rg, nr), r_hi = min(r_lo + rg, nr);
+      for (int base = r_lo; base < r_hi; base += 4 * (kGdThreads / 32)) {   // uniform trip count: the shuffles need whole warps
+        const int r = base + 4 * warp + fr;
+        const bool act = r < r_hi;
+        unsigned bk = 0u;                                                   // below every key of a real element
+        int bi = 0x7fffffff;
+        if (act) {
+          const float4* row4 = reinterpret_cast<const float4*>(stage + r * ldc);
+          for (int v = l8; v < nv_row; v += 8) {
+            const float4 q = row4[v];
+            const int c = 4 * v;                                            // c < C always; the row's last group may be padded
+            const unsigned k0 = okey(q.x), k1 = okey(q.y), k2 = okey(q.z), k3 = okey(q.w);
+            if (k0 > bk) { bk = k0; bi = c; }
+            if (c + 1 < C && k1 > bk) { bk = k1; bi = c + 1; }
+            if (c + 2 < C && k2 > bk) { bk = k2; bi = c + 2; }
+            if (c + 3 < C && k3 > bk) { bk = k3; bi = c + 3; }
+          }
+        }
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+          const unsigned ok = __shfl_xor_sync(0xffffffffu, bk, d);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+          if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+        }
+        if (act && l8 == 0) {
+          raw[t0 + r] = bi;
+          if (raw_out) raw_out[static_cast<long long>(b) * T + t0 + r] = bi;
+        }
       }
     }
   }

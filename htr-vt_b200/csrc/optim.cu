@@ -3,13 +3,13 @@
 // (torch.optim.AdamW as configured at model_v1/train.py:93) and the EMA of the state_dict
 // (model_v1/utils/utils.py:158-173).  The reference issues ~10^3 tiny launches per iteration (a norm, clone and
 // add_ per parameter, a lerp per state_dict entry); here every pass over the 53 M parameters is one launch per
-// <= 48 tensors: pointer tables travel as kernel parameters, a block finds its (tensor, chunk) by binary search over
+// <= 192 tensors: pointer tables travel as kernel parameters, a block finds its (tensor, chunk) by binary search over
 // the chunk prefix sums.  Pure HBM-bound streaming: 4 B/param (norm), 16 B/param (first step), 36 B/param (AdamW).
 #include "common.cuh"
 
 namespace htrvt {
 
-constexpr int kMtMax = 48;
+constexpr int kMtMax = 192;              // 10 KB of kernel parameters (CUDA >= 12.1 takes up to 32 KB)
 constexpr int kMtChunk = 16384;           // elements per block
 
 struct MtTable {

@@ -4,7 +4,7 @@ multi-tensor sm_100a kernels (csrc/optim.cu).
 The reference walks the parameter list in Python: a `norm` launch per tensor + `stack` + `norm` for the gradient
 norm, a `clone` and an `add_` per tensor in `first_step`, a pointer swap per tensor and the base optimizer's own
 per-tensor (or foreach) update in `second_step` - ~10^3 launches per iteration for the 102 parameters of HTR-VT.
-Here each pass (gradient norm, climb, restore + AdamW) is one launch per <= 48 tensors and the norm never visits the
+Here each pass (gradient norm, climb, restore + AdamW) is one launch per <= 192 tensors and the norm never visits the
 host.  Same call sequence as model_v1/train.py:117-126: `first_step(zero_grad=True)`, forward/backward,
 `second_step(zero_grad=True)`; `param_groups` (lr set by utils.update_lr_cos), `state_dict()` and `zero_grad()` behave
 as in the reference.  Only plain AdamW (the optimizer the reference trains with, train.py:93) has a fused path; any other

@@ -38,9 +38,9 @@ def _fusable(e, m):
 @torch.no_grad()
 def ema_update_(ema_module, model, decay, device="", key_prefix=""):
     """ema_module.state_dict()[k] <- decay * itself + (1 - decay) * model.state_dict()[key_prefix + k], in place.
-    fp32 CUDA entries go through htrvt_mt_ema (<= 48 tensors per launch); anything else uses the reference arithmetic."""
+    fp32 CUDA entries go through htrvt_mt_ema (<= 192 tensors per launch); anything else uses the reference arithmetic."""
     src = model.state_dict()
-    pairs_e, pairs_m = [], []
+    pairs_e, pairs_m, rest = [], [], {}
     for name, e in ema_module.state_dict().items():
         m = src[key_prefix + name].detach()
         if device:
@@ -49,7 +49,19 @@ def ema_update_(ema_module, model, decay, device="", key_prefix=""):
             pairs_e.append(e)
             pairs_m.append(m)
         else:
-            e.copy_(e * decay + (1. - decay) * m)
+            rest.setdefault((e.dtype, m.dtype, tuple(e.shape), tuple(m.shape), e.device, m.device), []).append((e, m))
+    for (_, _, es, ms_, ed, md), group in rest.items():
+        if len(group) > 1 and es == ms_ and ed == md and ed.type == "cuda":
+            # the int64 `num_batches_tracked` counters (one per BatchNorm): the reference's expression on the stacked
+            # entries - same type promotion (an integer tensor times a Python float is float32 whether 0-dim or not),
+            # same truncating conversion on the copy back - in 6 launches instead of 4 per counter
+            E = torch.stack([e for e, _ in group])
+            M = torch.stack([m for _, m in group])
+            R = (E * decay + (1. - decay) * M).to(E.dtype)
+            torch._foreach_copy_([e for e, _ in group], list(R.unbind(0)))
+        else:
+            for e, m in group:
+                e.copy_(e * decay + (1. - decay) * m)
     if pairs_e:
         check(lib().htrvt_mt_ema(len(pairs_e), _ptrs(pairs_e), _ptrs(pairs_m), _numels(pairs_e), float(decay),
                                  _stream()), "htrvt_mt_ema")

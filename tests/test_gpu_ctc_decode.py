@@ -264,6 +264,41 @@ def test_argmax_semantics_and_fused_decode():
     assert got == want
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,C", [(37, 7), (128, 80), (70, 13), (33, 4), (5, 1), (300, 90)])
+def test_argmax_signed_zeros_nan_payloads_denormals(T, C):
+    """The integer-key arg-max of the decode kernel against the oracle on what a key transform gets wrong first: -0 / +0
+    ties, NaNs with the sign bit set, denormals, +-inf, rows shorter than a 16-byte group, ragged lengths that end inside
+    a 32-row commit group."""
+    from importlib import import_module
+    ops = import_module("htr-vt_b200.ops")
+    rs = np.random.RandomState(T * 131 + C)
+    B = 9
+    pool = np.array([0.0, -0.0, 1e-42, -1e-42, 1.0, -1.0, np.inf, -np.inf, 3.5, -3.5], dtype=np.float32)
+    a = pool[rs.randint(0, len(pool), size=(B, T, C))]
+    a[0] = np.where(rs.rand(T, C) < 0.5, np.float32(0.0), np.float32(-0.0))          # only signed zeros
+    a[1] = -np.abs(a[1])                                                            # nothing above -0
+    nanbits = np.array([0x7fc00000, 0xffc00000, 0xff800001, 0x7f800001], dtype=np.uint32).view(np.float32)
+    m = rs.rand(T, C) < 0.1
+    a[2][m] = nanbits[rs.randint(0, 4, size=int(m.sum()))]
+    a[3] = -np.inf
+    lengths = rs.randint(0, T + 1, size=B).astype(np.int32)
+    lengths[0] = T
+    want_raw = O.argmax_first(a)
+    ids, lens, raw = ops.greedy_decode_ids(torch.from_numpy(a).cuda(), 1000, lengths=torch.from_numpy(lengths).cuda(),
+                                           want_raw=True)
+    raw, ids, lens = raw.cpu().numpy(), ids.cpu().numpy(), lens.cpu().numpy()
+    for b in range(B):
+        np.testing.assert_array_equal(raw[b, : lengths[b]], want_raw[b, : lengths[b]])
+    want = O.greedy_ids(np.concatenate([want_raw[b, : lengths[b]] for b in range(B)]), lengths.tolist(), 1000)
+    assert [ids[b, : lens[b]].tolist() for b in range(B)] == want
+    # a view with a row stride that is not a multiple of 4 floats takes the 4-byte staging path: same answer
+    wide = torch.zeros(B, T, C + 1).cuda()
+    wide[:, :, :C] = torch.from_numpy(a).cuda()
+    _, _, raw2 = ops.greedy_decode_ids(wide[:, :, :C], 1000, want_raw=True)
+    np.testing.assert_array_equal(raw2.cpu().numpy(), want_raw)
+
+
 class _StubLM(object):
     """Same deterministic scorer as oracle/make_golden.py::StubLM (stands in for KenLM: any .score(text))."""
 
