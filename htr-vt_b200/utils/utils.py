@@ -58,7 +58,11 @@ def ema_update_(ema_module, model, decay, device="", key_prefix=""):
             E = torch.stack([e for e, _ in group])
             M = torch.stack([m for _, m in group])
             R = (E * decay + (1. - decay) * M).to(E.dtype)
-            torch._foreach_copy_([e for e, _ in group], list(R.unbind(0)))
+            if hasattr(torch, "_foreach_copy_"):
+                torch._foreach_copy_([e for e, _ in group], list(R.unbind(0)))
+            else:
+                for (e, _), r in zip(group, R.unbind(0)):
+                    e.copy_(r)
         else:
             for e, m in group:
                 e.copy_(e * decay + (1. - decay) * m)
