@@ -424,6 +424,10 @@ class Engine(object):
     # ------------------------------------------------------------------------------------------
     def backward(self, sd, ctx, dlogits, grads, on_stage=None):
         """dlogits fp32 [B,T,C]; grads: name -> fp32 tensor (accumulated into, +=)."""
+        if ctx.moments is None:
+            # an eval-mode forward normalised with the running statistics: the BatchNorm backward kernels differentiate
+            # through BATCH statistics, so refuse before any gradient is written (INTEGRATION.md, limits)
+            raise ops.HtrvtError("backward needs a train-mode forward (batch statistics)")
         B, T, D, C = ctx.B, ctx.T, self.D, self.C
         M = B * T
         wp = ctx.wp
@@ -608,8 +612,6 @@ class Engine(object):
                 on_stage("stem:" + STEM_LAYERS[-1][0])
         unpack(lambda k: k not in unpacked)
         # ---- stem head: pool -> relu -> bn1 -> conv1 ---------------------------------------------
-        if ctx.moments is None:
-            raise ops.HtrvtError("backward needs a train-mode forward (batch statistics)")
         ops.stem_head_bwd(g, ctx.code1, ctx.x0, sd["patch_embed.conv1.weight"], ctx.moments,
                           sd["patch_embed.bn1.weight"], ctx.st1, grads["patch_embed.bn1.weight"],
                           grads["patch_embed.bn1.bias"], grads["patch_embed.conv1.weight"])

@@ -66,6 +66,18 @@ def test_eval_logits_match_oracle(cfg):
     assert ((am_got == am_want) | (margin < 4e-2 * np.abs(want).max())).all()
 
 
+def test_backward_through_eval_forward_refuses_before_writing_gradients():
+    """The BatchNorm backward kernels differentiate through batch statistics: a backward after model.eval() must fail
+    loudly and must not leave partial gradients behind (limits)."""
+    ops = import_module("htr-vt_b200.ops")
+    m, _ = _build(24, 128, 256, 2, 2, 5)
+    m.eval()
+    out = m(_images(6, 3, 128).cuda()).float()
+    with pytest.raises(ops.HtrvtError, match="train-mode forward"):
+        out.sum().backward()
+    assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in m.parameters())
+
+
 @pytest.mark.parametrize("cfg", [dict(nb_cls=24, W=128, D=256, depth=2, heads=2, B=3, seed=5),
                                  dict(nb_cls=80, W=512, D=768, depth=4, heads=6, B=2, seed=123)])
 def test_train_step_matches_oracle(cfg):
