@@ -54,23 +54,31 @@ class SAM(torch.optim.Optimizer):
 
     # -- helpers ------------------------------------------------------------------------------------
     def _live(self, group):
-        ps = [p for p in group["params"] if p.grad is not None]
-        for p in ps:
-            if not (_dense_f32(p.data) and _dense_f32(p.grad)):
+        """(parameters with a gradient, their gradients) - each `.grad` read once per pass: this runs on the host for
+        every one of the ~100 tensors, four times per iteration."""
+        ps, gs = [], []
+        for p in group["params"]:
+            g = p.grad
+            if g is None:
+                continue
+            if not (_dense_f32(p) and _dense_f32(g)):
                 raise RuntimeError("htr-vt_b200 SAM needs contiguous fp32 CUDA parameters and gradients")
-        return ps
+            ps.append(p)
+            gs.append(g)
+        return ps, gs
 
-    def _grad_norm_device(self):
+    def _grad_norm_device(self, live=None):
         """sum |g|^2 (adaptive: |abs(w) g|^2) over every parameter, left on the device as a float64 scalar."""
+        if live is None:
+            live = [(group,) + self._live(group) for group in self.param_groups]
         dev = self.param_groups[0]["params"][0].device
         if self._norm2 is None or self._norm2.device != dev:
             self._norm2 = torch.zeros((), dtype=torch.float64, device=dev)
         self._norm2.zero_()
-        for group in self.param_groups:
-            ps = self._live(group)
+        for group, ps, gs in live:
             if not ps:
                 continue
-            check(lib().htrvt_mt_sqnorm(len(ps), _ptrs([p.grad for p in ps]), _ptrs([p.data for p in ps]), _numels(ps),
+            check(lib().htrvt_mt_sqnorm(len(ps), _ptrs(gs), _ptrs(ps), _numels(ps),
                                         int(bool(group["adaptive"])), ctypes.c_void_p(self._norm2.data_ptr()),
                                         _stream()), "htrvt_mt_sqnorm")
         return self._norm2
@@ -81,9 +89,9 @@ class SAM(torch.optim.Optimizer):
     # -- the reference's two steps --------------------------------------------------------------------
     @torch.no_grad()
     def first_step(self, zero_grad=False):
-        norm2 = self._grad_norm_device()
-        for group in self.param_groups:
-            ps = self._live(group)
+        live = [(group,) + self._live(group) for group in self.param_groups]
+        norm2 = self._grad_norm_device(live)
+        for group, ps, gs in live:
             if not ps:
                 continue
             olds = []
@@ -92,8 +100,7 @@ class SAM(torch.optim.Optimizer):
                 if "old_p" not in st or st["old_p"].shape != p.shape:
                     st["old_p"] = torch.empty_like(p.data)
                 olds.append(st["old_p"])
-            check(lib().htrvt_mt_sam_first(len(ps), _ptrs([p.data for p in ps]), _ptrs([p.grad for p in ps]),
-                                           _ptrs(olds), _numels(ps), ctypes.c_void_p(norm2.data_ptr()),
+            check(lib().htrvt_mt_sam_first(len(ps), _ptrs(ps), _ptrs(gs), _ptrs(olds), _numels(ps), ctypes.c_void_p(norm2.data_ptr()),
                                            float(group["rho"]), int(bool(group["adaptive"])), _stream()),
                   "htrvt_mt_sam_first")
         _ops.weights_changed()
@@ -107,11 +114,11 @@ class SAM(torch.optim.Optimizer):
 
     @torch.no_grad()
     def second_step(self, zero_grad=False):
-        live = [(group, self._live(group)) for group in self.param_groups]
-        if not all(self._group_fusable(g) for g, ps in live if ps):
+        live = [(group,) + self._live(group) for group in self.param_groups]
+        if not all(self._group_fusable(g) for g, ps, _ in live if ps):
             # any group the fused kernel cannot express (other base optimizer, amsgrad / maximize, ...): the reference
             # sequence for EVERY group - back to "w" from "w + e(w)", then the base optimizer's own update (sam.py:31-37)
-            for _, ps in live:
+            for _, ps, _ in live:
                 for p in ps:
                     p.data.copy_(self.state[p]["old_p"])
             self.base_optimizer.step()
@@ -120,25 +127,26 @@ class SAM(torch.optim.Optimizer):
                 self.zero_grad()
             return
         bst = self.base_optimizer.state
-        for group, ps in live:
+        for group, ps, gs in live:
             if not ps:
                 continue
             olds = [self.state[p]["old_p"] for p in ps]
-            ms, vs = [], []
+            ms, vs, counters = [], [], []
             for p in ps:
                 st = bst[p]
                 if len(st) == 0:
                     st["step"] = torch.tensor(0.0, dtype=torch.float32)
                     st["exp_avg"] = torch.zeros_like(p.data)
                     st["exp_avg_sq"] = torch.zeros_like(p.data)
-                st["step"] += 1
+                counters.append(st["step"])
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
-            steps = {int(bst[p]["step"]) for p in ps}
+            torch._foreach_add_(counters, 1)          # torch.optim.AdamW's per-parameter step tensors, one call
+            steps = {int(c) for c in counters}
             if len(steps) != 1:
                 raise RuntimeError("htr-vt_b200 SAM: parameters of one group must share their step count")
             b1, b2 = group["betas"]
-            check(lib().htrvt_mt_adamw(len(ps), _ptrs([p.data for p in ps]), _ptrs([p.grad for p in ps]), _ptrs(ms),
+            check(lib().htrvt_mt_adamw(len(ps), _ptrs(ps), _ptrs(gs), _ptrs(ms),
                                        _ptrs(vs), _ptrs(olds), _numels(ps), float(group["lr"]), float(b1), float(b2),
                                        float(group["eps"]), float(group["weight_decay"]), steps.pop(), _stream()),
                   "htrvt_mt_adamw")
