@@ -295,7 +295,7 @@ int htrvt_conv1_wgrad(const void* dy_bf16, const float* x, float* grad, int accu
 /* ---- multi-tensor optimizer passes around the hot path -------------------------------
  * Replace the per-parameter loops of SAM (model_v1/utils/sam.py:15-59), torch.optim.AdamW as configured at
  * model_v1/train.py:93 and ModelEma.update (model_v1/utils/utils.py:158-173).  Arrays of n DEVICE pointers to fp32
- * tensors live on the HOST (they travel as kernel parameters, <= 48 tensors per launch); numel[i] elements each.
+ * tensors live on the HOST (they travel as kernel parameters, <= 192 tensors per launch); numel[i] elements each.
  * norm2: device double, zeroed by the caller, receives sum |g|^2 (adaptive: |abs(p) g|^2). */
 int htrvt_mt_sqnorm(int n, void* const* g, void* const* p, const long long* numel, int adaptive, double* norm2,
                     void* stream);
