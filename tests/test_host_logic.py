@@ -50,3 +50,35 @@ def test_shard_batch_covers_every_item_once():
             lo, hi = ddp.shard_batch(n, r, world)
             seen += list(range(lo, hi))
         assert seen == list(range(n))
+
+
+def test_ema_update_on_cpu_state_dicts_follows_the_reference_expression():
+    """ema_update_ on tensors the fused kernel does not take (CPU fp32, int64 counters, fp64): every entry goes through
+    model_v1/utils/utils.py:173's expression `ema_v.copy_(ema_v * decay + (1 - decay) * model_v)`, counters included
+    (float math, truncating copy back)."""
+    import copy
+    U = import_module("htr-vt_b200.utils.utils")
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Conv2d(1, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.Conv2d(4, 4, 3),
+                              torch.nn.BatchNorm2d(4))
+    net.register_buffer("wide", torch.randn(5, dtype=torch.float64))
+    shadow = copy.deepcopy(net)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(torch.randn_like(p))
+        net[1].num_batches_tracked.add_(7)
+        net[3].num_batches_tracked.add_(123456789)
+        net[1].running_var.mul_(3.0)
+        net.wide.add_(1.0)
+    want = {k: v.clone() for k, v in shadow.state_dict().items()}
+    for d in (0.1, 0.9999):
+        src = net.state_dict()
+        for k in want:
+            want[k] = (want[k] * d + (1. - d) * src[k]).to(want[k].dtype)
+        U.ema_update_(shadow, net, d)
+    got = shadow.state_dict()
+    assert list(got) == list(want)
+    for k in want:
+        assert got[k].dtype == want[k].dtype
+        assert torch.equal(got[k], want[k]), k
+    assert U.effective_decay(0.9999, 0) == 0.1 and U.effective_decay(0.9999, -1) == 0.9999
