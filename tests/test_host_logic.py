@@ -82,3 +82,21 @@ def test_ema_update_on_cpu_state_dicts_follows_the_reference_expression():
         assert got[k].dtype == want[k].dtype
         assert torch.equal(got[k], want[k]), k
     assert U.effective_decay(0.9999, 0) == 0.1 and U.effective_decay(0.9999, -1) == 0.9999
+
+
+def test_sam_refuses_cpu_parameters_loudly():
+    """No CPU fallback on the product path: the multi-tensor SAM raises on parameters the kernels cannot take instead of
+    quietly running another implementation; parameters without a gradient are skipped like the reference does
+    (model_v1/utils/sam.py:20)."""
+    import pytest
+    S = import_module("htr-vt_b200.utils.sam")
+    w = torch.nn.Parameter(torch.randn(4, 3))
+    frozen = torch.nn.Parameter(torch.randn(2))
+    opt = S.SAM([w, frozen], torch.optim.AdamW, lr=1e-3)
+    ps, gs = opt._live(opt.param_groups[0])
+    assert ps == [] and gs == []                       # nothing has a gradient yet
+    w.grad = torch.randn_like(w)
+    with pytest.raises(RuntimeError, match="contiguous fp32 CUDA"):
+        opt.first_step()
+    with pytest.raises(RuntimeError, match="contiguous fp32 CUDA"):
+        opt.second_step()
